@@ -1,0 +1,109 @@
+"""ctypes binding of libgsdfb200.so (include/gsdf_b200.h + include/gsdf_host.h).
+
+The library is the product: there is no Python or CPU fallback. If the shared object is missing the import fails
+loudly and tells the caller how to build it.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgsdfb200.so")
+
+
+class GsdfError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("gsdf_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+# gsdf_status (include/gsdf_b200.h)
+OK, EINVAL, ELEN, EEMPTY, ECUDA, ENOMEM, EPROGRAM, ESHORT, ERES = 0, -1, -2, -3, -4, -5, -6, -7, -8
+MESH_PRUNE, MESH_KEEP_CASES, MESH_KEEP_GRID = 1, 2, 4
+
+
+class Lattice(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("res", C.c_float), ("n", C.c_int32 * 3)]
+
+
+class TreeNode(C.Structure):  # gsdf_tree_node, 96 bytes
+    _fields_ = [("kind", C.c_int32), ("nchild", C.c_int32), ("child_off", C.c_int32), ("aux_off", C.c_int32),
+                ("aux_cnt", C.c_int32), ("iparam", C.c_int32 * 3), ("fparam", C.c_float * 16)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "gsdf_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C gsdf_b200/csrc` (needs nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, f32p, i32p, u8p, u64p = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)
+    sig = {
+        # include/gsdf_b200.h
+        "gsdf_version": (C.c_char_p, []),
+        "gsdf_last_error": (C.c_char_p, []),
+        "gsdf_device_count": (C.c_int, []),
+        "gsdf_set_device": (C.c_int, [C.c_int]),
+        "gsdf_program_create": (C.c_int, [vp, C.c_size_t, f32p, C.c_size_t, C.POINTER(vp)]),
+        "gsdf_program_destroy": (None, [vp]),
+        "gsdf_program_evaluations": (C.c_uint64, [vp]),
+        "gsdf_eval3": (C.c_int, [vp, vp, vp, C.c_size_t]),
+        "gsdf_eval2": (C.c_int, [vp, vp, vp, C.c_size_t]),
+        "gsdf_eval3_device": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
+        "gsdf_eval2_device": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
+        "gsdf_lattice_from_bounds": (C.c_int, [f32p, f32p, C.c_float, C.POINTER(Lattice)]),
+        "gsdf_grid_eval": (C.c_int, [vp, C.POINTER(Lattice), C.c_int, C.c_int, vp]),
+        "gsdf_grid_eval_device": (C.c_int, [vp, C.POINTER(Lattice), C.c_int, C.c_int, vp, vp]),
+        "gsdf_mesh_begin": (C.c_int, [vp, C.POINTER(Lattice), C.c_int, C.c_int, C.c_uint, C.POINTER(vp)]),
+        "gsdf_mesh_rerun": (C.c_int, [vp]),
+        "gsdf_mesh_read": (C.c_int64, [vp, vp, C.c_size_t]),
+        "gsdf_mesh_device_triangles": (C.c_int, [vp, C.POINTER(vp), u64p]),
+        "gsdf_mesh_stats": (C.c_int, [vp, u64p, u64p, u64p]),
+        "gsdf_mesh_cases": (C.c_int, [vp, vp, C.c_size_t]),
+        "gsdf_mesh_grid": (C.c_int, [vp, vp, C.c_size_t]),
+        "gsdf_mesh_timings": (C.c_int, [vp, f32p]),
+        "gsdf_mesh_destroy": (None, [vp]),
+        "gsdf_stl_pack": (C.c_int64, [vp, C.c_size_t, vp, C.c_size_t]),
+        "gsdf_mesh_stl": (C.c_int64, [vp, vp, C.c_size_t]),
+        "gsdf_image_eval2": (C.c_int, [vp, f32p, f32p, C.c_int, C.c_int, vp]),
+        # include/gsdf_host.h
+        "gsdfh_builder_new": (vp, []),
+        "gsdfh_builder_free": (None, [vp]),
+        "gsdfh_builder_err": (C.c_char_p, [vp]),
+        "gsdfh_builder_clear_errors": (None, [vp]),
+        "gsdfh_node": (C.c_int32, [vp, C.c_int32, f32p, C.c_int, i32p, C.c_int, i32p, C.c_int, f32p, C.c_int]),
+        "gsdfh_is2d": (C.c_int, [vp, C.c_int32]),
+        "gsdfh_bounds3": (C.c_int, [vp, C.c_int32, f32p]),
+        "gsdfh_bounds2": (C.c_int, [vp, C.c_int32, f32p]),
+        "gsdfh_thread_profile": (C.c_int32, [vp, C.c_int, C.c_float, C.c_float, C.c_int]),
+        "gsdfh_screw": (C.c_int32, [vp, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int]),
+        "gsdfh_nut": (C.c_int32, [vp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_float]),
+        "gsdfh_bolt": (C.c_int32, [vp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]),
+        "gsdfh_hexhead": (C.c_int32, [vp, C.c_float, C.c_float, C.c_int, C.c_int]),
+        "gsdfh_scene": (C.c_int32, [vp, C.c_char_p, C.c_float]),
+        "gsdfh_tree": (C.c_int, [vp, C.POINTER(C.POINTER(TreeNode)), i32p, C.POINTER(i32p), i32p, C.POINTER(f32p), i32p]),
+        "gsdfh_flatten": (vp, [vp, C.c_int32]),
+        "gsdfh_flat_blob": (vp, [vp, C.POINTER(C.c_size_t)]),
+        "gsdfh_flat_aux": (f32p, [vp, C.POINTER(C.c_size_t)]),
+        "gsdfh_flat_info": (None, [vp, i32p]),
+        "gsdfh_flat_free": (None, [vp]),
+        "gsdfh_compile": (C.c_int, [vp, C.c_int32, C.POINTER(vp)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library drift; tests check every symbol
+        fn.restype = res
+        fn.argtypes = args
+    lib._gsdf_signatures = sig
+    return lib
+
+
+lib = _load()
+
+
+def last_error():
+    return lib.gsdf_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    if rc < 0:
+        raise GsdfError(rc, last_error())
+    return rc

@@ -1,0 +1,622 @@
+// capi.cu -- implementation of the C ABI declared in include/gsdf_b200.h (device layer).
+// Handles own device buffers (grow-never-shrink) and one stream each; no CPU fallback exists: every compute entry
+// point fails with GSDF_ECUDA when no CUDA device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gsdf_b200.h"
+#include "../../include/gsdf_program.h"
+#include "kernels.cuh"
+
+using namespace gsdfk;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail(GSDF_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_));   \
+    } while (0)
+
+int g_device = 0;
+int g_sms = 0;
+
+int ensure_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) return fail(GSDF_ECUDA, "no CUDA device available (%s); libgsdfb200 has no CPU fallback", cudaGetErrorString(e));
+    CU(cudaSetDevice(g_device));
+    if (!g_sms) {
+        cudaDeviceProp p;
+        CU(cudaGetDeviceProperties(&p, g_device));
+        g_sms = p.multiProcessorCount;
+    }
+    return 0;
+}
+
+template <class T>
+int grow(T *&ptr, size_t &cap, size_t need) {
+    if (need <= cap) return 0;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    size_t want = need + need / 8;
+    cudaError_t e = cudaMalloc((void **)&ptr, want * sizeof(T));
+    if (e != cudaSuccess) return fail(GSDF_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+    cap = want;
+    return 0;
+}
+
+}  // namespace
+
+struct gsdf_program {
+    int device = 0;
+    uint8_t *d_blob = nullptr;
+    ProgView pv{};
+    int dim = 3;
+    uint32_t ninstr = 0;
+    uint64_t evals = 0;
+    cudaStream_t stream = nullptr;
+    float *d_pos = nullptr, *d_dist = nullptr;
+    size_t pos_cap = 0, dist_cap = 0;
+};
+
+namespace {
+
+// persistent launch: enough CTAs to fill the machine, never more than the work needs
+template <int P, class Gen>
+int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork, cudaStream_t st) {
+    if (nwork == 0) return 0;
+    auto kern = k_eval<P, Gen>;
+    const uint32_t smem = smem_total_bytes<P>(p->pv, kThreads);
+    static thread_local const void *configured = nullptr;
+    static thread_local uint32_t configured_smem = 0;
+    if (configured != (const void *)kern || configured_smem < smem) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<uint32_t>(smem, 48 * 1024)));
+        configured = (const void *)kern;
+        configured_smem = std::max<uint32_t>(smem, 48 * 1024);
+    }
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+    if (occ < 1) return fail(GSDF_EPROGRAM, "node program needs %u bytes of shared memory per CTA; does not fit", smem);
+    uint64_t blocks = (nwork + kThreads - 1) / kThreads;
+    blocks = std::min<uint64_t>(blocks, (uint64_t)g_sms * occ);
+    kern<<<(unsigned)blocks, kThreads, smem, st>>>(p->pv, gen);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_t aux_floats) {
+    uint32_t pc = 0, n = 0;
+    bool ended = false;
+    while (pc < h.nchunks) {
+        const uint32_t w0 = chunks[4 * pc], op = w0 & 0xff, len = (w0 >> 8) & 0xff;
+        if (op >= GSDF_OP__COUNT) return fail(GSDF_EPROGRAM, "instruction %u: unknown opcode %u", n, op);
+        if (op == GSDF_OP_ELLIPSE2D || op == GSDF_OP_BEZIERQ2D) return fail(GSDF_EPROGRAM, "instruction %u: opcode %u not implemented", n, op);
+        if (len < 1 || pc + len > h.nchunks) return fail(GSDF_EPROGRAM, "instruction %u: bad length %u", n, len);
+        static const uint8_t need2[] = {GSDF_OP_BOX, GSDF_OP_BOXFRAME, GSDF_OP_CYLINDER, GSDF_OP_HEX, GSDF_OP_DIAMOND2D, GSDF_OP_TRANSLATE,
+                                        GSDF_OP_ROTATE2D, GSDF_OP_ELONGATE, GSDF_OP_ARRAY2D_VAR, GSDF_OP_CIRC_ENTER, GSDF_OP_SCREW_ENTER};
+        static const uint8_t need3[] = {GSDF_OP_LINE2D, GSDF_OP_ARC2D, GSDF_OP_ARRAY_VAR};
+        uint32_t want = 1;
+        for (uint8_t o : need2) if (o == op) want = 2;
+        for (uint8_t o : need3) if (o == op) want = 3;
+        if (op == GSDF_OP_TRANSFORM) want = 4;
+        if (len != want) return fail(GSDF_EPROGRAM, "instruction %u (opcode %u): length %u, expected %u", n, op, len, want);
+        if (op == GSDF_OP_POLY2D) {
+            const uint64_t off = chunks[4 * pc + 1], nv = chunks[4 * pc + 2];
+            if ((off & 3) || nv < 3 || off + nv * GSDF_POLY_EDGE_FLOATS > aux_floats) return fail(GSDF_EPROGRAM, "instruction %u: polygon aux range out of bounds", n);
+        }
+        if (op == GSDF_OP_LINES2D) {
+            const uint64_t off = chunks[4 * pc + 1], ns = chunks[4 * pc + 2];
+            if ((off & 3) || off + ns * 4 > aux_floats) return fail(GSDF_EPROGRAM, "instruction %u: lines aux range out of bounds", n);
+        }
+        pc += len;
+        n++;
+        if (op == GSDF_OP_END) { ended = true; break; }
+    }
+    if (!ended || pc != h.nchunks) return fail(GSDF_EPROGRAM, "program does not end with END at its last chunk");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *gsdf_version(void) { return "gsdf-b200 0.1 (sm_100a)"; }
+const char *gsdf_last_error(void) { return g_err.c_str(); }
+
+int gsdf_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(GSDF_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+int gsdf_set_device(int device) {
+    int n = gsdf_device_count();
+    if (n < 0) return n;
+    if (device < 0 || device >= n) return fail(GSDF_EINVAL, "device %d out of range (have %d)", device, n);
+    g_device = device;
+    g_sms = 0;
+    return ensure_device();
+}
+
+int gsdf_program_create(const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats, gsdf_program **out) {
+    if (!blob || !out || blob_bytes < sizeof(gsdf_program_header)) return fail(GSDF_EINVAL, "gsdf_program_create: bad arguments");
+    gsdf_program_header h;
+    std::memcpy(&h, blob, sizeof h);
+    if (h.magic != GSDF_PROGRAM_MAGIC || h.version != GSDF_PROGRAM_VERSION) return fail(GSDF_EPROGRAM, "bad program magic/version");
+    if (h.nchunks == 0 || blob_bytes != sizeof h + (size_t)h.nchunks * 16) return fail(GSDF_EPROGRAM, "program size mismatch");
+    if (h.dim != 2 && h.dim != 3) return fail(GSDF_EPROGRAM, "program dim must be 2 or 3");
+    if (aux_floats && !aux) return fail(GSDF_EINVAL, "aux is NULL");
+    if (aux_floats & 3) return fail(GSDF_EPROGRAM, "aux length must be a multiple of 4 floats");
+    if (h.dstack < 1 || h.dstack > 64 || h.pstack > 32) return fail(GSDF_EPROGRAM, "stack depth out of range (d=%u p=%u)", h.dstack, h.pstack);
+    const uint32_t *chunks = reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(blob) + sizeof h);
+    int rc = validate_program(h, chunks, aux_floats);
+    if (rc) return rc;
+    rc = ensure_device();
+    if (rc) return rc;
+
+    gsdf_program *p = new gsdf_program();
+    p->device = g_device;
+    p->dim = (int)h.dim;
+    p->ninstr = h.ninstr;
+    const size_t prog_bytes = (size_t)h.nchunks * 16, aux_bytes = aux_floats * 4;
+    cudaError_t e = cudaMalloc((void **)&p->d_blob, prog_bytes + aux_bytes + 16);
+    if (e != cudaSuccess) { delete p; return fail(GSDF_ENOMEM, "cudaMalloc program: %s", cudaGetErrorString(e)); }
+    e = cudaMemcpy(p->d_blob, chunks, prog_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && aux_bytes) e = cudaMemcpy(p->d_blob + prog_bytes, aux, aux_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { cudaFree(p->d_blob); delete p; return fail(GSDF_ECUDA, "program upload: %s", cudaGetErrorString(e)); }
+    p->pv.g_prog = reinterpret_cast<const uint4 *>(p->d_blob);
+    p->pv.prog_bytes = (uint32_t)prog_bytes;
+    p->pv.aux_bytes = (uint32_t)aux_bytes;
+    p->pv.dslots = h.dstack;
+    p->pv.pslots = h.pstack;
+    // stage aux with the program when program + aux + stacks stay under ~100 KB (>= 2 CTAs/SM)
+    const uint32_t stacks = kThreads * 4u * 4u * (h.dstack + 3u * h.pstack);
+    p->pv.stage_aux = (prog_bytes + aux_bytes + stacks + 16 <= 100 * 1024) ? 1u : 0u;
+    if (prog_bytes + stacks + 16 > 200 * 1024) { gsdf_program_destroy(p); return fail(GSDF_EPROGRAM, "program too large for shared memory"); }
+    *out = p;
+    return 0;
+}
+
+void gsdf_program_destroy(gsdf_program *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    cudaFree(p->d_blob);
+    cudaFree(p->d_pos);
+    cudaFree(p->d_dist);
+    delete p;
+}
+
+uint64_t gsdf_program_evaluations(const gsdf_program *p) { return p ? p->evals : 0; }
+
+int gsdf_eval3_device(gsdf_program *p, const float *d_pos, float *d_dist, size_t n, void *stream) {
+    if (!p || !d_pos || !d_dist) return fail(GSDF_EINVAL, "gsdf_eval3_device: NULL argument");
+    if (p->dim != 3) return fail(GSDF_EINVAL, "program is not 3D");
+    if (n == 0) return fail(GSDF_EEMPTY, "empty buffers");
+    CU(cudaSetDevice(p->device));
+    GenPoints3 g{d_pos, d_dist, (uint64_t)n, (((uintptr_t)d_pos | (uintptr_t)d_dist) & 15) == 0 ? 1 : 0};
+    return launch_eval<4>(p, g, (n + 3) / 4, stream ? (cudaStream_t)stream : p->stream);
+}
+
+int gsdf_eval2_device(gsdf_program *p, const float *d_pos, float *d_dist, size_t n, void *stream) {
+    if (!p || !d_pos || !d_dist) return fail(GSDF_EINVAL, "gsdf_eval2_device: NULL argument");
+    if (p->dim != 2) return fail(GSDF_EINVAL, "program is not 2D");
+    if (n == 0) return fail(GSDF_EEMPTY, "empty buffers");
+    CU(cudaSetDevice(p->device));
+    GenPoints2 g{d_pos, d_dist, (uint64_t)n, (((uintptr_t)d_pos | (uintptr_t)d_dist) & 15) == 0 ? 1 : 0};
+    return launch_eval<4>(p, g, (n + 3) / 4, stream ? (cudaStream_t)stream : p->stream);
+}
+
+static int eval_host(gsdf_program *p, const float *pos, float *dist, size_t n, int dim) {
+    if (!p || !pos || !dist) return fail(GSDF_EINVAL, "gsdf_eval: NULL argument");
+    if (p->dim != dim) return fail(GSDF_EINVAL, "program is %dD, called as %dD", p->dim, dim);
+    if (n == 0) return fail(GSDF_EEMPTY, "empty buffers");
+    CU(cudaSetDevice(p->device));
+    int rc = grow(p->d_pos, p->pos_cap, n * 3);
+    if (rc) return rc;
+    rc = grow(p->d_dist, p->dist_cap, n);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(p->d_pos, pos, n * dim * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    rc = dim == 3 ? gsdf_eval3_device(p, p->d_pos, p->d_dist, n, p->stream) : gsdf_eval2_device(p, p->d_pos, p->d_dist, n, p->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dist, p->d_dist, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    p->evals += n;
+    return 0;
+}
+int gsdf_eval3(gsdf_program *p, const float *pos, float *dist, size_t n) { return eval_host(p, pos, dist, n, 3); }
+int gsdf_eval2(gsdf_program *p, const float *pos, float *dist, size_t n) { return eval_host(p, pos, dist, n, 2); }
+
+// ------------------------------------------------------------------------------------------------ lattice
+int gsdf_lattice_from_bounds(const float bbmin[3], const float bbmax[3], float res, gsdf_lattice *out) {
+    if (!bbmin || !bbmax || !out) return fail(GSDF_EINVAL, "gsdf_lattice_from_bounds: NULL argument");
+    if (!(res > 0)) return fail(GSDF_EINVAL, "invalid renderer cube resolution");  // flatrenderer.go:38
+    for (int a = 0; a < 3; a++) {
+        // bb.ScaleCentered(1.01): centre + size*1.01/2 (flatrenderer.go:47-48)
+        const float size = bbmax[a] - bbmin[a];
+        const float ns = 1.01f * size;
+        const float c = bbmin[a] + size * 0.5f;
+        const float half = ns * 0.5f;
+        const float mn = c - half, mx = c + half;
+        const int n = (int)ceilf((mx - mn) / res);  // flatrenderer.go:50-52
+        if (n <= 0) return fail(GSDF_ERES, "resolution not fine enough for marching cubes");
+        out->n[a] = n;
+        out->origin[a] = mn;
+    }
+    out->res = res;
+    return 0;
+}
+
+static Lat make_lat(const gsdf_lattice *lat, int k0, int k1, int pitch, bool vec) {
+    Lat L;
+    L.ox = lat->origin[0]; L.oy = lat->origin[1]; L.oz = lat->origin[2]; L.res = lat->res;
+    L.nx = lat->n[0]; L.ny = lat->n[1]; L.nz = lat->n[2];
+    L.k0 = k0; L.nk = k1 - k0;
+    L.nqx = (lat->n[0] + 1 + 3) / 4;
+    L.pitch = pitch;
+    L.vec = vec ? 1 : 0;
+    return L;
+}
+
+int gsdf_grid_eval_device(gsdf_program *p, const gsdf_lattice *lat, int k0, int k1, float *d_dist, void *stream) {
+    if (!p || !lat || !d_dist) return fail(GSDF_EINVAL, "gsdf_grid_eval_device: NULL argument");
+    if (p->dim != 3) return fail(GSDF_EINVAL, "program is not 3D");
+    if (k0 < 0 || k1 > lat->n[2] + 1 || k0 >= k1) return fail(GSDF_EINVAL, "bad corner-plane range [%d,%d)", k0, k1);
+    CU(cudaSetDevice(p->device));
+    const int pitch = lat->n[0] + 1;
+    const bool vec = (pitch % 4 == 0) && (((uintptr_t)d_dist & 15) == 0);
+    GenGrid g{make_lat(lat, k0, k1, pitch, vec), d_dist, nullptr, nullptr};
+    const uint64_t nwork = (uint64_t)g.L.nqx * (lat->n[1] + 1) * (k1 - k0);
+    return launch_eval<4>(p, g, nwork, stream ? (cudaStream_t)stream : p->stream);
+}
+
+int gsdf_grid_eval(gsdf_program *p, const gsdf_lattice *lat, int k0, int k1, float *dist) {
+    if (!p || !lat) return fail(GSDF_EINVAL, "gsdf_grid_eval: NULL argument");
+    if (k0 < 0 || k1 > lat->n[2] + 1 || k0 >= k1) return fail(GSDF_EINVAL, "bad corner-plane range [%d,%d)", k0, k1);
+    CU(cudaSetDevice(p->device));
+    const size_t n = (size_t)(lat->n[0] + 1) * (lat->n[1] + 1) * (k1 - k0);
+    int rc = grow(p->d_dist, p->dist_cap, n);
+    if (rc) return rc;
+    rc = gsdf_grid_eval_device(p, lat, k0, k1, p->d_dist, p->stream);
+    if (rc) return rc;
+    if (dist) CU(cudaMemcpyAsync(dist, p->d_dist, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    p->evals += n;
+    return 0;
+}
+
+int gsdf_image_eval2(gsdf_program *p, const float bbmin[2], const float bbmax[2], int w, int h, float *dist) {
+    if (!p || !bbmin || !bbmax || !dist) return fail(GSDF_EINVAL, "gsdf_image_eval2: NULL argument");
+    if (p->dim != 2) return fail(GSDF_EINVAL, "program is not 2D");
+    if (w <= 0 || h <= 0) return fail(GSDF_EINVAL, "bad image size");
+    CU(cudaSetDevice(p->device));
+    const size_t n = (size_t)w * h;
+    int rc = grow(p->d_dist, p->dist_cap, n);
+    if (rc) return rc;
+    GenImage g;
+    g.dx = (bbmax[0] - bbmin[0]) / (float)w;  // image.go:85-87
+    g.dy = (bbmax[1] - bbmin[1]) / (float)h;
+    g.xmin = bbmin[0] + g.dx / 2;
+    g.ymax = bbmax[1];
+    g.w = w; g.h = h; g.dist = p->d_dist;
+    rc = launch_eval<4>(p, g, (uint64_t)((w + 3) / 4) * h, p->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dist, p->d_dist, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    p->evals += n;
+    return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ mesher
+struct gsdf_mesher {
+    gsdf_program *prog = nullptr;
+    gsdf_lattice lat{};
+    unsigned flags = 0;
+    MeshDims D{};
+    float *d_grid = nullptr; size_t grid_cap = 0;
+    uint8_t *d_mask = nullptr; size_t mask_cap = 0;
+    uint32_t *d_list = nullptr; size_t list_cap = 0;
+    uint32_t *d_seg = nullptr; size_t seg_cap = 0;
+    uint32_t *d_blocksum = nullptr; size_t blocksum_cap = 0;
+    float *d_tris = nullptr; size_t tri_cap = 0;  // in floats
+    uint8_t *d_cases = nullptr; size_t cases_cap = 0;
+    uint8_t *d_stl = nullptr; size_t stl_cap = 0;
+    // device counters: [0] quad list length, [1] overflow flag, [2..3] total triangles (u64), [4] kept blocks
+    uint32_t *d_ctr = nullptr;
+    uint32_t *h_ctr = nullptr;  // pinned mirror
+    uint64_t ntri = 0, evals = 0, pruned = 0, read_pos = 0;
+    cudaEvent_t ev[5] = {};
+    float ms[5] = {};
+};
+
+namespace {
+
+__global__ void k_count_mask(const uint8_t *__restrict__ mask, uint64_t n, uint32_t *__restrict__ out) {
+    uint32_t c = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) c += mask[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+unsigned grid_for(uint64_t items, int per_block, int waves = 8) {
+    uint64_t b = (items + per_block - 1) / per_block;
+    b = std::min<uint64_t>(b, (uint64_t)g_sms * waves);
+    return (unsigned)std::max<uint64_t>(b, 1);
+}
+
+int mesh_run(gsdf_mesher *m) {
+    gsdf_program *p = m->prog;
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = p->stream;
+    const MeshDims &D = m->D;
+    const bool prune = (m->flags & GSDF_MESH_PRUNE) != 0;
+    const int nk = D.cz1 - D.cz0 + 1;
+    const uint64_t nquads = (uint64_t)D.nqx * (D.ny + 1) * nk;
+    const uint64_t nblocks = (uint64_t)D.nbx * D.nby * D.nbz;
+    const uint64_t nseg = (uint64_t)D.nsx * D.ny * (D.cz1 - D.cz0);
+    const uint64_t ncells = (uint64_t)D.nx * D.ny * (D.cz1 - D.cz0);
+    int rc;
+    if ((rc = grow(m->d_grid, m->grid_cap, (size_t)D.pitch * (D.ny + 1) * nk))) return rc;
+    if ((rc = grow(m->d_seg, m->seg_cap, (size_t)nseg))) return rc;
+    const uint64_t nscanblocks = (nseg + kThreads * kScanItems - 1) / (kThreads * kScanItems);
+    if ((rc = grow(m->d_blocksum, m->blocksum_cap, (size_t)nscanblocks))) return rc;
+    if (prune) {
+        if ((rc = grow(m->d_mask, m->mask_cap, (size_t)nblocks))) return rc;
+        if ((rc = grow(m->d_list, m->list_cap, (size_t)nquads))) return rc;
+    }
+    if (m->flags & GSDF_MESH_KEEP_CASES) {
+        if ((rc = grow(m->d_cases, m->cases_cap, (size_t)ncells))) return rc;
+    }
+    if (m->flags & GSDF_MESH_KEEP_GRID) CU(cudaMemsetAsync(m->d_grid, 0x7f, (size_t)D.pitch * (D.ny + 1) * nk * sizeof(float), st));
+    CU(cudaMemsetAsync(m->d_ctr, 0, 8 * sizeof(uint32_t), st));
+
+    CU(cudaEventRecord(m->ev[0], st));
+    const gsdf_lattice &lat = m->lat;
+    if (prune) {
+        GenCenters gc;
+        gc.ox = lat.origin[0]; gc.oy = lat.origin[1]; gc.oz = lat.origin[2]; gc.res = lat.res;
+        gc.nbx = D.nbx; gc.nby = D.nby; gc.nbz = D.nbz; gc.bz0 = D.bz0;
+        const float size = lat.res * 4.0f;          // ms3.Octree.CubeSize of a level-3 cube
+        gc.half = size * 0.5f;
+        gc.maxDist = size * (float)(1.73205080757 / 2);  // octreerenderer.go:182 with glrender.go:9
+        gc.mask = m->d_mask;
+        if ((rc = launch_eval<4>(p, gc, (uint64_t)((D.nbx + 3) / 4) * D.nby * D.nbz, st))) return rc;
+        k_compact_quads<<<grid_for(nquads, kThreads), kThreads, 0, st>>>(D, m->d_mask, m->d_list, m->d_ctr + 0);
+        CU(cudaGetLastError());
+        k_count_mask<<<grid_for(nblocks, kThreads, 2), kThreads, 0, st>>>(m->d_mask, nblocks, m->d_ctr + 4);
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(m->ev[1], st));
+    {
+        GenGrid g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
+        // with a device-side list length the launch is sized for the worst case; CTAs beyond the list exit at once
+        if ((rc = launch_eval<4>(p, g, nquads, st))) return rc;
+    }
+    CU(cudaEventRecord(m->ev[2], st));
+    MCArgs A;
+    A.D = D;
+    A.ox = lat.origin[0]; A.oy = lat.origin[1]; A.oz = lat.origin[2]; A.res = lat.res;
+    A.cubeDiag = (float)(2 * 1.73205080757) * lat.res;  // flatrenderer.go:202
+    A.grid = m->d_grid;
+    A.mask = prune ? m->d_mask : nullptr;
+    A.segcount = m->d_seg;
+    A.tris = m->d_tris;
+    A.tri_capacity = m->tri_cap / 9;
+    A.cases = (m->flags & GSDF_MESH_KEEP_CASES) ? m->d_cases : nullptr;
+    A.overflow = m->d_ctr + 1;
+    k_mc_count<<<grid_for(nseg, kThreads / 32), kThreads, 0, st>>>(A);
+    CU(cudaGetLastError());
+    k_scan_reduce<<<(unsigned)nscanblocks, kThreads, 0, st>>>(m->d_seg, nseg, m->d_blocksum);
+    CU(cudaGetLastError());
+    k_scan_blocksums<<<1, 1024, 0, st>>>(m->d_blocksum, (uint32_t)nscanblocks, reinterpret_cast<unsigned long long *>(m->d_ctr + 2));
+    CU(cudaGetLastError());
+    k_scan_apply<<<(unsigned)nscanblocks, kThreads, 0, st>>>(m->d_seg, nseg, m->d_blocksum);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(m->ev[3], st));
+
+    A.cases = nullptr;
+    bool emitted = false;
+    if (m->tri_cap > 0) {  // optimistic emit into the existing buffer (steady state: no mid-pipeline host sync)
+        k_mc_emit<<<grid_for(nseg, kThreads / 32), kThreads, 0, st>>>(A);
+        CU(cudaGetLastError());
+        emitted = true;
+    }
+    CU(cudaMemcpyAsync(m->h_ctr, m->d_ctr, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    uint64_t total;
+    std::memcpy(&total, m->h_ctr + 2, 8);
+    if (!emitted || total * 9 > m->tri_cap) {
+        if ((rc = grow(m->d_tris, m->tri_cap, (size_t)std::max<uint64_t>(total, 1) * 9))) return rc;
+        A.tris = m->d_tris;
+        A.tri_capacity = m->tri_cap / 9;
+        CU(cudaMemsetAsync(m->d_ctr + 1, 0, sizeof(uint32_t), st));
+        k_mc_emit<<<grid_for(nseg, kThreads / 32), kThreads, 0, st>>>(A);
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(m->ev[4], st));
+    CU(cudaStreamSynchronize(st));
+    m->ntri = total;
+    m->read_pos = 0;
+    if (prune) {
+        m->evals = nblocks + 4ull * m->h_ctr[0];
+        m->pruned = (nblocks - m->h_ctr[4]) * 64ull;  // Cube.DecomposesTo(1) of a level-3 cube = 8^2
+    } else {
+        m->evals = (uint64_t)(D.nx + 1) * (D.ny + 1) * nk;
+        m->pruned = 0;
+    }
+    for (int i = 0; i < 4; i++) cudaEventElapsedTime(&m->ms[i], m->ev[i], m->ev[i + 1]);
+    cudaEventElapsedTime(&m->ms[4], m->ev[0], m->ev[4]);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gsdf_mesh_begin(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, unsigned flags, gsdf_mesher **out) {
+    if (!p || !lat || !out) return fail(GSDF_EINVAL, "gsdf_mesh_begin: NULL argument");
+    if (p->dim != 3) return fail(GSDF_EINVAL, "program is not 3D");
+    if (!(lat->res > 0) || lat->n[0] <= 0 || lat->n[1] <= 0 || lat->n[2] <= 0) return fail(GSDF_ERES, "resolution not fine enough for marching cubes");
+    if (cz0 < 0 || cz1 > lat->n[2] || cz0 >= cz1) return fail(GSDF_EINVAL, "bad cell slab [%d,%d)", cz0, cz1);
+    int rc = ensure_device();
+    if (rc) return rc;
+    CU(cudaSetDevice(p->device));
+    gsdf_mesher *m = new gsdf_mesher();
+    m->prog = p;
+    m->lat = *lat;
+    m->flags = flags;
+    MeshDims &D = m->D;
+    D.nx = lat->n[0]; D.ny = lat->n[1]; D.nz = lat->n[2];
+    D.cz0 = cz0; D.cz1 = cz1;
+    D.nbx = (D.nx + 3) / 4; D.nby = (D.ny + 3) / 4;
+    D.bz0 = cz0 >> 2;
+    D.nbz = ((cz1 + 3) >> 2) - D.bz0;
+    D.nqx = (D.nx + 1 + 3) / 4;
+    D.pitch = D.nqx * 4;
+    D.nsx = (D.nx + 31) / 32;
+    cudaError_t e = cudaMalloc((void **)&m->d_ctr, 8 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&m->h_ctr, 8 * sizeof(uint32_t));
+    for (int i = 0; i < 5 && e == cudaSuccess; i++) e = cudaEventCreate(&m->ev[i]);
+    if (e != cudaSuccess) { gsdf_mesh_destroy(m); return fail(GSDF_ECUDA, "mesher setup: %s", cudaGetErrorString(e)); }
+    rc = mesh_run(m);
+    if (rc) { gsdf_mesh_destroy(m); return rc; }
+    *out = m;
+    return 0;
+}
+
+int gsdf_mesh_rerun(gsdf_mesher *m) {
+    if (!m) return fail(GSDF_EINVAL, "gsdf_mesh_rerun: NULL mesher");
+    return mesh_run(m);
+}
+
+int64_t gsdf_mesh_read(gsdf_mesher *m, float *tri9, size_t max_tris) {
+    if (!m || !tri9) return fail(GSDF_EINVAL, "gsdf_mesh_read: NULL argument");
+    if (max_tris < 5) return fail(GSDF_ESHORT, "short buffer");  // flatrenderer.go:187
+    CU(cudaSetDevice(m->prog->device));
+    const uint64_t left = m->ntri - m->read_pos;
+    const uint64_t n = std::min<uint64_t>(left, max_tris);
+    if (n == 0) return 0;  // io.EOF
+    CU(cudaMemcpy(tri9, m->d_tris + m->read_pos * 9, n * 9 * sizeof(float), cudaMemcpyDeviceToHost));
+    m->read_pos += n;
+    return (int64_t)n;
+}
+
+int gsdf_mesh_device_triangles(gsdf_mesher *m, const float **d_tri9, uint64_t *ntri) {
+    if (!m) return fail(GSDF_EINVAL, "NULL mesher");
+    if (d_tri9) *d_tri9 = m->d_tris;
+    if (ntri) *ntri = m->ntri;
+    return 0;
+}
+
+int gsdf_mesh_stats(const gsdf_mesher *m, uint64_t *evals, uint64_t *pruned, uint64_t *tris) {
+    if (!m) return fail(GSDF_EINVAL, "NULL mesher");
+    if (evals) *evals = m->evals;
+    if (pruned) *pruned = m->pruned;
+    if (tris) *tris = m->ntri;
+    return 0;
+}
+
+int gsdf_mesh_cases(gsdf_mesher *m, uint8_t *cases, size_t nbytes) {
+    if (!m || !cases) return fail(GSDF_EINVAL, "NULL argument");
+    if (!(m->flags & GSDF_MESH_KEEP_CASES)) return fail(GSDF_EINVAL, "mesher was not created with GSDF_MESH_KEEP_CASES");
+    const size_t need = (size_t)m->D.nx * m->D.ny * (m->D.cz1 - m->D.cz0);
+    if (nbytes != need) return fail(GSDF_ELEN, "cases buffer must be %zu bytes", need);
+    CU(cudaSetDevice(m->prog->device));
+    CU(cudaMemcpy(cases, m->d_cases, need, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int gsdf_mesh_grid(gsdf_mesher *m, float *grid, size_t nfloats) {
+    if (!m || !grid) return fail(GSDF_EINVAL, "NULL argument");
+    if (!(m->flags & GSDF_MESH_KEEP_GRID)) return fail(GSDF_EINVAL, "mesher was not created with GSDF_MESH_KEEP_GRID");
+    const MeshDims &D = m->D;
+    const size_t rows = (size_t)(D.ny + 1) * (D.cz1 - D.cz0 + 1);
+    if (nfloats != rows * (D.nx + 1)) return fail(GSDF_ELEN, "grid buffer must be %zu floats", rows * (D.nx + 1));
+    CU(cudaSetDevice(m->prog->device));
+    CU(cudaMemcpy2D(grid, (size_t)(D.nx + 1) * 4, m->d_grid, (size_t)D.pitch * 4, (size_t)(D.nx + 1) * 4, rows, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int gsdf_mesh_timings(const gsdf_mesher *m, float ms[5]) {
+    if (!m || !ms) return fail(GSDF_EINVAL, "NULL argument");
+    for (int i = 0; i < 5; i++) ms[i] = m->ms[i];
+    return 0;
+}
+
+void gsdf_mesh_destroy(gsdf_mesher *m) {
+    if (!m) return;
+    if (m->prog) cudaSetDevice(m->prog->device);
+    cudaFree(m->d_grid); cudaFree(m->d_mask); cudaFree(m->d_list); cudaFree(m->d_seg); cudaFree(m->d_blocksum);
+    cudaFree(m->d_tris); cudaFree(m->d_cases); cudaFree(m->d_stl); cudaFree(m->d_ctr);
+    if (m->h_ctr) cudaFreeHost(m->h_ctr);
+    for (auto &e : m->ev) if (e) cudaEventDestroy(e);
+    delete m;
+}
+
+// ------------------------------------------------------------------------------------------------ STL
+static int64_t stl_from_device(const float *d_tri9, uint64_t n, uint8_t *&d_stl, size_t &stl_cap, void *dst, size_t dst_bytes, cudaStream_t st) {
+    if (n == 0) return fail(GSDF_EEMPTY, "empty triangle slice");                         // stl.go:16-18
+    if (n > 0xffffffffull) return fail(GSDF_EINVAL, "amount of triangles in model exceeds STL design limits");  // stl.go:21-23
+    const size_t bytes = 84 + 50 * (size_t)n;
+    if (!dst || dst_bytes < bytes) return fail(GSDF_ELEN, "STL buffer needs %zu bytes", bytes);
+    // records start 16-byte aligned: 12 bytes of front padding + 84 header bytes = 96
+    int rc = grow(d_stl, stl_cap, bytes + 12 + 16);
+    if (rc) return rc;
+    uint8_t hdr[84] = {0};
+    const uint32_t cnt = (uint32_t)n;
+    std::memcpy(hdr + 80, &cnt, 4);
+    CU(cudaMemcpyAsync(d_stl + 12, hdr, 84, cudaMemcpyHostToDevice, st));
+    k_stl_pack<<<grid_for(n, kThreads), kThreads, 0, st>>>(d_tri9, n, d_stl + 96);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(dst, d_stl + 12, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return (int64_t)bytes;
+}
+
+int64_t gsdf_mesh_stl(gsdf_mesher *m, void *dst, size_t dst_bytes) {
+    if (!m) return fail(GSDF_EINVAL, "NULL mesher");
+    CU(cudaSetDevice(m->prog->device));
+    return stl_from_device(m->d_tris, m->ntri, m->d_stl, m->stl_cap, dst, dst_bytes, m->prog->stream);
+}
+
+int64_t gsdf_stl_pack(const float *tri9, size_t n, void *dst, size_t dst_bytes) {
+    if (n == 0) return fail(GSDF_EEMPTY, "empty triangle slice");
+    if (!tri9) return fail(GSDF_EINVAL, "NULL triangles");
+    int rc = ensure_device();
+    if (rc) return rc;
+    float *d_t = nullptr;
+    uint8_t *d_stl = nullptr;
+    size_t cap = 0;
+    cudaError_t e = cudaMalloc((void **)&d_t, n * 36);
+    if (e != cudaSuccess) return fail(GSDF_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+    e = cudaMemcpy(d_t, tri9, n * 36, cudaMemcpyHostToDevice);
+    int64_t r = e == cudaSuccess ? stl_from_device(d_t, n, d_stl, cap, dst, dst_bytes, 0) : fail(GSDF_ECUDA, "H2D: %s", cudaGetErrorString(e));
+    cudaFree(d_t);
+    cudaFree(d_stl);
+    return r;
+}
+
+}  // extern "C"

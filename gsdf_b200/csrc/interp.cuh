@@ -1,0 +1,530 @@
+// interp.cuh -- the node-program interpreter: one stack machine per point, P points per thread.
+//
+// Every thread of a CTA walks the SAME instruction stream held in shared memory, so opcode dispatch is warp-uniform
+// (one indirect branch per instruction, no divergence); only a few primitives branch per point inside their bodies.
+// Per-point formulas restate cpu_evaluators.go / forge/threads/threads.go:141-202 operation by operation; the file
+// must be compiled with -fmad=false so each float32 op rounds individually, as Go/amd64 does.
+//
+// Stacks live in shared memory, laid out [slot][component][point][thread] so a warp access is one conflict-free
+// 128-byte wavefront. The distance-stack top and the current position stay in registers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gsdf_program.h"
+#include "math32.cuh"
+
+namespace gsdfk {
+
+template <int P>
+struct Machine {
+    float px[P], py[P], pz[P];  // current position
+    float top[P];               // distance stack top
+    float *dstk;                // &dstack[threadIdx.x]
+    float *pstk;                // &pstack[threadIdx.x]
+    int stride;                 // blockDim.x
+    int dsp, psp;
+
+    __device__ __forceinline__ void init(float *d, float *p, int s) {
+        dstk = d; pstk = p; stride = s; dsp = -1; psp = 0;
+#pragma unroll
+        for (int j = 0; j < P; j++) top[j] = 0.f;
+    }
+    __device__ __forceinline__ void pushD() {
+        int s = dsp < 0 ? 0 : dsp;
+#pragma unroll
+        for (int j = 0; j < P; j++) dstk[(s * P + j) * stride] = top[j];
+        dsp++;
+    }
+    __device__ __forceinline__ void popBelow(float (&a)[P]) {
+        dsp--;
+#pragma unroll
+        for (int j = 0; j < P; j++) a[j] = dstk[(dsp * P + j) * stride];
+    }
+    __device__ __forceinline__ void pushPos(const float (&x)[P], const float (&y)[P], const float (&z)[P]) {
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            pstk[((psp * 3 + 0) * P + j) * stride] = x[j];
+            pstk[((psp * 3 + 1) * P + j) * stride] = y[j];
+            pstk[((psp * 3 + 2) * P + j) * stride] = z[j];
+        }
+        psp++;
+    }
+    __device__ __forceinline__ void loadPos(int slot) {
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            px[j] = pstk[((slot * 3 + 0) * P + j) * stride];
+            py[j] = pstk[((slot * 3 + 1) * P + j) * stride];
+            pz[j] = pstk[((slot * 3 + 2) * P + j) * stride];
+        }
+    }
+};
+
+__device__ __forceinline__ float4 ldf4(const uint4 *prog, int i) {
+    uint4 u = prog[i];
+    return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+}
+
+// Runs the program at the P positions already loaded in m.px/py/pz; result in m.top.
+template <int P>
+__device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restrict__ prog, const float4 *__restrict__ aux) {
+    using namespace m32;
+    int pc = 0;
+    for (;;) {
+        const uint4 h = prog[pc];
+        const uint32_t op = h.x & 0xffu;
+        const int len = (int)((h.x >> 8) & 0xffu);
+        const float f2 = __uint_as_float(h.z), f3 = __uint_as_float(h.w);
+        switch (op) {
+        case GSDF_OP_END:
+            return;
+        // ------------------------------------------------------------------ 3D primitives
+        case GSDF_OP_SPHERE: {  // cpu_evaluators.go:20-26
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = norm3(m.px[j], m.py[j], m.pz[j]) - f2;
+        } break;
+        case GSDF_OP_BOX: {  // :28-36
+            const float4 c = ldf4(prog, pc + 1);
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float qx = (absf(m.px[j]) - c.x) + c.w, qy = (absf(m.py[j]) - c.y) + c.w, qz = (absf(m.pz[j]) - c.z) + c.w;
+                m.top[j] = norm3(maxf(qx, 0.f), maxf(qy, 0.f), maxf(qz, 0.f)) + minf(maxf(qx, maxf(qy, qz)), 0.f) - c.w;
+            }
+        } break;
+        case GSDF_OP_BOXFRAME: {  // :38-57
+            const float4 c = ldf4(prog, pc + 1);
+            const float e = c.w;
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float x = absf(m.px[j]) - c.x, y = absf(m.py[j]) - c.y, z = absf(m.pz[j]) - c.z;
+                float qx = absf(x + e) + (-e), qy = absf(y + e) + (-e), qz = absf(z + e) + (-e);
+                float s1 = minf(0.f, maxf(x, maxf(qy, qz)));
+                float n1 = norm3(maxf(x, 0.f), maxf(qy, 0.f), maxf(qz, 0.f)) + s1;
+                float s2 = minf(0.f, maxf(qx, maxf(y, qz)));
+                float n2 = norm3(maxf(qx, 0.f), maxf(y, 0.f), maxf(qz, 0.f)) + s2;
+                float s3 = minf(0.f, maxf(qx, maxf(qy, z)));
+                float n3 = norm3(maxf(qx, 0.f), maxf(qy, 0.f), maxf(z, 0.f)) + s3;
+                m.top[j] = minf(n1, minf(n2, n3));
+            }
+        } break;
+        case GSDF_OP_TORUS: {  // :59-68  f2=rGreater f3=rLesser
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = norm2(hypot32(m.px[j], m.py[j]) - f2, m.pz[j]) - f3;
+        } break;
+        case GSDF_OP_CYLINDER: {  // :70-88
+            const float4 c = ldf4(prog, pc + 1);
+            m.pushD();
+            if (h.y == 0u) {
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    float dx = hypot32(m.px[j], m.py[j]) - c.x;
+                    float dy = absf(m.pz[j]) - c.y;
+                    m.top[j] = minf(0.f, maxf(dx, dy)) + hypot32(maxf(0.f, dx), maxf(0.f, dy));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    float dx = hypot32(m.px[j], m.py[j]) - c.x + c.z;
+                    float dy = absf(m.pz[j]) - c.y;
+                    m.top[j] = minf(maxf(dx, dy), 0.f) + hypot32(maxf(dx, 0.f), maxf(dy, 0.f)) - c.z;
+                }
+            }
+        } break;
+        case GSDF_OP_HEX: {  // :90-105  c=(side,h,clm)
+            const float4 c = ldf4(prog, pc + 1);
+            const float k1 = (float)(-0.8660254037844386467637231707529361834714026269051903140279034897);
+            const float twok1 = (float)(2 * -0.8660254037844386467637231707529361834714026269051903140279034897);
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float x = absf(m.px[j]), y = absf(m.py[j]), z = absf(m.pz[j]);
+                float pm = minf(k1 * x + 0.5f * y, 0.f);
+                x -= twok1 * pm;
+                y -= 1.0f * pm;
+                float d1 = hypot32(x - clampf(x, -c.z, c.z), y - c.x) * signf(y - c.x);
+                float d2 = z - c.y;
+                m.top[j] = minf(maxf(d1, d2), 0.f) + hypot32(maxf(d1, 0.f), maxf(d2, 0.f));
+            }
+        } break;
+        // ------------------------------------------------------------------ 2D primitives
+        case GSDF_OP_CIRCLE2D: {  // :661
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = norm2(m.px[j], m.py[j]) - f2;
+        } break;
+        case GSDF_OP_RECT2D: {  // :685  f2=bx f3=by
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float dx = absf(m.px[j]) - f2, dy = absf(m.py[j]) - f3;
+                m.top[j] = norm2(maxf(dx, 0.f), maxf(dy, 0.f)) + minf(0.f, maxf(dx, dy));
+            }
+        } break;
+        case GSDF_OP_LINE2D: {  // :551  c1=(ax,ay,bax,bay) c2=(dotba,w)
+            const float4 c1 = ldf4(prog, pc + 1), c2 = ldf4(prog, pc + 2);
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float pax = m.px[j] - c1.x, pay = m.py[j] - c1.y;
+                float hh = clampf((pax * c1.z + pay * c1.w) / c2.x, 0.f, 1.f);
+                m.top[j] = norm2(pax - hh * c1.z, pay - hh * c1.w) - c2.y;
+            }
+        } break;
+        case GSDF_OP_LINES2D: {  // :1145  w1=aux_off(floats) w2=nseg w3=w
+            const float4 *seg = aux + (h.y >> 2);
+            const int nseg = (int)h.z;
+            float d[P];
+#pragma unroll
+            for (int j = 0; j < P; j++) d[j] = 1e23f;
+            for (int s = 0; s < nseg; s++) {
+                const float4 ab = seg[s];
+                const float bax = ab.z - ab.x, bay = ab.w - ab.y;
+                const float dotba = bax * bax + bay * bay;
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    float pax = m.px[j] - ab.x, pay = m.py[j] - ab.y;
+                    float hh = clampf((pax * bax + pay * bay) / dotba, 0.f, 1.f);
+                    float ex = pax - hh * bax, ey = pay - hh * bay;
+                    d[j] = minf(d[j], ex * ex + ey * ey);
+                }
+            }
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = m32::sqrt(d[j]) - f3;
+        } break;
+        case GSDF_OP_ARC2D: {  // :564  c1=(r,t,s,c) c2=(scrx,scry)
+            const float4 c1 = ldf4(prog, pc + 1), c2 = ldf4(prog, pc + 2);
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float x = absf(m.px[j]), y = m.py[j];
+                m.top[j] = (c1.w * x > c1.z * y) ? norm2(x - c2.x, y - c2.y) - c1.y : absf(norm2(x, y) - c1.x) - c1.y;
+            }
+        } break;
+        case GSDF_OP_EQTRI2D: {  // :669  f2=r f3=r/k
+            const float k = (float)1.7320508075688772935274463415058723669428052538103806280558069794;
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float x = absf(m.px[j]) - f2, y = m.py[j] + f3;
+                if (x + k * y > 0.f) {
+                    float nx = x - k * y, ny = -k * x - y;
+                    x = 0.5f * nx; y = 0.5f * ny;
+                }
+                x -= clampf(x, -2.f * f2, 0.f);
+                m.top[j] = -norm2(x, y) * signf(y);
+            }
+        } break;
+        case GSDF_OP_HEX2D: {  // :718  f2=r f3=kz*r
+            const float kx = (float)(-0.8660254037844386467637231707529361834714026269051903140279034897), ky = 0.5f;
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float x = absf(m.px[j]), y = absf(m.py[j]);
+                float mm = 2.f * minf(kx * x + ky * y, 0.f);
+                x = x - mm * kx; y = y - mm * ky;
+                x = x - clampf(x, -f3, f3); y = y - f2;
+                m.top[j] = signf(y) * norm2(x, y);
+            }
+        } break;
+        case GSDF_OP_OCT2D: {  // :731  f2=r f3=kz*r
+            const float kx = -0.9238795325f, ky = 0.3826834323f;
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float x = absf(m.px[j]), y = absf(m.py[j]);
+                float mm = 2.f * minf(kx * x + ky * y, 0.f);
+                x = x - mm * kx; y = y - mm * ky;
+                mm = 2.f * minf(-kx * x + ky * y, 0.f);
+                x = x - mm * -kx; y = y - mm * ky;
+                x = x - clampf(x, -f3, f3); y = y - f2;
+                m.top[j] = signf(y) * norm2(x, y);
+            }
+        } break;
+        case GSDF_OP_DIAMOND2D: {  // :694  c=(bx,by,dot(b,b))
+            const float4 c = ldf4(prog, pc + 1);
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float x = absf(m.px[j]), y = absf(m.py[j]);
+                float ux = c.x - 2.f * x, uy = c.y - 2.f * y;
+                float hh = clampf((ux * c.x - uy * c.y) / c.z, -1.f, 1.f);
+                float d = norm2(x - (0.5f * c.x) * (1.f - hh), y - (0.5f * c.y) * (1.f + hh));
+                m.top[j] = d * signf(x * c.y + y * c.x - c.x * c.y);
+            }
+        } break;
+        case GSDF_OP_ROUNDX2D: {  // :705  f2=w f3=r
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float x = absf(m.px[j]), y = absf(m.py[j]);
+                float sub = 0.5f * minf(x + y, f2);
+                m.top[j] = norm2(x - sub, y - sub) - f3;
+            }
+        } break;
+        case GSDF_OP_POLY2D: {  // :793-818; aux records (v1x,v1y,ex,ey | norm2e,v2y,_,_)
+            const float4 *rec = aux + (h.y >> 2);
+            const int nv = (int)h.z;
+            float d[P];
+            uint32_t neg = 0u;  // bit j set <=> s == -1 for point j
+            {
+                const float4 r0 = rec[0];
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    float ax = m.px[j] - r0.x, ay = m.py[j] - r0.y;
+                    d[j] = ax * ax + ay * ay;
+                }
+            }
+            for (int iv = 0; iv < nv; iv++) {
+                const float4 ra = rec[2 * iv], rb = rec[2 * iv + 1];
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    float wx = m.px[j] - ra.x, wy = m.py[j] - ra.y;
+                    float c = clampf((wx * ra.z + wy * ra.w) / rb.x, 0.f, 1.f);
+                    float bx = wx - c * ra.z, by = wy - c * ra.w;
+                    d[j] = minf(d[j], bx * bx + by * by);
+                    bool b1 = m.py[j] >= ra.y, b2 = m.py[j] < rb.y, b3 = ra.z * wy > ra.w * wx;
+                    if ((b1 && b2 && b3) || (!b1 && !b2 && !b3)) neg ^= (1u << j);
+                }
+            }
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float s = (neg >> j) & 1u ? -1.f : 1.f;
+                m.top[j] = s * m32::sqrt(d[j]);
+            }
+        } break;
+        // ------------------------------------------------------------------ combiners
+        case GSDF_OP_MIN: {
+            float a[P]; m.popBelow(a);
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = minf(a[j], m.top[j]);
+        } break;
+        case GSDF_OP_MAX: {
+            float a[P]; m.popBelow(a);
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = maxf(a[j], m.top[j]);
+        } break;
+        case GSDF_OP_DIFF: {
+            float a[P]; m.popBelow(a);
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = maxf(a[j], -m.top[j]);
+        } break;
+        case GSDF_OP_XOR: {
+            float a[P]; m.popBelow(a);
+#pragma unroll
+            for (int j = 0; j < P; j++) { float b = m.top[j]; m.top[j] = maxf(minf(a[j], b), -maxf(a[j], b)); }
+        } break;
+        case GSDF_OP_SMOOTH_UNION: {  // :229-234
+            float a[P]; m.popBelow(a);
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float b = m.top[j];
+                float hh = clampf(0.5f + 0.5f * (b - a[j]) / f2, 0.f, 1.f);
+                m.top[j] = (b * (1.f - hh) + a[j] * hh) - f2 * hh * (1.f - hh);
+            }
+        } break;
+        case GSDF_OP_SMOOTH_DIFF: {  // :254-259
+            float a[P]; m.popBelow(a);
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float b = m.top[j];
+                float hh = clampf(0.5f - 0.5f * (b + a[j]) / f2, 0.f, 1.f);
+                m.top[j] = (a[j] * (1.f - hh) + (-b) * hh) + f2 * hh * (1.f - hh);
+            }
+        } break;
+        case GSDF_OP_SMOOTH_INTERSECT: {  // :279-284
+            float a[P]; m.popBelow(a);
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float b = m.top[j];
+                float hh = clampf(0.5f - 0.5f * (b - a[j]) / f2, 0.f, 1.f);
+                m.top[j] = (b * (1.f - hh) + a[j] * hh) + f2 * hh * (1.f - hh);
+            }
+        } break;
+        // ------------------------------------------------------------------ unary distance ops
+        case GSDF_OP_OFFSET:
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = m.top[j] + f2;
+            break;
+        case GSDF_OP_ANNULUS:
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = absf(m.top[j]) - f2;
+            break;
+        case GSDF_OP_MULDIST:
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = m.top[j] * f2;
+            break;
+        case GSDF_OP_SHELL_EXIT:
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = f2 * (absf(m.top[j]) - f2);
+            break;
+        case GSDF_OP_ADD_BELOW: {
+            float a[P]; m.popBelow(a);
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = m.top[j] + a[j];
+        } break;
+        case GSDF_OP_EXTRUDE_EXIT: {  // :524-529
+            float a[P]; m.popBelow(a);
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float d = m.top[j], wy = a[j];
+                m.top[j] = minf(0.f, maxf(d, wy)) + hypot32(maxf(d, 0.f), maxf(wy, 0.f));
+            }
+        } break;
+        case GSDF_OP_MAX_BELOW: {  // threads.go:176-180
+            float a[P]; m.popBelow(a);
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = maxf(m.top[j], a[j]);
+        } break;
+        // ------------------------------------------------------------------ position stack
+        case GSDF_OP_PUSH_POS: m.pushPos(m.px, m.py, m.pz); break;
+        case GSDF_OP_POP_POS: m.psp--; m.loadPos(m.psp); break;
+        case GSDF_OP_PEEK_POS: m.loadPos(m.psp - 1); break;
+        // ------------------------------------------------------------------ position transforms
+        case GSDF_OP_TRANSLATE: {  // :470, :980
+            const float4 c = ldf4(prog, pc + 1);
+#pragma unroll
+            for (int j = 0; j < P; j++) { m.px[j] = m.px[j] - c.x; m.py[j] = m.py[j] - c.y; m.pz[j] = m.pz[j] - c.z; }
+        } break;
+        case GSDF_OP_SCALE_POS:  // :300-302
+#pragma unroll
+            for (int j = 0; j < P; j++) { m.px[j] = f2 * m.px[j]; m.py[j] = f2 * m.py[j]; m.pz[j] = f2 * m.pz[j]; }
+            break;
+        case GSDF_OP_SYMMETRY:  // :314
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                if (h.y & 1u) m.px[j] = absf(m.px[j]);
+                if (h.y & 2u) m.py[j] = absf(m.py[j]);
+                if (h.y & 4u) m.pz[j] = absf(m.pz[j]);
+            }
+            break;
+        case GSDF_OP_TRANSFORM: {  // :488-498 MulPosition, w=1
+            const float4 r0 = ldf4(prog, pc + 1), r1 = ldf4(prog, pc + 2), r2 = ldf4(prog, pc + 3);
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float x = m.px[j], y = m.py[j], z = m.pz[j];
+                m.px[j] = r0.x * x + r0.y * y + r0.z * z + r0.w;
+                m.py[j] = r1.x * x + r1.y * y + r1.z * z + r1.w;
+                m.pz[j] = r2.x * x + r2.y * y + r2.z * z + r2.w;
+            }
+        } break;
+        case GSDF_OP_ROTATE2D: {  // :1186
+            const float4 c = ldf4(prog, pc + 1);
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float x = m.px[j], y = m.py[j];
+                m.px[j] = c.x * x + c.y * y;
+                m.py[j] = c.z * x + c.w * y;
+            }
+        } break;
+        case GSDF_OP_TWIST:  // :1257
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float s, c;
+                m32::sincos(f2 * m.pz[j], s, c);
+                float x = m.px[j], y = m.py[j];
+                m.px[j] = c * x - s * y;
+                m.py[j] = s * x + c * y;
+            }
+            break;
+        case GSDF_OP_ELONGATE: {  // :399-417
+            const float4 c = ldf4(prog, pc + 1);
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float qx = absf(m.px[j]) - c.x, qy = absf(m.py[j]) - c.y, qz = absf(m.pz[j]) - c.z;
+                m.top[j] = minf(maxf(qx, maxf(qy, qz)), 0.f);
+                m.px[j] = maxf(qx, 0.f); m.py[j] = maxf(qy, 0.f); m.pz[j] = maxf(qz, 0.f);
+            }
+        } break;
+        case GSDF_OP_ELONGATE2D:  // :1228-1246
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float qx = absf(m.px[j]) - f2, qy = absf(m.py[j]) - f3;
+                m.top[j] = minf(maxf(qx, qy), 0.f);
+                m.px[j] = maxf(qx, 0.f); m.py[j] = maxf(qy, 0.f);
+            }
+            break;
+        case GSDF_OP_ARRAY_VAR: {  // :368-383
+            const float4 s = ldf4(prog, pc + 1), n = ldf4(prog, pc + 2);
+            const float fi = (float)(h.y & 1u), fj = (float)((h.y >> 1) & 1u), fk = (float)((h.y >> 2) & 1u);
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float x = m.px[j], y = m.py[j], z = m.pz[j];
+                float idx = roundf(x / s.x), idy = roundf(y / s.y), idz = roundf(z / s.z);
+                float ox = signf(x - s.x * idx), oy = signf(y - s.y * idy), oz = signf(z - s.z * idz);
+                float rx = clampf(idx + fi * ox, 0.f, n.x), ry = clampf(idy + fj * oy, 0.f, n.y), rz = clampf(idz + fk * oz, 0.f, n.z);
+                m.px[j] = x - s.x * rx; m.py[j] = y - s.y * ry; m.pz[j] = z - s.z * rz;
+            }
+        } break;
+        case GSDF_OP_ARRAY2D_VAR: {  // :936-949  c=(sx,sy,nx-1,ny-1)
+            const float4 c = ldf4(prog, pc + 1);
+            const float fi = (float)(h.y & 1u), fj = (float)((h.y >> 1) & 1u);
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float x = m.px[j], y = m.py[j];
+                float idx = roundf(x / c.x), idy = roundf(y / c.y);
+                float ox = signf(x - c.x * idx), oy = signf(y - c.y * idy);
+                float rx = clampf(idx + fi * ox, 0.f, c.z), ry = clampf(idy + fj * oy, 0.f, c.w);
+                m.px[j] = x - c.x * rx; m.py[j] = y - c.y * ry;
+            }
+        } break;
+        case GSDF_OP_CIRC_ENTER: {  // :1056-1078  c=(angle,ncirc,ninsm1)
+            const float4 c = ldf4(prog, pc + 1);
+            float x0[P], y0[P];
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float x = m.px[j], y = m.py[j];
+                float pangle = m32::atan2(y, x);
+                float id = floorf(pangle / c.x);
+                if (id < 0.f) id += c.y;
+                float i0, i1;
+                if (id >= c.z) { i0 = c.z; i1 = 0.f; } else { i0 = id; i1 = id + 1.f; }
+                float s0, c0, s1, c1;
+                m32::sincos(c.x * i0, s0, c0);
+                m32::sincos(c.x * i1, s1, c1);
+                x0[j] = c0 * x + s0 * y; y0[j] = -s0 * x + c0 * y;
+                m.px[j] = c1 * x + s1 * y; m.py[j] = -s1 * x + c1 * y;
+            }
+            m.pushPos(x0, y0, m.pz);
+        } break;
+        case GSDF_OP_EXTRUDE_ENTER:  // :524-527  f2=h/2
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = absf(m.pz[j]) - f2;
+            break;
+        case GSDF_OP_REVOLVE:  // :545-547
+#pragma unroll
+            for (int j = 0; j < P; j++) { m.px[j] = hypot32(m.px[j], m.pz[j]) - f2; }
+            break;
+        case GSDF_OP_SCREW_ENTER: {  // threads.go:156-170,198-202  c=(pitch,lead,L/2,tanTaper)
+            const float4 c = ldf4(prog, pc + 1);
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                float x = m.px[j], y = m.py[j], z = m.pz[j];
+                float yy = hypot32(x, y);
+                yy += z * c.w;
+                float theta = m32::atan2(y, x);
+                float zz = z + c.y * theta / m32::kTwoPiF;
+                float sx = zz + c.x / 2.f;
+                float t = sx / c.x;
+                m.px[j] = c.x * (t - floorf(t)) - c.x / 2.f;
+                m.py[j] = yy;
+                m.top[j] = absf(z) - c.z;
+            }
+        } break;
+        default:
+            return;  // unknown opcode: rejected at gsdf_program_create, never reached
+        }
+        pc += len;
+    }
+}
+
+}  // namespace gsdfk

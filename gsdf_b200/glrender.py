@@ -1,0 +1,206 @@
+"""Mirror of the reference's `glrender` package on the hot path: Renderer.ReadTriangles (glrender/glrender.go:11-13),
+RenderAll (:17-36), NewOctreeRenderer (octreerenderer.go:45), FlatRenderer (flatrenderer.go:17), WriteBinarySTL /
+ReadBinarySTL (stl.go:15,175) and ImageRendererSDF2's evaluation (image.go:76-105), all on the B200.
+
+Triangles are numpy float32 arrays of shape (n, 3, 3): ms3.Triangle = [3]ms3.Vec.
+"""
+import ctypes as C
+import io as _io
+import struct
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check, GsdfError, Lattice
+
+marchingCubesMaxTriangles = 5  # marchcubes.go:11
+
+
+class EOF(Exception):
+    """io.EOF"""
+
+
+class ErrShortBuffer(GsdfError):
+    """io.ErrShortBuffer"""
+
+
+def lattice_from_bounds(bbmin, bbmax, res):
+    """FlatRenderer.Reset's lattice (flatrenderer.go:47-56)."""
+    lat = Lattice()
+    mn = (C.c_float * 3)(*[float(v) for v in bbmin])
+    mx = (C.c_float * 3)(*[float(v) for v in bbmax])
+    check(lib.gsdf_lattice_from_bounds(mn, mx, float(res), C.byref(lat)))
+    return lat
+
+
+class _Renderer:
+    """Common part of the two renderers: the whole slab is meshed on the device when the renderer is created
+    (or Reset); ReadTriangles streams the result out in FlatRenderer order."""
+    _flags = 0
+
+    def __init__(self, sdf, cubeResolution, evalBufferSize=0, numParallel=1, cz_range=None, keep_cases=False, keep_grid=False):
+        self._h = None
+        self.Reset(sdf, cubeResolution, cz_range=cz_range, keep_cases=keep_cases, keep_grid=keep_grid)
+
+    def Reset(self, sdf, cubeResolution, evalBufferSize=0, numParallel=1, cz_range=None, keep_cases=False, keep_grid=False):
+        if not (cubeResolution > 0):
+            raise GsdfError(_lib.EINVAL, "invalid renderer cube resolution")  # flatrenderer.go:38, octreerenderer.go:73
+        self.Close()
+        self.sdf = sdf
+        mn, mx = sdf.Bounds()
+        self.lat = lattice_from_bounds(mn, mx, cubeResolution)
+        cz0, cz1 = cz_range if cz_range is not None else (0, self.lat.n[2])
+        self.cz0, self.cz1 = int(cz0), int(cz1)
+        flags = self._flags | (_lib.MESH_KEEP_CASES if keep_cases else 0) | (_lib.MESH_KEEP_GRID if keep_grid else 0)
+        h = C.c_void_p()
+        check(lib.gsdf_mesh_begin(sdf._h, C.byref(self.lat), self.cz0, self.cz1, flags, C.byref(h)))
+        self._h = h
+
+    def Rerun(self):
+        """Mesh the same slab again into the same device buffers (timing loops)."""
+        check(lib.gsdf_mesh_rerun(self._h))
+
+    def Close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.gsdf_mesh_destroy(h)
+
+    __del__ = Close
+
+    def ReadTriangles(self, dst, userData=None):
+        """Renderer.ReadTriangles(dst []ms3.Triangle) -> n. Raises EOF when nothing is left (Go returns n, io.EOF)."""
+        if dst.dtype != np.float32 or not dst.flags.c_contiguous:
+            raise GsdfError(_lib.EINVAL, "dst must be C-contiguous float32 (n,3,3)")
+        cap = dst.size // 9
+        if cap < marchingCubesMaxTriangles:
+            raise ErrShortBuffer(_lib.ESHORT, "short buffer")  # flatrenderer.go:187
+        n = check(lib.gsdf_mesh_read(self._h, C.c_void_p(dst.ctypes.data), cap))
+        if n == 0:
+            raise EOF()
+        return int(n)
+
+    def _stats(self):
+        e, p, t = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib.gsdf_mesh_stats(self._h, C.byref(e), C.byref(p), C.byref(t)))
+        return e.value, p.value, t.value
+
+    def Evaluations(self):
+        return self._stats()[0]
+
+    def TotalPruned(self):
+        """Octree.TotalPruned() (octreerenderer.go:66): unit cubes inside pruned level-3 cubes."""
+        return self._stats()[1]
+
+    def NumTriangles(self):
+        return self._stats()[2]
+
+    def Timings(self):
+        ms = (C.c_float * 5)()
+        check(lib.gsdf_mesh_timings(self._h, ms))
+        return dict(prune_ms=ms[0], eval_ms=ms[1], classify_ms=ms[2], emit_ms=ms[3], total_ms=ms[4])
+
+    def Cases(self):
+        nx, ny = self.lat.n[0], self.lat.n[1]
+        out = np.empty((self.cz1 - self.cz0, ny, nx), dtype=np.uint8)
+        check(lib.gsdf_mesh_cases(self._h, C.c_void_p(out.ctypes.data), out.size))
+        return out
+
+    def Grid(self):
+        nx, ny = self.lat.n[0], self.lat.n[1]
+        out = np.empty((self.cz1 - self.cz0 + 1, ny + 1, nx + 1), dtype=np.float32)
+        check(lib.gsdf_mesh_grid(self._h, C.c_void_p(out.ctypes.data), out.size))
+        return out
+
+    def AllTriangles(self):
+        """All triangles of the slab in one device->host copy."""
+        nt = self.NumTriangles()
+        out = np.empty((nt, 3, 3), dtype=np.float32)
+        got = 0
+        while got < nt:
+            n = check(lib.gsdf_mesh_read(self._h, C.c_void_p(out[got:].ctypes.data), max(nt - got, 5)))
+            if n == 0:
+                break
+            got += n
+        return out[:got]
+
+    def STLBytes(self):
+        """WriteBinarySTL of the slab's triangles, packed on the device (one host write)."""
+        nt = self.NumTriangles()
+        buf = np.empty(84 + 50 * nt, dtype=np.uint8)
+        n = check(lib.gsdf_mesh_stl(self._h, C.c_void_p(buf.ctypes.data), buf.size))
+        return buf[:n].tobytes()
+
+
+class Octree(_Renderer):
+    """glrender.Octree: marching cubes with level-3 cube pruning (octreerenderer.go:15-284)."""
+    _flags = _lib.MESH_PRUNE
+
+
+class FlatRenderer(_Renderer):
+    """glrender.FlatRenderer: every lattice corner evaluated once (flatrenderer.go:17-256)."""
+    _flags = 0
+
+
+def NewOctreeRenderer(s, cubeResolution, evalBufferSize=64, **kw):
+    if evalBufferSize < 64:
+        raise GsdfError(_lib.EINVAL, "bad octree eval buffer size")  # octreerenderer.go:46
+    return Octree(s, cubeResolution, evalBufferSize, **kw)
+
+
+def NewFlatRenderer(s, cubeResolution, evalBufferSize=4096, numParallel=1, **kw):
+    if evalBufferSize < 8:
+        raise GsdfError(_lib.EINVAL, "flat renderer eval buffer size must be at least 8")  # flatrenderer.go:41
+    if numParallel < 1:
+        raise GsdfError(_lib.EINVAL, "flat renderer numParallel must be at least 1")       # flatrenderer.go:44
+    return FlatRenderer(s, cubeResolution, evalBufferSize, numParallel, **kw)
+
+
+def RenderAll(r, userData=None):
+    """glrender.RenderAll (glrender.go:17-36): 4096-triangle buffer until io.EOF."""
+    startSize = 4096
+    buf = np.empty((startSize, 3, 3), dtype=np.float32)
+    parts = []
+    while True:
+        try:
+            n = r.ReadTriangles(buf, userData)
+        except EOF:
+            break
+        parts.append(buf[:n].copy())
+    return np.concatenate(parts) if parts else np.zeros((0, 3, 3), np.float32)
+
+
+def WriteBinarySTL(w, model):
+    """glrender.WriteBinarySTL(w io.Writer, model []ms3.Triangle) (stl.go:15-62). Returns bytes written."""
+    model = np.ascontiguousarray(model, dtype=np.float32)
+    n = model.size // 9
+    if n == 0:
+        raise GsdfError(_lib.EEMPTY, "empty triangle slice")  # stl.go:16
+    buf = np.empty(84 + 50 * n, dtype=np.uint8)
+    nb = check(lib.gsdf_stl_pack(C.c_void_p(model.ctypes.data), n, C.c_void_p(buf.ctypes.data), buf.size))
+    w.write(buf[:nb].tobytes())
+    return int(nb)
+
+
+def ReadBinarySTL(r):
+    """glrender.ReadBinarySTL (stl.go:175-225): returns the triangles (n,3,3); normals are not returned."""
+    data = r.read()
+    if len(data) < 84:
+        raise GsdfError(_lib.EINVAL, "encountered EOF while reading STL header")
+    (count,) = struct.unpack_from("<I", data, 80)
+    if count == 0:
+        raise GsdfError(_lib.EINVAL, "STL header indicates 0 triangles present")
+    if len(data) < 84 + 50 * count:
+        raise GsdfError(_lib.EINVAL, "%d/%d STL triangles read: unexpected EOF" % ((len(data) - 84) // 50, count))
+    rec = np.frombuffer(data, dtype=np.uint8, count=50 * count, offset=84).reshape(count, 50)
+    return rec[:, 12:48].copy().view(np.float32).reshape(count, 3, 3)
+
+
+def ImageEvaluateSDF2(sdf2, width, height):
+    """The evaluation ImageRendererSDF2.Render performs (image.go:76-105): distances at pixel centres, row 0 at
+    Bounds().Max.Y. Returns float32 (height, width)."""
+    mn, mx = sdf2.Bounds()
+    out = np.empty((height, width), dtype=np.float32)
+    a = (C.c_float * 2)(float(mn[0]), float(mn[1]))
+    b = (C.c_float * 2)(float(mx[0]), float(mx[1]))
+    check(lib.gsdf_image_eval2(sdf2._h, a, b, int(width), int(height), C.c_void_p(out.ctypes.data)))
+    return out

@@ -1,0 +1,133 @@
+/*
+ * gsdf_b200.h -- C ABI of libgsdfb200.so: the B200 (sm_100a) SDF evaluator + mesher behind gsdf's own API.
+ *
+ * This is the drop-in boundary for the hot path
+ *     glbuild.Shader3D tree -> gleval.SDF3.Evaluate -> glrender.Renderer.ReadTriangles -> glrender.WriteBinarySTL
+ * Every entry point names the reference interface it replaces (paths relative to the soypat/gsdf repository).
+ * A Go maintainer binds these with cgo (INTEGRATION.md shows the stub); tests bind them with ctypes.
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every call returns 0 / a count on success, a negative
+ *     gsdf_status on failure; gsdf_last_error() returns a thread-local message for the last failure.
+ *   - the library never retains caller pointers after a call returns (same contract as
+ *     gleval/gpu_cgo.go:194-258, which copies in and out on every Evaluate).
+ *   - handles are single-caller (like gleval.SDF3Compute, gleval/gpu.go:82-103); distinct handles may be
+ *     used from distinct threads.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with GSDF_ECUDA.
+ */
+#ifndef GSDF_B200_H
+#define GSDF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    GSDF_OK = 0,
+    GSDF_EINVAL = -1,   /* bad argument */
+    GSDF_ELEN = -2,     /* gleval.errMismatchBufferLength (gleval/gleval.go:48) */
+    GSDF_EEMPTY = -3,   /* gleval.errEmptyBuffers (gleval/gleval.go:47); empty model in WriteBinarySTL (stl.go:16) */
+    GSDF_ECUDA = -4,    /* CUDA runtime error / no device */
+    GSDF_ENOMEM = -5,
+    GSDF_EPROGRAM = -6, /* malformed node program */
+    GSDF_ESHORT = -7,   /* io.ErrShortBuffer: triangle buffer < 5 (octreerenderer.go:132, flatrenderer.go:187) */
+    GSDF_ERES = -8      /* "resolution not fine enough for marching cubes" (flatrenderer.go:53, octreerenderer.go:232) */
+} gsdf_status;
+
+typedef struct gsdf_program gsdf_program; /* a compiled tree resident on one device */
+typedef struct gsdf_mesher gsdf_mesher;   /* one Renderer instance (glrender.Renderer) */
+
+/* Library / device ----------------------------------------------------------------------------------- */
+const char *gsdf_version(void);
+const char *gsdf_last_error(void);
+/* Number of CUDA devices visible, or <0. */
+int gsdf_device_count(void);
+/* Select the device later handles are created on (one process per GPU: pass LOCAL_RANK). Replaces
+ * gleval.Init1x1GLFW (gleval/gpu.go:21) as the "bring the GPU up" call; no OS-thread pinning is needed. */
+int gsdf_set_device(int device);
+
+/* Program -------------------------------------------------------------------------------------------- */
+/* Upload a flattened tree (include/gsdf_program.h). Replaces Programmer.WriteComputeSDF3 + NewComputeGPUSDF3
+ * (glbuild/glbuild.go:175, gleval/gpu.go:35): "compile" is an upload of a few KB, done once.
+ * blob = gsdf_program_header followed by header.nchunks 16-byte chunks; aux = side buffer of floats. */
+int gsdf_program_create(const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats, gsdf_program **out);
+void gsdf_program_destroy(gsdf_program *p);
+/* gleval Evaluations() counter (gleval/cpu.go:126, gleval/gpu.go:80): points successfully evaluated through
+ * gsdf_eval3/gsdf_eval2 on this handle. */
+uint64_t gsdf_program_evaluations(const gsdf_program *p);
+
+/* Evaluate ------------------------------------------------------------------------------------------- */
+/* gleval.SDF3.Evaluate(pos []ms3.Vec, dist []float32, userData) (gleval/gleval.go:15-24). HOST pointers:
+ * pos_xyz is n AoS float3 (ms3.Vec, 12 B), dist is n float32. Copies in, runs the kernel, copies out.
+ * n==0 -> GSDF_EEMPTY (gleval/cpu.go:97-99). The Go shim checks len(pos)!=len(dist) -> GSDF_ELEN before calling. */
+int gsdf_eval3(gsdf_program *p, const float *pos_xyz, float *dist, size_t n);
+/* gleval.SDF2.Evaluate (gleval/gleval.go:28-37): pos_xy is n AoS float2 (ms2.Vec, 8 B). */
+int gsdf_eval2(gsdf_program *p, const float *pos_xy, float *dist, size_t n);
+/* Same kernels on DEVICE pointers already resident in HBM (no copies); stream is a cudaStream_t or NULL. */
+int gsdf_eval3_device(gsdf_program *p, const float *d_pos_xyz, float *d_dist, size_t n, void *stream);
+int gsdf_eval2_device(gsdf_program *p, const float *d_pos_xy, float *d_dist, size_t n, void *stream);
+
+/* Dense lattice ---------------------------------------------------------------------------------------- */
+typedef struct {
+    float origin[3]; /* lattice corner (0,0,0): (Bounds() scaled 1.01 about its centre).Min */
+    float res;       /* cube resolution */
+    int32_t n[3];    /* cells per axis; corners are (n+1) per axis */
+} gsdf_lattice;
+
+/* FlatRenderer.Reset's lattice (glrender/flatrenderer.go:47-56): bb*1.01, n=ceil(size/res). GSDF_ERES if n<=0. */
+int gsdf_lattice_from_bounds(const float bbmin[3], const float bbmax[3], float res, gsdf_lattice *out);
+/* FlatRenderer.evalGrid / evalKRange (glrender/flatrenderer.go:103-182) for corner planes k in [k0,k1):
+ * positions origin + float32(i)*res are synthesised in-kernel; (n0+1)*(n1+1)*(k1-k0) distances, x fastest, are
+ * written to `dist` (HOST pointer) or, if dist is NULL, only computed (timing). */
+int gsdf_grid_eval(gsdf_program *p, const gsdf_lattice *lat, int k0, int k1, float *dist);
+/* Same, into a DEVICE buffer with row pitch (n0+1) floats. */
+int gsdf_grid_eval_device(gsdf_program *p, const gsdf_lattice *lat, int k0, int k1, float *d_dist, void *stream);
+
+/* Mesher --------------------------------------------------------------------------------------------------- */
+enum {
+    GSDF_MESH_PRUNE = 1u << 0,      /* octree level-3 prune (octreerenderer.go:180-191,240-284); off = FlatRenderer */
+    GSDF_MESH_KEEP_CASES = 1u << 1, /* also keep the 8-bit cube-case index per cell (parity checks) */
+    GSDF_MESH_KEEP_GRID = 1u << 2   /* keep the distance lattice readable through gsdf_mesh_grid */
+};
+/* glrender.NewOctreeRenderer / FlatRenderer.Reset (octreerenderer.go:45, flatrenderer.go:37) on cells
+ * cz in [cz0,cz1) of the lattice (Z-slab; pass 0,n[2] for everything). The whole slab is meshed on the device
+ * inside this call; triangles stay in HBM until read. */
+int gsdf_mesh_begin(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, unsigned flags, gsdf_mesher **out);
+/* Re-run the same slab on the same handle, reusing every device buffer (Renderer.Reset semantics). */
+int gsdf_mesh_rerun(gsdf_mesher *m);
+/* Renderer.ReadTriangles(dst []ms3.Triangle) (glrender/glrender.go:11-13): copies up to max_tris triangles
+ * (9 floats each, vertex order as marchcubes.go:64-68) in FlatRenderer order (cell index x fastest,
+ * flatrenderer.go:208-212). Returns the count (0 = io.EOF), GSDF_ESHORT if max_tris < 5. */
+int64_t gsdf_mesh_read(gsdf_mesher *m, float *tri9, size_t max_tris);
+/* Device pointer to the slab's triangle buffer (9 floats per triangle) and its count, for on-device consumers. */
+int gsdf_mesh_device_triangles(gsdf_mesher *m, const float **d_tri9, uint64_t *ntri);
+/* Evaluations() / Octree.TotalPruned() / len(triangles) (gsdfaux/gsdfaux.go:219-226). */
+int gsdf_mesh_stats(const gsdf_mesher *m, uint64_t *evals, uint64_t *pruned_unit_cubes, uint64_t *tris);
+/* Parity hooks: per-cell case indices (nx*ny*(cz1-cz0) bytes) and the corner lattice of the slab. */
+int gsdf_mesh_cases(gsdf_mesher *m, uint8_t *cases, size_t nbytes);
+int gsdf_mesh_grid(gsdf_mesher *m, float *grid, size_t nfloats);
+/* Milliseconds of device time (CUDA events) the last begin/rerun spent in: [0] prune, [1] fine eval,
+ * [2] classify+scan, [3] emit, [4] total. */
+int gsdf_mesh_timings(const gsdf_mesher *m, float ms[5]);
+void gsdf_mesh_destroy(gsdf_mesher *m);
+
+/* STL ---------------------------------------------------------------------------------------------------- */
+/* glrender.WriteBinarySTL (glrender/stl.go:15-62): 80 zero bytes + u32 count + 50 B per triangle (unit normal,
+ * 3 vertices, u16 0). Packs n HOST triangles into dst (needs 84+50*n bytes) on the device and returns the byte
+ * count, so the caller does ONE write. n==0 -> GSDF_EEMPTY. */
+int64_t gsdf_stl_pack(const float *tri9, size_t n, void *dst, size_t dst_bytes);
+/* Same, straight from a mesher's device triangles (no host round trip of the 36 B/triangle form). */
+int64_t gsdf_mesh_stl(gsdf_mesher *m, void *dst, size_t dst_bytes);
+
+/* 2D image ------------------------------------------------------------------------------------------------ */
+/* ImageRendererSDF2.Render's evaluation (glrender/image.go:76-105): dist[j*w+i] = sdf(x_i, y_j) with
+ * x_i = float32(i)*dx + (min.x+dx/2), y_j = max.y - float32(j)*dy. dist is a HOST pointer (w*h floats). */
+int gsdf_image_eval2(gsdf_program *p, const float bbmin[2], const float bbmax[2], int w, int h, float *dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,77 @@
+/*
+ * gsdf_host.h -- flat C wrapper over the C++ host layer (gsdf_b200/csrc/host): the mirror of gsdf.Builder,
+ * forge/threads and the flattener, so Python (ctypes) tests and bench.py can build the reference's scenes without a
+ * Go toolchain.  In a Go deployment this layer is NOT used: the Go flattener emits the node program
+ * directly from the live glbuild.Shader3D tree and calls include/gsdf_b200.h.
+ */
+#ifndef GSDF_HOST_H
+#define GSDF_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "gsdf_b200.h"
+#include "gsdf_tree.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gsdfh_builder gsdfh_builder;
+
+gsdfh_builder *gsdfh_builder_new(void);
+void gsdfh_builder_free(gsdfh_builder *b);
+/* gsdf.Builder.Err() (gsdf.go:88): accumulated shape errors joined by '\n', "" when none. */
+const char *gsdfh_builder_err(gsdfh_builder *b);
+void gsdfh_builder_clear_errors(gsdfh_builder *b);
+
+/* Extra call codes for gsdfh_node beyond gsdf_node_kind (constructors that are not 1:1 with a node type). */
+enum {
+    GSDFH_CALL_ROTATE = 200,        /* Builder.Rotate(s, radians, axis): f = {radians, ax, ay, az} (operations.go:394) */
+    GSDFH_CALL_TRANSFORM16 = 201,   /* Builder.Transform(s, m): f = 16 floats row-major (operations.go:340) */
+    GSDFH_CALL_TRIPRISM = 202,      /* NewTriangularPrism(triHeight, extrudeLength) (primitives.go:198) */
+    GSDFH_CALL_BOUNDSBOXFRAME = 203 /* NewBoundsBoxFrame(bb): f = {min.xyz, max.xyz} (primitives.go:12) */
+};
+/* Generic constructor: `kind` is a gsdf_node_kind (dispatches to the Builder method of the same name, with its
+ * validation) or a GSDFH_CALL_* code. f/ip are the constructor's float/int arguments in declaration order;
+ * children are node ids; aux is variable-length float data (polygon vertices, segments, displacements).
+ * Returns the new node id, or <0 (message via gsdfh_builder_err). */
+int32_t gsdfh_node(gsdfh_builder *b, int32_t kind, const float *f, int nf, const int32_t *ip, int ni, const int32_t *children,
+                   int nchild, const float *aux, int naux);
+
+int gsdfh_is2d(gsdfh_builder *b, int32_t id);
+/* Shader3D.Bounds() / Shader2D.Bounds(): out = {min..., max...} */
+int gsdfh_bounds3(gsdfh_builder *b, int32_t id, float out[6]);
+int gsdfh_bounds2(gsdfh_builder *b, int32_t id, float out[4]);
+
+/* forge/threads front-ends. thread_kind: 0 ISO{D,P,Ext} (iso.go:20), 1 NPT from nominal size in p0 (npt.go:63). */
+int32_t gsdfh_thread_profile(gsdfh_builder *b, int thread_kind, float p0, float p1, int ext);                 /* Threader.Thread */
+int32_t gsdfh_screw(gsdfh_builder *b, float length, int thread_kind, float p0, float p1, int ext);            /* threads.Screw */
+int32_t gsdfh_nut(gsdfh_builder *b, int thread_kind, float p0, float p1, int ext, int style, float tol);      /* threads.Nut */
+int32_t gsdfh_bolt(gsdfh_builder *b, int thread_kind, float p0, float p1, int ext, int style, float tol, float total_len,
+                   float shank_len);                                                                          /* threads.Bolt */
+int32_t gsdfh_hexhead(gsdfh_builder *b, float radius, float height, int round_neg, int round_pos);            /* threads.HexHead */
+/* The example scenes BASELINE.json names: "npt-flange", "bolt", "knurled-cylinder" (param = diameter, 0 -> 20). */
+int32_t gsdfh_scene(gsdfh_builder *b, const char *name, float param);
+
+/* Tree table export (for the CPU oracle in tests). Pointers stay valid until the builder is next mutated. */
+int gsdfh_tree(gsdfh_builder *b, const gsdf_tree_node **nodes, int32_t *nnodes, const int32_t **children, int32_t *nchildren,
+               const float **aux, int32_t *naux);
+
+/* Flattener: tree -> node program (include/gsdf_program.h). */
+typedef struct gsdfh_flat gsdfh_flat;
+gsdfh_flat *gsdfh_flatten(gsdfh_builder *b, int32_t root);
+const void *gsdfh_flat_blob(const gsdfh_flat *f, size_t *nbytes);
+const float *gsdfh_flat_aux(const gsdfh_flat *f, size_t *nfloats);
+/* info = {dim, ninstr, nchunks, dstack, pstack} */
+void gsdfh_flat_info(const gsdfh_flat *f, int32_t info[5]);
+void gsdfh_flat_free(gsdfh_flat *f);
+
+/* NewCUDASDF3 / NewCUDASDF2: flatten + gsdf_program_create in one call (mirrors gleval.NewComputeGPUSDF3,
+ * gleval/gpu.go:35). */
+int gsdfh_compile(gsdfh_builder *b, int32_t root, gsdf_program **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

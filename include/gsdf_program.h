@@ -1,0 +1,108 @@
+/*
+ * gsdf_program.h -- the packed SDF node program: the contract between the host-side flattener and the sm_100a
+ * interpreter kernels.
+ *
+ * The reference walks its glbuild.Shader3D tree with ForEachChild / ForEach2DChild (glbuild/glbuild.go:63-89) and,
+ * on its GPU path, turns every node into GLSL text (glbuild/glbuild.go:175-214).  Here the same walk emits a linear
+ * postfix instruction stream that a stack machine executes once per point.  The stream has NO data-dependent control
+ * flow: every thread of every warp executes the same opcode at the same time (warp-uniform dispatch).
+ *
+ * Machine state per point:   p = (x,y,z)  current position (2D nodes use x,y)
+ *                            D            distance stack (top cached in a register)
+ *                            P            position stack (only used where a later sibling needs the old p)
+ *
+ * Layout: the stream is an array of 16-byte chunks (4 x u32).  Chunk 0 of an instruction is the header
+ *     w0 = opcode | (nchunks << 8)      nchunks counts the header itself
+ *     w1, w2, w3 = op-specific raw 32-bit fields (int or float bits)
+ * followed by nchunks-1 parameter chunks of 4 floats.  The side buffer `aux` holds variable-length float data
+ * (polygon edge records, line segments); offsets into it are in floats.
+ *
+ * All derived constants (half sizes, reciprocals, tan(taper) ...) are computed by the flattener in float32 with the
+ * same operation order cpu_evaluators.go uses per Evaluate call, so kernels stay bit-comparable with the CPU path.
+ */
+#ifndef GSDF_PROGRAM_H
+#define GSDF_PROGRAM_H
+
+#include <stdint.h>
+
+#define GSDF_PROGRAM_MAGIC 0x46445347u /* "GSDF" */
+#define GSDF_PROGRAM_VERSION 1u
+
+/* Opcode semantics. "push(v)": D.push(v). "top": D top. "below": pop the entry under the top.
+ * Reference citations are cpu_evaluators.go unless a file is named. */
+enum gsdf_opcode {
+    GSDF_OP_END = 0,
+    /* ---- 3D primitives: push(f(p)) ---- */
+    GSDF_OP_SPHERE,      /* :20   w2=r */
+    GSDF_OP_BOX,         /* :28   c1=(hx,hy,hz,round) */
+    GSDF_OP_BOXFRAME,    /* :38   c1=(bx,by,bz,e) */
+    GSDF_OP_TORUS,       /* :59   w2=rGreater w3=rLesser */
+    GSDF_OP_CYLINDER,    /* :70   c1=(r,h',round,_) ; w1=1 when round!=0 */
+    GSDF_OP_HEX,         /* :90   c1=(side,h,clm,_) */
+    /* ---- 2D primitives: push(f(p.xy)) ---- */
+    GSDF_OP_CIRCLE2D,    /* :661  w2=r */
+    GSDF_OP_RECT2D,      /* :685  w2=bx w3=by */
+    GSDF_OP_LINE2D,      /* :551  c1=(ax,ay,bax,bay) c2=(dotba,w,_,_) */
+    GSDF_OP_LINES2D,     /* :1145 w1=aux_off w2=nseg w3=w ; aux: (ax,ay,bx,by) per segment */
+    GSDF_OP_ARC2D,       /* :564  c1=(r,t,s,c) c2=(scrx,scry,_,_) */
+    GSDF_OP_EQTRI2D,     /* :669  w2=r w3=r/k */
+    GSDF_OP_HEX2D,       /* :718  w2=r w3=kz*r */
+    GSDF_OP_OCT2D,       /* :731  w2=r w3=kz*r */
+    GSDF_OP_DIAMOND2D,   /* :694  c1=(bx,by,dot(b,b),_) */
+    GSDF_OP_ROUNDX2D,    /* :705  w2=w w3=r */
+    GSDF_OP_POLY2D,      /* :793  w1=aux_off w2=nverts ; aux: (v1x,v1y,ex,ey,norm2e,v2y,_,_) per edge (8 floats) */
+    GSDF_OP_ELLIPSE2D,   /* :750  reserved */
+    GSDF_OP_BEZIERQ2D,   /* :581  reserved */
+    /* ---- distance combiners: b=top, a=below, top=f(a,b) ---- */
+    GSDF_OP_MIN,         /* :14,124,821  union fold */
+    GSDF_OP_MAX,         /* :146,847     intersect */
+    GSDF_OP_DIFF,        /* :168,869     max(a,-b) */
+    GSDF_OP_XOR,         /* :190,891 */
+    GSDF_OP_SMOOTH_UNION,     /* :213 w2=k */
+    GSDF_OP_SMOOTH_DIFF,      /* :238 w2=k */
+    GSDF_OP_SMOOTH_INTERSECT, /* :263 w2=k */
+    /* ---- unary distance ops on top ---- */
+    GSDF_OP_OFFSET,      /* :454,964  top += w2 */
+    GSDF_OP_ANNULUS,     /* :1026     top = |top| - w2 */
+    GSDF_OP_MULDIST,     /* :308,1222 top *= w2 (scale exit) */
+    GSDF_OP_SHELL_EXIT,  /* :448      top = w2*(|top| - w2) */
+    GSDF_OP_ADD_BELOW,   /* :422,1251 a=below; top = top + a (elongate exit) */
+    GSDF_OP_EXTRUDE_EXIT,/* :524-529  wy=below; top = min(0,max(top,wy)) + hypot(max(top,0),max(wy,0)) */
+    GSDF_OP_MAX_BELOW,   /* threads.go:176-180 a=below; top = max(top, a) (screw exit) */
+    /* ---- position stack ---- */
+    GSDF_OP_PUSH_POS,    /* P.push(p) */
+    GSDF_OP_POP_POS,     /* p = P.pop() */
+    GSDF_OP_PEEK_POS,    /* p = P.top() */
+    /* ---- position transforms: p = f(p) ---- */
+    GSDF_OP_TRANSLATE,   /* :470,980  c1=(tx,ty,tz,_) : p -= t (2D: tz=0) */
+    GSDF_OP_SCALE_POS,   /* :300,437,1216  w2=inv : p *= inv */
+    GSDF_OP_SYMMETRY,    /* :314,998  w1=mask bits x=1,y=2,z=4 */
+    GSDF_OP_TRANSFORM,   /* :488      c1..c3 = rows of tInv (x00 x01 x02 x03 / ...) */
+    GSDF_OP_ROTATE2D,    /* :1186     c1=(x00,x01,x10,x11) */
+    GSDF_OP_TWIST,       /* :1257     w2=k */
+    GSDF_OP_ELONGATE,    /* :399      c1=(hx,hy,hz,_) : q=|p|-h ; push(min(max(q),0)) ; p=max(q,0) */
+    GSDF_OP_ELONGATE2D,  /* :1228     w2=hx w3=hy */
+    GSDF_OP_ARRAY_VAR,   /* :345      w1=variant(i|j<<1|k<<2) c1=(sx,sy,sz,_) c2=(nx-1,ny-1,nz-1,_) */
+    GSDF_OP_ARRAY2D_VAR, /* :914      w1=variant(i|j<<1) c1=(sx,sy,nx-1,ny-1) */
+    GSDF_OP_CIRC_ENTER,  /* :1042,1094 c1=(angle,ncirc,ninsm1,_) : P.push(p0) ; p=p1 */
+    GSDF_OP_EXTRUDE_ENTER, /* :506    w2=h/2 : push(|z|-h/2) */
+    GSDF_OP_REVOLVE,     /* :533      w2=off : p=(hypot(x,z)-off, y) */
+    GSDF_OP_SCREW_ENTER, /* threads.go:141-170 c1=(pitch,lead,L/2,tanTaper) : push(|z|-L/2) ; p=(saw,y) */
+    GSDF_OP__COUNT
+};
+
+/* Header that precedes the instruction chunks in the blob handed to gsdf_program_create (one 16-byte chunk x2). */
+typedef struct {
+    uint32_t magic;      /* GSDF_PROGRAM_MAGIC */
+    uint32_t version;    /* GSDF_PROGRAM_VERSION */
+    uint32_t nchunks;    /* number of 16-byte instruction chunks that follow (END included) */
+    uint32_t dim;        /* 3 or 2: dimension of the root */
+    uint32_t dstack;     /* distance-stack slots needed below the cached top */
+    uint32_t pstack;     /* position-stack slots needed */
+    uint32_t ninstr;     /* instruction count (informational) */
+    uint32_t reserved;
+} gsdf_program_header;   /* 32 bytes */
+
+#define GSDF_POLY_EDGE_FLOATS 8
+
+#endif

@@ -1,0 +1,191 @@
+"""ctypes binding of the CPU ORACLE (oracle/gsdf_oracle.c). TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+The product (gsdf_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libgsdf_oracle.so")
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("gsdf_oracle.c", "gsdf_oracle.h", "mc_tables.inc", "Makefile")]
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
+        subprocess.check_call(["make", "-s", "-C", _HERE])
+    return LIB_PATH
+
+
+class GoNode(C.Structure):  # go_node, 96 bytes (same layout as gsdf_tree_node)
+    _fields_ = [("kind", C.c_int32), ("nchild", C.c_int32), ("child_off", C.c_int32), ("aux_off", C.c_int32),
+                ("aux_cnt", C.c_int32), ("iparam", C.c_int32 * 3), ("fparam", C.c_float * 16)]
+
+
+class GoTree(C.Structure):
+    _fields_ = [("nodes", C.c_void_p), ("nnodes", C.c_int32), ("children", C.c_void_p), ("aux", C.c_void_p), ("root", C.c_int32)]
+
+
+class GoLattice(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("res", C.c_float), ("n", C.c_int32 * 3)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        f32p, vp = C.POINTER(C.c_float), C.c_void_p
+        for name in ("go_sqrt", "go_atan", "go_sin", "go_cos", "go_tan", "go_floor", "go_round"):
+            getattr(L, name).restype = C.c_float
+            getattr(L, name).argtypes = [C.c_float]
+        for name in ("go_hypot", "go_atan2", "go_min", "go_max"):
+            getattr(L, name).restype = C.c_float
+            getattr(L, name).argtypes = [C.c_float, C.c_float]
+        L.go_eval3.restype = C.c_int
+        L.go_eval3.argtypes = [C.POINTER(GoTree), vp, vp, C.c_size_t]
+        L.go_eval2.restype = C.c_int
+        L.go_eval2.argtypes = [C.POINTER(GoTree), vp, vp, C.c_size_t]
+        L.go_flat_lattice.restype = C.c_int
+        L.go_flat_lattice.argtypes = [f32p, f32p, C.c_float, C.POINTER(GoLattice)]
+        L.go_octree_levels.restype = C.c_int
+        L.go_octree_levels.argtypes = [f32p, f32p, C.c_float]
+        L.go_flat_eval_grid.restype = C.c_int64
+        L.go_flat_eval_grid.argtypes = [C.POINTER(GoTree), C.POINTER(GoLattice), vp, C.c_int, C.c_int]
+        L.go_flat_march.restype = C.c_int64
+        L.go_flat_march.argtypes = [C.POINTER(GoLattice), vp, vp, C.c_int64, vp, vp]
+        L.go_octree_prune_mask.restype = C.c_int64
+        L.go_octree_prune_mask.argtypes = [C.POINTER(GoTree), C.POINTER(GoLattice), vp]
+        L.go_mc_cube.restype = C.c_int
+        L.go_mc_cube.argtypes = [f32p, f32p, f32p, C.POINTER(C.c_int)]
+        L.go_stl_write.restype = C.c_int64
+        L.go_stl_write.argtypes = [vp, C.c_int64, vp]
+        L.go_stl_read.restype = C.c_int64
+        L.go_stl_read.argtypes = [vp, C.c_size_t, vp, C.c_int64]
+        L.go_image_eval2.restype = C.c_int
+        L.go_image_eval2.argtypes = [C.POINTER(GoTree), f32p, f32p, C.c_int, C.c_int, vp]
+        L.go_mc_edge_table.restype = C.POINTER(C.c_int)
+        L.go_mc_tri_table.restype = C.POINTER(C.c_int8)
+        L.go_mc_pair_table.restype = C.POINTER(C.c_int)
+        _lib = L
+    return _lib
+
+
+class Tree:
+    """A tree table (bytes of go_node records, children int32[], aux float32[], root id) kept alive for the C calls."""
+
+    def __init__(self, nodes_bytes, children, aux, root):
+        self._nodes = C.create_string_buffer(nodes_bytes, len(nodes_bytes))
+        self._children = np.ascontiguousarray(children, dtype=np.int32)
+        self._aux = np.ascontiguousarray(aux, dtype=np.float32)
+        if self._children.size == 0:
+            self._children = np.zeros(1, np.int32)
+        if self._aux.size == 0:
+            self._aux = np.zeros(1, np.float32)
+        self.c = GoTree(C.cast(self._nodes, C.c_void_p), len(nodes_bytes) // C.sizeof(GoNode),
+                        self._children.ctypes.data, self._aux.ctypes.data, int(root))
+
+    @classmethod
+    def from_shader(cls, shader):
+        """Builds the oracle's tree table from a gsdf_b200.gsdf Shader (the host-side tree, NOT the flattened program)."""
+        nb, ch, aux = shader.bld.tree_table()
+        return cls(nb, ch, aux, shader.id)
+
+    def eval3(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        dist = np.empty(len(pos), dtype=np.float32)
+        rc = lib().go_eval3(C.byref(self.c), pos.ctypes.data, dist.ctypes.data, len(pos))
+        if rc:
+            raise RuntimeError("oracle go_eval3 failed: %d" % rc)
+        return dist
+
+    def eval2(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 2)
+        dist = np.empty(len(pos), dtype=np.float32)
+        rc = lib().go_eval2(C.byref(self.c), pos.ctypes.data, dist.ctypes.data, len(pos))
+        if rc:
+            raise RuntimeError("oracle go_eval2 failed: %d" % rc)
+        return dist
+
+    def image_eval2(self, bbmin, bbmax, w, h):
+        out = np.empty((h, w), dtype=np.float32)
+        a = (C.c_float * 2)(float(bbmin[0]), float(bbmin[1]))
+        b = (C.c_float * 2)(float(bbmax[0]), float(bbmax[1]))
+        rc = lib().go_image_eval2(C.byref(self.c), a, b, w, h, out.ctypes.data)
+        if rc:
+            raise RuntimeError("oracle go_image_eval2 failed: %d" % rc)
+        return out
+
+
+def flat_lattice(bbmin, bbmax, res):
+    lat = GoLattice()
+    a = (C.c_float * 3)(*[float(v) for v in bbmin])
+    b = (C.c_float * 3)(*[float(v) for v in bbmax])
+    if lib().go_flat_lattice(a, b, float(res), C.byref(lat)) != 0:
+        raise RuntimeError("resolution not fine enough for marching cubes")
+    return lat
+
+
+def octree_levels(bbmin, bbmax, res):
+    a = (C.c_float * 3)(*[float(v) for v in bbmin])
+    b = (C.c_float * 3)(*[float(v) for v in bbmax])
+    return lib().go_octree_levels(a, b, float(res))
+
+
+def flat_eval_grid(tree, lat, nthreads=1, batch=4096):
+    """FlatRenderer.evalGrid: returns (grid float32[nz+1, ny+1, nx+1], evaluations)."""
+    nx, ny, nz = lat.n
+    grid = np.empty((nz + 1, ny + 1, nx + 1), dtype=np.float32)
+    ev = lib().go_flat_eval_grid(C.byref(tree.c), C.byref(lat), grid.ctypes.data, nthreads, batch)
+    if ev < 0:
+        raise RuntimeError("oracle go_flat_eval_grid failed: %d" % ev)
+    return grid, int(ev)
+
+
+def octree_prune_mask(tree, lat):
+    nx, ny, nz = lat.n
+    mask = np.empty(((nz + 3) // 4, (ny + 3) // 4, (nx + 3) // 4), dtype=np.uint8)
+    kept = lib().go_octree_prune_mask(C.byref(tree.c), C.byref(lat), mask.ctypes.data)
+    if kept < 0:
+        raise RuntimeError("oracle go_octree_prune_mask failed: %d" % kept)
+    return mask, int(kept)
+
+
+def flat_march(lat, grid, want_cases=False, blockmask=None, max_tris=None):
+    """FlatRenderer.ReadTriangles sweep: returns (triangles (n,3,3), cases or None)."""
+    nx, ny, nz = lat.n
+    grid = np.ascontiguousarray(grid, dtype=np.float32)
+    cases = np.empty((nz, ny, nx), dtype=np.uint8) if want_cases else None
+    mp = blockmask.ctypes.data if blockmask is not None else None
+    cp = cases.ctypes.data if cases is not None else None
+    if max_tris is None:
+        max_tris = lib().go_flat_march(C.byref(lat), grid.ctypes.data, None, 0, cp, mp)
+    tris = np.empty((max(max_tris, 1), 3, 3), dtype=np.float32)
+    n = lib().go_flat_march(C.byref(lat), grid.ctypes.data, tris.ctypes.data, max_tris, cp, mp)
+    return tris[:min(n, max_tris)], cases
+
+
+def stl_write(tris):
+    tris = np.ascontiguousarray(tris, dtype=np.float32)
+    n = tris.size // 9
+    buf = np.empty(84 + 50 * max(n, 0), dtype=np.uint8)
+    nb = lib().go_stl_write(tris.ctypes.data, n, buf.ctypes.data)
+    if nb < 0:
+        raise ValueError("empty triangle slice")
+    return buf[:nb].tobytes()
+
+
+def stl_read(data):
+    arr = np.frombuffer(data, dtype=np.uint8)
+    n = lib().go_stl_read(arr.ctypes.data, arr.size, None, 0)
+    if n < 0:
+        raise ValueError("bad STL")
+    tris = np.empty((n, 3, 3), dtype=np.float32)
+    lib().go_stl_read(arr.ctypes.data, arr.size, tris.ctypes.data, n)
+    return tris
