@@ -55,6 +55,7 @@ def _load():
         "gsdf_grid_eval_device": (C.c_int, [vp, C.POINTER(Lattice), C.c_int, C.c_int, vp, vp]),
         "gsdf_mesh_begin": (C.c_int, [vp, C.POINTER(Lattice), C.c_int, C.c_int, C.c_uint, C.POINTER(vp)]),
         "gsdf_mesh_rerun": (C.c_int, [vp]),
+        "gsdf_mesh_set_program": (C.c_int, [vp, vp]),
         "gsdf_mesh_read": (C.c_int64, [vp, vp, C.c_size_t]),
         "gsdf_mesh_device_triangles": (C.c_int, [vp, C.POINTER(vp), u64p]),
         "gsdf_mesh_stats": (C.c_int, [vp, u64p, u64p, u64p]),

@@ -512,6 +512,14 @@ int gsdf_mesh_rerun(gsdf_mesher *m) {
     return mesh_run(m);
 }
 
+int gsdf_mesh_set_program(gsdf_mesher *m, gsdf_program *p) {
+    if (!m || !p) return fail(GSDF_EINVAL, "gsdf_mesh_set_program: NULL argument");
+    if (p->dim != 3) return fail(GSDF_EINVAL, "program is not 3D");
+    if (p->device != m->prog->device) return fail(GSDF_EINVAL, "program lives on another device");
+    m->prog = p;
+    return 0;
+}
+
 int64_t gsdf_mesh_read(gsdf_mesher *m, float *tri9, size_t max_tris) {
     if (!m || !tri9) return fail(GSDF_EINVAL, "gsdf_mesh_read: NULL argument");
     if (max_tris < 5) return fail(GSDF_ESHORT, "short buffer");  // flatrenderer.go:187

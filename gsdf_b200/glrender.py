@@ -60,6 +60,11 @@ class _Renderer:
         """Mesh the same slab again into the same device buffers (timing loops)."""
         check(lib.gsdf_mesh_rerun(self._h))
 
+    def Rebind(self, sdf):
+        """Keep lattice and device buffers, evaluate another SDF3CUDA on the next Rerun."""
+        check(lib.gsdf_mesh_set_program(self._h, sdf._h))
+        self.sdf = sdf
+
     def Close(self):
         h, self._h = getattr(self, "_h", None), None
         if h:

@@ -98,6 +98,9 @@ enum {
 int gsdf_mesh_begin(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, unsigned flags, gsdf_mesher **out);
 /* Re-run the same slab on the same handle, reusing every device buffer (Renderer.Reset semantics). */
 int gsdf_mesh_rerun(gsdf_mesher *m);
+/* Point the mesher at another (3D) program on the same device, keeping lattice and buffers: Renderer.Reset with a
+ * new SDF (octreerenderer.go:72, flatrenderer.go:37). The caller keeps ownership of both programs. */
+int gsdf_mesh_set_program(gsdf_mesher *m, gsdf_program *p);
 /* Renderer.ReadTriangles(dst []ms3.Triangle) (glrender/glrender.go:11-13): copies up to max_tris triangles
  * (9 floats each, vertex order as marchcubes.go:64-68) in FlatRenderer order (cell index x fastest,
  * flatrenderer.go:208-212). Returns the count (0 = io.EOF), GSDF_ESHORT if max_tris < 5. */

@@ -1,0 +1,183 @@
+"""Scene lists for the parity tests. They restate the reference's own test corpora:
+   testPrimitives3D (gsdf_test.go:182-201), testBinOp3D (:203-231), testRandomUnary3D (:255-283),
+   testPrimitives2D (:285-353), testBinary2D (:355-373), testRandomUnary2D (:233-253),
+   examples/test/glsdf3test.go:100-114 (screw / NPT profile).
+Go's math/rand stream (rand.NewSource(1), gsdf_test.go:49) cannot be regenerated without Go, so the randomised
+unary operations list explicit parameter draws inside the generators' ranges (gsdf_test.go:572-730)."""
+import math
+
+import numpy as np
+
+from gsdf_b200 import gsdf
+
+
+def primitives3d(bld):
+    maxdim = 1.0
+    dx, dy, dz = maxdim, maxdim * 0.47, maxdim * 0.8
+    thick = maxdim / 10
+    return [
+        ("sphere", bld.NewSphere(1)),
+        ("box", bld.NewBox(dx, dy, dz, thick)),
+        ("boxframe", bld.NewBoxFrame(dx, dy, dz, thick)),
+        ("cylinder", bld.NewCylinder(dx, dy, 0)),
+        ("cylinder_round", bld.NewCylinder(dx, dy, thick)),
+        ("hexprism", bld.NewHexagonalPrism(dx, dy)),
+        ("torus", bld.NewTorus(dx, dy)),
+        ("triprism", bld.NewTriangularPrism(1, 0.5)),
+    ]
+
+
+def binops3d(bld):
+    s1 = bld.NewSphere(1)
+    s2 = bld.Translate(bld.NewBox(1, 0.6, .8, 0.1), 0.5, 0.7, 0.8)
+    out = [
+        ("union", bld.Union(s1, s2)), ("difference", bld.Difference(s1, s2)),
+        ("intersection", bld.Intersection(s1, s2)), ("xor", bld.Xor(s1, s2)),
+        ("smoothunion", bld.SmoothUnion(0.1, s1, s2)), ("smoothdiff", bld.SmoothDifference(0.1, s1, s2)),
+        ("smoothintersect", bld.SmoothIntersect(0.1, s1, s2)),
+        ("union3", bld.Union(s1, s2, bld.Translate(bld.NewSphere(0.4), -0.9, 0.2, 0.1))),
+    ]
+    return out
+
+
+def unary3d(bld):
+    s2 = bld.NewBox(1, 0.61, 0.8, 0.3)
+    s2d = bld.NewRectangle(1, 0.57)
+    mn, mx = s2.Bounds()
+    size = mx - mn
+    thickness = float(min(size.max() / 128, 0.37))
+    shell = bld.Shell(s2, thickness)
+    halfbox = bld.NewBox(size[0] * 20, size[1] / 3, size[2] * 20, 0)
+    halfbox = bld.Translate(bld.Translate(halfbox, 0, size[1] / 3, 0), 0, size[1] / 3, 0)
+    return [
+        ("rotate", bld.Rotate(s2, 0.73, (1.3, 2.1, 0.4))),
+        ("rotate_neg", bld.Rotate(s2, -0.31, (0.2, 0.1, 2.9))),
+        ("shell", bld.Difference(shell, halfbox)),
+        ("elongate", bld.Elongate(s2, 0.11, 0.27, 0.05)),
+        ("round", bld.Offset(s2, -0.12)),
+        ("scale", bld.Scale(s2, 1.73)),
+        ("scale_small", bld.Scale(s2, 0.05)),
+        ("symmetry_x", bld.Symmetry(bld.Translate(s2, 0.3, 0.2, 0.1), True, False, False)),
+        ("symmetry_yz", bld.Symmetry(bld.Translate(s2, 0.3, 0.2, 0.1), False, True, True)),
+        ("translate", bld.Translate(s2, 0.7, -1.1, 0.35)),
+        ("array", bld.Array(s2, 1.05, 0.7, 0.93, 3, 2, 4)),
+        ("circarray", bld.CircularArray(bld.Translate(s2, 1.4, 0, 0), 5, 7)),
+        ("circarray_full", bld.CircularArray(bld.Translate(s2, 1.4, 0, 0), 6, 6)),
+        ("twist", bld.Twist(s2, 0.61)),
+        ("extrude", bld.Extrude(s2d, 1.7)),
+        ("revolve", bld.Revolve(s2d, 0)),
+        ("revolve_off", bld.Revolve(bld.Translate2D(s2d, 2, 0), 0.5)),
+        ("transform", bld.Transform(s2, [[1, 0.2, 0, 0.3], [0, 1.1, 0.1, -0.2], [0.1, 0, 0.9, 0.5], [0, 0, 0, 1]])),
+    ]
+
+
+def nagon(n, r):
+    """ms2.PolygonBuilder.Nagon(n, r) vertices as an (n,2) float32 array (iterated rotation, like the builder)."""
+    a = np.float32(2 * math.pi) / np.float32(n)
+    c, s = np.float32(math.cos(a)), np.float32(math.sin(a))
+    v = np.array([r, 0], dtype=np.float32)
+    out = []
+    for _ in range(n):
+        out.append(v.copy())
+        v = np.array([c * v[0] - s * v[1], s * v[0] + c * v[1]], dtype=np.float32)
+    return np.array(out, dtype=np.float32)
+
+
+def primitives2d(bld):
+    maxdim = 1.0
+    dx, dy = maxdim, maxdim * 0.47
+    thick = maxdim / 10
+    verts = nagon(8, 1)
+    segs = np.array([[verts[i - 1], verts[i]] for i in range(len(verts))], dtype=np.float32)
+    poly = bld.NewPolygon(verts)
+    return [
+        ("circle", bld.NewCircle(maxdim)),
+        ("line", bld.NewLine2D(0, 0, dx, dy, thick)),
+        ("rect", bld.NewRectangle(dx, dy)),
+        ("arc", bld.NewArc(dx, math.pi / 3, thick)),
+        ("hexagon", bld.NewHexagon(maxdim)),
+        ("eqtri", bld.NewEquilateralTriangle(maxdim)),
+        ("poly", poly),
+        ("poly_selfclosed", bld.NewPolygon([[0, 0], [0, 1], [1, 1], [0, 0]])),
+        ("lines", bld.NewLines2D(segs, 0.1)),
+        ("displace", bld.TranslateMulti2D(poly, verts)),
+        ("octagon", bld.NewOctagon(dx)),
+        ("diamond", bld.NewDiamond2D(dx, dy)),
+        ("roundx", bld.NewRoundedX(dx, thick)),
+        ("union_lines", bld.Union2D(bld.NewLine2D(1, 2, 3, 4, 0.5), bld.NewLine2D(2, 3, 0, 0, 0.2), bld.NewLine2D(2, 3, 4, 5, 0.2),
+                                    bld.NewLines2D([[[0, 0], [1, 1]], [[2, 2], [3, 1]]], 0.5))),
+    ]
+
+
+def binops2d(bld):
+    s2 = bld.NewRectangle(1, 0.61)
+    s1 = bld.Translate2D(bld.NewCircle(0.4), 0.45, 1)
+    return [("union2d", bld.Union2D(s1, s2)), ("diff2d", bld.Difference2D(s1, s2)),
+            ("intersect2d", bld.Intersection2D(s1, s2)), ("xor2d", bld.Xor2D(s1, s2))]
+
+
+def unary2d(bld):
+    obj = bld.Translate2D(bld.NewRectangle(1, 0.61), 2, .3)
+    return [
+        ("array2d", bld.Array2D(obj, 0.83, 1.07, 3, 5)),
+        ("circarray2d", bld.CircularArray2D(obj, 4, 9)),
+        ("symmetry2d_x", bld.Symmetry2D(obj, True, False)),
+        ("symmetry2d_xy", bld.Symmetry2D(obj, True, True)),
+        ("rotate2d", bld.Rotate2D(obj, 1.234)),
+        ("annulus", bld.Annulus(obj, 0.21)),
+        ("offset2d", bld.Offset2D(obj, -0.13)),
+        ("scale2d", bld.Scale2D(obj, 0.77)),
+        ("elongate2d", bld.Elongate2D(obj, 0.4, 0.15)),
+    ]
+
+
+def threads3d(bld):
+    T = gsdf.threads
+    return [
+        ("screw_iso", T.Screw(bld, 5, T.ISO(1, 0.1, True))),          # examples/test/glsdf3test.go:100-114
+        ("hexhead", T.HexHead(bld, 3.4641018, 2.8867514, False, True)),
+        ("nut_npt_circ", T.Nut(bld, T.NPT(0.5), T.NutCircular)),
+        ("nut_iso_hex", T.Nut(bld, T.ISO(3, 0.5, False), T.NutHex)),
+    ]
+
+
+def threads2d(bld):
+    T = gsdf.threads
+    return [("iso_ext_profile", T.Thread(bld, T.ISO(1, 0.1, True))), ("npt_profile", T.Thread(bld, T.NPT(0.5)))]
+
+
+def scenes3d(bld):
+    return [("npt-flange", gsdf.scene(bld, "npt-flange")), ("bolt", gsdf.scene(bld, "bolt")),
+            ("knurled-cylinder", gsdf.scene(bld, "knurled-cylinder"))]
+
+
+def all3d(bld):
+    return primitives3d(bld) + binops3d(bld) + unary3d(bld) + threads3d(bld) + scenes3d(bld)
+
+
+def all2d(bld):
+    return primitives2d(bld) + binops2d(bld) + unary2d(bld) + threads2d(bld)
+
+
+def grid_counts(size, testres=1.0 / 3):
+    """shaderTestConfig.div (gsdf_test.go:60-73): n = int(clamp(dim/testres, 5, 32)) per axis."""
+    return [int(min(max(float(d) / testres, 5), 32)) for d in size]
+
+
+def append_grid(mn, mx, counts):
+    """ms3.AppendGrid / ms2.AppendGrid: nx*ny(*nz) points, endpoints inclusive, x fastest."""
+    axes = [np.linspace(float(a), float(b), n, dtype=np.float64).astype(np.float32) for a, b, n in zip(mn, mx, counts)]
+    if len(axes) == 3:
+        z, y, x = np.meshgrid(axes[2], axes[1], axes[0], indexing="ij")
+        return np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1).astype(np.float32)
+    y, x = np.meshgrid(axes[1], axes[0], indexing="ij")
+    return np.stack([x.ravel(), y.ravel()], axis=1).astype(np.float32)
+
+
+def sample_points(shader, margin=0.15, dense=None):
+    """The lattice testShader3D/2D evaluates (gsdf_test.go:429-436), widened by `margin` so outside points are hit too."""
+    mn, mx = shader.Bounds()
+    size = mx - mn
+    lo, hi = mn - margin * size, mx + margin * size
+    counts = dense if dense is not None else grid_counts(size)
+    return append_grid(lo, hi, counts)

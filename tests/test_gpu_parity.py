@@ -1,0 +1,380 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the same
+inputs. Distances, cube-case indices, triangles and STL bytes must be BIT-IDENTICAL: both sides evaluate the same
+float32 operation sequences with individually rounded operations (-fmad=false vs -ffp-contract=off).
+north_star's tolerance for distances is 1e-5 relative to cpu_evaluators.go; bit equality with the oracle is stricter.
+"""
+import ctypes as C
+import hashlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+import shapes
+import gsdf_b200
+from gsdf_b200 import gsdf, gleval, glrender, _lib
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REL_TOL = 1e-5  # north_star: "within 1e-5 relative float tolerance"
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def gpu_eval(s, pos):
+    sdf = gleval.NewCUDASDF2(s) if s.is2d else gleval.NewCUDASDF3(s)
+    out = np.empty(len(pos), np.float32)
+    sdf.Evaluate(np.ascontiguousarray(pos, np.float32), out)
+    return out, sdf
+
+
+def check_field(name, s, oracle, pos):
+    t = oracle.Tree.from_shader(s)
+    want = t.eval2(pos) if s.is2d else t.eval3(pos)
+    got, sdf = gpu_eval(s, pos)
+    rel = np.abs(got.astype(np.float64) - want) / np.maximum(1.0, np.abs(want))
+    assert rel.max() <= REL_TOL, (name, float(rel.max()))
+    nbad = int((bits(got) != bits(want)).sum())
+    assert nbad == 0, "%s: %d of %d distances differ in their bits (max rel %.3g)" % (name, nbad, len(pos), rel.max())
+    assert sdf.Evaluations() == len(pos)
+
+
+# ---------------------------------------------------------------------------------------------- Evaluate parity
+@pytest.mark.parametrize("corpus", ["primitives3d", "binops3d", "unary3d", "threads3d", "scenes3d",
+                                    "primitives2d", "binops2d", "unary2d", "threads2d"])
+def test_evaluate_matches_oracle_on_reference_lattices(oracle, bld, corpus):
+    """testShader3D/testShader2D (gsdf_test.go:429-525): sample the AppendGrid lattice of Bounds()."""
+    for name, s in getattr(shapes, corpus)(bld):
+        check_field(name, s, oracle, shapes.sample_points(s))
+
+
+def test_evaluate_golden_fixtures(bld):
+    g = np.load(os.path.join(GOLD, "distances.npz"))
+    for name, s in shapes.all3d(bld) + shapes.all2d(bld):
+        got, _ = gpu_eval(s, g[name + ".pos"])
+        assert np.array_equal(bits(got), bits(g[name + ".dist"])), name
+
+
+def test_sphere_64cubed_plumbing(oracle, bld):
+    """BASELINE config 0: single sphere, dense 64^3 lattice over Bounds()."""
+    s = bld.NewSphere(1)
+    pos = shapes.sample_points(s, margin=0, dense=[64, 64, 64])
+    assert len(pos) == 262144
+    check_field("sphere64", s, oracle, pos)
+    got, _ = gpu_eval(s, pos)
+    assert np.abs(got - (np.linalg.norm(pos.astype(np.float64), axis=1) - 1)).max() < 1e-6
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 31, 32, 33, 255, 256, 257, 1023, 4097])
+def test_evaluate_ragged_sizes(oracle, bld, n):
+    s = gsdf.scene(bld, "npt-flange")
+    rng = np.random.default_rng(n)
+    mn, mx = s.Bounds()
+    pos = (mn + rng.random((n, 3), dtype=np.float32) * (mx - mn)).astype(np.float32)
+    check_field("flange_n%d" % n, s, oracle, pos)
+
+
+def test_evaluate_unaligned_views(oracle, bld):
+    """Host slices that are not 16-byte aligned must still work (Go passes &pos[k])."""
+    s = bld.NewBox(1, 0.6, 0.8, 0.1)
+    rng = np.random.default_rng(5)
+    base = rng.uniform(-1, 1, (1001, 3)).astype(np.float32)
+    pos = base[1:]            # +12 bytes
+    dist_base = np.empty(1003, np.float32)
+    dist = dist_base[3:]      # +12 bytes
+    sdf = gleval.NewCUDASDF3(s)
+    sdf.Evaluate(pos, dist)
+    want = oracle.Tree.from_shader(s).eval3(pos)
+    assert np.array_equal(bits(dist), bits(want))
+
+
+def test_evaluate_errors(bld):
+    """gleval/cpu.go:93-100: errMismatchBufferLength / errEmptyBuffers; wrong dimension is rejected."""
+    sdf = gleval.NewCUDASDF3(bld.NewSphere(1))
+    with pytest.raises(gsdf_b200.GsdfError) as e:
+        sdf.Evaluate(np.zeros((4, 3), np.float32), np.zeros(3, np.float32))
+    assert e.value.code == _lib.ELEN
+    with pytest.raises(gsdf_b200.GsdfError) as e:
+        sdf.Evaluate(np.zeros((0, 3), np.float32), np.zeros(0, np.float32))
+    assert e.value.code == _lib.EEMPTY
+    assert sdf.Evaluations() == 0  # evals only advance on success (cpu.go:116)
+    with pytest.raises(gsdf_b200.GsdfError):
+        gleval.NewCUDASDF2(bld.NewSphere(1))
+    with pytest.raises(gsdf_b200.GsdfError):
+        gleval.NewCUDASDF3(bld.NewCircle(1))
+    rc = _lib.lib.gsdf_eval3(None, None, None, 0)
+    assert rc == _lib.EINVAL and "NULL" in _lib.last_error()
+
+
+def test_program_create_rejects_malformed_blobs(bld):
+    f = bld.flatten(bld.NewSphere(1))
+    h = C.c_void_p()
+    blob = bytearray(f["blob"])
+    blob[0] ^= 0xff  # magic
+    assert _lib.lib.gsdf_program_create(bytes(blob), len(blob), None, 0, C.byref(h)) == _lib.EPROGRAM
+    blob = bytearray(f["blob"])
+    blob[32] = 250   # unknown opcode
+    assert _lib.lib.gsdf_program_create(bytes(blob), len(blob), None, 0, C.byref(h)) == _lib.EPROGRAM
+    blob = bytearray(f["blob"])[:-16]  # END chopped off
+    assert _lib.lib.gsdf_program_create(bytes(blob), len(blob), None, 0, C.byref(h)) == _lib.EPROGRAM
+
+
+def test_evaluate_device_pointers(oracle, bld):
+    """gsdf_eval3_device on buffers already resident in HBM (torch only provides the device memory)."""
+    import torch
+    s = gsdf.scene(bld, "bolt")
+    pos = shapes.sample_points(s, dense=[40, 40, 40])
+    dpos = torch.from_numpy(pos).cuda()
+    ddist = torch.empty(len(pos), dtype=torch.float32, device="cuda")
+    sdf = gleval.NewCUDASDF3(s)
+    sdf.Evaluate(dpos, ddist)
+    torch.cuda.synchronize()
+    want = oracle.Tree.from_shader(s).eval3(pos)
+    assert np.array_equal(bits(ddist.cpu().numpy()), bits(want))
+
+
+def test_large_polygon_side_buffer_from_global(oracle, bld):
+    """A polygon too large to stage in shared memory is read from global memory; results are unchanged."""
+    rng = np.random.default_rng(9)
+    ang = np.sort(rng.uniform(0, 2 * np.pi, 6000))
+    r = 1 + 0.05 * rng.standard_normal(6000)
+    verts = np.stack([r * np.cos(ang), r * np.sin(ang)], 1).astype(np.float32)
+    s = bld.NewPolygon(verts)
+    pos = shapes.sample_points(s, dense=[48, 48])
+    check_field("bigpoly", s, oracle, pos)
+
+
+# ---------------------------------------------------------------------------------------------- dense lattice
+def test_grid_eval_matches_flatrenderer_lattice(oracle, bld):
+    """FlatRenderer.evalGrid (flatrenderer.go:103-182): same positions, same order, same bits; k-slabs concatenate."""
+    s = gsdf.scene(bld, "npt-flange")
+    sdf = gleval.NewCUDASDF3(s)
+    res = np.float32(s.Diagonal() / np.float32(90))
+    lat = glrender.lattice_from_bounds(*s.Bounds(), res)
+    olat = oracle.flat_lattice(*s.Bounds(), res)
+    assert list(lat.n) == list(olat.n) and list(lat.origin) == list(olat.origin) and lat.res == olat.res
+    want, ev = oracle.flat_eval_grid(oracle.Tree.from_shader(s), olat, nthreads=4)
+    nx, ny, nz = lat.n
+    got = np.empty((nz + 1, ny + 1, nx + 1), np.float32)
+    _lib.check(_lib.lib.gsdf_grid_eval(sdf._h, C.byref(lat), 0, nz + 1, C.c_void_p(got.ctypes.data)))
+    assert np.array_equal(bits(got), bits(want))
+    assert sdf.Evaluations() == ev
+    # split like evalGrid's goroutines: g*(nz+1)/G .. (g+1)*(nz+1)/G
+    G = 3
+    parts = []
+    for g in range(G):
+        k0, k1 = g * (nz + 1) // G, (g + 1) * (nz + 1) // G
+        part = np.empty((k1 - k0, ny + 1, nx + 1), np.float32)
+        _lib.check(_lib.lib.gsdf_grid_eval(sdf._h, C.byref(lat), k0, k1, C.c_void_p(part.ctypes.data)))
+        parts.append(part)
+    assert np.array_equal(bits(np.concatenate(parts)), bits(want))
+
+
+# ---------------------------------------------------------------------------------------------- mesher
+def oracle_mesh(oracle, s, res, prune):
+    t = oracle.Tree.from_shader(s)
+    lat = oracle.flat_lattice(*s.Bounds(), res)
+    grid, ev = oracle.flat_eval_grid(t, lat, nthreads=os.cpu_count() or 1)
+    mask = oracle.octree_prune_mask(t, lat)[0] if prune else None
+    tris, cases = oracle.flat_march(lat, grid, want_cases=True, blockmask=mask)
+    return lat, grid, mask, tris, cases
+
+
+def test_sphere_41072_on_gpu(oracle, bld):
+    """TestSphereMarchingTriangles (glrender_test.go:83-102) through the GPU Octree renderer + STL round trip."""
+    sdf = gleval.NewCUDASDF3(bld.NewSphere(1.0))
+    r = glrender.NewOctreeRenderer(sdf, np.float32(1.0 / 33), (1 << 12) + 1)
+    tris = glrender.RenderAll(r)
+    assert len(tris) == 41072
+    buf = io.BytesIO()
+    n = glrender.WriteBinarySTL(buf, tris)
+    assert n == buf.getbuffer().nbytes == 84 + 50 * 41072
+    buf.seek(0)
+    back = glrender.ReadBinarySTL(buf)
+    assert np.array_equal(bits(back), bits(tris))        # glrender_test.go:149-153
+    assert r.TotalPruned() > 0 and r.Evaluations() > 0
+    f = glrender.NewFlatRenderer(sdf, np.float32(1.0 / 33), 4096, 1)
+    assert np.array_equal(bits(glrender.RenderAll(f)), bits(tris))
+
+
+@pytest.mark.parametrize("prune", [False, True])
+@pytest.mark.parametrize("scene,resdiv", [("sphere", 70), ("npt-flange", 150), ("bolt", 160), ("knurled-cylinder", 170)])
+def test_mesh_bit_identical_to_oracle(oracle, bld, scene, resdiv, prune):
+    s = bld.NewSphere(1.0) if scene == "sphere" else gsdf.scene(bld, scene)
+    res = np.float32(s.Diagonal() / np.float32(resdiv))
+    lat, grid, mask, wt, wc = oracle_mesh(oracle, s, res, prune)
+    sdf = gleval.NewCUDASDF3(s)
+    R = (glrender.Octree if prune else glrender.FlatRenderer)(sdf, res, keep_cases=True, keep_grid=True)
+    assert list(R.lat.n) == list(lat.n)
+    cases = R.Cases()
+    assert int((cases != wc).sum()) == 0                       # cube-case indices bit-identical
+    tris = R.AllTriangles()
+    assert len(tris) == len(wt) == R.NumTriangles()
+    assert np.array_equal(bits(tris), bits(wt))                # same triangles, same order, same bits
+    assert R.STLBytes() == oracle.stl_write(wt)
+    if not prune:
+        assert np.array_equal(bits(R.Grid()), bits(grid))
+        assert R.Evaluations() == grid.size and R.TotalPruned() == 0
+    else:
+        kept = int(mask.sum())
+        assert R.TotalPruned() == (mask.size - kept) * 64
+        g = R.Grid()                                           # evaluated corners agree; pruned ones hold the fill value
+        ev = bits(g) != np.uint32(0x7f7f7f7f)
+        assert np.array_equal(bits(g)[ev], bits(grid)[ev]) and ev.sum() < grid.size
+    R.Rerun()                                                  # Reset/re-render reuses buffers and reproduces the result
+    assert np.array_equal(bits(R.AllTriangles()), bits(wt))
+
+
+def test_flange_resdiv400_readme_counts(bld):
+    """README.md:116,130: 423,852 triangles from both renderers; FlatRenderer evaluates 6,711,685 lattice corners."""
+    s = gsdf.scene(bld, "npt-flange")
+    sdf = gleval.NewCUDASDF3(s)
+    res = np.float32(s.Diagonal() / np.float32(400))
+    f = glrender.NewFlatRenderer(sdf, res)
+    assert list(f.lat.n) == [280, 280, 84]
+    assert f.NumTriangles() == 423852 and f.Evaluations() == 6711685
+    o = glrender.NewOctreeRenderer(sdf, res, 32768)
+    assert o.NumTriangles() == 423852 and o.Evaluations() < f.Evaluations()
+    g = np.load(os.path.join(GOLD, "meshes.npz"))
+    assert np.array_equal(bits(f.AllTriangles()), bits(o.AllTriangles()))
+
+
+def test_golden_mesh_fixtures(bld):
+    g = np.load(os.path.join(GOLD, "meshes.npz"))
+    for name in ["sphere", "npt-flange", "bolt", "knurled-cylinder"]:
+        s = bld.NewSphere(1.0) if name == "sphere" else gsdf.scene(bld, name)
+        sdf = gleval.NewCUDASDF3(s)
+        R = glrender.FlatRenderer(sdf, np.float32(g[name + ".res"]), keep_cases=True)
+        assert list(R.lat.n) == list(g[name + ".n"])
+        tris = R.AllTriangles()
+        assert len(tris) == int(g[name + ".ntri"])
+        assert hashlib.sha256(tris.tobytes()).digest() == g[name + ".tri_sha"].tobytes()
+        assert hashlib.sha256(R.Cases().tobytes()).digest() == g[name + ".case_sha"].tobytes()
+        assert hashlib.sha256(R.STLBytes()).digest() == g[name + ".stl_sha"].tobytes()
+        P = glrender.Octree(sdf, np.float32(g[name + ".res"]))
+        assert P.NumTriangles() == int(g[name + ".ntri_pruned"])
+
+
+def test_read_triangles_streaming_contract(bld):
+    """Renderer.ReadTriangles: any len(dst) >= 5 works and resumes; < 5 is io.ErrShortBuffer; then io.EOF."""
+    sdf = gleval.NewCUDASDF3(bld.NewSphere(1.0))
+    r = glrender.NewOctreeRenderer(sdf, np.float32(0.11), 64)
+    allt = r.AllTriangles()
+    r.Rerun()
+    with pytest.raises(glrender.ErrShortBuffer):
+        r.ReadTriangles(np.empty((4, 3, 3), np.float32))
+    got = []
+    for size in [5, 7, 64, 5, 1000, 33] * 1000:
+        buf = np.empty((size, 3, 3), np.float32)
+        try:
+            n = r.ReadTriangles(buf)
+        except glrender.EOF:
+            break
+        assert 0 < n <= size
+        got.append(buf[:n].copy())
+    assert np.array_equal(bits(np.concatenate(got)), bits(allt))
+    with pytest.raises(glrender.EOF):
+        r.ReadTriangles(np.empty((5, 3, 3), np.float32))
+
+
+def test_renderer_errors(bld):
+    sdf = gleval.NewCUDASDF3(bld.NewSphere(1.0))
+    with pytest.raises(gsdf_b200.GsdfError):
+        glrender.NewOctreeRenderer(sdf, 0.1, 63)        # octreerenderer.go:46
+    with pytest.raises(gsdf_b200.GsdfError):
+        glrender.NewOctreeRenderer(sdf, -1.0, 64)       # :73
+    with pytest.raises(gsdf_b200.GsdfError):
+        glrender.NewFlatRenderer(sdf, 0.1, 4)           # flatrenderer.go:41
+    with pytest.raises(gsdf_b200.GsdfError) as e:
+        glrender.WriteBinarySTL(io.BytesIO(), np.zeros((0, 3, 3), np.float32))  # stl.go:16
+    assert e.value.code == _lib.EEMPTY
+    # a renderer whose surface produces no triangles still terminates with EOF
+    far = gleval.NewCUDASDF3(bld.Offset(bld.NewSphere(1.0), 10.0))
+    r = glrender.NewFlatRenderer(far, np.float32(0.5))
+    assert r.NumTriangles() == 0 and len(glrender.RenderAll(r)) == 0
+
+
+def test_octree_awkward_resolutions_gpu(oracle, bld):
+    """TestOctree (glrender_test.go:104-124)."""
+    s = bld.NewSphere(1.0)
+    sdf = gleval.NewCUDASDF3(s)
+    r = glrender.NewOctreeRenderer(sdf, np.float32(1 / 32), 1 << 12)
+    for res in [1 / 4, 1 / 8, 1 / 37, 1 / 4.000001, 1 / 13, 1 / 3.5]:
+        r.Reset(sdf, np.float32(res))
+        _, _, _, wt, _ = oracle_mesh(oracle, s, np.float32(res), True)
+        tris = glrender.RenderAll(r)
+        assert len(tris) > 0 and np.array_equal(bits(tris), bits(wt))
+
+
+def test_z_slabs_concatenate_to_the_whole(bld):
+    """Multi-GPU partition: cells split by Z-slab, one shared corner plane, per-slab triangle buffers
+    concatenated in slab order reproduce the single-device output bit for bit, for aligned and unaligned cuts."""
+    s = gsdf.scene(bld, "npt-flange")
+    sdf = gleval.NewCUDASDF3(s)
+    res = np.float32(s.Diagonal() / np.float32(200))
+    whole = glrender.Octree(sdf, res, keep_cases=True)
+    nz = whole.lat.n[2]
+    wt, wc = whole.AllTriangles(), whole.Cases()
+    for cuts in ([0, 8, 20, nz], [0, 5, 6, 23, nz], [0, 1, nz]):
+        parts, cparts, ev = [], [], 0
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            r = glrender.Octree(sdf, res, cz_range=(a, b), keep_cases=True)
+            parts.append(r.AllTriangles())
+            cparts.append(r.Cases())
+            ev += r.Evaluations()
+        assert np.array_equal(bits(np.concatenate(parts)), bits(wt)), cuts
+        assert np.array_equal(np.concatenate(cparts), wc), cuts
+
+
+def test_image_eval_matches_oracle(oracle, bld):
+    """ImageRendererSDF2 evaluation (image.go:76-105) on a polygon-heavy 2D tree (config 5's evaluator path)."""
+    T = gsdf.threads
+    glyphs = [bld.Translate2D(bld.NewPolygon(shapes.nagon(n, 0.4)), 1.1 * i, 0) for i, n in enumerate([3, 5, 8, 13, 21])]
+    hole = bld.Translate2D(bld.NewCircle(0.15), 2.2, 0)
+    s = bld.Difference2D(bld.Union2D(*glyphs), hole)
+    sdf = gleval.NewCUDASDF2(s)
+    for w, h in [(640, 123), (257, 64), (1024, 32)]:
+        got = glrender.ImageEvaluateSDF2(sdf, w, h)
+        want = oracle.Tree.from_shader(s).image_eval2(*s.Bounds(), w, h)
+        assert np.array_equal(bits(got), bits(want)), (w, h)
+
+
+# ---------------------------------------------------------------------------------------------- full-size properties
+def test_flange_full_size_properties(bld):
+    """BASELINE config 1 at full size, size-independent properties: prune is lossless, every vertex lies on a cell
+    edge of the lattice, STL pack round-trips, re-running is idempotent."""
+    s = gsdf.scene(bld, "npt-flange")
+    sdf = gleval.NewCUDASDF3(s)
+    res = np.float32(s.Diagonal() / np.float32(400))
+    o = glrender.Octree(sdf, res)
+    tris = o.AllTriangles()
+    assert len(tris) == 423852
+    lat = o.lat
+    org = np.array(list(lat.origin), np.float64)
+    rel = (tris.reshape(-1, 3).astype(np.float64) - org) / float(lat.res)
+    frac = np.abs(rel - np.round(rel))
+    on_lattice = (frac < 1e-3).sum(axis=1)
+    assert (on_lattice >= 2).all()        # an edge vertex has at least two lattice-aligned coordinates
+    assert rel.min() >= -1e-3 and (rel.max(axis=0) <= np.array(list(lat.n)) + 1e-3).all()
+    stl = o.STLBytes()
+    back = glrender.ReadBinarySTL(io.BytesIO(stl))
+    assert np.array_equal(bits(back), bits(tris))
+    h1 = hashlib.sha256(tris.tobytes()).digest()
+    o.Rerun()
+    assert hashlib.sha256(o.AllTriangles().tobytes()).digest() == h1
+
+
+def test_knurled_large_prune_equals_flat(bld):
+    """A larger lattice than the oracle can finish quickly (knurled @ resdiv 600, 32 M corners): the pruned renderer
+    and the dense renderer agree bit for bit, and pruning skips most evaluations."""
+    s = gsdf.scene(bld, "knurled-cylinder")
+    sdf = gleval.NewCUDASDF3(s)
+    res = np.float32(s.Diagonal() / np.float32(600))
+    f = glrender.FlatRenderer(sdf, res)
+    o = glrender.Octree(sdf, res)
+    assert f.NumTriangles() == o.NumTriangles() > 100000
+    assert np.array_equal(bits(f.AllTriangles()), bits(o.AllTriangles()))
+    assert o.Evaluations() < 0.5 * f.Evaluations()

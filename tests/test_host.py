@@ -1,0 +1,187 @@
+"""Host layer (no GPU needed): Builder validation and Bounds() mirror the reference's rules, the flattener emits a
+well-formed program, and the C ABI library exports every symbol its headers declare."""
+import ctypes as C
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+import gsdf_b200
+from gsdf_b200 import gsdf, _lib
+import shapes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    declared = set()
+    for h in ("gsdf_b200.h", "gsdf_host.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        declared |= set(re.findall(r"\b(gsdfh?_[a-z0-9_]+)\s*\(", src))
+    assert len(declared) >= 45
+    lib = C.CDLL(_lib.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    bound = set(_lib.lib._gsdf_signatures)
+    assert declared == bound, (declared ^ bound)
+
+
+def test_no_cpu_fallback_without_a_device(bld):
+    """Without a CUDA device compute entry points fail with GSDF_ECUDA; nothing silently runs on the CPU."""
+    if gsdf_b200.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from gsdf_b200 import gleval
+    with pytest.raises(gsdf_b200.GsdfError) as e:
+        gleval.NewCUDASDF3(bld.NewSphere(1))
+    assert e.value.code == _lib.ECUDA
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_shape_errors_match_reference_rules():
+    b = gsdf.Builder()
+    for bad in (lambda: b.NewSphere(0), lambda: b.NewSphere(-1),                       # primitives.go:29
+                lambda: b.NewBox(1, 1, 1, 0.6), lambda: b.NewBox(0, 1, 1, 0),          # :66-71
+                lambda: b.NewCylinder(1, 1, 0.5), lambda: b.NewCylinder(1, 0, 0),      # :108-115
+                lambda: b.NewTorus(1, 0.6), lambda: b.NewBoxFrame(1, 1, 1, 1.5),       # :217, :260
+                lambda: b.NewHexagonalPrism(0, 1),                                     # :158
+                lambda: b.Symmetry(b.NewSphere(1), False, False, False),               # operations.go:286
+                lambda: b.CircularArray(b.NewSphere(1), 5, 4),                         # :771
+                lambda: b.CircularArray(b.NewSphere(1), 1, 1),                         # :768
+                lambda: b.Array(b.NewSphere(1), 1, 1, 1, 0, 1, 1),                     # :489
+                lambda: b.Twist(b.NewSphere(1), 0),                                    # :839
+                lambda: b.Rotate(b.NewSphere(1), 1, (0, 0, 0)),                        # :395
+                lambda: b.NewPolygon([[0, 0], [1, 1]]),                                # primitives2d.go:477
+                lambda: b.NewPolygon([[0, 0], [1, 1], [1, 1], [0, 1]]),                # :483
+                lambda: b.NewCircle(0), lambda: b.NewRectangle(1, -1),
+                lambda: b.Annulus(b.NewCircle(1), 0),                                  # operations2d.go:608
+                lambda: b.Extrude(b.NewCircle(1), -1),                                 # :108
+                lambda: b.Union(b.NewSphere(1)),                                       # operations.go:36
+                lambda: b.Difference(b.NewSphere(1), b.NewCircle(1)),                  # 2D passed as 3D
+                ):
+        with pytest.raises(gsdf.ShapeError):
+            bad()
+    # FlagNoDimensionPanic behaviour: errors accumulate (gsdf.go:100-106)
+    b2 = gsdf.Builder(panic_on_error=False)
+    b2.NewSphere(-1)
+    b2.NewCylinder(1, 1, 2)
+    assert "sphere" in b2.Err() and "cylinder" in b2.Err()
+    b2.ClearErrors()
+    assert b2.Err() == ""
+
+
+def test_degenerate_line_becomes_circle(bld):
+    """primitives2d.go:23-28"""
+    s = bld.NewLine2D(1, 1, 1, 1, 0.5)
+    mn, mx = s.Bounds()
+    assert np.allclose(mn, [-0.25, -0.25]) and np.allclose(mx, [0.25, 0.25])
+
+
+def test_bounds_mirror_reference(bld):
+    s = bld.NewSphere(2)
+    assert np.array_equal(np.concatenate(s.Bounds()), [-2, -2, -2, 2, 2, 2])
+    c = bld.NewCylinder(1, 3, 0.1)
+    assert np.array_equal(np.concatenate(c.Bounds()), [-1, -1, -1.5, 1, 1, 1.5])
+    h = bld.NewHexagonalPrism(1, 2)  # primitives.go:169-176: z extent is +-h (not h/2)
+    assert np.allclose(np.concatenate(h.Bounds()), [-1 / 0.8660254, -1, -2, 1 / 0.8660254, 1, 2])
+    t = bld.Translate(s, 1, 2, 3)
+    assert np.array_equal(np.concatenate(t.Bounds()), [-1, 0, 1, 3, 4, 5])
+    d = bld.Difference(s, t)
+    assert np.array_equal(np.concatenate(d.Bounds()), np.concatenate(s.Bounds()))          # operations.go:128
+    i = bld.Intersection(s, t)
+    assert np.array_equal(np.concatenate(i.Bounds()), [-1, 0, 1, 2, 2, 2])                  # :171
+    sc = bld.Scale(t, 2)
+    assert np.array_equal(np.concatenate(sc.Bounds()), [-2, 0, 2, 6, 8, 10])                # :257 (about the origin)
+    sy = bld.Symmetry(t, True, False, False)
+    assert np.array_equal(np.concatenate(sy.Bounds()), [-3, 0, 1, 3, 4, 5])                 # :297
+    of = bld.Offset(s, -0.5)
+    assert np.array_equal(np.concatenate(of.Bounds()), [-2.5, -2.5, -2.5, 2.5, 2.5, 2.5])   # :455
+    ar = bld.Array(s, 5, 5, 5, 2, 3, 1)
+    assert np.array_equal(np.concatenate(ar.Bounds()), [-2, -2, -2, 12, 17, 7])             # :504
+    el = bld.Elongate(s, 2, 0, 4)
+    assert np.array_equal(np.concatenate(el.Bounds()), [-3, -2, -4, 3, 2, 4])               # :688
+    ex = bld.Extrude(bld.NewRectangle(2, 4), 6)
+    assert np.array_equal(np.concatenate(ex.Bounds()), [-1, -2, -3, 1, 2, 3])               # operations2d.go:119
+    rv = bld.Revolve(bld.Translate2D(bld.NewRectangle(2, 4), 3, 0), 1)
+    assert np.array_equal(np.concatenate(rv.Bounds()), [-3, -2, -3, 3, 2, 3])               # :168
+    tw = bld.Twist(bld.NewBox(2, 2, 4, 0), 0.3)
+    r = np.float32(np.hypot(1, 1))
+    assert np.allclose(np.concatenate(tw.Bounds()), [-r, -r, -2, r, r, 2])                  # operations.go:850
+    u = bld.Union(s, t, bld.Translate(s, -5, 0, 0))
+    assert np.array_equal(np.concatenate(u.Bounds()), [-7, -2, -2, 3, 4, 5])
+    o2 = bld.Offset2D(bld.NewRectangle(2, 2), 0.5)                                          # operations2d.go:421-429: f>0 keeps bb
+    assert np.array_equal(np.concatenate(o2.Bounds()), [-1, -1, 1, 1])
+    o3 = bld.Offset2D(bld.NewRectangle(2, 2), -0.5)
+    assert np.array_equal(np.concatenate(o3.Bounds()), [-1.5, -1.5, 1.5, 1.5])
+
+
+def test_union_absorbs_nested_unions(bld):
+    """operations.go:44-48"""
+    a, b, c = bld.NewSphere(1), bld.NewSphere(2), bld.NewSphere(3)
+    u = bld.Union(bld.Union(a, b), c)
+    nb, ch, aux = bld.tree_table()
+    node = _lib.TreeNode.from_buffer_copy(nb[u.id * 96:(u.id + 1) * 96])
+    assert node.nchild == 3 and list(ch[node.child_off:node.child_off + 3]) == [a.id, b.id, c.id]
+
+
+def test_scene_trees(bld):
+    fl = gsdf.scene(bld, "npt-flange")
+    f = bld.flatten(fl)
+    assert f["dim"] == 3 and f["ninstr"] >= 12 and f["pstack"] >= 1 and f["dstack"] >= 2
+    assert abs(fl.Diagonal() - 86.71794) < 1e-3
+    kn = gsdf.scene(bld, "knurled-cylinder")
+    assert np.array_equal(np.concatenate(kn.Bounds()), [-10, -10, -25, 10, 10, 25])
+    assert abs(kn.Diagonal() / np.float32(1600) - 0.035903517) < 1e-8
+    bo = gsdf.scene(bld, "bolt")
+    assert bld.flatten(bo)["ninstr"] > 15
+    # NPT 1/2 internal ISO profile: 7 base vertices, apex smoothed with 5 facets -> 12 vertices (iso.go:59-70)
+    prof = gsdf.threads.Thread(bld, gsdf.threads.NPT(0.5))
+    nb, ch, aux = bld.tree_table()
+    node = _lib.TreeNode.from_buffer_copy(nb[prof.id * 96:(prof.id + 1) * 96])
+    assert node.aux_cnt == 24
+    ext = gsdf.threads.Thread(bld, gsdf.threads.ISO(3, 0.5, True))                          # 8 base, 2 smoothed -> 18
+    nb, ch, aux = bld.tree_table()
+    node = _lib.TreeNode.from_buffer_copy(nb[ext.id * 96:(ext.id + 1) * 96])
+    assert node.aux_cnt == 36
+
+
+def test_flattened_programs_are_well_formed(bld):
+    """Every corpus shape flattens; the stream is a chain of length-prefixed instructions ending in END."""
+    for name, s in shapes.all3d(bld) + shapes.all2d(bld):
+        f = bld.flatten(s)
+        blob = f["blob"]
+        magic, ver, nchunks, dim, dstack, pstack, ninstr, _ = struct.unpack_from("<8I", blob, 0)
+        assert magic == 0x46445347 and ver == 1 and dim == (2 if s.is2d else 3), name
+        assert len(blob) == 32 + 16 * nchunks and f["aux"].size % 4 == 0, name
+        words = np.frombuffer(blob, np.uint32, offset=32).reshape(-1, 4)
+        pc = n = depth_p = 0
+        last = None
+        while pc < nchunks:
+            op, ln = int(words[pc, 0]) & 0xff, (int(words[pc, 0]) >> 8) & 0xff
+            assert ln >= 1, name
+            last = op
+            pc += ln
+            n += 1
+        assert pc == nchunks and last == 0 and n == ninstr, name
+        assert 1 <= dstack <= 16 and pstack <= 8, name
+
+
+def test_position_liveness(bld):
+    """A transform whose position nobody reads again must not save it: scale(translate(sphere)) needs no P slots,
+    union(translate(a), b) needs one."""
+    s = bld.NewSphere(1)
+    assert bld.flatten(bld.Scale(bld.Translate(s, 1, 0, 0), 2))["pstack"] == 0
+    assert bld.flatten(bld.Union(bld.Translate(s, 1, 0, 0), s))["pstack"] == 1
+    assert bld.flatten(bld.Union(s, bld.Translate(s, 1, 0, 0)))["pstack"] == 0
+    assert bld.flatten(bld.CircularArray(s, 3, 5))["pstack"] == 1   # CIRC_ENTER parks p0 on the stack
+
+
+def test_unsupported_nodes_fail_loudly(bld):
+    import ctypes
+    from gsdf_b200._lib import lib
+    # ellipse2D is declared in the tree format but not implemented by the backend: flatten must refuse it
+    f = (ctypes.c_float * 2)(1.0, 2.0)
+    nid = lib.gsdfh_node(bld._h, 72, f, 2, None, 0, None, 0, None, 0)
+    assert nid < 0

@@ -1,0 +1,179 @@
+"""The CPU oracle against every known answer the reference holds for this path:
+   - glrender/glrender_test.go:83-99   sphere r=1, res=1/33 -> 41072 triangles
+   - README.md:116,130                 npt-flange resdiv 400 -> 6,711,685(+1 probe) evaluations, 423,852 triangles
+   - forge/threads/threads_test.go     ISO thread profile inside/outside signs
+   - gsdf_test.go:772-838, 887-910     no negative distance outside Bounds(); finite, 1-Lipschitz-ish fields
+   - glrender/glrender_test.go:126-155 STL write -> read round trip is bit equal
+   - closed form                       sphere distances
+"""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from gsdf_b200 import gsdf
+import shapes
+
+
+def test_sphere_closed_form(oracle, bld):
+    s = bld.NewSphere(1.5)
+    t = oracle.Tree.from_shader(s)
+    rng = np.random.default_rng(0)
+    pos = rng.uniform(-3, 3, (5000, 3)).astype(np.float32)
+    got = t.eval3(pos)
+    want = np.linalg.norm(pos.astype(np.float64), axis=1) - 1.5
+    assert np.abs(got - want).max() < 4e-7 * 5
+
+
+def test_sphere_41072_triangles(oracle, bld):
+    """TestSphereMarchingTriangles: both renderer semantics give the reference's count."""
+    s = bld.NewSphere(1.0)
+    t = oracle.Tree.from_shader(s)
+    res = np.float32(1.0 / 33)
+    lat = oracle.flat_lattice(*s.Bounds(), res)
+    assert oracle.octree_levels(*s.Bounds(), res) == 8
+    grid, ev = oracle.flat_eval_grid(t, lat, nthreads=2)
+    assert ev == (lat.n[0] + 1) * (lat.n[1] + 1) * (lat.n[2] + 1)
+    tris, _ = oracle.flat_march(lat, grid)
+    assert len(tris) == 41072
+    mask, kept = oracle.octree_prune_mask(t, lat)
+    tris2, _ = oracle.flat_march(lat, grid, blockmask=mask)
+    assert len(tris2) == 41072 and 0 < kept < mask.size
+    assert np.array_equal(tris.view(np.uint32), tris2.view(np.uint32))
+
+
+def test_octree_awkward_resolutions(oracle, bld):
+    """TestOctree (glrender_test.go:104-124): Reset at awkward resolutions still meshes."""
+    s = bld.NewSphere(1.0)
+    t = oracle.Tree.from_shader(s)
+    for res in [1 / 4, 1 / 8, 1 / 37, 1 / 4.000001, 1 / 13, 1 / 3.5]:
+        lat = oracle.flat_lattice(*s.Bounds(), np.float32(res))
+        grid, _ = oracle.flat_eval_grid(t, lat)
+        mask, _ = oracle.octree_prune_mask(t, lat)
+        a, _ = oracle.flat_march(lat, grid)
+        b, _ = oracle.flat_march(lat, grid, blockmask=mask)
+        assert len(a) > 0 and len(a) == len(b)
+
+
+def test_flange_readme_counts(oracle, bld):
+    """README.md:130: 'evaluated SDF 6711686 times and rendered 423852 triangles with resolution 0.21679485'."""
+    s = gsdf.scene(bld, "npt-flange")
+    mn, mx = s.Bounds()
+    assert np.allclose(mn, [-30, -30, -12.5], atol=1e-5) and np.allclose(mx, [30, 30, 5.3886], atol=1e-4)
+    res = np.float32(s.Diagonal() / np.float32(400))
+    assert "%.8f" % res == "0.21679485"
+    lat = oracle.flat_lattice(mn, mx, res)
+    assert list(lat.n) == [280, 280, 84]
+    t = oracle.Tree.from_shader(s)
+    grid, ev = oracle.flat_eval_grid(t, lat, nthreads=os.cpu_count() or 1)
+    assert ev + 1 == 6711686  # +1: NewCPUSDF3's probe evaluation (gleval/cpu.go:27)
+    tris, _ = oracle.flat_march(lat, grid)
+    assert len(tris) == 423852
+    assert oracle.octree_levels(mn, mx, res) == 10
+    mask, kept = oracle.octree_prune_mask(t, lat)
+    tris2, _ = oracle.flat_march(lat, grid, blockmask=mask)
+    assert len(tris2) == 423852  # README.md:116: the octree renderer emits the same count
+
+
+def test_iso_thread_signs(oracle, bld):
+    """forge/threads/threads_test.go:14-44."""
+    P, D = 0.1, 1.0
+    prof = gsdf.threads.Thread(bld, gsdf.threads.ISO(D, P, True))
+    t = oracle.Tree.from_shader(prof)
+    d = t.eval2(np.array([[P / 2, D / 2], [P / 2, D / 3]], dtype=np.float32))
+    assert d[0] >= 0 and np.isfinite(d[0])
+    assert d[1] <= 0 and np.isfinite(d[1])
+
+
+def _outside_boxes(mn, mx):
+    """test_bounds (gsdf_test.go:772-838): the 26 (8) neighbour boxes offset by size+1e-2."""
+    size = mx - mn
+    dim = len(mn)
+    offs = np.array(np.meshgrid(*[[-1, 0, 1]] * dim, indexing="ij")).reshape(dim, -1).T
+    for o in offs:
+        if not o.any():
+            continue
+        shift = o * (size + 1e-2)
+        yield mn + shift, mx + shift
+
+
+@pytest.mark.parametrize("which", ["3d", "2d"])
+def test_no_negative_distance_outside_bounds(oracle, bld, which):
+    items = (shapes.primitives3d(bld) + shapes.binops3d(bld) + shapes.threads3d(bld)) if which == "3d" else \
+            (shapes.primitives2d(bld) + shapes.binops2d(bld) + shapes.threads2d(bld))
+    for name, s in items:
+        t = oracle.Tree.from_shader(s)
+        mn, mx = s.Bounds()
+        for lo, hi in _outside_boxes(mn, mx):
+            pts = shapes.append_grid(lo, hi, [4] * len(mn))
+            d = t.eval3(pts) if which == "3d" else t.eval2(pts)
+            assert np.isfinite(d).all(), name
+            assert (d >= -1e-4).all(), (name, float(d.min()))
+
+
+def test_fields_finite_everywhere(oracle, bld):
+    for name, s in shapes.all3d(bld):
+        d = oracle.Tree.from_shader(s).eval3(shapes.sample_points(s))
+        assert np.isfinite(d).all(), name
+    for name, s in shapes.all2d(bld):
+        d = oracle.Tree.from_shader(s).eval2(shapes.sample_points(s))
+        assert np.isfinite(d).all(), name
+
+
+def test_exact_sdfs_are_lipschitz(oracle, bld):
+    """fieldIsValid2 (gsdf_test.go:887-910): |d(a)-d(b)| <= |a-b| for exact SDFs."""
+    for name, s in shapes.primitives3d(bld):
+        t = oracle.Tree.from_shader(s)
+        p = shapes.sample_points(s, dense=[12, 12, 12])
+        d = t.eval3(p)
+        dd = np.abs(np.diff(d))
+        dp = np.linalg.norm(np.diff(p, axis=0), axis=1)
+        assert (dd <= dp * (1 + 1e-4) + 1e-5).all(), name
+
+
+def test_stl_layout_and_round_trip(oracle, bld):
+    s = bld.NewSphere(1.0)
+    t = oracle.Tree.from_shader(s)
+    lat = oracle.flat_lattice(*s.Bounds(), np.float32(0.25))
+    grid, _ = oracle.flat_eval_grid(t, lat)
+    tris, _ = oracle.flat_march(lat, grid)
+    data = oracle.stl_write(tris)
+    assert len(data) == 84 + 50 * len(tris)                       # stl.go:24-31,53
+    assert data[:80] == b"\0" * 80 and struct.unpack_from("<I", data, 80)[0] == len(tris)
+    assert data[84 + 48:84 + 50] == b"\0\0"                       # attribute byte count
+    n = np.frombuffer(data, np.uint8, 50 * len(tris), 84).reshape(-1, 50)[:, :12].copy().view(np.float32)
+    assert np.allclose(np.linalg.norm(n, axis=1), 1, atol=1e-5)   # unit normals
+    back = oracle.stl_read(data)
+    assert np.array_equal(back.view(np.uint32), tris.view(np.uint32))  # glrender_test.go:149-153: bit equal
+    with pytest.raises(ValueError):
+        oracle.stl_write(np.zeros((0, 3, 3), np.float32))         # stl.go:16
+
+
+def test_mc_reversed_winding_and_single_cube(oracle):
+    """marchcubes.go:64-68: triangles are emitted as (pt[t+2], pt[t+1], pt[t]); case 1 = corner 0 inside."""
+    import ctypes as C
+    p = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], np.float32)
+    v = np.array([-1, 1, 1, 1, 1, 1, 1, 1], np.float32)
+    out = np.zeros(45, np.float32)
+    idx = C.c_int()
+    f32p = C.POINTER(C.c_float)
+    n = oracle.lib().go_mc_cube(p.ctypes.data_as(f32p), v.ctypes.data_as(f32p), out.ctypes.data_as(f32p), C.byref(idx))
+    assert n == 1 and idx.value == 1
+    tri = out[:9].reshape(3, 3)
+    # table row {0, 8, 3} reversed -> edges 3 (3-0), 8 (0-4), 0 (0-1), all at t = 0.5
+    assert np.allclose(tri, [[0, .5, 0], [0, 0, .5], [.5, 0, 0]])
+
+
+def test_image_positions(oracle, bld):
+    """image.go:85-105: x_i = float32(i)*dx + (min.x+dx/2); y_j = max.y - float32(j)*dy (un-shifted max)."""
+    c = bld.NewCircle(1.0)
+    t = oracle.Tree.from_shader(c)
+    mn, mx = c.Bounds()
+    w, h = 8, 4
+    img = t.image_eval2(mn, mx, w, h)
+    dx, dy = np.float32(2.0 / w), np.float32(2.0 / h)
+    xs = np.arange(w, dtype=np.float32) * dx + (np.float32(-1) + dx / 2)
+    ys = np.float32(1) - np.arange(h, dtype=np.float32) * dy
+    want = np.hypot(xs[None, :].astype(np.float64), ys[:, None].astype(np.float64)) - 1
+    assert np.abs(img - want).max() < 1e-6
