@@ -44,6 +44,7 @@ def _load():
         "gsdf_device_count": (C.c_int, []),
         "gsdf_set_device": (C.c_int, [C.c_int]),
         "gsdf_program_create": (C.c_int, [vp, C.c_size_t, f32p, C.c_size_t, C.POINTER(vp)]),
+        "gsdf_program_update": (C.c_int, [vp, vp, C.c_size_t, f32p, C.c_size_t]),
         "gsdf_program_destroy": (None, [vp]),
         "gsdf_program_evaluations": (C.c_uint64, [vp]),
         "gsdf_eval3": (C.c_int, [vp, vp, vp, C.c_size_t]),

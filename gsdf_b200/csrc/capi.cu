@@ -75,28 +75,30 @@ struct gsdf_program {
     cudaStream_t stream = nullptr;
     float *d_pos = nullptr, *d_dist = nullptr;
     size_t pos_cap = 0, dist_cap = 0;
+    uint32_t *d_sched = nullptr;  // work-tile scheduler of k_eval (self-resetting)
+    size_t blob_cap = 0;          // bytes allocated at d_blob
 };
 
 namespace {
 
-// persistent launch: enough CTAs to fill the machine, never more than the work needs
+// persistent launch: at most one resident wave of CTAs; they pull 256-item tiles from the program's scheduler
 template <int P, class Gen>
-int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork, cudaStream_t st) {
-    if (nwork == 0) return 0;
+int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st) {
+    if (nwork_upper_bound == 0) return 0;
     auto kern = k_eval<P, Gen>;
     const uint32_t smem = smem_total_bytes<P>(p->pv, kThreads);
-    static thread_local const void *configured = nullptr;
-    static thread_local uint32_t configured_smem = 0;
-    if (configured != (const void *)kern || configured_smem < smem) {
+    static thread_local uint32_t cached_smem = 0xffffffffu;
+    static thread_local int cached_occ = 0;
+    if (cached_smem != smem) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<uint32_t>(smem, 48 * 1024)));
-        configured = (const void *)kern;
-        configured_smem = std::max<uint32_t>(smem, 48 * 1024);
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+        if (occ < 1) return fail(GSDF_EPROGRAM, "node program needs %u bytes of shared memory per CTA; does not fit", smem);
+        cached_occ = occ;
+        cached_smem = smem;
     }
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
-    if (occ < 1) return fail(GSDF_EPROGRAM, "node program needs %u bytes of shared memory per CTA; does not fit", smem);
-    uint64_t blocks = (nwork + kThreads - 1) / kThreads;
-    blocks = std::min<uint64_t>(blocks, (uint64_t)g_sms * occ);
+    uint64_t blocks = (nwork_upper_bound + kThreads - 1) / kThreads;
+    blocks = std::min<uint64_t>(blocks, (uint64_t)g_sms * cached_occ);
     kern<<<(unsigned)blocks, kThreads, smem, st>>>(p->pv, gen);
     CU(cudaGetLastError());
     return 0;
@@ -157,9 +159,8 @@ int gsdf_set_device(int device) {
     return ensure_device();
 }
 
-int gsdf_program_create(const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats, gsdf_program **out) {
-    if (!blob || !out || blob_bytes < sizeof(gsdf_program_header)) return fail(GSDF_EINVAL, "gsdf_program_create: bad arguments");
-    gsdf_program_header h;
+static int parse_blob(const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats, gsdf_program_header &h, const uint32_t *&chunks) {
+    if (!blob || blob_bytes < sizeof(gsdf_program_header)) return fail(GSDF_EINVAL, "program blob is NULL or too short");
     std::memcpy(&h, blob, sizeof h);
     if (h.magic != GSDF_PROGRAM_MAGIC || h.version != GSDF_PROGRAM_VERSION) return fail(GSDF_EPROGRAM, "bad program magic/version");
     if (h.nchunks == 0 || blob_bytes != sizeof h + (size_t)h.nchunks * 16) return fail(GSDF_EPROGRAM, "program size mismatch");
@@ -167,23 +168,30 @@ int gsdf_program_create(const void *blob, size_t blob_bytes, const float *aux, s
     if (aux_floats && !aux) return fail(GSDF_EINVAL, "aux is NULL");
     if (aux_floats & 3) return fail(GSDF_EPROGRAM, "aux length must be a multiple of 4 floats");
     if (h.dstack < 1 || h.dstack > 64 || h.pstack > 32) return fail(GSDF_EPROGRAM, "stack depth out of range (d=%u p=%u)", h.dstack, h.pstack);
-    const uint32_t *chunks = reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(blob) + sizeof h);
-    int rc = validate_program(h, chunks, aux_floats);
-    if (rc) return rc;
-    rc = ensure_device();
-    if (rc) return rc;
+    chunks = reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(blob) + sizeof h);
+    const size_t prog_bytes = (size_t)h.nchunks * 16;
+    const uint32_t stacks = kThreads * 4u * 4u * (h.dstack + 3u * h.pstack);
+    if (prog_bytes + stacks + 16 > 200 * 1024) return fail(GSDF_EPROGRAM, "program too large for shared memory");
+    return validate_program(h, chunks, aux_floats);
+}
 
-    gsdf_program *p = new gsdf_program();
-    p->device = g_device;
+// copies chunks + aux into p->d_blob (growing it if needed) and refreshes the kernel-side view
+static int upload_blob(gsdf_program *p, const gsdf_program_header &h, const uint32_t *chunks, const float *aux, size_t aux_floats) {
+    const size_t prog_bytes = (size_t)h.nchunks * 16, aux_bytes = aux_floats * 4;
+    if (prog_bytes + aux_bytes + 16 > p->blob_cap) {
+        if (p->d_blob) cudaFree(p->d_blob);
+        p->d_blob = nullptr;
+        p->blob_cap = 0;
+        const size_t want = std::max<size_t>(4096, 2 * (prog_bytes + aux_bytes + 16));
+        cudaError_t e = cudaMalloc((void **)&p->d_blob, want);
+        if (e != cudaSuccess) return fail(GSDF_ENOMEM, "cudaMalloc program: %s", cudaGetErrorString(e));
+        p->blob_cap = want;
+    }
+    CU(cudaMemcpyAsync(p->d_blob, chunks, prog_bytes, cudaMemcpyHostToDevice, p->stream));
+    if (aux_bytes) CU(cudaMemcpyAsync(p->d_blob + prog_bytes, aux, aux_bytes, cudaMemcpyHostToDevice, p->stream));
+    CU(cudaStreamSynchronize(p->stream));  // the caller's buffers may go away after we return
     p->dim = (int)h.dim;
     p->ninstr = h.ninstr;
-    const size_t prog_bytes = (size_t)h.nchunks * 16, aux_bytes = aux_floats * 4;
-    cudaError_t e = cudaMalloc((void **)&p->d_blob, prog_bytes + aux_bytes + 16);
-    if (e != cudaSuccess) { delete p; return fail(GSDF_ENOMEM, "cudaMalloc program: %s", cudaGetErrorString(e)); }
-    e = cudaMemcpy(p->d_blob, chunks, prog_bytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && aux_bytes) e = cudaMemcpy(p->d_blob + prog_bytes, aux, aux_bytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { cudaFree(p->d_blob); delete p; return fail(GSDF_ECUDA, "program upload: %s", cudaGetErrorString(e)); }
     p->pv.g_prog = reinterpret_cast<const uint4 *>(p->d_blob);
     p->pv.prog_bytes = (uint32_t)prog_bytes;
     p->pv.aux_bytes = (uint32_t)aux_bytes;
@@ -192,9 +200,40 @@ int gsdf_program_create(const void *blob, size_t blob_bytes, const float *aux, s
     // stage aux with the program when program + aux + stacks stay under ~100 KB (>= 2 CTAs/SM)
     const uint32_t stacks = kThreads * 4u * 4u * (h.dstack + 3u * h.pstack);
     p->pv.stage_aux = (prog_bytes + aux_bytes + stacks + 16 <= 100 * 1024) ? 1u : 0u;
-    if (prog_bytes + stacks + 16 > 200 * 1024) { gsdf_program_destroy(p); return fail(GSDF_EPROGRAM, "program too large for shared memory"); }
+    return 0;
+}
+
+int gsdf_program_create(const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats, gsdf_program **out) {
+    if (!out) return fail(GSDF_EINVAL, "gsdf_program_create: out is NULL");
+    gsdf_program_header h;
+    const uint32_t *chunks = nullptr;
+    int rc = parse_blob(blob, blob_bytes, aux, aux_floats, h, chunks);
+    if (rc) return rc;
+    rc = ensure_device();
+    if (rc) return rc;
+    gsdf_program *p = new gsdf_program();
+    p->device = g_device;
+    cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_sched, 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(p->d_sched, 0, 2 * sizeof(uint32_t));
+    if (e != cudaSuccess) { gsdf_program_destroy(p); return fail(GSDF_ECUDA, "program setup: %s", cudaGetErrorString(e)); }
+    p->pv.sched = p->d_sched;
+    rc = upload_blob(p, h, chunks, aux, aux_floats);
+    if (rc) { gsdf_program_destroy(p); return rc; }
     *out = p;
     return 0;
+}
+
+int gsdf_program_update(gsdf_program *p, const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats) {
+    if (!p) return fail(GSDF_EINVAL, "gsdf_program_update: NULL program");
+    gsdf_program_header h;
+    const uint32_t *chunks = nullptr;
+    int rc = parse_blob(blob, blob_bytes, aux, aux_floats, h, chunks);
+    if (rc) return rc;
+    if ((int)h.dim != p->dim) return fail(GSDF_EINVAL, "cannot change a %dD program into a %dD one", p->dim, (int)h.dim);
+    CU(cudaSetDevice(p->device));
+    CU(cudaStreamSynchronize(p->stream));  // nothing may still be reading the old program
+    return upload_blob(p, h, chunks, aux, aux_floats);
 }
 
 void gsdf_program_destroy(gsdf_program *p) {
@@ -202,6 +241,7 @@ void gsdf_program_destroy(gsdf_program *p) {
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamDestroy(p->stream);
     cudaFree(p->d_blob);
+    cudaFree(p->d_sched);
     cudaFree(p->d_pos);
     cudaFree(p->d_dist);
     delete p;
@@ -285,7 +325,7 @@ int gsdf_grid_eval_device(gsdf_program *p, const gsdf_lattice *lat, int k0, int 
     CU(cudaSetDevice(p->device));
     const int pitch = lat->n[0] + 1;
     const bool vec = (pitch % 4 == 0) && (((uintptr_t)d_dist & 15) == 0);
-    GenGrid g{make_lat(lat, k0, k1, pitch, vec), d_dist, nullptr, nullptr};
+    GenGrid<4> g{make_lat(lat, k0, k1, pitch, vec), d_dist, nullptr, nullptr};
     const uint64_t nwork = (uint64_t)g.L.nqx * (lat->n[1] + 1) * (k1 - k0);
     return launch_eval<4>(p, g, nwork, stream ? (cudaStream_t)stream : p->stream);
 }
@@ -337,8 +377,10 @@ struct gsdf_mesher {
     MeshDims D{};
     float *d_grid = nullptr; size_t grid_cap = 0;
     uint8_t *d_mask = nullptr; size_t mask_cap = 0;
+    uint32_t *d_mbits = nullptr; size_t mbits_cap = 0;
     uint32_t *d_list = nullptr; size_t list_cap = 0;
     uint32_t *d_seg = nullptr; size_t seg_cap = 0;
+    uint32_t *d_seglist = nullptr; size_t seglist_cap = 0;
     uint32_t *d_blocksum = nullptr; size_t blocksum_cap = 0;
     float *d_tris = nullptr; size_t tri_cap = 0;  // in floats
     uint8_t *d_cases = nullptr; size_t cases_cap = 0;
@@ -352,14 +394,6 @@ struct gsdf_mesher {
 };
 
 namespace {
-
-__global__ void k_count_mask(const uint8_t *__restrict__ mask, uint64_t n, uint32_t *__restrict__ out) {
-    uint32_t c = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) c += mask[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
-}
 
 unsigned grid_for(uint64_t items, int per_block, int waves = 8) {
     uint64_t b = (items + per_block - 1) / per_block;
@@ -376,15 +410,20 @@ int mesh_run(gsdf_mesher *m) {
     const int nk = D.cz1 - D.cz0 + 1;
     const uint64_t nquads = (uint64_t)D.nqx * (D.ny + 1) * nk;
     const uint64_t nblocks = (uint64_t)D.nbx * D.nby * D.nbz;
-    const uint64_t nseg = (uint64_t)D.nsx * D.ny * (D.cz1 - D.cz0);
-    const uint64_t ncells = (uint64_t)D.nx * D.ny * (D.cz1 - D.cz0);
+    const uint64_t nrows = (uint64_t)D.ny * (D.cz1 - D.cz0);
+    const uint64_t ncells = nrows * D.nx;
+    if (nquads >= 0xffffffffull) return fail(GSDF_EINVAL, "slab too large: %llu lattice quads (limit 2^32); use more Z-slabs", (unsigned long long)nquads);
     int rc;
     if ((rc = grow(m->d_grid, m->grid_cap, (size_t)D.pitch * (D.ny + 1) * nk))) return rc;
+    const uint64_t nseg = nrows * (uint64_t)D.nsx;
+    if (nseg >= 0xffffffffull) return fail(GSDF_EINVAL, "slab too large: %llu cell segments (limit 2^32); use more Z-slabs", (unsigned long long)nseg);
     if ((rc = grow(m->d_seg, m->seg_cap, (size_t)nseg))) return rc;
+    if ((rc = grow(m->d_seglist, m->seglist_cap, (size_t)nseg))) return rc;
     const uint64_t nscanblocks = (nseg + kThreads * kScanItems - 1) / (kThreads * kScanItems);
     if ((rc = grow(m->d_blocksum, m->blocksum_cap, (size_t)nscanblocks))) return rc;
     if (prune) {
         if ((rc = grow(m->d_mask, m->mask_cap, (size_t)nblocks))) return rc;
+        if ((rc = grow(m->d_mbits, m->mbits_cap, (size_t)D.nwx * D.nby * D.nbz))) return rc;
         if ((rc = grow(m->d_list, m->list_cap, (size_t)nquads))) return rc;
     }
     if (m->flags & GSDF_MESH_KEEP_CASES) {
@@ -403,16 +442,17 @@ int mesh_run(gsdf_mesher *m) {
         gc.half = size * 0.5f;
         gc.maxDist = size * (float)(1.73205080757 / 2);  // octreerenderer.go:182 with glrender.go:9
         gc.mask = m->d_mask;
-        if ((rc = launch_eval<4>(p, gc, (uint64_t)((D.nbx + 3) / 4) * D.nby * D.nbz, st))) return rc;
-        k_compact_quads<<<grid_for(nquads, kThreads), kThreads, 0, st>>>(D, m->d_mask, m->d_list, m->d_ctr + 0);
+        if ((rc = launch_eval<1>(p, gc, nblocks, st))) return rc;
+        const uint64_t ncrows = (uint64_t)(D.ny + 1) * nk;
+        k_mask_bits<<<grid_for((uint64_t)D.nby * D.nbz, kThreads / 32), kThreads, 0, st>>>(D, m->d_mask, m->d_mbits, m->d_ctr + 4);
         CU(cudaGetLastError());
-        k_count_mask<<<grid_for(nblocks, kThreads, 2), kThreads, 0, st>>>(m->d_mask, nblocks, m->d_ctr + 4);
+        k_compact_quads<<<grid_for(ncrows, kThreads / 32), kThreads, 0, st>>>(D, m->d_mbits, m->d_list, m->d_ctr + 0);
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(m->ev[1], st));
     {
-        GenGrid g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
-        // with a device-side list length the launch is sized for the worst case; CTAs beyond the list exit at once
+        GenGrid<4> g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
+        // with a device-side list length the launch is sized for the worst case; surplus CTAs find no tile and exit
         if ((rc = launch_eval<4>(p, g, nquads, st))) return rc;
     }
     CU(cudaEventRecord(m->ev[2], st));
@@ -421,13 +461,18 @@ int mesh_run(gsdf_mesher *m) {
     A.ox = lat.origin[0]; A.oy = lat.origin[1]; A.oz = lat.origin[2]; A.res = lat.res;
     A.cubeDiag = (float)(2 * 1.73205080757) * lat.res;  // flatrenderer.go:202
     A.grid = m->d_grid;
-    A.mask = prune ? m->d_mask : nullptr;
+    A.mbits = prune ? m->d_mbits : nullptr;
+    CU(cudaGetSymbolAddress((void **)&A.t_ntri, g_mc_ntri));
+    CU(cudaGetSymbolAddress((void **)&A.t_tris, g_mc_tris));
     A.segcount = m->d_seg;
     A.tris = m->d_tris;
     A.tri_capacity = m->tri_cap / 9;
     A.cases = (m->flags & GSDF_MESH_KEEP_CASES) ? m->d_cases : nullptr;
     A.overflow = m->d_ctr + 1;
-    k_mc_count<<<grid_for(nseg, kThreads / 32), kThreads, 0, st>>>(A);
+    A.seg_list = m->d_seglist;
+    A.seg_count = m->d_ctr + 5;
+    const unsigned mcgrid = grid_for(nrows * (uint64_t)((D.nsx + 3) / 4), kThreads / 32, 16);
+    k_mc_count<<<mcgrid, kThreads, 0, st>>>(A);
     CU(cudaGetLastError());
     k_scan_reduce<<<(unsigned)nscanblocks, kThreads, 0, st>>>(m->d_seg, nseg, m->d_blocksum);
     CU(cudaGetLastError());
@@ -440,10 +485,11 @@ int mesh_run(gsdf_mesher *m) {
     A.cases = nullptr;
     bool emitted = false;
     if (m->tri_cap > 0) {  // optimistic emit into the existing buffer (steady state: no mid-pipeline host sync)
-        k_mc_emit<<<grid_for(nseg, kThreads / 32), kThreads, 0, st>>>(A);
+        k_mc_emit<<<mcgrid, kThreads, 0, st>>>(A);
         CU(cudaGetLastError());
         emitted = true;
     }
+    CU(cudaEventRecord(m->ev[4], st));
     CU(cudaMemcpyAsync(m->h_ctr, m->d_ctr, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     uint64_t total;
@@ -453,11 +499,11 @@ int mesh_run(gsdf_mesher *m) {
         A.tris = m->d_tris;
         A.tri_capacity = m->tri_cap / 9;
         CU(cudaMemsetAsync(m->d_ctr + 1, 0, sizeof(uint32_t), st));
-        k_mc_emit<<<grid_for(nseg, kThreads / 32), kThreads, 0, st>>>(A);
+        k_mc_emit<<<mcgrid, kThreads, 0, st>>>(A);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(m->ev[4], st));
+        CU(cudaStreamSynchronize(st));
     }
-    CU(cudaEventRecord(m->ev[4], st));
-    CU(cudaStreamSynchronize(st));
     m->ntri = total;
     m->read_pos = 0;
     if (prune) {
@@ -497,6 +543,7 @@ int gsdf_mesh_begin(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, 
     D.nqx = (D.nx + 1 + 3) / 4;
     D.pitch = D.nqx * 4;
     D.nsx = (D.nx + 31) / 32;
+    D.nwx = (D.nbx + 31) / 32;
     cudaError_t e = cudaMalloc((void **)&m->d_ctr, 8 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&m->h_ctr, 8 * sizeof(uint32_t));
     for (int i = 0; i < 5 && e == cudaSuccess; i++) e = cudaEventCreate(&m->ev[i]);
@@ -577,7 +624,7 @@ int gsdf_mesh_timings(const gsdf_mesher *m, float ms[5]) {
 void gsdf_mesh_destroy(gsdf_mesher *m) {
     if (!m) return;
     if (m->prog) cudaSetDevice(m->prog->device);
-    cudaFree(m->d_grid); cudaFree(m->d_mask); cudaFree(m->d_list); cudaFree(m->d_seg); cudaFree(m->d_blocksum);
+    cudaFree(m->d_grid); cudaFree(m->d_mask); cudaFree(m->d_mbits); cudaFree(m->d_list); cudaFree(m->d_seg); cudaFree(m->d_seglist); cudaFree(m->d_blocksum);
     cudaFree(m->d_tris); cudaFree(m->d_cases); cudaFree(m->d_stl); cudaFree(m->d_ctr);
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
     for (auto &e : m->ev) if (e) cudaEventDestroy(e);

@@ -1,13 +1,15 @@
 // kernels.cuh -- sm_100a kernels of the SDF evaluate + mesh path.
 //
-//   k_eval<P,Gen>      one persistent grid; each thread interprets the node program at P points produced by a
-//                      generator functor (AoS point lists, the dense lattice, a compacted quad list, block centres,
-//                      image rows) and hands the distances to the generator's sink.
-//   k_compact_quads    octree level-3 prune -> compacted list of 4-corner lattice quads that still need evaluating
-//   k_mc_count/emit    marching-cubes classification per 32-cell row segment with a warp inclusive scan; triangle
-//                      offsets come from an exclusive scan over segment counts so output order is the reference
-//                      FlatRenderer's (cell index x fastest, flatrenderer.go:208-212) and fully deterministic.
-//   k_scan_*           three-kernel exclusive scan over segment counts.
+//   k_eval<P,Gen>      persistent CTAs pull 256-item tiles from an atomic counter; each thread interprets the node
+//                      program at P points produced by a generator functor (AoS point lists, the dense lattice, a
+//                      compacted quad list, prune-cube centres, image rows) and hands the distances to its sink.
+//   k_compact_quads    octree level-3 prune mask -> compacted list of 4-corner lattice quads that still need evaluating
+//   k_mc_count/emit    marching cubes. Classification from 4 coalesced row loads + shuffles. Pass 1 (warp per cell row)
+//                      writes a triangle count per row and a compact list of non-empty 32-cell segments; an exclusive
+//                      scan turns row counts into offsets; pass 2 (warp per listed segment) places each cell's
+//                      triangles with a warp inclusive scan. Output order is the reference FlatRenderer's (cell index
+//                      x fastest, flatrenderer.go:208-212) and fully deterministic.
+//   k_scan_*           three-kernel exclusive scan over row counts.
 //   k_stl_pack         glrender/stl.go:33-61 record packing.
 //
 // The node program (+ side buffer when it fits) is staged into shared memory once per CTA by a 1-D bulk async copy
@@ -29,6 +31,7 @@ struct ProgView {
     uint32_t aux_bytes;      // bytes of aux that follow the chunks
     uint32_t stage_aux;      // 1: aux is staged to smem with the program; 0: read from global
     uint32_t dslots, pslots; // stack slots
+    uint32_t *sched;         // [0] next tile, [1] finished CTAs (self-resetting work counter)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -59,7 +62,7 @@ __device__ __forceinline__ void bulk_stage(void *s_dst, const void *g_src, uint3
         : "memory");
 }
 
-// Shared memory: [prog (+aux)] [mbarrier, padded to 16] [dstack] [pstack]
+// Shared memory: [prog (+aux)] [mbarrier + tile slot, 16 bytes] [dstack] [pstack]
 __host__ __device__ inline uint32_t smem_stage_bytes(const ProgView &pv) { return pv.prog_bytes + (pv.stage_aux ? pv.aux_bytes : 0u); }
 template <int P>
 __host__ __device__ inline uint32_t smem_total_bytes(const ProgView &pv, int threads) {
@@ -71,6 +74,7 @@ __global__ void __launch_bounds__(kThreads) k_eval(ProgView pv, Gen gen) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t stage = smem_stage_bytes(pv);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + stage);
+    volatile uint32_t *s_tile = reinterpret_cast<volatile uint32_t *>(smem + stage + 8);
     bulk_stage(smem, pv.g_prog, stage, bar);
     const uint4 *prog = reinterpret_cast<const uint4 *>(smem);
     const float4 *aux = pv.stage_aux ? reinterpret_cast<const float4 *>(smem + pv.prog_bytes)
@@ -80,11 +84,25 @@ __global__ void __launch_bounds__(kThreads) k_eval(ProgView pv, Gen gen) {
 
     Machine<P> m;
     const uint64_t nwork = gen.work_items();
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwork; w += (uint64_t)gridDim.x * blockDim.x) {
+    for (;;) {
+        if (threadIdx.x == 0) *s_tile = atomicAdd(pv.sched, 1u);
+        __syncthreads();
+        const uint64_t w = (uint64_t)(*s_tile) * blockDim.x + threadIdx.x;
+        __syncthreads();
+        if (w - threadIdx.x >= nwork) break;
+        if (w >= nwork) continue;
         m.init(dstk, pstk, blockDim.x);
-        if (!gen.load(w, m.px, m.py, m.pz)) continue;
+        gen.load(w, m.px, m.py, m.pz);
         run_program<P>(m, prog, aux);
         gen.store(w, m.top);
+    }
+    // the last CTA to leave re-arms the scheduler for the next launch
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(pv.sched + 1, 1u) == gridDim.x - 1) {
+            pv.sched[0] = 0u;
+            pv.sched[1] = 0u;
+        }
     }
 }
 
@@ -93,7 +111,7 @@ __global__ void __launch_bounds__(kThreads) k_eval(ProgView pv, Gen gen) {
 struct GenPoints3 {
     const float *pos; float *dist; uint64_t n; int vec;  // vec: both pointers 16-byte aligned
     __device__ uint64_t work_items() const { return (n + 3) / 4; }
-    __device__ bool load(uint64_t w, float (&x)[4], float (&y)[4], float (&z)[4]) const {
+    __device__ void load(uint64_t w, float (&x)[4], float (&y)[4], float (&z)[4]) const {
         const uint64_t i0 = w * 4;
         if (vec && i0 + 4 <= n) {
             const float4 *p4 = reinterpret_cast<const float4 *>(pos) + w * 3;
@@ -107,7 +125,6 @@ struct GenPoints3 {
                 x[j] = __ldg(pos + 3 * i); y[j] = __ldg(pos + 3 * i + 1); z[j] = __ldg(pos + 3 * i + 2);
             }
         }
-        return true;
     }
     __device__ void store(uint64_t w, const float (&d)[4]) const {
         const uint64_t i0 = w * 4;
@@ -123,7 +140,7 @@ struct GenPoints3 {
 struct GenPoints2 {
     const float *pos; float *dist; uint64_t n; int vec;
     __device__ uint64_t work_items() const { return (n + 3) / 4; }
-    __device__ bool load(uint64_t w, float (&x)[4], float (&y)[4], float (&z)[4]) const {
+    __device__ void load(uint64_t w, float (&x)[4], float (&y)[4], float (&z)[4]) const {
         const uint64_t i0 = w * 4;
         if (vec && i0 + 4 <= n) {
             const float4 *p4 = reinterpret_cast<const float4 *>(pos) + w * 2;
@@ -138,7 +155,6 @@ struct GenPoints2 {
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) z[j] = 0.f;
-        return true;
     }
     __device__ void store(uint64_t w, const float (&d)[4]) const {
         const uint64_t i0 = w * 4;
@@ -161,89 +177,80 @@ struct Lat {
     int vec;           // rows 16-byte aligned -> float4 stores
 };
 // FlatRenderer.evalKRange (glrender/flatrenderer.go:146-182): positions origin + float32(i)*res, x fastest.
+// Work unit = a quad of 4 consecutive corners of one lattice row, split over 4/P threads.
 // list==nullptr: every quad of the slab; else the compacted quad ids produced by k_compact_quads.
+template <int P>
 struct GenGrid {
+    static_assert(P == 1 || P == 2 || P == 4, "P must divide 4");
     Lat L; float *dist; const uint32_t *list; const uint32_t *count;
-    __device__ uint64_t work_items() const { return list ? (uint64_t)*count : (uint64_t)L.nqx * (L.ny + 1) * L.nk; }
-    __device__ void decode(uint64_t w, int &m, int &j, int &k) const {
-        uint64_t q = list ? (uint64_t)list[w] : w;
-        m = (int)(q % L.nqx); q /= L.nqx;
-        j = (int)(q % (L.ny + 1));
-        k = (int)(q / (L.ny + 1));
+    __device__ uint64_t work_items() const { return (list ? (uint64_t)*count : (uint64_t)L.nqx * (L.ny + 1) * L.nk) * (4 / P); }
+    __device__ void decode(uint64_t w, int &i0, int &j, int &k) const {
+        const uint32_t sub = (uint32_t)(w % (4 / P));
+        uint32_t q = list ? list[w / (4 / P)] : (uint32_t)(w / (4 / P));
+        const uint32_t m = q % (uint32_t)L.nqx; q /= (uint32_t)L.nqx;
+        j = (int)(q % (uint32_t)(L.ny + 1));
+        k = (int)(q / (uint32_t)(L.ny + 1));
+        i0 = (int)(4 * m + P * sub);
     }
-    __device__ bool load(uint64_t w, float (&x)[4], float (&y)[4], float (&z)[4]) const {
-        int m, j, k;
-        decode(w, m, j, k);
+    __device__ void load(uint64_t w, float (&x)[P], float (&y)[P], float (&z)[P]) const {
+        int i0, j, k;
+        decode(w, i0, j, k);
         const float yy = L.oy + (float)j * L.res, zz = L.oz + (float)(L.k0 + k) * L.res;
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const int i = min(4 * m + t, L.nx);
+        for (int t = 0; t < P; t++) {
+            const int i = min(i0 + t, L.nx);
             x[t] = L.ox + (float)i * L.res; y[t] = yy; z[t] = zz;
         }
-        return true;
     }
-    __device__ void store(uint64_t w, const float (&d)[4]) const {
-        int m, j, k;
-        decode(w, m, j, k);
-        float *row = dist + ((size_t)k * (L.ny + 1) + j) * L.pitch + 4 * m;
-        if (L.vec && 4 * m + 3 < L.pitch) {
-            *reinterpret_cast<float4 *>(row) = make_float4(d[0], d[1], d[2], d[3]);
+    __device__ void store(uint64_t w, const float (&d)[P]) const {
+        int i0, j, k;
+        decode(w, i0, j, k);
+        float *row = dist + ((size_t)k * (L.ny + 1) + j) * L.pitch + i0;
+        if (L.vec) {  // pitch is a multiple of 4 and covers every quad: no bounds check needed
+            if (P == 4) *reinterpret_cast<float4 *>(row) = make_float4(d[0], d[P > 1 ? 1 : 0], d[P > 2 ? 2 : 0], d[P > 3 ? 3 : 0]);
+            else if (P == 2) *reinterpret_cast<float2 *>(row) = make_float2(d[0], d[P > 1 ? 1 : 0]);
+            else row[0] = d[0];
         } else {
 #pragma unroll
-            for (int t = 0; t < 4; t++) if (4 * m + t <= L.nx) row[t] = d[t];
+            for (int t = 0; t < P; t++) if (i0 + t <= L.nx) row[t] = d[t];
         }
     }
 };
 
 // Octree prune (glrender/octreerenderer.go:180-191, 240-284): evaluate the centre of every level-3 cube (4 cells
-// wide) of the slab; keep it iff |d| < size*sqrt3/2. One byte per block, x fastest.
+// wide) of the slab; keep it iff |d| < size*sqrt3/2. One byte per block, x fastest. One cube per thread: the pass is
+// small and latency bound, so it wants threads, not per-thread ILP.
 struct GenCenters {
     float ox, oy, oz, res; int nbx, nby, nbz, bz0; float half, maxDist; uint8_t *mask;
-    __device__ uint64_t work_items() const { return (uint64_t)((nbx + 3) / 4) * nby * nbz; }
-    __device__ void decode(uint64_t w, int &bq, int &by, int &bz) const {
-        const int nq = (nbx + 3) / 4;
-        bq = (int)(w % nq); w /= nq;
-        by = (int)(w % nby); bz = (int)(w / nby);
+    __device__ uint64_t work_items() const { return (uint64_t)nbx * nby * nbz; }
+    __device__ void load(uint64_t w, float (&x)[1], float (&y)[1], float (&z)[1]) const {
+        uint32_t t = (uint32_t)w;
+        const int bx = (int)(t % (uint32_t)nbx); t /= (uint32_t)nbx;
+        const int by = (int)(t % (uint32_t)nby), bz = (int)(t / (uint32_t)nby);
+        x[0] = (ox + (float)(4 * bx) * res) + half;
+        y[0] = (oy + (float)(4 * by) * res) + half;
+        z[0] = (oz + (float)(4 * (bz0 + bz)) * res) + half;
     }
-    __device__ bool load(uint64_t w, float (&x)[4], float (&y)[4], float (&z)[4]) const {
-        int bq, by, bz;
-        decode(w, bq, by, bz);
-        const float yy = (oy + (float)(4 * by) * res) + half, zz = (oz + (float)(4 * (bz0 + bz)) * res) + half;
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const int bx = min(4 * bq + t, nbx - 1);
-            x[t] = (ox + (float)(4 * bx) * res) + half; y[t] = yy; z[t] = zz;
-        }
-        return true;
-    }
-    __device__ void store(uint64_t w, const float (&d)[4]) const {
-        int bq, by, bz;
-        decode(w, bq, by, bz);
-        uint8_t *row = mask + ((size_t)bz * nby + by) * nbx;
-#pragma unroll
-        for (int t = 0; t < 4; t++)
-            if (4 * bq + t < nbx) row[4 * bq + t] = fabsf(d[t]) >= maxDist ? 0 : 1;
-    }
+    __device__ void store(uint64_t w, const float (&d)[1]) const { mask[w] = fabsf(d[0]) >= maxDist ? 0 : 1; }
 };
 
 // ImageRendererSDF2.Render positions (glrender/image.go:85-105).
 struct GenImage {
     float xmin, ymax, dx, dy; int w, h; float *dist;
     __device__ uint64_t work_items() const { return (uint64_t)((w + 3) / 4) * h; }
-    __device__ bool load(uint64_t wi, float (&x)[4], float (&y)[4], float (&z)[4]) const {
-        const int nq = (w + 3) / 4;
-        const int q = (int)(wi % nq), j = (int)(wi / nq);
+    __device__ void load(uint64_t wi, float (&x)[4], float (&y)[4], float (&z)[4]) const {
+        const uint32_t nq = (uint32_t)(w + 3) / 4;
+        const int q = (int)((uint32_t)wi % nq), j = (int)((uint32_t)wi / nq);
         const float yy = ymax - (float)j * dy;
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             const int i = min(4 * q + t, w - 1);
             x[t] = (float)i * dx + xmin; y[t] = yy; z[t] = 0.f;
         }
-        return true;
     }
     __device__ void store(uint64_t wi, const float (&d)[4]) const {
-        const int nq = (w + 3) / 4;
-        const int q = (int)(wi % nq), j = (int)(wi / nq);
+        const uint32_t nq = (uint32_t)(w + 3) / 4;
+        const int q = (int)((uint32_t)wi % nq), j = (int)((uint32_t)wi / nq);
         float *row = dist + (size_t)j * w;
         if ((w & 3) == 0) {
             *reinterpret_cast<float4 *>(row + 4 * q) = make_float4(d[0], d[1], d[2], d[3]);
@@ -262,51 +269,91 @@ struct MeshDims {
     int nqx;                 // quads per corner row
     int pitch;               // grid row pitch (floats)
     int nsx;                 // 32-cell segments per cell row
+    int nwx;                 // 32-bit words per block row of the bit mask = ceil(nbx/32)
 };
 
-__device__ __forceinline__ bool block_on(const uint8_t *mask, const MeshDims &D, int bx, int by, int bz) {
-    if (bx < 0 || by < 0 || bx >= D.nbx || by >= D.nby) return false;
-    const int lz = bz - D.bz0;
-    if (lz < 0 || lz >= D.nbz) return false;
-    return mask[((size_t)lz * D.nby + by) * D.nbx + bx] != 0;
+// Byte mask -> bit rows: one warp per block row (by,bz); word w of a row holds blocks 32w..32w+31. Also counts the
+// kept blocks (Octree.TotalPruned bookkeeping).
+__global__ void __launch_bounds__(kThreads) k_mask_bits(MeshDims D, const uint8_t *__restrict__ mask, uint32_t *__restrict__ bits,
+                                                       uint32_t *__restrict__ kept) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t nrows = (uint32_t)D.nby * (uint32_t)D.nbz;
+    const uint32_t wpg = gridDim.x * (blockDim.x >> 5);
+    uint32_t cnt = 0;
+    for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += wpg) {
+        const uint8_t *row = mask + (size_t)r * D.nbx;
+        for (int w = 0; w < D.nwx; w++) {
+            const int b = 32 * w + lane;
+            const uint32_t word = __ballot_sync(0xffffffffu, b < D.nbx && row[b] != 0);
+            if (lane == 0) { bits[(size_t)r * D.nwx + w] = word; cnt += __popc(word); }
+        }
+    }
+    if (lane == 0 && cnt) atomicAdd(kept, cnt);
 }
 
-// One thread per lattice quad (m,j,k) of the slab's corner planes: it must be evaluated iff some kept block owns a
-// cell that touches one of its 4 corners. Survivors are appended warp-aggregated (ballot + one atomicAdd per warp).
-__global__ void __launch_bounds__(kThreads) k_compact_quads(MeshDims D, const uint8_t *__restrict__ mask, uint32_t *__restrict__ list,
+__device__ __forceinline__ uint32_t bit_at(const uint32_t *row, int b) { return b < 0 ? 0u : (row[b >> 5] >> (b & 31)) & 1u; }
+
+// One warp per lattice corner row (j,k) of the slab: a quad (4 consecutive corners starting at 4m) must be evaluated
+// iff some kept block owns a cell touching one of its corners. Such cells have cy in {j-1,j}, cz in {k-1,k} (inside the
+// slab) and cx in [4m-1, 4m+3], i.e. blocks m-1 and m of up to four block rows. Survivors are appended
+// warp-aggregated: one ballot + one atomicAdd per 32 quads.
+__global__ void __launch_bounds__(kThreads) k_compact_quads(MeshDims D, const uint32_t *__restrict__ bits, uint32_t *__restrict__ list,
                                                            uint32_t *__restrict__ count) {
-    const uint64_t nq = (uint64_t)D.nqx * (D.ny + 1) * (D.cz1 - D.cz0 + 1);
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < nq; base += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t q = base + threadIdx.x;
-        bool need = false;
-        if (q < nq) {
-            uint64_t t = q;
-            const int m = (int)(t % D.nqx); t /= D.nqx;
-            const int j = (int)(t % (D.ny + 1));
-            const int k = D.cz0 + (int)(t / (D.ny + 1));
-            // cells touching corner plane k inside the slab: cz = k-1 (if >= cz0) and cz = k (if < cz1)
+    __shared__ uint32_t s_cnt[kThreads / 32];
+    __shared__ uint32_t s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nrows = (uint32_t)(D.ny + 1) * (uint32_t)(D.cz1 - D.cz0 + 1);
+    const uint32_t rpg = gridDim.x * (blockDim.x >> 5);
+    // CTA-uniform trip count: every iteration the 8 warps take 8 consecutive rows and share ONE atomicAdd
+    for (uint32_t r0 = blockIdx.x * (blockDim.x >> 5); r0 < nrows; r0 += rpg) {
+        const uint32_t r = r0 + warp;
+        const uint32_t *rows[4];
+        int nr = 0;
+        if (r < nrows) {
+            const int j = (int)(r % (uint32_t)(D.ny + 1));
+            const int k = D.cz0 + (int)(r / (uint32_t)(D.ny + 1));
+            // the (at most 2 x 2) block rows whose cells touch this corner row
+            const int by0 = j - 1 >= 0 ? (j - 1) >> 2 : -1, by1 = j < D.ny ? j >> 2 : -1;
+            const int bz0 = k - 1 >= D.cz0 ? (k - 1) >> 2 : -1, bz1 = k < D.cz1 ? k >> 2 : -1;
 #pragma unroll
-            for (int dz = -1; dz <= 0; dz++) {
-                const int cz = k + dz;
-                if (cz < D.cz0 || cz >= D.cz1) continue;
+            for (int a = 0; a < 2; a++) {
+                const int by = a ? by1 : by0;
+                if (by < 0 || (a && by1 == by0)) continue;
 #pragma unroll
-                for (int dy = -1; dy <= 0; dy++) {
-                    const int cy = j + dy;
-                    if (cy < 0 || cy >= D.ny) continue;
-                    // cells cx in [4m-1, 4m+3] -> blocks m-1 (via cx=4m-1) and m
-                    if (4 * m - 1 >= 0 && block_on(mask, D, m - 1, cy >> 2, cz >> 2)) need = true;
-                    if (4 * m < D.nx && block_on(mask, D, m, cy >> 2, cz >> 2)) need = true;
+                for (int c = 0; c < 2; c++) {
+                    const int bz = c ? bz1 : bz0;
+                    if (bz < 0 || (c && bz1 == bz0)) continue;
+                    rows[nr++] = bits + ((size_t)(bz - D.bz0) * D.nby + by) * D.nwx;
                 }
             }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, need);
-        if (bal) {
-            const int lane = threadIdx.x & 31;
-            uint32_t wbase = 0;
-            if (lane == 0) wbase = atomicAdd(count, (uint32_t)__popc(bal));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (need) list[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)q;
+        auto needed = [&](int m) -> bool {
+            uint32_t need = 0u;
+            if (m < D.nqx)
+                for (int t = 0; t < nr; t++) {
+                    if (m < D.nbx) need |= bit_at(rows[t], m);
+                    if (m - 1 < D.nbx) need |= bit_at(rows[t], m - 1);
+                }
+            return need != 0u;
+        };
+        uint32_t mine = 0u;
+        for (int m0 = 0; m0 < D.nqx; m0 += 32) mine += __popc(__ballot_sync(0xffffffffu, needed(m0 + lane)));
+        if (lane == 0) s_cnt[warp] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < kThreads / 32; w++) { const uint32_t c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(count, tot) : 0u;
         }
+        __syncthreads();
+        uint32_t o = s_base + s_cnt[warp];
+        for (int m0 = 0; m0 < D.nqx && mine; m0 += 32) {
+            const bool need = needed(m0 + lane);
+            const unsigned bal = __ballot_sync(0xffffffffu, need);
+            if (need) list[o + __popc(bal & ((1u << lane) - 1u))] = r * (uint32_t)D.nqx + (uint32_t)(m0 + lane);
+            o += __popc(bal);
+        }
+        __syncthreads();
     }
 }
 
@@ -315,29 +362,17 @@ struct MCArgs {
     MeshDims D;
     float ox, oy, oz, res, cubeDiag;
     const float *grid;      // slab corner planes, plane 0 = corner plane cz0
-    const uint8_t *mask;    // nullptr = FlatRenderer semantics (no prune)
-    uint32_t *segcount;     // per segment triangle count (count pass) / exclusive offsets (emit pass)
+    const uint32_t *mbits;  // prune bit rows (k_mask_bits); nullptr = FlatRenderer semantics (no prune)
+    const uint8_t *t_ntri;  // marching-cubes tables in GLOBAL memory (divergent __constant__ reads serialise)
+    const int8_t *t_tris;
+    uint32_t *segcount;     // per 32-cell segment: triangle count (pass 1) / exclusive offset (pass 2)
     float *tris;            // 9 floats per triangle
     uint64_t tri_capacity;
-    uint8_t *cases;         // optional nx*ny*(cz1-cz0) bytes
+    uint8_t *cases;         // optional nx*ny*(cz1-cz0) bytes (pass 1 only)
     uint32_t *overflow;     // set to 1 if a triangle did not fit
+    uint32_t *seg_list;     // compact list of non-empty 32-cell segments (pass 1 -> pass 2)
+    uint32_t *seg_count;
 };
-
-// marchcubes.go:39-44 + flatrenderer.go:215-233: corner order (0,0,0)(1,0,0)(1,1,0)(0,1,0)(0,0,1)(1,0,1)(1,1,1)(0,1,1)
-__device__ __forceinline__ int mc_classify(const MCArgs &A, int cx, int cy, int cz, float (&v)[8]) {
-    const MeshDims &D = A.D;
-    if (A.mask && !block_on(A.mask, D, cx >> 2, cy >> 2, cz >> 2)) return 0;
-    const size_t sy = (size_t)D.pitch, sz = sy * (D.ny + 1);
-    const float *g = A.grid + (size_t)(cz - D.cz0) * sz + (size_t)cy * sy + cx;
-    v[0] = __ldg(g);
-    if (fabsf(v[0]) > A.cubeDiag) return 0;  // flatrenderer.go:218-220
-    v[1] = __ldg(g + 1); v[2] = __ldg(g + 1 + sy); v[3] = __ldg(g + sy);
-    v[4] = __ldg(g + sz); v[5] = __ldg(g + 1 + sz); v[6] = __ldg(g + 1 + sy + sz); v[7] = __ldg(g + sy + sz);
-    int index = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) if (v[i] < 0.f) index |= 1 << i;
-    return index;
-}
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
     const int lane = threadIdx.x & 31;
@@ -347,31 +382,6 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
         if (lane >= o) v += t;
     }
     return v;
-}
-
-// Pass 1: triangles per 32-cell row segment. One warp per segment.
-__global__ void __launch_bounds__(kThreads) k_mc_count(MCArgs A) {
-    __shared__ uint8_t s_ntri[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = c_mc_ntri[i];
-    __syncthreads();
-    const MeshDims &D = A.D;
-    const uint64_t nseg = (uint64_t)D.nsx * D.ny * (D.cz1 - D.cz0);
-    const int lane = threadIdx.x & 31;
-    const uint64_t wpg = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    for (uint64_t s = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < nseg; s += wpg) {
-        uint64_t t = s;
-        const int sx = (int)(t % D.nsx); t /= D.nsx;
-        const int cy = (int)(t % D.ny);
-        const int cz = D.cz0 + (int)(t / D.ny);
-        const int cx = sx * 32 + lane;
-        int index = 0;
-        float v[8];
-        if (cx < D.nx) index = mc_classify(A, cx, cy, cz, v);
-        if (A.cases && cx < D.nx) A.cases[((size_t)(cz - D.cz0) * D.ny + cy) * D.nx + cx] = (uint8_t)index;
-        uint32_t n = s_ntri[index];
-        const uint32_t incl = warp_incl_scan(n);
-        if (lane == 31) A.segcount[s] = incl;
-    }
 }
 
 // marchcubes.go:76-98
@@ -385,52 +395,175 @@ __device__ __forceinline__ float3 mc_interp(float3 p1, float3 p2, float v1, floa
     return make_float3(p1.x + t * (p2.x - p1.x), p1.y + t * (p2.y - p1.y), p1.z + t * (p2.z - p1.z));
 }
 
-// Pass 2: emit. segcount now holds exclusive offsets; the warp inclusive scan places each cell's triangles.
-__global__ void __launch_bounds__(kThreads) k_mc_emit(MCArgs A) {
+// Classification of one 32-cell segment of cell row (g00..g11 point at the four corner rows of the cube row).
+// 4 coalesced row loads give every lane the x=cx column of its cube, the x=cx+1 column comes from the next lane by
+// shuffle (corner order of flatrenderer.go:222-233); case index per marchcubes.go:39-44, reject rule
+// flatrenderer.go:218-220. v[] = corner values 0..7.
+__device__ __forceinline__ int mc_classify_segment(const float *g00, const float *g01, const float *g10, const float *g11, int cx, int nx,
+                                                   bool act, float cubeDiag, float (&v)[8]) {
+    const int lane = threadIdx.x & 31;
+    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+    if (cx <= nx) { a00 = __ldg(g00 + cx); a01 = __ldg(g01 + cx); a10 = __ldg(g10 + cx); a11 = __ldg(g11 + cx); }
+    float b00 = __shfl_down_sync(0xffffffffu, a00, 1), b01 = __shfl_down_sync(0xffffffffu, a01, 1);
+    float b10 = __shfl_down_sync(0xffffffffu, a10, 1), b11 = __shfl_down_sync(0xffffffffu, a11, 1);
+    if (lane == 31 && cx + 1 <= nx) { b00 = __ldg(g00 + cx + 1); b01 = __ldg(g01 + cx + 1); b10 = __ldg(g10 + cx + 1); b11 = __ldg(g11 + cx + 1); }
+    v[0] = a00; v[1] = b00; v[2] = b01; v[3] = a01; v[4] = a10; v[5] = b10; v[6] = b11; v[7] = a11;
+    int index = 0;
+    if (act && !(fabsf(a00) > cubeDiag)) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) index |= (v[i] < 0.f ? 1 : 0) << i;
+    }
+    return index;
+}
+
+// Pass 1: one warp per group of 4 consecutive 32-cell segments (= 32 prune blocks) of a cell row: one mask load +
+// ballot decides which of its segments can hold surface; the others cost nothing. Writes the triangle count of every
+// segment (the exclusive scan over this array gives output offsets in FlatRenderer cell order) and appends non-empty
+// segments to a compact work list for pass 2.
+__global__ void __launch_bounds__(kThreads) k_mc_count(MCArgs A) {
     __shared__ uint8_t s_ntri[256];
-    __shared__ int8_t s_tris[256 * 16];
-    __shared__ uint16_t s_edges[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_ntri[i] = c_mc_ntri[i]; s_edges[i] = c_mc_edges[i]; }
-    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) s_tris[i] = c_mc_tris[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = A.t_ntri[i];
     __syncthreads();
     const MeshDims &D = A.D;
-    const uint64_t nseg = (uint64_t)D.nsx * D.ny * (D.cz1 - D.cz0);
-    const int lane = threadIdx.x & 31;
-    const uint64_t wpg = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    for (uint64_t s = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < nseg; s += wpg) {
-        uint64_t t = s;
-        const int sx = (int)(t % D.nsx); t /= D.nsx;
-        const int cy = (int)(t % D.ny);
-        const int cz = D.cz0 + (int)(t / D.ny);
-        const int cx = sx * 32 + lane;
-        int index = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nrows = (uint32_t)D.ny * (uint32_t)(D.cz1 - D.cz0);
+    const uint32_t ngroups = (uint32_t)(D.nsx + 3) / 4;
+    const uint32_t ntasks = nrows * ngroups;
+    const uint32_t wpg = gridDim.x * (blockDim.x >> 5);
+    const size_t sy = (size_t)D.pitch, sz = sy * (D.ny + 1);
+    __shared__ uint32_t s_cnt[kThreads / 32];
+    __shared__ uint32_t s_base;
+    // CTA-uniform trip count so the 8 warps can share one atomicAdd per iteration for the work-list append
+    for (uint32_t task0 = blockIdx.x * (blockDim.x >> 5); task0 < ntasks; task0 += wpg) {
+        const uint32_t task = task0 + warp;
+        uint32_t mine = 0u;  // lane sgm keeps the count of segment sgm
+        uint32_t s0 = 0u;
+        int nsg = 0;
+        if (task < ntasks) {
+            const uint32_t r = task / ngroups, g = task - r * ngroups;
+            const int cy = (int)(r % (uint32_t)D.ny);
+            const int czl = (int)(r / (uint32_t)D.ny);
+            const int cz = D.cz0 + czl;
+            const int b0 = (int)g * 32;
+            uint32_t word = 0xffffffffu;
+            if (A.mbits) word = A.mbits[((size_t)((cz >> 2) - D.bz0) * D.nby + (cy >> 2)) * D.nwx + g];
+            s0 = r * (uint32_t)D.nsx + g * 4u;
+            nsg = min(4, D.nsx - (int)g * 4);
+            if (word == 0u) {
+                if (lane < nsg) A.segcount[s0 + lane] = 0u;
+                if (A.cases)
+                    for (int c = lane; c < 128; c += 32) { const int cx = 4 * b0 + c; if (cx < D.nx) A.cases[(size_t)r * D.nx + cx] = 0; }
+            } else {
+                const float *g00 = A.grid + (size_t)czl * sz + (size_t)cy * sy;
+                const float *g01 = g00 + sy, *g10 = g00 + sz, *g11 = g10 + sy;
+#pragma unroll
+                for (int sgm = 0; sgm < 4; sgm++) {
+                    if (sgm >= nsg) break;
+                    const int x0 = 4 * b0 + 32 * sgm;
+                    const uint32_t bits = (word >> (8 * sgm)) & 0xffu;
+                    const int cx = x0 + lane;
+                    int index = 0;
+                    uint32_t n = 0u;
+                    if (bits != 0u) {
+                        const bool act = cx < D.nx && ((bits >> (lane >> 2)) & 1u);
+                        float v[8];
+                        index = mc_classify_segment(g00, g01, g10, g11, cx, D.nx, act, A.cubeDiag, v);
+                        n = s_ntri[index];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+                    }
+                    if (A.cases && cx < D.nx) A.cases[(size_t)r * D.nx + cx] = (uint8_t)index;
+                    if (lane == sgm) mine = n;
+                }
+                if (lane < nsg) A.segcount[s0 + lane] = mine;
+            }
+        }
+        const unsigned nz = __ballot_sync(0xffffffffu, lane < nsg && mine != 0u);
+        if (lane == 0) s_cnt[warp] = (uint32_t)__popc(nz);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < kThreads / 32; w++) { const uint32_t c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(A.seg_count, tot) : 0u;
+        }
+        __syncthreads();
+        if ((nz >> lane) & 1u) A.seg_list[s_base + s_cnt[warp] + __popc(nz & ((1u << lane) - 1u))] = s0 + lane;
+        __syncthreads();
+    }
+}
+
+// Pass 2: one warp per non-empty segment. segcount[] now holds exclusive triangle offsets. A surface usually crosses
+// a row segment in only a few cells, so the segment's triangle VERTICES (3 per triangle) are dealt round-robin to
+// the 32 lanes: each lane finds the owning cell of its vertex by a shuffle search over the inclusive scan of the
+// per-cell triangle counts, interpolates that one edge and stores 3 floats.
+__global__ void __launch_bounds__(kThreads) k_mc_emit(MCArgs A) {
+    __shared__ uint8_t s_ntri[256];
+    __shared__ __align__(16) int8_t s_tris[256 * 16];
+    __shared__ float s_v[(kThreads / 32) * 8 * 32];  // [warp][corner][lane]
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = A.t_ntri[i];
+    for (int i = threadIdx.x; i < 256 * 16 / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_tris)[i] = reinterpret_cast<const uint4 *>(A.t_tris)[i];
+    __syncthreads();
+    const MeshDims &D = A.D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nseg = *A.seg_count;
+    const uint32_t wpg = gridDim.x * (blockDim.x >> 5);
+    const size_t sy = (size_t)D.pitch, sz = sy * (D.ny + 1);
+    float *vw = s_v + warp * 256;
+    for (uint32_t t = blockIdx.x * (blockDim.x >> 5) + warp; t < nseg; t += wpg) {
+        const uint32_t s = A.seg_list[t];
+        const uint32_t r = s / (uint32_t)D.nsx;
+        const int x0 = (int)(s - r * (uint32_t)D.nsx) << 5;
+        const int cy = (int)(r % (uint32_t)D.ny);
+        const int czl = (int)(r / (uint32_t)D.ny);
+        const int cz = D.cz0 + czl;
+        const float *g00 = A.grid + (size_t)czl * sz + (size_t)cy * sy;
+        const float *g01 = g00 + sy, *g10 = g00 + sz, *g11 = g10 + sy;
+        const int cx = x0 + lane;
+        bool act = cx < D.nx;
+        if (A.mbits) act = act && bit_at(A.mbits + ((size_t)((cz >> 2) - D.bz0) * D.nby + (cy >> 2)) * D.nwx, min(cx, D.nx - 1) >> 2) != 0u;
         float v[8];
-        if (cx < D.nx) index = mc_classify(A, cx, cy, cz, v);
+        const int index = mc_classify_segment(g00, g01, g10, g11, cx, D.nx, act, A.cubeDiag, v);
         const uint32_t n = s_ntri[index];
         const uint32_t incl = warp_incl_scan(n);
-        if (n == 0) continue;
-        uint64_t o = (uint64_t)A.segcount[s] + (incl - n);
-        // corner positions, flatrenderer.go:235-247
-        const float r = A.res;
-        const float x0 = A.ox + (float)cx * r, y0 = A.oy + (float)cy * r, z0 = A.oz + (float)cz * r;
-        const float x1 = x0 + r, y1 = y0 + r, z1 = z0 + r;
-        const float3 p[8] = {{x0, y0, z0}, {x1, y0, z0}, {x1, y1, z0}, {x0, y1, z0}, {x0, y0, z1}, {x1, y0, z1}, {x1, y1, z1}, {x0, y1, z1}};
-        const uint32_t edges = s_edges[index];
-        float3 pts[12];
-        // edge -> corner pairs (marchcubes.go:101-114), compile-time so p[]/v[] stay in registers
-        constexpr int PA[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3};
-        constexpr int PB[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
 #pragma unroll
-        for (int e = 0; e < 12; e++) {
-            if (edges & (1u << e)) pts[e] = mc_interp(p[PA[e]], p[PB[e]], v[PA[e]], v[PB[e]]);
-        }
-        const int8_t *tb = s_tris + 16 * index;
-        for (uint32_t k = 0; k < n; k++, o++) {
-            if (o >= A.tri_capacity) { *A.overflow = 1u; break; }
-            // marchcubes.go:64-68: (points[t+2], points[t+1], points[t])
-            const float3 a = pts[tb[3 * k + 2]], b = pts[tb[3 * k + 1]], c = pts[tb[3 * k]];
-            float *dst = A.tris + 9 * o;
-            dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = b.x; dst[4] = b.y; dst[5] = b.z; dst[6] = c.x; dst[7] = c.y; dst[8] = c.z;
+        for (int i = 0; i < 8; i++) vw[i * 32 + lane] = v[i];
+        __syncwarp();
+        const uint64_t obase = (uint64_t)A.segcount[s];
+        // corner positions, flatrenderer.go:235-247
+        const float rr = A.res;
+        const float py0 = A.oy + (float)cy * rr, pz0 = A.oz + (float)cz * rr;
+        const float py1 = py0 + rr, pz1 = pz0 + rr;
+        for (uint32_t ibase = 0; ibase < 3u * total; ibase += 32) {  // warp-uniform trip count: shuffles use all lanes
+            const uint32_t item = ibase + lane;
+            const bool live = item < 3u * total;
+            const uint32_t tri = live ? item / 3u : total - 1u, j = live ? item - 3u * tri : 0u;
+            // owner = first lane whose inclusive count exceeds tri (binary search by shuffle)
+            int lo = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint32_t probe = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+                if (probe <= tri) lo += step;
+            }
+            const int owner = lo;
+            const uint32_t oincl = __shfl_sync(0xffffffffu, incl, owner);
+            const uint32_t on = __shfl_sync(0xffffffffu, n, owner);
+            const int oindex = __shfl_sync(0xffffffffu, index, owner);
+            if (!live) continue;
+            const uint32_t k = tri - (oincl - on);
+            const uint64_t o = obase + tri;
+            if (o >= A.tri_capacity) { *A.overflow = 1u; continue; }
+            const float px0 = A.ox + (float)(x0 + owner) * rr, px1 = px0 + rr;
+            // marchcubes.go:64-68: vertex j of the triangle is points[table[3k + 2 - j]]
+            const int e = s_tris[16 * oindex + 3 * (int)k + 2 - (int)j];
+            // edge -> corner pair (marchcubes.go:101-114), packed 4 bits per edge
+            const int ca = (int)((0x321076543210ull >> (4 * e)) & 0xf), cb = (int)((0x765447650321ull >> (4 * e)) & 0xf);
+            const float3 pa = make_float3((((ca + 1) >> 1) & 1) ? px1 : px0, ((ca >> 1) & 1) ? py1 : py0, (ca >> 2) ? pz1 : pz0);
+            const float3 pb = make_float3((((cb + 1) >> 1) & 1) ? px1 : px0, ((cb >> 1) & 1) ? py1 : py0, (cb >> 2) ? pz1 : pz0);
+            const float3 q = mc_interp(pa, pb, vw[ca * 32 + owner], vw[cb * 32 + owner]);
+            float *dst = A.tris + 9 * o + 3 * j;
+            dst[0] = q.x; dst[1] = q.y; dst[2] = q.z;
         }
     }
 }

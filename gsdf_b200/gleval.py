@@ -42,6 +42,14 @@ class _SDFCUDA:
         self._h = h
         self._bounds = shader.Bounds()
 
+    def Update(self, shader):
+        """Re-flatten `shader` (same dimension) and upload it into this evaluator's device buffers."""
+        f = shader.bld.flatten(shader)
+        aux = np.ascontiguousarray(f["aux"], dtype=np.float32)
+        check(lib.gsdf_program_update(self._h, f["blob"], len(f["blob"]), aux.ctypes.data_as(C.POINTER(C.c_float)), aux.size))
+        self.shader = shader
+        self._bounds = shader.Bounds()
+
     def Close(self):
         h, self._h = getattr(self, "_h", None), None
         if h:

@@ -54,6 +54,10 @@ int gsdf_set_device(int device);
  * (glbuild/glbuild.go:175, gleval/gpu.go:35): "compile" is an upload of a few KB, done once.
  * blob = gsdf_program_header followed by header.nchunks 16-byte chunks; aux = side buffer of floats. */
 int gsdf_program_create(const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats, gsdf_program **out);
+/* Re-upload a (re-)flattened tree of the same dimension into an existing handle: device buffers, stream and scheduler
+ * are reused, so an edited tree costs one small host->device copy (the GL path recompiles its shader instead,
+ * gleval/gpu.go:35-54). Renderers bound to the handle see the new tree on their next run. */
+int gsdf_program_update(gsdf_program *p, const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats);
 void gsdf_program_destroy(gsdf_program *p);
 /* gleval Evaluations() counter (gleval/cpu.go:126, gleval/gpu.go:80): points successfully evaluated through
  * gsdf_eval3/gsdf_eval2 on this handle. */

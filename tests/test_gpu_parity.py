@@ -367,14 +367,51 @@ def test_flange_full_size_properties(bld):
     assert hashlib.sha256(o.AllTriangles().tobytes()).digest() == h1
 
 
-def test_knurled_large_prune_equals_flat(bld):
-    """A larger lattice than the oracle can finish quickly (knurled @ resdiv 600, 32 M corners): the pruned renderer
-    and the dense renderer agree bit for bit, and pruning skips most evaluations."""
+def test_knurled_large_prune_is_a_subsequence_of_flat(bld):
+    """A larger lattice than the oracle can finish quickly (knurled @ resdiv 600, 32 M corners). The level-3 prune rule
+    (octreerenderer.go:180-191) is only lossless for 1-Lipschitz fields; twist + smooth-k make this field slightly
+    steeper, so -- exactly like the reference's Octree -- the pruned renderer may drop a few cells the dense one keeps.
+    Properties that must hold: every pruned triangle is a dense triangle, in the same order; the loss is tiny; and
+    pruning skips most evaluations."""
     s = gsdf.scene(bld, "knurled-cylinder")
     sdf = gleval.NewCUDASDF3(s)
     res = np.float32(s.Diagonal() / np.float32(600))
     f = glrender.FlatRenderer(sdf, res)
     o = glrender.Octree(sdf, res)
-    assert f.NumTriangles() == o.NumTriangles() > 100000
-    assert np.array_equal(bits(f.AllTriangles()), bits(o.AllTriangles()))
+    nf, no = f.NumTriangles(), o.NumTriangles()
+    assert 100000 < no <= nf and (nf - no) < 1e-3 * nf
+    ft = np.ascontiguousarray(f.AllTriangles()).view(np.uint8).reshape(nf, 36)
+    ot = np.ascontiguousarray(o.AllTriangles()).view(np.uint8).reshape(no, 36)
+    fkeys = [x.tobytes() for x in ft]
+    okeys = [x.tobytes() for x in ot]
+    it = iter(fkeys)
+    assert all(k in it for k in okeys)          # subsequence test: consumes `it` in order
     assert o.Evaluations() < 0.5 * f.Evaluations()
+
+
+def test_program_update_reuses_the_handle(oracle, bld):
+    """gsdf_program_update: an edited tree is re-uploaded into the same evaluator; a bound renderer sees it on its next
+    run; the dimension cannot change."""
+    a = bld.NewSphere(1.0)
+    b = bld.Difference(bld.NewBox(1.6, 1.6, 1.6, 0.1), bld.NewCylinder(0.4, 3, 0))   # fits inside a's bounds
+    sdf = gleval.NewCUDASDF3(a)
+    res = np.float32(0.07)
+    r = glrender.NewOctreeRenderer(sdf, res, 64)
+    n_a = r.NumTriangles()
+    pos = shapes.sample_points(a, dense=[20, 20, 20])
+    out = np.empty(len(pos), np.float32)
+    sdf.Evaluate(pos, out)
+    assert np.array_equal(bits(out), bits(oracle.Tree.from_shader(a).eval3(pos)))
+    sdf.Update(b)
+    sdf.Evaluate(pos, out)
+    assert np.array_equal(bits(out), bits(oracle.Tree.from_shader(b).eval3(pos)))
+    r.Rerun()     # same lattice (sphere bounds), new tree
+    lat = oracle.flat_lattice(*a.Bounds(), res)
+    tb = oracle.Tree.from_shader(b)
+    grid, _ = oracle.flat_eval_grid(tb, lat)
+    mask, _ = oracle.octree_prune_mask(tb, lat)
+    wt, _ = oracle.flat_march(lat, grid, blockmask=mask)
+    assert r.NumTriangles() == len(wt) != n_a
+    assert np.array_equal(bits(r.AllTriangles()), bits(wt))
+    with pytest.raises(gsdf_b200.GsdfError):
+        sdf.Update(bld.NewCircle(1.0))

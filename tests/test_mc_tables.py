@@ -46,12 +46,13 @@ def test_oracle_and_cuda_tables_agree(oracle):
 
 
 def test_emit_kernel_pair_table_matches():
-    """kernels.cuh hard-codes the 12 edge->corner pairs so they are compile-time constants."""
+    """kernels.cuh packs the 12 edge->corner pairs 4 bits per edge into two 64-bit literals."""
     src = open(os.path.join(ROOT, "gsdf_b200", "csrc", "kernels.cuh")).read()
-    pa = [int(x) for x in re.search(r"PA\[12\]\s*=\s*\{([^}]*)\}", src).group(1).split(",")]
-    pb = [int(x) for x in re.search(r"PB\[12\]\s*=\s*\{([^}]*)\}", src).group(1).split(",")]
+    m = re.search(r"\(0x([0-9a-f]+)ull >> \(4 \* e\)\) & 0xf\), cb = \(int\)\(\(0x([0-9a-f]+)ull >> \(4 \* e\)\)", src)
+    assert m
+    pa, pb = int(m.group(1), 16), int(m.group(2), 16)
     _, _, _, cp = _cuh_tables()
-    assert [v for ab in zip(pa, pb) for v in ab] == cp
+    assert [v for e in range(12) for v in ((pa >> (4 * e)) & 0xf, (pb >> (4 * e)) & 0xf)] == cp
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not present (GPU box)")
