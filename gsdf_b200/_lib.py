@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgsdfb200.so")
+LIB_PATH = os.environ.get("GSDF_B200_LIB") or os.path.join(_HERE, "libgsdfb200.so")  # env override: kernel A/B experiments
 
 
 class GsdfError(RuntimeError):

@@ -86,20 +86,20 @@ template <int P, class Gen>
 int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st) {
     if (nwork_upper_bound == 0) return 0;
     auto kern = k_eval<P, Gen>;
-    const uint32_t smem = smem_total_bytes<P>(p->pv, kThreads);
+    const uint32_t smem = smem_total_bytes<P>(p->pv, kEvalThreads);
     static thread_local uint32_t cached_smem = 0xffffffffu;
     static thread_local int cached_occ = 0;
     if (cached_smem != smem) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<uint32_t>(smem, 48 * 1024)));
         int occ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kEvalThreads, smem));
         if (occ < 1) return fail(GSDF_EPROGRAM, "node program needs %u bytes of shared memory per CTA; does not fit", smem);
         cached_occ = occ;
         cached_smem = smem;
     }
-    uint64_t blocks = (nwork_upper_bound + kThreads - 1) / kThreads;
+    uint64_t blocks = (nwork_upper_bound + kEvalThreads - 1) / kEvalThreads;
     blocks = std::min<uint64_t>(blocks, (uint64_t)g_sms * cached_occ);
-    kern<<<(unsigned)blocks, kThreads, smem, st>>>(p->pv, gen);
+    kern<<<(unsigned)blocks, kEvalThreads, smem, st>>>(p->pv, gen);
     CU(cudaGetLastError());
     return 0;
 }
@@ -170,7 +170,7 @@ static int parse_blob(const void *blob, size_t blob_bytes, const float *aux, siz
     if (h.dstack < 1 || h.dstack > 64 || h.pstack > 32) return fail(GSDF_EPROGRAM, "stack depth out of range (d=%u p=%u)", h.dstack, h.pstack);
     chunks = reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(blob) + sizeof h);
     const size_t prog_bytes = (size_t)h.nchunks * 16;
-    const uint32_t stacks = kThreads * 4u * 4u * (h.dstack + 3u * h.pstack);
+    const uint32_t stacks = kEvalThreads * 4u * 4u * (h.dstack + 3u * h.pstack);
     if (prog_bytes + stacks + 16 > 200 * 1024) return fail(GSDF_EPROGRAM, "program too large for shared memory");
     return validate_program(h, chunks, aux_floats);
 }
@@ -198,7 +198,7 @@ static int upload_blob(gsdf_program *p, const gsdf_program_header &h, const uint
     p->pv.dslots = h.dstack;
     p->pv.pslots = h.pstack;
     // stage aux with the program when program + aux + stacks stay under ~100 KB (>= 2 CTAs/SM)
-    const uint32_t stacks = kThreads * 4u * 4u * (h.dstack + 3u * h.pstack);
+    const uint32_t stacks = kEvalThreads * 4u * 4u * (h.dstack + 3u * h.pstack);
     p->pv.stage_aux = (prog_bytes + aux_bytes + stacks + 16 <= 100 * 1024) ? 1u : 0u;
     return 0;
 }

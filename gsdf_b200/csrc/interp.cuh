@@ -14,6 +14,12 @@
 #include "../../include/gsdf_program.h"
 #include "math32.cuh"
 
+// Lockstep: a CTA barrier per interpreted instruction keeps all warps of the CTA inside the same opcode body, so the
+// CTA is ONE instruction-cache stream (see kernels.cuh for the measured effect). Define GSDF_NO_LOCKSTEP to disable.
+#if !defined(GSDF_NO_LOCKSTEP) && !defined(GSDF_LOCKSTEP)
+#define GSDF_LOCKSTEP 1
+#endif
+
 namespace gsdfk {
 
 template <int P>
@@ -71,6 +77,9 @@ __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restri
     using namespace m32;
     int pc = 0;
     for (;;) {
+#ifdef GSDF_LOCKSTEP
+        __syncthreads();  // keep the CTA's warps on the same opcode body: one instruction-cache stream per CTA
+#endif
         const uint4 h = prog[pc];
         const uint32_t op = h.x & 0xffu;
         const int len = (int)((h.x >> 8) & 0xffu);

@@ -23,7 +23,17 @@
 
 namespace gsdfk {
 
-constexpr int kThreads = 256;
+#ifndef GSDF_THREADS
+#define GSDF_THREADS 256
+#endif
+constexpr int kThreads = GSDF_THREADS;   // CTA size of the MC / scan / STL kernels and default of k_eval
+// Measured on B200 (scripts/ab_eval.py): 512-thread CTAs whose warps are kept on the same opcode body by a barrier
+// per instruction (GSDF_LOCKSTEP) cut instruction-fetch stalls: -13 % (flange) / -14 % (knurled) evaluate time
+// versus free-running 256-thread CTAs.
+#ifndef GSDF_EVAL_THREADS
+#define GSDF_EVAL_THREADS 512
+#endif
+constexpr int kEvalThreads = GSDF_EVAL_THREADS;  // CTA size of the interpreter kernel
 
 struct ProgView {
     const uint4 *g_prog;     // device: program chunks followed by aux (16-byte aligned)
@@ -70,7 +80,7 @@ __host__ __device__ inline uint32_t smem_total_bytes(const ProgView &pv, int thr
 }
 
 template <int P, class Gen>
-__global__ void __launch_bounds__(kThreads) k_eval(ProgView pv, Gen gen) {
+__global__ void __launch_bounds__(kEvalThreads) k_eval(ProgView pv, Gen gen) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t stage = smem_stage_bytes(pv);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + stage);
@@ -90,11 +100,20 @@ __global__ void __launch_bounds__(kThreads) k_eval(ProgView pv, Gen gen) {
         const uint64_t w = (uint64_t)(*s_tile) * blockDim.x + threadIdx.x;
         __syncthreads();
         if (w - threadIdx.x >= nwork) break;
+#ifdef GSDF_LOCKSTEP
+        // every thread of the tile runs the program (barriers inside); threads past the end redo the last item
+        const uint64_t wc = w < nwork ? w : nwork - 1;
+        m.init(dstk, pstk, blockDim.x);
+        gen.load(wc, m.px, m.py, m.pz);
+        run_program<P>(m, prog, aux);
+        if (w < nwork) gen.store(w, m.top);
+#else
         if (w >= nwork) continue;
         m.init(dstk, pstk, blockDim.x);
         gen.load(w, m.px, m.py, m.pz);
         run_program<P>(m, prog, aux);
         gen.store(w, m.top);
+#endif
     }
     // the last CTA to leave re-arms the scheduler for the next launch
     if (threadIdx.x == 0) {

@@ -14,6 +14,13 @@
 #include <stdint.h>
 
 #define M32_HD __host__ __device__ __forceinline__
+// Large helpers (hypot, atan2, sincos) can be kept out of line to shrink the interpreter's instruction footprint
+// (the evaluate kernel stalls on instruction fetch when every opcode body inlines its own copies).
+#ifdef GSDF_NOINLINE_MATH
+#define M32_BIG static __host__ __device__ __noinline__
+#else
+#define M32_BIG __host__ __device__ __forceinline__
+#endif
 
 namespace m32 {
 
@@ -57,7 +64,7 @@ M32_HD float add(float a, float b) {
 }
 
 // math32.Hypot: p*Sqrt(1+(q/p)^2) with p>=q (NOT sqrt(p*p+q*q)).
-M32_HD float hypot32(float p, float q) {
+M32_BIG float hypot32(float p, float q) {
     p = fabsf(p);
     q = fabsf(q);
     if (p < q) { float t = p; p = q; q = t; }
@@ -100,7 +107,7 @@ M32_HD float atan(float x) {
     if (x > 0.0f) return satan(x);
     return -satan(-x);
 }
-M32_HD float atan2(float y, float x) {
+M32_BIG float atan2(float y, float x) {
     if (y != y || x != x) return NAN;
     if (y == 0.0f) {
         if (x >= 0.0f && !signbit(x)) return copysignf(0.0f, y);
@@ -167,7 +174,7 @@ M32_HD float cos(float x) {
     return sign ? -y : y;
 }
 // math32.Sincos shares one reduction; the two results equal Sin(x), Cos(x) bit for bit.
-M32_HD void sincos(float x, float &s, float &c) {
+M32_BIG void sincos(float x, float &s, float &c) {
     if (x == 0.0f) { s = x; c = 1.0f; return; }
     if (x != x || isinf(x)) { s = NAN; c = NAN; return; }
     bool ssign = false, csign = false;

@@ -52,7 +52,7 @@ class _SDFCUDA:
 
     def Close(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:  # lib can already be gone at interpreter shutdown
             lib.gsdf_program_destroy(h)
 
     __del__ = Close

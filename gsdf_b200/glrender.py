@@ -67,7 +67,7 @@ class _Renderer:
 
     def Close(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:
             lib.gsdf_mesh_destroy(h)
 
     __del__ = Close

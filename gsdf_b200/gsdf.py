@@ -85,7 +85,7 @@ class Builder:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:
             lib.gsdfh_builder_free(h)
 
     def Err(self):

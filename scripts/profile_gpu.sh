@@ -1,13 +1,11 @@
 #!/bin/bash
-# Run under gpurun (1 GPU): launch list of one bench run + full captures of the two heaviest kernels.
-set -x
+# Run under gpurun (1 GPU): launch list of one bench run + full captures of every kernel of the step.
+# Numbers printed by a run under ncu are never bench values.
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_eval -s 8 -c 2 -f -o gpurun_out/prof_eval \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_mc_emit -s 3 -c 1 -f -o gpurun_out/prof_emit \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_mc_count -s 3 -c 1 -f -o gpurun_out/prof_count \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+for k in "k_eval" "k_mc_emit" "k_mc_count" "k_compact_quads"; do
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 8 -c 2 -f -o gpurun_out/prof_$k \
+      python bench.py --steps 3 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+done
 ls -la gpurun_out
