@@ -58,7 +58,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -245,7 +245,8 @@ def run_cuda(args, rank, local_rank, world):
     # ---------------- Z-slab partition of ONE lattice across the ranks (north_star's layout; strong scaling)
     zslab = None
     if world > 1:
-        cuts = [(r * nz // world) // 4 * 4 if r else 0 for r in range(world)] + [nz]  # align to the 4-cell prune blocks
+        from gsdf_b200 import slab
+        cuts = slab.slab_cuts(nz, world)  # interior cuts aligned to the 4-cell prune blocks
         Rz = glrender.NewOctreeRenderer(sdf, res, 1 << 15, cz_range=(cuts[rank], cuts[rank + 1]))
         for _ in range(3):
             l2_flush(); Rz.Rerun()
@@ -331,7 +332,7 @@ def run_cuda(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

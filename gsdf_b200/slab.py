@@ -1,0 +1,53 @@
+"""Z-slab partition of one lattice across ranks (the reference's own CPU split is
+FlatRenderer.evalGrid's k-slabs, glrender/flatrenderer.go:120-122).
+
+Rank g of G meshes cells cz in [cuts[g], cuts[g+1]) and evaluates corner planes [cuts[g], cuts[g+1]] (one shared plane
+between neighbours). There is NO collective on the data path: every rank produces its own triangle buffer; buffers
+concatenated in rank order reproduce the single-device output (FlatRenderer cell order: z slowest). torch.distributed is
+used only to gather results / counts at the end when the caller wants them in one place.
+"""
+import numpy as np
+
+
+def slab_cuts(nz, world, align=4):
+    """Cell-layer cut points [0, ..., nz]: near-equal slabs, interior cuts aligned down to the 4-cell prune blocks so
+    no block is evaluated by two ranks. Ranks beyond the available layers get empty slabs (cut == next cut)."""
+    if nz <= 0 or world <= 0:
+        raise ValueError("nz and world must be positive")
+    cuts = [0]
+    for g in range(1, world):
+        c = (g * nz) // world
+        if align > 1:
+            c = (c // align) * align
+        cuts.append(max(c, cuts[-1]))
+    cuts.append(nz)
+    return cuts
+
+
+def rank_slab(nz, rank, world, align=4):
+    cuts = slab_cuts(nz, world, align)
+    return cuts[rank], cuts[rank + 1]
+
+
+def gather_triangles(local_tris, group=None, dst=0):
+    """Concatenate per-rank triangle arrays (n_i,3,3) on `dst` in rank order (= FlatRenderer cell order). Returns the
+    concatenated array on dst, None elsewhere. Uses torch.distributed (gloo or nccl); object gather keeps it backend
+    neutral -- this is result collection, not a data-path collective."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    parts = [None] * world if rank == dst else None
+    dist.gather_object(np.ascontiguousarray(local_tris, dtype=np.float32), parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return np.concatenate([p.reshape(-1, 3, 3) for p in parts]) if parts else np.zeros((0, 3, 3), np.float32)
+
+
+def total_count(n_local, group=None):
+    """Sum of per-rank counts (triangles, evaluations) via all_reduce on a CPU tensor (gloo) or CUDA tensor (nccl)."""
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([int(n_local)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, group=group)
+    return int(t.item())

@@ -950,15 +950,27 @@ int go_mc_cube(const float p[24], const float v[8], float tri9[45], int *case_in
 #define GLRENDER_SQRT3 1.73205080757
 
 /* flatrenderer.go:199-250 */
+int64_t go_flat_march_slab(const go_lattice *lat, const float *grid, float *tri9, int64_t max_tris, uint8_t *cases,
+                           const uint8_t *blockmask, int cz0, int cz1);
+
 int64_t go_flat_march(const go_lattice *lat, const float *grid, float *tri9, int64_t max_tris, uint8_t *cases,
                       const uint8_t *blockmask) {
+    return go_flat_march_slab(lat, grid, tri9, max_tris, cases, blockmask, 0, lat->n[2]);
+}
+
+/* Same sweep restricted to cell layers cz in [cz0,cz1): what one rank of the Z-slab partition produces (the
+ * reference's own split is evalGrid's k-slabs, flatrenderer.go:120-122). grid/cases/blockmask cover the WHOLE lattice. */
+int64_t go_flat_march_slab(const go_lattice *lat, const float *grid, float *tri9, int64_t max_tris, uint8_t *cases,
+                           const uint8_t *blockmask, int cz0, int cz1) {
     int nx = lat->n[0], ny = lat->n[1], nz = lat->n[2];
     size_t sy = (size_t)nx + 1, sz = sy * ((size_t)ny + 1);
     float r = lat->res;
     float cubeDiag = (float)(2 * GLRENDER_SQRT3) * r; /* Go folds 2*sqrt3 as a constant, then float32 multiply */
     int nbx = (nx + 3) / 4, nby = (ny + 3) / 4;
     int64_t ntri = 0;
-    for (int cz = 0; cz < nz; cz++)
+    if (cz0 < 0) cz0 = 0;
+    if (cz1 > nz) cz1 = nz;
+    for (int cz = cz0; cz < cz1; cz++)
         for (int cy = 0; cy < ny; cy++)
             for (int cx = 0; cx < nx; cx++) {
                 size_t ci = (size_t)cx + (size_t)nx * ((size_t)cy + (size_t)ny * cz);

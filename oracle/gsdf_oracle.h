@@ -6,7 +6,7 @@
  * CUDA path against it.  Nothing in the shipped product path (gsdf_b200/) may import, link or call it.
  *
  * PARITY PINNING STATUS
- *   pinned   : marching-cubes tables (checked against glrender/marchcubes.go:101-412 by tests/test_oracle_tables.py
+ *   pinned   : marching-cubes tables (checked against glrender/marchcubes.go:101-412 by tests/test_mc_tables.py
  *              when /root/reference is present), lattice formula (README.md:130 eval count 6,711,685+1),
  *              sphere KAT 41072 triangles (glrender/glrender_test.go:83-99), ISO thread sign KAT
  *              (forge/threads/threads_test.go:14-44), STL byte layout (glrender/stl.go:15-119).
@@ -104,6 +104,10 @@ int64_t go_flat_eval_grid(const go_tree *t, const go_lattice *lat, float *grid, 
  * returns number of triangles (counting continues past max_tris; only the first max_tris are stored). */
 int64_t go_flat_march(const go_lattice *lat, const float *grid, float *tri9, int64_t max_tris, uint8_t *cases,
                       const uint8_t *blockmask);
+
+/* The same sweep for cell layers [cz0,cz1) only (one rank's Z-slab); arrays still describe the whole lattice. */
+int64_t go_flat_march_slab(const go_lattice *lat, const float *grid, float *tri9, int64_t max_tris, uint8_t *cases,
+                           const uint8_t *blockmask, int cz0, int cz1);
 
 /* octreerenderer.go:180-191,240-284: the level-3 prune rule on the flat lattice.
  * mask gets ceil(n/4)^3 bytes (x fastest): 1 if |d(centre)| < size*sqrt3/2 for the 4-cell cube, else 0.

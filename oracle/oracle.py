@@ -60,6 +60,8 @@ def lib():
         L.go_flat_eval_grid.argtypes = [C.POINTER(GoTree), C.POINTER(GoLattice), vp, C.c_int, C.c_int]
         L.go_flat_march.restype = C.c_int64
         L.go_flat_march.argtypes = [C.POINTER(GoLattice), vp, vp, C.c_int64, vp, vp]
+        L.go_flat_march_slab.restype = C.c_int64
+        L.go_flat_march_slab.argtypes = [C.POINTER(GoLattice), vp, vp, C.c_int64, vp, vp, C.c_int, C.c_int]
         L.go_octree_prune_mask.restype = C.c_int64
         L.go_octree_prune_mask.argtypes = [C.POINTER(GoTree), C.POINTER(GoLattice), vp]
         L.go_mc_cube.restype = C.c_int
@@ -157,17 +159,19 @@ def octree_prune_mask(tree, lat):
     return mask, int(kept)
 
 
-def flat_march(lat, grid, want_cases=False, blockmask=None, max_tris=None):
-    """FlatRenderer.ReadTriangles sweep: returns (triangles (n,3,3), cases or None)."""
+def flat_march(lat, grid, want_cases=False, blockmask=None, max_tris=None, cz_range=None):
+    """FlatRenderer.ReadTriangles sweep: returns (triangles (n,3,3), cases or None). cz_range restricts the sweep to
+    one Z-slab of cell layers (grid / cases / blockmask still describe the whole lattice)."""
     nx, ny, nz = lat.n
+    cz0, cz1 = cz_range if cz_range is not None else (0, nz)
     grid = np.ascontiguousarray(grid, dtype=np.float32)
     cases = np.empty((nz, ny, nx), dtype=np.uint8) if want_cases else None
     mp = blockmask.ctypes.data if blockmask is not None else None
     cp = cases.ctypes.data if cases is not None else None
     if max_tris is None:
-        max_tris = lib().go_flat_march(C.byref(lat), grid.ctypes.data, None, 0, cp, mp)
+        max_tris = lib().go_flat_march_slab(C.byref(lat), grid.ctypes.data, None, 0, cp, mp, cz0, cz1)
     tris = np.empty((max(max_tris, 1), 3, 3), dtype=np.float32)
-    n = lib().go_flat_march(C.byref(lat), grid.ctypes.data, tris.ctypes.data, max_tris, cp, mp)
+    n = lib().go_flat_march_slab(C.byref(lat), grid.ctypes.data, tris.ctypes.data, max_tris, cp, mp, cz0, cz1)
     return tris[:min(n, max_tris)], cases
 
 
