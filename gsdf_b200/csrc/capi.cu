@@ -1,11 +1,13 @@
 // capi.cu -- implementation of the C ABI declared in include/gsdf_b200.h (device layer).
 // Handles own device buffers (grow-never-shrink) and one stream each; no CPU fallback exists: every compute entry
 // point fails with GSDF_ECUDA when no CUDA device is usable.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -388,12 +390,38 @@ struct gsdf_mesher {
     // device counters: [0] quad list length, [1] overflow flag, [2..3] total triangles (u64), [4] kept blocks
     uint32_t *d_ctr = nullptr;
     uint32_t *h_ctr = nullptr;  // pinned mirror
+    CUtensorMap tmap;             // 3-D view of d_grid for the TMA-staged classification
+    const float *tmap_grid = nullptr;
+    bool use_tma = true;
     uint64_t ntri = 0, evals = 0, pruned = 0, read_pos = 0;
     cudaEvent_t ev[5] = {};
     float ms[5] = {};
 };
 
 namespace {
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_grid_tensor_map(CUtensorMap *out, float *grid, int pitch, int rows, int planes) {
+    static encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return fail(GSDF_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        fn = (encode_tiled_fn)p;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * 4 * (cuuint64_t)rows};  // bytes, dims 1..2
+    const cuuint32_t box[3] = {(cuuint32_t)kBoxX, (cuuint32_t)kBoxY, (cuuint32_t)kBoxZ};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, grid, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(GSDF_ECUDA, "cuTensorMapEncodeTiled failed (%d) for a %d x %d x %d lattice", (int)r, pitch, rows, planes);
+    return 0;
+}
 
 unsigned grid_for(uint64_t items, int per_block, int waves = 8) {
     uint64_t b = (items + per_block - 1) / per_block;
@@ -472,7 +500,16 @@ int mesh_run(gsdf_mesher *m) {
     A.seg_list = m->d_seglist;
     A.seg_count = m->d_ctr + 5;
     const unsigned mcgrid = grid_for(nrows * (uint64_t)((D.nsx + 3) / 4), kThreads / 32, 16);
-    k_mc_count<<<mcgrid, kThreads, 0, st>>>(A);
+    if (m->use_tma) {
+        if (m->tmap_grid != m->d_grid) {  // (re)describe the lattice buffer: pitch x (ny+1) x nk floats
+            if ((rc = make_grid_tensor_map(&m->tmap, m->d_grid, D.pitch, D.ny + 1, nk))) return rc;
+            m->tmap_grid = m->d_grid;
+        }
+        const uint64_t ntiles = (uint64_t)((D.nsx + 3) / 4) * ((D.ny + kTileY - 1) / kTileY) * (D.cz1 - D.cz0);
+        k_mc_count_tma<<<grid_for(ntiles, 1, 16), 256, 0, st>>>(m->tmap, A);
+    } else {
+        k_mc_count<<<mcgrid, kThreads, 0, st>>>(A);
+    }
     CU(cudaGetLastError());
     k_scan_reduce<<<(unsigned)nscanblocks, kThreads, 0, st>>>(m->d_seg, nseg, m->d_blocksum);
     CU(cudaGetLastError());
@@ -534,6 +571,7 @@ int gsdf_mesh_begin(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, 
     m->prog = p;
     m->lat = *lat;
     m->flags = flags;
+    m->use_tma = getenv("GSDF_NO_TMA") == nullptr;  // A/B switch for the classification kernel
     MeshDims &D = m->D;
     D.nx = lat->n[0]; D.ny = lat->n[1]; D.nz = lat->n[2];
     D.cz0 = cz0; D.cz1 = cz1;

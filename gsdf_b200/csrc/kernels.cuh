@@ -15,6 +15,7 @@
 // The node program (+ side buffer when it fits) is staged into shared memory once per CTA by a 1-D bulk async copy
 // (cp.async.bulk.shared::cluster.global, completion on an mbarrier: SASS UBLKCP / SYNCS).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -503,6 +504,106 @@ __global__ void __launch_bounds__(kThreads) k_mc_count(MCArgs A) {
         if (threadIdx.x == 0) {
             uint32_t tot = 0;
             for (int w = 0; w < kThreads / 32; w++) { const uint32_t c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(A.seg_count, tot) : 0u;
+        }
+        __syncthreads();
+        if ((nz >> lane) & 1u) A.seg_list[s_base + s_cnt[warp] + __popc(nz & ((1u << lane) - 1u))] = s0 + lane;
+        __syncthreads();
+    }
+}
+
+// Pass 1, TMA form (default): one CTA per tile of 128 x 8 cells of one layer. The tile's 2 x 9 x 132 corner stencil is
+// fetched by ONE 3-D tensor copy (cp.async.bulk.tensor.3d -> SASS UTMALDG) into shared memory, completion on an
+// mbarrier; each of the 8 warps then classifies one cell row out of shared memory (8 conflict-free LDS per cell, no
+// global loads, every lattice value read from L2 once per tile instead of up to four times). Tiles whose 2 x 32 prune
+// blocks are all empty never issue the copy. Output is identical to k_mc_count.
+constexpr int kTileX = 128, kTileY = 8, kBoxX = 132, kBoxY = 9, kBoxZ = 2;
+__global__ void __launch_bounds__(256) k_mc_count_tma(const __grid_constant__ CUtensorMap tmap, MCArgs A) {
+    __shared__ __align__(128) float s_tile[kBoxZ][kBoxY][kBoxX];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint8_t s_ntri[256];
+    __shared__ uint32_t s_cnt[8];
+    __shared__ uint32_t s_base;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = A.t_ntri[i];
+    const uint32_t bar = smem_u32(&s_bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const MeshDims &D = A.D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ntx = (uint32_t)(D.nsx + 3) / 4, nty = (uint32_t)(D.ny + kTileY - 1) / kTileY, ntz = (uint32_t)(D.cz1 - D.cz0);
+    const uint32_t ntiles = ntx * nty * ntz;
+    uint32_t phase = 0;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t tx = tile % ntx, ty = (tile / ntx) % nty, tz = tile / (ntx * nty);
+        const int cz = D.cz0 + (int)tz, cy0 = (int)ty * kTileY;
+        // prune words of the (up to) two block rows this tile touches
+        uint32_t word0 = 0xffffffffu, word1 = 0xffffffffu;
+        if (A.mbits) {
+            const size_t rowb = ((size_t)((cz >> 2) - D.bz0) * D.nby + (cy0 >> 2)) * D.nwx + tx;
+            word0 = A.mbits[rowb];
+            word1 = ((cy0 >> 2) + 1 < D.nby) ? A.mbits[rowb + D.nwx] : 0u;
+        }
+        const bool active = (word0 | word1) != 0u;   // CTA-uniform
+        if (active) {
+            if (threadIdx.x == 0) {
+                const uint32_t bytes = kBoxZ * kBoxY * kBoxX * 4;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                        smem_u32(&s_tile[0][0][0])),
+                    "l"(&tmap), "r"((int)tx * kTileX), "r"(cy0), "r"((int)tz), "r"(bar)
+                    : "memory");
+            }
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "TW_LOOP:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@p bra TW_DONE;\n\t"
+                "bra TW_LOOP;\n\t"
+                "TW_DONE:\n\t"
+                "}" ::"r"(bar), "r"(phase)
+                : "memory");
+            phase ^= 1u;
+        }
+        // warp `warp` owns cell row cy of the tile
+        const int cy = cy0 + warp;
+        const uint32_t r = tz * (uint32_t)D.ny + (uint32_t)cy;
+        const uint32_t s0 = r * (uint32_t)D.nsx + tx * 4u;
+        const int nsg = cy < D.ny ? min(4, D.nsx - (int)tx * 4) : 0;
+        const uint32_t word = ((cy >> 2) == (cy0 >> 2)) ? word0 : word1;
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int sgm = 0; sgm < 4; sgm++) {
+            if (sgm >= nsg) break;
+            const int lx = 32 * sgm + lane, cx = (int)tx * kTileX + lx;
+            const uint32_t bits = (word >> (8 * sgm)) & 0xffu;
+            int index = 0;
+            uint32_t n = 0u;
+            if (bits != 0u) {  // warp-uniform
+                const bool act = cx < D.nx && ((bits >> (lane >> 2)) & 1u);
+                const float v0 = s_tile[0][warp][lx], v1 = s_tile[0][warp][lx + 1], v2 = s_tile[0][warp + 1][lx + 1], v3 = s_tile[0][warp + 1][lx];
+                const float v4 = s_tile[1][warp][lx], v5 = s_tile[1][warp][lx + 1], v6 = s_tile[1][warp + 1][lx + 1], v7 = s_tile[1][warp + 1][lx];
+                if (act && !(fabsf(v0) > A.cubeDiag))
+                    index = (v0 < 0.f ? 1 : 0) | (v1 < 0.f ? 2 : 0) | (v2 < 0.f ? 4 : 0) | (v3 < 0.f ? 8 : 0) | (v4 < 0.f ? 16 : 0) |
+                            (v5 < 0.f ? 32 : 0) | (v6 < 0.f ? 64 : 0) | (v7 < 0.f ? 128 : 0);
+                n = s_ntri[index];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+            }
+            if (A.cases && cx < D.nx) A.cases[(size_t)r * D.nx + cx] = (uint8_t)index;
+            if (lane == sgm) mine = n;
+        }
+        if (lane < nsg) A.segcount[s0 + lane] = mine;
+        const unsigned nz = __ballot_sync(0xffffffffu, lane < nsg && mine != 0u);
+        if (lane == 0) s_cnt[warp] = (uint32_t)__popc(nz);
+        __syncthreads();  // also: every warp is done reading s_tile before the next tile's copy may land
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < 8; w++) { const uint32_t c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
             s_base = tot ? atomicAdd(A.seg_count, tot) : 0u;
         }
         __syncthreads();
