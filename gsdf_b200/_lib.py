@@ -58,6 +58,8 @@ def _load():
         "gsdf_mesh_rerun": (C.c_int, [vp]),
         "gsdf_mesh_set_program": (C.c_int, [vp, vp]),
         "gsdf_mesh_read": (C.c_int64, [vp, vp, C.c_size_t]),
+        "gsdf_mesh_read_async": (C.c_int64, [vp, vp, C.c_size_t]),
+        "gsdf_mesh_wait": (C.c_int, [vp]),
         "gsdf_mesh_device_triangles": (C.c_int, [vp, C.POINTER(vp), u64p]),
         "gsdf_mesh_stats": (C.c_int, [vp, u64p, u64p, u64p]),
         "gsdf_mesh_cases": (C.c_int, [vp, vp, C.c_size_t]),

@@ -395,6 +395,7 @@ struct gsdf_mesher {
     bool use_tma = true;
     uint64_t ntri = 0, evals = 0, pruned = 0, read_pos = 0;
     cudaEvent_t ev[5] = {};
+    cudaStream_t copy_stream = nullptr;
     float ms[5] = {};
 };
 
@@ -433,6 +434,7 @@ int mesh_run(gsdf_mesher *m) {
     gsdf_program *p = m->prog;
     CU(cudaSetDevice(p->device));
     cudaStream_t st = p->stream;
+    if (m->copy_stream) CU(cudaStreamSynchronize(m->copy_stream));  // an earlier async read may still use d_tris
     const MeshDims &D = m->D;
     const bool prune = (m->flags & GSDF_MESH_PRUNE) != 0;
     const int nk = D.cz1 - D.cz0 + 1;
@@ -585,6 +587,7 @@ int gsdf_mesh_begin(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, 
     cudaError_t e = cudaMalloc((void **)&m->d_ctr, 8 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&m->h_ctr, 8 * sizeof(uint32_t));
     for (int i = 0; i < 5 && e == cudaSuccess; i++) e = cudaEventCreate(&m->ev[i]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { gsdf_mesh_destroy(m); return fail(GSDF_ECUDA, "mesher setup: %s", cudaGetErrorString(e)); }
     rc = mesh_run(m);
     if (rc) { gsdf_mesh_destroy(m); return rc; }
@@ -615,6 +618,26 @@ int64_t gsdf_mesh_read(gsdf_mesher *m, float *tri9, size_t max_tris) {
     CU(cudaMemcpy(tri9, m->d_tris + m->read_pos * 9, n * 9 * sizeof(float), cudaMemcpyDeviceToHost));
     m->read_pos += n;
     return (int64_t)n;
+}
+
+int64_t gsdf_mesh_read_async(gsdf_mesher *m, float *tri9, size_t max_tris) {
+    if (!m || !tri9) return fail(GSDF_EINVAL, "gsdf_mesh_read_async: NULL argument");
+    if (max_tris < 5) return fail(GSDF_ESHORT, "short buffer");
+    CU(cudaSetDevice(m->prog->device));
+    const uint64_t left = m->ntri - m->read_pos;
+    const uint64_t n = std::min<uint64_t>(left, max_tris);
+    if (n == 0) return 0;
+    CU(cudaStreamWaitEvent(m->copy_stream, m->ev[4], 0));  // emit of the last run has finished
+    CU(cudaMemcpyAsync(tri9, m->d_tris + m->read_pos * 9, n * 9 * sizeof(float), cudaMemcpyDeviceToHost, m->copy_stream));
+    m->read_pos += n;
+    return (int64_t)n;
+}
+
+int gsdf_mesh_wait(gsdf_mesher *m) {
+    if (!m) return fail(GSDF_EINVAL, "gsdf_mesh_wait: NULL mesher");
+    CU(cudaSetDevice(m->prog->device));
+    CU(cudaStreamSynchronize(m->copy_stream));
+    return 0;
 }
 
 int gsdf_mesh_device_triangles(gsdf_mesher *m, const float **d_tri9, uint64_t *ntri) {
@@ -666,6 +689,7 @@ void gsdf_mesh_destroy(gsdf_mesher *m) {
     cudaFree(m->d_tris); cudaFree(m->d_cases); cudaFree(m->d_stl); cudaFree(m->d_ctr);
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
     for (auto &e : m->ev) if (e) cudaEventDestroy(e);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     delete m;
 }
 

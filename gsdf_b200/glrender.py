@@ -136,6 +136,41 @@ class _Renderer:
         return buf[:n].tobytes()
 
 
+class SlabPipeline:
+    """One lattice split into `nslabs` Z-slabs on ONE device, each with its own renderer: the device->host copy of
+    slab i overlaps the kernels of slab i+1 (gsdf_mesh_read_async). Output = the slabs' triangles in slab order =
+    FlatRenderer cell order, identical to a single renderer's. The same split across ranks is the multi-GPU layout."""
+
+    def __init__(self, sdf, cubeResolution, nslabs=3, prune=True):
+        from . import slab as _slab
+        mn, mx = sdf.Bounds()
+        lat = lattice_from_bounds(mn, mx, cubeResolution)
+        cuts = _slab.slab_cuts(lat.n[2], nslabs)
+        cls = Octree if prune else FlatRenderer
+        self.parts = [cls(sdf, cubeResolution, cz_range=(a, b)) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        self.lat = lat
+
+    def NumTriangles(self):
+        return sum(p.NumTriangles() for p in self.parts)
+
+    def RenderToHost(self, dst):
+        """Re-render every slab and stream its triangles into dst (float32 (n,3,3), ideally pinned). Returns n."""
+        flat = dst.reshape(-1)
+        got = 0
+        for p in self.parts:
+            check(lib.gsdf_mesh_rerun(p._h))
+            cap = flat.size // 9 - got
+            n = check(lib.gsdf_mesh_read_async(p._h, C.c_void_p(flat[9 * got:].ctypes.data), max(cap, 5))) if p.NumTriangles() else 0
+            got += n
+        for p in self.parts:
+            check(lib.gsdf_mesh_wait(p._h))
+        return got
+
+    def Close(self):
+        for p in self.parts:
+            p.Close()
+
+
 class Octree(_Renderer):
     """glrender.Octree: marching cubes with level-3 cube pruning (octreerenderer.go:15-284)."""
     _flags = _lib.MESH_PRUNE

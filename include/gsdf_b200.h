@@ -109,6 +109,11 @@ int gsdf_mesh_set_program(gsdf_mesher *m, gsdf_program *p);
  * (9 floats each, vertex order as marchcubes.go:64-68) in FlatRenderer order (cell index x fastest,
  * flatrenderer.go:208-212). Returns the count (0 = io.EOF), GSDF_ESHORT if max_tris < 5. */
 int64_t gsdf_mesh_read(gsdf_mesher *m, float *tri9, size_t max_tris);
+/* Asynchronous form: enqueues the copy of up to max_tris triangles (from the current read position) on the mesher's
+ * copy stream and returns their count at once; tri9 must stay valid (and should be pinned) until gsdf_mesh_wait.
+ * Lets the device->host transfer of one slab overlap the kernels of the next one (separate meshers per slab). */
+int64_t gsdf_mesh_read_async(gsdf_mesher *m, float *tri9, size_t max_tris);
+int gsdf_mesh_wait(gsdf_mesher *m);
 /* Device pointer to the slab's triangle buffer (9 floats per triangle) and its count, for on-device consumers. */
 int gsdf_mesh_device_triangles(gsdf_mesher *m, const float **d_tri9, uint64_t *ntri);
 /* Evaluations() / Octree.TotalPruned() / len(triangles) (gsdfaux/gsdfaux.go:219-226). */

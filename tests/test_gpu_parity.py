@@ -415,3 +415,19 @@ def test_program_update_reuses_the_handle(oracle, bld):
     assert np.array_equal(bits(r.AllTriangles()), bits(wt))
     with pytest.raises(gsdf_b200.GsdfError):
         sdf.Update(bld.NewCircle(1.0))
+
+
+def test_slab_pipeline_equals_single_renderer(bld):
+    """glrender.SlabPipeline: slabs rendered one after the other with asynchronous reads reproduce the single renderer."""
+    s = gsdf.scene(bld, "npt-flange")
+    sdf = gleval.NewCUDASDF3(s)
+    res = np.float32(s.Diagonal() / np.float32(220))
+    whole = glrender.Octree(sdf, res).AllTriangles()
+    for nslabs in (1, 2, 3, 5):
+        pipe = glrender.SlabPipeline(sdf, res, nslabs=nslabs)
+        dst = np.zeros((len(whole) + 8, 3, 3), np.float32)
+        for _ in range(2):
+            n = pipe.RenderToHost(dst)
+            assert n == len(whole) == pipe.NumTriangles()
+            assert np.array_equal(bits(dst[:n]), bits(whole)), nslabs
+        pipe.Close()
