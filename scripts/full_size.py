@@ -12,7 +12,10 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
 b = gsdf.Builder()
 out = []
-for name, resdiv in [("npt-flange", 400), ("bolt", 800), ("knurled-cylinder", 1600)]:
+SCENES = [("npt-flange", 400), ("bolt", 800), ("knurled-cylinder", 1600)]
+if len(sys.argv) > 1:
+    SCENES = [x for x in SCENES if x[0] in sys.argv[1:]]
+for name, resdiv in SCENES:
     s = gsdf.scene(b, name)
     sdf = gleval.NewCUDASDF3(s)
     res = np.float32(s.Diagonal() / np.float32(resdiv))
@@ -42,6 +45,9 @@ for name, resdiv in [("npt-flange", 400), ("bolt", 800), ("knurled-cylinder", 16
         tot = slab.total_count(nt)
         rec["tris_all_ranks"] = tot
     print(json.dumps(rec), flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/full_size_w%d_r%d.jsonl" % (world, rank), "a") as f:
+        f.write(json.dumps(rec) + "\n")
     R.Close(); sdf.Close(); del tris
     torch.cuda.empty_cache()
 if world > 1:
