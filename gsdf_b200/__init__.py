@@ -4,11 +4,13 @@ Sub-modules mirror the reference's packages on that path:
     gsdf_b200.gsdf      gsdf.Builder, forge/threads, example scenes (host-side tree construction)
     gsdf_b200.gleval    gleval.SDF3 / SDF2 evaluators on the GPU
     gsdf_b200.glrender  Renderer / RenderAll / WriteBinarySTL / image evaluation
+    gsdf_b200.gsdfaux   RenderShader3D driver (the caller of the hot path)
+    gsdf_b200.slab      Z-slab partition helpers for one process per GPU
 
 Importing the package loads gsdf_b200/libgsdfb200.so and fails loudly if it has not been built.
 """
 from . import _lib  # noqa: F401  (raises ImportError with build instructions when the .so is missing)
-from . import gsdf, gleval, glrender  # noqa: F401
+from . import gsdf, gleval, glrender, gsdfaux, slab  # noqa: F401
 from ._lib import GsdfError, lib  # noqa: F401
 
 

@@ -52,6 +52,7 @@ def _load():
         "gsdf_eval3_device": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
         "gsdf_eval2_device": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
         "gsdf_lattice_from_bounds": (C.c_int, [f32p, f32p, C.c_float, C.POINTER(Lattice)]),
+        "gsdf_octree_levels": (C.c_int, [f32p, f32p, C.c_float]),
         "gsdf_grid_eval": (C.c_int, [vp, C.POINTER(Lattice), C.c_int, C.c_int, vp]),
         "gsdf_grid_eval_device": (C.c_int, [vp, C.POINTER(Lattice), C.c_int, C.c_int, vp, vp]),
         "gsdf_mesh_begin": (C.c_int, [vp, C.POINTER(Lattice), C.c_int, C.c_int, C.c_uint, C.POINTER(vp)]),

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -79,15 +80,15 @@ struct gsdf_program {
     size_t pos_cap = 0, dist_cap = 0;
     uint32_t *d_sched = nullptr;  // work-tile scheduler of k_eval (self-resetting)
     size_t blob_cap = 0;          // bytes allocated at d_blob
+    bool needs_ext = false;       // program contains ellipse2D / quadbezier2d -> EXT interpreter instantiation
 };
 
 namespace {
 
 // persistent launch: at most one resident wave of CTAs; they pull 256-item tiles from the program's scheduler
-template <int P, class Gen>
-int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st) {
-    if (nwork_upper_bound == 0) return 0;
-    auto kern = k_eval<P, Gen>;
+template <int P, class Gen, bool EXT>
+int launch_eval_impl(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st) {
+    auto kern = k_eval<P, Gen, EXT>;
     const uint32_t smem = smem_total_bytes<P>(p->pv, kEvalThreads);
     static thread_local uint32_t cached_smem = 0xffffffffu;
     static thread_local int cached_occ = 0;
@@ -105,6 +106,13 @@ int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_boun
     CU(cudaGetLastError());
     return 0;
 }
+// persistent launch: at most one resident wave of CTAs; they pull tiles from the program's scheduler
+template <int P, class Gen>
+int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st) {
+    if (nwork_upper_bound == 0) return 0;
+    return p->needs_ext ? launch_eval_impl<P, Gen, true>(p, gen, nwork_upper_bound, st)
+                        : launch_eval_impl<P, Gen, false>(p, gen, nwork_upper_bound, st);
+}
 
 int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_t aux_floats) {
     uint32_t pc = 0, n = 0;
@@ -112,7 +120,6 @@ int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_
     while (pc < h.nchunks) {
         const uint32_t w0 = chunks[4 * pc], op = w0 & 0xff, len = (w0 >> 8) & 0xff;
         if (op >= GSDF_OP__COUNT) return fail(GSDF_EPROGRAM, "instruction %u: unknown opcode %u", n, op);
-        if (op == GSDF_OP_ELLIPSE2D || op == GSDF_OP_BEZIERQ2D) return fail(GSDF_EPROGRAM, "instruction %u: opcode %u not implemented", n, op);
         if (len < 1 || pc + len > h.nchunks) return fail(GSDF_EPROGRAM, "instruction %u: bad length %u", n, len);
         static const uint8_t need2[] = {GSDF_OP_BOX, GSDF_OP_BOXFRAME, GSDF_OP_CYLINDER, GSDF_OP_HEX, GSDF_OP_DIAMOND2D, GSDF_OP_TRANSLATE,
                                         GSDF_OP_ROTATE2D, GSDF_OP_ELONGATE, GSDF_OP_ARRAY2D_VAR, GSDF_OP_CIRC_ENTER, GSDF_OP_SCREW_ENTER};
@@ -120,7 +127,7 @@ int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_
         uint32_t want = 1;
         for (uint8_t o : need2) if (o == op) want = 2;
         for (uint8_t o : need3) if (o == op) want = 3;
-        if (op == GSDF_OP_TRANSFORM) want = 4;
+        if (op == GSDF_OP_TRANSFORM || op == GSDF_OP_BEZIERQ2D) want = 4;
         if (len != want) return fail(GSDF_EPROGRAM, "instruction %u (opcode %u): length %u, expected %u", n, op, len, want);
         if (op == GSDF_OP_POLY2D) {
             const uint64_t off = chunks[4 * pc + 1], nv = chunks[4 * pc + 2];
@@ -194,6 +201,12 @@ static int upload_blob(gsdf_program *p, const gsdf_program_header &h, const uint
     CU(cudaStreamSynchronize(p->stream));  // the caller's buffers may go away after we return
     p->dim = (int)h.dim;
     p->ninstr = h.ninstr;
+    p->needs_ext = false;
+    for (uint32_t pc = 0; pc < h.nchunks;) {
+        const uint32_t op = chunks[4 * pc] & 0xff, len = (chunks[4 * pc] >> 8) & 0xff;
+        if (op == GSDF_OP_ELLIPSE2D || op == GSDF_OP_BEZIERQ2D) p->needs_ext = true;
+        pc += len ? len : 1;
+    }
     p->pv.g_prog = reinterpret_cast<const uint4 *>(p->d_blob);
     p->pv.prog_bytes = (uint32_t)prog_bytes;
     p->pv.aux_bytes = (uint32_t)aux_bytes;
@@ -307,6 +320,20 @@ int gsdf_lattice_from_bounds(const float bbmin[3], const float bbmax[3], float r
     }
     out->res = res;
     return 0;
+}
+
+int gsdf_octree_levels(const float bbmin[3], const float bbmax[3], float res) {
+    if (!bbmin || !bbmax) return fail(GSDF_EINVAL, "gsdf_octree_levels: NULL argument");
+    if (!(res > 0) || std::isinf(res)) return fail(GSDF_EINVAL, "invalid renderer cube resolution");  // octreerenderer.go:223
+    float longAxis = 0;
+    for (int a = 0; a < 3; a++) {
+        const float size = bbmax[a] - bbmin[a];
+        const float ns = 1.01f * size, c = bbmin[a] + size * 0.5f, half = ns * 0.5f;
+        longAxis = fmaxf(longAxis, (c + half) - (c - half));
+    }
+    const int levels = (int)ceilf(log2f(longAxis / res)) + 1;  // :229-231
+    if (levels <= 1) return fail(GSDF_ERES, "resolution not fine enough for marching cubes");
+    return levels;
 }
 
 static Lat make_lat(const gsdf_lattice *lat, int k0, int k1, int pitch, bool vec) {

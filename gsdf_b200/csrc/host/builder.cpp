@@ -193,6 +193,15 @@ NodeId Builder::Twist(NodeId s, float k) {
     return push(GSDF_N_TWIST, {k}, {s});
 }
 
+NodeId Builder::OverloadShader3DBounds(NodeId s, const Box3 &bb) {
+    if (!need3(s, "OverloadShader3DBounds")) return -1;
+    return push(GSDF_N_BOUNDS3, {bb.min.x, bb.min.y, bb.min.z, bb.max.x, bb.max.y, bb.max.z}, {s});
+}
+NodeId Builder::OverloadShader2DBounds(NodeId s, const Box2 &bb) {
+    if (!need2(s, "OverloadShader2DBounds")) return -1;
+    return push(GSDF_N_BOUNDS2, {bb.min.x, bb.min.y, bb.max.x, bb.max.y}, {s});
+}
+
 // ------------------------------------------------------------------ 2D -> 3D
 NodeId Builder::Extrude(NodeId s2, float h) {
     if (!need2(s2, "Extrude")) return -1;
@@ -285,6 +294,14 @@ NodeId Builder::NewDiamond2D(float w, float h) {
 NodeId Builder::NewRoundedX(float width, float thick) {
     if (!(width > 0 && thick > 0 && !isInfPos(width) && !isInfPos(thick))) shapeErrorf("bad x dimension");  // :603
     return push(GSDF_N_ROUNDX2D, {width, thick}, {});
+}
+
+NodeId Builder::NewEllipse(float a, float b) {
+    if (!(a > 0 && b > 0 && !isInfPos(a) && !isInfPos(b))) shapeErrorf("bad ellipse dimension");  // :422
+    return push(GSDF_N_ELLIPSE2D, {a, b}, {});
+}
+NodeId Builder::NewQuadraticBezier2D(Vec2 a, Vec2 b, Vec2 c, float thick) {  // :644 (no validation in the reference)
+    return push(GSDF_N_BEZIERQ2D, {a.x, a.y, b.x, b.y, c.x, c.y, thick}, {});
 }
 
 // ------------------------------------------------------------------ 2D operations (operations2d.go)
@@ -434,6 +451,7 @@ Box3 Builder::Bounds3(NodeId id) const {
         return b;
     }
     case GSDF_N_SHELL: return Bounds3(ch(0));  // :732
+    case GSDF_N_BOUNDS3: return {{f[0], f[1], f[2]}, {f[3], f[4], f[5]}};  // glbuild.go:1092
     case GSDF_N_CIRCARRAY: {  // :783
         Box3 bb = Bounds3(ch(0));
         Box2 bb2{{bb.min.x, bb.min.y}, {bb.max.x, bb.max.y}};
@@ -518,6 +536,23 @@ Box2 Builder::Bounds2(NodeId id) const {
         for (int i = 0; i + 1 < n.aux_cnt; i += 2) { mn = minElem(mn, {a[i], a[i + 1]}); mx = maxElem(mx, {a[i], a[i + 1]}); }
         return {mn, mx};
     }
+    case GSDF_N_BEZIERQ2D: {  // :648-672 (iquilezles.org/articles/bezierbbox)
+        Vec2 p0{f[0], f[1]}, p1{f[2], f[3]}, p2{f[4], f[5]};
+        Vec2 mn = minElem(p0, p2), mx = maxElem(p0, p2);
+        if (p1.x < mn.x || p1.x > mx.x || p1.y < mn.y || p1.y > mx.y) {
+            Vec2 denom = add(p0, sub(p2, scale(2, p1)));
+            Vec2 num = sub(p0, p1);
+            Vec2 t{m32::clampf(num.x / denom.x, 0.f, 1.f), m32::clampf(num.y / denom.y, 0.f, 1.f)};
+            Vec2 s_{1 - t.x, 1 - t.y};
+            Vec2 q1{s_.x * s_.x * p0.x, s_.y * s_.y * p0.y};
+            Vec2 q2{2 * (s_.x * t.x * p1.x), 2 * (s_.y * t.y * p1.y)};
+            Vec2 q3{p2.x * (t.x * t.x), p2.y * (t.y * t.y)};
+            Vec2 q = add(q1, add(q2, q3));
+            mn = minElem(mn, q); mx = maxElem(mx, q);
+        }
+        float h = f[6] / 2;
+        return {{mn.x + -h, mn.y + -h}, {mx.x + h, mx.y + h}};
+    }
     case GSDF_N_ROUNDX2D: {  // :610
         float xd2 = f[0] / 2 + f[1];
         return {{-xd2, -xd2}, {xd2, xd2}};
@@ -573,6 +608,7 @@ Box2 Builder::Bounds2(NodeId id) const {
         return bb;
     }
     case GSDF_N_SCALE2D: return Bounds2(ch(0)).scaleOrigin({f[0], f[0]});  // :728
+    case GSDF_N_BOUNDS2: return {{f[0], f[1]}, {f[2], f[3]}};              // glbuild.go:1117
     case GSDF_N_TRANSLATEMULTI2D: {  // :784
         Box2 bb{}, elem = Bounds2(ch(0));
         for (int i = 0; i + 1 < n.aux_cnt; i += 2) bb = bb.unionWith(elem.addVec({a[i], a[i + 1]}));

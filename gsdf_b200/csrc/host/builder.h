@@ -46,6 +46,8 @@ public:
     NodeId Shell(NodeId s, float thickness);                          // :723
     NodeId CircularArray(NodeId s, int numInstances, int circleDiv);  // :764
     NodeId Twist(NodeId s, float k);                                  // :835
+    NodeId OverloadShader3DBounds(NodeId s, const Box3 &bb);          // glbuild/glbuild.go:1080
+    NodeId OverloadShader2DBounds(NodeId s, const Box2 &bb);          // glbuild/glbuild.go:1105
     // ---- 2D -> 3D (operations2d.go) ----
     NodeId Extrude(NodeId s2, float h);                               // :104
     NodeId Revolve(NodeId s2, float axisOffset);                      // :149
@@ -63,6 +65,8 @@ public:
     NodeId NewPolygon(std::vector<Vec2> vertices);                          // :458 (+ validatePolygon :471)
     NodeId NewDiamond2D(float w, float h);                                  // :560
     NodeId NewRoundedX(float width, float thick);                           // :602
+    NodeId NewEllipse(float a, float b);                                    // :421
+    NodeId NewQuadraticBezier2D(Vec2 a, Vec2 b, Vec2 c, float thick);       // :644
     // ---- 2D operations (operations2d.go) ----
     NodeId Union2D(const std::vector<NodeId> &shaders);               // :18
     NodeId Difference2D(NodeId a, NodeId b);                          // :201

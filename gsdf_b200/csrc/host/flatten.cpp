@@ -144,6 +144,10 @@ struct Emitter {
             if (!emit(b.child(n, 0), restore, n.kind == GSDF_N_OFFSET2D)) return false;
             opf(GSDF_OP_OFFSET, f[0]);
             return true;
+        case GSDF_N_BOUNDS3:  // glbuild wrappers only change Bounds(); the flattener sees through them
+            return emit(b.child(n, 0), restore, false);
+        case GSDF_N_BOUNDS2:
+            return emit(b.child(n, 0), restore, true);
         case GSDF_N_ANNULUS2D:
             if (!emit(b.child(n, 0), restore, true)) return false;
             opf(GSDF_OP_ANNULUS, f[0]);
@@ -276,10 +280,20 @@ struct Emitter {
             popP();
             return true;
         }
-        case GSDF_N_ELLIPSE2D:
-        case GSDF_N_BEZIERQ2D:
-            err = "ellipse2D / quadbezier2d are not supported by the CUDA backend yet";
-            return false;
+        case GSDF_N_ELLIPSE2D: opf(GSDF_OP_ELLIPSE2D, f[0], f[1]); pushD(); return true;
+        case GSDF_N_BEZIERQ2D: {  // per-shape constants of cpu_evaluators.go:583-593
+            float Ax = f[0], Ay = f[1], Bx = f[2], By = f[3], Cx = f[4], Cy = f[5];
+            float ax = Bx - Ax, ay = By - Ay;
+            float a2 = ax * ax + ay * ay;
+            float bx = Ax + (Cx - 2 * Bx), by = Ay + (Cy - 2 * By);
+            float cx = 2 * ax, cy = 2 * ay;
+            float kk = 1.f / (bx * bx + by * by);
+            float kx = kk * (ax * bx + ay * by);
+            header(GSDF_OP_BEZIERQ2D, 4, 0, fbits(f[6] / 2), 0);
+            chunk(Ax, Ay, ax, ay); chunk(bx, by, cx, cy); chunk(kk, kx, kx * kx, a2);
+            pushD();
+            return true;
+        }
         }
         err = "unknown node kind";
         return false;

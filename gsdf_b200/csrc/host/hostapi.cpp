@@ -86,6 +86,8 @@ int32_t gsdfh_node(gsdfh_builder *hb, int32_t kind, const float *f, int nf, cons
     case GSDF_N_SHELL: return b.Shell(C(0), F(0));
     case GSDF_N_CIRCARRAY: return b.CircularArray(C(0), I(0), I(1));
     case GSDF_N_TWIST: return b.Twist(C(0), F(0));
+    case GSDF_N_BOUNDS3: return b.OverloadShader3DBounds(C(0), Box3{{F(0), F(1), F(2)}, {F(3), F(4), F(5)}});
+    case GSDF_N_BOUNDS2: return b.OverloadShader2DBounds(C(0), Box2{{F(0), F(1)}, {F(2), F(3)}});
     case GSDF_N_EXTRUDE: return b.Extrude(C(0), F(0));
     case GSDF_N_REVOLVE: return b.Revolve(C(0), F(0));
     case GSDF_N_SCREW: return b.NewScrew(C(0), F(0), F(1), F(2), F(3));  // pitch, lead, length, taper
@@ -100,6 +102,8 @@ int32_t gsdfh_node(gsdfh_builder *hb, int32_t kind, const float *f, int nf, cons
     case GSDF_N_POLY2D: return b.NewPolygon(pts());
     case GSDF_N_DIAMOND2D: return b.NewDiamond2D(F(0), F(1));
     case GSDF_N_ROUNDX2D: return b.NewRoundedX(F(0), F(1));
+    case GSDF_N_ELLIPSE2D: return b.NewEllipse(F(0), F(1));
+    case GSDF_N_BEZIERQ2D: return b.NewQuadraticBezier2D(Vec2{F(0), F(1)}, Vec2{F(2), F(3)}, Vec2{F(4), F(5)}, F(6));
     case GSDF_N_UNION2D: return b.Union2D(kids());
     case GSDF_N_DIFF2D: return b.Difference2D(C(0), C(1));
     case GSDF_N_INTERSECT2D: return b.Intersection2D(C(0), C(1));

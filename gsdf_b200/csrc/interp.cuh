@@ -72,7 +72,10 @@ __device__ __forceinline__ float4 ldf4(const uint4 *prog, int i) {
 }
 
 // Runs the program at the P positions already loaded in m.px/py/pz; result in m.top.
-template <int P>
+// EXT selects the instantiation that also carries the rarely used heavy 2-D primitives (ellipse2D, quadbezier2d: double
+// precision cbrt, exp/log). Keeping them out of the default kernel matters: with them compiled in, the kernel needs a
+// real call stack and the common path slows down by ~20 % (measured); programs that contain them run the EXT kernel.
+template <int P, bool EXT>
 __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restrict__ prog, const float4 *__restrict__ aux) {
     using namespace m32;
     int pc = 0;
@@ -273,6 +276,90 @@ __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restri
                 float x = absf(m.px[j]), y = absf(m.py[j]);
                 float sub = 0.5f * minf(x + y, f2);
                 m.top[j] = norm2(x - sub, y - sub) - f3;
+            }
+        } break;
+        case GSDF_OP_ELLIPSE2D: if constexpr (EXT) {  // :750-791  f2=a f3=b
+            const float sq3 = (float)1.7320508075688772935274463415058723669428052538103806280558069794;
+            m.pushD();
+#pragma unroll 1
+            for (int j = 0; j < P; j++) {
+                float a = f2, b = f3;
+                float x = absf(m.px[j]), y = absf(m.py[j]);
+                if (x > y) { float t = x; x = y; y = t; t = a; a = b; b = t; }
+                const float l = b * b - a * a;
+                const float mm = a * x / l, m2 = mm * mm;
+                const float nn = b * y / l, n2 = nn * nn;
+                const float c = (m2 + n2 - 1.f) / 3.f;
+                const float c3 = c * c * c;
+                const float q = c3 + 2.f * m2 * n2;
+                const float d = c3 + m2 * n2;
+                const float g = mm + mm * n2;
+                float co;
+                if (d < 0.f) {
+                    const float hh = m32::acos(q / c3) / 3.f;
+                    float sh, ch;
+                    m32::sincos(hh, sh, ch);
+                    const float t = sq3 * sh;
+                    const float rx = m32::sqrt(-c * (ch + t + 2.f) + m2);
+                    const float ry = m32::sqrt(-c * (ch - t + 2.f) + m2);
+                    co = (ry + signf(l) * rx + absf(g) / (rx * ry) - mm) / 2.f;
+                } else {
+                    const float hh = 2.f * mm * nn * m32::sqrt(d);
+                    const float s_ = signf(q + hh) * m32::cbrt32(absf(q + hh));
+                    const float u = signf(q - hh) * m32::cbrt32(absf(q - hh));
+                    const float rx = -s_ - u - 4.f * c + 2.f * m2;
+                    const float ry = sq3 * (s_ - u);
+                    const float rm = hypot32(rx, ry);
+                    co = (ry / m32::sqrt(rm - rx) + 2.f * g / rm - mm) / 2.f;
+                }
+                const float rx2 = a * co, ry2 = b * m32::sqrt(1.f - co * co);
+                m.top[j] = norm2(rx2 - x, ry2 - y) * signf(y - ry2);
+            }
+        } break;
+        case GSDF_OP_BEZIERQ2D: if constexpr (EXT) {  // :581-659  c1=(Ax,Ay,ax,ay) c2=(bx,by,cx,cy) c3=(kk,kx,kx2,a2) w2=thick/2
+            const float sq3 = (float)1.7320508075688772935274463415058723669428052538103806280558069794;
+            const float4 c1 = ldf4(prog, pc + 1), c2 = ldf4(prog, pc + 2), c3 = ldf4(prog, pc + 3);
+            const float third = (float)(1. / 3);
+            m.pushD();
+#pragma unroll 1
+            for (int j = 0; j < P; j++) {
+                const float dx = c1.x - m.px[j], dy = c1.y - m.py[j];
+                const float ky = c3.x * (2.f * c3.w + (dx * c2.x + dy * c2.y)) / 3.f;
+                const float kz = c3.x * (dx * c1.z + dy * c1.w);
+                const float g = ky - c3.z;
+                const float q = c3.y * (2.f * c3.z - 3.f * ky) + kz;
+                const float g3 = g * g * g;
+                const float q2 = q * q;
+                float hh = q2 + 4.f * g3;
+                float res;
+                if (hh >= 0.f) {
+                    hh = m32::sqrt(hh);
+                    float xx = 0.5f * (hh + -q), xy = 0.5f * (-hh + -q);
+                    if (absf(g) < 0.001f) {
+                        const float k = (1.0f - g3 / q2) * g3 / q;
+                        xx = k; xy = -k - q;
+                    }
+                    const float ux = signf(xx) * m32::pow_frac(absf(xx), third);
+                    const float uy = signf(xy) * m32::pow_frac(absf(xy), third);
+                    float t = ux + uy;
+                    t -= (t * (t * t + 3.0f * g) + q) / (3.0f * t * t + 3.0f * g);
+                    t = clampf(t - c3.y, 0.f, 1.f);
+                    const float wx = dx + t * (c2.z + t * c2.x), wy = dy + t * (c2.w + t * c2.y);
+                    res = wx * wx + wy * wy;
+                } else {
+                    const float z = m32::sqrt(-g);
+                    const float xm = m32::sqrt(0.5f + 0.5f * (q / (2.f * g * z)));  // cos_acos_3, gsdf.go:186-189
+                    const float mm = xm * (xm * (xm * (xm * -0.008972f + 0.039071f) - 0.107074f) + 0.576975f) + 0.5f;
+                    float nn = m32::sqrt(1.f - mm * mm);
+                    nn *= sq3;
+                    const float tx = clampf((mm + mm) * z - c3.y, 0.f, 1.f);
+                    const float ty = clampf((-nn - mm) * z - c3.y, 0.f, 1.f);
+                    const float qxx = dx + tx * (c2.z + tx * c2.x), qxy = dy + tx * (c2.w + tx * c2.y);
+                    const float qyx = dx + ty * (c2.z + ty * c2.x), qyy = dy + ty * (c2.w + ty * c2.y);
+                    const float ddx = qxx * qxx + qxy * qxy, ddy = qyx * qyx + qyy * qyy;
+                    res = ddx < ddy ? ddx : ddy;
+                }
+                m.top[j] = m32::sqrt(res) - f2;
             }
         } break;
         case GSDF_OP_POLY2D: {  // :793-818; aux records (v1x,v1y,ex,ey | norm2e,v2y,_,_)

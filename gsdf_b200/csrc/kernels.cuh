@@ -80,7 +80,7 @@ __host__ __device__ inline uint32_t smem_total_bytes(const ProgView &pv, int thr
     return smem_stage_bytes(pv) + 16u + (uint32_t)threads * P * 4u * (pv.dslots + 3u * pv.pslots);
 }
 
-template <int P, class Gen>
+template <int P, class Gen, bool EXT>
 __global__ void __launch_bounds__(kEvalThreads) k_eval(ProgView pv, Gen gen) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t stage = smem_stage_bytes(pv);
@@ -106,13 +106,13 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval(ProgView pv, Gen gen) {
         const uint64_t wc = w < nwork ? w : nwork - 1;
         m.init(dstk, pstk, blockDim.x);
         gen.load(wc, m.px, m.py, m.pz);
-        run_program<P>(m, prog, aux);
+        run_program<P, EXT>(m, prog, aux);
         if (w < nwork) gen.store(w, m.top);
 #else
         if (w >= nwork) continue;
         m.init(dstk, pstk, blockDim.x);
         gen.load(w, m.px, m.py, m.pz);
-        run_program<P>(m, prog, aux);
+        run_program<P, EXT>(m, prog, aux);
         gen.store(w, m.top);
 #endif
     }

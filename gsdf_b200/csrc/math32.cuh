@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #define M32_HD __host__ __device__ __forceinline__
 // Large helpers (hypot, atan2, sincos) can be kept out of line to shrink the interpreter's instruction footprint
@@ -225,5 +226,103 @@ M32_HD float asin(float x) {
     return sign ? -temp : temp;
 }
 M32_HD float acos(float x) { return add((float)(kPi / 2), -asin(x)); }
+
+// math32.Cbrt restated as FreeBSD's cbrtf: integer seed, two Newton steps in double precision, one rounding to float32.
+// Double arithmetic uses explicit round-to-nearest intrinsics on the device so nothing is contracted.
+M32_HD float cbrt32(float x) {
+    uint32_t hx;
+#ifdef __CUDA_ARCH__
+    hx = __float_as_uint(x);
+#else
+    memcpy(&hx, &x, 4);
+#endif
+    const uint32_t sign = hx & 0x80000000u;
+    hx ^= sign;
+    if (hx >= 0x7f800000u) return add(x, x);
+    float t;
+    if (hx < 0x00800000u) {
+        if (hx == 0u) return x;
+        uint32_t w = 0x4b800000u;  // 2**24
+#ifdef __CUDA_ARCH__
+        t = mul(__uint_as_float(w), x);
+        w = sign | ((__float_as_uint(t) & 0x7fffffffu) / 3u + 642849266u);
+        t = __uint_as_float(w);
+#else
+        memcpy(&t, &w, 4); t *= x; memcpy(&w, &t, 4);
+        w = sign | ((w & 0x7fffffffu) / 3u + 642849266u);
+        memcpy(&t, &w, 4);
+#endif
+    } else {
+        const uint32_t w = sign | (hx / 3u + 709958130u);
+#ifdef __CUDA_ARCH__
+        t = __uint_as_float(w);
+#else
+        memcpy(&t, &w, 4);
+#endif
+    }
+#ifdef __CUDA_ARCH__
+    const double xd = (double)x;
+    double T = (double)t, r = __dmul_rn(__dmul_rn(T, T), T);
+    T = __ddiv_rn(__dmul_rn(T, __dadd_rn(__dadd_rn(xd, xd), r)), __dadd_rn(__dadd_rn(xd, r), r));
+    r = __dmul_rn(__dmul_rn(T, T), T);
+    T = __ddiv_rn(__dmul_rn(T, __dadd_rn(__dadd_rn(xd, xd), r)), __dadd_rn(__dadd_rn(xd, r), r));
+    return (float)T;
+#else
+    double T = t, r = T * T * T;
+    T = T * ((double)x + x + r) / (x + r + r);
+    r = T * T * T;
+    T = T * ((double)x + x + r) / (x + r + r);
+    return (float)T;
+#endif
+}
+
+// math32 log.go / exp.go (ports of Go's math.Log / math.Exp), float32 arithmetic.
+M32_HD float log32(float x) {
+    const float Ln2Hi = 6.93147180369123816490e-01f, Ln2Lo = 1.90821492927058770002e-10f;
+    const float L1 = 6.666666666666735130e-01f, L2 = 3.999999999940941908e-01f, L3 = 2.857142874366239149e-01f,
+                L4 = 2.222219843214978396e-01f, L5 = 1.818357216161805012e-01f, L6 = 1.531383769920937332e-01f,
+                L7 = 1.479819860511658591e-01f;
+    if (x != x || (isinf(x) && x > 0.f)) return x;
+    if (x < 0.f) return NAN;
+    if (x == 0.f) return -INFINITY;
+    int ki;
+    float f1 = frexpf(x, &ki);
+    if (f1 < (float)(1.41421356237309504880168872420969808 / 2)) { f1 = mul(f1, 2.f); ki--; }
+    const float f = add(f1, -1.f);
+    const float k = (float)ki;
+    const float s_ = div(f, add(2.f, f));
+    const float s2 = mul(s_, s_);
+    const float s4 = mul(s2, s2);
+    const float t1 = mul(s2, add(L1, mul(s4, add(L3, mul(s4, add(L5, mul(s4, L7)))))));
+    const float t2 = mul(s4, add(L2, mul(s4, add(L4, mul(s4, L6)))));
+    const float R = add(t1, t2);
+    const float hfsq = mul(mul(0.5f, f), f);
+    return add(mul(k, Ln2Hi), -add(add(hfsq, -add(mul(s_, add(hfsq, R)), mul(k, Ln2Lo))), -f));
+}
+M32_HD float exp32(float x) {
+    const float Ln2Hi = 6.93147180369123816490e-01f, Ln2Lo = 1.90821492927058770002e-10f, Log2e = 1.44269504088896338700e+00f;
+    const float P1 = 1.66666666666666657415e-01f, P2 = -2.77777777770155933842e-03f, P3 = 6.61375632143793436117e-05f,
+                P4 = -1.65339022054652515390e-06f, P5 = 4.13813679705723846039e-08f;
+    if (x != x || (isinf(x) && x > 0.f)) return x;
+    if (isinf(x)) return 0.f;
+    if (x > 88.72283905206835f) return INFINITY;
+    if (x < -103.97207708f) return 0.f;
+    int k = 0;
+    if (x < 0.f) k = (int)add(mul(Log2e, x), -0.5f);
+    else if (x > 0.f) k = (int)add(mul(Log2e, x), 0.5f);
+    const float hi = add(x, -mul((float)k, Ln2Hi));
+    const float lo = mul((float)k, Ln2Lo);
+    const float r = add(hi, -lo);
+    const float t = mul(r, r);
+    const float c = add(r, -mul(t, add(P1, mul(t, add(P2, mul(t, add(P3, mul(t, add(P4, mul(t, P5))))))))));
+    const float y = add(1.f, -add(add(lo, -div(mul(r, c), add(2.f, -c))), -hi));
+    return ldexpf(y, k);
+}
+// math32.Pow(x, y) for x >= 0, 0 < y < 0.5: Exp(y*Log(x)) (Go pow.go with yi = 0).
+M32_HD float pow_frac(float x, float y) {
+    if (x == 0.f) return 0.f;
+    if (x == 1.f) return 1.f;
+    return exp32(mul(y, log32(x)));
+}
 
 }  // namespace m32

@@ -181,9 +181,17 @@ class FlatRenderer(_Renderer):
     _flags = 0
 
 
+def octree_levels(bbmin, bbmax, res):
+    """makeICube's level count (octreerenderer.go:222-235); raises for a resolution too coarse to march."""
+    mn = (C.c_float * 3)(*[float(v) for v in bbmin])
+    mx = (C.c_float * 3)(*[float(v) for v in bbmax])
+    return check(lib.gsdf_octree_levels(mn, mx, float(res)))
+
+
 def NewOctreeRenderer(s, cubeResolution, evalBufferSize=64, **kw):
     if evalBufferSize < 64:
         raise GsdfError(_lib.EINVAL, "bad octree eval buffer size")  # octreerenderer.go:46
+    octree_levels(*s.Bounds(), cubeResolution)  # early error check, octreerenderer.go:50-53
     return Octree(s, cubeResolution, evalBufferSize, **kw)
 
 
@@ -232,7 +240,25 @@ def ReadBinarySTL(r):
     if len(data) < 84 + 50 * count:
         raise GsdfError(_lib.EINVAL, "%d/%d STL triangles read: unexpected EOF" % ((len(data) - 84) // 50, count))
     rec = np.frombuffer(data, dtype=np.uint8, count=50 * count, offset=84).reshape(count, 50)
-    return rec[:, 12:48].copy().view(np.float32).reshape(count, 3, 3)
+    tris = rec[:, 12:48].copy().view(np.float32).reshape(count, 3, 3)
+    normals = rec[:, 0:12].copy().view(np.float32).reshape(count, 3)
+    # stlTriangle.validate (stl.go:129-150): inf/NaN and degenerate triangles are errors; a stored normal that is
+    # neither +n nor -n of the vertices (tolerance 5e-2) is counted, more than 10,000 of them is an error (:207-214).
+    if not np.isfinite(normals).all():
+        raise GsdfError(_lib.EINVAL, "inf/NaN STL triangle normal")
+    if not np.isfinite(tris).all():
+        raise GsdfError(_lib.EINVAL, "inf/NaN STL triangle vertex")
+    v = tris.astype(np.float64) * 10.0
+    calc = np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0])
+    ln = np.linalg.norm(calc, axis=1)
+    degenerate = ln <= 1e-12
+    if degenerate.any():
+        raise GsdfError(_lib.EINVAL, "%d/%d STL triangles read: triangle is degenerate" % (int(np.argmax(degenerate)) + 1, count))
+    calc /= ln[:, None]
+    bad = ~((np.abs(calc - normals) <= 5e-2).all(axis=1) | (np.abs(-calc - normals) <= 5e-2).all(axis=1))
+    if int(bad.sum()) > 10000:
+        raise GsdfError(_lib.EINVAL, "got too many normal vector mismatches (%d)" % int(bad.sum()))
+    return tris
 
 
 def ImageEvaluateSDF2(sdf2, width, height):

@@ -16,12 +16,12 @@ from ._lib import lib
 K = dict(
     SPHERE=1, BOX=2, CYLINDER=3, HEX=4, TORUS=5, BOXFRAME=6,
     UNION=16, DIFF=17, INTERSECT=18, XOR=19, SMOOTH_UNION=20, SMOOTH_DIFF=21, SMOOTH_INTERSECT=22, SCALE=23,
-    SYMMETRY=24, TRANSFORM=25, TRANSLATE=26, OFFSET=27, ARRAY=28, ELONGATE=29, SHELL=30, CIRCARRAY=31, TWIST=32,
+    SYMMETRY=24, TRANSFORM=25, TRANSLATE=26, OFFSET=27, ARRAY=28, ELONGATE=29, SHELL=30, CIRCARRAY=31, TWIST=32, BOUNDS3=33,
     EXTRUDE=40, REVOLVE=41, SCREW=42,
     LINE2D=64, LINES2D=65, ARC2D=66, CIRCLE2D=67, EQTRI2D=68, RECT2D=69, HEX2D=70, OCT2D=71, ELLIPSE2D=72, POLY2D=73,
     DIAMOND2D=74, ROUNDX2D=75, BEZIERQ2D=76,
     UNION2D=96, DIFF2D=97, INTERSECT2D=98, XOR2D=99, ARRAY2D=100, OFFSET2D=101, TRANSLATE2D=102, ROTATE2D=103,
-    SYMMETRY2D=104, ANNULUS2D=105, CIRCARRAY2D=106, SCALE2D=107, TRANSLATEMULTI2D=108, ELONGATE2D=109,
+    SYMMETRY2D=104, ANNULUS2D=105, CIRCARRAY2D=106, SCALE2D=107, TRANSLATEMULTI2D=108, ELONGATE2D=109, BOUNDS2=110,
     CALL_ROTATE=200, CALL_TRANSFORM16=201, CALL_TRIPRISM=202, CALL_BOUNDSBOXFRAME=203,
 )
 
@@ -147,6 +147,10 @@ class Builder:
     def CircularArray(self, s, numInstances, circleDiv): return self._node("CIRCARRAY", ip=[numInstances, circleDiv], children=[s])
     def Twist(self, s, k): return self._node("TWIST", [k], children=[s])
 
+    # ------------------------------------------------------------------ glbuild wrappers (glbuild/glbuild.go:1080-1128)
+    def OverloadShader3DBounds(self, s, bbmin, bbmax): return self._node("BOUNDS3", list(bbmin) + list(bbmax), children=[s])
+    def OverloadShader2DBounds(self, s, bbmin, bbmax): return self._node("BOUNDS2", list(bbmin) + list(bbmax), children=[s])
+
     # ------------------------------------------------------------------ 2D -> 3D (operations2d.go)
     def Extrude(self, s, h): return self._node("EXTRUDE", [h], children=[s])
     def Revolve(self, s, axisOffset): return self._node("REVOLVE", [axisOffset], children=[s])
@@ -163,6 +167,8 @@ class Builder:
     def NewPolygon(self, vertices): return self._node("POLY2D", aux=np.asarray(vertices, dtype=np.float32))
     def NewDiamond2D(self, x_width, y_height): return self._node("DIAMOND2D", [x_width, y_height])
     def NewRoundedX(self, width, thick): return self._node("ROUNDX2D", [width, thick])
+    def NewEllipse(self, a, b): return self._node("ELLIPSE2D", [a, b])
+    def NewQuadraticBezier2D(self, a, b, c, thick): return self._node("BEZIERQ2D", [a[0], a[1], b[0], b[1], c[0], c[1], thick])
 
     # ------------------------------------------------------------------ 2D operations (operations2d.go)
     def Union2D(self, *shaders): return self._node("UNION2D", children=shaders)

@@ -83,6 +83,9 @@ typedef struct {
 
 /* FlatRenderer.Reset's lattice (glrender/flatrenderer.go:47-56): bb*1.01, n=ceil(size/res). GSDF_ERES if n<=0. */
 int gsdf_lattice_from_bounds(const float bbmin[3], const float bbmax[3], float res, gsdf_lattice *out);
+/* makeICube's level count (glrender/octreerenderer.go:222-235): ceil(log2(longAxis/res))+1 on the 1.01-scaled box;
+ * GSDF_ERES when it is <= 1 ("resolution not fine enough for marching cubes"), GSDF_EINVAL for res <= 0 / NaN / Inf. */
+int gsdf_octree_levels(const float bbmin[3], const float bbmax[3], float res);
 /* FlatRenderer.evalGrid / evalKRange (glrender/flatrenderer.go:103-182) for corner planes k in [k0,k1):
  * positions origin + float32(i)*res are synthesised in-kernel; (n0+1)*(n1+1)*(k1-k0) distances, x fastest, are
  * written to `dist` (HOST pointer) or, if dist is NULL, only computed (timing). */

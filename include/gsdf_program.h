@@ -51,8 +51,8 @@ enum gsdf_opcode {
     GSDF_OP_DIAMOND2D,   /* :694  c1=(bx,by,dot(b,b),_) */
     GSDF_OP_ROUNDX2D,    /* :705  w2=w w3=r */
     GSDF_OP_POLY2D,      /* :793  w1=aux_off w2=nverts ; aux: (v1x,v1y,ex,ey,norm2e,v2y,_,_) per edge (8 floats) */
-    GSDF_OP_ELLIPSE2D,   /* :750  reserved */
-    GSDF_OP_BEZIERQ2D,   /* :581  reserved */
+    GSDF_OP_ELLIPSE2D,   /* :750  w2=a w3=b */
+    GSDF_OP_BEZIERQ2D,   /* :581  w2=thick/2 c1=(Ax,Ay,ax,ay) c2=(bx,by,cx,cy) c3=(kk,kx,kx2,a2) */
     /* ---- distance combiners: b=top, a=below, top=f(a,b) ---- */
     GSDF_OP_MIN,         /* :14,124,821  union fold */
     GSDF_OP_MAX,         /* :146,847     intersect */

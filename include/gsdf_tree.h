@@ -37,6 +37,7 @@ enum gsdf_node_kind {
     GSDF_N_SHELL,        /* :727  thick                                                   */
     GSDF_N_CIRCARRAY,    /* :777  iparam nInst, circleDiv                                 */
     GSDF_N_TWIST,        /* :845  k                                                       */
+    GSDF_N_BOUNDS3,      /* glbuild/glbuild.go:1080-1102 overloadBounds3: bb min.xyz, max.xyz ; Evaluate forwards */
     /* 2D -> 3D */
     GSDF_N_EXTRUDE = 40, /* operations2d.go:114  h                                        */
     GSDF_N_REVOLVE,      /* operations2d.go:163  off                                      */
@@ -69,7 +70,8 @@ enum gsdf_node_kind {
     GSDF_N_CIRCARRAY2D,  /* :668  iparam nInst, circleDiv                                 */
     GSDF_N_SCALE2D,      /* :723  scale                                                   */
     GSDF_N_TRANSLATEMULTI2D, /* :767 aux = (x,y) per displacement                         */
-    GSDF_N_ELONGATE2D    /* :816  h.xy                                                    */
+    GSDF_N_ELONGATE2D,   /* :816  h.xy                                                    */
+    GSDF_N_BOUNDS2       /* glbuild/glbuild.go:1105-1128 overloadBounds2: bb min.xy, max.xy ; Evaluate forwards */
 };
 
 typedef struct {

@@ -169,6 +169,97 @@ float go_tan(float x) {
     return sign ? -y : y;
 }
 
+/* math32 asin.go: Asin via Sqrt + satan; Acos = Pi/2 - Asin. */
+static float go_asin(float x) {
+    if (x == 0) return x;
+    int sign = 0;
+    if (x < 0) { x = -x; sign = 1; }
+    if (x > 1) return NAN;
+    float temp = sqrtf(1 - x * x);
+    if (x > 0.7f) temp = (float)(GO_PI / 2) - go_satan(temp / x);
+    else temp = go_satan(x / temp);
+    return sign ? -temp : temp;
+}
+float go_acos(float x) { return (float)(GO_PI / 2) - go_asin(x); }
+
+/* math32.Cbrt restated as FreeBSD's cbrtf (integer seed + two double-precision Newton steps, result rounded once to
+ * float32): pure arithmetic, so the CUDA side can run the identical sequence. UNPINNED against math32's own choice. */
+float go_cbrt(float x) {
+    uint32_t hx;
+    memcpy(&hx, &x, 4);
+    const uint32_t sign = hx & 0x80000000u;
+    hx ^= sign;
+    if (hx >= 0x7f800000u) return x + x;
+    float t;
+    if (hx < 0x00800000u) {
+        if (hx == 0) return x;
+        uint32_t two24 = 0x4b800000u, high;
+        memcpy(&t, &two24, 4);
+        t *= x;
+        memcpy(&high, &t, 4);
+        high = sign | ((high & 0x7fffffffu) / 3 + 642849266u);
+        memcpy(&t, &high, 4);
+    } else {
+        uint32_t w = sign | (hx / 3 + 709958130u);
+        memcpy(&t, &w, 4);
+    }
+    double T = t, r = T * T * T;
+    T = T * ((double)x + x + r) / (x + r + r);
+    r = T * T * T;
+    T = T * ((double)x + x + r) / (x + r + r);
+    return (float)T;
+}
+
+/* math32 log.go / exp.go (ports of Go's math.Log / math.Exp, FreeBSD e_log.c / e_exp.c), float32 arithmetic. */
+float go_log(float x) {
+    const float Ln2Hi = 6.93147180369123816490e-01f, Ln2Lo = 1.90821492927058770002e-10f;
+    const float L1 = 6.666666666666735130e-01f, L2 = 3.999999999940941908e-01f, L3 = 2.857142874366239149e-01f,
+                L4 = 2.222219843214978396e-01f, L5 = 1.818357216161805012e-01f, L6 = 1.531383769920937332e-01f,
+                L7 = 1.479819860511658591e-01f;
+    if (isnan(x) || (isinf(x) && x > 0)) return x;
+    if (x < 0) return NAN;
+    if (x == 0) return -INFINITY;
+    int ki;
+    float f1 = frexpf(x, &ki);
+    if (f1 < (float)(1.41421356237309504880168872420969808 / 2)) { f1 *= 2; ki--; }
+    float f = f1 - 1;
+    float k = (float)ki;
+    float s_ = f / (2 + f);
+    float s2 = s_ * s_;
+    float s4 = s2 * s2;
+    float t1 = s2 * (L1 + s4 * (L3 + s4 * (L5 + s4 * L7)));
+    float t2 = s4 * (L2 + s4 * (L4 + s4 * L6));
+    float R = t1 + t2;
+    float hfsq = 0.5f * f * f;
+    return k * Ln2Hi - ((hfsq - (s_ * (hfsq + R) + k * Ln2Lo)) - f);
+}
+float go_exp(float x) {
+    const float Ln2Hi = 6.93147180369123816490e-01f, Ln2Lo = 1.90821492927058770002e-10f, Log2e = 1.44269504088896338700e+00f;
+    const float P1 = 1.66666666666666657415e-01f, P2 = -2.77777777770155933842e-03f, P3 = 6.61375632143793436117e-05f,
+                P4 = -1.65339022054652515390e-06f, P5 = 4.13813679705723846039e-08f;
+    if (isnan(x) || (isinf(x) && x > 0)) return x;
+    if (isinf(x)) return 0;
+    if (x > 88.72283905206835f) return INFINITY;
+    if (x < -103.97207708f) return 0;
+    int k = 0;
+    if (x < 0) k = (int)(Log2e * x - 0.5f);
+    else if (x > 0) k = (int)(Log2e * x + 0.5f);
+    float hi = x - (float)k * Ln2Hi;
+    float lo = (float)k * Ln2Lo;
+    float r = hi - lo;
+    float t = r * r;
+    float c = r - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+    float y = 1 - ((lo - (r * c) / (2 - c)) - hi);
+    return ldexpf(y, k);
+}
+/* math32.Pow(x, y) for x >= 0 and 0 < y < 0.5 (the only use on this path: powelem2(1./3, |x|), gsdf.go:182):
+ * yi = 0, so the result is Exp(yf*Log(x)) (Go pow.go). */
+static float go_pow_frac(float x, float y) {
+    if (x == 0) return 0;
+    if (x == 1) return 1;
+    return go_exp(y * go_log(x));
+}
+
 /* gsdf.go:148-167 */
 static inline float signf(float a) { return a == 0 ? 0 : copysignf(1, a); }
 static inline float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -454,6 +545,8 @@ static int eval3(const go_tree *t, int id, const v3 *pos, float *dist, size_t n)
         free(tr);
         return err;
     }
+    case GO_BOUNDS3: /* glbuild/glbuild.go:1095-1101: overloadBounds3.Evaluate forwards to the wrapped shader */
+        return eval3(t, child_id(t, nd, 0), pos, dist, n);
     case GO_EXTRUDE: { /* cpu_evaluators.go:506-531; field h */
         SCRATCH(v2, p2, n);
         for (size_t i = 0; i < n; i++) { p2[i].x = pos[i].x; p2[i].y = pos[i].y; }
@@ -508,6 +601,8 @@ static int eval2(const go_tree *t, int id, const v2 *pos, float *dist, size_t n)
     const float *aux = t->aux + nd->aux_off;
     int err = 0;
     switch (nd->kind) {
+    case GO_BOUNDS2: /* glbuild/glbuild.go:1120-1126 */
+        return eval2(t, child_id(t, nd, 0), pos, dist, n);
     case GO_CIRCLE2D: /* cpu_evaluators.go:661-667 */
         for (size_t i = 0; i < n; i++) dist[i] = norm2(pos[i].x, pos[i].y) - f[0];
         return 0;
@@ -789,8 +884,96 @@ static int eval2(const go_tree *t, int id, const v2 *pos, float *dist, size_t n)
         free(a); free(tr);
         return err;
     }
+    case GO_ELLIPSE2D: { /* cpu_evaluators.go:750-791; fields a, b */
+        const float sq3 = (float)GSDF_SQRT3;
+        for (size_t i = 0; i < n; i++) {
+            float a = f[0], b = f[1];
+            float px = go_abs(pos[i].x), py = go_abs(pos[i].y);
+            if (px > py) { float t = px; px = py; py = t; t = a; a = b; b = t; }
+            float l = b * b - a * a;
+            float m = a * px / l, m2 = m * m;
+            float nn = b * py / l, n2 = nn * nn;
+            float c = (m2 + n2 - 1) / 3;
+            float c3 = c * c * c;
+            float q = c3 + 2 * m2 * n2;
+            float d = c3 + m2 * n2;
+            float g = m + m * n2;
+            float co;
+            if (d < 0) {
+                float h = go_acos(q / c3) / 3;
+                float sh = go_sin(h), ch = go_cos(h);
+                float t = sq3 * sh;
+                float rx = sqrtf(-c * (ch + t + 2) + m2);
+                float ry = sqrtf(-c * (ch - t + 2) + m2);
+                co = (ry + signf(l) * rx + go_abs(g) / (rx * ry) - m) / 2;
+            } else {
+                float h = 2 * m * nn * sqrtf(d);
+                float s_ = signf(q + h) * go_cbrt(go_abs(q + h));
+                float u = signf(q - h) * go_cbrt(go_abs(q - h));
+                float rx = -s_ - u - 4 * c + 2 * m2;
+                float ry = sq3 * (s_ - u);
+                float rm = go_hypot(rx, ry);
+                co = (ry / sqrtf(rm - rx) + 2 * g / rm - m) / 2;
+            }
+            float rx2 = a * co, ry2 = b * sqrtf(1 - co * co);
+            dist[i] = norm2(rx2 - px, ry2 - py) * signf(py - ry2);
+        }
+        return 0;
+    }
+    case GO_BEZIERQ2D: { /* cpu_evaluators.go:581-659; fields a(2), b(2), c(2), thick */
+        const float sq3 = (float)GSDF_SQRT3;
+        float thick = f[6] / 2;
+        float Ax = f[0], Ay = f[1], Bx = f[2], By = f[3], Cx = f[4], Cy = f[5];
+        float ax = Bx - Ax, ay = By - Ay;
+        float a2 = ax * ax + ay * ay;
+        float bx = Ax + (Cx - 2 * Bx), by = Ay + (Cy - 2 * By);
+        float cx = 2 * ax, cy = 2 * ay;
+        float kk = 1.f / (bx * bx + by * by);
+        float kx = kk * (ax * bx + ay * by);
+        float kx2 = kx * kx;
+        for (size_t i = 0; i < n; i++) {
+            float dx = Ax - pos[i].x, dy = Ay - pos[i].y;
+            float ky = kk * (2 * a2 + (dx * bx + dy * by)) / 3;
+            float kz = kk * (dx * ax + dy * ay);
+            float g = ky - kx2;
+            float q = kx * (2 * kx2 - 3 * ky) + kz;
+            float g3 = g * g * g;
+            float q2 = q * q;
+            float h = q2 + 4 * g3;
+            float res;
+            if (h >= 0) {
+                h = sqrtf(h);
+                float xx = 0.5f * (h + -q), xy = 0.5f * (-h + -q);
+                if (go_abs(g) < 0.001f) {
+                    float k = (1.0f - g3 / q2) * g3 / q;
+                    xx = k; xy = -k - q;
+                }
+                float ux = signf(xx) * go_pow_frac(go_abs(xx), (float)(1. / 3));
+                float uy = signf(xy) * go_pow_frac(go_abs(xy), (float)(1. / 3));
+                float t = ux + uy;
+                t -= (t * (t * t + 3.0f * g) + q) / (3.0f * t * t + 3.0f * g);
+                t = clampf(t - kx, 0, 1);
+                float wx = dx + t * (cx + t * bx), wy = dy + t * (cy + t * by);
+                res = wx * wx + wy * wy;
+            } else {
+                float z = sqrtf(-g);
+                float xm = sqrtf(0.5f + 0.5f * (q / (2 * g * z))); /* cos_acos_3, gsdf.go:186-189 */
+                float m = xm * (xm * (xm * (xm * -0.008972f + 0.039071f) - 0.107074f) + 0.576975f) + 0.5f;
+                float nn = sqrtf(1 - m * m);
+                nn *= sq3;
+                float tx = clampf((m + m) * z - kx, 0, 1);
+                float ty = clampf((-nn - m) * z - kx, 0, 1);
+                float qxx = dx + tx * (cx + tx * bx), qxy = dy + tx * (cy + tx * by);
+                float qyx = dx + ty * (cx + ty * bx), qyy = dy + ty * (cy + ty * by);
+                float ddx = qxx * qxx + qxy * qxy, ddy = qyx * qyx + qyy * qyy;
+                res = ddx < ddy ? ddx : ddy;
+            }
+            dist[i] = sqrtf(res) - thick;
+        }
+        return 0;
+    }
     default:
-        return -1; /* GO_ELLIPSE2D, GO_BEZIERQ2D: not restated yet (need math32.Acos/Cbrt/Pow) */
+        return -1;
     }
 }
 

@@ -35,7 +35,7 @@ enum {
     /* 3D operations (operations.go) */
     GO_UNION = 16, GO_DIFF, GO_INTERSECT, GO_XOR, GO_SMOOTH_UNION, GO_SMOOTH_DIFF, GO_SMOOTH_INTERSECT,
     GO_SCALE, GO_SYMMETRY, GO_TRANSFORM, GO_TRANSLATE, GO_OFFSET, GO_ARRAY, GO_ELONGATE, GO_SHELL,
-    GO_CIRCARRAY, GO_TWIST,
+    GO_CIRCARRAY, GO_TWIST, GO_BOUNDS3,
     /* 2D -> 3D (operations2d.go, forge/threads/threads.go) */
     GO_EXTRUDE = 40, GO_REVOLVE, GO_SCREW,
     /* 2D primitives (primitives2d.go) */
@@ -43,7 +43,7 @@ enum {
     GO_ELLIPSE2D, GO_POLY2D, GO_DIAMOND2D, GO_ROUNDX2D, GO_BEZIERQ2D,
     /* 2D operations (operations2d.go) */
     GO_UNION2D = 96, GO_DIFF2D, GO_INTERSECT2D, GO_XOR2D, GO_ARRAY2D, GO_OFFSET2D, GO_TRANSLATE2D,
-    GO_ROTATE2D, GO_SYMMETRY2D, GO_ANNULUS2D, GO_CIRCARRAY2D, GO_SCALE2D, GO_TRANSLATEMULTI2D, GO_ELONGATE2D
+    GO_ROTATE2D, GO_SYMMETRY2D, GO_ANNULUS2D, GO_CIRCARRAY2D, GO_SCALE2D, GO_TRANSLATEMULTI2D, GO_ELONGATE2D, GO_BOUNDS2
 };
 
 typedef struct {
@@ -72,6 +72,10 @@ float go_atan2(float y, float x);
 float go_sin(float x);
 float go_cos(float x);
 float go_tan(float x);
+float go_acos(float x);
+float go_cbrt(float x);
+float go_log(float x);
+float go_exp(float x);
 float go_floor(float x);
 float go_round(float x);
 float go_min(float a, float b);

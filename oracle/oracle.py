@@ -42,7 +42,7 @@ def lib():
         build()
         L = C.CDLL(LIB_PATH)
         f32p, vp = C.POINTER(C.c_float), C.c_void_p
-        for name in ("go_sqrt", "go_atan", "go_sin", "go_cos", "go_tan", "go_floor", "go_round"):
+        for name in ("go_sqrt", "go_atan", "go_sin", "go_cos", "go_tan", "go_floor", "go_round", "go_acos", "go_cbrt", "go_log", "go_exp"):
             getattr(L, name).restype = C.c_float
             getattr(L, name).argtypes = [C.c_float]
         for name in ("go_hypot", "go_atan2", "go_min", "go_max"):

@@ -104,6 +104,10 @@ def primitives2d(bld):
         ("octagon", bld.NewOctagon(dx)),
         ("diamond", bld.NewDiamond2D(dx, dy)),
         ("roundx", bld.NewRoundedX(dx, thick)),
+        ("ellipse", bld.NewEllipse(1, 2)),
+        ("ellipse_wide", bld.NewEllipse(1.7, 0.6)),
+        ("bezier", bld.NewQuadraticBezier2D((dx, dy), (dx + maxdim, dy), (dx, dy + maxdim), thick)),
+        ("bezier_flat", bld.NewQuadraticBezier2D((-1, 0), (0.05, 0.4), (1.2, 0.1), 0.05)),
         ("union_lines", bld.Union2D(bld.NewLine2D(1, 2, 3, 4, 0.5), bld.NewLine2D(2, 3, 0, 0, 0.2), bld.NewLine2D(2, 3, 4, 5, 0.2),
                                     bld.NewLines2D([[[0, 0], [1, 1]], [[2, 2], [3, 1]]], 0.5))),
     ]

@@ -431,3 +431,23 @@ def test_slab_pipeline_equals_single_renderer(bld):
             assert n == len(whole) == pipe.NumTriangles()
             assert np.array_equal(bits(dst[:n]), bits(whole)), nslabs
         pipe.Close()
+
+
+def test_bounds_overload_and_driver(oracle, bld, capsys):
+    """OverloadShader3DBounds changes the lattice (Bounds) but not the field; gsdfaux.RenderShader3D logs the
+    reference's lines and writes a valid STL with one write."""
+    from gsdf_b200 import gsdfaux
+    s = bld.NewSphere(1.0)
+    w = bld.OverloadShader3DBounds(s, (-1.5, -1.5, -1.5), (1.5, 1.5, 1.5))
+    check_field("overload", w, oracle, shapes.sample_points(w))
+    buf = io.BytesIO()
+    tris = gsdfaux.RenderShader3D(w, gsdfaux.RenderConfig(STLOutput=buf, Resolution=0.09, UseGPU=True))
+    out = capsys.readouterr().out
+    assert "evaluated SDF" in out and "percent evaluations omitted in octree pruning step" in out and "render done" in out
+    lat, grid, mask, wt, _ = oracle_mesh(oracle, w, np.float32(0.09), True)
+    assert np.array_equal(bits(tris), bits(wt))
+    buf.seek(0)
+    assert np.array_equal(bits(glrender.ReadBinarySTL(buf)), bits(wt))
+    with pytest.raises(gsdf_b200.GsdfError) as e:
+        glrender.NewOctreeRenderer(gleval.NewCUDASDF3(s), 5.0, 64)     # makeICube: resolution not fine enough
+    assert e.value.code == _lib.ERES

@@ -178,10 +178,67 @@ def test_position_liveness(bld):
     assert bld.flatten(bld.CircularArray(s, 3, 5))["pstack"] == 1   # CIRC_ENTER parks p0 on the stack
 
 
-def test_unsupported_nodes_fail_loudly(bld):
+def test_unknown_constructor_kinds_fail_loudly(bld):
     import ctypes
     from gsdf_b200._lib import lib
-    # ellipse2D is declared in the tree format but not implemented by the backend: flatten must refuse it
     f = (ctypes.c_float * 2)(1.0, 2.0)
-    nid = lib.gsdfh_node(bld._h, 72, f, 2, None, 0, None, 0, None, 0)
-    assert nid < 0
+    assert lib.gsdfh_node(bld._h, 999, f, 2, None, 0, None, 0, None, 0) < 0
+    assert "unsupported constructor kind" in bld.Err()
+    bld.ClearErrors()
+
+
+def test_bounds_overload_wrapper(oracle, bld):
+    """glbuild.OverloadShader3DBounds (glbuild.go:1080-1102): Bounds() is replaced, Evaluate forwards, and the flattener
+    sees through the wrapper (same program as the wrapped shader)."""
+    s = bld.NewSphere(1.0)
+    w = bld.OverloadShader3DBounds(s, (-2, -2, -2), (2, 3, 4))
+    assert np.array_equal(np.concatenate(w.Bounds()), [-2, -2, -2, 2, 3, 4])
+    assert bld.flatten(w)["blob"] == bld.flatten(s)["blob"]
+    pts = np.random.default_rng(0).uniform(-2, 2, (64, 3)).astype(np.float32)
+    assert np.array_equal(oracle.Tree.from_shader(w).eval3(pts), oracle.Tree.from_shader(s).eval3(pts))
+    c = bld.NewCircle(1.0)
+    w2 = bld.OverloadShader2DBounds(c, (-3, -3), (3, 3))
+    assert np.array_equal(np.concatenate(w2.Bounds()), [-3, -3, 3, 3]) and w2.is2d
+    assert bld.flatten(bld.Extrude(w2, 1))["ninstr"] == bld.flatten(bld.Extrude(c, 1))["ninstr"]
+
+
+def test_octree_levels_formula(oracle):
+    """makeICube (octreerenderer.go:222-235): sphere r=1, res=1/33 -> 8 levels; flange@400 -> 10; too coarse -> error."""
+    from gsdf_b200 import glrender
+    assert glrender.octree_levels((-1, -1, -1), (1, 1, 1), 1 / 33) == 8 == oracle.octree_levels((-1, -1, -1), (1, 1, 1), 1 / 33)
+    assert glrender.octree_levels((-30, -30, -12.5), (30, 30, 5.3886), 0.21679485) == 10
+    with pytest.raises(gsdf_b200.GsdfError) as e:
+        glrender.octree_levels((-1, -1, -1), (1, 1, 1), 3.0)
+    assert e.value.code == _lib.ERES
+    with pytest.raises(gsdf_b200.GsdfError):
+        glrender.octree_levels((-1, -1, -1), (1, 1, 1), 0.0)
+
+
+def test_read_binary_stl_validation(oracle, bld):
+    """ReadBinarySTL / stlTriangle.validate (stl.go:129-225)."""
+    import io
+    from gsdf_b200 import glrender
+    s = bld.NewSphere(1.0)
+    t = oracle.Tree.from_shader(s)
+    lat = oracle.flat_lattice(*s.Bounds(), np.float32(0.3))
+    grid, _ = oracle.flat_eval_grid(t, lat)
+    tris, _ = oracle.flat_march(lat, grid)
+    data = bytearray(oracle.stl_write(tris))
+    back = glrender.ReadBinarySTL(io.BytesIO(bytes(data)))
+    assert np.array_equal(back.view(np.uint32), tris.view(np.uint32))
+    with pytest.raises(gsdf_b200.GsdfError):
+        glrender.ReadBinarySTL(io.BytesIO(bytes(data[:50])))            # truncated header
+    with pytest.raises(gsdf_b200.GsdfError):
+        glrender.ReadBinarySTL(io.BytesIO(bytes(data[:84 + 49])))       # truncated record
+    bad = bytearray(data)
+    bad[80:84] = struct.pack("<I", 0)
+    with pytest.raises(gsdf_b200.GsdfError):
+        glrender.ReadBinarySTL(io.BytesIO(bytes(bad)))                  # zero triangles (stl.go:183)
+    bad = bytearray(data)
+    bad[84 + 12:84 + 16] = struct.pack("<f", float("nan"))
+    with pytest.raises(gsdf_b200.GsdfError):
+        glrender.ReadBinarySTL(io.BytesIO(bytes(bad)))                  # NaN vertex
+    bad = bytearray(data)
+    bad[84 + 24:84 + 48] = bad[84 + 12:84 + 24] * 2                     # all three vertices equal -> degenerate
+    with pytest.raises(gsdf_b200.GsdfError):
+        glrender.ReadBinarySTL(io.BytesIO(bytes(bad)))
