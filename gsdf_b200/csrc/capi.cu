@@ -411,6 +411,8 @@ struct gsdf_mesher {
     uint32_t *d_seg = nullptr; size_t seg_cap = 0;
     uint32_t *d_seglist = nullptr; size_t seglist_cap = 0;
     uint32_t *d_blocksum = nullptr; size_t blocksum_cap = 0;
+    unsigned long long *d_scanstate = nullptr; size_t scanstate_cap = 0;
+    uint32_t scan_epoch = 0;
     float *d_tris = nullptr; size_t tri_cap = 0;  // in floats
     uint8_t *d_cases = nullptr; size_t cases_cap = 0;
     uint8_t *d_stl = nullptr; size_t stl_cap = 0;
@@ -478,6 +480,16 @@ int mesh_run(gsdf_mesher *m) {
     if ((rc = grow(m->d_seglist, m->seglist_cap, (size_t)nseg))) return rc;
     const uint64_t nscanblocks = (nseg + kThreads * kScanItems - 1) / (kThreads * kScanItems);
     if ((rc = grow(m->d_blocksum, m->blocksum_cap, (size_t)nscanblocks))) return rc;
+    const uint64_t nscantiles = (nseg + kScanTile - 1) / kScanTile;
+    if (nscantiles > m->scanstate_cap) {
+        if ((rc = grow(m->d_scanstate, m->scanstate_cap, (size_t)nscantiles))) return rc;
+        CU(cudaMemsetAsync(m->d_scanstate, 0, m->scanstate_cap * sizeof(unsigned long long), st));
+        m->scan_epoch = 0;
+    }
+    if (++m->scan_epoch >= (1u << 29)) {  // epoch field is 30 bits wide
+        CU(cudaMemsetAsync(m->d_scanstate, 0, m->scanstate_cap * sizeof(unsigned long long), st));
+        m->scan_epoch = 1;
+    }
     if (prune) {
         if ((rc = grow(m->d_mask, m->mask_cap, (size_t)nblocks))) return rc;
         if ((rc = grow(m->d_mbits, m->mbits_cap, (size_t)D.nwx * D.nby * D.nbz))) return rc;
@@ -540,12 +552,18 @@ int mesh_run(gsdf_mesher *m) {
         k_mc_count<<<mcgrid, kThreads, 0, st>>>(A);
     }
     CU(cudaGetLastError());
-    k_scan_reduce<<<(unsigned)nscanblocks, kThreads, 0, st>>>(m->d_seg, nseg, m->d_blocksum);
-    CU(cudaGetLastError());
-    k_scan_blocksums<<<1, 1024, 0, st>>>(m->d_blocksum, (uint32_t)nscanblocks, reinterpret_cast<unsigned long long *>(m->d_ctr + 2));
-    CU(cudaGetLastError());
-    k_scan_apply<<<(unsigned)nscanblocks, kThreads, 0, st>>>(m->d_seg, nseg, m->d_blocksum);
-    CU(cudaGetLastError());
+    if (getenv("GSDF_SCAN3")) {  // A/B: the three-kernel scan
+        k_scan_reduce<<<(unsigned)nscanblocks, kThreads, 0, st>>>(m->d_seg, nseg, m->d_blocksum);
+        CU(cudaGetLastError());
+        k_scan_blocksums<<<1, 1024, 0, st>>>(m->d_blocksum, (uint32_t)nscanblocks, reinterpret_cast<unsigned long long *>(m->d_ctr + 2));
+        CU(cudaGetLastError());
+        k_scan_apply<<<(unsigned)nscanblocks, kThreads, 0, st>>>(m->d_seg, nseg, m->d_blocksum);
+        CU(cudaGetLastError());
+    } else {
+        k_scan_lookback<<<(unsigned)nscantiles, kThreads, 0, st>>>(m->d_seg, (uint32_t)nseg, m->d_scanstate, m->d_ctr + 6, m->scan_epoch,
+                                                               reinterpret_cast<unsigned long long *>(m->d_ctr + 2));
+        CU(cudaGetLastError());
+    }
     CU(cudaEventRecord(m->ev[3], st));
 
     A.cases = nullptr;
@@ -712,7 +730,7 @@ int gsdf_mesh_timings(const gsdf_mesher *m, float ms[5]) {
 void gsdf_mesh_destroy(gsdf_mesher *m) {
     if (!m) return;
     if (m->prog) cudaSetDevice(m->prog->device);
-    cudaFree(m->d_grid); cudaFree(m->d_mask); cudaFree(m->d_mbits); cudaFree(m->d_list); cudaFree(m->d_seg); cudaFree(m->d_seglist); cudaFree(m->d_blocksum);
+    cudaFree(m->d_grid); cudaFree(m->d_mask); cudaFree(m->d_mbits); cudaFree(m->d_list); cudaFree(m->d_seg); cudaFree(m->d_seglist); cudaFree(m->d_scanstate); cudaFree(m->d_blocksum);
     cudaFree(m->d_tris); cudaFree(m->d_cases); cudaFree(m->d_stl); cudaFree(m->d_ctr);
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
     for (auto &e : m->ev) if (e) cudaEventDestroy(e);

@@ -292,6 +292,16 @@ struct MeshDims {
     int nwx;                 // 32-bit words per block row of the bit mask = ceil(nbx/32)
 };
 
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
 // Byte mask -> bit rows: one warp per block row (by,bz); word w of a row holds blocks 32w..32w+31. Also counts the
 // kept blocks (Octree.TotalPruned bookkeeping).
 __global__ void __launch_bounds__(kThreads) k_mask_bits(MeshDims D, const uint8_t *__restrict__ mask, uint32_t *__restrict__ bits,
@@ -324,56 +334,61 @@ __global__ void __launch_bounds__(kThreads) k_compact_quads(MeshDims D, const ui
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nrows = (uint32_t)(D.ny + 1) * (uint32_t)(D.cz1 - D.cz0 + 1);
     const uint32_t rpg = gridDim.x * (blockDim.x >> 5);
+    const int nqw = (D.nqx + 31) >> 5;  // 32-quad words per corner row
     // CTA-uniform trip count: every iteration the 8 warps take 8 consecutive rows and share ONE atomicAdd
     for (uint32_t r0 = blockIdx.x * (blockDim.x >> 5); r0 < nrows; r0 += rpg) {
         const uint32_t r = r0 + warp;
-        const uint32_t *rows[4];
-        int nr = 0;
-        if (r < nrows) {
-            const int j = (int)(r % (uint32_t)(D.ny + 1));
-            const int k = D.cz0 + (int)(r / (uint32_t)(D.ny + 1));
-            // the (at most 2 x 2) block rows whose cells touch this corner row
-            const int by0 = j - 1 >= 0 ? (j - 1) >> 2 : -1, by1 = j < D.ny ? j >> 2 : -1;
-            const int bz0 = k - 1 >= D.cz0 ? (k - 1) >> 2 : -1, bz1 = k < D.cz1 ? k >> 2 : -1;
-#pragma unroll
-            for (int a = 0; a < 2; a++) {
-                const int by = a ? by1 : by0;
-                if (by < 0 || (a && by1 == by0)) continue;
-#pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    const int bz = c ? bz1 : bz0;
-                    if (bz < 0 || (c && bz1 == bz0)) continue;
-                    rows[nr++] = bits + ((size_t)(bz - D.bz0) * D.nby + by) * D.nwx;
-                }
-            }
-        }
-        auto needed = [&](int m) -> bool {
-            uint32_t need = 0u;
-            if (m < D.nqx)
-                for (int t = 0; t < nr; t++) {
-                    if (m < D.nbx) need |= bit_at(rows[t], m);
-                    if (m - 1 < D.nbx) need |= bit_at(rows[t], m - 1);
-                }
-            return need != 0u;
-        };
         uint32_t mine = 0u;
-        for (int m0 = 0; m0 < D.nqx; m0 += 32) mine += __popc(__ballot_sync(0xffffffffu, needed(m0 + lane)));
-        if (lane == 0) s_cnt[warp] = mine;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t tot = 0;
-            for (int w = 0; w < kThreads / 32; w++) { const uint32_t c = s_cnt[w]; s_cnt[w] = tot; tot += c; }
-            s_base = tot ? atomicAdd(count, tot) : 0u;
+        // need-word w (kept by lane w of the warp; rows wider than 1024 quads loop) has bit q set iff quad 32w+q must
+        // be evaluated: blocks m and m-1 of the touching block rows, i.e. word | word<<1 | carry of the previous word.
+        for (int w0 = 0; w0 < nqw; w0 += 32) {
+            const int w = w0 + lane;
+            uint32_t needw = 0u;
+            if (r < nrows && w < nqw) {
+                const int j = (int)(r % (uint32_t)(D.ny + 1));
+                const int k = D.cz0 + (int)(r / (uint32_t)(D.ny + 1));
+                const int by0 = j - 1 >= 0 ? (j - 1) >> 2 : -1, by1 = j < D.ny ? j >> 2 : -1;
+                const int bz0 = k - 1 >= D.cz0 ? (k - 1) >> 2 : -1, bz1 = k < D.cz1 ? k >> 2 : -1;
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    const int by = a ? by1 : by0;
+                    if (by < 0 || (a && by1 == by0)) continue;
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const int bz = c ? bz1 : bz0;
+                        if (bz < 0 || (c && bz1 == bz0)) continue;
+                        const uint32_t *row = bits + ((size_t)(bz - D.bz0) * D.nby + by) * D.nwx;
+                        const uint32_t cur = w < D.nwx ? row[w] : 0u;
+                        const uint32_t prev = (w >= 1 && w - 1 < D.nwx) ? row[w - 1] : 0u;
+                        needw |= cur | (cur << 1) | (prev >> 31);
+                    }
+                }
+                const int rem = D.nqx - 32 * w;  // quads of this word that exist
+                if (rem < 32) needw &= (1u << rem) - 1u;
+            }
+            // exclusive position of each word's quads inside the row chunk, then one CTA-wide atomic
+            const uint32_t pc = (uint32_t)__popc(needw);
+            const uint32_t incl = warp_incl_scan(pc);
+            const uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
+            if (lane == 0) s_cnt[warp] = wtot;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t tot = 0;
+                for (int i = 0; i < kThreads / 32; i++) { const uint32_t c = s_cnt[i]; s_cnt[i] = tot; tot += c; }
+                s_base = tot ? atomicAdd(count, tot) : 0u;
+            }
+            __syncthreads();
+            // expand: lane q of the warp writes quad (32*ww + q) for every word ww of this chunk
+            const uint32_t wbase = s_base + s_cnt[warp];
+            for (int ww = 0; ww < 32 && w0 + ww < nqw; ww++) {
+                const uint32_t word = __shfl_sync(0xffffffffu, needw, ww);
+                if (word == 0u) continue;
+                const uint32_t off = __shfl_sync(0xffffffffu, incl - pc, ww);
+                if ((word >> lane) & 1u) list[wbase + off + __popc(word & ((1u << lane) - 1u))] = r * (uint32_t)D.nqx + (uint32_t)(32 * (w0 + ww) + lane);
+            }
+            mine += wtot;
+            __syncthreads();
         }
-        __syncthreads();
-        uint32_t o = s_base + s_cnt[warp];
-        for (int m0 = 0; m0 < D.nqx && mine; m0 += 32) {
-            const bool need = needed(m0 + lane);
-            const unsigned bal = __ballot_sync(0xffffffffu, need);
-            if (need) list[o + __popc(bal & ((1u << lane) - 1u))] = r * (uint32_t)D.nqx + (uint32_t)(m0 + lane);
-            o += __popc(bal);
-        }
-        __syncthreads();
     }
 }
 
@@ -394,15 +409,6 @@ struct MCArgs {
     uint32_t *seg_count;
 };
 
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
-    }
-    return v;
-}
 
 // marchcubes.go:76-98
 __device__ __forceinline__ float3 mc_interp(float3 p1, float3 p2, float v1, float v2) {
@@ -757,6 +763,87 @@ __global__ void __launch_bounds__(kThreads) k_scan_apply(uint32_t *__restrict__ 
     for (int i = 0; i < kScanItems; i++) {
         if (base + i < n) data[base + i] = run;
         run += v[i];
+    }
+}
+
+// Single-pass exclusive scan (decoupled look-back): tiles of 2048 items are claimed in order from an atomic ticket, each
+// publishes its aggregate, looks back over its predecessors until it meets an inclusive prefix, publishes its own
+// inclusive prefix and writes its items. State words carry an epoch so the array never needs clearing:
+//   state = epoch << 34 | flag << 32 | value,  flag 1 = aggregate, 2 = inclusive prefix.
+constexpr int kScanTile = kThreads * 8;
+__global__ void __launch_bounds__(kThreads) k_scan_lookback(uint32_t *__restrict__ data, uint32_t n, unsigned long long *__restrict__ state,
+                                                           uint32_t *__restrict__ ticket, uint32_t epoch, unsigned long long *__restrict__ total) {
+    __shared__ uint32_t s_w[kThreads / 32];
+    __shared__ uint32_t s_tile, s_prefix;
+    const uint32_t ntiles = (n + kScanTile - 1) / kScanTile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= ntiles) return;
+    const uint32_t base = tile * kScanTile + threadIdx.x * 8;
+    uint32_t v[8], sum = 0;
+    if (base + 8 <= n) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(data + base), b = *reinterpret_cast<const uint4 *>(data + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = base + i < n ? data[base + i] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) sum += v[i];
+    const uint32_t incl = warp_incl_scan(sum);
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t w = threadIdx.x < kThreads / 32 ? s_w[threadIdx.x] : 0u;
+        const uint32_t wi = warp_incl_scan(w);
+        if (threadIdx.x < kThreads / 32) s_w[threadIdx.x] = wi - w;
+        const uint32_t agg = __shfl_sync(0xffffffffu, wi, 31);  // tile aggregate
+        // lane 0 publishes, then the warp looks back 32 tiles at a time
+        const unsigned long long tag = (unsigned long long)epoch << 34;
+        if (threadIdx.x == 0) {
+            const unsigned long long st = tag | ((tile == 0 ? 2ull : 1ull) << 32) | agg;
+            atomicExch(&state[tile], st);
+        }
+        uint32_t prefix = 0;
+        if (tile > 0) {
+            int look = (int)tile - 1;
+            for (;;) {
+                const int idx = look - (int)threadIdx.x;
+                unsigned long long st = 0;
+                if (idx >= 0) {
+                    do { st = *reinterpret_cast<volatile unsigned long long *>(&state[idx]); } while ((st >> 34) != epoch || ((st >> 32) & 3ull) == 0ull);
+                }
+                const uint32_t flag = idx >= 0 ? (uint32_t)((st >> 32) & 3ull) : 2u;  // before tile 0: inclusive prefix 0
+                const uint32_t val = idx >= 0 ? (uint32_t)st : 0u;
+                const unsigned incl_mask = __ballot_sync(0xffffffffu, flag == 2u);
+                // take values up to and including the first inclusive prefix (lowest lane = nearest tile)
+                const int stop = incl_mask ? __ffs(incl_mask) - 1 : 31;
+                uint32_t part = (int)threadIdx.x <= stop ? val : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                prefix += part;
+                if (incl_mask) break;
+                look -= 32;
+            }
+            if (threadIdx.x == 0) atomicExch(&state[tile], tag | (2ull << 32) | (unsigned long long)(prefix + agg));
+        }
+        if (threadIdx.x == 0) {
+            s_prefix = prefix;
+            if (tile == ntiles - 1) *total = (unsigned long long)prefix + agg;
+        }
+    }
+    __syncthreads();
+    uint32_t run = s_prefix + s_w[threadIdx.x >> 5] + (incl - sum);
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { o[i] = run; run += v[i]; }
+    if (base + 8 <= n) {
+        *reinterpret_cast<uint4 *>(data + base) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4 *>(data + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (base + i < n) data[base + i] = o[i];
     }
 }
 
