@@ -35,7 +35,7 @@ METRIC = "sdf_evals_per_sec"
 UNIT = "evals/s"
 RESDIV = 400
 SCENE = "npt-flange"
-KERNELS_PER_STEP = 9  # centres, mask-bits, compact, fine eval, mc-count, 3x scan, mc-emit
+KERNELS_PER_STEP = 7  # centres, mask-bits, compact, fine eval, mc-count (TMA), look-back scan, mc-emit
 
 
 def measured_peaks():
