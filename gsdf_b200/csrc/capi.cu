@@ -117,6 +117,13 @@ int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_boun
 int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_t aux_floats) {
     uint32_t pc = 0, n = 0;
     bool ended = false;
+    std::vector<uint8_t> starts(h.nchunks, 0);  // instruction boundaries, for slab-guard jump targets
+    for (uint32_t q = 0; q < h.nchunks;) {
+        starts[q] = 1;
+        const uint32_t len = (chunks[4 * q] >> 8) & 0xff;
+        if (len < 1) break;
+        q += len;
+    }
     while (pc < h.nchunks) {
         const uint32_t w0 = chunks[4 * pc], op = w0 & 0xff, len = (w0 >> 8) & 0xff;
         if (op >= GSDF_OP__COUNT) return fail(GSDF_EPROGRAM, "instruction %u: unknown opcode %u", n, op);
@@ -132,6 +139,12 @@ int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_
         if (op == GSDF_OP_POLY2D) {
             const uint64_t off = chunks[4 * pc + 1], nv = chunks[4 * pc + 2];
             if ((off & 3) || nv < 3 || off + nv * GSDF_POLY_EDGE_FLOATS > aux_floats) return fail(GSDF_EPROGRAM, "instruction %u: polygon aux range out of bounds", n);
+        }
+        if (op == GSDF_OP_EXTRUDE_ENTER || op == GSDF_OP_SCREW_ENTER) {
+            const uint32_t kind = chunks[4 * pc + 1] & 0xff, target = chunks[4 * pc + 1] >> 8;
+            if (kind > GSDF_GUARD_SMOOTH_UNION) return fail(GSDF_EPROGRAM, "instruction %u: unknown slab guard %u", n, kind);
+            if (kind != GSDF_GUARD_NONE && (target <= pc + len || target >= h.nchunks || !starts[target]))
+                return fail(GSDF_EPROGRAM, "instruction %u: slab guard target %u is not a later instruction", n, target);
         }
         if (op == GSDF_OP_LINES2D) {
             const uint64_t off = chunks[4 * pc + 1], ns = chunks[4 * pc + 2];

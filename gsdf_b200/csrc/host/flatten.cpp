@@ -7,6 +7,7 @@
 // All per-node constants are derived in float32 exactly as the node's Evaluate method derives them per call.
 #include "flatten.h"
 
+#include <cstdlib>
 #include <cstring>
 
 #include "../math32.cuh"
@@ -20,13 +21,44 @@ constexpr double kSqrt3 = 1.7320508075688772935274463415058723669428052538103806
 
 inline uint32_t fbits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 
+// Slab guard handed down from a combiner to a later child (include/gsdf_program.h "slab guards").
+struct Guard {
+    uint32_t kind = GSDF_GUARD_NONE;
+    float k = 0;
+};
+
 struct Emitter {
     const Builder &b;
     Program &out;
     int d = 0, p = 0, dmax = 0, pmax = 0;
+    bool guards = true;
     std::string err;
 
-    Emitter(const Builder &bb, Program &o) : b(bb), out(o) {}
+    Emitter(const Builder &bb, Program &o) : b(bb), out(o) {
+        const char *e = std::getenv("GSDF_NO_GUARDS");
+        guards = !(e && *e && *e != '0');
+    }
+
+    // Nodes whose Evaluate forwards the child's distance unchanged (they only move p).
+    static bool transparent(int kind) {
+        return kind == GSDF_N_TRANSLATE || kind == GSDF_N_TRANSFORM || kind == GSDF_N_SYMMETRY || kind == GSDF_N_TWIST ||
+               kind == GSDF_N_BOUNDS3;
+    }
+    // True when `id` is a screw/extrude reached through transparent nodes only: its value is >= |z|-h/2 in its own
+    // frame, which the ENTER op has in hand before any of the expensive 2-D work.
+    bool guardable(NodeId id) const {
+        while (b.valid(id) && transparent(b.node(id).kind) && b.node(id).nchild == 1) id = b.child(b.node(id), 0);
+        return b.valid(id) && (b.node(id).kind == GSDF_N_SCREW || b.node(id).kind == GSDF_N_EXTRUDE);
+    }
+    Guard guardFor(NodeId child, uint32_t kind, float k = 0) const {
+        Guard g;
+        if (guards && guardable(child)) { g.kind = kind; g.k = k; }
+        return g;
+    }
+    // The skip lands right behind the guarded node's own exit op (the restoring POP_POS ops of its wrappers follow).
+    void patchGuard(size_t headerWord, const Guard &g) {
+        if (g.kind != GSDF_GUARD_NONE) out.chunks[headerWord + 1] = g.kind | ((uint32_t)(out.chunks.size() / 4) << 8);
+    }
 
     void header(uint32_t op, uint32_t nchunks, uint32_t w1 = 0, uint32_t w2 = 0, uint32_t w3 = 0) {
         out.chunks.insert(out.chunks.end(), {op | (nchunks << 8), w1, w2, w3});
@@ -44,10 +76,10 @@ struct Emitter {
 
     // Emits `enter`, the child, `exit` for a unary position transform.
     template <class Enter, class Exit>
-    bool unaryPos(const gsdf_tree_node &n, bool restore, bool child2d, Enter enter, Exit exit) {
+    bool unaryPos(const gsdf_tree_node &n, bool restore, bool child2d, Enter enter, Exit exit, Guard g = Guard{}) {
         if (restore) pushP();
         enter();
-        if (!emit(b.child(n, 0), false, child2d)) return false;
+        if (!emit(b.child(n, 0), false, child2d, g)) return false;
         exit();
         if (restore) popP();
         return true;
@@ -55,13 +87,16 @@ struct Emitter {
     bool binary(const gsdf_tree_node &n, bool restore, bool is2d, uint32_t op, float k, bool hasK) {
         if (n.nchild != 2) { err = "binary operation needs 2 children"; return false; }
         if (!emit(b.child(n, 0), true, is2d)) return false;
-        if (!emit(b.child(n, 1), restore, is2d)) return false;
+        Guard g;
+        if (!is2d && op == GSDF_OP_DIFF) g = guardFor(b.child(n, 1), GSDF_GUARD_DIFF);
+        if (!is2d && op == GSDF_OP_SMOOTH_UNION && k > 0) g = guardFor(b.child(n, 1), GSDF_GUARD_SMOOTH_UNION, k);
+        if (!emit(b.child(n, 1), restore, is2d, g)) return false;
         if (hasK) opf(op, k); else op0(op);
         popD();
         return true;
     }
 
-    bool emit(NodeId id, bool restore, bool expect2d) {
+    bool emit(NodeId id, bool restore, bool expect2d, Guard g = Guard{}) {
         if (!b.valid(id)) { err = "invalid node id in tree"; return false; }
         const gsdf_tree_node &n = b.node(id);
         if (expect2d != b.is2D(id)) { err = "2D/3D node kind mismatch in tree"; return false; }
@@ -94,9 +129,14 @@ struct Emitter {
         case GSDF_N_UNION2D: {
             bool is2d = n.kind == GSDF_N_UNION2D;
             if (n.nchild < 2) { err = "OpUnion must have at least 2 elements"; return false; }  // operations.go:110-114
+            // min is order-independent, so guardable children go last where the running min can guard them
+            std::vector<NodeId> order;
+            for (int k = 0; k < n.nchild; k++) if (is2d || !guards || !guardable(b.child(n, k))) order.push_back(b.child(n, k));
+            for (int k = 0; k < n.nchild; k++) if (!(is2d || !guards || !guardable(b.child(n, k)))) order.push_back(b.child(n, k));
             for (int k = 0; k < n.nchild; k++) {
                 bool last = k == n.nchild - 1;
-                if (!emit(b.child(n, k), last ? restore : true, is2d)) return false;
+                Guard cg = (k > 0 && !is2d) ? guardFor(order[k], GSDF_GUARD_MIN) : Guard{};
+                if (!emit(order[k], last ? restore : true, is2d, cg)) return false;
                 if (k > 0) { op0(GSDF_OP_MIN); popD(); }
             }
             return true;
@@ -124,7 +164,7 @@ struct Emitter {
         case GSDF_N_SYMMETRY:
         case GSDF_N_SYMMETRY2D: {
             uint32_t mask = (uint32_t)n.iparam[0];
-            return unaryPos(n, restore, n.kind == GSDF_N_SYMMETRY2D, [&] { header(GSDF_OP_SYMMETRY, 1, mask); }, [] {});
+            return unaryPos(n, restore, n.kind == GSDF_N_SYMMETRY2D, [&] { header(GSDF_OP_SYMMETRY, 1, mask); }, [] {}, g);
         }
         case GSDF_N_TRANSFORM:
             return unaryPos(n, restore, false,
@@ -132,9 +172,9 @@ struct Emitter {
                                 header(GSDF_OP_TRANSFORM, 4);
                                 chunk(f[0], f[1], f[2], f[3]); chunk(f[4], f[5], f[6], f[7]); chunk(f[8], f[9], f[10], f[11]);
                             },
-                            [] {});
+                            [] {}, g);
         case GSDF_N_TRANSLATE:
-            return unaryPos(n, restore, false, [&] { header(GSDF_OP_TRANSLATE, 2); chunk(f[0], f[1], f[2]); }, [] {});
+            return unaryPos(n, restore, false, [&] { header(GSDF_OP_TRANSLATE, 2); chunk(f[0], f[1], f[2]); }, [] {}, g);
         case GSDF_N_TRANSLATE2D:
             return unaryPos(n, restore, true, [&] { header(GSDF_OP_TRANSLATE, 2); chunk(f[0], f[1], 0.f); }, [] {});
         case GSDF_N_ROTATE2D:
@@ -145,7 +185,7 @@ struct Emitter {
             opf(GSDF_OP_OFFSET, f[0]);
             return true;
         case GSDF_N_BOUNDS3:  // glbuild wrappers only change Bounds(); the flattener sees through them
-            return emit(b.child(n, 0), restore, false);
+            return emit(b.child(n, 0), restore, false, g);
         case GSDF_N_BOUNDS2:
             return emit(b.child(n, 0), restore, true);
         case GSDF_N_ANNULUS2D:
@@ -153,7 +193,7 @@ struct Emitter {
             opf(GSDF_OP_ANNULUS, f[0]);
             return true;
         case GSDF_N_TWIST:
-            return unaryPos(n, restore, false, [&] { opf(GSDF_OP_TWIST, f[0]); }, [] {});
+            return unaryPos(n, restore, false, [&] { opf(GSDF_OP_TWIST, f[0]); }, [] {}, g);
         case GSDF_N_ELONGATE: {  // h := Scale(0.5, e.h)  cpu_evaluators.go:412
             bool ok = unaryPos(n, restore, false,
                                [&] { header(GSDF_OP_ELONGATE, 2); chunk(0.5f * f[0], 0.5f * f[1], 0.5f * f[2]); pushD(); },
@@ -202,18 +242,24 @@ struct Emitter {
         }
         // ---------------- 2D -> 3D
         case GSDF_N_EXTRUDE: {  // h := e.h / 2  cpu_evaluators.go:524
-            opf(GSDF_OP_EXTRUDE_ENTER, f[0] / 2); pushD();
+            size_t hw = out.chunks.size();
+            header(GSDF_OP_EXTRUDE_ENTER, 1, 0, fbits(f[0] / 2), fbits(g.k)); pushD();
             if (!emit(b.child(n, 0), restore, true)) return false;
             op0(GSDF_OP_EXTRUDE_EXIT); popD();
+            patchGuard(hw, g);
             return true;
         }
         case GSDF_N_REVOLVE:
             return unaryPos(n, restore, true, [&] { opf(GSDF_OP_REVOLVE, f[0]); }, [] {});
         case GSDF_N_SCREW: {  // threads.go:151-155: atanTaper := math.Tan(taper)
             float tanTaper = m32::tan(f[3]);
+            size_t hw = 0;
             return unaryPos(n, restore, true,
-                            [&] { header(GSDF_OP_SCREW_ENTER, 2); chunk(f[0], f[1], f[2], tanTaper); pushD(); },
-                            [&] { op0(GSDF_OP_MAX_BELOW); popD(); });
+                            [&] {
+                                hw = out.chunks.size();
+                                header(GSDF_OP_SCREW_ENTER, 2, 0, 0, fbits(g.k)); chunk(f[0], f[1], f[2], tanTaper); pushD();
+                            },
+                            [&] { op0(GSDF_OP_MAX_BELOW); popD(); patchGuard(hw, g); });
         }
         // ---------------- 2D primitives
         case GSDF_N_CIRCLE2D: opf(GSDF_OP_CIRCLE2D, f[0]); pushD(); return true;

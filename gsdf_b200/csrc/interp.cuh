@@ -30,9 +30,10 @@ struct Machine {
     float *pstk;                // &pstack[threadIdx.x]
     int stride;                 // blockDim.x
     int dsp, psp;
+    bool skip;                  // CTA-uniform: a slab guard fired, the next combiner keeps `a` (gsdf_program.h)
 
     __device__ __forceinline__ void init(float *d, float *p, int s) {
-        dstk = d; pstk = p; stride = s; dsp = -1; psp = 0;
+        dstk = d; pstk = p; stride = s; dsp = -1; psp = 0; skip = false;
 #pragma unroll
         for (int j = 0; j < P; j++) top[j] = 0.f;
     }
@@ -69,6 +70,15 @@ struct Machine {
 __device__ __forceinline__ float4 ldf4(const uint4 *prog, int i) {
     uint4 u = prog[i];
     return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+}
+
+// Slab-guard predicate (include/gsdf_program.h): true when a subtree whose value is >= w cannot change the result of
+// the combiner that follows, given the value `a` already on top of the distance stack. Strict comparisons (and a != 0
+// for the smooth blend) keep the skipped result bit-identical, signed zeros included.
+__device__ __forceinline__ bool guard_dead(uint32_t kind, float w, float a, float k) {
+    if (kind == GSDF_GUARD_DIFF) return -w < a;
+    if (kind == GSDF_GUARD_MIN) return w > a;
+    return (w - a) >= k && a != 0.f;
 }
 
 // Runs the program at the P positions already loaded in m.px/py/pz; result in m.top.
@@ -396,6 +406,7 @@ __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restri
         } break;
         // ------------------------------------------------------------------ combiners
         case GSDF_OP_MIN: {
+            if (m.skip) { m.skip = false; break; }
             float a[P]; m.popBelow(a);
 #pragma unroll
             for (int j = 0; j < P; j++) m.top[j] = minf(a[j], m.top[j]);
@@ -406,6 +417,7 @@ __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restri
             for (int j = 0; j < P; j++) m.top[j] = maxf(a[j], m.top[j]);
         } break;
         case GSDF_OP_DIFF: {
+            if (m.skip) { m.skip = false; break; }
             float a[P]; m.popBelow(a);
 #pragma unroll
             for (int j = 0; j < P; j++) m.top[j] = maxf(a[j], -m.top[j]);
@@ -416,6 +428,7 @@ __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restri
             for (int j = 0; j < P; j++) { float b = m.top[j]; m.top[j] = maxf(minf(a[j], b), -maxf(a[j], b)); }
         } break;
         case GSDF_OP_SMOOTH_UNION: {  // :229-234
+            if (m.skip) { m.skip = false; break; }
             float a[P]; m.popBelow(a);
 #pragma unroll
             for (int j = 0; j < P; j++) {
@@ -590,17 +603,29 @@ __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restri
             }
             m.pushPos(x0, y0, m.pz);
         } break;
-        case GSDF_OP_EXTRUDE_ENTER:  // :524-527  f2=h/2
+        case GSDF_OP_EXTRUDE_ENTER: {  // :524-527  f2=h/2
+            if (h.y & 0xffu) {
+                bool dead = true;
+#pragma unroll
+                for (int j = 0; j < P; j++) dead &= guard_dead(h.y & 0xffu, absf(m.pz[j]) - f2, m.top[j], f3);
+                if (__syncthreads_and(dead)) { m.skip = true; pc = (int)(h.y >> 8); continue; }
+            }
             m.pushD();
 #pragma unroll
             for (int j = 0; j < P; j++) m.top[j] = absf(m.pz[j]) - f2;
-            break;
+        } break;
         case GSDF_OP_REVOLVE:  // :545-547
 #pragma unroll
             for (int j = 0; j < P; j++) { m.px[j] = hypot32(m.px[j], m.pz[j]) - f2; }
             break;
         case GSDF_OP_SCREW_ENTER: {  // threads.go:156-170,198-202  c=(pitch,lead,L/2,tanTaper)
             const float4 c = ldf4(prog, pc + 1);
+            if (h.y & 0xffu) {
+                bool dead = true;
+#pragma unroll
+                for (int j = 0; j < P; j++) dead &= guard_dead(h.y & 0xffu, absf(m.pz[j]) - c.z, m.top[j], f3);
+                if (__syncthreads_and(dead)) { m.skip = true; pc = (int)(h.y >> 8); continue; }
+            }
             m.pushD();
 #pragma unroll
             for (int j = 0; j < P; j++) {

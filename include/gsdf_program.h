@@ -85,11 +85,27 @@ enum gsdf_opcode {
     GSDF_OP_ARRAY_VAR,   /* :345      w1=variant(i|j<<1|k<<2) c1=(sx,sy,sz,_) c2=(nx-1,ny-1,nz-1,_) */
     GSDF_OP_ARRAY2D_VAR, /* :914      w1=variant(i|j<<1) c1=(sx,sy,nx-1,ny-1) */
     GSDF_OP_CIRC_ENTER,  /* :1042,1094 c1=(angle,ncirc,ninsm1,_) : P.push(p0) ; p=p1 */
-    GSDF_OP_EXTRUDE_ENTER, /* :506    w2=h/2 : push(|z|-h/2) */
+    GSDF_OP_EXTRUDE_ENTER, /* :506    w1=guard w2=h/2 w3=guard k : push(|z|-h/2) */
     GSDF_OP_REVOLVE,     /* :533      w2=off : p=(hypot(x,z)-off, y) */
-    GSDF_OP_SCREW_ENTER, /* threads.go:141-170 c1=(pitch,lead,L/2,tanTaper) : push(|z|-L/2) ; p=(saw,y) */
+    GSDF_OP_SCREW_ENTER, /* threads.go:141-170 w1=guard w3=guard k c1=(pitch,lead,L/2,tanTaper) : push(|z|-L/2) ; p=(saw,y) */
     GSDF_OP__COUNT
 };
+
+/* Slab guards -- the one place the stream has control flow, and it is CTA-uniform and value-preserving.
+ *
+ * An extrude or screw node returns a value s >= w = |z| - h/2 in its own frame (cpu_evaluators.go:524-529: the
+ * extrusion formula is >= its w argument; threads.go:176-180: max(profile, w)).  w is known at the ENTER op, before
+ * any of the 2-D work below it (a 100-edge polygon for a thread profile).  When that node is the later operand of a
+ * combiner whose result cannot depend on any s >= w, the whole subtree is dead for that point:
+ *     GSDF_GUARD_DIFF          a=top:  -w < a            =>  max(a, -s) == a
+ *     GSDF_GUARD_MIN           a=top:   w > a            =>  min(a, s)  == a
+ *     GSDF_GUARD_SMOOTH_UNION  a=top:   w - a >= k, a!=0 =>  h clamps to 1 and the blend returns a bit for bit
+ * ENTER's w1 = kind | target<<8.  If the predicate holds for EVERY point of the CTA's tile (one __syncthreads_and) the
+ * interpreter jumps to chunk `target` (just behind the node's exit op; restoring POP_POS ops still run) and the next
+ * combiner is a no-op that leaves a on top.  Otherwise the tile runs the full stream.  Either way each point's result
+ * is bit-identical to the unguarded program's.  Work tiles are runs of neighbouring lattice cells, so the predicate
+ * is uniform over most tiles of a part whose threaded/extruded feature occupies a fraction of its volume. */
+enum gsdf_guard_kind { GSDF_GUARD_NONE = 0, GSDF_GUARD_DIFF = 1, GSDF_GUARD_MIN = 2, GSDF_GUARD_SMOOTH_UNION = 3 };
 
 /* Header that precedes the instruction chunks in the blob handed to gsdf_program_create (one 16-byte chunk x2). */
 typedef struct {

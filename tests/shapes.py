@@ -145,6 +145,26 @@ def threads3d(bld):
     ]
 
 
+def guards3d(bld):
+    """Screw / extrude nodes as the later operand of difference, union and smooth union -- the positions where the
+    flattener plants slab guards (include/gsdf_program.h) -- directly and through translate / transform / symmetry."""
+    T = gsdf.threads
+    star = bld.NewPolygon(nagon(7, 0.9))
+    ext = bld.Extrude(star, 0.6)
+    screw = T.Screw(bld, 2.0, T.ISO(1, 0.25, True))
+    return [
+        ("diff_box_extrude", bld.Difference(bld.NewBox(2.4, 2.4, 2.0, 0.1), bld.Translate(ext, 0.2, 0.1, 0.5))),
+        ("union_sphere_extrude", bld.Union(bld.Translate(ext, 0, 0, -1.2), bld.NewSphere(0.7), bld.Translate(ext, 0.3, 0, 1.4))),
+        ("smoothunion_cyl_extrude", bld.SmoothUnion(0.25, bld.NewCylinder(0.5, 3.0, 0.05), bld.Translate(ext, 0, 0, 0.9))),
+        ("smoothunion_extrude_first", bld.SmoothUnion(0.25, bld.Translate(ext, 0, 0, 0.9), bld.NewCylinder(0.5, 3.0, 0.05))),
+        ("diff_cyl_rotated_screw", bld.Difference(bld.NewCylinder(1.1, 3.0, 0), bld.Rotate(screw, 0.4, (1, 0.2, 0)))),
+        ("union_screw_symmetry", bld.Union(bld.NewBox(0.8, 0.8, 3.5, 0), bld.Symmetry(bld.Translate(screw, 1.3, 0, 0), True, False, False))),
+        ("nested_guards", bld.Union(bld.NewSphere(0.5), bld.Translate(bld.Difference(bld.NewCylinder(0.9, 1.2, 0), screw), 0, 0, 1.6))),
+        ("guard_under_scale", bld.Scale(bld.Difference(bld.NewSphere(1.2), bld.Translate(ext, 0, 0, 0.8)), 2.5)),
+        ("union_two_extrudes", bld.Union(ext, bld.Translate(bld.Extrude(bld.NewCircle(0.4), 2.5), 0.2, 0, 0))),
+    ]
+
+
 def threads2d(bld):
     T = gsdf.threads
     return [("iso_ext_profile", T.Thread(bld, T.ISO(1, 0.1, True))), ("npt_profile", T.Thread(bld, T.NPT(0.5)))]
@@ -156,7 +176,7 @@ def scenes3d(bld):
 
 
 def all3d(bld):
-    return primitives3d(bld) + binops3d(bld) + unary3d(bld) + threads3d(bld) + scenes3d(bld)
+    return primitives3d(bld) + binops3d(bld) + unary3d(bld) + threads3d(bld) + scenes3d(bld) + guards3d(bld)
 
 
 def all2d(bld):

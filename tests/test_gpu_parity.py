@@ -7,6 +7,7 @@ import ctypes as C
 import hashlib
 import io
 import os
+import struct
 
 import numpy as np
 import pytest
@@ -43,7 +44,7 @@ def check_field(name, s, oracle, pos):
 
 
 # ---------------------------------------------------------------------------------------------- Evaluate parity
-@pytest.mark.parametrize("corpus", ["primitives3d", "binops3d", "unary3d", "threads3d", "scenes3d",
+@pytest.mark.parametrize("corpus", ["primitives3d", "binops3d", "unary3d", "threads3d", "scenes3d", "guards3d",
                                     "primitives2d", "binops2d", "unary2d", "threads2d"])
 def test_evaluate_matches_oracle_on_reference_lattices(oracle, bld, corpus):
     """testShader3D/testShader2D (gsdf_test.go:429-525): sample the AppendGrid lattice of Bounds()."""
@@ -120,6 +121,37 @@ def test_program_create_rejects_malformed_blobs(bld):
     assert _lib.lib.gsdf_program_create(bytes(blob), len(blob), None, 0, C.byref(h)) == _lib.EPROGRAM
     blob = bytearray(f["blob"])[:-16]  # END chopped off
     assert _lib.lib.gsdf_program_create(bytes(blob), len(blob), None, 0, C.byref(h)) == _lib.EPROGRAM
+
+
+def test_slab_guards_do_not_change_a_single_bit(oracle, bld, monkeypatch):
+    """Dense x-fastest lattices, so whole CTA tiles lie outside the guarded slab and really take the skip: the guarded
+    program, the unguarded program (GSDF_NO_GUARDS=1 at flatten time) and the oracle agree bit for bit."""
+    for name, s in shapes.guards3d(bld) + [("npt-flange", gsdf.scene(bld, "npt-flange")), ("bolt", gsdf.scene(bld, "bolt"))]:
+        pos = shapes.sample_points(s, margin=0.3, dense=(96, 40, 48))
+        guarded, _ = gpu_eval(s, pos)
+        with monkeypatch.context() as mp:
+            mp.setenv("GSDF_NO_GUARDS", "1")
+            plain, _ = gpu_eval(s, pos)
+        assert np.array_equal(bits(guarded), bits(plain)), name
+        t = oracle.Tree.from_shader(s)
+        assert np.array_equal(bits(guarded), bits(t.eval3(pos))), name
+
+
+def test_program_create_rejects_bad_guard_targets(bld):
+    s = shapes.guards3d(bld)[0][1]
+    f = bld.flatten(s)
+    words = np.frombuffer(f["blob"], np.uint32, offset=32).reshape(-1, 4)
+    at = [i for i in range(len(words)) if (int(words[i, 1]) & 0xff) == 1 and (int(words[i, 1]) >> 8) > i][0]
+    h = C.c_void_p()
+    aux = np.ascontiguousarray(f["aux"], np.float32)
+    auxp = aux.ctypes.data_as(C.POINTER(C.c_float))
+    for bad in (at, 1 << 20, at + 1):  # not forward, out of range, the very next chunk
+        blob = bytearray(f["blob"])
+        struct.pack_into("<I", blob, 32 + 16 * at + 4, 1 | (bad << 8))
+        assert _lib.lib.gsdf_program_create(bytes(blob), len(blob), auxp, aux.size, C.byref(h)) == _lib.EPROGRAM, bad
+    blob = bytearray(f["blob"])
+    struct.pack_into("<I", blob, 32 + 16 * at + 4, 9 | (int(words[at, 1]) >> 8 << 8))  # unknown guard kind
+    assert _lib.lib.gsdf_program_create(bytes(blob), len(blob), auxp, aux.size, C.byref(h)) == _lib.EPROGRAM
 
 
 def test_evaluate_device_pointers(oracle, bld):

@@ -242,3 +242,56 @@ def test_read_binary_stl_validation(oracle, bld):
     bad[84 + 24:84 + 48] = bad[84 + 12:84 + 24] * 2                     # all three vertices equal -> degenerate
     with pytest.raises(gsdf_b200.GsdfError):
         glrender.ReadBinarySTL(io.BytesIO(bytes(bad)))
+
+
+def _instructions(blob):
+    nchunks = struct.unpack_from("<8I", blob, 0)[2]
+    words = np.frombuffer(blob, np.uint32, offset=32).reshape(-1, 4)
+    pc, out = 0, []
+    while pc < nchunks:
+        op, ln = int(words[pc, 0]) & 0xff, (int(words[pc, 0]) >> 8) & 0xff
+        out.append((pc, op, ln, int(words[pc, 1])))
+        pc += ln
+    return out
+
+
+def _opcodes():
+    import re
+    src = open(os.path.join(os.path.dirname(__file__), "..", "include", "gsdf_program.h")).read()
+    body = src[src.index("enum gsdf_opcode {"):src.index("GSDF_OP__COUNT")]
+    return {n[len("GSDF_OP_"):]: i for i, n in enumerate(re.findall(r"^\s*(GSDF_OP_[A-Z0-9_]+)", body, re.M))}
+
+
+def test_slab_guards_are_planted_where_they_are_sound(bld, monkeypatch):
+    """include/gsdf_program.h "slab guards": a screw/extrude that is the LATER operand of difference / union / smooth
+    union (through position-only wrappers) carries a guard whose target is the instruction right behind its own exit
+    op; first operands, intersections and distance-changing wrappers carry none."""
+    OP = _opcodes()
+    enter = {OP["EXTRUDE_ENTER"]: OP["EXTRUDE_EXIT"], OP["SCREW_ENTER"]: OP["MAX_BELOW"]}
+    want = {"diff_box_extrude": [1], "union_sphere_extrude": [2, 2], "smoothunion_cyl_extrude": [3],
+            "smoothunion_extrude_first": [0], "diff_cyl_rotated_screw": [1], "union_screw_symmetry": [2],
+            "nested_guards": [1], "guard_under_scale": [1], "union_two_extrudes": [0, 2]}
+    for name, s in shapes.guards3d(bld):
+        ins = _instructions(bld.flatten(s)["blob"])
+        kinds = []
+        for i, (pc, op, ln, w1) in enumerate(ins):
+            if op not in enter:
+                continue
+            kinds.append(w1 & 0xff)
+            if w1 & 0xff:
+                depth, j = 0, i
+                while True:  # the matching exit op of this node
+                    if ins[j][1] in enter: depth += 1
+                    if ins[j][1] in enter.values():
+                        depth -= 1
+                        if depth == 0: break
+                    j += 1
+                assert w1 >> 8 == ins[j + 1][0], name
+        assert kinds == want[name], (name, kinds)
+    # the flange's nut thread and the bolt's screw are the benchmark scenes' guarded nodes
+    for scene, kind in (("npt-flange", 1), ("bolt", 2)):
+        ins = _instructions(bld.flatten(gsdf.scene(bld, scene))["blob"])
+        assert [w1 & 0xff for pc, op, ln, w1 in ins if op == OP["SCREW_ENTER"]] == [kind], scene
+    monkeypatch.setenv("GSDF_NO_GUARDS", "1")
+    for name, s in shapes.guards3d(bld):
+        assert all((w1 & 0xff) == 0 for pc, op, ln, w1 in _instructions(bld.flatten(s)["blob"]) if op in enter), name
