@@ -25,6 +25,10 @@ class Lattice(C.Structure):
     _fields_ = [("origin", C.c_float * 3), ("res", C.c_float), ("n", C.c_int32 * 3)]
 
 
+class ColorConv(C.Structure):  # gsdf_colorconv
+    _fields_ = [("kind", C.c_int32), ("p", C.c_float * 7), ("c0", C.c_uint32), ("c1", C.c_uint32)]
+
+
 class TreeNode(C.Structure):  # gsdf_tree_node, 96 bytes
     _fields_ = [("kind", C.c_int32), ("nchild", C.c_int32), ("child_off", C.c_int32), ("aux_off", C.c_int32),
                 ("aux_cnt", C.c_int32), ("iparam", C.c_int32 * 3), ("fparam", C.c_float * 16)]
@@ -70,6 +74,11 @@ def _load():
         "gsdf_stl_pack": (C.c_int64, [vp, C.c_size_t, vp, C.c_size_t]),
         "gsdf_mesh_stl": (C.c_int64, [vp, vp, C.c_size_t]),
         "gsdf_image_eval2": (C.c_int, [vp, f32p, f32p, C.c_int, C.c_int, vp]),
+        "gsdf_colorconv_inigo_quilez": (C.c_int, [C.c_float, C.POINTER(ColorConv)]),
+        "gsdf_colorconv_linear_gradient": (C.c_int, [C.c_float, C.c_uint32, C.c_uint32, C.POINTER(ColorConv)]),
+        "gsdf_image_render2": (C.c_int, [vp, f32p, f32p, C.c_int, C.c_int, C.POINTER(ColorConv), vp]),
+        "gsdf_image_eval2_device": (C.c_int, [vp, f32p, f32p, C.c_int, C.c_int, vp, vp]),
+        "gsdf_image_render2_device": (C.c_int, [vp, f32p, f32p, C.c_int, C.c_int, C.POINTER(ColorConv), vp, vp]),
         # include/gsdf_host.h
         "gsdfh_builder_new": (vp, []),
         "gsdfh_builder_free": (None, [vp]),
@@ -85,6 +94,19 @@ def _load():
         "gsdfh_bolt": (C.c_int32, [vp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]),
         "gsdfh_hexhead": (C.c_int32, [vp, C.c_float, C.c_float, C.c_int, C.c_int]),
         "gsdfh_scene": (C.c_int32, [vp, C.c_char_p, C.c_float]),
+        "gsdfh_font_new": (vp, []),
+        "gsdfh_font_free": (None, [vp]),
+        "gsdfh_font_err": (C.c_char_p, [vp]),
+        "gsdfh_font_configure": (C.c_int, [vp, C.c_float]),
+        "gsdfh_font_load_ttf": (C.c_int, [vp, vp, C.c_size_t]),
+        "gsdfh_font_textline": (C.c_int32, [vp, vp, C.c_char_p]),
+        "gsdfh_font_glyph": (C.c_int32, [vp, vp, C.c_uint32]),
+        "gsdfh_font_kern": (C.c_float, [vp, C.c_uint32, C.c_uint32]),
+        "gsdfh_font_advance_width": (C.c_float, [vp, C.c_uint32]),
+        "gsdfh_font_scaleout": (C.c_float, [vp]),
+        "gsdfh_font_glyph_index": (C.c_int32, [vp, C.c_uint32]),
+        "gsdfh_font_glyph_segments": (C.c_int32, [vp, C.c_int32, i32p, C.c_int32]),
+        "gsdfh_font_info": (C.c_int, [vp, i32p]),
         "gsdfh_tree": (C.c_int, [vp, C.POINTER(C.POINTER(TreeNode)), i32p, C.POINTER(i32p), i32p, C.POINTER(f32p), i32p]),
         "gsdfh_flatten": (vp, [vp, C.c_int32]),
         "gsdfh_flat_blob": (vp, [vp, C.POINTER(C.c_size_t)]),

@@ -387,25 +387,95 @@ int gsdf_grid_eval(gsdf_program *p, const gsdf_lattice *lat, int k0, int k1, flo
     return 0;
 }
 
-int gsdf_image_eval2(gsdf_program *p, const float bbmin[2], const float bbmax[2], int w, int h, float *dist) {
-    if (!p || !bbmin || !bbmax || !dist) return fail(GSDF_EINVAL, "gsdf_image_eval2: NULL argument");
+// out: HOST pointer when d_out is NULL (staged through the handle's buffer and copied back), else ignored and the image is
+// written straight to the DEVICE buffer d_out on `stream` with no synchronisation.
+static int image_run(gsdf_program *p, const float bbmin[2], const float bbmax[2], int w, int h, const gsdf_colorconv *conv, void *out,
+                     bool color, void *d_out = nullptr, void *stream = nullptr) {
+    if (!p || !bbmin || !bbmax || (!out && !d_out)) return fail(GSDF_EINVAL, "gsdf_image: NULL argument");
     if (p->dim != 2) return fail(GSDF_EINVAL, "program is not 2D");
     if (w <= 0 || h <= 0) return fail(GSDF_EINVAL, "bad image size");
+    if (conv && (conv->kind < GSDF_CONV_DEFAULT || conv->kind > GSDF_CONV_HSV_GRADIENT)) return fail(GSDF_EINVAL, "unknown colour conversion %d", conv->kind);
     CU(cudaSetDevice(p->device));
     const size_t n = (size_t)w * h;
-    int rc = grow(p->d_dist, p->dist_cap, n);
+    int rc = d_out ? 0 : grow(p->d_dist, p->dist_cap, n);  // 4 B/pixel either way (float or RGBA8)
     if (rc) return rc;
-    GenImage g;
+    float *target = d_out ? static_cast<float *>(d_out) : p->d_dist;
+    cudaStream_t st = d_out && stream ? (cudaStream_t)stream : p->stream;
+    GenImage g{};
     g.dx = (bbmax[0] - bbmin[0]) / (float)w;  // image.go:85-87
     g.dy = (bbmax[1] - bbmin[1]) / (float)h;
     g.xmin = bbmin[0] + g.dx / 2;
-    g.ymax = bbmax[1];
-    g.w = w; g.h = h; g.dist = p->d_dist;
-    rc = launch_eval<4>(p, g, (uint64_t)((w + 3) / 4) * h, p->stream);
+    g.ymax = bbmax[1];                        // un-shifted Max, image.go:92
+    g.w = w; g.h = h; g.dist = target;
+    g.rgba = color ? reinterpret_cast<uint32_t *>(target) : nullptr;
+    g.cc.kind = GSDF_CONV_DEFAULT;
+    if (conv) { g.cc.kind = conv->kind; for (int i = 0; i < 7; i++) g.cc.p[i] = conv->p[i]; g.cc.c0 = conv->c0; g.cc.c1 = conv->c1; }
+    rc = launch_eval<4>(p, g, (uint64_t)((w + 3) / 4) * h, st);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(dist, p->d_dist, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaStreamSynchronize(p->stream));
     p->evals += n;
+    if (d_out) return 0;
+    CU(cudaMemcpyAsync(out, p->d_dist, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int gsdf_image_eval2_device(gsdf_program *p, const float bbmin[2], const float bbmax[2], int w, int h, float *d_dist, void *stream) {
+    if (!d_dist || ((uintptr_t)d_dist & 15)) return fail(GSDF_EINVAL, "gsdf_image_eval2_device: d_dist must be a 16-byte aligned device pointer");
+    return image_run(p, bbmin, bbmax, w, h, nullptr, nullptr, false, d_dist, stream);
+}
+
+int gsdf_image_render2_device(gsdf_program *p, const float bbmin[2], const float bbmax[2], int w, int h, const gsdf_colorconv *conv,
+                              uint8_t *d_rgba, void *stream) {
+    if (!d_rgba || ((uintptr_t)d_rgba & 15)) return fail(GSDF_EINVAL, "gsdf_image_render2_device: d_rgba must be a 16-byte aligned device pointer");
+    return image_run(p, bbmin, bbmax, w, h, conv, nullptr, true, d_rgba, stream);
+}
+
+int gsdf_image_eval2(gsdf_program *p, const float bbmin[2], const float bbmax[2], int w, int h, float *dist) {
+    return image_run(p, bbmin, bbmax, w, h, nullptr, dist, false);
+}
+
+int gsdf_image_render2(gsdf_program *p, const float bbmin[2], const float bbmax[2], int w, int h, const gsdf_colorconv *conv, uint8_t *rgba) {
+    return image_run(p, bbmin, bbmax, w, h, conv, rgba, true);
+}
+
+int gsdf_colorconv_inigo_quilez(float characteristic_distance, gsdf_colorconv *out) {
+    if (!out) return fail(GSDF_EINVAL, "gsdf_colorconv_inigo_quilez: NULL argument");
+    *out = gsdf_colorconv{};
+    out->kind = GSDF_CONV_INIGO_QUILEZ;
+    out->p[0] = 1.f / characteristic_distance;  // color.go:22
+    return 0;
+}
+
+// gsdfaux/color.go:192-217 on float32
+static void rgb_to_hsv(float r, float g, float b, float &h, float &s, float &v) {
+    const float xmax = std::max(r, std::max(g, b)), xmin = std::min(r, std::min(g, b));
+    const float c = xmax - xmin;
+    v = xmax;
+    h = 0.f; s = 0.f;
+    if (c == 0.f) h = 0.f;
+    else if (v == r) h = (g - b) / (c * 6.f);
+    else if (v == g) h = (float)(1.0 / 3) + (b - r) / (c * 6.f);
+    else if (v == b) h = (float)(2.0 / 3) + (r - g) / (c * 6.f);
+    if (h < 0.f) h += 1.f;
+    if (xmax > 0.f) s = c / xmax;
+}
+
+int gsdf_colorconv_linear_gradient(float gradient_length, uint32_t rgba0, uint32_t rgba1, gsdf_colorconv *out) {
+    if (!out) return fail(GSDF_EINVAL, "gsdf_colorconv_linear_gradient: NULL argument");
+    *out = gsdf_colorconv{};
+    if (rgba0 == 0xff000000u && rgba1 == 0xffffffffu) {  // color.Black -> color.White (color.go:52-54)
+        out->kind = GSDF_CONV_BW_LINEAR;
+        out->p[0] = gradient_length;
+        return 0;
+    }
+    out->kind = GSDF_CONV_HSV_GRADIENT;
+    const uint32_t c[2] = {rgba0, rgba1};
+    for (int i = 0; i < 2; i++)  // colorToHSV (color.go:127-130) on the 8-bit channels
+        rgb_to_hsv((float)(c[i] & 255u) / 255.f, (float)((c[i] >> 8) & 255u) / 255.f, (float)((c[i] >> 16) & 255u) / 255.f, out->p[3 * i], out->p[3 * i + 1],
+                   out->p[3 * i + 2]);
+    out->p[6] = gradient_length;
+    out->c0 = rgba0;
+    out->c1 = rgba1;
     return 0;
 }
 

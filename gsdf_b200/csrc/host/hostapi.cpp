@@ -6,6 +6,7 @@
 #include "../../../include/gsdf_host.h"
 #include "builder.h"
 #include "flatten.h"
+#include "textsdf.h"
 #include "threads.h"
 
 using namespace gsdfhost;
@@ -14,6 +15,10 @@ struct gsdfh_builder {
     Builder b;
     std::string err;      // last fatal error of a C call
     std::string errjoin;  // storage for gsdfh_builder_err
+};
+struct gsdfh_font {
+    textsdf::Font f;
+    std::string err;
 };
 struct gsdfh_flat {
     Program prog;
@@ -170,6 +175,46 @@ int32_t gsdfh_scene(gsdfh_builder *b, const char *name, float param) {
     else return failb(b, "unknown scene: " + n);
     if (id < 0) b->err = err;
     return id;
+}
+
+gsdfh_font *gsdfh_font_new(void) { return new gsdfh_font(); }
+void gsdfh_font_free(gsdfh_font *f) { delete f; }
+const char *gsdfh_font_err(gsdfh_font *f) { return f->err.c_str(); }
+int gsdfh_font_configure(gsdfh_font *f, float tol) { f->err.clear(); return f->f.Configure(tol, f->err) ? 0 : GSDF_EINVAL; }
+int gsdfh_font_load_ttf(gsdfh_font *f, const void *ttf, size_t n) {
+    f->err.clear();
+    if (!ttf) { f->err = "nil font data"; return GSDF_EINVAL; }
+    return f->f.LoadTTFBytes(static_cast<const uint8_t *>(ttf), n, f->err) ? 0 : GSDF_EINVAL;
+}
+int32_t gsdfh_font_textline(gsdfh_font *f, gsdfh_builder *b, const char *utf8) {
+    f->err.clear();
+    return f->f.TextLine(b->b, utf8 ? utf8 : "", f->err);
+}
+int32_t gsdfh_font_glyph(gsdfh_font *f, gsdfh_builder *b, uint32_t rune) {
+    f->err.clear();
+    return f->f.Glyph(b->b, rune, f->err);
+}
+float gsdfh_font_kern(gsdfh_font *f, uint32_t c0, uint32_t c1) { return f->f.loaded() ? f->f.Kern(c0, c1) : 0.f; }
+float gsdfh_font_advance_width(gsdfh_font *f, uint32_t c) { return f->f.loaded() ? f->f.AdvanceWidth(c) : 0.f; }
+float gsdfh_font_scaleout(gsdfh_font *f) { return f->f.loaded() ? f->f.scaleout() : 0.f; }
+int32_t gsdfh_font_glyph_index(gsdfh_font *f, uint32_t rune) { return f->f.loaded() ? f->f.sfnt().GlyphIndex(rune) : -1; }
+int32_t gsdfh_font_glyph_segments(gsdfh_font *f, int32_t gi, int32_t *out7, int32_t maxseg) {
+    f->err.clear();
+    if (!f->f.loaded()) { f->err = "textsdf: no font loaded"; return -1; }
+    std::vector<textsdf::Segment> segs;
+    if (!f->f.sfnt().LoadGlyph(gi, f->f.sfnt().UnitsPerEm(), segs, f->err)) return -1;
+    if (out7)
+        for (int32_t i = 0; i < (int32_t)segs.size() && i < maxseg; i++) {
+            out7[7 * i] = segs[i].op;
+            for (int k = 0; k < 3; k++) { out7[7 * i + 1 + 2 * k] = segs[i].x[k]; out7[7 * i + 2 + 2 * k] = segs[i].y[k]; }
+        }
+    return (int32_t)segs.size();
+}
+int gsdfh_font_info(gsdfh_font *f, int32_t info[6]) {
+    if (!f->f.loaded()) return GSDF_EINVAL;
+    info[0] = f->f.sfnt().UnitsPerEm(); info[1] = f->f.sfnt().NumGlyphs();
+    f->f.sfnt().Bounds(f->f.sfnt().UnitsPerEm(), info + 2);
+    return 0;
 }
 
 int gsdfh_tree(gsdfh_builder *b, const gsdf_tree_node **nodes, int32_t *nnodes, const int32_t **children, int32_t *nchildren,

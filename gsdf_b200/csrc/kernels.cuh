@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "colormap.cuh"
 #include "interp.cuh"
 #include "mc_tables.cuh"
 
@@ -254,9 +255,10 @@ struct GenCenters {
     __device__ void store(uint64_t w, const float (&d)[1]) const { mask[w] = fabsf(d[0]) >= maxDist ? 0 : 1; }
 };
 
-// ImageRendererSDF2.Render positions (glrender/image.go:85-105).
+// ImageRendererSDF2.Render positions (glrender/image.go:85-105). rgba != nullptr: the colour conversion is applied in
+// the sink and four RGBA8 pixels leave as one 16-byte store (image.go:112-116 fused); else the distances are stored.
 struct GenImage {
-    float xmin, ymax, dx, dy; int w, h; float *dist;
+    float xmin, ymax, dx, dy; int w, h; float *dist; uint32_t *rgba; ColorConv cc;
     __device__ uint64_t work_items() const { return (uint64_t)((w + 3) / 4) * h; }
     __device__ void load(uint64_t wi, float (&x)[4], float (&y)[4], float (&z)[4]) const {
         const uint32_t nq = (uint32_t)(w + 3) / 4;
@@ -271,6 +273,19 @@ struct GenImage {
     __device__ void store(uint64_t wi, const float (&d)[4]) const {
         const uint32_t nq = (uint32_t)(w + 3) / 4;
         const int q = (int)((uint32_t)wi % nq), j = (int)((uint32_t)wi / nq);
+        if (rgba) {
+            uint32_t c[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) c[t] = color_of(cc, d[t]);
+            uint32_t *row = rgba + (size_t)j * w;
+            if ((w & 3) == 0) {
+                *reinterpret_cast<uint4 *>(row + 4 * q) = make_uint4(c[0], c[1], c[2], c[3]);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; t++) if (4 * q + t < w) row[4 * q + t] = c[t];
+            }
+            return;
+        }
         float *row = dist + (size_t)j * w;
         if ((w & 3) == 0) {
             *reinterpret_cast<float4 *>(row + 4 * q) = make_float4(d[0], d[1], d[2], d[3]);

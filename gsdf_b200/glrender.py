@@ -270,3 +270,35 @@ def ImageEvaluateSDF2(sdf2, width, height):
     b = (C.c_float * 2)(float(mx[0]), float(mx[1]))
     check(lib.gsdf_image_eval2(sdf2._h, a, b, int(width), int(height), C.c_void_p(out.ctypes.data)))
     return out
+
+
+class ImageRendererSDF2:
+    """glrender.ImageRendererSDF2 (image.go:20-118) with the colour conversion applied on the device.
+
+    `conversion` is None (black inside / white outside / red NaN, image.go:50-61) or a _lib.ColorConv made by
+    gsdfaux.ColorConversionLinearGradient / ColorConversionInigoQuilez -- the reference takes a Go closure; the
+    closures gsdfaux provides are data here so the kernel that evaluates a pixel also colours it."""
+
+    def __init__(self, evalBufferSize, conversion=None):
+        if evalBufferSize < 4096:
+            raise GsdfError(_lib.EINVAL, "too small evaluation buffer size")  # image.go:46-48
+        if conversion is not None and not isinstance(conversion, _lib.ColorConv):
+            raise GsdfError(_lib.EINVAL, "conversion must be None or a gsdfaux.ColorConversion* value")
+        self.evalBufferSize, self.conv = int(evalBufferSize), conversion
+
+    def Render(self, sdf2, img, userData=None):
+        """Fills img, a uint8 array (height, width, 4) in image.RGBA.Pix order. userData is ignored (gpu.go:82)."""
+        if not (isinstance(img, np.ndarray) and img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 4 and img.flags.c_contiguous):
+            raise GsdfError(_lib.EINVAL, "img must be a C-contiguous uint8 array (height, width, 4)")
+        h, w = img.shape[:2]
+        if self.evalBufferSize < w:  # image.go:80-82
+            raise GsdfError(_lib.EINVAL, "require evaluation buffer (%d) to be at least of length of image rows (%d)" % (self.evalBufferSize, w))
+        mn, mx = sdf2.Bounds()
+        a = (C.c_float * 2)(float(mn[0]), float(mn[1]))
+        b = (C.c_float * 2)(float(mx[0]), float(mx[1]))
+        check(lib.gsdf_image_render2(sdf2._h, a, b, int(w), int(h), C.byref(self.conv) if self.conv is not None else None,
+                                     C.c_void_p(img.ctypes.data)))
+
+
+def NewImageRendererSDF2(evalBufferSize, conversion=None):
+    return ImageRendererSDF2(evalBufferSize, conversion)

@@ -201,6 +201,15 @@ class Builder:
         auxv = np.ctypeslib.as_array(aux, shape=(na.value,)).copy() if na.value else np.zeros(0, np.float32)
         return nb, chv, auxv
 
+    def tree_nodes(self):
+        """The node table as a list of TreeNode records (kind, nchild, child_off, aux_off, aux_cnt, iparam, fparam)."""
+        nb, _, _ = self.tree_table()
+        n = len(nb) // C.sizeof(_lib.TreeNode)
+        return list((_lib.TreeNode * n).from_buffer_copy(nb)) if n else []
+
+    def tree_children(self):
+        return self.tree_table()[1]
+
     def flatten(self, root):
         """Flattener output for inspection: dict(blob, aux, dim, ninstr, nchunks, dstack, pstack)."""
         f = lib.gsdfh_flatten(self._h, root.id)

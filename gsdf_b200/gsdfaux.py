@@ -1,11 +1,68 @@
 """Mirror of the reference's driver gsdfaux.RenderShader3D (gsdfaux/gsdfaux.go:63-241) for the CUDA backend: pick the
 evaluator, pick the renderer, RenderAll, log what the reference logs, WriteBinarySTL. It is the CALLER of the hot
 path, kept thin; bench.py measures the same sequence."""
+import ctypes as C
+import struct
 import time
+import zlib
 
 import numpy as np
 
-from . import gleval, glrender
+from . import _lib, gleval, glrender
+from .gsdf import _hypot32
+from ._lib import check, lib
+
+Black, White = 0xff000000, 0xffffffff  # color.Black / color.White as R | G<<8 | B<<16 | A<<24
+
+
+def RGBA(r, g, b, a=255):
+    """color.RGBA{r,g,b,a} packed the way gsdf_colorconv takes colours."""
+    return (int(r) & 255) | (int(g) & 255) << 8 | (int(b) & 255) << 16 | (int(a) & 255) << 24
+
+
+def ColorConversionInigoQuilez(characteristicDistance):
+    """gsdfaux.ColorConversionInigoQuilez (color.go:21-47) as data for the fused image kernel."""
+    cc = _lib.ColorConv()
+    check(lib.gsdf_colorconv_inigo_quilez(float(characteristicDistance), C.byref(cc)))
+    return cc
+
+
+def ColorConversionLinearGradient(gradientLength, c0, c1):
+    """gsdfaux.ColorConversionLinearGradient (color.go:51-73); Black -> White selects the grayscale form (:52-54)."""
+    cc = _lib.ColorConv()
+    check(lib.gsdf_colorconv_linear_gradient(float(gradientLength), int(c0), int(c1), C.byref(cc)))
+    return cc
+
+
+def _png_bytes(img):
+    """Minimal RGBA8 PNG encoder (image/png's role in RenderPNGFile, gsdfaux.go:289): filter 0, one IDAT."""
+    h, w = img.shape[:2]
+    raw = np.empty((h, 1 + 4 * w), np.uint8)
+    raw[:, 0] = 0
+    raw[:, 1:] = img.reshape(h, 4 * w)
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+    return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)) + \
+        chunk(b"IDAT", zlib.compress(raw.tobytes(), 6)) + chunk(b"IEND", b"")
+
+
+def RenderPNGFile(filename, sdf, picHeight, colorConversion=None):
+    """gsdfaux.RenderPNGFile (gsdfaux.go:267-296): width from the aspect ratio (float64 like the reference, :273-274),
+    nil conversion -> Inigo Quilez with characteristic distance Diagonal/3 (:269-271). Returns the RGBA array."""
+    mn, mx = sdf.Bounds()
+    if colorConversion is None:
+        sz = (mx - mn).astype(np.float32)
+        colorConversion = ColorConversionInigoQuilez(_hypot32(sz[0], sz[1]) / np.float32(3))
+    sz = (mx - mn).astype(np.float32)
+    pixPerUnit = float(picHeight) / float(sz[1])
+    picWidth = int(pixPerUnit * float(sz[0]))
+    img = np.empty((int(picHeight), picWidth, 4), np.uint8)
+    renderer = glrender.NewImageRendererSDF2(max(4096, picWidth), colorConversion)
+    renderer.Render(sdf, img)
+    with open(filename, "wb") as fp:
+        fp.write(_png_bytes(img))
+    return img
 
 
 class RenderConfig:

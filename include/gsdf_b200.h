@@ -142,6 +142,35 @@ int64_t gsdf_mesh_stl(gsdf_mesher *m, void *dst, size_t dst_bytes);
  * x_i = float32(i)*dx + (min.x+dx/2), y_j = max.y - float32(j)*dy. dist is a HOST pointer (w*h floats). */
 int gsdf_image_eval2(gsdf_program *p, const float bbmin[2], const float bbmax[2], int w, int h, float *dist);
 
+/* Colour conversion of ImageRendererSDF2 (glrender/image.go:20-24,50-62) fused into the evaluation: the reference calls a
+ * Go closure per pixel through img.Set (image.go:112-116); here the conversions gsdfaux offers are data, applied by
+ * the kernel that produced the distance, and the image leaves the device as RGBA8 (4 B/pixel). */
+typedef enum {
+    GSDF_CONV_DEFAULT = 0,      /* NewImageRendererSDF2(nil): NaN/Inf red, d>0 white, else black (image.go:50-61) */
+    GSDF_CONV_BW_LINEAR = 1,    /* blackAndWhiteLinearSmooth(edge) (gsdfaux/color.go:77-95); edge 0 = hard step (:97-102) */
+    GSDF_CONV_INIGO_QUILEZ = 2, /* ColorConversionInigoQuilez(characteristicDistance) (gsdfaux/color.go:21-47) */
+    GSDF_CONV_HSV_GRADIENT = 3  /* ColorConversionLinearGradient(len, c0, c1), general case (gsdfaux/color.go:51-73) */
+} gsdf_conv_kind;
+typedef struct {
+    int32_t kind;
+    float p[7];      /* BW_LINEAR: p0 = edge; INIGO_QUILEZ: p0 = 1/characteristicDistance; HSV: h0,s0,v0,h1,s1,v1,len */
+    uint32_t c0, c1; /* HSV: end colours as little-endian RGBA8 bytes (R | G<<8 | B<<16 | A<<24) */
+} gsdf_colorconv;
+/* gsdfaux.ColorConversionInigoQuilez (color.go:21): inv = 1/characteristicDistance in float32. */
+int gsdf_colorconv_inigo_quilez(float characteristic_distance, gsdf_colorconv *out);
+/* gsdfaux.ColorConversionLinearGradient(gradientLength, c0, c1) (color.go:51): black -> white selects BW_LINEAR like the
+ * reference (:52-54); other colours are converted to HSV on the host as colorToHSV does (:127-130). rgba = R|G<<8|B<<16|A<<24. */
+int gsdf_colorconv_linear_gradient(float gradient_length, uint32_t rgba0, uint32_t rgba1, gsdf_colorconv *out);
+/* ImageRendererSDF2.Render (glrender/image.go:76-118) with the conversion fused: rgba[j*w+i] = conv(sdf(x_i, y_j)),
+ * positions as gsdf_image_eval2. conv NULL = GSDF_CONV_DEFAULT. rgba is a HOST pointer to w*h*4 bytes (image.RGBA.Pix). */
+int gsdf_image_render2(gsdf_program *p, const float bbmin[2], const float bbmax[2], int w, int h, const gsdf_colorconv *conv,
+                       uint8_t *rgba);
+/* Same two calls into 16-byte aligned DEVICE buffers (w*h floats / w*h*4 bytes) on `stream` (cudaStream_t or NULL = the
+ * handle's stream), no copies and no synchronisation: the image stays in HBM for an on-device consumer. */
+int gsdf_image_eval2_device(gsdf_program *p, const float bbmin[2], const float bbmax[2], int w, int h, float *d_dist, void *stream);
+int gsdf_image_render2_device(gsdf_program *p, const float bbmin[2], const float bbmax[2], int w, int h, const gsdf_colorconv *conv,
+                              uint8_t *d_rgba, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

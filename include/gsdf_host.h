@@ -54,6 +54,32 @@ int32_t gsdfh_hexhead(gsdfh_builder *b, float radius, float height, int round_ne
 /* The example scenes BASELINE.json names: "npt-flange", "bolt", "knurled-cylinder" (param = diameter, 0 -> 20). */
 int32_t gsdfh_scene(gsdfh_builder *b, const char *name, float param);
 
+/* forge/textsdf (font.go): TrueType font -> polygon SDF tree. The font bytes are supplied by the caller (the reference
+ * embeds iso-3098.ttf, embed.go:10-16; this library ships no font). */
+typedef struct gsdfh_font gsdfh_font;
+gsdfh_font *gsdfh_font_new(void);
+void gsdfh_font_free(gsdfh_font *f);
+const char *gsdfh_font_err(gsdfh_font *f);
+/* Font.Configure(FontConfig{RelativeGlyphTolerance}) (font.go:40-51); 0 = default. Returns 0 or <0. */
+int gsdfh_font_configure(gsdfh_font *f, float relative_glyph_tolerance);
+/* Font.LoadTTFBytes (font.go:54-62). */
+int gsdfh_font_load_ttf(gsdfh_font *f, const void *ttf, size_t nbytes);
+/* Font.TextLine(s) (font.go:89-141): utf-8 text -> root node id in builder b, or <0 (gsdfh_font_err). */
+int32_t gsdfh_font_textline(gsdfh_font *f, gsdfh_builder *b, const char *utf8);
+/* Font.Glyph(c) (font.go:159-165). */
+int32_t gsdfh_font_glyph(gsdfh_font *f, gsdfh_builder *b, uint32_t rune);
+/* Font.Kern / Font.AdvanceWidth (font.go:144-156) and the unexported scaleout (font.go:208-212). */
+float gsdfh_font_kern(gsdfh_font *f, uint32_t c0, uint32_t c1);
+float gsdfh_font_advance_width(gsdfh_font *f, uint32_t c);
+float gsdfh_font_scaleout(gsdfh_font *f);
+/* sfnt pieces the reference calls, for parser tests: glyph index of a rune; contour segments of a glyph at
+ * ppem = unitsPerEm as rows {op, x0,y0, x1,y1, x2,y2} (op 0 MoveTo, 1 LineTo, 2 QuadTo, 3 CubeTo; Y down). Returns the
+ * number of segments (call with out==NULL to size), <0 on error. info = {unitsPerEm, numGlyphs, bounds min.x, min.y,
+ * max.x, max.y}. */
+int32_t gsdfh_font_glyph_index(gsdfh_font *f, uint32_t rune);
+int32_t gsdfh_font_glyph_segments(gsdfh_font *f, int32_t glyph_index, int32_t *out7, int32_t max_segments);
+int gsdfh_font_info(gsdfh_font *f, int32_t info[6]);
+
 /* Tree table export (for the CPU oracle in tests). Pointers stay valid until the builder is next mutated. */
 int gsdfh_tree(gsdfh_builder *b, const gsdf_tree_node **nodes, int32_t *nnodes, const int32_t **children, int32_t *nchildren,
                const float **aux, int32_t *naux);

@@ -1262,6 +1262,91 @@ int go_image_eval2(const go_tree *t, const float bbmin[2], const float bbmax[2],
     return err;
 }
 
+/* ---- colour conversions: glrender/image.go:50-61, gsdfaux/color.go ------------------------------------------------
+ * ms1.SmoothStep / ms1.Interp / ms3.InterpElem are from the un-vendored soypat/geometry module (GLSL smoothstep / mix
+ * semantics): parity UNPINNED like the rest of that module. uint8(f) follows Go/amd64: truncate, keep the low byte. */
+static uint32_t go_u(float f) { return (uint32_t)(int32_t)f; }
+static uint32_t go_rgba(uint32_t r, uint32_t g, uint32_t b, uint32_t a) { return (r & 255u) | (g & 255u) << 8 | (b & 255u) << 16 | (a & 255u) << 24; }
+void go_rgb_to_hsv(float r, float g, float b, float hsv[3]) {
+    float xmax = r > g ? (r > b ? r : b) : (g > b ? g : b), xmin = r < g ? (r < b ? r : b) : (g < b ? g : b);
+    float c = xmax - xmin, h = 0, s = 0, v = xmax;
+    if (c == 0) h = 0;
+    else if (v == r) h = (g - b) / (c * 6);
+    else if (v == g) h = (float)(1.0 / 3) + (b - r) / (c * 6);
+    else if (v == b) h = (float)(2.0 / 3) + (r - g) / (c * 6);
+    if (h < 0) h += 1;
+    if (xmax > 0) s = c / xmax;
+    hsv[0] = h; hsv[1] = s; hsv[2] = v;
+}
+static void go_hsv_to_rgb(float h, float s, float v, float *r, float *g, float *b) { /* color.go:165-188 */
+    float c = s * v;
+    float x = c * (1 - fabsf(fmodf(h * 6, 2) - 1));
+    float m = v - c;
+    *r = *g = *b = 0;
+    if (h >= 0 && h <= (float)(1.0 / 6)) { *r = c; *g = x; *b = 0; }
+    else if (h > (float)(1.0 / 6) && h <= (float)(2.0 / 6)) { *r = x; *g = c; *b = 0; }
+    else if (h > (float)(2.0 / 6) && h <= (float)(3.0 / 6)) { *r = 0; *g = c; *b = x; }
+    else if (h > (float)(3.0 / 6) && h <= (float)(4.0 / 6)) { *r = 0; *g = x; *b = c; }
+    else if (h > (float)(4.0 / 6) && h <= (float)(5.0 / 6)) { *r = x; *g = 0; *b = c; }
+    else if (h > (float)(5.0 / 6) && h <= 1.0f) { *r = c; *g = 0; *b = x; }
+    *r += m; *g += m; *b += m;
+}
+uint32_t go_color_of(const go_colorconv *cc, float d) {
+    const uint32_t black = 0xff000000u, white = 0xffffffffu, red = 0xff0000ffu;
+    if (cc->kind == 1) { /* color.go:77-102 */
+        float edge = cc->p[0];
+        if (edge == 0) return d < 0 ? black : white;
+        float blend = d / edge + 0.5f;
+        if (blend <= 0) return black;
+        if (blend >= 1) return white;
+        blend = clampf(blend, 0, 1);
+        uint32_t y = go_u(blend * 255);
+        return go_rgba(y, y, y, 255);
+    }
+    if (cc->kind == 2) { /* color.go:21-47 */
+        if (isnan(d)) return red;
+        d *= cc->p[0];
+        float c[3];
+        if (d > 0) { c[0] = 0.9f; c[1] = 0.6f; c[2] = 0.3f; } else { c[0] = 0.65f; c[1] = 0.85f; c[2] = 1.0f; }
+        float f = 1 - go_exp(-6 * fabsf(d));
+        for (int i = 0; i < 3; i++) c[i] *= f;
+        f = 0.8f + 0.2f * go_cos(150 * d);
+        for (int i = 0; i < 3; i++) c[i] *= f;
+        float t = clampf((fabsf(d) - 0.f) / (0.01f - 0.f), 0, 1);
+        t = t * t * (3 - 2 * t);
+        float mx = 1 - t;
+        for (int i = 0; i < 3; i++) c[i] = c[i] * (1 - mx) + 1.f * mx;
+        return go_rgba(go_u(c[0] * 255), go_u(c[1] * 255), go_u(c[2] * 255), 255);
+    }
+    if (cc->kind == 3) { /* color.go:57-72 */
+        float blend = d / cc->p[6] + 0.5f;
+        if (blend <= 0) return cc->c0;
+        if (blend >= 1) return cc->c1;
+        float h0 = cc->p[0], h1 = cc->p[3];
+        if (h1 - h0 > 0.5f) h0 += 1.0f;
+        else if (h1 - h0 < -0.5f) h1 += 1.0f;
+        float h = h0 * (1 - blend) + h1 * blend;
+        float s_ = cc->p[1] * (1 - blend) + cc->p[4] * blend;
+        float v = cc->p[2] * (1 - blend) + cc->p[5] * blend;
+        float r, g, b;
+        go_hsv_to_rgb(h, s_, v, &r, &g, &b);
+        return go_rgba(go_u(clampf(r, 0, 1) * 255), go_u(clampf(g, 0, 1) * 255), go_u(clampf(b, 0, 1) * 255), 255);
+    }
+    if (isnan(d) || isinf(d)) return red; /* image.go:50-61 */
+    return d > 0 ? white : black;
+}
+int go_image_render2(const go_tree *t, const float bbmin[2], const float bbmax[2], int w, int h, const go_colorconv *cc, uint8_t *rgba) {
+    float *dist = (float *)malloc(sizeof(float) * (size_t)w * h);
+    if (!dist) return -2;
+    int err = go_image_eval2(t, bbmin, bbmax, w, h, dist);
+    go_colorconv def;
+    memset(&def, 0, sizeof def);
+    if (!cc) cc = &def;
+    for (size_t i = 0; !err && i < (size_t)w * h; i++) { uint32_t c = go_color_of(cc, dist[i]); memcpy(rgba + 4 * i, &c, 4); }
+    free(dist);
+    return err;
+}
+
 const int *go_mc_edge_table(void) { return go_mc_edges; }
 const int8_t *go_mc_tri_table(void) { return go_mc_tris; }
 const int *go_mc_pair_table(void) { return go_mc_pairs; }

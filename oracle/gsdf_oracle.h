@@ -130,6 +130,15 @@ int64_t go_stl_read(const uint8_t *src, size_t nbytes, float *tri9, int64_t max_
 /* ---- ImageRendererSDF2 positions (glrender/image.go:76-105) ---- */
 int go_image_eval2(const go_tree *t, const float bbmin[2], const float bbmax[2], int w, int h, float *dist);
 
+/* Colour conversions of the 2-D image path: kind 0 = NewImageRendererSDF2(nil) (glrender/image.go:50-61), 1 =
+ * blackAndWhiteLinearSmooth (gsdfaux/color.go:77-102), 2 = ColorConversionInigoQuilez (:21-47), 3 =
+ * ColorConversionLinearGradient general case (:57-72). p / c0 / c1 as gsdf_colorconv (include/gsdf_b200.h). */
+typedef struct { int32_t kind; float p[7]; uint32_t c0, c1; } go_colorconv;
+uint32_t go_color_of(const go_colorconv *cc, float d);
+void go_rgb_to_hsv(float r, float g, float b, float hsv[3]);     /* gsdfaux/color.go:192-217 */
+/* ImageRendererSDF2.Render (glrender/image.go:76-118) into RGBA8 (image.RGBA.Pix order). */
+int go_image_render2(const go_tree *t, const float bbmin[2], const float bbmax[2], int w, int h, const go_colorconv *cc, uint8_t *rgba);
+
 /* tables, for cross-checking */
 const int *go_mc_edge_table(void);     /* 256 */
 const int8_t *go_mc_tri_table(void);   /* 256*16, -1 terminated */

@@ -33,6 +33,40 @@ class GoLattice(C.Structure):
     _fields_ = [("origin", C.c_float * 3), ("res", C.c_float), ("n", C.c_int32 * 3)]
 
 
+class GoColorConv(C.Structure):  # go_colorconv: same layout as gsdf_colorconv
+    _fields_ = [("kind", C.c_int32), ("p", C.c_float * 7), ("c0", C.c_uint32), ("c1", C.c_uint32)]
+
+
+def colorconv(kind, p=(), c0=0, c1=0):
+    cc = GoColorConv()
+    cc.kind = kind
+    for i, v in enumerate(p):
+        cc.p[i] = float(v)
+    cc.c0, cc.c1 = int(c0), int(c1)
+    return cc
+
+
+def colorconv_linear_gradient(length, rgba0, rgba1):
+    """gsdfaux.ColorConversionLinearGradient (color.go:51-73); colours as R|G<<8|B<<16|A<<24."""
+    if rgba0 == 0xff000000 and rgba1 == 0xffffffff:
+        return colorconv(1, [length])
+    hsv = []
+    for c in (rgba0, rgba1):
+        out = (C.c_float * 3)()
+        f = np.float32
+        lib().go_rgb_to_hsv(f(c & 255) / f(255), f((c >> 8) & 255) / f(255), f((c >> 16) & 255) / f(255), out)
+        hsv += list(out)
+    return colorconv(3, hsv + [length], rgba0, rgba1)
+
+
+def colorconv_inigo_quilez(characteristic):
+    return colorconv(2, [np.float32(1) / np.float32(characteristic)])
+
+
+def color_of(cc, d):
+    return np.array([lib().go_color_of(C.byref(cc), float(v)) for v in np.asarray(d, np.float32).reshape(-1)], np.uint32)
+
+
 _lib = None
 
 
@@ -72,6 +106,12 @@ def lib():
         L.go_stl_read.argtypes = [vp, C.c_size_t, vp, C.c_int64]
         L.go_image_eval2.restype = C.c_int
         L.go_image_eval2.argtypes = [C.POINTER(GoTree), f32p, f32p, C.c_int, C.c_int, vp]
+        L.go_color_of.restype = C.c_uint32
+        L.go_color_of.argtypes = [C.POINTER(GoColorConv), C.c_float]
+        L.go_rgb_to_hsv.restype = None
+        L.go_rgb_to_hsv.argtypes = [C.c_float, C.c_float, C.c_float, f32p]
+        L.go_image_render2.restype = C.c_int
+        L.go_image_render2.argtypes = [C.POINTER(GoTree), f32p, f32p, C.c_int, C.c_int, C.POINTER(GoColorConv), vp]
         L.go_mc_edge_table.restype = C.POINTER(C.c_int)
         L.go_mc_tri_table.restype = C.POINTER(C.c_int8)
         L.go_mc_pair_table.restype = C.POINTER(C.c_int)
@@ -123,6 +163,17 @@ class Tree:
         if rc:
             raise RuntimeError("oracle go_image_eval2 failed: %d" % rc)
         return out
+
+
+def image_render2(tree, bbmin, bbmax, w, h, cc=None):
+    """ImageRendererSDF2.Render: uint8 (h, w, 4)."""
+    out = np.empty((h, w, 4), dtype=np.uint8)
+    a = (C.c_float * 2)(float(bbmin[0]), float(bbmin[1]))
+    b = (C.c_float * 2)(float(bbmax[0]), float(bbmax[1]))
+    rc = lib().go_image_render2(C.byref(tree.c), a, b, w, h, C.byref(cc) if cc is not None else None, out.ctypes.data)
+    if rc:
+        raise RuntimeError("oracle go_image_render2 failed: %d" % rc)
+    return out
 
 
 def flat_lattice(bbmin, bbmax, res):
