@@ -19,6 +19,7 @@ class GsdfError(RuntimeError):
 # gsdf_status (include/gsdf_b200.h)
 OK, EINVAL, ELEN, EEMPTY, ECUDA, ENOMEM, EPROGRAM, ESHORT, ERES = 0, -1, -2, -3, -4, -5, -6, -7, -8
 MESH_PRUNE, MESH_KEEP_CASES, MESH_KEEP_GRID = 1, 2, 4
+DC_NAIVE, DC_LEAST_SQUARES, DC_LEAST_SQUARES_CHISELED = 0, 1, 2
 
 
 class Lattice(C.Structure):
@@ -79,6 +80,13 @@ def _load():
         "gsdf_image_render2": (C.c_int, [vp, f32p, f32p, C.c_int, C.c_int, C.POINTER(ColorConv), vp]),
         "gsdf_image_eval2_device": (C.c_int, [vp, f32p, f32p, C.c_int, C.c_int, vp, vp]),
         "gsdf_image_render2_device": (C.c_int, [vp, f32p, f32p, C.c_int, C.c_int, C.POINTER(ColorConv), vp, vp]),
+        "gsdf_dc_levels": (C.c_int, [f32p, f32p, C.c_float, f32p]),
+        "gsdf_dc_begin": (C.c_int, [vp, f32p, f32p, C.c_float, C.c_int, C.POINTER(vp)]),
+        "gsdf_dc_rerun": (C.c_int, [vp]),
+        "gsdf_dc_read": (C.c_int64, [vp, vp, C.c_size_t]),
+        "gsdf_dc_device_triangles": (C.c_int, [vp, C.POINTER(vp), u64p]),
+        "gsdf_dc_stats": (C.c_int, [vp, u64p]),
+        "gsdf_dc_destroy": (None, [vp]),
         # include/gsdf_host.h
         "gsdfh_builder_new": (vp, []),
         "gsdfh_builder_free": (None, [vp]),

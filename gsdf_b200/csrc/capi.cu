@@ -16,6 +16,7 @@
 #include "../../include/gsdf_b200.h"
 #include "../../include/gsdf_program.h"
 #include "kernels.cuh"
+#include "dualcontour.cuh"
 
 using namespace gsdfk;
 
@@ -820,6 +821,217 @@ void gsdf_mesh_destroy(gsdf_mesher *m) {
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     delete m;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ dual contouring
+struct gsdf_dualcontour {
+    gsdf_program *prog = nullptr;
+    int device = 0;
+    float bbmin[3], bbmax[3], res = 0;
+    int placer = 0, levels = 0;
+    DCGrid G{};
+    float *d_dist = nullptr; size_t dist_cap = 0;
+    uint32_t *d_eidx = nullptr; size_t eidx_cap = 0;
+    uint32_t *d_cubekey = nullptr; size_t cubekey_cap = 0;
+    float4 *d_dc4 = nullptr; size_t dc4_cap = 0;
+    float *d_nrm = nullptr; size_t nrm_cap = 0;
+    float3 *d_fin = nullptr; size_t fin_cap = 0;
+    uint32_t *d_qcount = nullptr; size_t qcount_cap = 0;
+    float *d_tris = nullptr; size_t tri_cap = 0;
+    unsigned long long *d_scanstate = nullptr; size_t scanstate_cap = 0;
+    uint32_t scan_epoch = 0;
+    uint32_t *d_ctr = nullptr;            // [0] scan ticket, [2..3] scan total (u64), [4..5] cubes with neighbours (u64)
+    uint32_t *h_ctr = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    uint64_t ncubes = 0, ntri = 0, with_nb = 0, evals = 0;
+    float ms = 0;
+};
+
+namespace {
+
+int dc_scan(gsdf_dualcontour *d, uint32_t *data, uint32_t n, cudaStream_t st) {
+    const uint64_t ntiles = ((uint64_t)n + kScanTile - 1) / kScanTile;
+    int rc;
+    if (ntiles > d->scanstate_cap) {
+        if ((rc = grow(d->d_scanstate, d->scanstate_cap, (size_t)ntiles))) return rc;
+        CU(cudaMemsetAsync(d->d_scanstate, 0, d->scanstate_cap * sizeof(unsigned long long), st));
+        d->scan_epoch = 0;
+    }
+    if (++d->scan_epoch >= (1u << 29)) {
+        CU(cudaMemsetAsync(d->d_scanstate, 0, d->scanstate_cap * sizeof(unsigned long long), st));
+        d->scan_epoch = 1;
+    }
+    CU(cudaMemsetAsync(d->d_ctr, 0, 4 * sizeof(uint32_t), st));
+    if (n == 0) return 0;
+    k_scan_lookback<<<(unsigned)ntiles, kThreads, 0, st>>>(data, n, d->d_scanstate, d->d_ctr, d->scan_epoch, reinterpret_cast<unsigned long long *>(d->d_ctr + 2));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int dc_run(gsdf_dualcontour *d) {
+    gsdf_program *p = d->prog;
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = p->stream;
+    const DCGrid &G = d->G;
+    int rc;
+    if ((rc = grow(d->d_dist, d->dist_cap, (size_t)G.ncell + 4))) return rc;
+    if ((rc = grow(d->d_eidx, d->eidx_cap, (size_t)G.ncell + 8))) return rc;
+    CU(cudaEventRecord(d->ev[0], st));
+    // Reset: every level-1 cube origin, in octree BFS order (dual_contour.go:37-57)
+    GenDC g{};
+    g.mode = 0; g.G = G; g.dist = d->d_dist;
+    if ((rc = launch_eval<4>(p, g, ((uint64_t)G.ncell + 3) / 4, st))) return rc;
+    k_dc_flags<<<grid_for(G.ncell, 256), 256, 0, st>>>(d->d_dist, G.ncell, G.res, d->d_eidx);
+    CU(cudaGetLastError());
+    if ((rc = dc_scan(d, d->d_eidx, G.ncell, st))) return rc;
+    CU(cudaMemcpyAsync(d->h_ctr, d->d_ctr, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    unsigned long long tot;
+    std::memcpy(&tot, d->h_ctr + 2, 8);
+    d->ncubes = tot;
+    d->ntri = 0; d->with_nb = 0;
+    const uint32_t nc = (uint32_t)d->ncubes;
+    d->evals = (uint64_t)G.ncell + 4ull * nc + (d->placer != GSDF_DC_NAIVE ? 18ull * nc : 0ull);
+    if (nc == 0) {
+        CU(cudaEventRecord(d->ev[1], st));
+        CU(cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&d->ms, d->ev[0], d->ev[1]);
+        return 0;
+    }
+    if ((rc = grow(d->d_cubekey, d->cubekey_cap, (size_t)nc))) return rc;
+    if ((rc = grow(d->d_dc4, d->dc4_cap, (size_t)nc))) return rc;
+    if ((rc = grow(d->d_fin, d->fin_cap, (size_t)nc))) return rc;
+    if ((rc = grow(d->d_qcount, d->qcount_cap, (size_t)nc + 8))) return rc;
+    k_dc_compact<<<grid_for(G.ncell, 256), 256, 0, st>>>(d->d_dist, d->d_eidx, G.ncell, G.res, d->d_cubekey);
+    CU(cudaGetLastError());
+    // RenderAll: origin + edge ends (dual_contour.go:85-107)
+    g.mode = 1; g.cubekey = d->d_cubekey; g.ncubes = nc; g.dc4 = d->d_dc4;
+    if ((rc = launch_eval<4>(p, g, nc, st))) return rc;
+    DCArgs A{};
+    A.G = G; A.dist = d->d_dist; A.eidx = d->d_eidx; A.cubekey = d->d_cubekey; A.ncubes = nc; A.dc4 = d->d_dc4;
+    A.fin = d->d_fin; A.qcount = d->d_qcount; A.placer = d->placer;
+    A.with_neighbors = reinterpret_cast<unsigned long long *>(d->d_ctr + 4);
+    if (d->placer != GSDF_DC_NAIVE) {
+        if ((rc = grow(d->d_nrm, d->nrm_cap, (size_t)nc * 9))) return rc;
+        const double normStep = d->placer == GSDF_DC_LEAST_SQUARES_CHISELED ? 1e-4 : 2e-8;  // vertexplacement.go:42-46
+        float step = (float)normStep;
+        step *= 0.5f;  // gleval.go:54
+        g.mode = 2; g.step = step; g.nrm = d->d_nrm;
+        if ((rc = launch_eval<4>(p, g, (uint64_t)nc * 6, st))) return rc;
+        A.nrm = d->d_nrm;
+        A.sqrtLambda = d->placer == GSDF_DC_LEAST_SQUARES_CHISELED ? (float)(std::sqrt(1e-5) * normStep) : (float)std::sqrt(1e-5);  // :116-122
+    }
+    CU(cudaMemsetAsync(d->d_ctr + 4, 0, 2 * sizeof(uint32_t), st));
+    k_dc_place<<<(nc + 127) / 128, 128, 0, st>>>(A);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(d->h_ctr + 4, d->d_ctr + 4, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if ((rc = dc_scan(d, d->d_qcount, nc, st))) return rc;
+    CU(cudaMemcpyAsync(d->h_ctr, d->d_ctr, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::memcpy(&tot, d->h_ctr + 2, 8);
+    const uint64_t nquads = tot;
+    std::memcpy(&tot, d->h_ctr + 4, 8);
+    d->with_nb = tot;
+    d->ntri = 2 * nquads;
+    if (nquads) {
+        if ((rc = grow(d->d_tris, d->tri_cap, (size_t)nquads * 18))) return rc;
+        A.tris = d->d_tris;
+        k_dc_emit<<<(nc + 127) / 128, 128, 0, st>>>(A);
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(d->ev[1], st));
+    CU(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&d->ms, d->ev[0], d->ev[1]);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gsdf_dc_levels(const float bbmin[3], const float bbmax[3], float res, float origin[3]) {
+    if (!bbmin || !bbmax) return fail(GSDF_EINVAL, "gsdf_dc_levels: NULL argument");
+    if (!(res > 0) || std::isnan(res) || std::isinf(res)) return fail(GSDF_EINVAL, "invalid renderer cube resolution");  // octreerenderer.go:223-225
+    const float sub = res / 2;  // dual_contour.go:31-32: bb = Bounds().Add(-res/2) (a translation)
+    float mn[3], mx[3];
+    for (int a = 0; a < 3; a++) { mn[a] = bbmin[a] + -sub; mx[a] = bbmax[a] + -sub; }
+    const float longAxis = std::fmax(mx[0] - mn[0], std::fmax(mx[1] - mn[1], mx[2] - mn[2]));
+    const int levels = (int)std::ceil(std::log2(longAxis / res)) + 1;  // octreerenderer.go:229-231
+    if (levels <= 1) return fail(GSDF_ERES, "resolution not fine enough for marching cubes");
+    if (origin) { origin[0] = mn[0]; origin[1] = mn[1]; origin[2] = mn[2]; }
+    return levels;
+}
+
+int gsdf_dc_begin(gsdf_program *p, const float bbmin[3], const float bbmax[3], float res, int placer, gsdf_dualcontour **out) {
+    if (!p || !bbmin || !bbmax || !out) return fail(GSDF_EINVAL, "gsdf_dc_begin: NULL argument");
+    if (p->dim != 3) return fail(GSDF_EINVAL, "program is not 3D");
+    if (placer < GSDF_DC_NAIVE || placer > GSDF_DC_LEAST_SQUARES_CHISELED) return fail(GSDF_EINVAL, "nil DualContourer argument to Reset");  // dual_contour.go:28-30
+    float org[3];
+    const int levels = gsdf_dc_levels(bbmin, bbmax, res, org);
+    if (levels < 0) return levels;
+    if (levels > 11) return fail(GSDF_EINVAL, "dual contour octree has %d levels (%d^3 cubes); limit is 11 levels", levels, 1 << (levels - 1));
+    int rc = ensure_device();
+    if (rc) return rc;
+    CU(cudaSetDevice(p->device));
+    gsdf_dualcontour *d = new gsdf_dualcontour();
+    d->prog = p;
+    d->device = p->device;
+    for (int a = 0; a < 3; a++) { d->bbmin[a] = bbmin[a]; d->bbmax[a] = bbmax[a]; }
+    d->res = res; d->placer = placer; d->levels = levels;
+    d->G.ox = org[0]; d->G.oy = org[1]; d->G.oz = org[2]; d->G.res = res;
+    d->G.bits = levels - 1;
+    d->G.ncell = 1u << (3 * (levels - 1));
+    cudaError_t e = cudaMalloc((void **)&d->d_ctr, 8 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&d->h_ctr, 8 * sizeof(uint32_t));
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreate(&d->ev[i]);
+    if (e != cudaSuccess) { gsdf_dc_destroy(d); return fail(GSDF_ECUDA, "dual contour setup: %s", cudaGetErrorString(e)); }
+    rc = dc_run(d);
+    if (rc) { gsdf_dc_destroy(d); return rc; }
+    *out = d;
+    return 0;
+}
+
+int gsdf_dc_rerun(gsdf_dualcontour *d) {
+    if (!d) return fail(GSDF_EINVAL, "gsdf_dc_rerun: NULL renderer");
+    return dc_run(d);
+}
+
+int64_t gsdf_dc_read(gsdf_dualcontour *d, float *tri9, size_t max_tris) {
+    if (!d || (!tri9 && max_tris)) return fail(GSDF_EINVAL, "gsdf_dc_read: NULL argument");
+    CU(cudaSetDevice(d->prog->device));
+    const uint64_t n = std::min<uint64_t>(d->ntri, max_tris);
+    if (n) CU(cudaMemcpy(tri9, d->d_tris, n * 9 * sizeof(float), cudaMemcpyDeviceToHost));
+    return (int64_t)n;
+}
+
+int gsdf_dc_device_triangles(gsdf_dualcontour *d, const float **d_tri9, uint64_t *ntri) {
+    if (!d || !d_tri9 || !ntri) return fail(GSDF_EINVAL, "gsdf_dc_device_triangles: NULL argument");
+    *d_tri9 = d->d_tris;
+    *ntri = d->ntri;
+    return 0;
+}
+
+int gsdf_dc_stats(const gsdf_dualcontour *d, uint64_t stats[6]) {
+    if (!d || !stats) return fail(GSDF_EINVAL, "gsdf_dc_stats: NULL argument");
+    stats[0] = (uint64_t)d->levels; stats[1] = d->ncubes; stats[2] = d->with_nb; stats[3] = d->ntri; stats[4] = d->evals;
+    stats[5] = (uint64_t)(d->ms * 1000.f + 0.5f);  /* microseconds of device time */
+    return 0;
+}
+
+void gsdf_dc_destroy(gsdf_dualcontour *d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    cudaFree(d->d_dist); cudaFree(d->d_eidx); cudaFree(d->d_cubekey); cudaFree(d->d_dc4); cudaFree(d->d_nrm); cudaFree(d->d_fin);
+    cudaFree(d->d_qcount); cudaFree(d->d_tris); cudaFree(d->d_scanstate); cudaFree(d->d_ctr);
+    if (d->h_ctr) cudaFreeHost(d->h_ctr);
+    for (auto &e : d->ev) if (e) cudaEventDestroy(e);
+    delete d;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ------------------------------------------------------------------------------------------------ STL
 static int64_t stl_from_device(const float *d_tri9, uint64_t n, uint8_t *&d_stl, size_t &stl_cap, void *dst, size_t dst_bytes, cudaStream_t st) {

@@ -302,3 +302,68 @@ class ImageRendererSDF2:
 
 def NewImageRendererSDF2(evalBufferSize, conversion=None):
     return ImageRendererSDF2(evalBufferSize, conversion)
+
+
+class DualContourLeastSquares:
+    """glrender.DualContourLeastSquares (dual_contour_vertexplacement.go:16-23): QEF vertex placement."""
+
+    def __init__(self, Chiseled=False):
+        self.Chiseled = bool(Chiseled)
+
+    @property
+    def _kind(self):
+        return _lib.DC_LEAST_SQUARES_CHISELED if self.Chiseled else _lib.DC_LEAST_SQUARES
+
+
+class DualContourNaive:
+    """Mean-of-crossings vertex placement (the DualContourer of dual_contour_test.go:355-389)."""
+    _kind = _lib.DC_NAIVE
+
+
+class DualContourRenderer:
+    """glrender.DualContourRenderer (dual_contour.go:12-218): Reset(sdf, res, vertexPlacer) then RenderAll(dst)."""
+
+    def __init__(self):
+        self._h = None
+
+    def Reset(self, sdf, res, vertexPlacer, userData=None):
+        if vertexPlacer is None or not hasattr(vertexPlacer, "_kind"):
+            raise GsdfError(_lib.EINVAL, "nil DualContourer argument to Reset")  # dual_contour.go:28-30
+        self.Close()
+        mn, mx = sdf.Bounds()
+        a = (C.c_float * 3)(*[float(v) for v in mn])
+        b = (C.c_float * 3)(*[float(v) for v in mx])
+        h = C.c_void_p()
+        check(lib.gsdf_dc_begin(sdf._h, a, b, float(res), int(vertexPlacer._kind), C.byref(h)))
+        self._h, self._sdf = h, sdf
+
+    def Rerun(self):
+        check(lib.gsdf_dc_rerun(self._h))
+
+    def Stats(self):
+        st = (C.c_uint64 * 6)()
+        check(lib.gsdf_dc_stats(self._h, st))
+        return dict(levels=int(st[0]), cubes=int(st[1]), with_neighbors=int(st[2]), triangles=int(st[3]), evals=int(st[4]), device_ms=st[5] / 1000.0)
+
+    def RenderAll(self, dst=None, userData=None):
+        """Appends the mesh to dst (float32 (n,3,3) or None) and returns the result, like RenderAll(dst, userData)."""
+        if self._h is None:
+            raise GsdfError(_lib.EINVAL, "DualContourRenderer.RenderAll before Reset")
+        n = self.Stats()["triangles"]
+        out = np.empty((n, 3, 3), np.float32)
+        if n:
+            check(lib.gsdf_dc_read(self._h, C.c_void_p(out.ctypes.data), n))
+        if dst is not None and len(dst):
+            return np.concatenate([np.asarray(dst, np.float32).reshape(-1, 3, 3), out])
+        return out
+
+    def Close(self):
+        h, self._h = self._h, None
+        if h is not None and lib is not None:
+            lib.gsdf_dc_destroy(h)
+
+    def __del__(self):
+        try:
+            self.Close()
+        except Exception:
+            pass

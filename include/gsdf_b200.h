@@ -129,6 +129,32 @@ int gsdf_mesh_grid(gsdf_mesher *m, float *grid, size_t nfloats);
 int gsdf_mesh_timings(const gsdf_mesher *m, float ms[5]);
 void gsdf_mesh_destroy(gsdf_mesher *m);
 
+/* Dual contouring --------------------------------------------------------------------------------------------- */
+/* glrender.DualContourRenderer (glrender/dual_contour.go:12-218) with its vertex placement strategies
+ * (glrender/dual_contour_vertexplacement.go) and gleval.NormalsCentralDiff (gleval/gleval.go:53-108) on the device. */
+typedef struct gsdf_dualcontour gsdf_dualcontour;
+typedef enum {
+    GSDF_DC_NAIVE = 0,                 /* DualContourNaive: mean of the edge crossings (dual_contour_test.go:355-389) */
+    GSDF_DC_LEAST_SQUARES = 1,         /* DualContourLeastSquares{} (dual_contour_vertexplacement.go:16-138) */
+    GSDF_DC_LEAST_SQUARES_CHISELED = 2 /* DualContourLeastSquares{Chiseled: true} (:21, :43-46, :118-121) */
+} gsdf_dc_placer;
+/* makeICube on Bounds().Add(-res/2) (dual_contour.go:31-36, octreerenderer.go:222-235): octree level count, GSDF_ERES if
+ * <= 1; origin (optional) receives the octree origin. */
+int gsdf_dc_levels(const float bbmin[3], const float bbmax[3], float res, float origin[3]);
+/* DualContourRenderer.Reset(sdf, res, placer) + RenderAll: the whole mesh is built on the device inside this call.
+ * bbmin/bbmax = sdf.Bounds(). Limits: at most 1024 cubes per axis (11 levels). */
+int gsdf_dc_begin(gsdf_program *p, const float bbmin[3], const float bbmax[3], float res, int placer, gsdf_dualcontour **out);
+/* Re-run with the same parameters, reusing every device buffer. */
+int gsdf_dc_rerun(gsdf_dualcontour *d);
+/* RenderAll's result: copies up to max_tris triangles (9 floats each, cube order, two per quad) from the start of the
+ * mesh; returns the number copied. */
+int64_t gsdf_dc_read(gsdf_dualcontour *d, float *tri9, size_t max_tris);
+int gsdf_dc_device_triangles(gsdf_dualcontour *d, const float **d_tri9, uint64_t *ntri);
+/* stats = {octree levels, cubes kept by the prune (len(cubebuf)), cubes that received a vertex (len(Neighbors) > 0),
+ * triangles, SDF evaluations the reference performs for this render, microseconds of device time}. */
+int gsdf_dc_stats(const gsdf_dualcontour *d, uint64_t stats[6]);
+void gsdf_dc_destroy(gsdf_dualcontour *d);
+
 /* STL ---------------------------------------------------------------------------------------------------- */
 /* glrender.WriteBinarySTL (glrender/stl.go:15-62): 80 zero bytes + u32 count + 50 B per triangle (unit normal,
  * 3 vertices, u16 0). Packs n HOST triangles into dst (needs 84+50*n bytes) on the device and returns the byte

@@ -121,6 +121,15 @@ int64_t go_octree_prune_mask(const go_tree *t, const go_lattice *lat, uint8_t *m
 /* marchcubes.go:34-73 single cube (exported for table/unit tests). p: 8 corners xyz, v: 8 values. returns ntri. */
 int go_mc_cube(const float p[24], const float v[8], float tri9[45], int *case_index);
 
+/* ---- dual contouring (gsdf_oracle_dc.c): glrender/dual_contour.go + dual_contour_vertexplacement.go ---- */
+/* makeICube on Bounds().Add(-res/2) (dual_contour.go:31-34): level count (<0 = resolution too coarse) and octree origin. */
+int go_dc_levels(const float bbmin[3], const float bbmax[3], float res, float origin[3]);
+/* DualContourRenderer.Reset + RenderAll. placer: 0 DualContourNaive (dual_contour_test.go:355), 1 DualContourLeastSquares{},
+ * 2 DualContourLeastSquares{Chiseled:true}. Returns the triangle count (only the first max_tris are stored) or <0.
+ * stats (optional): {levels, cubes kept, cubes with neighbours, evaluations}. */
+int64_t go_dual_contour(const go_tree *t, const float bbmin[3], const float bbmax[3], float res, int placer, float *tri9, int64_t max_tris,
+                        int64_t *stats);
+
 /* ---- STL (glrender/stl.go:15-62) ---- */
 /* dst needs 84 + 50*ntri bytes. returns bytes written, or <0 (empty model is an error, stl.go:16). */
 int64_t go_stl_write(const float *tri9, int64_t ntri, uint8_t *dst);

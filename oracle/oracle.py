@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "_build", "libgsdf_oracle.so")
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("gsdf_oracle.c", "gsdf_oracle.h", "mc_tables.inc", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("gsdf_oracle.c", "gsdf_oracle_dc.c", "gsdf_oracle.h", "mc_tables.inc", "Makefile")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
         subprocess.check_call(["make", "-s", "-C", _HERE])
     return LIB_PATH
@@ -112,6 +112,10 @@ def lib():
         L.go_rgb_to_hsv.argtypes = [C.c_float, C.c_float, C.c_float, f32p]
         L.go_image_render2.restype = C.c_int
         L.go_image_render2.argtypes = [C.POINTER(GoTree), f32p, f32p, C.c_int, C.c_int, C.POINTER(GoColorConv), vp]
+        L.go_dc_levels.restype = C.c_int
+        L.go_dc_levels.argtypes = [f32p, f32p, C.c_float, f32p]
+        L.go_dual_contour.restype = C.c_int64
+        L.go_dual_contour.argtypes = [C.POINTER(GoTree), f32p, f32p, C.c_float, C.c_int, vp, C.c_int64, C.POINTER(C.c_int64)]
         L.go_mc_edge_table.restype = C.POINTER(C.c_int)
         L.go_mc_tri_table.restype = C.POINTER(C.c_int8)
         L.go_mc_pair_table.restype = C.POINTER(C.c_int)
@@ -174,6 +178,22 @@ def image_render2(tree, bbmin, bbmax, w, h, cc=None):
     if rc:
         raise RuntimeError("oracle go_image_render2 failed: %d" % rc)
     return out
+
+
+DC_NAIVE, DC_LSQ, DC_LSQ_CHISELED = 0, 1, 2
+
+
+def dual_contour(tree, bbmin, bbmax, res, placer=DC_LSQ):
+    """DualContourRenderer.Reset + RenderAll: returns (triangles (n,3,3), stats dict)."""
+    a = (C.c_float * 3)(*[float(v) for v in bbmin])
+    b = (C.c_float * 3)(*[float(v) for v in bbmax])
+    st = (C.c_int64 * 4)()
+    n = lib().go_dual_contour(C.byref(tree.c), a, b, float(res), placer, None, 0, st)
+    if n < 0:
+        raise RuntimeError("oracle go_dual_contour failed: %d" % n)
+    tris = np.empty((max(n, 1), 3, 3), dtype=np.float32)
+    lib().go_dual_contour(C.byref(tree.c), a, b, float(res), placer, tris.ctypes.data, n, st)
+    return tris[:n], dict(levels=st[0], cubes=st[1], with_neighbors=st[2], evals=st[3])
 
 
 def flat_lattice(bbmin, bbmax, res):
