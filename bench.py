@@ -319,7 +319,9 @@ def run_cuda(args, rank, local_rank, world):
         tree = O.Tree.from_shader(s)
         lat = O.flat_lattice(*s.Bounds(), res)
         threads = max(1, (os.cpu_count() or 1) - 1)
-        reps = 5
+        # bounded sample: full renders of the same workload until ~12 s of CPU work have accumulated
+        times, ev, nt = cpu_render(O, tree, lat, threads, 3)
+        reps = max(5, min(400, int(12.0 / max(sum(times) / len(times), 1e-3))))
         times, ev, nt = cpu_render(O, tree, lat, threads, reps)
         assert nt == ntri, "CPU oracle and CUDA path disagree on the triangle count"
         sec = sum(times) / len(times)
