@@ -18,7 +18,7 @@ class GsdfError(RuntimeError):
 
 # gsdf_status (include/gsdf_b200.h)
 OK, EINVAL, ELEN, EEMPTY, ECUDA, ENOMEM, EPROGRAM, ESHORT, ERES = 0, -1, -2, -3, -4, -5, -6, -7, -8
-MESH_PRUNE, MESH_KEEP_CASES, MESH_KEEP_GRID = 1, 2, 4
+MESH_PRUNE, MESH_KEEP_CASES, MESH_KEEP_GRID, MESH_STAGE_TIMING = 1, 2, 4, 8
 DC_NAIVE, DC_LEAST_SQUARES, DC_LEAST_SQUARES_CHISELED = 0, 1, 2
 
 

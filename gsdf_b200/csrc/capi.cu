@@ -510,6 +510,11 @@ struct gsdf_mesher {
     cudaEvent_t ev[5] = {};
     cudaStream_t copy_stream = nullptr;
     float ms[5] = {};
+    // steady-state reruns replay the whole launch sequence (2 memsets + 7 kernels) as ONE CUDA graph
+    cudaGraphExec_t gexec = nullptr;
+    std::vector<uint8_t> gkey;  // snapshot of every pointer / size the captured launches were built from
+    bool allow_graph = true;
+    uint64_t runs = 0;
 };
 
 namespace {
@@ -582,33 +587,7 @@ int mesh_run(gsdf_mesher *m) {
     if (m->flags & GSDF_MESH_KEEP_CASES) {
         if ((rc = grow(m->d_cases, m->cases_cap, (size_t)ncells))) return rc;
     }
-    if (m->flags & GSDF_MESH_KEEP_GRID) CU(cudaMemsetAsync(m->d_grid, 0x7f, (size_t)D.pitch * (D.ny + 1) * nk * sizeof(float), st));
-    CU(cudaMemsetAsync(m->d_ctr, 0, 8 * sizeof(uint32_t), st));
-
-    CU(cudaEventRecord(m->ev[0], st));
     const gsdf_lattice &lat = m->lat;
-    if (prune) {
-        GenCenters gc;
-        gc.ox = lat.origin[0]; gc.oy = lat.origin[1]; gc.oz = lat.origin[2]; gc.res = lat.res;
-        gc.nbx = D.nbx; gc.nby = D.nby; gc.nbz = D.nbz; gc.bz0 = D.bz0;
-        const float size = lat.res * 4.0f;          // ms3.Octree.CubeSize of a level-3 cube
-        gc.half = size * 0.5f;
-        gc.maxDist = size * (float)(1.73205080757 / 2);  // octreerenderer.go:182 with glrender.go:9
-        gc.mask = m->d_mask;
-        if ((rc = launch_eval<1>(p, gc, nblocks, st))) return rc;
-        const uint64_t ncrows = (uint64_t)(D.ny + 1) * nk;
-        k_mask_bits<<<grid_for((uint64_t)D.nby * D.nbz, kThreads / 32), kThreads, 0, st>>>(D, m->d_mask, m->d_mbits, m->d_ctr + 4);
-        CU(cudaGetLastError());
-        k_compact_quads<<<grid_for(ncrows, kThreads / 32), kThreads, 0, st>>>(D, m->d_mbits, m->d_list, m->d_ctr + 0);
-        CU(cudaGetLastError());
-    }
-    CU(cudaEventRecord(m->ev[1], st));
-    {
-        GenGrid<4> g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
-        // with a device-side list length the launch is sized for the worst case; surplus CTAs find no tile and exit
-        if ((rc = launch_eval<4>(p, g, nquads, st))) return rc;
-    }
-    CU(cudaEventRecord(m->ev[2], st));
     MCArgs A;
     A.D = D;
     A.ox = lat.origin[0]; A.oy = lat.origin[1]; A.oz = lat.origin[2]; A.res = lat.res;
@@ -625,18 +604,49 @@ int mesh_run(gsdf_mesher *m) {
     A.seg_list = m->d_seglist;
     A.seg_count = m->d_ctr + 5;
     const unsigned mcgrid = grid_for(nrows * (uint64_t)((D.nsx + 3) / 4), kThreads / 32, 16);
+    if (m->use_tma && m->tmap_grid != m->d_grid) {  // (re)describe the lattice buffer: pitch x (ny+1) x nk floats
+        if ((rc = make_grid_tensor_map(&m->tmap, m->d_grid, D.pitch, D.ny + 1, nk))) return rc;
+        m->tmap_grid = m->d_grid;
+    }
+    const bool emitted = m->tri_cap > 0;  // optimistic emit into the existing buffer (steady state: no mid-pipeline host sync)
+    static const bool scan3 = getenv("GSDF_SCAN3") != nullptr;  // A/B: the three-kernel scan
+
+    // The launch sequence of one render. stage_events: record the per-stage timing events (eager path only).
+    auto enqueue = [&](bool stage_events, uint32_t epoch, bool clear_scan) -> int {
+    int rc = 0;
+    if (m->flags & GSDF_MESH_KEEP_GRID) CU(cudaMemsetAsync(m->d_grid, 0x7f, (size_t)D.pitch * (D.ny + 1) * nk * sizeof(float), st));
+    CU(cudaMemsetAsync(m->d_ctr, 0, 8 * sizeof(uint32_t), st));
+    if (clear_scan) CU(cudaMemsetAsync(m->d_scanstate, 0, (size_t)nscantiles * sizeof(unsigned long long), st));
+    if (prune) {
+        GenCenters gc;
+        gc.ox = lat.origin[0]; gc.oy = lat.origin[1]; gc.oz = lat.origin[2]; gc.res = lat.res;
+        gc.nbx = D.nbx; gc.nby = D.nby; gc.nbz = D.nbz; gc.bz0 = D.bz0;
+        const float size = lat.res * 4.0f;          // ms3.Octree.CubeSize of a level-3 cube
+        gc.half = size * 0.5f;
+        gc.maxDist = size * (float)(1.73205080757 / 2);  // octreerenderer.go:182 with glrender.go:9
+        gc.mask = m->d_mask;
+        if ((rc = launch_eval<1>(p, gc, nblocks, st))) return rc;
+        const uint64_t ncrows = (uint64_t)(D.ny + 1) * nk;
+        k_mask_bits<<<grid_for((uint64_t)D.nby * D.nbz, kThreads / 32), kThreads, 0, st>>>(D, m->d_mask, m->d_mbits, m->d_ctr + 4);
+        CU(cudaGetLastError());
+        k_compact_quads<<<grid_for(ncrows, kThreads / 32), kThreads, 0, st>>>(D, m->d_mbits, m->d_list, m->d_ctr + 0);
+        CU(cudaGetLastError());
+    }
+    if (stage_events) CU(cudaEventRecord(m->ev[1], st));
+    {
+        GenGrid<4> g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
+        // with a device-side list length the launch is sized for the worst case; surplus CTAs find no tile and exit
+        if ((rc = launch_eval<4>(p, g, nquads, st))) return rc;
+    }
+    if (stage_events) CU(cudaEventRecord(m->ev[2], st));
     if (m->use_tma) {
-        if (m->tmap_grid != m->d_grid) {  // (re)describe the lattice buffer: pitch x (ny+1) x nk floats
-            if ((rc = make_grid_tensor_map(&m->tmap, m->d_grid, D.pitch, D.ny + 1, nk))) return rc;
-            m->tmap_grid = m->d_grid;
-        }
         const uint64_t ntiles = (uint64_t)((D.nsx + 3) / 4) * ((D.ny + kTileY - 1) / kTileY) * (D.cz1 - D.cz0);
         k_mc_count_tma<<<grid_for(ntiles, 1, 16), 256, 0, st>>>(m->tmap, A);
     } else {
         k_mc_count<<<mcgrid, kThreads, 0, st>>>(A);
     }
     CU(cudaGetLastError());
-    if (getenv("GSDF_SCAN3")) {  // A/B: the three-kernel scan
+    if (scan3) {
         k_scan_reduce<<<(unsigned)nscanblocks, kThreads, 0, st>>>(m->d_seg, nseg, m->d_blocksum);
         CU(cudaGetLastError());
         k_scan_blocksums<<<1, 1024, 0, st>>>(m->d_blocksum, (uint32_t)nscanblocks, reinterpret_cast<unsigned long long *>(m->d_ctr + 2));
@@ -644,18 +654,54 @@ int mesh_run(gsdf_mesher *m) {
         k_scan_apply<<<(unsigned)nscanblocks, kThreads, 0, st>>>(m->d_seg, nseg, m->d_blocksum);
         CU(cudaGetLastError());
     } else {
-        k_scan_lookback<<<(unsigned)nscantiles, kThreads, 0, st>>>(m->d_seg, (uint32_t)nseg, m->d_scanstate, m->d_ctr + 6, m->scan_epoch,
+        k_scan_lookback<<<(unsigned)nscantiles, kThreads, 0, st>>>(m->d_seg, (uint32_t)nseg, m->d_scanstate, m->d_ctr + 6, epoch,
                                                                reinterpret_cast<unsigned long long *>(m->d_ctr + 2));
         CU(cudaGetLastError());
     }
-    CU(cudaEventRecord(m->ev[3], st));
-
-    A.cases = nullptr;
-    bool emitted = false;
-    if (m->tri_cap > 0) {  // optimistic emit into the existing buffer (steady state: no mid-pipeline host sync)
-        k_mc_emit<<<mcgrid, kThreads, 0, st>>>(A);
+    if (stage_events) CU(cudaEventRecord(m->ev[3], st));
+    if (emitted) {
+        MCArgs E = A;
+        E.cases = nullptr;
+        k_mc_emit<<<mcgrid, kThreads, 0, st>>>(E);
         CU(cudaGetLastError());
-        emitted = true;
+    }
+    return rc;
+    };  // enqueue
+
+    // Graph key: everything the captured launches were built from. Any change (buffer regrowth, another program,
+    // gsdf_program_update with a different size) re-captures.
+    struct GraphKey {
+        const void *ptr[10];
+        size_t tri_cap;
+        ProgView pv;
+        unsigned flags;
+        int ext, tma;
+    } key;
+    std::memset(&key, 0, sizeof key);
+    const void *kp[10] = {m->d_grid, m->d_mask, m->d_mbits, m->d_list, m->d_seg, m->d_seglist, m->d_scanstate, m->d_tris, m->d_cases, m->d_blocksum};
+    std::memcpy(key.ptr, kp, sizeof kp);
+    key.tri_cap = m->tri_cap; key.pv = p->pv; key.flags = m->flags; key.ext = p->needs_ext ? 1 : 0; key.tma = m->use_tma ? 1 : 0;
+    const bool use_graph = m->allow_graph && !(m->flags & GSDF_MESH_STAGE_TIMING) && emitted && m->runs > 0 && !scan3;
+    if (use_graph) {
+        if (!m->gexec || m->gkey.size() != sizeof key || std::memcmp(m->gkey.data(), &key, sizeof key) != 0) {
+            if (m->gexec) { cudaGraphExecDestroy(m->gexec); m->gexec = nullptr; }
+            cudaGraph_t g = nullptr;
+            CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int erc = enqueue(false, 1u, true);
+            const cudaError_t ce = cudaStreamEndCapture(st, &g);
+            if (erc) { if (g) cudaGraphDestroy(g); return erc; }
+            if (ce != cudaSuccess) return fail(GSDF_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+            const cudaError_t ie = cudaGraphInstantiate(&m->gexec, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { m->gexec = nullptr; return fail(GSDF_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+            m->gkey.assign(reinterpret_cast<const uint8_t *>(&key), reinterpret_cast<const uint8_t *>(&key) + sizeof key);
+        }
+        CU(cudaEventRecord(m->ev[0], st));
+        CU(cudaGraphLaunch(m->gexec, st));
+        m->scan_epoch = 1;  // the graph clears the look-back state and scans with epoch 1
+    } else {
+        CU(cudaEventRecord(m->ev[0], st));
+        if ((rc = enqueue(true, m->scan_epoch, false))) return rc;
     }
     CU(cudaEventRecord(m->ev[4], st));
     CU(cudaMemcpyAsync(m->h_ctr, m->d_ctr, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -666,6 +712,7 @@ int mesh_run(gsdf_mesher *m) {
         if ((rc = grow(m->d_tris, m->tri_cap, (size_t)std::max<uint64_t>(total, 1) * 9))) return rc;
         A.tris = m->d_tris;
         A.tri_capacity = m->tri_cap / 9;
+        A.cases = nullptr;
         CU(cudaMemsetAsync(m->d_ctr + 1, 0, sizeof(uint32_t), st));
         k_mc_emit<<<mcgrid, kThreads, 0, st>>>(A);
         CU(cudaGetLastError());
@@ -681,8 +728,10 @@ int mesh_run(gsdf_mesher *m) {
         m->evals = (uint64_t)(D.nx + 1) * (D.ny + 1) * nk;
         m->pruned = 0;
     }
-    for (int i = 0; i < 4; i++) cudaEventElapsedTime(&m->ms[i], m->ev[i], m->ev[i + 1]);
+    if (use_graph) { for (int i = 0; i < 4; i++) m->ms[i] = 0.f; }  // stage events are not recorded inside the graph
+    else { for (int i = 0; i < 4; i++) cudaEventElapsedTime(&m->ms[i], m->ev[i], m->ev[i + 1]); }
     cudaEventElapsedTime(&m->ms[4], m->ev[0], m->ev[4]);
+    m->runs++;
     return 0;
 }
 
@@ -703,6 +752,7 @@ int gsdf_mesh_begin(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, 
     m->lat = *lat;
     m->flags = flags;
     m->use_tma = getenv("GSDF_NO_TMA") == nullptr;  // A/B switch for the classification kernel
+    m->allow_graph = getenv("GSDF_NO_GRAPH") == nullptr;  // A/B switch: eager launches instead of the CUDA graph
     MeshDims &D = m->D;
     D.nx = lat->n[0]; D.ny = lat->n[1]; D.nz = lat->n[2];
     D.cz0 = cz0; D.cz1 = cz1;
@@ -819,6 +869,7 @@ void gsdf_mesh_destroy(gsdf_mesher *m) {
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
     for (auto &e : m->ev) if (e) cudaEventDestroy(e);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    if (m->gexec) cudaGraphExecDestroy(m->gexec);
     delete m;
 }
 

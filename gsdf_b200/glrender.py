@@ -38,11 +38,11 @@ class _Renderer:
     (or Reset); ReadTriangles streams the result out in FlatRenderer order."""
     _flags = 0
 
-    def __init__(self, sdf, cubeResolution, evalBufferSize=0, numParallel=1, cz_range=None, keep_cases=False, keep_grid=False):
+    def __init__(self, sdf, cubeResolution, evalBufferSize=0, numParallel=1, cz_range=None, keep_cases=False, keep_grid=False, stage_timing=False):
         self._h = None
-        self.Reset(sdf, cubeResolution, cz_range=cz_range, keep_cases=keep_cases, keep_grid=keep_grid)
+        self.Reset(sdf, cubeResolution, cz_range=cz_range, keep_cases=keep_cases, keep_grid=keep_grid, stage_timing=stage_timing)
 
-    def Reset(self, sdf, cubeResolution, evalBufferSize=0, numParallel=1, cz_range=None, keep_cases=False, keep_grid=False):
+    def Reset(self, sdf, cubeResolution, evalBufferSize=0, numParallel=1, cz_range=None, keep_cases=False, keep_grid=False, stage_timing=False):
         if not (cubeResolution > 0):
             raise GsdfError(_lib.EINVAL, "invalid renderer cube resolution")  # flatrenderer.go:38, octreerenderer.go:73
         self.Close()
@@ -51,7 +51,8 @@ class _Renderer:
         self.lat = lattice_from_bounds(mn, mx, cubeResolution)
         cz0, cz1 = cz_range if cz_range is not None else (0, self.lat.n[2])
         self.cz0, self.cz1 = int(cz0), int(cz1)
-        flags = self._flags | (_lib.MESH_KEEP_CASES if keep_cases else 0) | (_lib.MESH_KEEP_GRID if keep_grid else 0)
+        flags = self._flags | (_lib.MESH_KEEP_CASES if keep_cases else 0) | (_lib.MESH_KEEP_GRID if keep_grid else 0) | \
+            (_lib.MESH_STAGE_TIMING if stage_timing else 0)
         h = C.c_void_p()
         check(lib.gsdf_mesh_begin(sdf._h, C.byref(self.lat), self.cz0, self.cz1, flags, C.byref(h)))
         self._h = h
@@ -100,6 +101,9 @@ class _Renderer:
         return self._stats()[2]
 
     def Timings(self):
+        """Device milliseconds of the last run. Per-stage entries are only filled by a renderer created with
+        stage_timing=True (eager launches with events between stages); otherwise reruns replay one CUDA graph and only
+        total_ms is measured."""
         ms = (C.c_float * 5)()
         check(lib.gsdf_mesh_timings(self._h, ms))
         return dict(prune_ms=ms[0], eval_ms=ms[1], classify_ms=ms[2], emit_ms=ms[3], total_ms=ms[4])

@@ -97,7 +97,9 @@ int gsdf_grid_eval_device(gsdf_program *p, const gsdf_lattice *lat, int k0, int 
 enum {
     GSDF_MESH_PRUNE = 1u << 0,      /* octree level-3 prune (octreerenderer.go:180-191,240-284); off = FlatRenderer */
     GSDF_MESH_KEEP_CASES = 1u << 1, /* also keep the 8-bit cube-case index per cell (parity checks) */
-    GSDF_MESH_KEEP_GRID = 1u << 2   /* keep the distance lattice readable through gsdf_mesh_grid */
+    GSDF_MESH_KEEP_GRID = 1u << 2,  /* keep the distance lattice readable through gsdf_mesh_grid */
+    GSDF_MESH_STAGE_TIMING = 1u << 3 /* time every stage (gsdf_mesh_timings [0..3]): launches eagerly with events between the
+                                        stages; without it steady-state reruns replay one CUDA graph and only [4] is filled */
 };
 /* glrender.NewOctreeRenderer / FlatRenderer.Reset (octreerenderer.go:45, flatrenderer.go:37) on cells
  * cz in [cz0,cz1) of the lattice (Z-slab; pass 0,n[2] for everything). The whole slab is meshed on the device

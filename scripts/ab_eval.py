@@ -10,7 +10,7 @@ for name, resdiv in [("npt-flange", 400), ("bolt", 400), ("knurled-cylinder", 50
     sdf = gleval.NewCUDASDF3(s)
     res = np.float32(s.Diagonal() / np.float32(resdiv))
     for cls in (glrender.Octree, glrender.FlatRenderer):
-        R = cls(sdf, res)
+        R = cls(sdf, res, stage_timing=os.environ.get("GSDF_AB_GRAPH") is None)
         ts = []
         for i in range(8):
             flush.fill_(1); torch.cuda.synchronize()

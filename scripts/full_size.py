@@ -22,7 +22,7 @@ for name, resdiv in SCENES:
     lat = glrender.lattice_from_bounds(*s.Bounds(), res)
     cz = slab.rank_slab(lat.n[2], rank, world)
     t0 = time.perf_counter()
-    R = glrender.Octree(sdf, res, cz_range=cz)
+    R = glrender.Octree(sdf, res, cz_range=cz, stage_timing=True)
     t1 = time.perf_counter()
     for _ in range(3):
         R.Rerun()
