@@ -115,6 +115,37 @@ int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_boun
                         : launch_eval_impl<P, Gen, false>(p, gen, nwork_upper_bound, st);
 }
 
+// Streaming Evaluate (k_eval_stream): persistent grid, one resident wave, tiles dealt round-robin.
+template <int DIM, bool EXT>
+int launch_stream_impl(const gsdf_program *p, const float *d_pos, float *d_dist, uint64_t n, cudaStream_t st) {
+    auto kern = k_eval_stream<DIM, EXT>;
+    const uint32_t base = smem_total_bytes<4>(p->pv, kEvalThreads);
+    const uint32_t smem = ((base + 127u) & ~127u) + 2u * stream_stage_bytes<DIM>(kEvalThreads);
+    static thread_local uint32_t cached_smem = 0xffffffffu;
+    static thread_local int cached_occ = 0;
+    if (cached_smem != smem) {
+        if (smem > 227u * 1024u) { cached_smem = 0xffffffffu; return 1; }  // does not fit: caller falls back to k_eval
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<uint32_t>(smem, 48 * 1024)));
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kEvalThreads, smem));
+        if (occ < 1) return 1;
+        cached_occ = occ;
+        cached_smem = smem;
+    }
+    const uint64_t tiles = (n + (uint64_t)kEvalThreads * 4 - 1) / ((uint64_t)kEvalThreads * 4);
+    const unsigned blocks = (unsigned)std::min<uint64_t>(tiles, (uint64_t)g_sms * cached_occ);
+    kern<<<blocks, kEvalThreads, smem, st>>>(p->pv, d_pos, d_dist, n);
+    CU(cudaGetLastError());
+    return 0;
+}
+// returns 0 launched, 1 not applicable (caller uses the generic kernel), <0 error
+template <int DIM>
+int launch_stream(const gsdf_program *p, const float *d_pos, float *d_dist, uint64_t n, cudaStream_t st) {
+    static const bool off = getenv("GSDF_NO_STREAM") != nullptr;  // A/B switch
+    if (off || ((((uintptr_t)d_pos | (uintptr_t)d_dist) & 15) != 0) || n < (uint64_t)kEvalThreads * 4) return 1;
+    return p->needs_ext ? launch_stream_impl<DIM, true>(p, d_pos, d_dist, n, st) : launch_stream_impl<DIM, false>(p, d_pos, d_dist, n, st);
+}
+
 int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_t aux_floats) {
     uint32_t pc = 0, n = 0;
     bool ended = false;
@@ -283,6 +314,8 @@ int gsdf_eval3_device(gsdf_program *p, const float *d_pos, float *d_dist, size_t
     if (p->dim != 3) return fail(GSDF_EINVAL, "program is not 3D");
     if (n == 0) return fail(GSDF_EEMPTY, "empty buffers");
     CU(cudaSetDevice(p->device));
+    const int src = launch_stream<3>(p, d_pos, d_dist, (uint64_t)n, stream ? (cudaStream_t)stream : p->stream);
+    if (src <= 0) return src;
     GenPoints3 g{d_pos, d_dist, (uint64_t)n, (((uintptr_t)d_pos | (uintptr_t)d_dist) & 15) == 0 ? 1 : 0};
     return launch_eval<4>(p, g, (n + 3) / 4, stream ? (cudaStream_t)stream : p->stream);
 }
@@ -292,6 +325,8 @@ int gsdf_eval2_device(gsdf_program *p, const float *d_pos, float *d_dist, size_t
     if (p->dim != 2) return fail(GSDF_EINVAL, "program is not 2D");
     if (n == 0) return fail(GSDF_EEMPTY, "empty buffers");
     CU(cudaSetDevice(p->device));
+    const int src = launch_stream<2>(p, d_pos, d_dist, (uint64_t)n, stream ? (cudaStream_t)stream : p->stream);
+    if (src <= 0) return src;
     GenPoints2 g{d_pos, d_dist, (uint64_t)n, (((uintptr_t)d_pos | (uintptr_t)d_dist) & 15) == 0 ? 1 : 0};
     return launch_eval<4>(p, g, (n + 3) / 4, stream ? (cudaStream_t)stream : p->stream);
 }

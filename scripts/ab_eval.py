@@ -18,5 +18,5 @@ for name, resdiv in [("npt-flange", 400), ("bolt", 400), ("knurled-cylinder", 50
         t = {k: float(np.median([x[k] for x in ts[2:]])) for k in ts[0]}
         print("%-28s %-18s %-12s evals=%9d tris=%8d  prune %.3f eval %.3f classify %.3f emit %.3f total %.3f ms  -> %.1f Geval/s executed" % (
             os.path.basename(_lib.LIB_PATH), name, cls.__name__, R.Evaluations(), R.NumTriangles(), t["prune_ms"], t["eval_ms"], t["classify_ms"], t["emit_ms"], t["total_ms"],
-            R.Evaluations() / t["eval_ms"] / 1e6))
+            R.Evaluations() / max(t["eval_ms"], 1e-9) / 1e6))
         R.Close()

@@ -54,3 +54,39 @@ def test_graph_follows_program_updates_and_rebinding(bld):
     R.Rebind(sdf)
     R.Rerun()
     assert np.array_equal(R.AllTriangles().view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("scene", ["sphere", "npt-flange", "poly2d"])
+def test_streaming_evaluate_tiles_and_tails(oracle, bld, scene):
+    """k_eval_stream (bulk-async double-buffered position tiles): full tiles, the partial last tile, sizes below one
+    tile (generic kernel), many tiles per CTA, and unaligned device pointers (generic kernel) all agree with the oracle."""
+    import torch
+    s = {"sphere": lambda: bld.NewSphere(1.0), "npt-flange": lambda: gsdf.scene(bld, "npt-flange"),
+         "poly2d": lambda: bld.NewPolygon(np.array([[0, 0], [2, 0], [2.5, 1.5], [1, 1], [0.2, 2]], np.float32))}[scene]()
+    d = 2 if s.is2d else 3
+    sdf = gleval.NewCUDASDF2(s) if d == 2 else gleval.NewCUDASDF3(s)
+    t = oracle.Tree.from_shader(s)
+    mn, mx = s.Bounds()
+    rng = np.random.default_rng(11)
+    nmax = 2048 * 700 + 1234  # more tiles than resident CTAs (296): every CTA loops over >= 2 tiles
+    pos_all = (mn - 0.1 * (mx - mn) + rng.random((nmax, d), dtype=np.float32) * 1.2 * (mx - mn)).astype(np.float32)
+    want_all = t.eval2(pos_all) if d == 2 else t.eval3(pos_all)
+    dpos_all = torch.from_numpy(pos_all).cuda()
+    for n in (5, 2047, 2048, 2049, 4096, 6151, 2048 * 300 + 1, nmax):
+        dpos = dpos_all[:n].contiguous()
+        out = torch.full((n,), 7.0, dtype=torch.float32, device="cuda")
+        sdf.Evaluate(dpos, out)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), want_all[:n].view(np.uint32)), (scene, n, int((got.view(np.uint32) != want_all[:n].view(np.uint32)).sum()))
+    # a misaligned view (offset by one point: 12 or 8 bytes) must take the generic path and still be right
+    n = 5000
+    dpos = dpos_all[1:n + 1]
+    out = torch.empty(n + 1, dtype=torch.float32, device="cuda")[1:]
+    sdf.Evaluate(dpos, out)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want_all[1:n + 1].view(np.uint32))
+    # host buffers go through the same kernel
+    host = np.empty(6151, np.float32)
+    sdf.Evaluate(pos_all[:6151], host)
+    assert np.array_equal(host.view(np.uint32), want_all[:6151].view(np.uint32))
