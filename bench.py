@@ -322,6 +322,22 @@ def run_cuda(args, rank, local_rank, world):
         except Exception:
             traffic = None
 
+    # What actually bounds the dominant kernel: warp-instruction issue. Warp instructions per launch come from the ncu
+    # capture of this same command (profiles/traffic.json, smsp__inst_executed.sum); the duration is the live one.
+    issue = None
+    try:
+        winst = json.load(open(tpath)).get(kname.split(" ")[0] + ".warp_inst")
+        if winst and clocks and clocks.get("sm_mhz"):
+            props = torch.cuda.get_device_properties(local_rank)
+            peak_issue = props.multi_processor_count * 4 * clocks["sm_mhz"] * 1e6  # 4 schedulers/SM, 1 warp-instr/clk each
+            ach = winst / (kms * 1e-3)
+            issue = {"bound": "warp-instruction issue (FP32/ALU/XU pipes)", "achieved": ach / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-instr/s",
+                     "frac": ach / peak_issue, "warp_instructions_per_launch": winst,
+                     "thread_instructions_per_eval": winst * 32 / max(fine_evals, 1),
+                     "source": "smsp__inst_executed.sum from profiles/ (ncu --set full) / live CUDA-event kernel time; peak = SMs x 4 x SM clock"}
+    except Exception:
+        issue = None
+
     # ---------------- CPU baseline beside it (rank 0, N == 1 only): bounded sample of the same workload
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -362,6 +378,7 @@ def run_cuda(args, rank, local_rank, world):
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": kbytes, "avg_launch_ms": kms, "peak_source": peak_src,
                      "note": "deep CSG trees are FP32-issue bound, not HBM bound (DESIGN.md); see profiles/ for issue-slot utilisation"},
+        "roofline_issue": issue,
         "cpu_baseline": cpu,
         "clocks": clocks,
     }

@@ -67,6 +67,8 @@ def main():
                 elif "GenCenters" in d["Kernel Name"]:
                     short = "k_eval<GenCenters>"
                 traffic[short] = tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum")
+                if "smsp__inst_executed.sum" in d:  # warp instructions per launch (issue-slot roofline in bench.py)
+                    traffic[short + ".warp_inst"] = float(d["smsp__inst_executed.sum"].replace(",", ""))
             except Exception:
                 pass
     open(os.path.join(OUT, "%s_ncu_full_summary.txt" % TAG), "w").write("\n".join(lines) + "\n")
