@@ -161,7 +161,7 @@ int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_
         if (op >= GSDF_OP__COUNT) return fail(GSDF_EPROGRAM, "instruction %u: unknown opcode %u", n, op);
         if (len < 1 || pc + len > h.nchunks) return fail(GSDF_EPROGRAM, "instruction %u: bad length %u", n, len);
         static const uint8_t need2[] = {GSDF_OP_BOX, GSDF_OP_BOXFRAME, GSDF_OP_CYLINDER, GSDF_OP_HEX, GSDF_OP_DIAMOND2D, GSDF_OP_TRANSLATE,
-                                        GSDF_OP_ROTATE2D, GSDF_OP_ELONGATE, GSDF_OP_ARRAY2D_VAR, GSDF_OP_CIRC_ENTER, GSDF_OP_SCREW_ENTER};
+                                        GSDF_OP_ROTATE2D, GSDF_OP_ELONGATE, GSDF_OP_ARRAY2D_VAR, GSDF_OP_CIRC_ENTER, GSDF_OP_SCREW_ENTER, GSDF_OP_BBOX_GUARD2D};
         static const uint8_t need3[] = {GSDF_OP_LINE2D, GSDF_OP_ARC2D, GSDF_OP_ARRAY_VAR};
         uint32_t want = 1;
         for (uint8_t o : need2) if (o == op) want = 2;
@@ -171,6 +171,17 @@ int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_
         if (op == GSDF_OP_POLY2D) {
             const uint64_t off = chunks[4 * pc + 1], nv = chunks[4 * pc + 2];
             if ((off & 3) || nv < 3 || off + nv * GSDF_POLY_EDGE_FLOATS > aux_floats) return fail(GSDF_EPROGRAM, "instruction %u: polygon aux range out of bounds", n);
+        }
+        if (op == GSDF_OP_CULL_UB2D) {
+            const uint64_t off = chunks[4 * pc + 1], np = chunks[4 * pc + 2];
+            if ((off & 3) || np < 2 || (np & 1) || off + np * 2 > aux_floats) return fail(GSDF_EPROGRAM, "instruction %u: anchor aux range out of bounds", n);
+        }
+        if (op == GSDF_OP_BBOX_GUARD2D) {
+            const uint32_t kind = chunks[4 * pc + 1] & 0xff, target = chunks[4 * pc + 1] >> 8;
+            if (kind != GSDF_GUARD_DIFF && kind != GSDF_GUARD_MIN) return fail(GSDF_EPROGRAM, "instruction %u: unknown box guard %u", n, kind);
+            if (target <= pc + len || target >= h.nchunks || !starts[target]) return fail(GSDF_EPROGRAM, "instruction %u: box guard target %u is not a later instruction", n, target);
+            const uint32_t top = chunks[4 * target] & 0xff;
+            if (top != (kind == GSDF_GUARD_MIN ? (uint32_t)GSDF_OP_MIN : (uint32_t)GSDF_OP_DIFF)) return fail(GSDF_EPROGRAM, "instruction %u: box guard target is not its combiner", n);
         }
         if (op == GSDF_OP_EXTRUDE_ENTER || op == GSDF_OP_SCREW_ENTER) {
             const uint32_t kind = chunks[4 * pc + 1] & 0xff, target = chunks[4 * pc + 1] >> 8;
@@ -446,7 +457,7 @@ static int image_run(gsdf_program *p, const float bbmin[2], const float bbmax[2]
     g.rgba = color ? reinterpret_cast<uint32_t *>(target) : nullptr;
     g.cc.kind = GSDF_CONV_DEFAULT;
     if (conv) { g.cc.kind = conv->kind; for (int i = 0; i < 7; i++) g.cc.p[i] = conv->p[i]; g.cc.c0 = conv->c0; g.cc.c1 = conv->c1; }
-    rc = launch_eval<4>(p, g, (uint64_t)((w + 3) / 4) * h, st);
+    rc = launch_eval<4>(p, g, (uint64_t)((((w + 3) / 4) + 31) / 32) * ((h + 15) / 16) * 512u, st);
     if (rc) return rc;
     p->evals += n;
     if (d_out) return 0;

@@ -55,6 +55,65 @@ struct Emitter {
         if (guards && guardable(child)) { g.kind = kind; g.k = k; }
         return g;
     }
+    // ---- box guards (include/gsdf_program.h): 2-D operands whose value is >= dist(p, Bounds()) outside their box
+    bool boxBounded(NodeId id) const {
+        if (!b.valid(id)) return false;
+        const gsdf_tree_node &n = b.node(id);
+        switch (n.kind) {
+        case GSDF_N_POLY2D: case GSDF_N_CIRCLE2D: case GSDF_N_RECT2D: return true;
+        case GSDF_N_TRANSLATE2D: return boxBounded(b.child(n, 0));
+        case GSDF_N_DIFF2D: return boxBounded(b.child(n, 0));  // max(a, -b) >= a
+        case GSDF_N_UNION2D:
+            for (int k = 0; k < n.nchild; k++) if (!boxBounded(b.child(n, k))) return false;
+            return n.nchild > 0;
+        default: return false;
+        }
+    }
+    // Points ON the outline of the operand's zero set, in the operand's own frame: the operand's value at p is <= |p - v|.
+    void anchorsOf(NodeId id, std::vector<Vec2> &out) const {
+        if (!b.valid(id)) return;
+        const gsdf_tree_node &n = b.node(id);
+        const float *f = n.fparam;
+        switch (n.kind) {
+        case GSDF_N_POLY2D: {
+            const float *v = &b.aux()[n.aux_off];
+            for (int i = 0; i < n.aux_cnt / 2; i++) out.push_back({v[2 * i], v[2 * i + 1]});
+            return;
+        }
+        case GSDF_N_CIRCLE2D: out.insert(out.end(), {{f[0], 0}, {-f[0], 0}, {0, f[0]}, {0, -f[0]}}); return;
+        case GSDF_N_RECT2D: out.insert(out.end(), {{0.5f * f[0], 0.5f * f[1]}, {-0.5f * f[0], 0.5f * f[1]}, {0.5f * f[0], -0.5f * f[1]}, {-0.5f * f[0], -0.5f * f[1]}}); return;
+        case GSDF_N_TRANSLATE2D: {
+            size_t first = out.size();
+            anchorsOf(b.child(n, 0), out);
+            for (size_t i = first; i < out.size(); i++) { out[i].x += f[0]; out[i].y += f[1]; }
+            return;
+        }
+        case GSDF_N_UNION2D:  // min(a, b) <= each operand
+            for (int k = 0; k < n.nchild; k++) anchorsOf(b.child(n, k), out);
+            return;
+        case GSDF_N_DIFF2D: {  // max(a, -b) <= |p - v| for v on a's outline and outside b: keep a's anchors clear of b's box
+            std::vector<Vec2> a;
+            anchorsOf(b.child(n, 0), a);
+            const Box2 bb = b.Bounds2(b.child(n, 1));
+            for (Vec2 v : a) if (v.x < bb.min.x || v.x > bb.max.x || v.y < bb.min.y || v.y > bb.max.y) out.push_back(v);
+            return;
+        }
+        default: return;
+        }
+    }
+    static float boxScale(const Box2 &bb) {
+        return 1e-5f * std::max(std::max(std::fabs(bb.min.x), std::fabs(bb.max.x)), std::max(std::fabs(bb.min.y), std::fabs(bb.max.y)));
+    }
+    // Emits BBOX_GUARD2D for the operand `child` (box in the current frame); returns the header word to patch, or 0.
+    size_t boxGuard(NodeId child, uint32_t kind, float margin) {
+        const Box2 bb = b.Bounds2(child);
+        size_t hw = out.chunks.size();
+        header(GSDF_OP_BBOX_GUARD2D, 2, kind, 0, fbits(margin));
+        chunk(bb.min.x, bb.min.y, bb.max.x, bb.max.y);
+        return hw;
+    }
+    void patchBoxGuard(size_t hw, uint32_t kind) { out.chunks[hw + 1] = kind | ((uint32_t)(out.chunks.size() / 4) << 8); }
+
     // The skip lands right behind the guarded node's own exit op (the restoring POP_POS ops of its wrappers follow).
     void patchGuard(size_t headerWord, const Guard &g) {
         if (g.kind != GSDF_GUARD_NONE) out.chunks[headerWord + 1] = g.kind | ((uint32_t)(out.chunks.size() / 4) << 8);
@@ -90,7 +149,12 @@ struct Emitter {
         Guard g;
         if (!is2d && op == GSDF_OP_DIFF) g = guardFor(b.child(n, 1), GSDF_GUARD_DIFF);
         if (!is2d && op == GSDF_OP_SMOOTH_UNION && k > 0) g = guardFor(b.child(n, 1), GSDF_GUARD_SMOOTH_UNION, k);
+        // box guard for the subtrahend of a 2-D difference: tiles that stay outside the minuend never evaluate it
+        size_t bhw = 0;
+        const bool bguard = guards && is2d && op == GSDF_OP_DIFF && boxBounded(b.child(n, 1));
+        if (bguard) bhw = boxGuard(b.child(n, 1), GSDF_GUARD_DIFF, boxScale(b.Bounds2(b.child(n, 1))));
         if (!emit(b.child(n, 1), restore, is2d, g)) return false;
+        if (bguard) patchBoxGuard(bhw, GSDF_GUARD_DIFF);  // lands on the DIFF op, which keeps `a`
         if (hasK) opf(op, k); else op0(op);
         popD();
         return true;
@@ -133,6 +197,36 @@ struct Emitter {
             std::vector<NodeId> order;
             for (int k = 0; k < n.nchild; k++) if (is2d || !guards || !guardable(b.child(n, k))) order.push_back(b.child(n, k));
             for (int k = 0; k < n.nchild; k++) if (!(is2d || !guards || !guardable(b.child(n, k)))) order.push_back(b.child(n, k));
+            // 2-D union of bounded shapes (text): upper bound from anchor points, then a box guard per operand
+            if (is2d && guards && n.nchild >= 3) {
+                std::vector<Vec2> anchors;
+                int nbounded = 0;
+                for (int k = 0; k < n.nchild; k++) {
+                    std::vector<Vec2> a;
+                    anchorsOf(order[k], a);
+                    const size_t want = 8;  // a few per operand, evenly spaced along its outline
+                    for (size_t i = 0; i < std::min(want, a.size()); i++) anchors.push_back(a[i * a.size() / std::min(want, a.size())]);
+                    nbounded += boxBounded(order[k]) ? 1 : 0;
+                }
+                if (!anchors.empty() && nbounded >= 2) {
+                    if (anchors.size() % 2) anchors.push_back(anchors.back());
+                    const float margin = boxScale(b.Bounds2(id));
+                    while (out.aux.size() % 4) out.aux.push_back(0.f);
+                    const uint32_t off = (uint32_t)out.aux.size();
+                    for (Vec2 v : anchors) { out.aux.push_back(v.x); out.aux.push_back(v.y); }
+                    header(GSDF_OP_CULL_UB2D, 1, off, (uint32_t)anchors.size(), fbits(margin));
+                    pushD();
+                    for (int k = 0; k < n.nchild; k++) {
+                        const bool last = k == n.nchild - 1;
+                        const bool gd = boxBounded(order[k]);
+                        size_t hw = gd ? boxGuard(order[k], GSDF_GUARD_MIN, margin) : 0;
+                        if (!emit(order[k], last ? restore : true, true)) return false;
+                        if (gd) patchBoxGuard(hw, GSDF_GUARD_MIN);  // lands on this operand's MIN, which keeps the running minimum
+                        op0(GSDF_OP_MIN); popD();
+                    }
+                    return true;
+                }
+            }
             for (int k = 0; k < n.nchild; k++) {
                 bool last = k == n.nchild - 1;
                 Guard cg = (k > 0 && !is2d) ? guardFor(order[k], GSDF_GUARD_MIN) : Guard{};

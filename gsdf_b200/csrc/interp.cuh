@@ -603,6 +603,35 @@ __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restri
             }
             m.pushPos(x0, y0, m.pz);
         } break;
+        case GSDF_OP_CULL_UB2D: {  // box guards (gsdf_program.h): upper bound of the union from anchor points on the outlines
+            const float4 *an = aux + (h.y >> 2);
+            const int npairs = (int)(h.z >> 1);
+            float best[P];
+#pragma unroll
+            for (int j = 0; j < P; j++) best[j] = 3.0e38f;
+            for (int q = 0; q < npairs; q++) {
+                const float4 v = an[q];
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    const float ax = m.px[j] - v.x, ay = m.py[j] - v.y, bx = m.px[j] - v.z, by = m.py[j] - v.w;
+                    best[j] = minf(best[j], minf(ax * ax + ay * ay, bx * bx + by * by));
+                }
+            }
+            m.pushD();
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = m32::sqrt(best[j]) * 1.0001f + f3;
+        } break;
+        case GSDF_OP_BBOX_GUARD2D: {
+            const float4 bx = ldf4(prog, pc + 1);
+            bool dead = true;
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                const float dx = maxf(maxf(bx.x - m.px[j], m.px[j] - bx.z), 0.f), dy = maxf(maxf(bx.y - m.py[j], m.py[j] - bx.w), 0.f);
+                const float w = m32::sqrt(dx * dx + dy * dy) * 0.9999f - f3;
+                dead &= guard_dead(h.y & 0xffu, w, m.top[j], 0.f);
+            }
+            if (__syncthreads_and(dead)) { m.skip = true; pc = (int)(h.y >> 8); continue; }
+        } break;
         case GSDF_OP_EXTRUDE_ENTER: {  // :524-527  f2=h/2
             if (h.y & 0xffu) {
                 bool dead = true;

@@ -350,12 +350,22 @@ struct GenCenters {
 // ImageRendererSDF2.Render positions (glrender/image.go:85-105). rgba != nullptr: the colour conversion is applied in
 // the sink and four RGBA8 pixels leave as one 16-byte store (image.go:112-116 fused); else the distances are stored.
 struct GenImage {
+    // Work items are grouped into 2-D tiles of 32 quads x 16 rows (128 x 16 pixels = one 512-thread CTA tile), so that a
+    // tile is spatially compact and the CTA-uniform guards (gsdf_program.h) fire; a warp still covers 512 contiguous
+    // bytes of one image row.
     float xmin, ymax, dx, dy; int w, h; float *dist; uint32_t *rgba; ColorConv cc;
-    __device__ uint64_t work_items() const { return (uint64_t)((w + 3) / 4) * h; }
+    __device__ uint32_t tiles_x() const { return ((uint32_t)(w + 3) / 4 + 31u) / 32u; }
+    __device__ uint64_t work_items() const { return (uint64_t)tiles_x() * (((uint32_t)h + 15u) / 16u) * 512u; }
+    __device__ void decode(uint64_t wi, int &q, int &j) const {
+        const uint32_t t = (uint32_t)(wi & 511u), tile = (uint32_t)(wi >> 9);
+        const uint32_t tx = tile % tiles_x(), ty = tile / tiles_x();
+        q = (int)(tx * 32u + (t & 31u));
+        j = (int)(ty * 16u + (t >> 5));
+    }
     __device__ void load(uint64_t wi, float (&x)[4], float (&y)[4], float (&z)[4]) const {
-        const uint32_t nq = (uint32_t)(w + 3) / 4;
-        const int q = (int)((uint32_t)wi % nq), j = (int)((uint32_t)wi / nq);
-        const float yy = ymax - (float)j * dy;
+        int q, j;
+        decode(wi, q, j);
+        const float yy = ymax - (float)min(j, h - 1) * dy;
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             const int i = min(4 * q + t, w - 1);
@@ -363,8 +373,9 @@ struct GenImage {
         }
     }
     __device__ void store(uint64_t wi, const float (&d)[4]) const {
-        const uint32_t nq = (uint32_t)(w + 3) / 4;
-        const int q = (int)((uint32_t)wi % nq), j = (int)((uint32_t)wi / nq);
+        int q, j;
+        decode(wi, q, j);
+        if (j >= h || 4 * q >= w) return;
         if (rgba) {
             uint32_t c[4];
 #pragma unroll

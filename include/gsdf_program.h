@@ -88,8 +88,28 @@ enum gsdf_opcode {
     GSDF_OP_EXTRUDE_ENTER, /* :506    w1=guard w2=h/2 w3=guard k : push(|z|-h/2) */
     GSDF_OP_REVOLVE,     /* :533      w2=off : p=(hypot(x,z)-off, y) */
     GSDF_OP_SCREW_ENTER, /* threads.go:141-170 w1=guard w3=guard k c1=(pitch,lead,L/2,tanTaper) : push(|z|-L/2) ; p=(saw,y) */
+    /* ---- 2-D bounding-box culling of union / difference operands (see "box guards" below) ---- */
+    GSDF_OP_CULL_UB2D,   /* w1=aux_off w2=npts w3=abs margin ; aux: anchor points (x,y) ON the operands' outlines.
+                            push(U), U = (1+1e-4)*min_k |p - v_k| + margin >= min over the union's operands */
+    GSDF_OP_BBOX_GUARD2D,/* w1=guard kind | target<<8, w3=abs margin, c1=(minx,miny,maxx,maxy) of the operand that follows:
+                            w = (1-1e-4)*dist(p, box) - margin <= operand(p) ; guard_dead(kind, w, top) for the whole tile
+                            => jump to `target` (the operand's combiner, which then keeps `top`) */
     GSDF_OP__COUNT
 };
+
+/* Box guards -- the slab-guard idea for 2-D unions of bounded shapes (glyphs of a text line, forge/textsdf/font.go:89-141).
+ *
+ * For operands built only from exact 2-D primitives (poly2D, circle, rect), translate2D, union2D and the minuend of
+ * diff2D, the value at p is >= dist(p, Bounds()) outside the box and <= |p - v| for any point v on the operand's
+ * outline. A union first pushes U (CULL_UB2D, from a few anchor points per operand) as an EXTRA operand of its min fold:
+ * U >= the operand that owns the nearest anchor >= the true minimum, so min(U, d_1 .. d_n) == min(d_1 .. d_n) bit for
+ * bit. Each operand is then preceded by BBOX_GUARD2D(MIN): when its box is farther than the running minimum for every
+ * point of the CTA's tile, the operand (hundreds of polygon edges) is skipped and its MIN keeps the running value; the
+ * operand holding the minimum can never be skipped because its lower bound is <= its value <= the running minimum.
+ * The subtrahend of a diff2D is guarded the same way with GSDF_GUARD_DIFF (-w < a => max(a, -s) == a): the hole of a
+ * glyph is only evaluated by tiles that reach into the glyph. Relative (1e-4) and absolute (1e-5 * coordinate scale)
+ * margins absorb the float rounding of the bounds themselves. Image tiles are 128 x 16 pixels, so the predicate is
+ * uniform over almost every tile. */
 
 /* Slab guards -- the one place the stream has control flow, and it is CTA-uniform and value-preserving.
  *

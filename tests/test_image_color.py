@@ -162,3 +162,46 @@ def test_image_renderer_errors(bld):
         glrender.NewImageRendererSDF2(4096, bad).Render(sdf, np.zeros((4, 4, 4), np.uint8))
     with pytest.raises(gsdf_b200.GsdfError):
         glrender.NewImageRendererSDF2(4096).Render(sdf3, np.zeros((4, 4, 4), np.uint8))
+
+
+@pytest.mark.gpu
+def test_box_guards_do_not_change_a_single_bit(oracle, bld, monkeypatch):
+    """Unions of bounded 2-D shapes run with box guards (include/gsdf_program.h): tiles skip operands whose bounding box is
+    farther than the running minimum. Images (2-D tiles) and point lists, guarded and unguarded, equal the oracle."""
+    rng = np.random.default_rng(5)
+
+    def blob(n, r, cx, cy, seed):
+        g = np.random.default_rng(seed)
+        ang = np.sort(g.uniform(0, 2 * np.pi, n))
+        rad = r * (1 + 0.3 * np.sin(3 * ang + seed))
+        return np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], 1).astype(np.float32)
+
+    shapes2 = {
+        "text": fontfix.text_scene(bld),
+        "text-small-tol": fontfix.text_scene(bld, "p8~A", tol=0.01),
+        "blobs": bld.Union2D(*[bld.NewPolygon(blob(9 + k, 0.4, 1.3 * (k % 4), 1.1 * (k // 4), k)) for k in range(10)]),
+        "mixed": bld.Union2D(bld.NewCircle(0.5), bld.Translate2D(bld.NewRectangle(1.0, 0.4), 2.0, 0.3),
+                             bld.Translate2D(bld.Difference2D(bld.NewCircle(0.6), bld.NewCircle(0.3)), 4.0, -0.2),
+                             bld.Translate2D(bld.NewHexagon(0.4), 1.0, 1.5),   # not box-bounded: never guarded, still correct
+                             bld.Translate2D(bld.NewPolygon(blob(12, 0.5, 0, 0, 3)), 3.0, 1.4)),
+    }
+    for name, s in shapes2.items():
+        t = oracle.Tree.from_shader(s)
+        mn, mx = s.Bounds()
+        for guards in (True, False):
+            if guards:
+                monkeypatch.delenv("GSDF_NO_GUARDS", raising=False)
+            else:
+                monkeypatch.setenv("GSDF_NO_GUARDS", "1")
+            sdf = gleval.NewCUDASDF2(s)
+            for w, h in [(640, 200), (131, 37), (64, 1024)]:
+                got = glrender.ImageEvaluateSDF2(sdf, w, h)
+                want = t.image_eval2(mn, mx, w, h)
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (name, guards, w, h, int((got.view(np.uint32) != want.view(np.uint32)).sum()))
+            # point lists: spatially sorted (guards fire) and shuffled (they rarely do)
+            pos = (mn - 0.5 * (mx - mn) + rng.random((30000, 2), dtype=np.float32) * 2.0 * (mx - mn)).astype(np.float32)
+            for arr in (pos[np.lexsort((pos[:, 0], pos[:, 1]))], pos):
+                arr = np.ascontiguousarray(arr)
+                out = np.empty(len(arr), np.float32)
+                sdf.Evaluate(arr, out)
+                assert np.array_equal(out.view(np.uint32), t.eval2(arr).view(np.uint32)), (name, guards)

@@ -198,3 +198,37 @@ def test_text_image_matches_the_oracle_golden(oracle, bld):
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "text_image.npz"))
     assert np.array_equal(np.concatenate([mn, mx]).view(np.uint32), z["bounds"].view(np.uint32))
     assert np.array_equal(img.view(np.uint32), z["dist"].view(np.uint32))
+
+
+def _ops(flat):
+    import struct
+    words = np.frombuffer(flat["blob"], np.uint32, offset=32).reshape(-1, 4)
+    out, pc = [], 0
+    while pc < len(words):
+        op, ln = int(words[pc, 0]) & 0xff, (int(words[pc, 0]) >> 8) & 0xff
+        out.append((pc, op, ln, words[pc]))
+        pc += ln
+    return out
+
+
+def test_box_guards_are_emitted_for_the_text_union(bld, monkeypatch):
+    """include/gsdf_program.h "box guards": the text union gets one CULL_UB2D, one BBOX_GUARD2D(MIN) per glyph and one
+    BBOX_GUARD2D(DIFF) per hole; every guard's target is its combiner; GSDF_NO_GUARDS=1 removes them all."""
+    OP_MIN, OP_DIFF, OP_CULL, OP_BBOX = 20, 22, 51, 52  # enum gsdf_opcode (include/gsdf_program.h)
+    s = fontfix.text_scene(bld)
+    ops = _ops(bld.flatten(s))
+    kinds = [o[1] for o in ops]
+    assert kinds.count(OP_CULL) == 1 and kinds.index(OP_CULL) == 0
+    guards = [o for o in ops if o[1] == OP_BBOX]
+    starts = {o[0]: o[1] for o in ops}
+    nmin = sum(1 for g in guards if int(g[3][1]) & 0xff == 2)
+    ndiff = sum(1 for g in guards if int(g[3][1]) & 0xff == 1)
+    assert nmin == 7          # one per glyph of "Abc123~"
+    assert ndiff == 2         # 'A' and 'b' have a hole (Difference2D, font.go:250-254)
+    for g in guards:
+        kind, target = int(g[3][1]) & 0xff, int(g[3][1]) >> 8
+        assert target > g[0] and starts[target] == (OP_MIN if kind == 2 else OP_DIFF)
+    assert kinds.count(OP_MIN) == 7  # U is an extra operand of the fold: one MIN per glyph
+    monkeypatch.setenv("GSDF_NO_GUARDS", "1")
+    plain = [o[1] for o in _ops(bld.flatten(s))]
+    assert OP_CULL not in plain and OP_BBOX not in plain and plain.count(OP_MIN) == 6
