@@ -137,7 +137,7 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
         "readme_reference": {"evals_per_sec": 6711686 / 0.313, "hardware": "i5-12400F, 11 goroutines (README.md:128-130)"},
     }
-    print(json.dumps(line))
+    emit_json(line)
 
 
 def bind_to_gpu_numa(local_rank):
@@ -410,12 +410,29 @@ def run_cuda(args, rank, local_rank, world):
     }
     if zslab:
         line["zslab"] = zslab
-    print(json.dumps(line))
+    emit_json(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit_json(line):
+    """The contract is ONE JSON line on stdout. Libraries (NCCL's version banner when NCCL_DEBUG is set, torch warnings)
+    also write to fd 1, so main() points fd 1 at stderr for the whole run and the line goes to the saved descriptor."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_OUT is not None:
+        os.write(_JSON_OUT, data)
+    else:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+
+
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -927,6 +927,8 @@ struct gsdf_dualcontour {
     int device = 0;
     float bbmin[3], bbmax[3], res = 0;
     int placer = 0, levels = 0;
+    int part = 0, nparts = 1;   // this handle owns the part-th of nparts equal ranges of the octree BFS cube order
+    uint64_t owned_cubes = 0;
     DCGrid G{};
     float *d_dist = nullptr; size_t dist_cap = 0;
     uint32_t *d_eidx = nullptr; size_t eidx_cap = 0;
@@ -976,8 +978,26 @@ int dc_run(gsdf_dualcontour *d) {
     if ((rc = grow(d->d_eidx, d->eidx_cap, (size_t)G.ncell + 8))) return rc;
     CU(cudaEventRecord(d->ev[0], st));
     // Reset: every level-1 cube origin, in octree BFS order (dual_contour.go:37-57)
+    // Owned key range and the box of cube origins this part needs: its octants grown by one cube on the low side
+    // (FinalVertex of the -1 neighbours, dual_contour.go:282-298) and by one more on both sides for THEIR edge data.
+    const uint32_t key0 = (uint32_t)((uint64_t)G.ncell * d->part / d->nparts), key1 = (uint32_t)((uint64_t)G.ncell * (d->part + 1) / d->nparts);
+    const int N = 1 << G.bits;
+    int blo[3] = {N, N, N}, bhi[3] = {0, 0, 0};
+    if (d->nparts == 1) { blo[0] = blo[1] = blo[2] = 0; bhi[0] = bhi[1] = bhi[2] = N; }
+    else {
+        const uint32_t oct = G.ncell / 8;  // nparts divides 8: the range is a run of top-level octants
+        for (uint32_t k = key0; k < key1; k += oct) {
+            int i, j, kk;
+            dc_unkey(k, G.bits, i, j, kk);
+            const int c[3] = {i, j, kk};
+            for (int a = 0; a < 3; a++) { blo[a] = std::min(blo[a], c[a]); bhi[a] = std::max(bhi[a], c[a] + N / 2); }
+        }
+        for (int a = 0; a < 3; a++) { blo[a] = std::max(0, blo[a] - 1); bhi[a] = std::min(N, bhi[a] + 1); }
+    }
     GenDC g{};
     g.mode = 0; g.G = G; g.dist = d->d_dist;
+    for (int a = 0; a < 3; a++) { g.blo[a] = blo[a]; g.bhi[a] = bhi[a]; }
+    g.clip = d->nparts > 1 ? 1 : 0;
     if ((rc = launch_eval<4>(p, g, ((uint64_t)G.ncell + 3) / 4, st))) return rc;
     k_dc_flags<<<grid_for(G.ncell, 256), 256, 0, st>>>(d->d_dist, G.ncell, G.res, d->d_eidx);
     CU(cudaGetLastError());
@@ -989,7 +1009,8 @@ int dc_run(gsdf_dualcontour *d) {
     d->ncubes = tot;
     d->ntri = 0; d->with_nb = 0;
     const uint32_t nc = (uint32_t)d->ncubes;
-    d->evals = (uint64_t)G.ncell + 4ull * nc + (d->placer != GSDF_DC_NAIVE ? 18ull * nc : 0ull);
+    const uint64_t norig = (uint64_t)(bhi[0] - blo[0]) * (bhi[1] - blo[1]) * (bhi[2] - blo[2]);
+    d->evals = norig + 4ull * nc + (d->placer != GSDF_DC_NAIVE ? 18ull * nc : 0ull);
     if (nc == 0) {
         CU(cudaEventRecord(d->ev[1], st));
         CU(cudaStreamSynchronize(st));
@@ -1009,6 +1030,7 @@ int dc_run(gsdf_dualcontour *d) {
     A.G = G; A.dist = d->d_dist; A.eidx = d->d_eidx; A.cubekey = d->d_cubekey; A.ncubes = nc; A.dc4 = d->d_dc4;
     A.fin = d->d_fin; A.qcount = d->d_qcount; A.placer = d->placer;
     A.with_neighbors = reinterpret_cast<unsigned long long *>(d->d_ctr + 4);
+    A.key0 = key0; A.key1 = key1;
     if (d->placer != GSDF_DC_NAIVE) {
         if ((rc = grow(d->d_nrm, d->nrm_cap, (size_t)nc * 9))) return rc;
         const double normStep = d->placer == GSDF_DC_LEAST_SQUARES_CHISELED ? 1e-4 : 2e-8;  // vertexplacement.go:42-46
@@ -1061,7 +1083,14 @@ int gsdf_dc_levels(const float bbmin[3], const float bbmax[3], float res, float 
 }
 
 int gsdf_dc_begin(gsdf_program *p, const float bbmin[3], const float bbmax[3], float res, int placer, gsdf_dualcontour **out) {
+    return gsdf_dc_begin_part(p, bbmin, bbmax, res, placer, 0, 1, out);
+}
+
+int gsdf_dc_begin_part(gsdf_program *p, const float bbmin[3], const float bbmax[3], float res, int placer, int part, int nparts,
+                       gsdf_dualcontour **out) {
     if (!p || !bbmin || !bbmax || !out) return fail(GSDF_EINVAL, "gsdf_dc_begin: NULL argument");
+    if (!(nparts == 1 || nparts == 2 || nparts == 4 || nparts == 8) || part < 0 || part >= nparts)
+        return fail(GSDF_EINVAL, "dual contour parts: nparts must be 1, 2, 4 or 8 (runs of top-level octants) and 0 <= part < nparts");
     if (p->dim != 3) return fail(GSDF_EINVAL, "program is not 3D");
     if (placer < GSDF_DC_NAIVE || placer > GSDF_DC_LEAST_SQUARES_CHISELED) return fail(GSDF_EINVAL, "nil DualContourer argument to Reset");  // dual_contour.go:28-30
     float org[3];
@@ -1076,6 +1105,7 @@ int gsdf_dc_begin(gsdf_program *p, const float bbmin[3], const float bbmax[3], f
     d->device = p->device;
     for (int a = 0; a < 3; a++) { d->bbmin[a] = bbmin[a]; d->bbmax[a] = bbmax[a]; }
     d->res = res; d->placer = placer; d->levels = levels;
+    d->part = part; d->nparts = nparts;
     d->G.ox = org[0]; d->G.oy = org[1]; d->G.oz = org[2]; d->G.res = res;
     d->G.bits = levels - 1;
     d->G.ncell = 1u << (3 * (levels - 1));

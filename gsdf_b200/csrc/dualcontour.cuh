@@ -51,8 +51,29 @@ __device__ __forceinline__ float dc_isect(float o, float e) { return -o / (e - o
 
 // Generator for the three interpreter passes (one k_eval instantiation; `mode` is launch-uniform).
 struct GenDC {
+    static constexpr bool kTileSkip = true;
     int mode;
     DCGrid G;
+    int blo[3], bhi[3];        // mode 0: cube origins outside [blo, bhi) are not needed by this part (multi-GPU octant split)
+    int clip;                  // 0: the box is the whole grid (single part), no test needed
+    __device__ bool dead(uint64_t w) const {
+        if (mode != 0 || !clip) return false;
+        bool out = true;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const uint32_t key = min((uint32_t)(4 * w + t), G.ncell - 1);
+            int i, j, k;
+            dc_unkey(key, G.bits, i, j, k);
+            out &= (i < blo[0] || i >= bhi[0] || j < blo[1] || j >= bhi[1] || k < blo[2] || k >= bhi[2]);
+        }
+        return out;
+    }
+    __device__ void store_dead(uint64_t w) const {  // +inf = pruned (|d| >= 2 res)
+        const float inf = __int_as_float(0x7f800000);
+        if (4 * w + 4 <= G.ncell) reinterpret_cast<float4 *>(dist)[w] = make_float4(inf, inf, inf, inf);
+        else
+            for (int t = 0; t < 4; t++) if (4 * w + t < G.ncell) dist[4 * w + t] = inf;
+    }
     float *dist;               // mode 0 out: dist[key]
     const uint32_t *cubekey;   // modes 1,2: key of cube e
     uint32_t ncubes;
@@ -142,6 +163,7 @@ struct DCArgs {
     float sqrtLambda;
     float *tris;
     unsigned long long *with_neighbors;
+    uint32_t key0, key1;      // cubes with key in [key0, key1) are OWNED by this part: only they emit quads / are counted
 };
 
 // cubeMap[iv] (dual_contour.go:98): cube index of cell (i,j,k) or -1
@@ -210,7 +232,9 @@ __global__ void __launch_bounds__(128) k_dc_place(DCArgs A) {
         for (int q = 0; q < 4 && all; q++) all = dc_lookup(A, ci + kDcEnb[a][q][0], cj + kDcEnb[a][q][1], ck + kDcEnb[a][q][2]) >= 0;
         nq += all ? 1u : 0u;
     }
-    A.qcount[c] = nq;
+    const uint32_t ckey = A.cubekey[c];
+    const bool owned = ckey >= A.key0 && ckey < A.key1;
+    A.qcount[c] = owned ? nq : 0u;
     // entries (n, a): cube n whose active a-edge touches this voxel, i.e. this cube = n + ENB[a][q]
     uint32_t ent[12];
     int nnb = 0;
@@ -229,7 +253,7 @@ __global__ void __launch_bounds__(128) k_dc_place(DCArgs A) {
         ent[j + 1] = v;
     }
     if (nnb == 0) { A.fin[c] = co; return; }  // default FinalVertex = cube origin (dual_contour.go:114)
-    atomicAdd(A.with_neighbors, 1ull);
+    if (owned) atomicAdd(A.with_neighbors, 1ull);
     // contribution of entry (n, a): the edge's linear zero crossing
     auto contrib = [&](uint32_t n, int a) {
         int i, j, k;
@@ -291,6 +315,7 @@ __global__ void __launch_bounds__(128) k_dc_emit(DCArgs A) {
     dc_unkey(A.cubekey[c], A.G.bits, ci, cj, ck);
     const float4 own = A.dc4[c];
     uint64_t o = (uint64_t)A.qcount[c];
+    if (A.cubekey[c] < A.key0 || A.cubekey[c] >= A.key1) return;
     for (int a = 0; a < 3; a++) {
         const float ed = a == 0 ? own.y : (a == 1 ? own.z : own.w);
         if (!dc_active(own.x, ed)) continue;

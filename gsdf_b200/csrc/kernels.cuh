@@ -102,6 +102,12 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval(ProgView pv, Gen gen) {
         const uint64_t w = (uint64_t)(*s_tile) * blockDim.x + threadIdx.x;
         __syncthreads();
         if (w - threadIdx.x >= nwork) break;
+        if constexpr (Gen::kTileSkip) {  // generator-level CTA-uniform skip of a whole tile (GenDC: cubes outside this rank's region)
+            if (__syncthreads_and(gen.dead(w < nwork ? w : nwork - 1))) {
+                if (w < nwork) gen.store_dead(w);
+                continue;
+            }
+        }
 #ifdef GSDF_LOCKSTEP
         // every thread of the tile runs the program (barriers inside); threads past the end redo the last item
         const uint64_t wc = w < nwork ? w : nwork - 1;
@@ -130,6 +136,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval(ProgView pv, Gen gen) {
 // ---------------------------------------------------------------------------------------------- generators
 // gleval.SDF3.Evaluate on an AoS float3 list (gleval/gleval.go:15-24): 4 points per thread, 3x float4 loads.
 struct GenPoints3 {
+    static constexpr bool kTileSkip = false;
     const float *pos; float *dist; uint64_t n; int vec;  // vec: both pointers 16-byte aligned
     __device__ uint64_t work_items() const { return (n + 3) / 4; }
     __device__ void load(uint64_t w, float (&x)[4], float (&y)[4], float (&z)[4]) const {
@@ -159,6 +166,7 @@ struct GenPoints3 {
 };
 // gleval.SDF2.Evaluate (gleval/gleval.go:28-37): AoS float2, 2x float4 loads per 4 points.
 struct GenPoints2 {
+    static constexpr bool kTileSkip = false;
     const float *pos; float *dist; uint64_t n; int vec;
     __device__ uint64_t work_items() const { return (n + 3) / 4; }
     __device__ void load(uint64_t w, float (&x)[4], float (&y)[4], float (&z)[4]) const {
@@ -294,6 +302,7 @@ struct Lat {
 // list==nullptr: every quad of the slab; else the compacted quad ids produced by k_compact_quads.
 template <int P>
 struct GenGrid {
+    static constexpr bool kTileSkip = false;
     static_assert(P == 1 || P == 2 || P == 4, "P must divide 4");
     Lat L; float *dist; const uint32_t *list; const uint32_t *count;
     __device__ uint64_t work_items() const { return (list ? (uint64_t)*count : (uint64_t)L.nqx * (L.ny + 1) * L.nk) * (4 / P); }
@@ -334,6 +343,7 @@ struct GenGrid {
 // wide) of the slab; keep it iff |d| < size*sqrt3/2. One byte per block, x fastest. One cube per thread: the pass is
 // small and latency bound, so it wants threads, not per-thread ILP.
 struct GenCenters {
+    static constexpr bool kTileSkip = false;
     float ox, oy, oz, res; int nbx, nby, nbz, bz0; float half, maxDist; uint8_t *mask;
     __device__ uint64_t work_items() const { return (uint64_t)nbx * nby * nbz; }
     __device__ void load(uint64_t w, float (&x)[1], float (&y)[1], float (&z)[1]) const {
@@ -350,6 +360,7 @@ struct GenCenters {
 // ImageRendererSDF2.Render positions (glrender/image.go:85-105). rgba != nullptr: the colour conversion is applied in
 // the sink and four RGBA8 pixels leave as one 16-byte store (image.go:112-116 fused); else the distances are stored.
 struct GenImage {
+    static constexpr bool kTileSkip = false;
     // Work items are grouped into 2-D tiles of 32 quads x 16 rows (128 x 16 pixels = one 512-thread CTA tile), so that a
     // tile is spatially compact and the CTA-uniform guards (gsdf_program.h) fire; a warp still covers 512 contiguous
     // bytes of one image row.

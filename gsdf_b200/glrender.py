@@ -330,7 +330,9 @@ class DualContourRenderer:
     def __init__(self):
         self._h = None
 
-    def Reset(self, sdf, res, vertexPlacer, userData=None):
+    def Reset(self, sdf, res, vertexPlacer, userData=None, part=0, nparts=1):
+        """part / nparts (1, 2, 4, 8): multi-GPU split by top-level octants; rank r passes part=r, nparts=world size and
+        the ranks' RenderAll results concatenated in rank order equal the single-renderer mesh."""
         if vertexPlacer is None or not hasattr(vertexPlacer, "_kind"):
             raise GsdfError(_lib.EINVAL, "nil DualContourer argument to Reset")  # dual_contour.go:28-30
         self.Close()
@@ -338,7 +340,7 @@ class DualContourRenderer:
         a = (C.c_float * 3)(*[float(v) for v in mn])
         b = (C.c_float * 3)(*[float(v) for v in mx])
         h = C.c_void_p()
-        check(lib.gsdf_dc_begin(sdf._h, a, b, float(res), int(vertexPlacer._kind), C.byref(h)))
+        check(lib.gsdf_dc_begin_part(sdf._h, a, b, float(res), int(vertexPlacer._kind), int(part), int(nparts), C.byref(h)))
         self._h, self._sdf = h, sdf
 
     def Rerun(self):

@@ -146,6 +146,12 @@ int gsdf_dc_levels(const float bbmin[3], const float bbmax[3], float res, float 
 /* DualContourRenderer.Reset(sdf, res, placer) + RenderAll: the whole mesh is built on the device inside this call.
  * bbmin/bbmax = sdf.Bounds(). Limits: at most 1024 cubes per axis (11 levels). */
 int gsdf_dc_begin(gsdf_program *p, const float bbmin[3], const float bbmax[3], float res, int placer, gsdf_dualcontour **out);
+/* Multi-GPU form: this handle owns part `part` of `nparts` (1, 2, 4 or 8) equal, contiguous ranges of the octree's BFS
+ * cube order -- runs of top-level octants. It evaluates its octants plus a two-cube border (the neighbour data the QEF
+ * and the quads of its own cubes need), and emits only the quads of its own cubes; the parts' triangle buffers
+ * concatenated in part order are bit-identical to the single-handle mesh. No collective on the data path. */
+int gsdf_dc_begin_part(gsdf_program *p, const float bbmin[3], const float bbmax[3], float res, int placer, int part, int nparts,
+                       gsdf_dualcontour **out);
 /* Re-run with the same parameters, reusing every device buffer. */
 int gsdf_dc_rerun(gsdf_dualcontour *d);
 /* RenderAll's result: copies up to max_tris triangles (9 floats each, cube order, two per quad) from the start of the

@@ -180,3 +180,36 @@ def test_gpu_dual_contour_errors(bld):
     sdf2 = gleval.NewCUDASDF2(bld.NewCircle(1.0))
     with pytest.raises(gsdf_b200.GsdfError):
         dcr.Reset(sdf2, 0.1, glrender.DualContourNaive())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,res,placer", [("sphere", 1.0 / 6, "lsq"), ("snowman", 3.0 / 64, "chiseled"), ("flange", None, "chiseled"), ("box", 2.0 / 8, "naive")])
+def test_gpu_dual_contour_octant_parts_concatenate_to_the_whole(bld, shape, res, placer):
+    """Multi-GPU layout: part r of nparts owns a run of top-level octants (a contiguous range of the BFS cube order) and
+    recomputes a two-cube border instead of exchanging halos; the parts' meshes concatenated in part order are
+    bit-identical to the single-renderer mesh (same property as test_z_slabs_concatenate_to_the_whole for marching cubes)."""
+    s = gsdf.scene(bld, "npt-flange") if shape == "flange" else SHAPES[shape](bld)
+    if res is None:
+        res = s.Diagonal() / np.float32(90)
+    sdf = gleval.NewCUDASDF3(s)
+    vp = {"naive": glrender.DualContourNaive(), "lsq": glrender.DualContourLeastSquares(), "chiseled": glrender.DualContourLeastSquares(Chiseled=True)}[placer]
+    whole = glrender.DualContourRenderer()
+    whole.Reset(sdf, np.float32(res), vp)
+    want = whole.RenderAll(None)
+    assert len(want) > 0
+    for nparts in (2, 4, 8):
+        parts, nb = [], 0
+        for r in range(nparts):
+            d = glrender.DualContourRenderer()
+            d.Reset(sdf, np.float32(res), vp, part=r, nparts=nparts)
+            parts.append(d.RenderAll(None))
+            nb += d.Stats()["with_neighbors"]
+            if nparts == 8:
+                assert d.Stats()["evals"] < whole.Stats()["evals"]  # an octant plus its border, not the whole cube
+            d.Close()
+        got = np.concatenate(parts)
+        assert len(got) == len(want), (nparts, [len(p) for p in parts])
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), nparts
+        assert nb == whole.Stats()["with_neighbors"]
+    with pytest.raises(gsdf_b200.GsdfError, match="nparts must be"):
+        glrender.DualContourRenderer().Reset(sdf, np.float32(res), vp, part=0, nparts=3)
