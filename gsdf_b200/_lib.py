@@ -62,6 +62,9 @@ def _load():
         "gsdf_grid_eval_device": (C.c_int, [vp, C.POINTER(Lattice), C.c_int, C.c_int, vp, vp]),
         "gsdf_mesh_begin": (C.c_int, [vp, C.POINTER(Lattice), C.c_int, C.c_int, C.c_uint, C.POINTER(vp)]),
         "gsdf_mesh_rerun": (C.c_int, [vp]),
+        "gsdf_mesh_rerun_begin": (C.c_int, [vp]),
+        "gsdf_mesh_rerun_end": (C.c_int, [vp]),
+        "gsdf_mesh_read_prefix_async": (C.c_int64, [vp, vp, C.c_size_t]),
         "gsdf_mesh_set_program": (C.c_int, [vp, vp]),
         "gsdf_mesh_read": (C.c_int64, [vp, vp, C.c_size_t]),
         "gsdf_mesh_read_async": (C.c_int64, [vp, vp, C.c_size_t]),

@@ -561,6 +561,10 @@ struct gsdf_mesher {
     std::vector<uint8_t> gkey;  // snapshot of every pointer / size the captured launches were built from
     bool allow_graph = true;
     uint64_t runs = 0;
+    // a render that was enqueued (mesh_run_begin) and not yet finished (mesh_run_end)
+    bool pending = false, pend_graph = false, pend_emitted = false;
+    MCArgs pendA{};
+    unsigned pend_mcgrid = 0;
 };
 
 namespace {
@@ -594,7 +598,11 @@ unsigned grid_for(uint64_t items, int per_block, int waves = 8) {
     return (unsigned)std::max<uint64_t>(b, 1);
 }
 
-int mesh_run(gsdf_mesher *m) {
+int mesh_run_end(gsdf_mesher *m);
+
+// Enqueues one render on the program's stream and returns without waiting (mesh_run_end finishes it).
+int mesh_run_begin(gsdf_mesher *m) {
+    if (m->pending) { int erc = mesh_run_end(m); if (erc) return erc; }
     gsdf_program *p = m->prog;
     CU(cudaSetDevice(p->device));
     cudaStream_t st = p->stream;
@@ -661,8 +669,11 @@ int mesh_run(gsdf_mesher *m) {
     auto enqueue = [&](bool stage_events, uint32_t epoch, bool clear_scan) -> int {
     int rc = 0;
     if (m->flags & GSDF_MESH_KEEP_GRID) CU(cudaMemsetAsync(m->d_grid, 0x7f, (size_t)D.pitch * (D.ny + 1) * nk * sizeof(float), st));
-    CU(cudaMemsetAsync(m->d_ctr, 0, 8 * sizeof(uint32_t), st));
-    if (clear_scan) CU(cudaMemsetAsync(m->d_scanstate, 0, (size_t)nscantiles * sizeof(unsigned long long), st));
+    {
+        const uint32_t nstate = clear_scan ? (uint32_t)nscantiles : 0u;
+        k_clear_state<<<(unsigned)std::min<uint64_t>(std::max<uint64_t>((nstate + 255) / 256, 1), 64), 256, 0, st>>>(m->d_ctr, 8, m->d_scanstate, nstate);
+        CU(cudaGetLastError());
+    }
     if (prune) {
         GenCenters gc;
         gc.ox = lat.origin[0]; gc.oy = lat.origin[1]; gc.oz = lat.origin[2]; gc.res = lat.res;
@@ -711,6 +722,8 @@ int mesh_run(gsdf_mesher *m) {
         k_mc_emit<<<mcgrid, kThreads, 0, st>>>(E);
         CU(cudaGetLastError());
     }
+    k_publish_counters<<<1, 32, 0, st>>>(m->d_ctr, m->h_ctr, 8);  // cudaMallocHost memory is device-mapped under UVA
+    CU(cudaGetLastError());
     return rc;
     };  // enqueue
 
@@ -750,11 +763,30 @@ int mesh_run(gsdf_mesher *m) {
         if ((rc = enqueue(true, m->scan_epoch, false))) return rc;
     }
     CU(cudaEventRecord(m->ev[4], st));
-    CU(cudaMemcpyAsync(m->h_ctr, m->d_ctr, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    m->pending = true; m->pend_graph = use_graph; m->pend_emitted = emitted; m->pendA = A; m->pend_mcgrid = mcgrid;
+    return 0;
+}
+
+// Waits for the enqueued render, reads its counters, re-emits if the triangle buffer was too small, fills the statistics.
+int mesh_run_end(gsdf_mesher *m) {
+    if (!m->pending) return 0;
+    m->pending = false;
+    gsdf_program *p = m->prog;
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = p->stream;
+    const MeshDims &D = m->D;
+    const bool prune = (m->flags & GSDF_MESH_PRUNE) != 0;
+    const int nk = D.cz1 - D.cz0 + 1;
+    const uint64_t nblocks = (uint64_t)D.nbx * D.nby * D.nbz;
+    const bool use_graph = m->pend_graph, emitted = m->pend_emitted;
+    MCArgs A = m->pendA;
+    const unsigned mcgrid = m->pend_mcgrid;
+    int rc;
+    CU(cudaEventSynchronize(m->ev[4]));  // the counters were published to m->h_ctr by the last kernel of the sequence
     uint64_t total;
     std::memcpy(&total, m->h_ctr + 2, 8);
     if (!emitted || total * 9 > m->tri_cap) {
+        if (m->copy_stream) CU(cudaStreamSynchronize(m->copy_stream));  // a speculative prefix read may be using d_tris
         if ((rc = grow(m->d_tris, m->tri_cap, (size_t)std::max<uint64_t>(total, 1) * 9))) return rc;
         A.tris = m->d_tris;
         A.tri_capacity = m->tri_cap / 9;
@@ -779,6 +811,11 @@ int mesh_run(gsdf_mesher *m) {
     cudaEventElapsedTime(&m->ms[4], m->ev[0], m->ev[4]);
     m->runs++;
     return 0;
+}
+
+int mesh_run(gsdf_mesher *m) {
+    int rc = mesh_run_begin(m);
+    return rc ? rc : mesh_run_end(m);
 }
 
 }  // namespace
@@ -825,6 +862,26 @@ int gsdf_mesh_rerun(gsdf_mesher *m) {
     return mesh_run(m);
 }
 
+int gsdf_mesh_rerun_begin(gsdf_mesher *m) {
+    if (!m) return fail(GSDF_EINVAL, "gsdf_mesh_rerun_begin: NULL mesher");
+    return mesh_run_begin(m);
+}
+
+int gsdf_mesh_rerun_end(gsdf_mesher *m) {
+    if (!m) return fail(GSDF_EINVAL, "gsdf_mesh_rerun_end: NULL mesher");
+    return mesh_run_end(m);
+}
+
+int64_t gsdf_mesh_read_prefix_async(gsdf_mesher *m, float *tri9, size_t ntris) {
+    if (!m || (!tri9 && ntris)) return fail(GSDF_EINVAL, "gsdf_mesh_read_prefix_async: NULL argument");
+    CU(cudaSetDevice(m->prog->device));
+    const uint64_t n = std::min<uint64_t>(ntris, m->tri_cap / 9);
+    if (n == 0) return 0;
+    CU(cudaStreamWaitEvent(m->copy_stream, m->ev[4], 0));  // after the emit of the render enqueued last
+    CU(cudaMemcpyAsync(tri9, m->d_tris, n * 9 * sizeof(float), cudaMemcpyDeviceToHost, m->copy_stream));
+    return (int64_t)n;
+}
+
 int gsdf_mesh_set_program(gsdf_mesher *m, gsdf_program *p) {
     if (!m || !p) return fail(GSDF_EINVAL, "gsdf_mesh_set_program: NULL argument");
     if (p->dim != 3) return fail(GSDF_EINVAL, "program is not 3D");
@@ -835,6 +892,7 @@ int gsdf_mesh_set_program(gsdf_mesher *m, gsdf_program *p) {
 
 int64_t gsdf_mesh_read(gsdf_mesher *m, float *tri9, size_t max_tris) {
     if (!m || !tri9) return fail(GSDF_EINVAL, "gsdf_mesh_read: NULL argument");
+    if (m->pending) { const int erc = mesh_run_end(m); if (erc) return erc; }
     if (max_tris < 5) return fail(GSDF_ESHORT, "short buffer");  // flatrenderer.go:187
     CU(cudaSetDevice(m->prog->device));
     const uint64_t left = m->ntri - m->read_pos;
@@ -847,6 +905,7 @@ int64_t gsdf_mesh_read(gsdf_mesher *m, float *tri9, size_t max_tris) {
 
 int64_t gsdf_mesh_read_async(gsdf_mesher *m, float *tri9, size_t max_tris) {
     if (!m || !tri9) return fail(GSDF_EINVAL, "gsdf_mesh_read_async: NULL argument");
+    if (m->pending) { const int erc = mesh_run_end(m); if (erc) return erc; }
     if (max_tris < 5) return fail(GSDF_ESHORT, "short buffer");
     CU(cudaSetDevice(m->prog->device));
     const uint64_t left = m->ntri - m->read_pos;
@@ -867,6 +926,7 @@ int gsdf_mesh_wait(gsdf_mesher *m) {
 
 int gsdf_mesh_device_triangles(gsdf_mesher *m, const float **d_tri9, uint64_t *ntri) {
     if (!m) return fail(GSDF_EINVAL, "NULL mesher");
+    if (m->pending) return fail(GSDF_EINVAL, "a render is in flight on this mesher: call gsdf_mesh_rerun_end first");
     if (d_tri9) *d_tri9 = m->d_tris;
     if (ntri) *ntri = m->ntri;
     return 0;
@@ -874,6 +934,7 @@ int gsdf_mesh_device_triangles(gsdf_mesher *m, const float **d_tri9, uint64_t *n
 
 int gsdf_mesh_stats(const gsdf_mesher *m, uint64_t *evals, uint64_t *pruned, uint64_t *tris) {
     if (!m) return fail(GSDF_EINVAL, "NULL mesher");
+    if (m->pending) return fail(GSDF_EINVAL, "a render is in flight on this mesher: call gsdf_mesh_rerun_end first");
     if (evals) *evals = m->evals;
     if (pruned) *pruned = m->pruned;
     if (tris) *tris = m->ntri;
@@ -882,6 +943,7 @@ int gsdf_mesh_stats(const gsdf_mesher *m, uint64_t *evals, uint64_t *pruned, uin
 
 int gsdf_mesh_cases(gsdf_mesher *m, uint8_t *cases, size_t nbytes) {
     if (!m || !cases) return fail(GSDF_EINVAL, "NULL argument");
+    if (m->pending) return fail(GSDF_EINVAL, "a render is in flight on this mesher: call gsdf_mesh_rerun_end first");
     if (!(m->flags & GSDF_MESH_KEEP_CASES)) return fail(GSDF_EINVAL, "mesher was not created with GSDF_MESH_KEEP_CASES");
     const size_t need = (size_t)m->D.nx * m->D.ny * (m->D.cz1 - m->D.cz0);
     if (nbytes != need) return fail(GSDF_ELEN, "cases buffer must be %zu bytes", need);
@@ -892,6 +954,7 @@ int gsdf_mesh_cases(gsdf_mesher *m, uint8_t *cases, size_t nbytes) {
 
 int gsdf_mesh_grid(gsdf_mesher *m, float *grid, size_t nfloats) {
     if (!m || !grid) return fail(GSDF_EINVAL, "NULL argument");
+    if (m->pending) return fail(GSDF_EINVAL, "a render is in flight on this mesher: call gsdf_mesh_rerun_end first");
     if (!(m->flags & GSDF_MESH_KEEP_GRID)) return fail(GSDF_EINVAL, "mesher was not created with GSDF_MESH_KEEP_GRID");
     const MeshDims &D = m->D;
     const size_t rows = (size_t)(D.ny + 1) * (D.cz1 - D.cz0 + 1);
@@ -903,6 +966,7 @@ int gsdf_mesh_grid(gsdf_mesher *m, float *grid, size_t nfloats) {
 
 int gsdf_mesh_timings(const gsdf_mesher *m, float ms[5]) {
     if (!m || !ms) return fail(GSDF_EINVAL, "NULL argument");
+    if (m->pending) return fail(GSDF_EINVAL, "a render is in flight on this mesher: call gsdf_mesh_rerun_end first");
     for (int i = 0; i < 5; i++) ms[i] = m->ms[i];
     return 0;
 }
@@ -1182,6 +1246,7 @@ static int64_t stl_from_device(const float *d_tri9, uint64_t n, uint8_t *&d_stl,
 
 int64_t gsdf_mesh_stl(gsdf_mesher *m, void *dst, size_t dst_bytes) {
     if (!m) return fail(GSDF_EINVAL, "NULL mesher");
+    if (m->pending) return fail(GSDF_EINVAL, "a render is in flight on this mesher: call gsdf_mesh_rerun_end first");
     CU(cudaSetDevice(m->prog->device));
     return stl_from_device(m->d_tris, m->ntri, m->d_stl, m->stl_cap, dst, dst_bytes, m->prog->stream);
 }

@@ -823,6 +823,22 @@ __global__ void __launch_bounds__(kThreads) k_mc_emit(MCArgs A) {
     }
 }
 
+// Zeroes the render's counters and (graph replays) the look-back scan state in one small kernel. cudaMemsetAsync nodes of
+// this size may be served by a copy engine, where they queue behind a large device->host triangle read in flight.
+__global__ void __launch_bounds__(256) k_clear_state(uint32_t *__restrict__ ctr, int nctr, unsigned long long *__restrict__ scanstate, uint32_t nstate) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (uint32_t)nctr) ctr[i] = 0u;
+    for (uint32_t k = i; k < nstate; k += gridDim.x * blockDim.x) scanstate[k] = 0ull;
+}
+
+// Publishes the render's device counters into mapped pinned host memory with plain stores. A cudaMemcpyAsync would queue
+// behind whatever the device->host copy engine is doing -- e.g. the 11 MB triangle read of the previous Z-slab -- and
+// stall the host's "how many triangles?" wait by the length of that copy; a store from an SM does not.
+__global__ void k_publish_counters(const uint32_t *__restrict__ d_ctr, volatile uint32_t *h_ctr, int n) {
+    if ((int)threadIdx.x < n) h_ctr[threadIdx.x] = d_ctr[threadIdx.x];
+    __threadfence_system();
+}
+
 // ---------------------------------------------------------------------------------------------- exclusive scan
 constexpr int kScanItems = 4;  // per thread; 1024 per block
 __global__ void __launch_bounds__(kThreads) k_scan_reduce(const uint32_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ blocksum) {

@@ -158,13 +158,45 @@ class SlabPipeline:
         return sum(p.NumTriangles() for p in self.parts)
 
     def RenderToHost(self, dst):
-        """Re-render every slab and stream its triangles into dst (float32 (n,3,3), ideally pinned). Returns n."""
+        """Re-render every slab and stream its triangles into dst (float32 (n,3,3), ideally pinned). Returns n.
+
+        Steady state is fully asynchronous: every slab's render is enqueued (gsdf_mesh_rerun_begin) followed by the copy
+        of as many triangles as that slab produced LAST time (gsdf_mesh_read_prefix_async), so slab i's copy runs under
+        slab i+1's kernels and the host never waits for a count in between. The counts are checked afterwards; if any
+        slab produced a different number (another tree was uploaded), the slabs are re-read at the right offsets."""
         flat = dst.reshape(-1)
+        cap = flat.size // 9
+        spec = getattr(self, "_last_counts", None)
+        if spec is not None and sum(spec) <= cap:
+            off = 0
+            for p, n in zip(self.parts, spec):
+                check(lib.gsdf_mesh_rerun_begin(p._h))
+                if n:
+                    got = check(lib.gsdf_mesh_read_prefix_async(p._h, C.c_void_p(flat[9 * off:].ctypes.data), n))
+                    if got != n:
+                        spec = None  # the slab's buffer shrank below the speculated count: fall through to the re-read
+                        break
+                off += n
+            for p in self.parts:
+                check(lib.gsdf_mesh_rerun_end(p._h))
+            for p in self.parts:
+                check(lib.gsdf_mesh_wait(p._h))
+            counts = [p.NumTriangles() for p in self.parts]
+            if spec is not None and counts == list(spec):
+                return sum(counts)
+        else:
+            for p in self.parts:
+                check(lib.gsdf_mesh_rerun(p._h))
+            counts = [p.NumTriangles() for p in self.parts]
+        # first call, or the speculation missed: read every slab at its true offset
+        self._last_counts = counts
+        if sum(counts) > cap:
+            raise GsdfError(_lib.ESHORT, "destination holds %d triangles, the render produced %d" % (cap, sum(counts)))
         got = 0
-        for p in self.parts:
-            check(lib.gsdf_mesh_rerun(p._h))
-            cap = flat.size // 9 - got
-            n = check(lib.gsdf_mesh_read_async(p._h, C.c_void_p(flat[9 * got:].ctypes.data), max(cap, 5))) if p.NumTriangles() else 0
+        for p, n in zip(self.parts, counts):
+            if n:
+                k = check(lib.gsdf_mesh_read_async(p._h, C.c_void_p(flat[9 * got:].ctypes.data), max(n, 5)))
+                assert k == n
             got += n
         for p in self.parts:
             check(lib.gsdf_mesh_wait(p._h))

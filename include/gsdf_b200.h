@@ -119,6 +119,19 @@ int64_t gsdf_mesh_read(gsdf_mesher *m, float *tri9, size_t max_tris);
  * Lets the device->host transfer of one slab overlap the kernels of the next one (separate meshers per slab). */
 int64_t gsdf_mesh_read_async(gsdf_mesher *m, float *tri9, size_t max_tris);
 int gsdf_mesh_wait(gsdf_mesher *m);
+/* Split form of gsdf_mesh_rerun for pipelines of several meshers (Z-slabs of one lattice, or successive renders):
+ * _begin enqueues the render and returns at once; _end waits for it, reads its counters and finishes the bookkeeping
+ * (re-emitting if the triangle buffer was too small). Between the two only gsdf_mesh_read_prefix_async and gsdf_mesh_wait
+ * may be called on the handle. */
+int gsdf_mesh_rerun_begin(gsdf_mesher *m);
+int gsdf_mesh_rerun_end(gsdf_mesher *m);
+/* Enqueues, behind the render enqueued last, the copy of the FIRST ntris triangles of the slab's buffer to tri9 (pinned
+ * host memory) without knowing how many the render will produce -- the caller speculates (normally: the count of the
+ * previous render) and checks gsdf_mesh_stats after gsdf_mesh_rerun_end; on a mismatch it re-reads with gsdf_mesh_read.
+ * This takes the "how many triangles?" round trip out of the critical path: the copy of slab i runs under the kernels of
+ * slab i+1 with no host synchronisation in between. Returns the number of triangles whose copy was enqueued (ntris clamped
+ * to the buffer's capacity); gsdf_mesh_wait completes it. */
+int64_t gsdf_mesh_read_prefix_async(gsdf_mesher *m, float *tri9, size_t ntris);
 /* Device pointer to the slab's triangle buffer (9 floats per triangle) and its count, for on-device consumers. */
 int gsdf_mesh_device_triangles(gsdf_mesher *m, const float **d_tri9, uint64_t *ntri);
 /* Evaluations() / Octree.TotalPruned() / len(triangles) (gsdfaux/gsdfaux.go:219-226). */

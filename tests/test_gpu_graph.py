@@ -90,3 +90,44 @@ def test_streaming_evaluate_tiles_and_tails(oracle, bld, scene):
     host = np.empty(6151, np.float32)
     sdf.Evaluate(pos_all[:6151], host)
     assert np.array_equal(host.view(np.uint32), want_all[:6151].view(np.uint32))
+
+
+def test_slab_pipeline_speculative_reads(bld):
+    """SlabPipeline.RenderToHost in steady state copies each slab's triangles with the PREVIOUS render's count, without a
+    host round trip per slab; the result must equal the single renderer's, and a tree change between two calls (counts
+    no longer match) must be detected and repaired."""
+    s1 = gsdf.scene(bld, "npt-flange")
+    s2 = bld.Difference(s1, bld.Translate(bld.NewSphere(9.0), 20.0, 0.0, -9.0))  # same bounds, different surface
+    sdf = gleval.NewCUDASDF3(s1)
+    res = np.float32(s1.Diagonal() / np.float32(150))
+    single = glrender.Octree(sdf, res)
+    want1 = single.AllTriangles()
+    for ns in (2, 3, 5):
+        P = glrender.SlabPipeline(sdf, res, nslabs=ns)
+        host = np.zeros((len(want1) + 4096, 3, 3), np.float32)
+        for it in range(4):  # call 0: synchronous; 1..: speculative
+            n = P.RenderToHost(host)
+            assert n == len(want1) and np.array_equal(host[:n].view(np.uint32), want1.view(np.uint32)), (ns, it)
+        sdf.Update(s2)
+        single.Rerun()
+        want2 = single.AllTriangles()
+        assert len(want2) != len(want1)
+        for it in range(3):  # first call after the change mis-speculates and re-reads
+            n = P.RenderToHost(host)
+            assert n == len(want2) and np.array_equal(host[:n].view(np.uint32), want2.view(np.uint32)), (ns, it)
+        sdf.Update(s1)
+        single.Rerun()
+        n = P.RenderToHost(host)
+        assert n == len(want1) and np.array_equal(host[:n].view(np.uint32), want1.view(np.uint32))
+        # a too small destination is an error, not a silent truncation
+        with pytest.raises(Exception):
+            P.RenderToHost(np.zeros((100, 3, 3), np.float32))
+        # accessors refuse to run while a render is in flight
+        from gsdf_b200._lib import lib, check
+        import gsdf_b200
+        check(lib.gsdf_mesh_rerun_begin(P.parts[0]._h))
+        with pytest.raises(gsdf_b200.GsdfError, match="in flight"):
+            P.parts[0].NumTriangles()
+        check(lib.gsdf_mesh_rerun_end(P.parts[0]._h))
+        assert P.parts[0].NumTriangles() > 0
+        P.Close()
