@@ -535,7 +535,6 @@ struct gsdf_mesher {
     unsigned flags = 0;
     MeshDims D{};
     float *d_grid = nullptr; size_t grid_cap = 0;
-    uint8_t *d_mask = nullptr; size_t mask_cap = 0;
     uint32_t *d_mbits = nullptr; size_t mbits_cap = 0;
     uint32_t *d_list = nullptr; size_t list_cap = 0;
     uint32_t *d_seg = nullptr; size_t seg_cap = 0;
@@ -634,7 +633,6 @@ int mesh_run_begin(gsdf_mesher *m) {
         m->scan_epoch = 1;
     }
     if (prune) {
-        if ((rc = grow(m->d_mask, m->mask_cap, (size_t)nblocks))) return rc;
         if ((rc = grow(m->d_mbits, m->mbits_cap, (size_t)D.nwx * D.nby * D.nbz))) return rc;
         if ((rc = grow(m->d_list, m->list_cap, (size_t)nquads))) return rc;
     }
@@ -669,11 +667,7 @@ int mesh_run_begin(gsdf_mesher *m) {
     auto enqueue = [&](bool stage_events, uint32_t epoch, bool clear_scan) -> int {
     int rc = 0;
     if (m->flags & GSDF_MESH_KEEP_GRID) CU(cudaMemsetAsync(m->d_grid, 0x7f, (size_t)D.pitch * (D.ny + 1) * nk * sizeof(float), st));
-    {
-        const uint32_t nstate = clear_scan ? (uint32_t)nscantiles : 0u;
-        k_clear_state<<<(unsigned)std::min<uint64_t>(std::max<uint64_t>((nstate + 255) / 256, 1), 64), 256, 0, st>>>(m->d_ctr, 8, m->d_scanstate, nstate);
-        CU(cudaGetLastError());
-    }
+    (void)clear_scan;  // counters and scan state were re-armed by the previous render's k_finish_render (or by the allocation)
     if (prune) {
         GenCenters gc;
         gc.ox = lat.origin[0]; gc.oy = lat.origin[1]; gc.oz = lat.origin[2]; gc.res = lat.res;
@@ -681,11 +675,9 @@ int mesh_run_begin(gsdf_mesher *m) {
         const float size = lat.res * 4.0f;          // ms3.Octree.CubeSize of a level-3 cube
         gc.half = size * 0.5f;
         gc.maxDist = size * (float)(1.73205080757 / 2);  // octreerenderer.go:182 with glrender.go:9
-        gc.mask = m->d_mask;
-        if ((rc = launch_eval<1>(p, gc, nblocks, st))) return rc;
+        gc.nwx = D.nwx; gc.bits = m->d_mbits; gc.kept = m->d_ctr + 4;
+        if ((rc = launch_eval<1>(p, gc, (uint64_t)D.nwx * 32u * D.nby * D.nbz, st))) return rc;
         const uint64_t ncrows = (uint64_t)(D.ny + 1) * nk;
-        k_mask_bits<<<grid_for((uint64_t)D.nby * D.nbz, kThreads / 32), kThreads, 0, st>>>(D, m->d_mask, m->d_mbits, m->d_ctr + 4);
-        CU(cudaGetLastError());
         k_compact_quads<<<grid_for(ncrows, kThreads / 32), kThreads, 0, st>>>(D, m->d_mbits, m->d_list, m->d_ctr + 0);
         CU(cudaGetLastError());
     }
@@ -722,8 +714,11 @@ int mesh_run_begin(gsdf_mesher *m) {
         k_mc_emit<<<mcgrid, kThreads, 0, st>>>(E);
         CU(cudaGetLastError());
     }
-    k_publish_counters<<<1, 32, 0, st>>>(m->d_ctr, m->h_ctr, 8);  // cudaMallocHost memory is device-mapped under UVA
-    CU(cudaGetLastError());
+    {   // publish the counters (cudaMallocHost memory is device-mapped under UVA) and re-arm the state for the next render
+        const uint32_t nstate = (uint32_t)nscantiles;
+        k_finish_render<<<(unsigned)std::min<uint64_t>(std::max<uint64_t>((nstate + 255) / 256, 1), 64), 256, 0, st>>>(m->d_ctr, m->h_ctr, 8, m->d_scanstate, nstate);
+        CU(cudaGetLastError());
+    }
     return rc;
     };  // enqueue
 
@@ -737,7 +732,7 @@ int mesh_run_begin(gsdf_mesher *m) {
         int ext, tma;
     } key;
     std::memset(&key, 0, sizeof key);
-    const void *kp[10] = {m->d_grid, m->d_mask, m->d_mbits, m->d_list, m->d_seg, m->d_seglist, m->d_scanstate, m->d_tris, m->d_cases, m->d_blocksum};
+    const void *kp[10] = {m->d_grid, nullptr, m->d_mbits, m->d_list, m->d_seg, m->d_seglist, m->d_scanstate, m->d_tris, m->d_cases, m->d_blocksum};
     std::memcpy(key.ptr, kp, sizeof kp);
     key.tri_cap = m->tri_cap; key.pv = p->pv; key.flags = m->flags; key.ext = p->needs_ext ? 1 : 0; key.tma = m->use_tma ? 1 : 0;
     const bool use_graph = m->allow_graph && !(m->flags & GSDF_MESH_STAGE_TIMING) && emitted && m->runs > 0 && !scan3;
@@ -791,9 +786,11 @@ int mesh_run_end(gsdf_mesher *m) {
         A.tris = m->d_tris;
         A.tri_capacity = m->tri_cap / 9;
         A.cases = nullptr;
-        CU(cudaMemsetAsync(m->d_ctr + 1, 0, sizeof(uint32_t), st));
+        // k_finish_render re-armed the counters already: give the emit its segment-list length back, clear again after
+        CU(cudaMemcpyAsync(m->d_ctr + 5, m->h_ctr + 5, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         k_mc_emit<<<mcgrid, kThreads, 0, st>>>(A);
         CU(cudaGetLastError());
+        CU(cudaMemsetAsync(m->d_ctr, 0, 8 * sizeof(uint32_t), st));
         CU(cudaEventRecord(m->ev[4], st));
         CU(cudaStreamSynchronize(st));
     }
@@ -847,6 +844,7 @@ int gsdf_mesh_begin(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, 
     D.nsx = (D.nx + 31) / 32;
     D.nwx = (D.nbx + 31) / 32;
     cudaError_t e = cudaMalloc((void **)&m->d_ctr, 8 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(m->d_ctr, 0, 8 * sizeof(uint32_t));  // every render leaves them zeroed for the next (k_finish_render)
     if (e == cudaSuccess) e = cudaMallocHost((void **)&m->h_ctr, 8 * sizeof(uint32_t));
     for (int i = 0; i < 5 && e == cudaSuccess; i++) e = cudaEventCreate(&m->ev[i]);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
@@ -974,7 +972,7 @@ int gsdf_mesh_timings(const gsdf_mesher *m, float ms[5]) {
 void gsdf_mesh_destroy(gsdf_mesher *m) {
     if (!m) return;
     if (m->prog) cudaSetDevice(m->prog->device);
-    cudaFree(m->d_grid); cudaFree(m->d_mask); cudaFree(m->d_mbits); cudaFree(m->d_list); cudaFree(m->d_seg); cudaFree(m->d_seglist); cudaFree(m->d_scanstate); cudaFree(m->d_blocksum);
+    cudaFree(m->d_grid); cudaFree(m->d_mbits); cudaFree(m->d_list); cudaFree(m->d_seg); cudaFree(m->d_seglist); cudaFree(m->d_scanstate); cudaFree(m->d_blocksum);
     cudaFree(m->d_tris); cudaFree(m->d_cases); cudaFree(m->d_stl); cudaFree(m->d_ctr);
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
     for (auto &e : m->ev) if (e) cudaEventDestroy(e);

@@ -340,21 +340,33 @@ struct GenGrid {
 };
 
 // Octree prune (glrender/octreerenderer.go:180-191, 240-284): evaluate the centre of every level-3 cube (4 cells
-// wide) of the slab; keep it iff |d| < size*sqrt3/2. One byte per block, x fastest. One cube per thread: the pass is
-// small and latency bound, so it wants threads, not per-thread ILP.
+// wide) of the slab; keep it iff |d| < size*sqrt3/2. One cube per thread: the pass is small and latency bound, so it
+// wants threads, not per-thread ILP. Work items are block rows padded to whole warps (32*nwx per row), so a warp's 32
+// verdicts are exactly one word of the prune bit rows: the sink writes the word with one ballot (no byte mask, no second
+// pass) and adds the kept count to the Octree.TotalPruned bookkeeping.
 struct GenCenters {
     static constexpr bool kTileSkip = false;
-    float ox, oy, oz, res; int nbx, nby, nbz, bz0; float half, maxDist; uint8_t *mask;
-    __device__ uint64_t work_items() const { return (uint64_t)nbx * nby * nbz; }
+    float ox, oy, oz, res; int nbx, nby, nbz, bz0, nwx; float half, maxDist; uint32_t *bits; uint32_t *kept;
+    __device__ uint64_t work_items() const { return (uint64_t)nwx * 32u * nby * nbz; }
     __device__ void load(uint64_t w, float (&x)[1], float (&y)[1], float (&z)[1]) const {
-        uint32_t t = (uint32_t)w;
-        const int bx = (int)(t % (uint32_t)nbx); t /= (uint32_t)nbx;
-        const int by = (int)(t % (uint32_t)nby), bz = (int)(t / (uint32_t)nby);
+        const uint32_t rowlen = (uint32_t)nwx * 32u;
+        const uint32_t row = (uint32_t)(w / rowlen);
+        const int bx = min((int)(w - (uint64_t)row * rowlen), nbx - 1);  // padding lanes repeat the row's last cube
+        const int by = (int)(row % (uint32_t)nby), bz = (int)(row / (uint32_t)nby);
         x[0] = (ox + (float)(4 * bx) * res) + half;
         y[0] = (oy + (float)(4 * by) * res) + half;
         z[0] = (oz + (float)(4 * (bz0 + bz)) * res) + half;
     }
-    __device__ void store(uint64_t w, const float (&d)[1]) const { mask[w] = fabsf(d[0]) >= maxDist ? 0 : 1; }
+    __device__ void store(uint64_t w, const float (&d)[1]) const {
+        const uint32_t rowlen = (uint32_t)nwx * 32u;
+        const uint32_t col = (uint32_t)(w % rowlen);
+        const bool keep = (int)col < nbx && !(fabsf(d[0]) >= maxDist);
+        const uint32_t word = __ballot_sync(__activemask(), keep);  // work items are multiples of 32: whole warps arrive here
+        if ((threadIdx.x & 31) == 0) {
+            bits[w >> 5] = word;  // word (w>>5) = row * nwx + col/32
+            if (word) atomicAdd(kept, (uint32_t)__popc(word));
+        }
+    }
 };
 
 // ImageRendererSDF2.Render positions (glrender/image.go:85-105). rgba != nullptr: the colour conversion is applied in
@@ -429,25 +441,6 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
         if (lane >= o) v += t;
     }
     return v;
-}
-
-// Byte mask -> bit rows: one warp per block row (by,bz); word w of a row holds blocks 32w..32w+31. Also counts the
-// kept blocks (Octree.TotalPruned bookkeeping).
-__global__ void __launch_bounds__(kThreads) k_mask_bits(MeshDims D, const uint8_t *__restrict__ mask, uint32_t *__restrict__ bits,
-                                                       uint32_t *__restrict__ kept) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t nrows = (uint32_t)D.nby * (uint32_t)D.nbz;
-    const uint32_t wpg = gridDim.x * (blockDim.x >> 5);
-    uint32_t cnt = 0;
-    for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += wpg) {
-        const uint8_t *row = mask + (size_t)r * D.nbx;
-        for (int w = 0; w < D.nwx; w++) {
-            const int b = 32 * w + lane;
-            const uint32_t word = __ballot_sync(0xffffffffu, b < D.nbx && row[b] != 0);
-            if (lane == 0) { bits[(size_t)r * D.nwx + w] = word; cnt += __popc(word); }
-        }
-    }
-    if (lane == 0 && cnt) atomicAdd(kept, cnt);
 }
 
 __device__ __forceinline__ uint32_t bit_at(const uint32_t *row, int b) { return b < 0 ? 0u : (row[b >> 5] >> (b & 31)) & 1u; }
@@ -823,19 +816,16 @@ __global__ void __launch_bounds__(kThreads) k_mc_emit(MCArgs A) {
     }
 }
 
-// Zeroes the render's counters and (graph replays) the look-back scan state in one small kernel. cudaMemsetAsync nodes of
-// this size may be served by a copy engine, where they queue behind a large device->host triangle read in flight.
-__global__ void __launch_bounds__(256) k_clear_state(uint32_t *__restrict__ ctr, int nctr, unsigned long long *__restrict__ scanstate, uint32_t nstate) {
+// Last node of a render: publishes the device counters into mapped pinned host memory with plain stores, then re-arms the
+// state for the NEXT render (counters, look-back scan state) so that a render needs no separate clear pass.
+// Why stores and not cudaMemcpyAsync / cudaMemsetAsync: small copies and memsets may be served by a copy engine, where they
+// queue behind a device->host triangle read in flight (the 11 MB read of the previous Z-slab stalled the host's "how many
+// triangles?" wait by 200 us, scripts/exp_pipe.py); a store from an SM does not.
+__global__ void __launch_bounds__(256) k_finish_render(uint32_t *__restrict__ d_ctr, volatile uint32_t *h_ctr, int nctr,
+                                                      unsigned long long *__restrict__ scanstate, uint32_t nstate) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < (uint32_t)nctr) ctr[i] = 0u;
+    if (i < (uint32_t)nctr) { h_ctr[i] = d_ctr[i]; d_ctr[i] = 0u; }
     for (uint32_t k = i; k < nstate; k += gridDim.x * blockDim.x) scanstate[k] = 0ull;
-}
-
-// Publishes the render's device counters into mapped pinned host memory with plain stores. A cudaMemcpyAsync would queue
-// behind whatever the device->host copy engine is doing -- e.g. the 11 MB triangle read of the previous Z-slab -- and
-// stall the host's "how many triangles?" wait by the length of that copy; a store from an SM does not.
-__global__ void k_publish_counters(const uint32_t *__restrict__ d_ctr, volatile uint32_t *h_ctr, int n) {
-    if ((int)threadIdx.x < n) h_ctr[threadIdx.x] = d_ctr[threadIdx.x];
     __threadfence_system();
 }
 
