@@ -240,6 +240,14 @@ def run_cuda(args, rank, local_rank, world):
     value = units / (dev_ms * 1e-3)
     tri_rate = allsum(ntri * args.steps) / (dev_ms * 1e-3)
 
+    if args.device_only:
+        if rank == 0:
+            emit_json({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "ms_per_step": dev_ms / args.steps,
+                       "note": "--device-only: profiling aid, not a bench line", "stage_ms": {k: sum(st[k] for st in stages) / len(stages) for k in stages[0]}})
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
     # ---------------- end to end through the public API with host buffers
     import ctypes as C
     host_tris = torch.empty((ntri + 8, 3, 3), dtype=torch.float32).pin_memory()
@@ -460,6 +468,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-only", action="store_true",
+                    help="profiling aid: run only the device-resident loops (stage-timed + graph replay) and print their summary, no e2e legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -718,9 +718,8 @@ __global__ void __launch_bounds__(256) k_mc_count_tma(const __grid_constant__ CU
                 if (act && !(fabsf(v0) > A.cubeDiag))
                     index = (v0 < 0.f ? 1 : 0) | (v1 < 0.f ? 2 : 0) | (v2 < 0.f ? 4 : 0) | (v3 < 0.f ? 8 : 0) | (v4 < 0.f ? 16 : 0) |
                             (v5 < 0.f ? 32 : 0) | (v6 < 0.f ? 64 : 0) | (v7 < 0.f ? 128 : 0);
-                n = s_ntri[index];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+                // most segments of a kept block hold no surface: one ballot decides, and the sum is one redux.sync
+                if (__ballot_sync(0xffffffffu, index != 0 && index != 255) != 0u) n = __reduce_add_sync(0xffffffffu, (uint32_t)s_ntri[index]);
             }
             if (A.cases && cx < D.nx) A.cases[(size_t)r * D.nx + cx] = (uint8_t)index;
             if (lane == sgm) mine = n;
