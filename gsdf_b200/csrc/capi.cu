@@ -664,10 +664,10 @@ int mesh_run_begin(gsdf_mesher *m) {
     static const bool scan3 = getenv("GSDF_SCAN3") != nullptr;  // A/B: the three-kernel scan
 
     // The launch sequence of one render. stage_events: record the per-stage timing events (eager path only).
-    auto enqueue = [&](bool stage_events, uint32_t epoch, bool clear_scan) -> int {
+    auto enqueue = [&](bool stage_events, uint32_t epoch) -> int {
     int rc = 0;
     if (m->flags & GSDF_MESH_KEEP_GRID) CU(cudaMemsetAsync(m->d_grid, 0x7f, (size_t)D.pitch * (D.ny + 1) * nk * sizeof(float), st));
-    (void)clear_scan;  // counters and scan state were re-armed by the previous render's k_finish_render (or by the allocation)
+    // counters and look-back scan state are already zero: re-armed by the previous render's k_finish_render (or by the allocation)
     if (prune) {
         GenCenters gc;
         gc.ox = lat.origin[0]; gc.oy = lat.origin[1]; gc.oz = lat.origin[2]; gc.res = lat.res;
@@ -741,7 +741,7 @@ int mesh_run_begin(gsdf_mesher *m) {
             if (m->gexec) { cudaGraphExecDestroy(m->gexec); m->gexec = nullptr; }
             cudaGraph_t g = nullptr;
             CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            const int erc = enqueue(false, 1u, true);
+            const int erc = enqueue(false, 1u);
             const cudaError_t ce = cudaStreamEndCapture(st, &g);
             if (erc) { if (g) cudaGraphDestroy(g); return erc; }
             if (ce != cudaSuccess) return fail(GSDF_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
@@ -752,10 +752,10 @@ int mesh_run_begin(gsdf_mesher *m) {
         }
         CU(cudaEventRecord(m->ev[0], st));
         CU(cudaGraphLaunch(m->gexec, st));
-        m->scan_epoch = 1;  // the graph clears the look-back state and scans with epoch 1
+        m->scan_epoch = 1;  // every render leaves the look-back state zeroed; the graph scans with epoch 1
     } else {
         CU(cudaEventRecord(m->ev[0], st));
-        if ((rc = enqueue(true, m->scan_epoch, false))) return rc;
+        if ((rc = enqueue(true, m->scan_epoch))) return rc;
     }
     CU(cudaEventRecord(m->ev[4], st));
     m->pending = true; m->pend_graph = use_graph; m->pend_emitted = emitted; m->pendA = A; m->pend_mcgrid = mcgrid;
