@@ -301,10 +301,14 @@ def run_cuda(args, rank, local_rank, world):
         _lib.check(_lib.lib.gsdf_program_update(sdf._h, blob, len(blob), auxp, aux.size))
         return pipe.RenderToHost(host_np)
 
-    e2e_sec = timed(e2e_pipe_step)
+    pipe_sec = timed(e2e_pipe_step)
     assert np.array_equal(host_np[:ntri].view(np.uint32), ref_tris.view(np.uint32)), "slab pipeline and single renderer disagree"
-    e2e_value = units / e2e_sec
     pipe.Close()
+    # Both are calls a user can make; the headline is the faster one on this box (with several ranks behind one PCIe
+    # uplink the pipelined copies contend and the plain round trip can win). Both are always reported.
+    e2e_sec = min(pipe_sec, single_sec)
+    e2e_is_pipe = pipe_sec <= single_sec
+    e2e_value = units / e2e_sec
 
     # Throughput form of the same loop (extra, not the headline): two renderers / two pinned buffers, the D2H copy of
     # step i (gsdf_mesh_read_async) overlaps the kernels of step i+1. Every step still uploads its tree and delivers
@@ -423,9 +427,11 @@ def run_cuda(args, rank, local_rank, world):
         "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_sec * 1e3 / args.steps, "triangles_per_sec": ntri * world * args.steps / e2e_sec,
-                "path": "per step: gsdf_program_update(upload flattened tree) -> glrender.SlabPipeline(%d Z-slabs).RenderToHost: gsdf_mesh_rerun_begin + gsdf_mesh_read_prefix_async per slab (copy of slab i under the kernels of slab i+1, copy sizes predicted from the previous step and verified), all triangles in pinned host memory when the step returns" % E2E_SLABS,
+                "path": "slab_pipeline" if e2e_is_pipe else "single_renderer",
+                "slab_pipeline": {"value": units / pipe_sec, "unit": UNIT, "ms_per_step": pipe_sec * 1e3 / args.steps,
+                                  "path": "per step: gsdf_program_update(upload flattened tree) -> glrender.SlabPipeline(%d Z-slabs).RenderToHost: gsdf_mesh_rerun_begin + gsdf_mesh_read_prefix_async per slab (copy of slab i under the kernels of slab i+1, copy sizes predicted from the previous step and verified), all triangles in pinned host memory when the step returns" % E2E_SLABS},
                 "single_renderer": {"value": units / single_sec, "unit": UNIT, "ms_per_step": single_sec * 1e3 / args.steps,
-                                    "path": "gsdf_program_update -> gsdf_mesh_rerun -> gsdf_mesh_read, one renderer, fully synchronous"},
+                                    "path": "per step: gsdf_program_update -> gsdf_mesh_rerun -> gsdf_mesh_read, one renderer, fully synchronous"},
                 "overlapped": {"value": units / ov_sec, "unit": UNIT, "ms_per_step": ov_sec * 1e3 / args.steps,
                                "note": "same per-step work, D2H of step i overlapped with the kernels of step i+1 (gsdf_mesh_read_async, two renderers)"}},
         "gpu_launches": KERNELS_PER_STEP * args.steps,
