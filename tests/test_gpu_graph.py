@@ -131,3 +131,51 @@ def test_slab_pipeline_speculative_reads(bld):
         check(lib.gsdf_mesh_rerun_end(P.parts[0]._h))
         assert P.parts[0].NumTriangles() > 0
         P.Close()
+
+
+def test_empty_and_tiny_meshes(oracle, bld):
+    """Edge cases: a lattice the surface never enters (zero triangles through every path), and lattices smaller than one
+    prune block / one TMA tile."""
+    import io
+    import gsdf_b200
+    # a sphere whose bounds were overloaded to a box far outside it: every distance is positive, no triangle anywhere
+    far = bld.OverloadShader3DBounds(bld.NewSphere(1.0), [10, 10, 10], [12, 12.5, 11])
+    sdf = gleval.NewCUDASDF3(far)
+    t = oracle.Tree.from_shader(far)
+    for cls in (glrender.Octree, glrender.FlatRenderer):
+        R = cls(sdf, np.float32(0.1))
+        for _ in range(3):
+            R.Rerun()
+        assert R.NumTriangles() == 0 and len(R.AllTriangles()) == 0
+        with pytest.raises(glrender.EOF):
+            R.ReadTriangles(np.empty((16, 3, 3), np.float32))
+        with pytest.raises(gsdf_b200.GsdfError):
+            R.STLBytes()  # WriteBinarySTL refuses an empty model (stl.go:16-18)
+    P = glrender.SlabPipeline(sdf, np.float32(0.1), nslabs=3)
+    host = np.zeros((64, 3, 3), np.float32)
+    for _ in range(3):
+        assert P.RenderToHost(host) == 0
+    d = glrender.DualContourRenderer()
+    d.Reset(sdf, np.float32(0.1), glrender.DualContourLeastSquares())
+    assert d.Stats()["triangles"] == 0 and len(d.RenderAll(None)) == 0
+    d.Rerun()
+    assert d.Stats()["cubes"] == 0
+    # tiny lattices: 1..3 cells per axis (one partial prune block, a partial TMA tile), reruns through the graph
+    s = bld.NewSphere(1.0)
+    sdf = gleval.NewCUDASDF3(s)
+    mn, mx = s.Bounds()
+    for res in (0.7, 1.1, 1.9):
+        lat = oracle.flat_lattice(mn, mx, np.float32(res))
+        grid, _ = oracle.flat_eval_grid(t := oracle.Tree.from_shader(s), lat)
+        want, _ = oracle.flat_march(lat, grid)
+        for cls in (glrender.FlatRenderer, glrender.Octree):
+            R = cls(sdf, np.float32(res))
+            for _ in range(3):
+                R.Rerun()
+            got = R.AllTriangles()
+            if cls is glrender.FlatRenderer:
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), res
+            else:
+                mask, _ = oracle.octree_prune_mask(t, lat)
+                wp, _ = oracle.flat_march(lat, grid, blockmask=mask)
+                assert np.array_equal(got.view(np.uint32), wp.view(np.uint32)), res
