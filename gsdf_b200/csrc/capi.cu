@@ -539,6 +539,7 @@ struct gsdf_mesher {
     uint32_t *d_list = nullptr; size_t list_cap = 0;
     uint32_t *d_seg = nullptr; size_t seg_cap = 0;
     uint32_t *d_seglist = nullptr; size_t seglist_cap = 0;
+    uint8_t *d_segcases = nullptr; size_t segcases_cap = 0;  // 32 case bytes per listed segment (TMA count pass -> emit)
     uint32_t *d_blocksum = nullptr; size_t blocksum_cap = 0;
     unsigned long long *d_scanstate = nullptr; size_t scanstate_cap = 0;
     uint32_t scan_epoch = 0;
@@ -620,6 +621,10 @@ int mesh_run_begin(gsdf_mesher *m) {
     if (nseg >= 0xffffffffull) return fail(GSDF_EINVAL, "slab too large: %llu cell segments (limit 2^32); use more Z-slabs", (unsigned long long)nseg);
     if ((rc = grow(m->d_seg, m->seg_cap, (size_t)nseg))) return rc;
     if ((rc = grow(m->d_seglist, m->seglist_cap, (size_t)nseg))) return rc;
+    static const bool pre_classified = getenv("GSDF_EMIT_RECLASSIFY") == nullptr;  // A/B switch: pass 2 classifies again
+    if (m->use_tma && pre_classified) {  // one byte per cell at most (every segment listed): never overflows
+        if ((rc = grow(m->d_segcases, m->segcases_cap, (size_t)nseg * 32))) return rc;
+    }
     const uint64_t nscanblocks = (nseg + kThreads * kScanItems - 1) / (kThreads * kScanItems);
     if ((rc = grow(m->d_blocksum, m->blocksum_cap, (size_t)nscanblocks))) return rc;
     const uint64_t nscantiles = (nseg + kScanTile - 1) / kScanTile;
@@ -655,6 +660,7 @@ int mesh_run_begin(gsdf_mesher *m) {
     A.overflow = m->d_ctr + 1;
     A.seg_list = m->d_seglist;
     A.seg_count = m->d_ctr + 5;
+    A.seg_cases = (m->use_tma && pre_classified) ? m->d_segcases : nullptr;
     const unsigned mcgrid = grid_for(nrows * (uint64_t)((D.nsx + 3) / 4), kThreads / 32, 16);
     if (m->use_tma && m->tmap_grid != m->d_grid) {  // (re)describe the lattice buffer: pitch x (ny+1) x nk floats
         if ((rc = make_grid_tensor_map(&m->tmap, m->d_grid, D.pitch, D.ny + 1, nk))) return rc;
@@ -732,7 +738,7 @@ int mesh_run_begin(gsdf_mesher *m) {
         int ext, tma;
     } key;
     std::memset(&key, 0, sizeof key);
-    const void *kp[10] = {m->d_grid, nullptr, m->d_mbits, m->d_list, m->d_seg, m->d_seglist, m->d_scanstate, m->d_tris, m->d_cases, m->d_blocksum};
+    const void *kp[10] = {m->d_grid, nullptr, m->d_mbits, m->d_list, m->d_seg, m->d_seglist, m->d_scanstate, m->d_tris, m->d_cases, m->d_segcases};
     std::memcpy(key.ptr, kp, sizeof kp);
     key.tri_cap = m->tri_cap; key.pv = p->pv; key.flags = m->flags; key.ext = p->needs_ext ? 1 : 0; key.tma = m->use_tma ? 1 : 0;
     const bool use_graph = m->allow_graph && !(m->flags & GSDF_MESH_STAGE_TIMING) && emitted && m->runs > 0 && !scan3;
@@ -972,7 +978,7 @@ int gsdf_mesh_timings(const gsdf_mesher *m, float ms[5]) {
 void gsdf_mesh_destroy(gsdf_mesher *m) {
     if (!m) return;
     if (m->prog) cudaSetDevice(m->prog->device);
-    cudaFree(m->d_grid); cudaFree(m->d_mbits); cudaFree(m->d_list); cudaFree(m->d_seg); cudaFree(m->d_seglist); cudaFree(m->d_scanstate); cudaFree(m->d_blocksum);
+    cudaFree(m->d_grid); cudaFree(m->d_mbits); cudaFree(m->d_list); cudaFree(m->d_seg); cudaFree(m->d_seglist); cudaFree(m->d_segcases); cudaFree(m->d_scanstate); cudaFree(m->d_blocksum);
     cudaFree(m->d_tris); cudaFree(m->d_cases); cudaFree(m->d_stl); cudaFree(m->d_ctr);
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
     for (auto &e : m->ev) if (e) cudaEventDestroy(e);

@@ -529,6 +529,8 @@ struct MCArgs {
     uint32_t *overflow;     // set to 1 if a triangle did not fit
     uint32_t *seg_list;     // compact list of non-empty 32-cell segments (pass 1 -> pass 2)
     uint32_t *seg_count;
+    uint8_t *seg_cases;     // optional: the 32 cube-case indices of seg_list[i] at [32*i, 32*i+32) (k_mc_count_tma -> k_mc_emit),
+                            // so that pass 2 does not classify again
 };
 
 
@@ -704,6 +706,7 @@ __global__ void __launch_bounds__(256) k_mc_count_tma(const __grid_constant__ CU
         const int nsg = cy < D.ny ? min(4, D.nsx - (int)tx * 4) : 0;
         const uint32_t word = ((cy >> 2) == (cy0 >> 2)) ? word0 : word1;
         uint32_t mine = 0u;
+        uint32_t cases4 = 0u;  // this lane's cube-case index in each of the warp's four segments, one byte each
 #pragma unroll
         for (int sgm = 0; sgm < 4; sgm++) {
             if (sgm >= nsg) break;
@@ -723,6 +726,7 @@ __global__ void __launch_bounds__(256) k_mc_count_tma(const __grid_constant__ CU
             }
             if (A.cases && cx < D.nx) A.cases[(size_t)r * D.nx + cx] = (uint8_t)index;
             if (lane == sgm) mine = n;
+            cases4 |= (uint32_t)index << (8 * sgm);
         }
         if (lane < nsg) A.segcount[s0 + lane] = mine;
         const unsigned nz = __ballot_sync(0xffffffffu, lane < nsg && mine != 0u);
@@ -734,7 +738,13 @@ __global__ void __launch_bounds__(256) k_mc_count_tma(const __grid_constant__ CU
             s_base = tot ? atomicAdd(A.seg_count, tot) : 0u;
         }
         __syncthreads();
-        if ((nz >> lane) & 1u) A.seg_list[s_base + s_cnt[warp] + __popc(nz & ((1u << lane) - 1u))] = s0 + lane;
+        const uint32_t lpos = s_base + s_cnt[warp];
+        if ((nz >> lane) & 1u) A.seg_list[lpos + __popc(nz & ((1u << lane) - 1u))] = s0 + lane;
+        if (A.seg_cases && nz) {  // warp-uniform: the case bytes of every non-empty segment, 32 coalesced bytes each
+#pragma unroll
+            for (int sgm = 0; sgm < 4; sgm++)
+                if ((nz >> sgm) & 1u) A.seg_cases[(size_t)(lpos + __popc(nz & ((1u << sgm) - 1u))) * 32u + lane] = (uint8_t)(cases4 >> (8 * sgm));
+        }
         __syncthreads();
     }
 }
@@ -766,17 +776,23 @@ __global__ void __launch_bounds__(kThreads) k_mc_emit(MCArgs A) {
         const float *g00 = A.grid + (size_t)czl * sz + (size_t)cy * sy;
         const float *g01 = g00 + sy, *g10 = g00 + sz, *g11 = g10 + sy;
         const int cx = x0 + lane;
-        bool act = cx < D.nx;
-        if (A.mbits) act = act && bit_at(A.mbits + ((size_t)((cz >> 2) - D.bz0) * D.nby + (cy >> 2)) * D.nwx, min(cx, D.nx - 1) >> 2) != 0u;
-        float v[8];
-        const int index = mc_classify_segment(g00, g01, g10, g11, cx, D.nx, act, A.cubeDiag, v);
+        const bool precl = A.seg_cases != nullptr;  // launch-uniform: pass 1 left the case indices, corner values come from the lattice
+        int index;
+        if (precl) {
+            index = (int)A.seg_cases[(size_t)t * 32u + lane];
+        } else {
+            bool act = cx < D.nx;
+            if (A.mbits) act = act && bit_at(A.mbits + ((size_t)((cz >> 2) - D.bz0) * D.nby + (cy >> 2)) * D.nwx, min(cx, D.nx - 1) >> 2) != 0u;
+            float v[8];
+            index = mc_classify_segment(g00, g01, g10, g11, cx, D.nx, act, A.cubeDiag, v);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; i++) vw[i * 32 + lane] = v[i];
+            __syncwarp();
+        }
         const uint32_t n = s_ntri[index];
         const uint32_t incl = warp_incl_scan(n);
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; i++) vw[i * 32 + lane] = v[i];
-        __syncwarp();
         const uint64_t obase = (uint64_t)A.segcount[s];
         // corner positions, flatrenderer.go:235-247
         const float rr = A.res;
@@ -808,7 +824,14 @@ __global__ void __launch_bounds__(kThreads) k_mc_emit(MCArgs A) {
             const int ca = (int)((0x321076543210ull >> (4 * e)) & 0xf), cb = (int)((0x765447650321ull >> (4 * e)) & 0xf);
             const float3 pa = make_float3((((ca + 1) >> 1) & 1) ? px1 : px0, ((ca >> 1) & 1) ? py1 : py0, (ca >> 2) ? pz1 : pz0);
             const float3 pb = make_float3((((cb + 1) >> 1) & 1) ? px1 : px0, ((cb >> 1) & 1) ? py1 : py0, (cb >> 2) ? pz1 : pz0);
-            const float3 q = mc_interp(pa, pb, vw[ca * 32 + owner], vw[cb * 32 + owner]);
+            float va, vb;
+            if (precl) {  // corner c of cell (x0+owner): x bit ((c+1)>>1)&1, y bit (c>>1)&1, z bit c>>2 (flatrenderer.go:222-233)
+                va = __ldg(g00 + (size_t)(ca >> 2) * sz + (size_t)((ca >> 1) & 1) * sy + (x0 + owner + (((ca + 1) >> 1) & 1)));
+                vb = __ldg(g00 + (size_t)(cb >> 2) * sz + (size_t)((cb >> 1) & 1) * sy + (x0 + owner + (((cb + 1) >> 1) & 1)));
+            } else {
+                va = vw[ca * 32 + owner]; vb = vw[cb * 32 + owner];
+            }
+            const float3 q = mc_interp(pa, pb, va, vb);
             float *dst = A.tris + 9 * o + 3 * j;
             dst[0] = q.x; dst[1] = q.y; dst[2] = q.z;
         }
