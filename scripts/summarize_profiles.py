@@ -35,7 +35,12 @@ KEYS = [
 
 
 def raw(rep):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """Rows of the raw page: from a .ncu-rep (via `ncu -i`) or from a CSV exported on the GPU box (*.raw.csv; reports embed
+    the whole module and weigh ~17 MB each, more than gpurun merges back, so only the dominant kernel's report travels)."""
+    if rep.endswith(".csv"):
+        txt = open(rep).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
     return [dict(zip(hdr, r)) for r in rows[2:]], dict(zip(hdr, units))
@@ -47,7 +52,7 @@ def main():
     traffic = {}
     lines = []
     for f in sorted(os.listdir(gout)):
-        if not f.endswith(".ncu-rep"):
+        if not (f.endswith(".ncu-rep") or f.endswith(".raw.csv")):
             continue
         rows, units = raw(os.path.join(gout, f))
         for d in rows:
