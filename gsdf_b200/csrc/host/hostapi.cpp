@@ -36,6 +36,10 @@ bool make_threader(gsdfh_builder *b, int kind, float p0, float p1, int ext, thre
         if (!threads::Threader::NPTFromNominal(p0, t)) { b->err = "nominal measurement not found"; return false; }  // npt.go:73
         return true;
     }
+    if (kind == 2) { t = threads::Threader::UTS(p0, p1, ext != 0); return true; }                           // UTS{D, TPI, Ext}
+    if (kind == 3) { t = threads::Threader::Basic(threads::Kind::Acme, p0, p1); return true; }               // Acme{D, P}
+    if (kind == 4) { t = threads::Threader::Basic(threads::Kind::ANSIButtress, p0, p1); return true; }       // ANSIButtress{D, P}
+    if (kind == 5) { t = threads::Threader::Basic(threads::Kind::PlasticButtress, p0, p1); return true; }    // PlasticButtress{D, P}
     b->err = "unknown thread kind";
     return false;
 }
@@ -172,6 +176,7 @@ int32_t gsdfh_scene(gsdfh_builder *b, const char *name, float param) {
     if (n == "npt-flange") id = scenes::NptFlange(b->b, err);
     else if (n == "bolt") id = scenes::Bolt(b->b, err);
     else if (n == "knurled-cylinder") id = scenes::KnurledCylinder(b->b, param > 0 ? param : 20.f, err);
+    else if (n == "fibonacci-showerhead") id = scenes::FibonacciShowerhead(b->b, err);
     else return failb(b, "unknown scene: " + n);
     if (id < 0) b->err = err;
     return id;

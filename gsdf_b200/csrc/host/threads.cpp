@@ -35,6 +35,18 @@ Threader Threader::ISO(float D, float P, bool ext) {
     return t;
 }
 
+Threader Threader::Basic(Kind kind, float D, float P) {
+    Threader t;
+    t.kind = kind; t.D = D; t.P = P;
+    return t;
+}
+
+Threader Threader::UTS(float D, float TPI, bool ext) {
+    Threader t;
+    t.kind = Kind::UTS; t.D = D; t.TPI = TPI; t.Ext = ext;
+    return t;
+}
+
 bool Threader::NPTFromNominal(float nominal, Threader &out) {
     struct Spec { float N, D, tpi, ftof; };
     static const Spec tbl[] = {  // npt.go:44-57
@@ -58,7 +70,7 @@ bool Threader::NPTFromNominal(float nominal, Threader &out) {
 Parameters Threader::ThreadParams() const {
     Parameters p;
     float d = D, pitch = P;
-    if (kind == Kind::NPT) pitch = 1.0f / TPI;            // npt.go:24
+    if (kind == Kind::NPT || kind == Kind::UTS) pitch = 1.0f / TPI;  // npt.go:24, uts.go:20
     if (kind == Kind::Knurl) { d = KRadius * 2; pitch = KPitch; }  // knurl.go:46
     float radius = d / 2;                                 // threads.go:213-223 (basic.ThreadParams)
     p.Name = "basic"; p.Radius = radius; p.Pitch = pitch; p.Starts = 1; p.Taper = 0; p.HexF2F = metricf2f(radius);
@@ -79,8 +91,45 @@ NodeId Threader::Thread(Builder &bld, std::string &err) const {
         poly.addXY(0, KRadius + KHeight);
         poly.addXY(-KPitch / 2, KRadius);
         poly.addXY(-KPitch / 2, 0);
-    } else {  // iso.go:37-77 (NPT: ISO{D, 1/TPI} with Ext=false, npt.go:34-36)
-        float d = D, p = (kind == Kind::NPT) ? 1.0f / TPI : P;
+    } else if (kind == Kind::Acme) {  // acme.go:22-45
+        float radius = D / 2;
+        float h = radius - 0.5f * P;
+        float theta = (float)(29.0 / 2.0) * (float)m32::kPi / 180.0f;
+        float delta = 0.25f * P * m32::tan(theta);
+        float xOfs0 = 0.25f * P - delta, xOfs1 = 0.25f * P + delta;
+        poly.addXY(radius, 0);
+        poly.addXY(radius, h);
+        poly.addXY(xOfs1, h);
+        poly.addXY(xOfs0, radius);
+        poly.addXY(-xOfs0, radius);
+        poly.addXY(-xOfs1, h);
+        poly.addXY(-radius, h);
+        poly.addXY(-radius, 0);
+    } else if (kind == Kind::ANSIButtress || kind == Kind::PlasticButtress) {
+        // ansibuttress.go:22-46 (tangents through math32.Tan) / plasticbuttress.go:26-56 (tangents as constants, more rounding)
+        const bool plastic = kind == Kind::PlasticButtress;
+        float radius = D / 2, p = P;
+        float t0 = plastic ? 1.0f : m32::tan(45.0f * (float)m32::kPi / 180);
+        float t1 = plastic ? (float)0.1227845609029046 : m32::tan(7.0f * (float)m32::kPi / 180);
+        float sum = plastic ? (float)(1.0 + 0.1227845609029046) : t0 + t1;  // untyped constant sum is exact in Go
+        float h0 = p / sum;
+        float h1 = ((float)(0.6 / 2.0) * p) + (0.5f * h0);
+        float hp = p / 2.0f;
+        poly.addXY(p, 0);
+        poly.addXY(p, radius);
+        if (plastic) {
+            poly.addXY(hp - ((h0 - h1) * t1), radius).smooth(0.05f * p, 5);
+            poly.addXY(t0 * h0 - hp, radius - h1).smooth(0.15f * p, 5);
+            poly.addXY((h0 - h1) * t0 - hp, radius).smooth(0.15f * p, 5);
+        } else {
+            poly.addXY(hp - ((h0 - h1) * t1), radius);
+            poly.addXY(t0 * h0 - hp, radius - h1).smooth(0.0714f * p, 5);
+            poly.addXY((h0 - h1) * t0 - hp, radius);
+        }
+        poly.addXY(-p, radius);
+        poly.addXY(-p, 0);
+    } else {  // iso.go:37-77 (NPT: ISO{D, 1/TPI} with Ext=false, npt.go:34-36; UTS: ISO{D, 1/TPI, Ext}, uts.go:25-27)
+        float d = D, p = (kind == Kind::NPT || kind == Kind::UTS) ? 1.0f / TPI : P;
         bool ext = (kind == Kind::NPT) ? false : Ext;
         float radius = d / 2;
         const double tanTheta = kSind30 / kCosd30;
@@ -268,6 +317,35 @@ NodeId KnurledCylinder(Builder &bld, float diameter, std::string &err) {  // knu
     obj = bld.SmoothDifference(sk, obj, bld.Translate(vent, 0, 0, length / 2));
     err = bld.Err();
     return obj;
+}
+
+// examples/fibonacci-showerhead/showerhead.go:31-92 (the PNG side output of :55-56 is not part of the shape)
+NodeId FibonacciShowerhead(Builder &bld, std::string &err) {
+    const double threadExtDiameter = 65., threadedLength = 5., threadTurns = 3., threadPitch = threadedLength / threadTurns;
+    const double showerheadBaseThick = 2.5, showerheadWall = 4., threadheight = 5.;
+    const threads::Threader showerThread = threads::Threader::Basic(threads::Kind::PlasticButtress, (float)threadExtDiameter, (float)threadPitch);
+    NodeId knurled = threads::KnurledHead(bld, (float)(threadExtDiameter / 2 + showerheadWall), (float)threadheight, 1, err);
+    if (knurled < 0) return -1;
+    NodeId thr = threads::Screw(bld, (float)(threadheight + .5), showerThread, err);
+    if (thr < 0) return -1;
+    NodeId object = bld.Difference(knurled, thr);
+    NodeId base = bld.NewCylinder((float)(threadExtDiameter / 2 + showerheadWall), (float)showerheadBaseThick, 0);
+    base = bld.Translate(base, 0, 0, (float)-(threadedLength / 2 + showerheadBaseThick / 2 - 1));
+    NodeId hole = bld.NewCylinder(0.8f, (float)(showerheadBaseThick * 10), 0);
+    NodeId holes = hole;
+    for (int i = 0; i < 130; i++) {  // fibonacci(i), showerhead.go:137-146
+        const float nf = (float)i;
+        const float a = nf * 137.3f / 360 * (float)m32::kPi;
+        const float r = 2.6f * m32::sqrt(nf);
+        float sa, ca;
+        m32::sincos(a, sa, ca);
+        holes = bld.Union({holes, bld.Translate(hole, r * ca, r * sa, 0)});
+    }
+    base = bld.Difference(base, holes);
+    object = bld.Union({object, base});
+    const std::string berr = bld.Err();
+    if (!berr.empty()) { err = berr; return -1; }
+    return object;
 }
 
 }  // namespace scenes

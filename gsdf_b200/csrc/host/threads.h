@@ -19,7 +19,7 @@ struct Parameters {
     float HexHeight() const;
 };
 
-enum class Kind { ISO, NPT, Knurl };
+enum class Kind { ISO, NPT, Knurl, UTS, Acme, ANSIButtress, PlasticButtress };  // uts.go, acme.go, ansibuttress.go, plasticbuttress.go
 // One value type covers the reference's Threader implementations used by the benchmark scenes.
 struct Threader {
     Kind kind = Kind::ISO;
@@ -32,6 +32,8 @@ struct Threader {
     int kstarts = 0;
 
     static Threader ISO(float D, float P, bool ext);
+    static Threader Basic(Kind kind, float D, float P);       // Acme / ANSIButtress / PlasticButtress {D, P}
+    static Threader UTS(float D, float TPI, bool ext);        // uts.go:8-15
     static bool NPTFromNominal(float nominal, Threader &out);  // npt.go:63-74
     Parameters ThreadParams() const;                            // iso.go:33, npt.go:23, knurl.go:45
     NodeId Thread(Builder &bld, std::string &err) const;        // iso.go:37, npt.go:34, knurl.go:28
@@ -54,6 +56,7 @@ namespace scenes {
 NodeId NptFlange(Builder &bld, std::string &err);                 // examples/npt-flange/flange.go:23-59
 NodeId Bolt(Builder &bld, std::string &err);                      // examples/bolt/main.go:26-41
 NodeId KnurledCylinder(Builder &bld, float diameter, std::string &err);  // examples/knurled-cylinder/knurled-cyl.go:57-107
+NodeId FibonacciShowerhead(Builder &bld, std::string &err);       // examples/fibonacci-showerhead/showerhead.go:31-92
 }  // namespace scenes
 
 }  // namespace gsdfhost

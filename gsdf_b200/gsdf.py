@@ -247,9 +247,35 @@ class NPT:
         self.p0, self.p1, self.ext = float(nominal), 0.0, False
 
 
+class UTS:
+    """threads.UTS{D, TPI, Ext} (forge/threads/uts.go:8-15)."""
+    kind = 2
+
+    def __init__(self, D, TPI, Ext=False):
+        self.p0, self.p1, self.ext = float(D), float(TPI), bool(Ext)
+
+
+class Acme:
+    """threads.Acme{D, P} (forge/threads/acme.go:10-15)."""
+    kind = 3
+
+    def __init__(self, D, P):
+        self.p0, self.p1, self.ext = float(D), float(P), False
+
+
+class ANSIButtress(Acme):
+    """threads.ANSIButtress{D, P} (forge/threads/ansibuttress.go:10-15)."""
+    kind = 4
+
+
+class PlasticButtress(Acme):
+    """threads.PlasticButtress{D, P} (forge/threads/plasticbuttress.go:9-14)."""
+    kind = 5
+
+
 class threads:
     """Namespace mirroring package forge/threads."""
-    ISO, NPT = ISO, NPT
+    ISO, NPT, UTS, Acme, ANSIButtress, PlasticButtress = ISO, NPT, UTS, Acme, ANSIButtress, PlasticButtress
     NutCircular, NutHex, NutKnurl = NutCircular, NutHex, NutKnurl
 
     @staticmethod
@@ -269,5 +295,6 @@ class threads:
 
 def scene(bld, name, param=0.0):
     """The example programs' scene() functions: 'npt-flange' (examples/npt-flange/flange.go:23), 'bolt'
-    (examples/bolt/main.go:26), 'knurled-cylinder' (examples/knurled-cylinder/knurled-cyl.go:57, param = -d)."""
+    (examples/bolt/main.go:26), 'knurled-cylinder' (examples/knurled-cylinder/knurled-cyl.go:57, param = -d),
+    'fibonacci-showerhead' (examples/fibonacci-showerhead/showerhead.go:31)."""
     return bld._wrap(lib.gsdfh_scene(bld._h, name.encode(), float(param)))

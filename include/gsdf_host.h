@@ -44,14 +44,17 @@ int gsdfh_is2d(gsdfh_builder *b, int32_t id);
 int gsdfh_bounds3(gsdfh_builder *b, int32_t id, float out[6]);
 int gsdfh_bounds2(gsdfh_builder *b, int32_t id, float out[4]);
 
-/* forge/threads front-ends. thread_kind: 0 ISO{D,P,Ext} (iso.go:20), 1 NPT from nominal size in p0 (npt.go:63). */
+/* forge/threads front-ends. thread_kind: 0 ISO{D,P,Ext} (iso.go:20), 1 NPT from nominal size in p0 (npt.go:63),
+ * 2 UTS{D,TPI,Ext} (uts.go:8), 3 Acme{D,P} (acme.go:10), 4 ANSIButtress{D,P} (ansibuttress.go:10), 5 PlasticButtress{D,P}
+ * (plasticbuttress.go:9). */
 int32_t gsdfh_thread_profile(gsdfh_builder *b, int thread_kind, float p0, float p1, int ext);                 /* Threader.Thread */
 int32_t gsdfh_screw(gsdfh_builder *b, float length, int thread_kind, float p0, float p1, int ext);            /* threads.Screw */
 int32_t gsdfh_nut(gsdfh_builder *b, int thread_kind, float p0, float p1, int ext, int style, float tol);      /* threads.Nut */
 int32_t gsdfh_bolt(gsdfh_builder *b, int thread_kind, float p0, float p1, int ext, int style, float tol, float total_len,
                    float shank_len);                                                                          /* threads.Bolt */
 int32_t gsdfh_hexhead(gsdfh_builder *b, float radius, float height, int round_neg, int round_pos);            /* threads.HexHead */
-/* The example scenes BASELINE.json names: "npt-flange", "bolt", "knurled-cylinder" (param = diameter, 0 -> 20). */
+/* The example scenes BASELINE.json names: "npt-flange", "bolt", "knurled-cylinder" (param = diameter, 0 -> 20); plus
+ * "fibonacci-showerhead" (the reference README's second timed example, a known-answer test for the oracle). */
 int32_t gsdfh_scene(gsdfh_builder *b, const char *name, float param);
 
 /* forge/textsdf (font.go): TrueType font -> polygon SDF tree. The font bytes are supplied by the caller (the reference

@@ -274,6 +274,26 @@ def test_flange_resdiv400_readme_counts(bld):
     assert np.array_equal(bits(f.AllTriangles()), bits(o.AllTriangles()))
 
 
+def test_showerhead_resdiv350_readme_counts(oracle, bld):
+    """README.md:152,165: fibonacci-showerhead at resdiv 350 -> 309,872 triangles from both renderers, 1,512,024 lattice
+    corners; a 675-instruction program (131-operand union). Bit-identical to the oracle."""
+    s = gsdf.scene(bld, "fibonacci-showerhead")
+    sdf = gleval.NewCUDASDF3(s)
+    res = np.float32(s.Diagonal() / np.float32(350))
+    f = glrender.NewFlatRenderer(sdf, res)
+    assert f.NumTriangles() == 309872 and f.Evaluations() == 1512024
+    o = glrender.NewOctreeRenderer(sdf, res, 32768)
+    assert o.NumTriangles() == 309849  # level-3 prune rule on a non-Lipschitz field: see tests/test_oracle_kat.py
+    t = oracle.Tree.from_shader(s)
+    lat = oracle.flat_lattice(*s.Bounds(), res)
+    grid, _ = oracle.flat_eval_grid(t, lat, nthreads=os.cpu_count() or 1)
+    want, _ = oracle.flat_march(lat, grid)
+    assert np.array_equal(bits(f.AllTriangles()), bits(want))
+    mask, _ = oracle.octree_prune_mask(t, lat)
+    wantp, _ = oracle.flat_march(lat, grid, blockmask=mask)
+    assert np.array_equal(bits(o.AllTriangles()), bits(wantp))
+
+
 def test_golden_mesh_fixtures(bld):
     g = np.load(os.path.join(GOLD, "meshes.npz"))
     for name in ["sphere", "npt-flange", "bolt", "knurled-cylinder"]:
