@@ -1,0 +1,158 @@
+//go:build cgo && cuda
+
+package glrender
+
+/*
+#cgo LDFLAGS: -lgsdfb200
+#include "gsdf_b200.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"image"
+	"io"
+	"unsafe"
+
+	"github.com/soypat/geometry/ms3"
+	"github.com/soypat/gsdf/gleval"
+)
+
+func cudaErr() error { return errors.New(C.GoString(C.gsdf_last_error())) }
+
+// MesherCUDA implements Renderer (glrender.go:11-13): octree-pruned or dense marching cubes on the device.
+type MesherCUDA struct{ h *C.gsdf_mesher }
+
+// NewCUDARenderer mirrors NewOctreeRenderer(s, res, evalBufferSize) (octreerenderer.go:45); prune=false gives
+// FlatRenderer semantics (flatrenderer.go:37). cz0, cz1 select a Z-slab of cell layers (0, 0 = the whole lattice): one
+// MesherCUDA per GPU / per pipeline stage, triangles appended in slab order. The slab is meshed inside this call.
+func NewCUDARenderer(s *gleval.SDF3CUDA, res float32, prune bool, cz0, cz1 int) (*MesherCUDA, error) {
+	bb := s.Bounds()
+	var lat C.gsdf_lattice
+	if rc := C.gsdf_lattice_from_bounds((*C.float)(unsafe.Pointer(&bb.Min)), (*C.float)(unsafe.Pointer(&bb.Max)), C.float(res), &lat); rc != 0 {
+		return nil, cudaErr() // "resolution not fine enough for marching cubes" (flatrenderer.go:53)
+	}
+	if cz0 == 0 && cz1 == 0 {
+		cz1 = int(lat.n[2])
+	}
+	flags := C.uint(0)
+	if prune {
+		flags = C.GSDF_MESH_PRUNE
+	}
+	var h *C.gsdf_mesher
+	if rc := C.gsdf_mesh_begin((*C.gsdf_program)(s.Handle()), &lat, C.int(cz0), C.int(cz1), flags, &h); rc != 0 {
+		return nil, cudaErr()
+	}
+	return &MesherCUDA{h: h}, nil
+}
+
+// ReadTriangles implements Renderer. ms3.Triangle = [3]ms3.Vec = 9 float32.
+func (m *MesherCUDA) ReadTriangles(dst []ms3.Triangle, userData any) (int, error) {
+	if len(dst) < 5 {
+		return 0, io.ErrShortBuffer // octreerenderer.go:132, flatrenderer.go:187
+	}
+	n := C.gsdf_mesh_read(m.h, (*C.float)(unsafe.Pointer(&dst[0])), C.size_t(len(dst)))
+	switch {
+	case n < 0:
+		return 0, cudaErr()
+	case n == 0:
+		return 0, io.EOF // octreerenderer.go:156, flatrenderer.go:206
+	}
+	return int(n), nil
+}
+
+func (m *MesherCUDA) stats() (evals, pruned, tris uint64) {
+	var e, p, t C.uint64_t
+	C.gsdf_mesh_stats(m.h, &e, &p, &t)
+	return uint64(e), uint64(p), uint64(t)
+}
+func (m *MesherCUDA) Evaluations() uint64 { e, _, _ := m.stats(); return e }
+func (m *MesherCUDA) TotalPruned() uint64 { _, p, _ := m.stats(); return p } // gsdfaux.go:220-221
+func (m *MesherCUDA) Rerun() error {
+	if C.gsdf_mesh_rerun(m.h) != 0 {
+		return cudaErr()
+	}
+	return nil
+}
+func (m *MesherCUDA) Close() { C.gsdf_mesh_destroy(m.h); m.h = nil }
+
+// WriteBinarySTL packs the records on the device and does ONE Write (stl.go:53 does one per triangle).
+func (m *MesherCUDA) WriteBinarySTL(w io.Writer) (int, error) {
+	_, _, t := m.stats()
+	buf := make([]byte, 84+50*int(t))
+	if n := C.gsdf_mesh_stl(m.h, unsafe.Pointer(&buf[0]), C.size_t(len(buf))); n < 0 {
+		return 0, cudaErr() // "empty triangle slice" (stl.go:16)
+	}
+	return w.Write(buf)
+}
+
+// CUDAColorConv is the data form of the conversions gsdfaux offers as closures (gsdfaux/color.go:21-102).
+type CUDAColorConv struct{ c C.gsdf_colorconv }
+
+func ColorConvInigoQuilez(characteristicDistance float32) (cc CUDAColorConv) {
+	C.gsdf_colorconv_inigo_quilez(C.float(characteristicDistance), &cc.c)
+	return cc
+}
+func ColorConvLinearGradient(gradientLength float32, c0, c1 [4]uint8) (cc CUDAColorConv) {
+	pack := func(c [4]uint8) C.uint32_t { return C.uint32_t(c[0]) | C.uint32_t(c[1])<<8 | C.uint32_t(c[2])<<16 | C.uint32_t(c[3])<<24 }
+	C.gsdf_colorconv_linear_gradient(C.float(gradientLength), pack(c0), pack(c1), &cc.c)
+	return cc
+}
+
+// RenderRGBA is ImageRendererSDF2.Render (image.go:76-118) with the conversion fused into the evaluation kernel.
+// conv == nil selects NewImageRendererSDF2(nil)'s black / white / red scheme (image.go:50-61).
+func RenderRGBA(s *gleval.SDF2CUDA, img *image.RGBA, conv *CUDAColorConv) error {
+	bb := s.Bounds()
+	r := img.Bounds()
+	if img.Stride != 4*r.Dx() {
+		return errors.New("RenderRGBA needs a tightly packed image.RGBA")
+	}
+	var cp *C.gsdf_colorconv
+	if conv != nil {
+		cp = &conv.c
+	}
+	if rc := C.gsdf_image_render2((*C.gsdf_program)(s.Handle()), (*C.float)(unsafe.Pointer(&bb.Min)), (*C.float)(unsafe.Pointer(&bb.Max)),
+		C.int(r.Dx()), C.int(r.Dy()), cp, (*C.uint8_t)(unsafe.Pointer(&img.Pix[0]))); rc != 0 {
+		return cudaErr()
+	}
+	return nil
+}
+
+// DualContourCUDA is DualContourRenderer (dual_contour.go:12-218) on the device.
+type DualContourCUDA struct{ h *C.gsdf_dualcontour }
+
+// Reset mirrors DualContourRenderer.Reset(sdf, res, vertexPlacer, userData): vertexPlacer *DualContourLeastSquares maps to
+// GSDF_DC_LEAST_SQUARES(_CHISELED). part / nparts (1, 2, 4, 8) split the octree by top-level octants across GPUs.
+func (dcr *DualContourCUDA) Reset(sdf *gleval.SDF3CUDA, res float32, vertexPlacer *DualContourLeastSquares, part, nparts int) error {
+	if vertexPlacer == nil {
+		return errors.New("nil DualContourer argument to Reset") // dual_contour.go:28-30
+	}
+	placer := C.int(C.GSDF_DC_LEAST_SQUARES)
+	if vertexPlacer.Chiseled {
+		placer = C.GSDF_DC_LEAST_SQUARES_CHISELED
+	}
+	if dcr.h != nil {
+		C.gsdf_dc_destroy(dcr.h)
+		dcr.h = nil
+	}
+	bb := sdf.Bounds()
+	if rc := C.gsdf_dc_begin_part((*C.gsdf_program)(sdf.Handle()), (*C.float)(unsafe.Pointer(&bb.Min)), (*C.float)(unsafe.Pointer(&bb.Max)),
+		C.float(res), placer, C.int(part), C.int(nparts), &dcr.h); rc != 0 {
+		return cudaErr() // same messages as makeICube (octreerenderer.go:223-233)
+	}
+	return nil
+}
+
+// RenderAll appends the mesh to dst like DualContourRenderer.RenderAll (dual_contour.go:73-218).
+func (dcr *DualContourCUDA) RenderAll(dst []ms3.Triangle, userData any) ([]ms3.Triangle, error) {
+	var st [6]C.uint64_t
+	C.gsdf_dc_stats(dcr.h, &st[0])
+	n := int(st[3])
+	out := make([]ms3.Triangle, n)
+	if n > 0 {
+		if got := C.gsdf_dc_read(dcr.h, (*C.float)(unsafe.Pointer(&out[0])), C.size_t(n)); got < 0 {
+			return dst, cudaErr()
+		}
+	}
+	return append(dst, out...), nil
+}
