@@ -1,0 +1,196 @@
+package glbuild
+
+// CUDA node program: the packed instruction stream of include/gsdf_program.h that libgsdfb200.so interprets on the GPU,
+// and the tree walk that produces it. The Program type and the emitter interface live in glbuild (like Programmer, the
+// GLSL code generator they stand beside, glbuild.go:175) so that gleval can flatten a tree without importing package
+// gsdf, which itself imports gleval; the per-node emitters live next to the node types (gsdf/cuda_flatten.go,
+// forge/threads/cuda_flatten.go).
+
+import (
+	"errors"
+	"fmt"
+	"unsafe"
+
+	math "github.com/chewxy/math32"
+)
+
+// Opcodes: enum gsdf_opcode of include/gsdf_program.h, in declaration order.
+const (
+	OpEnd uint32 = iota
+	OpSphere
+	OpBox
+	OpBoxFrame
+	OpTorus
+	OpCylinder
+	OpHex
+	OpCircle2D
+	OpRect2D
+	OpLine2D
+	OpLines2D
+	OpArc2D
+	OpEqTri2D
+	OpHex2D
+	OpOct2D
+	OpDiamond2D
+	OpRoundX2D
+	OpPoly2D
+	OpEllipse2D
+	OpBezierQ2D
+	OpMin
+	OpMax
+	OpDiff
+	OpXor
+	OpSmoothUnion
+	OpSmoothDiff
+	OpSmoothIntersect
+	OpOffset
+	OpAnnulus
+	OpMulDist
+	OpShellExit
+	OpAddBelow
+	OpExtrudeExit
+	OpMaxBelow
+	OpPushPos
+	OpPopPos
+	OpPeekPos
+	OpTranslate
+	OpScalePos
+	OpSymmetry
+	OpTransform
+	OpRotate2D
+	OpTwist
+	OpElongate
+	OpElongate2D
+	OpArrayVar
+	OpArray2DVar
+	OpCircEnter
+	OpExtrudeEnter
+	OpRevolve
+	OpScrewEnter
+)
+
+const (
+	programMagic   = 0x46445347 // "GSDF"
+	programVersion = 1
+	polyEdgeFloats = 8
+)
+
+// Program accumulates the instruction chunks (4 x uint32 each) and the float side buffer.
+type Program struct {
+	Chunks       []uint32
+	Aux          []float32
+	Dim          int
+	D, P         int // current distance / position stack depth
+	Dmax, Pmax   int
+	ninstr       int
+}
+
+// ProgramEmitter is implemented by every node type of gsdf and forge/threads (their cuda_flatten.go files).
+// restore: a later sibling still needs the current position, so the node must leave p as it found it.
+type ProgramEmitter interface {
+	AppendProgram(p *Program, restore bool) error
+}
+
+func fbits(f float32) uint32 { return math.Float32bits(f) }
+
+func (p *Program) Header(op, nchunks, w1, w2, w3 uint32) {
+	p.Chunks = append(p.Chunks, op|nchunks<<8, w1, w2, w3)
+	p.ninstr++
+}
+func (p *Program) Chunk(a, b, c, d float32) { p.Chunks = append(p.Chunks, fbits(a), fbits(b), fbits(c), fbits(d)) }
+func (p *Program) Op0(op uint32)            { p.Header(op, 1, 0, 0, 0) }
+func (p *Program) Opf(op uint32, f2, f3 float32) { p.Header(op, 1, 0, fbits(f2), fbits(f3)) }
+func (p *Program) PushD() {
+	p.D++
+	if p.D > p.Dmax {
+		p.Dmax = p.D
+	}
+}
+func (p *Program) PopD() { p.D-- }
+func (p *Program) PushP() {
+	p.Op0(OpPushPos)
+	p.P++
+	if p.P > p.Pmax {
+		p.Pmax = p.P
+	}
+}
+func (p *Program) PopP() { p.Op0(OpPopPos); p.P-- }
+func (p *Program) AlignAux(n int) uint32 {
+	for len(p.Aux)%n != 0 {
+		p.Aux = append(p.Aux, 0)
+	}
+	return uint32(len(p.Aux))
+}
+
+// Emit sees through the glbuild wrappers, then dispatches to the node's emitter.
+func Emit(p *Program, s Shader, restore bool) error {
+	for {
+		u := Unwrap(s)
+		if u == nil {
+			break
+		}
+		s = u
+	}
+	e, ok := s.(ProgramEmitter)
+	if !ok {
+		return fmt.Errorf("%T has no CUDA program emitter", s)
+	}
+	return e.AppendProgram(p, restore)
+}
+
+// unary emits enter, the child, exit for a position transform.
+func (p *Program) Unary(child Shader, restore bool, enter, exit func()) error {
+	if restore {
+		p.PushP()
+	}
+	enter()
+	if err := Emit(p, child, false); err != nil {
+		return err
+	}
+	if exit != nil {
+		exit()
+	}
+	if restore {
+		p.PopP()
+	}
+	return nil
+}
+
+func (p *Program) Binary(a, b Shader, restore bool, emitOp func()) error {
+	if err := Emit(p, a, true); err != nil { // the first operand must leave p intact for the second
+		return err
+	}
+	if err := Emit(p, b, restore); err != nil {
+		return err
+	}
+	emitOp()
+	p.PopD()
+	return nil
+}
+
+// Flatten3 / Flatten2 replace Programmer.WriteComputeSDF3/2 (glbuild/glbuild.go:175,218) for the CUDA backend:
+// blob = gsdf_program_header + chunks, aux = side buffer, ready for gsdf_program_create.
+func Flatten3(root Shader3D) (blob []byte, aux []float32, err error) { return flatten(root, 3) }
+func Flatten2(root Shader2D) (blob []byte, aux []float32, err error) { return flatten(root, 2) }
+
+func flatten(root Shader, dim int) ([]byte, []float32, error) {
+	var p Program
+	p.Dim = dim
+	if err := Emit(&p, root, false); err != nil {
+		return nil, nil, err
+	}
+	p.Header(OpEnd, 1, 0, 0, 0)
+	if p.D != 1 {
+		return nil, nil, errors.New("internal: distance stack imbalance")
+	}
+	dstack := 1 // the top is cached in a register; slot 0 also absorbs the first push
+	if p.Dmax > 1 {
+		dstack = p.Dmax - 1
+	}
+	p.AlignAux(4)
+	hdr := [8]uint32{programMagic, programVersion, uint32(len(p.Chunks) / 4), uint32(dim), uint32(dstack), uint32(p.Pmax), uint32(p.ninstr), 0}
+	words := append(hdr[:], p.Chunks...)
+	blob := unsafe.Slice((*byte)(unsafe.Pointer(&words[0])), 4*len(words)) // little-endian hosts, like the C side
+	return append([]byte(nil), blob...), p.Aux, nil
+}
+

@@ -14,7 +14,6 @@ import (
 
 	"github.com/soypat/geometry/ms2"
 	"github.com/soypat/geometry/ms3"
-	"github.com/soypat/gsdf"
 	"github.com/soypat/gsdf/glbuild"
 )
 
@@ -50,7 +49,7 @@ type SDF3CUDA struct {
 
 // NewCUDASDF3 mirrors NewComputeGPUSDF3(source, bb, cfg) (gpu.go:35): the tree is flattened once and uploaded once.
 func NewCUDASDF3(root glbuild.Shader3D) (*SDF3CUDA, error) {
-	blob, aux, err := gsdf.Flatten3(root)
+	blob, aux, err := glbuild.Flatten3(root)
 	if err != nil {
 		return nil, err
 	}
@@ -85,7 +84,7 @@ func (s *SDF3CUDA) Handle() unsafe.Pointer { return unsafe.Pointer(s.h) }
 // Update re-flattens root into this evaluator's device buffers (an edited tree costs one small upload; the GL path
 // recompiles its shader instead, gpu.go:35-54).
 func (s *SDF3CUDA) Update(root glbuild.Shader3D) error {
-	blob, aux, err := gsdf.Flatten3(root)
+	blob, aux, err := glbuild.Flatten3(root)
 	if err != nil {
 		return err
 	}
@@ -108,7 +107,7 @@ type SDF2CUDA struct {
 }
 
 func NewCUDASDF2(root glbuild.Shader2D) (*SDF2CUDA, error) {
-	blob, aux, err := gsdf.Flatten2(root)
+	blob, aux, err := glbuild.Flatten2(root)
 	if err != nil {
 		return nil, err
 	}
