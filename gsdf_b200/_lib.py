@@ -86,6 +86,7 @@ def _load():
         "gsdf_dc_levels": (C.c_int, [f32p, f32p, C.c_float, f32p]),
         "gsdf_dc_begin": (C.c_int, [vp, f32p, f32p, C.c_float, C.c_int, C.POINTER(vp)]),
         "gsdf_dc_begin_part": (C.c_int, [vp, f32p, f32p, C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+        "gsdf_dc_part_region": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), i32p]),
         "gsdf_dc_rerun": (C.c_int, [vp]),
         "gsdf_dc_read": (C.c_int64, [vp, vp, C.c_size_t]),
         "gsdf_dc_device_triangles": (C.c_int, [vp, C.POINTER(vp), u64p]),

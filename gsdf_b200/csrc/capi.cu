@@ -1017,6 +1017,29 @@ struct gsdf_dualcontour {
 
 namespace {
 
+// Owned key range of part `part` of `nparts` and the box [lo, hi) of cube origins it must evaluate: its run of top-level
+// octants grown by one cube on the low side (FinalVertex of the -1 neighbours, dual_contour.go:282-298) and by one cube on
+// the high side (the +1 neighbours whose edge data those vertices need), clipped to the grid. Pure host arithmetic (unit-tested without a device).
+void dc_part_region(int levels, int part, int nparts, uint32_t keys[2], int32_t box[6]) {
+    const int bits = levels - 1, N = 1 << bits;
+    const uint64_t ncell = 1ull << (3 * bits);
+    keys[0] = (uint32_t)(ncell * (uint64_t)part / (uint64_t)nparts);
+    keys[1] = (uint32_t)(ncell * (uint64_t)(part + 1) / (uint64_t)nparts);
+    int lo[3] = {N, N, N}, hi[3] = {0, 0, 0};
+    if (nparts == 1) { lo[0] = lo[1] = lo[2] = 0; hi[0] = hi[1] = hi[2] = N; }
+    else {
+        const uint64_t oct = ncell / 8;  // nparts divides 8: the range is a run of top-level octants
+        for (uint64_t k = keys[0]; k < keys[1]; k += oct) {
+            int i, j, kk;
+            dc_unkey((uint32_t)k, bits, i, j, kk);
+            const int c[3] = {i, j, kk};
+            for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], c[a]); hi[a] = std::max(hi[a], c[a] + N / 2); }
+        }
+        for (int a = 0; a < 3; a++) { lo[a] = std::max(0, lo[a] - 1); hi[a] = std::min(N, hi[a] + 1); }
+    }
+    for (int a = 0; a < 3; a++) { box[a] = lo[a]; box[3 + a] = hi[a]; }
+}
+
 int dc_scan(gsdf_dualcontour *d, uint32_t *data, uint32_t n, cudaStream_t st) {
     const uint64_t ntiles = ((uint64_t)n + kScanTile - 1) / kScanTile;
     int rc;
@@ -1046,22 +1069,14 @@ int dc_run(gsdf_dualcontour *d) {
     if ((rc = grow(d->d_eidx, d->eidx_cap, (size_t)G.ncell + 8))) return rc;
     CU(cudaEventRecord(d->ev[0], st));
     // Reset: every level-1 cube origin, in octree BFS order (dual_contour.go:37-57)
-    // Owned key range and the box of cube origins this part needs: its octants grown by one cube on the low side
-    // (FinalVertex of the -1 neighbours, dual_contour.go:282-298) and by one more on both sides for THEIR edge data.
-    const uint32_t key0 = (uint32_t)((uint64_t)G.ncell * d->part / d->nparts), key1 = (uint32_t)((uint64_t)G.ncell * (d->part + 1) / d->nparts);
-    const int N = 1 << G.bits;
-    int blo[3] = {N, N, N}, bhi[3] = {0, 0, 0};
-    if (d->nparts == 1) { blo[0] = blo[1] = blo[2] = 0; bhi[0] = bhi[1] = bhi[2] = N; }
-    else {
-        const uint32_t oct = G.ncell / 8;  // nparts divides 8: the range is a run of top-level octants
-        for (uint32_t k = key0; k < key1; k += oct) {
-            int i, j, kk;
-            dc_unkey(k, G.bits, i, j, kk);
-            const int c[3] = {i, j, kk};
-            for (int a = 0; a < 3; a++) { blo[a] = std::min(blo[a], c[a]); bhi[a] = std::max(bhi[a], c[a] + N / 2); }
-        }
-        for (int a = 0; a < 3; a++) { blo[a] = std::max(0, blo[a] - 1); bhi[a] = std::min(N, bhi[a] + 1); }
+    uint32_t keys[2];
+    int blo[3], bhi[3];
+    {
+        int32_t box[6];
+        dc_part_region(d->levels, d->part, d->nparts, keys, box);
+        for (int a = 0; a < 3; a++) { blo[a] = box[a]; bhi[a] = box[3 + a]; }
     }
+    const uint32_t key0 = keys[0], key1 = keys[1];
     GenDC g{};
     g.mode = 0; g.G = G; g.dist = d->d_dist;
     for (int a = 0; a < 3; a++) { g.blo[a] = blo[a]; g.bhi[a] = bhi[a]; }
@@ -1148,6 +1163,15 @@ int gsdf_dc_levels(const float bbmin[3], const float bbmax[3], float res, float 
     if (levels <= 1) return fail(GSDF_ERES, "resolution not fine enough for marching cubes");
     if (origin) { origin[0] = mn[0]; origin[1] = mn[1]; origin[2] = mn[2]; }
     return levels;
+}
+
+int gsdf_dc_part_region(int levels, int part, int nparts, uint32_t keys[2], int32_t box[6]) {
+    if (!keys || !box) return fail(GSDF_EINVAL, "gsdf_dc_part_region: NULL argument");
+    if (levels < 2 || levels > 11) return fail(GSDF_EINVAL, "dual contour octree levels must be in [2, 11]");
+    if (!(nparts == 1 || nparts == 2 || nparts == 4 || nparts == 8) || part < 0 || part >= nparts)
+        return fail(GSDF_EINVAL, "dual contour parts: nparts must be 1, 2, 4 or 8 (runs of top-level octants) and 0 <= part < nparts");
+    dc_part_region(levels, part, nparts, keys, box);
+    return 0;
 }
 
 int gsdf_dc_begin(gsdf_program *p, const float bbmin[3], const float bbmax[3], float res, int placer, gsdf_dualcontour **out) {

@@ -51,3 +51,14 @@ def total_count(n_local, group=None):
     t = torch.tensor([int(n_local)], dtype=torch.int64, device=dev)
     dist.all_reduce(t, group=group)
     return int(t.item())
+
+
+def octant_part(levels, part, nparts):
+    """Dual-contouring partition (gsdf_dc_begin_part): the part's key range [k0, k1) in the octree's BFS cube order and
+    the half-open box (lo[3], hi[3]) of cube indices it evaluates (own octants + one-cube border on each side). Host arithmetic only."""
+    import ctypes as C
+    from ._lib import lib, check
+    keys = (C.c_uint32 * 2)()
+    box = (C.c_int32 * 6)()
+    check(lib.gsdf_dc_part_region(int(levels), int(part), int(nparts), keys, box))
+    return (int(keys[0]), int(keys[1])), (tuple(box[:3]), tuple(box[3:]))

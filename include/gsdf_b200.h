@@ -160,11 +160,15 @@ int gsdf_dc_levels(const float bbmin[3], const float bbmax[3], float res, float 
  * bbmin/bbmax = sdf.Bounds(). Limits: at most 1024 cubes per axis (11 levels). */
 int gsdf_dc_begin(gsdf_program *p, const float bbmin[3], const float bbmax[3], float res, int placer, gsdf_dualcontour **out);
 /* Multi-GPU form: this handle owns part `part` of `nparts` (1, 2, 4 or 8) equal, contiguous ranges of the octree's BFS
- * cube order -- runs of top-level octants. It evaluates its octants plus a two-cube border (the neighbour data the QEF
+ * cube order -- runs of top-level octants. It evaluates its octants plus a one-cube border on each side (the neighbour data the QEF
  * and the quads of its own cubes need), and emits only the quads of its own cubes; the parts' triangle buffers
  * concatenated in part order are bit-identical to the single-handle mesh. No collective on the data path. */
 int gsdf_dc_begin_part(gsdf_program *p, const float bbmin[3], const float bbmax[3], float res, int placer, int part, int nparts,
                        gsdf_dualcontour **out);
+/* The partition itself (host arithmetic, no device needed): keys = the part's range [keys[0], keys[1]) of the octree's
+ * BFS cube order (index = per-level child indices of i3.Cube.Octree(), most significant level first); box = {lo.xyz,
+ * hi.xyz}, the half-open range of cube indices whose origins the part evaluates (its octants plus a one-cube border on each side). */
+int gsdf_dc_part_region(int levels, int part, int nparts, uint32_t keys[2], int32_t box[6]);
 /* Re-run with the same parameters, reusing every device buffer. */
 int gsdf_dc_rerun(gsdf_dualcontour *d);
 /* RenderAll's result: copies up to max_tris triangles (9 floats each, cube order, two per quad) from the start of the

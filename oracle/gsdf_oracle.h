@@ -130,6 +130,10 @@ int go_dc_levels(const float bbmin[3], const float bbmax[3], float res, float or
 int64_t go_dual_contour(const go_tree *t, const float bbmin[3], const float bbmax[3], float res, int placer, float *tri9, int64_t max_tris,
                         int64_t *stats);
 
+/* Same, also reporting per quad (= per two triangles) the BFS key of the cube that emitted it (multi-rank partition tests). */
+int64_t go_dual_contour_ex(const go_tree *t, const float bbmin[3], const float bbmax[3], float res, int placer, float *tri9, int64_t max_tris,
+                           int64_t *stats, uint32_t *quad_keys);
+
 /* ---- STL (glrender/stl.go:15-62) ---- */
 /* dst needs 84 + 50*ntri bytes. returns bytes written, or <0 (empty model is an error, stl.go:16). */
 int64_t go_stl_write(const float *tri9, int64_t ntri, uint8_t *dst);

@@ -112,8 +112,15 @@ static float clampf_(float v, float lo, float hi) { return v < lo ? lo : (v > hi
 /* placer: 0 = DualContourNaive, 1 = DualContourLeastSquares{}, 2 = DualContourLeastSquares{Chiseled: true}.
  * tri9: up to max_tris triangles; returns the triangle count (counting continues past max_tris) or <0.
  * stats (optional, 4 x int64): {levels, cubes kept by the prune, cubes with >= 1 neighbour entry, SDF evaluations}. */
+int64_t go_dual_contour_ex(const go_tree *t, const float bbmin[3], const float bbmax[3], float res, int placer, float *tri9, int64_t max_tris,
+                           int64_t *stats, uint32_t *quad_keys);
 int64_t go_dual_contour(const go_tree *t, const float bbmin[3], const float bbmax[3], float res, int placer, float *tri9, int64_t max_tris,
                         int64_t *stats) {
+    return go_dual_contour_ex(t, bbmin, bbmax, res, placer, tri9, max_tris, stats, NULL);
+}
+/* quad_keys (optional, one per quad = per two triangles, same max_tris bound): BFS key of the cube that emitted the quad. */
+int64_t go_dual_contour_ex(const go_tree *t, const float bbmin[3], const float bbmax[3], float res, int placer, float *tri9, int64_t max_tris,
+                           int64_t *stats, uint32_t *quad_keys) {
     float org[3];
     int levels = go_dc_levels(bbmin, bbmax, res, org);
     if (levels <= 1) return -1;
@@ -286,6 +293,7 @@ int64_t go_dual_contour(const go_tree *t, const float bbmin[3], const float bbma
             if (!all) continue;
             if (flip[a]) { v3 t0 = quad[0], t1 = quad[1]; quad[0] = quad[3]; quad[1] = quad[2]; quad[2] = t1; quad[3] = t0; }
             const v3 tri[2][3] = {{quad[0], quad[1], quad[2]}, {quad[2], quad[3], quad[0]}};
+            if (quad_keys && nt + 1 < max_tris) quad_keys[nt / 2] = (uint32_t)dc_key(cu->i, cu->j, cu->k, bits);
             for (int w = 0; w < 2; w++) {
                 if (tri9 && nt < max_tris) memcpy(tri9 + 9 * nt, tri[w], 36);
                 nt++;
@@ -295,6 +303,5 @@ int64_t go_dual_contour(const go_tree *t, const float bbmin[3], const float bbma
 #undef CELL
     if (stats) { stats[0] = levels; stats[1] = (int64_t)nc; stats[2] = withnb; stats[3] = evals; }
     free(cubes); free(map);
-    (void)dc_key;
     return nt;
 }

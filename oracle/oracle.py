@@ -116,6 +116,8 @@ def lib():
         L.go_dc_levels.argtypes = [f32p, f32p, C.c_float, f32p]
         L.go_dual_contour.restype = C.c_int64
         L.go_dual_contour.argtypes = [C.POINTER(GoTree), f32p, f32p, C.c_float, C.c_int, vp, C.c_int64, C.POINTER(C.c_int64)]
+        L.go_dual_contour_ex.restype = C.c_int64
+        L.go_dual_contour_ex.argtypes = [C.POINTER(GoTree), f32p, f32p, C.c_float, C.c_int, vp, C.c_int64, C.POINTER(C.c_int64), vp]
         L.go_mc_edge_table.restype = C.POINTER(C.c_int)
         L.go_mc_tri_table.restype = C.POINTER(C.c_int8)
         L.go_mc_pair_table.restype = C.POINTER(C.c_int)
@@ -194,6 +196,17 @@ def dual_contour(tree, bbmin, bbmax, res, placer=DC_LSQ):
     tris = np.empty((max(n, 1), 3, 3), dtype=np.float32)
     lib().go_dual_contour(C.byref(tree.c), a, b, float(res), placer, tris.ctypes.data, n, st)
     return tris[:n], dict(levels=st[0], cubes=st[1], with_neighbors=st[2], evals=st[3])
+
+
+def dual_contour_quad_keys(tree, bbmin, bbmax, res, placer=DC_LSQ):
+    """BFS cube key of the cube that emitted each quad of dual_contour()'s mesh (uint32, one per two triangles)."""
+    a = (C.c_float * 3)(*[float(v) for v in bbmin])
+    b = (C.c_float * 3)(*[float(v) for v in bbmax])
+    n = lib().go_dual_contour(C.byref(tree.c), a, b, float(res), placer, None, 0, None)
+    tris = np.empty((max(n, 1), 3, 3), dtype=np.float32)
+    keys = np.zeros(max(n // 2, 1), dtype=np.uint32)
+    lib().go_dual_contour_ex(C.byref(tree.c), a, b, float(res), placer, tris.ctypes.data, n, None, keys.ctypes.data)
+    return keys[:n // 2]
 
 
 def flat_lattice(bbmin, bbmax, res):

@@ -186,7 +186,7 @@ def test_gpu_dual_contour_errors(bld):
 @pytest.mark.parametrize("shape,res,placer", [("sphere", 1.0 / 6, "lsq"), ("snowman", 3.0 / 64, "chiseled"), ("flange", None, "chiseled"), ("box", 2.0 / 8, "naive")])
 def test_gpu_dual_contour_octant_parts_concatenate_to_the_whole(bld, shape, res, placer):
     """Multi-GPU layout: part r of nparts owns a run of top-level octants (a contiguous range of the BFS cube order) and
-    recomputes a two-cube border instead of exchanging halos; the parts' meshes concatenated in part order are
+    recomputes a one-cube border on each side instead of exchanging halos; the parts' meshes concatenated in part order are
     bit-identical to the single-renderer mesh (same property as test_z_slabs_concatenate_to_the_whole for marching cubes)."""
     s = gsdf.scene(bld, "npt-flange") if shape == "flange" else SHAPES[shape](bld)
     if res is None:

@@ -71,3 +71,88 @@ def test_two_rank_gloo_slab_gather(tmp_path, oracle):
     txt = open(out).read()
     assert txt.startswith("ok"), txt
     assert int(txt.split()[1]) > 1000
+
+
+def _bfs_unkey(key, bits):
+    """Octree BFS cube order -> cube index: child order of i3.Cube.Octree() = Bourke corner order, top level first."""
+    x = y = z = 0
+    for b in range(bits - 1, -1, -1):
+        c = (key >> (3 * b)) & 7
+        zb, r = c >> 2, c & 3
+        yb = r >> 1
+        xb = 3 - r if yb else r
+        x |= xb << b
+        y |= yb << b
+        z |= zb << b
+    return x, y, z
+
+
+def test_dual_contour_octant_parts_cover_and_border():
+    """gsdf_dc_part_region (host arithmetic of gsdf_dc_begin_part): the parts' key ranges tile the BFS order; every cube a
+    part owns, its -1 neighbours (quad corners) and their +1 neighbours (QEF edge data: at most the cube's own +1) lie
+    inside the part's box."""
+    for levels in (3, 4, 6):
+        bits = levels - 1
+        N = 1 << bits
+        for nparts in (1, 2, 4, 8):
+            ranges = []
+            for part in range(nparts):
+                (k0, k1), (lo, hi) = slab.octant_part(levels, part, nparts)
+                ranges.append((k0, k1))
+                assert all(0 <= lo[a] < hi[a] <= N for a in range(3))
+                step = max(1, (k1 - k0) // 4096)
+                for key in list(range(k0, k1, step)) + [k1 - 1]:
+                    c = _bfs_unkey(key, bits)
+                    for a in range(3):
+                        assert max(c[a] - 1, 0) >= lo[a]
+                        assert min(c[a] + 1, N - 1) < hi[a]
+                if nparts == 8:  # one octant plus its border, not the whole grid
+                    assert all(hi[a] - lo[a] <= N // 2 + 2 for a in range(3))
+            assert ranges[0][0] == 0 and ranges[-1][1] == N ** 3
+            assert all(a[1] == b[0] for a, b in zip(ranges[:-1], ranges[1:]))
+    import gsdf_b200
+    with pytest.raises(gsdf_b200.GsdfError):
+        slab.octant_part(5, 0, 3)
+    with pytest.raises(gsdf_b200.GsdfError):
+        slab.octant_part(5, 4, 4)
+
+
+def _dc_worker(rank, world, port, out_path):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import torch.distributed as dist
+    from gsdf_b200 import gsdf
+    from gsdf_b200 import slab as S
+    from oracle import oracle as O
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        bld = gsdf.Builder()
+        s = bld.Union(bld.NewSphere(0.4), bld.Translate(bld.NewSphere(0.3), 0, 0, 0.45), bld.Translate(bld.NewSphere(0.2), 0, 0, 0.8))
+        res = np.float32(3.0 / 64)
+        tree = O.Tree.from_shader(s)
+        whole, st = O.dual_contour(tree, *s.Bounds(), res, O.DC_LSQ_CHISELED)
+        # the oracle meshes globally; a rank keeps the triangles of the cubes it owns. Two triangles per quad, quads in cube
+        # (= BFS key) order: ownership is decided by the quad's owning cube, recovered from the triangle's first vertex run.
+        (k0, k1), _ = S.octant_part(st["levels"], rank, world)
+        keys = O.dual_contour_quad_keys(tree, *s.Bounds(), res, O.DC_LSQ_CHISELED)
+        mine = whole[np.repeat((keys >= k0) & (keys < k1), 2)]
+        total = S.total_count(len(mine))
+        allt = S.gather_triangles(mine, dst=0)
+        if rank == 0:
+            ok = total == len(whole) and np.array_equal(allt.view(np.uint32), whole.view(np.uint32))
+            with open(out_path, "w") as f:
+                f.write("ok %d" % total if ok else "mismatch %d %d" % (total, len(whole)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_dual_contour_parts(tmp_path, oracle):
+    """The dual-contour mesh split by owned key range over 2 gloo ranks and gathered in rank order equals the whole mesh
+    (the oracle stands in for the device renderer; quads are emitted in BFS key order, so ranges concatenate)."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "dc.txt")
+    mp.spawn(_dc_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    txt = open(out).read()
+    assert txt.startswith("ok"), txt
+    assert int(txt.split()[1]) > 1000
