@@ -205,3 +205,92 @@ def sample_points(shader, margin=0.15, dense=None):
     lo, hi = mn - margin * size, mx + margin * size
     counts = dense if dense is not None else grid_counts(size)
     return append_grid(lo, hi, counts)
+
+
+# ---------------------------------------------------------------------------------------------- random trees
+def _rand2d(bld, rng, depth):
+    """A random 2-D tree of at most `depth` operation levels over random primitives (parameters inside the ranges the
+    reference's randomised tests draw from, gsdf_test.go:572-730)."""
+    u = lambda a, b: float(rng.uniform(a, b))
+    if depth <= 0 or rng.random() < 0.1:
+        k = int(rng.integers(0, 10))
+        if k == 0: return bld.NewCircle(u(0.3, 1.2))
+        if k == 1: return bld.NewRectangle(u(0.3, 1.5), u(0.3, 1.5))
+        if k == 2: return bld.NewHexagon(u(0.3, 1.0))
+        if k == 3: return bld.NewOctagon(u(0.3, 1.0))
+        if k == 4: return bld.NewEquilateralTriangle(u(0.4, 1.2))
+        if k == 5: return bld.NewPolygon(nagon(int(rng.integers(3, 12)), np.float32(u(0.4, 1.2))))
+        if k == 6: return bld.NewLine2D(u(-1, 0), u(-1, 0), u(0.1, 1), u(0.1, 1), u(0.05, 0.3))
+        if k == 7: return bld.NewDiamond2D(u(0.3, 1.2), u(0.3, 1.2))
+        if k == 8: return bld.NewArc(u(0.5, 1.2), u(0.3, 2.5), u(0.05, 0.2))
+        return bld.NewRoundedX(u(0.5, 1.2), u(0.05, 0.2))
+    k = int(rng.integers(0, 13))
+    a = _rand2d(bld, rng, depth - 1)
+    if k == 0: return bld.Union2D(a, _rand2d(bld, rng, depth - 1), *[_rand2d(bld, rng, 0) for _ in range(int(rng.integers(0, 3)))])
+    if k == 1: return bld.Difference2D(a, bld.Translate2D(_rand2d(bld, rng, depth - 1), u(-0.5, 0.5), u(-0.5, 0.5)))
+    if k == 2: return bld.Intersection2D(a, _rand2d(bld, rng, depth - 1))
+    if k == 3: return bld.Xor2D(a, bld.Translate2D(_rand2d(bld, rng, depth - 1), u(-0.5, 0.5), u(-0.5, 0.5)))
+    if k == 4: return bld.Translate2D(a, u(-1.5, 1.5), u(-1.5, 1.5))
+    if k == 5: return bld.Rotate2D(a, u(-3, 3))
+    if k == 6: return bld.Scale2D(a, u(0.3, 2.5))
+    if k == 7: return bld.Offset2D(a, u(-0.1, 0.2))
+    if k == 8: return bld.Annulus(a, u(0.02, 0.15))
+    if k == 9: return bld.Symmetry2D(bld.Translate2D(a, u(0, 1), u(0, 1)), bool(rng.integers(0, 2)), True)
+    if k == 10: return bld.Elongate2D(a, u(0.05, 0.6), u(0.05, 0.6))
+    if k == 11: return bld.Array2D(a, u(1.5, 3.0), u(1.5, 3.0), int(rng.integers(1, 4)), int(rng.integers(1, 4)))
+    div = int(rng.integers(3, 10))
+    return bld.CircularArray2D(bld.Translate2D(a, u(1.5, 3.0), 0), int(rng.integers(1, div + 1)), div)
+
+
+def _rand3d(bld, rng, depth):
+    u = lambda a, b: float(rng.uniform(a, b))
+    if depth <= 0 or rng.random() < 0.2:
+        k = int(rng.integers(0, 10))
+        if k == 0: return bld.NewSphere(u(0.3, 1.2))
+        if k == 1: return bld.NewBox(u(0.5, 1.5), u(0.5, 1.5), u(0.5, 1.5), u(0, 0.12))
+        if k == 2: return bld.NewCylinder(u(0.3, 1.0), u(0.5, 2.0), 0 if rng.random() < 0.5 else u(0.01, 0.1))
+        if k == 3: return bld.NewHexagonalPrism(u(0.4, 1.2), u(0.4, 1.5))
+        if k == 4: return bld.NewTorus(u(0.8, 1.5), u(0.1, 0.35))
+        if k == 5: return bld.NewBoxFrame(u(0.8, 1.5), u(0.8, 1.5), u(0.8, 1.5), u(0.05, 0.15))
+        if k == 6: return bld.NewTriangularPrism(u(0.5, 1.2), u(0.3, 1.5))
+        if k == 7: return bld.Extrude(_rand2d(bld, rng, 1), u(0.3, 2.0))
+        if k == 8: return bld.Revolve(bld.Translate2D(_rand2d(bld, rng, 1), u(1.5, 3.0), 0), 0 if rng.random() < 0.5 else u(0.1, 0.5))
+        T = gsdf.threads
+        return T.Screw(bld, u(1.0, 3.0), T.ISO(u(0.8, 1.6), u(0.1, 0.3), bool(rng.integers(0, 2))))
+    k = int(rng.integers(0, 18))
+    a = _rand3d(bld, rng, depth - 1)
+    other = lambda: bld.Translate(_rand3d(bld, rng, depth - 1), u(-0.6, 0.6), u(-0.6, 0.6), u(-0.6, 0.6))
+    if k == 0: return bld.Union(a, other(), *[_rand3d(bld, rng, 0) for _ in range(int(rng.integers(0, 3)))])
+    if k == 1: return bld.Difference(a, other())
+    if k == 2: return bld.Intersection(a, other())
+    if k == 3: return bld.Xor(a, other())
+    if k == 4: return bld.SmoothUnion(u(0.05, 0.4), a, other())
+    if k == 5: return bld.SmoothDifference(u(0.05, 0.4), a, other())
+    if k == 6: return bld.SmoothIntersect(u(0.05, 0.4), a, other())
+    if k == 7: return bld.Translate(a, u(-1.5, 1.5), u(-1.5, 1.5), u(-1.5, 1.5))
+    if k == 8: return bld.Rotate(a, u(-3, 3), (u(0.1, 1), u(-1, 1), u(-1, 1)))
+    if k == 9: return bld.Scale(a, u(0.2, 3.0))
+    if k == 10: return bld.Offset(a, u(-0.05, 0.15))
+    if k == 11: return bld.Shell(a, u(0.02, 0.1))
+    if k == 12: return bld.Elongate(a, u(0.05, 0.5), u(0.05, 0.5), u(0.05, 0.5))
+    if k == 13: return bld.Symmetry(bld.Translate(a, u(0, 1), u(0, 1), u(0, 1)), True, bool(rng.integers(0, 2)), bool(rng.integers(0, 2)))
+    if k == 14: return bld.Twist(a, u(-0.8, 0.8))
+    if k == 15: return bld.Array(a, u(2.0, 4.0), u(2.0, 4.0), u(2.0, 4.0), int(rng.integers(1, 3)), int(rng.integers(1, 3)), int(rng.integers(1, 3)))
+    if k == 16:
+        div = int(rng.integers(3, 9))
+        return bld.CircularArray(bld.Translate(a, u(1.5, 3.0), 0, 0), int(rng.integers(1, div + 1)), div)
+    return bld.Transform(a, [[u(0.8, 1.2), u(-0.2, 0.2), 0, u(-0.5, 0.5)], [0, u(0.8, 1.2), u(-0.2, 0.2), u(-0.5, 0.5)],
+                             [u(-0.2, 0.2), 0, u(0.8, 1.2), u(-0.5, 0.5)], [0, 0, 0, 1]])
+
+
+def random_trees(bld, seed, count, dim=3, depth=4, max_dstack=16, max_pstack=8):
+    """`count` seeded random trees (numpy Generator, PCG64: reproducible everywhere) that fit the interpreter's stacks."""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < count:
+        s = (_rand3d if dim == 3 else _rand2d)(bld, rng, depth)
+        f = bld.flatten(s)
+        if f["dstack"] > max_dstack or f["pstack"] > max_pstack:
+            continue
+        out.append(("rand%dd_%d_%d" % (dim, seed, len(out)), s))
+    return out

@@ -52,6 +52,16 @@ def test_evaluate_matches_oracle_on_reference_lattices(oracle, bld, corpus):
         check_field(name, s, oracle, shapes.sample_points(s))
 
 
+@pytest.mark.parametrize("dim", [3, 2])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_trees_bit_identical(oracle, bld, seed, dim):
+    """Seeded random compositions of every constructor (testRandomUnary3D/2D taken further, gsdf_test.go:233-283):
+    nesting exercises the flattener's stack allocation, position liveness and guard placement on trees nobody wrote
+    by hand. Points past the end of the reference lattice are included through the margin."""
+    for name, s in shapes.random_trees(bld, seed, 40, dim):
+        check_field(name, s, oracle, shapes.sample_points(s))
+
+
 def test_evaluate_golden_fixtures(bld):
     g = np.load(os.path.join(GOLD, "distances.npz"))
     for name, s in shapes.all3d(bld) + shapes.all2d(bld):
@@ -258,6 +268,23 @@ def test_mesh_bit_identical_to_oracle(oracle, bld, scene, resdiv, prune):
         assert np.array_equal(bits(g)[ev], bits(grid)[ev]) and ev.sum() < grid.size
     R.Rerun()                                                  # Reset/re-render reuses buffers and reproduces the result
     assert np.array_equal(bits(R.AllTriangles()), bits(wt))
+
+
+@pytest.mark.parametrize("prune", [False, True])
+def test_random_trees_mesh_bit_identical(oracle, bld, prune):
+    """The mesher on seeded random trees (tests/shapes.py): lattice, cube-case indices, triangles and their order are
+    the oracle's for shapes with thin shells, arrays and non-Lipschitz fields, with and without the octree prune."""
+    for name, s in shapes.random_trees(bld, 11, 10, 3, depth=3):
+        res = np.float32(s.Diagonal() / np.float32(60))
+        lat, grid, mask, wt, wc = oracle_mesh(oracle, s, res, prune)
+        sdf = gleval.NewCUDASDF3(s)
+        R = (glrender.Octree if prune else glrender.FlatRenderer)(sdf, res, keep_cases=True)
+        assert list(R.lat.n) == list(lat.n), name
+        assert int((R.Cases() != wc).sum()) == 0, name
+        tris = R.AllTriangles()
+        assert len(tris) == len(wt) == R.NumTriangles(), name
+        assert np.array_equal(bits(tris), bits(wt)), name
+        R.Close()
 
 
 def test_flange_resdiv400_readme_counts(bld):

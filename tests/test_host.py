@@ -168,6 +168,23 @@ def test_flattened_programs_are_well_formed(bld):
         assert 1 <= dstack <= 16 and pstack <= 8, name
 
 
+def test_random_trees_flatten_within_stack_limits(oracle, bld):
+    """The seeded random trees of the GPU fuzz test (tests/shapes.py): every one flattens to a well-formed program, the
+    oracle evaluates it to finite values, and the generator is reproducible (same seed, same programs)."""
+    import shapes
+    for dim in (3, 2):
+        a = shapes.random_trees(bld, 1, 25, dim)
+        b = shapes.random_trees(bld, 1, 25, dim)
+        for (name, s), (_, s2) in zip(a, b):
+            f, f2 = bld.flatten(s), bld.flatten(s2)
+            assert f["blob"] == f2["blob"] and np.array_equal(f["aux"], f2["aux"]), name
+            assert 1 <= f["dstack"] <= 16 and f["pstack"] <= 8, name
+            t = oracle.Tree.from_shader(s)
+            pos = shapes.sample_points(s)
+            d = t.eval3(pos) if dim == 3 else t.eval2(pos)
+            assert np.isfinite(d).all(), name
+
+
 def test_position_liveness(bld):
     """A transform whose position nobody reads again must not save it: scale(translate(sphere)) needs no P slots,
     union(translate(a), b) needs one."""
