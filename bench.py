@@ -419,7 +419,7 @@ def run_cuda(args, rank, local_rank, world):
                    (SCENE, RESDIV, nx + 1, ny + 1, nz + 1, "" if world == 1 else "; one full render per GPU per step"),
                    "renderer": "Octree (prune)", "evals_per_step_dense_equivalent": lattice_evals, "evals_executed_per_step": evals_exec,
                    "triangles_per_step": ntri, "l2": "flushed between steps (256 MiB write); working set 27 MB < 126 MB L2",
-                   "timing": "CUDA events on the launching stream around each step (one CUDA-graph replay of 7 kernel nodes), summed over the timed steps, max over ranks"},
+                   "timing": "CUDA events on the launching stream around each step (one CUDA-graph replay of 7 kernel nodes chained by programmatic dependent launch), summed over the timed steps, max over ranks"},
         "triangles_per_sec": tri_rate,
         "evals_executed_per_sec": allsum(evals_exec * args.steps) / (dev_ms * 1e-3) if world == 1 else None,
         "stage_ms": mean,

@@ -41,6 +41,15 @@ int fail(int code, const char *fmt, ...) {
 int g_device = 0;
 int g_sms = 0;
 
+// Every compute entry point starts here: select the handle's device and drop any stale NON-sticky error another library
+// (or a teardown path) left in this thread's runtime state, so that the cudaGetLastError() checks behind our launches
+// report our launches only. Sticky errors (a faulted context) are not cleared by this and still surface.
+cudaError_t use_device(int dev) {
+    const cudaError_t e = cudaSetDevice(dev);
+    if (e == cudaSuccess) (void)cudaGetLastError();
+    return e;
+}
+
 int ensure_device() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -87,8 +96,23 @@ struct gsdf_program {
 namespace {
 
 // persistent launch: at most one resident wave of CTAs; they pull 256-item tiles from the program's scheduler
+// Launch with (pdl) or without the programmatic-stream-serialization attribute: with it the kernel may become resident
+// while its predecessor on the stream drains and runs up to its pdl_wait() (kernels.cuh); captured into a CUDA graph the
+// attribute becomes a programmatic dependency edge.
+template <class... KArgs, class... Args>
+cudaError_t launch_chain(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int P, class Gen, bool EXT>
-int launch_eval_impl(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st) {
+int launch_eval_impl(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st, bool pdl) {
     auto kern = k_eval<P, Gen, EXT>;
     const uint32_t smem = smem_total_bytes<P>(p->pv, kEvalThreads);
     static thread_local uint32_t cached_smem = 0xffffffffu;
@@ -103,16 +127,17 @@ int launch_eval_impl(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper
     }
     uint64_t blocks = (nwork_upper_bound + kEvalThreads - 1) / kEvalThreads;
     blocks = std::min<uint64_t>(blocks, (uint64_t)g_sms * cached_occ);
-    kern<<<(unsigned)blocks, kEvalThreads, smem, st>>>(p->pv, gen);
+    if (pdl) CU(launch_chain(true, kern, dim3((unsigned)blocks), dim3(kEvalThreads), smem, st, p->pv, gen));
+    else kern<<<(unsigned)blocks, kEvalThreads, smem, st>>>(p->pv, gen);
     CU(cudaGetLastError());
     return 0;
 }
 // persistent launch: at most one resident wave of CTAs; they pull tiles from the program's scheduler
 template <int P, class Gen>
-int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st) {
+int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st, bool pdl = false) {
     if (nwork_upper_bound == 0) return 0;
-    return p->needs_ext ? launch_eval_impl<P, Gen, true>(p, gen, nwork_upper_bound, st)
-                        : launch_eval_impl<P, Gen, false>(p, gen, nwork_upper_bound, st);
+    return p->needs_ext ? launch_eval_impl<P, Gen, true>(p, gen, nwork_upper_bound, st, pdl)
+                        : launch_eval_impl<P, Gen, false>(p, gen, nwork_upper_bound, st, pdl);
 }
 
 // Streaming Evaluate (k_eval_stream): persistent grid, one resident wave, tiles dealt round-robin.
@@ -302,7 +327,7 @@ int gsdf_program_update(gsdf_program *p, const void *blob, size_t blob_bytes, co
     int rc = parse_blob(blob, blob_bytes, aux, aux_floats, h, chunks);
     if (rc) return rc;
     if ((int)h.dim != p->dim) return fail(GSDF_EINVAL, "cannot change a %dD program into a %dD one", p->dim, (int)h.dim);
-    CU(cudaSetDevice(p->device));
+    CU(use_device(p->device));
     CU(cudaStreamSynchronize(p->stream));  // nothing may still be reading the old program
     return upload_blob(p, h, chunks, aux, aux_floats);
 }
@@ -316,6 +341,7 @@ void gsdf_program_destroy(gsdf_program *p) {
     cudaFree(p->d_pos);
     cudaFree(p->d_dist);
     delete p;
+    (void)cudaGetLastError();
 }
 
 uint64_t gsdf_program_evaluations(const gsdf_program *p) { return p ? p->evals : 0; }
@@ -324,7 +350,7 @@ int gsdf_eval3_device(gsdf_program *p, const float *d_pos, float *d_dist, size_t
     if (!p || !d_pos || !d_dist) return fail(GSDF_EINVAL, "gsdf_eval3_device: NULL argument");
     if (p->dim != 3) return fail(GSDF_EINVAL, "program is not 3D");
     if (n == 0) return fail(GSDF_EEMPTY, "empty buffers");
-    CU(cudaSetDevice(p->device));
+    CU(use_device(p->device));
     const int src = launch_stream<3>(p, d_pos, d_dist, (uint64_t)n, stream ? (cudaStream_t)stream : p->stream);
     if (src <= 0) return src;
     GenPoints3 g{d_pos, d_dist, (uint64_t)n, (((uintptr_t)d_pos | (uintptr_t)d_dist) & 15) == 0 ? 1 : 0};
@@ -335,7 +361,7 @@ int gsdf_eval2_device(gsdf_program *p, const float *d_pos, float *d_dist, size_t
     if (!p || !d_pos || !d_dist) return fail(GSDF_EINVAL, "gsdf_eval2_device: NULL argument");
     if (p->dim != 2) return fail(GSDF_EINVAL, "program is not 2D");
     if (n == 0) return fail(GSDF_EEMPTY, "empty buffers");
-    CU(cudaSetDevice(p->device));
+    CU(use_device(p->device));
     const int src = launch_stream<2>(p, d_pos, d_dist, (uint64_t)n, stream ? (cudaStream_t)stream : p->stream);
     if (src <= 0) return src;
     GenPoints2 g{d_pos, d_dist, (uint64_t)n, (((uintptr_t)d_pos | (uintptr_t)d_dist) & 15) == 0 ? 1 : 0};
@@ -346,7 +372,7 @@ static int eval_host(gsdf_program *p, const float *pos, float *dist, size_t n, i
     if (!p || !pos || !dist) return fail(GSDF_EINVAL, "gsdf_eval: NULL argument");
     if (p->dim != dim) return fail(GSDF_EINVAL, "program is %dD, called as %dD", p->dim, dim);
     if (n == 0) return fail(GSDF_EEMPTY, "empty buffers");
-    CU(cudaSetDevice(p->device));
+    CU(use_device(p->device));
     int rc = grow(p->d_pos, p->pos_cap, n * 3);
     if (rc) return rc;
     rc = grow(p->d_dist, p->dist_cap, n);
@@ -411,7 +437,7 @@ int gsdf_grid_eval_device(gsdf_program *p, const gsdf_lattice *lat, int k0, int 
     if (!p || !lat || !d_dist) return fail(GSDF_EINVAL, "gsdf_grid_eval_device: NULL argument");
     if (p->dim != 3) return fail(GSDF_EINVAL, "program is not 3D");
     if (k0 < 0 || k1 > lat->n[2] + 1 || k0 >= k1) return fail(GSDF_EINVAL, "bad corner-plane range [%d,%d)", k0, k1);
-    CU(cudaSetDevice(p->device));
+    CU(use_device(p->device));
     const int pitch = lat->n[0] + 1;
     const bool vec = (pitch % 4 == 0) && (((uintptr_t)d_dist & 15) == 0);
     GenGrid<4> g{make_lat(lat, k0, k1, pitch, vec), d_dist, nullptr, nullptr};
@@ -422,7 +448,7 @@ int gsdf_grid_eval_device(gsdf_program *p, const gsdf_lattice *lat, int k0, int 
 int gsdf_grid_eval(gsdf_program *p, const gsdf_lattice *lat, int k0, int k1, float *dist) {
     if (!p || !lat) return fail(GSDF_EINVAL, "gsdf_grid_eval: NULL argument");
     if (k0 < 0 || k1 > lat->n[2] + 1 || k0 >= k1) return fail(GSDF_EINVAL, "bad corner-plane range [%d,%d)", k0, k1);
-    CU(cudaSetDevice(p->device));
+    CU(use_device(p->device));
     const size_t n = (size_t)(lat->n[0] + 1) * (lat->n[1] + 1) * (k1 - k0);
     int rc = grow(p->d_dist, p->dist_cap, n);
     if (rc) return rc;
@@ -442,7 +468,7 @@ static int image_run(gsdf_program *p, const float bbmin[2], const float bbmax[2]
     if (p->dim != 2) return fail(GSDF_EINVAL, "program is not 2D");
     if (w <= 0 || h <= 0) return fail(GSDF_EINVAL, "bad image size");
     if (conv && (conv->kind < GSDF_CONV_DEFAULT || conv->kind > GSDF_CONV_HSV_GRADIENT)) return fail(GSDF_EINVAL, "unknown colour conversion %d", conv->kind);
-    CU(cudaSetDevice(p->device));
+    CU(use_device(p->device));
     const size_t n = (size_t)w * h;
     int rc = d_out ? 0 : grow(p->d_dist, p->dist_cap, n);  // 4 B/pixel either way (float or RGBA8)
     if (rc) return rc;
@@ -560,6 +586,7 @@ struct gsdf_mesher {
     cudaGraphExec_t gexec = nullptr;
     std::vector<uint8_t> gkey;  // snapshot of every pointer / size the captured launches were built from
     bool allow_graph = true;
+    int device = 0;   // device of the program the mesher was created on (destroy must not touch prog: it may be gone)
     uint64_t runs = 0;
     // a render that was enqueued (mesh_run_begin) and not yet finished (mesh_run_end)
     bool pending = false, pend_graph = false, pend_emitted = false;
@@ -604,7 +631,7 @@ int mesh_run_end(gsdf_mesher *m);
 int mesh_run_begin(gsdf_mesher *m) {
     if (m->pending) { int erc = mesh_run_end(m); if (erc) return erc; }
     gsdf_program *p = m->prog;
-    CU(cudaSetDevice(p->device));
+    CU(use_device(p->device));
     cudaStream_t st = p->stream;
     if (m->copy_stream) CU(cudaStreamSynchronize(m->copy_stream));  // an earlier async read may still use d_tris
     const MeshDims &D = m->D;
@@ -670,8 +697,12 @@ int mesh_run_begin(gsdf_mesher *m) {
     static const bool scan3 = getenv("GSDF_SCAN3") != nullptr;  // A/B: the three-kernel scan
 
     // The launch sequence of one render. stage_events: record the per-stage timing events (eager path only).
+    // Programmatic dependent launch between the kernels of the render: every kernel but the first carries the
+    // attribute. Stage-timed renders keep plain launches (an event record between two kernels breaks the chain anyway).
+    static const bool pdl_on = !(getenv("GSDF_PDL") != nullptr && getenv("GSDF_PDL")[0] == '0');  // default on; GSDF_PDL=0 is the A/B switch
     auto enqueue = [&](bool stage_events, uint32_t epoch) -> int {
     int rc = 0;
+    const bool pdl = pdl_on && !stage_events && !scan3 && !(m->flags & GSDF_MESH_KEEP_GRID);
     if (m->flags & GSDF_MESH_KEEP_GRID) CU(cudaMemsetAsync(m->d_grid, 0x7f, (size_t)D.pitch * (D.ny + 1) * nk * sizeof(float), st));
     // counters and look-back scan state are already zero: re-armed by the previous render's k_finish_render (or by the allocation)
     if (prune) {
@@ -684,21 +715,22 @@ int mesh_run_begin(gsdf_mesher *m) {
         gc.nwx = D.nwx; gc.bits = m->d_mbits; gc.kept = m->d_ctr + 4;
         if ((rc = launch_eval<1>(p, gc, (uint64_t)D.nwx * 32u * D.nby * D.nbz, st))) return rc;
         const uint64_t ncrows = (uint64_t)(D.ny + 1) * nk;
-        k_compact_quads<<<grid_for(ncrows, kThreads / 32), kThreads, 0, st>>>(D, m->d_mbits, m->d_list, m->d_ctr + 0);
+        CU(launch_chain(pdl, k_compact_quads, dim3(grid_for(ncrows, kThreads / 32)), dim3(kThreads), 0, st, D, (const uint32_t *)m->d_mbits, m->d_list, m->d_ctr + 0));
         CU(cudaGetLastError());
     }
     if (stage_events) CU(cudaEventRecord(m->ev[1], st));
     {
         GenGrid<4> g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
         // with a device-side list length the launch is sized for the worst case; surplus CTAs find no tile and exit
-        if ((rc = launch_eval<4>(p, g, nquads, st))) return rc;
+        if ((rc = launch_eval<4>(p, g, nquads, st, pdl && prune))) return rc;
     }
     if (stage_events) CU(cudaEventRecord(m->ev[2], st));
     if (m->use_tma) {
         const uint64_t ntiles = (uint64_t)((D.nsx + 3) / 4) * ((D.ny + kTileY - 1) / kTileY) * (D.cz1 - D.cz0);
-        k_mc_count_tma<<<grid_for(ntiles, 1, 16), 256, 0, st>>>(m->tmap, A);
+        static const bool count_v1 = getenv("GSDF_COUNT_V1") != nullptr;  // A/B switch: one cell per lane
+        CU(launch_chain(pdl, count_v1 ? k_mc_count_tma : k_mc_count_tma4, dim3(grid_for(ntiles, 1, 16)), dim3(256), 0, st, m->tmap, A));
     } else {
-        k_mc_count<<<mcgrid, kThreads, 0, st>>>(A);
+        CU(launch_chain(pdl, k_mc_count, dim3(mcgrid), dim3(kThreads), 0, st, A));
     }
     CU(cudaGetLastError());
     if (scan3) {
@@ -709,20 +741,21 @@ int mesh_run_begin(gsdf_mesher *m) {
         k_scan_apply<<<(unsigned)nscanblocks, kThreads, 0, st>>>(m->d_seg, nseg, m->d_blocksum);
         CU(cudaGetLastError());
     } else {
-        k_scan_lookback<<<(unsigned)nscantiles, kThreads, 0, st>>>(m->d_seg, (uint32_t)nseg, m->d_scanstate, m->d_ctr + 6, epoch,
-                                                               reinterpret_cast<unsigned long long *>(m->d_ctr + 2));
+        CU(launch_chain(pdl, k_scan_lookback, dim3((unsigned)nscantiles), dim3(kThreads), 0, st, m->d_seg, (uint32_t)nseg, m->d_scanstate, m->d_ctr + 6, epoch,
+                        reinterpret_cast<unsigned long long *>(m->d_ctr + 2)));
         CU(cudaGetLastError());
     }
     if (stage_events) CU(cudaEventRecord(m->ev[3], st));
     if (emitted) {
         MCArgs E = A;
         E.cases = nullptr;
-        k_mc_emit<<<mcgrid, kThreads, 0, st>>>(E);
+        CU(launch_chain(pdl, k_mc_emit, dim3(mcgrid), dim3(kThreads), 0, st, E));
         CU(cudaGetLastError());
     }
     {   // publish the counters (cudaMallocHost memory is device-mapped under UVA) and re-arm the state for the next render
         const uint32_t nstate = (uint32_t)nscantiles;
-        k_finish_render<<<(unsigned)std::min<uint64_t>(std::max<uint64_t>((nstate + 255) / 256, 1), 64), 256, 0, st>>>(m->d_ctr, m->h_ctr, 8, m->d_scanstate, nstate);
+        CU(launch_chain(pdl, k_finish_render, dim3((unsigned)std::min<uint64_t>(std::max<uint64_t>((nstate + 255) / 256, 1), 64)), dim3(256), 0, st,
+                        m->d_ctr, (volatile uint32_t *)m->h_ctr, 8, m->d_scanstate, nstate));
         CU(cudaGetLastError());
     }
     return rc;
@@ -773,7 +806,7 @@ int mesh_run_end(gsdf_mesher *m) {
     if (!m->pending) return 0;
     m->pending = false;
     gsdf_program *p = m->prog;
-    CU(cudaSetDevice(p->device));
+    CU(use_device(p->device));
     cudaStream_t st = p->stream;
     const MeshDims &D = m->D;
     const bool prune = (m->flags & GSDF_MESH_PRUNE) != 0;
@@ -832,9 +865,10 @@ int gsdf_mesh_begin(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, 
     if (cz0 < 0 || cz1 > lat->n[2] || cz0 >= cz1) return fail(GSDF_EINVAL, "bad cell slab [%d,%d)", cz0, cz1);
     int rc = ensure_device();
     if (rc) return rc;
-    CU(cudaSetDevice(p->device));
+    CU(use_device(p->device));
     gsdf_mesher *m = new gsdf_mesher();
     m->prog = p;
+    m->device = p->device;
     m->lat = *lat;
     m->flags = flags;
     m->use_tma = getenv("GSDF_NO_TMA") == nullptr;  // A/B switch for the classification kernel
@@ -878,7 +912,7 @@ int gsdf_mesh_rerun_end(gsdf_mesher *m) {
 
 int64_t gsdf_mesh_read_prefix_async(gsdf_mesher *m, float *tri9, size_t ntris) {
     if (!m || (!tri9 && ntris)) return fail(GSDF_EINVAL, "gsdf_mesh_read_prefix_async: NULL argument");
-    CU(cudaSetDevice(m->prog->device));
+    CU(use_device(m->prog->device));
     const uint64_t n = std::min<uint64_t>(ntris, m->tri_cap / 9);
     if (n == 0) return 0;
     CU(cudaStreamWaitEvent(m->copy_stream, m->ev[4], 0));  // after the emit of the render enqueued last
@@ -898,7 +932,7 @@ int64_t gsdf_mesh_read(gsdf_mesher *m, float *tri9, size_t max_tris) {
     if (!m || !tri9) return fail(GSDF_EINVAL, "gsdf_mesh_read: NULL argument");
     if (m->pending) { const int erc = mesh_run_end(m); if (erc) return erc; }
     if (max_tris < 5) return fail(GSDF_ESHORT, "short buffer");  // flatrenderer.go:187
-    CU(cudaSetDevice(m->prog->device));
+    CU(use_device(m->prog->device));
     const uint64_t left = m->ntri - m->read_pos;
     const uint64_t n = std::min<uint64_t>(left, max_tris);
     if (n == 0) return 0;  // io.EOF
@@ -911,7 +945,7 @@ int64_t gsdf_mesh_read_async(gsdf_mesher *m, float *tri9, size_t max_tris) {
     if (!m || !tri9) return fail(GSDF_EINVAL, "gsdf_mesh_read_async: NULL argument");
     if (m->pending) { const int erc = mesh_run_end(m); if (erc) return erc; }
     if (max_tris < 5) return fail(GSDF_ESHORT, "short buffer");
-    CU(cudaSetDevice(m->prog->device));
+    CU(use_device(m->prog->device));
     const uint64_t left = m->ntri - m->read_pos;
     const uint64_t n = std::min<uint64_t>(left, max_tris);
     if (n == 0) return 0;
@@ -923,7 +957,7 @@ int64_t gsdf_mesh_read_async(gsdf_mesher *m, float *tri9, size_t max_tris) {
 
 int gsdf_mesh_wait(gsdf_mesher *m) {
     if (!m) return fail(GSDF_EINVAL, "gsdf_mesh_wait: NULL mesher");
-    CU(cudaSetDevice(m->prog->device));
+    CU(use_device(m->prog->device));
     CU(cudaStreamSynchronize(m->copy_stream));
     return 0;
 }
@@ -951,7 +985,7 @@ int gsdf_mesh_cases(gsdf_mesher *m, uint8_t *cases, size_t nbytes) {
     if (!(m->flags & GSDF_MESH_KEEP_CASES)) return fail(GSDF_EINVAL, "mesher was not created with GSDF_MESH_KEEP_CASES");
     const size_t need = (size_t)m->D.nx * m->D.ny * (m->D.cz1 - m->D.cz0);
     if (nbytes != need) return fail(GSDF_ELEN, "cases buffer must be %zu bytes", need);
-    CU(cudaSetDevice(m->prog->device));
+    CU(use_device(m->prog->device));
     CU(cudaMemcpy(cases, m->d_cases, need, cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -963,7 +997,7 @@ int gsdf_mesh_grid(gsdf_mesher *m, float *grid, size_t nfloats) {
     const MeshDims &D = m->D;
     const size_t rows = (size_t)(D.ny + 1) * (D.cz1 - D.cz0 + 1);
     if (nfloats != rows * (D.nx + 1)) return fail(GSDF_ELEN, "grid buffer must be %zu floats", rows * (D.nx + 1));
-    CU(cudaSetDevice(m->prog->device));
+    CU(use_device(m->prog->device));
     CU(cudaMemcpy2D(grid, (size_t)(D.nx + 1) * 4, m->d_grid, (size_t)D.pitch * 4, (size_t)(D.nx + 1) * 4, rows, cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -977,7 +1011,7 @@ int gsdf_mesh_timings(const gsdf_mesher *m, float ms[5]) {
 
 void gsdf_mesh_destroy(gsdf_mesher *m) {
     if (!m) return;
-    if (m->prog) cudaSetDevice(m->prog->device);
+    cudaSetDevice(m->device);
     cudaFree(m->d_grid); cudaFree(m->d_mbits); cudaFree(m->d_list); cudaFree(m->d_seg); cudaFree(m->d_seglist); cudaFree(m->d_segcases); cudaFree(m->d_scanstate); cudaFree(m->d_blocksum);
     cudaFree(m->d_tris); cudaFree(m->d_cases); cudaFree(m->d_stl); cudaFree(m->d_ctr);
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
@@ -985,6 +1019,7 @@ void gsdf_mesh_destroy(gsdf_mesher *m) {
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->gexec) cudaGraphExecDestroy(m->gexec);
     delete m;
+    (void)cudaGetLastError();  // teardown never leaves a stale (non-sticky) error behind for the next launch check
 }
 
 }  // extern "C"
@@ -1061,7 +1096,7 @@ int dc_scan(gsdf_dualcontour *d, uint32_t *data, uint32_t n, cudaStream_t st) {
 
 int dc_run(gsdf_dualcontour *d) {
     gsdf_program *p = d->prog;
-    CU(cudaSetDevice(p->device));
+    CU(use_device(p->device));
     cudaStream_t st = p->stream;
     const DCGrid &G = d->G;
     int rc;
@@ -1191,7 +1226,7 @@ int gsdf_dc_begin_part(gsdf_program *p, const float bbmin[3], const float bbmax[
     if (levels > 11) return fail(GSDF_EINVAL, "dual contour octree has %d levels (%d^3 cubes); limit is 11 levels", levels, 1 << (levels - 1));
     int rc = ensure_device();
     if (rc) return rc;
-    CU(cudaSetDevice(p->device));
+    CU(use_device(p->device));
     gsdf_dualcontour *d = new gsdf_dualcontour();
     d->prog = p;
     d->device = p->device;
@@ -1218,7 +1253,7 @@ int gsdf_dc_rerun(gsdf_dualcontour *d) {
 
 int64_t gsdf_dc_read(gsdf_dualcontour *d, float *tri9, size_t max_tris) {
     if (!d || (!tri9 && max_tris)) return fail(GSDF_EINVAL, "gsdf_dc_read: NULL argument");
-    CU(cudaSetDevice(d->prog->device));
+    CU(use_device(d->prog->device));
     const uint64_t n = std::min<uint64_t>(d->ntri, max_tris);
     if (n) CU(cudaMemcpy(tri9, d->d_tris, n * 9 * sizeof(float), cudaMemcpyDeviceToHost));
     return (int64_t)n;
@@ -1246,6 +1281,7 @@ void gsdf_dc_destroy(gsdf_dualcontour *d) {
     if (d->h_ctr) cudaFreeHost(d->h_ctr);
     for (auto &e : d->ev) if (e) cudaEventDestroy(e);
     delete d;
+    (void)cudaGetLastError();
 }
 
 }  // extern "C"
@@ -1275,7 +1311,7 @@ static int64_t stl_from_device(const float *d_tri9, uint64_t n, uint8_t *&d_stl,
 int64_t gsdf_mesh_stl(gsdf_mesher *m, void *dst, size_t dst_bytes) {
     if (!m) return fail(GSDF_EINVAL, "NULL mesher");
     if (m->pending) return fail(GSDF_EINVAL, "a render is in flight on this mesher: call gsdf_mesh_rerun_end first");
-    CU(cudaSetDevice(m->prog->device));
+    CU(use_device(m->prog->device));
     return stl_from_device(m->d_tris, m->ntri, m->d_stl, m->stl_cap, dst, dst_bytes, m->prog->stream);
 }
 

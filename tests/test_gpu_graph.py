@@ -179,3 +179,16 @@ def test_empty_and_tiny_meshes(oracle, bld):
                 mask, _ = oracle.octree_prune_mask(t, lat)
                 wp, _ = oracle.flat_march(lat, grid, blockmask=mask)
                 assert np.array_equal(got.view(np.uint32), wp.view(np.uint32)), res
+
+
+def test_programmatic_dependent_launch_is_bit_identical():
+    """The kernels of a render are chained by programmatic dependent launch (kernels.cuh pdl_trigger / pdl_wait; GSDF_PDL=0
+    switches it off). The switch is read once per process, so the check runs in children: graph replays, eager renders
+    and the 3-slab pipeline, with and without the programmatic edges, against stage-timed renders, which always use plain
+    launches (scripts/check_pdl.py)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for pdl in ("1", "0"):
+        env = dict(os.environ, GSDF_PDL=pdl)
+        r = subprocess.run([sys.executable, os.path.join(root, "scripts", "check_pdl.py")], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "PDL CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
