@@ -645,7 +645,7 @@ int mesh_run_begin(gsdf_mesher *m) {
     int rc;
     if ((rc = grow(m->d_grid, m->grid_cap, (size_t)D.pitch * (D.ny + 1) * nk))) return rc;
     const uint64_t nseg = nrows * (uint64_t)D.nsx;
-    if (nseg >= 0xffffffffull) return fail(GSDF_EINVAL, "slab too large: %llu cell segments (limit 2^32); use more Z-slabs", (unsigned long long)nseg);
+    if (nseg >= 0xfff00000ull) return fail(GSDF_EINVAL, "slab too large: %llu cell segments (limit 2^32 - 2^20: grid-stride counters are 32-bit); use more Z-slabs", (unsigned long long)nseg);
     if ((rc = grow(m->d_seg, m->seg_cap, (size_t)nseg))) return rc;
     if ((rc = grow(m->d_seglist, m->seglist_cap, (size_t)nseg))) return rc;
     static const bool pre_classified = getenv("GSDF_EMIT_RECLASSIFY") == nullptr;  // A/B switch: pass 2 classifies again
@@ -727,8 +727,12 @@ int mesh_run_begin(gsdf_mesher *m) {
     if (stage_events) CU(cudaEventRecord(m->ev[2], st));
     if (m->use_tma) {
         const uint64_t ntiles = (uint64_t)((D.nsx + 3) / 4) * ((D.ny + kTileY - 1) / kTileY) * (D.cz1 - D.cz0);
-        static const bool count_v1 = getenv("GSDF_COUNT_V1") != nullptr;  // A/B switch: one cell per lane
-        CU(launch_chain(pdl, count_v1 ? k_mc_count_tma : k_mc_count_tma4, dim3(grid_for(ntiles, 1, 16)), dim3(256), 0, st, m->tmap, A));
+        static const bool count_v1 = getenv("GSDF_COUNT_V1") != nullptr;  // A/B switch: one cell per lane, no prefetch
+        // test knob: cap the grid so that small, oracle-checked lattices run many tiles per CTA through both stencil buffers
+        static const unsigned count_grid_cap = getenv("GSDF_COUNT_GRID") ? (unsigned)std::max(1, atoi(getenv("GSDF_COUNT_GRID"))) : 0u;
+        unsigned cgrid = grid_for(ntiles, 1, 16);
+        if (count_grid_cap) cgrid = std::min(cgrid, count_grid_cap);
+        CU(launch_chain(pdl, count_v1 ? k_mc_count_tma : k_mc_count_tma4, dim3(cgrid), dim3(256), 0, st, m->tmap, A));
     } else {
         CU(launch_chain(pdl, k_mc_count, dim3(mcgrid), dim3(kThreads), 0, st, A));
     }

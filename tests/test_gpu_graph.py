@@ -192,3 +192,16 @@ def test_programmatic_dependent_launch_is_bit_identical():
         env = dict(os.environ, GSDF_PDL=pdl)
         r = subprocess.run([sys.executable, os.path.join(root, "scripts", "check_pdl.py")], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "PDL CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("cap", ["3", "37"])
+def test_count_kernel_tile_loop_matches_oracle(cap):
+    """On the small lattices the oracle can mesh, the classification kernel's default grid gives every CTA one tile, so
+    its tile loop (mbarrier phase flips, stencil buffer reuse, kept and pruned tiles in any order) would only be checked
+    against known triangle COUNTS at full size. The child caps the grid (GSDF_COUNT_GRID, read once per process): each
+    CTA then walks tens of tiles, and cases and triangles are compared with the oracle (tests/count_pipeline_child.py)."""
+    import os, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, GSDF_COUNT_GRID=cap)
+    r = subprocess.run([sys.executable, os.path.join(here, "count_pipeline_child.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "COUNT PIPELINE OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
