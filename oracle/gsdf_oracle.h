@@ -124,6 +124,8 @@ int go_mc_cube(const float p[24], const float v[8], float tri9[45], int *case_in
 /* ---- dual contouring (gsdf_oracle_dc.c): glrender/dual_contour.go + dual_contour_vertexplacement.go ---- */
 /* makeICube on Bounds().Add(-res/2) (dual_contour.go:31-34): level count (<0 = resolution too coarse) and octree origin. */
 int go_dc_levels(const float bbmin[3], const float bbmax[3], float res, float origin[3]);
+/* leastSquaresMGS64 (dual_contour_vertexplacement.go:148-223) on K <= 32 rows; A is K x 3 row-major */
+int go_lsq_mgs64(int K, const float *A_rowmajor, const float *b, float x3[3]);
 /* DualContourRenderer.Reset + RenderAll. placer: 0 DualContourNaive (dual_contour_test.go:355), 1 DualContourLeastSquares{},
  * 2 DualContourLeastSquares{Chiseled:true}. Returns the triangle count (only the first max_tris are stored) or <0.
  * stats (optional): {levels, cubes kept, cubes with neighbours, evaluations}. */

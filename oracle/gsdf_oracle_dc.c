@@ -107,6 +107,14 @@ static void lsq_mgs64(int K, float A[][3], const float *b, float x3[3]) {
     }
     for (int c = 0; c < 3; c++) x3[c] = (float)x[c];
 }
+/* exported for the known-answer tests (dual_contour_test.go:20-137 state two QEF systems with known solutions) */
+int go_lsq_mgs64(int K, const float *A_rowmajor, const float *b, float x3[3]) {
+    if (K < 0 || K > 32) return -1;
+    float A[32][3];
+    for (int k = 0; k < K; k++) for (int c = 0; c < 3; c++) A[k][c] = A_rowmajor[3 * k + c];
+    lsq_mgs64(K, A, b, x3);
+    return 0;
+}
 static float clampf_(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 /* placer: 0 = DualContourNaive, 1 = DualContourLeastSquares{}, 2 = DualContourLeastSquares{Chiseled: true}.

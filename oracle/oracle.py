@@ -118,6 +118,8 @@ def lib():
         L.go_dual_contour.argtypes = [C.POINTER(GoTree), f32p, f32p, C.c_float, C.c_int, vp, C.c_int64, C.POINTER(C.c_int64)]
         L.go_dual_contour_ex.restype = C.c_int64
         L.go_dual_contour_ex.argtypes = [C.POINTER(GoTree), f32p, f32p, C.c_float, C.c_int, vp, C.c_int64, C.POINTER(C.c_int64), vp]
+        L.go_lsq_mgs64.restype = C.c_int
+        L.go_lsq_mgs64.argtypes = [C.c_int, f32p, f32p, f32p]
         L.go_mc_edge_table.restype = C.POINTER(C.c_int)
         L.go_mc_tri_table.restype = C.POINTER(C.c_int8)
         L.go_mc_pair_table.restype = C.POINTER(C.c_int)
@@ -196,6 +198,20 @@ def dual_contour(tree, bbmin, bbmax, res, placer=DC_LSQ):
     tris = np.empty((max(n, 1), 3, 3), dtype=np.float32)
     lib().go_dual_contour(C.byref(tree.c), a, b, float(res), placer, tris.ctypes.data, n, st)
     return tris[:n], dict(levels=st[0], cubes=st[1], with_neighbors=st[2], evals=st[3])
+
+
+def lsq_mgs64(A, b):
+    """leastSquaresMGS64 (dual_contour_vertexplacement.go:148-223): float64 modified Gram-Schmidt solve of the K x 3
+    system A x = b given in float32; returns x as float32[3]."""
+    A = np.ascontiguousarray(A, dtype=np.float32).reshape(-1, 3)
+    b = np.ascontiguousarray(b, dtype=np.float32).reshape(-1)
+    assert len(A) == len(b)
+    x = np.zeros(3, dtype=np.float32)
+    f32p = C.POINTER(C.c_float)
+    rc = lib().go_lsq_mgs64(len(A), A.ctypes.data_as(f32p), b.ctypes.data_as(f32p), x.ctypes.data_as(f32p))
+    if rc != 0:
+        raise RuntimeError("oracle go_lsq_mgs64: too many rows")
+    return x
 
 
 def dual_contour_quad_keys(tree, bbmin, bbmax, res, placer=DC_LSQ):

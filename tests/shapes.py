@@ -175,6 +175,35 @@ def scenes3d(bld):
             ("knurled-cylinder", gsdf.scene(bld, "knurled-cylinder"))]
 
 
+def geb(bld, share=True):
+    """TestTransformDuplicateBug (gsdf_test.go:90-133): three extruded, non-uniformly scaled, offset letters, each used
+    TWICE (a DAG, not a tree) under rotations and intersections. share=False builds the same shape from separately
+    constructed, identical nodes."""
+    def letter():
+        s3 = bld.Extrude(bld.NewCircle(1), 1.0)
+        s3 = bld.Transform(s3, [[1.2, 0, 0, 0], [0, 1.3, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])  # ms3.ScalingMat4({1.2, 1.3, 1})
+        return bld.Offset(s3, -0.025)
+    if share:
+        G3, E3, B3 = letter(), letter(), letter()
+        g, e, b = (lambda: G3), (lambda: E3), (lambda: B3)
+    else:
+        g = e = b = letter
+    deg90 = math.pi / 2
+    geb1 = bld.Intersection(bld.Intersection(g(), bld.Rotate(e(), deg90, (0, 1, 0))), bld.Rotate(b(), -deg90, (1, 0, 0)))
+    geb2 = bld.Intersection(bld.Intersection(e(), bld.Rotate(g(), deg90, (0, 1, 0))), bld.Rotate(b(), -deg90, (1, 0, 0)))
+    mn, mx = geb2.Bounds()
+    geb2 = bld.Translate(geb2, 0, 0, float((mx - mn)[2] * np.float32(1.5)))
+    return bld.Union(geb1, geb2)
+
+
+def dag3d(bld):
+    """Shapes whose nodes are shared between several parents."""
+    s = bld.NewBox(1, 0.6, 0.8, 0.1)
+    twice = bld.Union(bld.Translate(s, 1.2, 0, 0), bld.Rotate(s, 0.8, (0, 0, 1)), bld.Scale(s, 0.5))
+    return [("geb_shared", geb(bld, True)), ("shared_box_union", twice),
+            ("shared_smooth", bld.SmoothUnion(0.2, twice, bld.Translate(twice, 0, 0, 0.9)))]
+
+
 def all3d(bld):
     return primitives3d(bld) + binops3d(bld) + unary3d(bld) + threads3d(bld) + scenes3d(bld) + guards3d(bld)
 

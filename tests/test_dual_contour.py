@@ -34,6 +34,36 @@ SHAPES = {
 
 
 # ---------------------------------------------------------------------------------------------- oracle (CPU)
+def _qef_rows(points, normals, origin, lam):
+    """The system DualContourLeastSquares hands to leastSquaresMGS64 (dual_contour_vertexplacement.go:107-133): one row
+    n_i . x = n_i . (p_i - origin) per plane plus three regularisation rows sqrt(lam) * (x - bias)."""
+    p = np.asarray(points, np.float32) - np.asarray(origin, np.float32)
+    n = np.asarray(normals, np.float32)
+    n = n / np.linalg.norm(n, axis=1, keepdims=True).astype(np.float32)
+    sl = np.float32(np.sqrt(lam))
+    bias = p.mean(axis=0, dtype=np.float32)
+    A = np.concatenate([n, sl * np.eye(3, dtype=np.float32)])
+    b = np.concatenate([(n * p).sum(axis=1, dtype=np.float32), sl * bias])
+    return A.astype(np.float32), b.astype(np.float32)
+
+
+def test_qef_solver_known_answers(oracle):
+    """TestQEFSolver / TestQEFSolverDiagonalPlanes (dual_contour_test.go:20-137): three orthogonal planes meet at
+    (0.5, 0.5, 0.5) (tolerance 1e-4, lambda 1e-6); three diagonal planes through (1, 1, 1) seen from the cube origin
+    (0.5, 0.5, 0.5) (tolerance 1e-3, lambda 1e-8). The reference test solves the normal equations by a 3x3 inverse;
+    the renderer's own solver is leastSquaresMGS64, restated in the oracle -- both must find the same points."""
+    A, b = _qef_rows([[0.5, 0, 0], [0, 0.5, 0], [0, 0, 0.5]], [[1, 0, 0], [0, 1, 0], [0, 0, 1]], [0, 0, 0], 1e-6)
+    x = oracle.lsq_mgs64(A, b)
+    assert np.abs(x - np.float32(0.5)).max() < 1e-4
+    org = np.array([0.5, 0.5, 0.5], np.float32)
+    A, b = _qef_rows([[1, 1, 1]] * 3, [[1, 1, 0], [0, 1, 1], [1, 0, 1]], org, 1e-8)
+    x = oracle.lsq_mgs64(A, b) + org
+    assert np.abs(x - np.float32(1.0)).max() < 1e-3
+    # fewer than three rows: the zero vector (dual_contour_vertexplacement.go:151-153); rank-deficient columns are zeroed
+    assert np.array_equal(oracle.lsq_mgs64(A[:2], b[:2]), np.zeros(3, np.float32))
+    x = oracle.lsq_mgs64([[1, 0, 0], [1, 0, 0], [0, 1, 0]], [2, 2, 3])
+    assert np.allclose(x, [2, 3, 0], atol=1e-6)
+
 def test_sphere_vertices_on_surface(oracle, bld):
     """TestDualContourSphereVerticesOnSurface (dual_contour_test.go:140-221): r=1, res=r/8."""
     s = bld.NewSphere(1.0)

@@ -44,7 +44,7 @@ def check_field(name, s, oracle, pos):
 
 
 # ---------------------------------------------------------------------------------------------- Evaluate parity
-@pytest.mark.parametrize("corpus", ["primitives3d", "binops3d", "unary3d", "threads3d", "scenes3d", "guards3d",
+@pytest.mark.parametrize("corpus", ["primitives3d", "binops3d", "unary3d", "threads3d", "scenes3d", "guards3d", "dag3d",
                                     "primitives2d", "binops2d", "unary2d", "threads2d"])
 def test_evaluate_matches_oracle_on_reference_lattices(oracle, bld, corpus):
     """testShader3D/testShader2D (gsdf_test.go:429-525): sample the AppendGrid lattice of Bounds()."""

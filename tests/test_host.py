@@ -185,6 +185,21 @@ def test_random_trees_flatten_within_stack_limits(oracle, bld):
             assert np.isfinite(d).all(), name
 
 
+def test_shared_subtrees_flatten_like_duplicated_ones(oracle, bld):
+    """TestTransformDuplicateBug (gsdf_test.go:90-133): a node reachable through several parents (a DAG) must behave like
+    separate identical nodes -- same program bytes, same oracle field."""
+    import shapes
+    a, b = shapes.geb(bld, True), shapes.geb(bld, False)
+    fa, fb = bld.flatten(a), bld.flatten(b)
+    assert fa["blob"] == fb["blob"] and np.array_equal(fa["aux"], fb["aux"])
+    assert np.array_equal(a.Bounds()[0], b.Bounds()[0]) and np.array_equal(a.Bounds()[1], b.Bounds()[1])
+    pos = shapes.sample_points(a)
+    da, db = oracle.Tree.from_shader(a).eval3(pos), oracle.Tree.from_shader(b).eval3(pos)
+    assert np.array_equal(da.view(np.uint32), db.view(np.uint32)) and (da < 0).any() and (da > 0).any()
+    for name, s in shapes.dag3d(bld):
+        assert np.isfinite(oracle.Tree.from_shader(s).eval3(shapes.sample_points(s))).all(), name
+
+
 def test_position_liveness(bld):
     """A transform whose position nobody reads again must not save it: scale(translate(sphere)) needs no P slots,
     union(translate(a), b) needs one."""
