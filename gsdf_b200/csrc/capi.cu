@@ -638,7 +638,6 @@ int mesh_run_begin(gsdf_mesher *m) {
     const bool prune = (m->flags & GSDF_MESH_PRUNE) != 0;
     const int nk = D.cz1 - D.cz0 + 1;
     const uint64_t nquads = (uint64_t)D.nqx * (D.ny + 1) * nk;
-    const uint64_t nblocks = (uint64_t)D.nbx * D.nby * D.nbz;
     const uint64_t nrows = (uint64_t)D.ny * (D.cz1 - D.cz0);
     const uint64_t ncells = nrows * D.nx;
     if (nquads >= 0xffffffffull) return fail(GSDF_EINVAL, "slab too large: %llu lattice quads (limit 2^32); use more Z-slabs", (unsigned long long)nquads);

@@ -16,7 +16,6 @@ namespace gsdfhost {
 
 namespace {
 
-constexpr double kTribisect = 0.8660254037844386467637231707529361834714026269051903140279034897;
 constexpr double kSqrt3 = 1.7320508075688772935274463415058723669428052538103806280558069794;
 
 inline uint32_t fbits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }

@@ -135,6 +135,19 @@ def test_resolution_errors(oracle, bld):
     assert oracle.lib().go_dc_levels(a, b, 0.125, None) == 5
 
 
+def test_dual_render_bolt(oracle, bld):
+    """TestDualRender (glrender_test.go:22-53): the rotated M3 bolt at res 0.5 through DualContourLeastSquares gives a
+    non-empty mesh that survives the STL writer; quads come as triangle pairs."""
+    s = gsdf.scene(bld, "bolt")
+    t = oracle.Tree.from_shader(s)
+    tris, st = oracle.dual_contour(t, *s.Bounds(), np.float32(0.5), oracle.DC_LSQ)
+    assert len(tris) > 0 and len(tris) % 2 == 0 and np.isfinite(tris).all()
+    mn, mx = s.Bounds()
+    assert (tris.reshape(-1, 3) >= mn - 1.0).all() and (tris.reshape(-1, 3) <= mx + 1.0).all()
+    stl = oracle.stl_write(tris)
+    assert len(stl) == 84 + 50 * len(tris)
+
+
 # ---------------------------------------------------------------------------------------------- CUDA (GPU)
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape,res", [("sphere", 1.0 / 8), ("sphere", 1.0 / 6), ("box", 2.0 / 8), ("snowman", 3.0 / 64)])
