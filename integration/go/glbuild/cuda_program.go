@@ -9,6 +9,7 @@ package glbuild
 import (
 	"errors"
 	"fmt"
+	"os"
 	"unsafe"
 
 	math "github.com/chewxy/math32"
@@ -75,6 +76,61 @@ const (
 	polyEdgeFloats = 8
 )
 
+// Slab guards (include/gsdf_program.h, "slab guards"; gsdf_b200/csrc/host/flatten.cpp is the executable specification).
+// An extrusion or screw returns a value >= w = |z| - h/2 in its own frame, and its ENTER op has w in hand before any of the
+// 2-D work below it. When such a node is the LATER operand of a difference, union or smooth union -- directly or through
+// nodes that only move p -- the combiner hands it a guard: if the combiner's result cannot depend on any value >= w for
+// every point of the CTA's tile, the interpreter jumps behind the node's exit op. Results are bit-identical either way.
+const (
+	GuardNone uint32 = iota
+	GuardDiff        // a = top:  -w < a             =>  max(a, -s) == a
+	GuardMin         // a = top:   w > a             =>  min(a, s)  == a
+	GuardSmoothUnion // a = top:   w - a >= k, a != 0 =>  the blend returns a
+)
+
+// Guard is what a combiner hands down to a later operand.
+type Guard struct {
+	Kind uint32
+	K    float32 // smooth-union radius
+}
+
+// SlabBoundedNode is implemented by the node types whose value is bounded below by |z| - h/2 of their own frame and whose
+// ENTER op evaluates the guard: gsdf.extrusion and threads.screw.
+type SlabBoundedNode interface{ SlabBounded() }
+
+// DistTransparentNode is implemented by the node types whose Evaluate forwards the child's distance unchanged and only
+// moves p (translate, transform, symmetry, twist): a guard passes through them to their child.
+type DistTransparentNode interface{ DistTransparentChild() Shader }
+
+// guardsOff mirrors the C++ flattener's A/B switch.
+var guardsOff = func() bool { e := os.Getenv("GSDF_NO_GUARDS"); return e != "" && e[0] != '0' }()
+
+func unwrapAll(s Shader) Shader {
+	for {
+		u := Unwrap(s)
+		if u == nil {
+			return s
+		}
+		s = u
+	}
+}
+
+// Guardable reports whether s is an extrusion / screw reached through distance-transparent nodes (and wrappers) only.
+func Guardable(s Shader) bool {
+	for s != nil {
+		s = unwrapAll(s)
+		if _, ok := s.(SlabBoundedNode); ok {
+			return true
+		}
+		t, ok := s.(DistTransparentNode)
+		if !ok {
+			return false
+		}
+		s = t.DistTransparentChild()
+	}
+	return false
+}
+
 // Program accumulates the instruction chunks (4 x uint32 each) and the float side buffer.
 type Program struct {
 	Chunks       []uint32
@@ -83,6 +139,30 @@ type Program struct {
 	D, P         int // current distance / position stack depth
 	Dmax, Pmax   int
 	ninstr       int
+	pending      Guard // set by a combiner right before it emits a guardable operand, taken by that operand's ENTER op
+}
+
+// GuardFor returns the guard a combiner of the given kind may hand to `child` (none if the child is not guardable).
+func (p *Program) GuardFor(child Shader, kind uint32, k float32) Guard {
+	if p.Dim == 3 && !guardsOff && Guardable(child) {
+		return Guard{Kind: kind, K: k}
+	}
+	return Guard{}
+}
+
+// SetGuard arms the guard for the operand emitted next. Guardable(child) guarantees that the chain of emitters below
+// consists of distance-transparent nodes, which leave it alone, and ends in a SlabBoundedNode, which takes it.
+func (p *Program) SetGuard(g Guard) { p.pending = g }
+
+// TakeGuard is called by extrusion / screw at the start of their emitter.
+func (p *Program) TakeGuard() Guard { g := p.pending; p.pending = Guard{}; return g }
+
+// PatchGuard stores kind | target<<8 into word 1 of the ENTER header at chunk word index hw; the target is the chunk
+// right behind the node's own exit op (the restoring POP_POS ops of its wrappers follow and still run).
+func (p *Program) PatchGuard(hw int, g Guard) {
+	if g.Kind != GuardNone {
+		p.Chunks[hw+1] = g.Kind | uint32(len(p.Chunks)/4)<<8
+	}
 }
 
 // ProgramEmitter is implemented by every node type of gsdf and forge/threads (their cuda_flatten.go files).
@@ -157,8 +237,16 @@ func (p *Program) Unary(child Shader, restore bool, enter, exit func()) error {
 }
 
 func (p *Program) Binary(a, b Shader, restore bool, emitOp func()) error {
+	return p.BinaryGuarded(a, b, restore, GuardNone, 0, emitOp)
+}
+
+// BinaryGuarded is Binary for the combiners that can guard their second operand (difference, smooth union).
+func (p *Program) BinaryGuarded(a, b Shader, restore bool, kind uint32, k float32, emitOp func()) error {
 	if err := Emit(p, a, true); err != nil { // the first operand must leave p intact for the second
 		return err
+	}
+	if kind != GuardNone {
+		p.SetGuard(p.GuardFor(b, kind, k))
 	}
 	if err := Emit(p, b, restore); err != nil {
 		return err

@@ -13,6 +13,8 @@ import (
 	"github.com/soypat/gsdf/glbuild"
 )
 
+func fbits(f float32) uint32 { return math.Float32bits(f) }
+
 // ---------------------------------------------------------------------------------------------- 3D primitives
 
 func (s *sphere) AppendProgram(p *glbuild.Program, _ bool) error { p.Opf(glbuild.OpSphere, s.r, 0); p.PushD(); return nil }
@@ -59,9 +61,26 @@ func (u *OpUnion) AppendProgram(p *glbuild.Program, restore bool) error {
 	if len(u.joined) < 2 {
 		return errors.New("OpUnion must have at least 2 elements") // operations.go:110-114
 	}
-	for k := range u.joined {
-		last := k == len(u.joined)-1
-		if err := glbuild.Emit(p, u.joined[k], restore || !last); err != nil {
+	// min is order-independent (math32.Min of finite values), so guardable operands go last, where the running minimum
+	// can guard them (flatten.cpp, GSDF_N_UNION)
+	guarded := func(c glbuild.Shader3D) bool { return p.GuardFor(c, glbuild.GuardMin, 0).Kind != glbuild.GuardNone }
+	order := make([]glbuild.Shader3D, 0, len(u.joined))
+	for _, c := range u.joined {
+		if !guarded(c) {
+			order = append(order, c)
+		}
+	}
+	for _, c := range u.joined {
+		if guarded(c) {
+			order = append(order, c)
+		}
+	}
+	for k := range order {
+		last := k == len(order)-1
+		if k > 0 {
+			p.SetGuard(p.GuardFor(order[k], glbuild.GuardMin, 0))
+		}
+		if err := glbuild.Emit(p, order[k], restore || !last); err != nil {
 			return err
 		}
 		if k > 0 {
@@ -89,14 +108,20 @@ func (u *OpUnion2D) AppendProgram(p *glbuild.Program, restore bool) error {
 	return nil
 }
 
-func (u *diff) AppendProgram(p *glbuild.Program, r bool) error        { return p.Binary(u.s1, u.s2, r, func() { p.Op0(glbuild.OpDiff) }) }
+func (u *diff) AppendProgram(p *glbuild.Program, r bool) error {
+	return p.BinaryGuarded(u.s1, u.s2, r, glbuild.GuardDiff, 0, func() { p.Op0(glbuild.OpDiff) })
+}
 func (u *intersect) AppendProgram(p *glbuild.Program, r bool) error   { return p.Binary(u.s1, u.s2, r, func() { p.Op0(glbuild.OpMax) }) }
 func (u *xor) AppendProgram(p *glbuild.Program, r bool) error         { return p.Binary(u.s1, u.s2, r, func() { p.Op0(glbuild.OpXor) }) }
 func (u *diff2D) AppendProgram(p *glbuild.Program, r bool) error      { return p.Binary(u.s1, u.s2, r, func() { p.Op0(glbuild.OpDiff) }) }
 func (u *intersect2D) AppendProgram(p *glbuild.Program, r bool) error { return p.Binary(u.s1, u.s2, r, func() { p.Op0(glbuild.OpMax) }) }
 func (u *xor2D) AppendProgram(p *glbuild.Program, r bool) error       { return p.Binary(u.s1, u.s2, r, func() { p.Op0(glbuild.OpXor) }) }
 func (u *smoothUnion) AppendProgram(p *glbuild.Program, r bool) error {
-	return p.Binary(u.s1, u.s2, r, func() { p.Opf(glbuild.OpSmoothUnion, u.k, 0) })
+	kind := glbuild.GuardNone
+	if u.k > 0 {
+		kind = glbuild.GuardSmoothUnion
+	}
+	return p.BinaryGuarded(u.s1, u.s2, r, kind, u.k, func() { p.Opf(glbuild.OpSmoothUnion, u.k, 0) })
 }
 func (u *smoothDiff) AppendProgram(p *glbuild.Program, r bool) error {
 	return p.Binary(u.s1, u.s2, r, func() { p.Opf(glbuild.OpSmoothDiff, u.k, 0) })
@@ -250,15 +275,25 @@ func (u *circarray2D) AppendProgram(p *glbuild.Program, r bool) error { return c
 // ---------------------------------------------------------------------------------------------- 2D -> 3D
 
 func (u *extrusion) AppendProgram(p *glbuild.Program, r bool) error { // h := e.h / 2, cpu_evaluators.go:524
-	p.Header(glbuild.OpExtrudeEnter, 1, 0, fbits(u.h/2), 0)
+	g := p.TakeGuard()
+	hw := len(p.Chunks)
+	p.Header(glbuild.OpExtrudeEnter, 1, 0, fbits(u.h/2), fbits(g.K))
 	p.PushD()
 	if err := glbuild.Emit(p, u.s, r); err != nil {
 		return err
 	}
 	p.Op0(glbuild.OpExtrudeExit)
 	p.PopD()
+	p.PatchGuard(hw, g)
 	return nil
 }
+
+// Slab guards (glbuild/cuda_program.go): the extrusion evaluates them; these nodes only move p and pass them on.
+func (u *extrusion) SlabBounded()                            {}
+func (u *translate) DistTransparentChild() glbuild.Shader   { return u.s }
+func (u *transform) DistTransparentChild() glbuild.Shader   { return u.s }
+func (u *symmetry) DistTransparentChild() glbuild.Shader    { return u.s }
+func (u *twist) DistTransparentChild() glbuild.Shader       { return u.s }
 func (u *revolution) AppendProgram(p *glbuild.Program, r bool) error {
 	return p.Unary(u.s2d, r, func() { p.Opf(glbuild.OpRevolve, u.off, 0) }, nil)
 }
