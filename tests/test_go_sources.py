@@ -122,3 +122,39 @@ def test_every_reference_node_type_has_an_emitter_reading_real_fields():
         assert typ in structs, typ
         for used in set(re.findall(r"\b%s\.(\w+)" % recv, chunk)):
             assert used in all_fields(typ) or (typ, used) in methods, (typ, used)
+
+
+def test_cgo_calls_pass_as_many_arguments_as_the_prototypes_take():
+    hdr = re.sub(r"/\*.*?\*/", "", read(ROOT, "include", "gsdf_b200.h"), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(gsdf_\w+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    assert len(protos) >= 40
+
+    def top_level_args(s):
+        depth, cur, out = 0, "", []
+        for ch in s:
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            if ch == "," and depth == 0:
+                out.append(cur)
+                cur = ""
+            else:
+                cur += ch
+        return out + ([cur] if cur.strip() else [])
+    calls = 0
+    for path in glob.glob(os.path.join(GO, "*", "*.go")):
+        src = strip_go(read(path))
+        for m in re.finditer(r"C\.(gsdf_\w+)\(", src):
+            if m.group(1) not in protos:
+                continue            # a type conversion such as C.gsdf_lattice(...)
+            i = j = m.end()
+            depth = 1
+            while depth:
+                depth += src[j] == "("
+                depth -= src[j] == ")"
+                j += 1
+            assert len(top_level_args(src[i:j - 1])) == protos[m.group(1)], (path, m.group(1))
+            calls += 1
+    assert calls >= 15
