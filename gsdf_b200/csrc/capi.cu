@@ -214,6 +214,15 @@ int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_
             if (kind != GSDF_GUARD_NONE && (target <= pc + len || target >= h.nchunks || !starts[target]))
                 return fail(GSDF_EPROGRAM, "instruction %u: slab guard target %u is not a later instruction", n, target);
         }
+        if (op == GSDF_OP_CYLINDER || op == GSDF_OP_TORUS || op == GSDF_OP_CIRCLE2D || op == GSDF_OP_SCREW_ENTER) {
+            // radius reuse (gsdf_program.h, experimental): flag word is w1, for SCREW_ENTER w2
+            const uint32_t fl = chunks[4 * pc + (op == GSDF_OP_SCREW_ENTER ? 2 : 1)] & (GSDF_RXY_READ | GSDF_RXY_WRITE);
+#ifdef GSDF_RXY
+            if (fl == (GSDF_RXY_READ | GSDF_RXY_WRITE)) return fail(GSDF_EPROGRAM, "instruction %u: radius flags READ and WRITE are exclusive", n);
+#else
+            if (fl) return fail(GSDF_EPROGRAM, "instruction %u: radius-reuse flags need a library built with -DGSDF_RXY (unset GSDF_RXY in the flattener's environment)", n);
+#endif
+        }
         if (op == GSDF_OP_LINES2D) {
             const uint64_t off = chunks[4 * pc + 1], ns = chunks[4 * pc + 2];
             if ((off & 3) || off + ns * 4 > aux_floats) return fail(GSDF_EPROGRAM, "instruction %u: lines aux range out of bounds", n);
@@ -230,7 +239,11 @@ int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_
 
 extern "C" {
 
+#ifdef GSDF_RXY
+const char *gsdf_version(void) { return "gsdf-b200 0.1 (sm_100a) +rxy"; }  // experimental radius-reuse build (gsdf_program.h)
+#else
 const char *gsdf_version(void) { return "gsdf-b200 0.1 (sm_100a)"; }
+#endif
 const char *gsdf_last_error(void) { return g_err.c_str(); }
 
 int gsdf_device_count(void) {
@@ -260,7 +273,7 @@ static int parse_blob(const void *blob, size_t blob_bytes, const float *aux, siz
     if (h.dstack < 1 || h.dstack > 64 || h.pstack > 32) return fail(GSDF_EPROGRAM, "stack depth out of range (d=%u p=%u)", h.dstack, h.pstack);
     chunks = reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(blob) + sizeof h);
     const size_t prog_bytes = (size_t)h.nchunks * 16;
-    const uint32_t stacks = kEvalThreads * 4u * 4u * (h.dstack + 3u * h.pstack);
+    const uint32_t stacks = kEvalThreads * 4u * 4u * (h.dstack + 3u * h.pstack + kRxySlots);
     if (prog_bytes + stacks + 16 > 200 * 1024) return fail(GSDF_EPROGRAM, "program too large for shared memory");
     return validate_program(h, chunks, aux_floats);
 }
@@ -294,7 +307,7 @@ static int upload_blob(gsdf_program *p, const gsdf_program_header &h, const uint
     p->pv.dslots = h.dstack;
     p->pv.pslots = h.pstack;
     // stage aux with the program when program + aux + stacks stay under ~100 KB (>= 2 CTAs/SM)
-    const uint32_t stacks = kEvalThreads * 4u * 4u * (h.dstack + 3u * h.pstack);
+    const uint32_t stacks = kEvalThreads * 4u * 4u * (h.dstack + 3u * h.pstack + kRxySlots);
     p->pv.stage_aux = (prog_bytes + aux_bytes + stacks + 16 <= 100 * 1024) ? 1u : 0u;
     return 0;
 }

@@ -439,6 +439,63 @@ struct Emitter {
     }
 };
 
+// Radius reuse (include/gsdf_program.h, "Radius reuse"; experimental, GSDF_RXY=1): a post-pass over the finished
+// straight-line stream. `ver` names the current (x, y) of the machine symbolically: ops that can change x or y give it a
+// fresh name, the position stack restores earlier names, and a one-slot cache remembers for which name the radius
+// Hypot(x, y) was stored. Stores happen only outside every region a guard can skip, so the simulation is exact.
+void planRadiusReuse(Program &out) {
+    std::vector<uint32_t> &c = out.chunks;
+    const uint32_t nch = (uint32_t)(c.size() / 4);
+    std::vector<int> delta(nch + 1, 0);      // +1 where a skippable region starts, -1 at its jump target
+    std::vector<uint8_t> isTarget(nch + 1, 0);
+    for (uint32_t pc = 0; pc < nch;) {
+        const uint32_t op = c[4 * pc] & 0xff, len = (c[4 * pc] >> 8) & 0xff;
+        if ((op == GSDF_OP_EXTRUDE_ENTER || op == GSDF_OP_SCREW_ENTER) && (c[4 * pc + 1] & 0xff)) {
+            const uint32_t t = c[4 * pc + 1] >> 8;   // a firing slab guard skips the ENTER op itself
+            delta[pc]++; delta[t]--; isTarget[t] = 1;
+        }
+        if (op == GSDF_OP_BBOX_GUARD2D) {
+            const uint32_t t = c[4 * pc + 1] >> 8;   // the guard op always runs; the operand behind it may not
+            delta[pc + len]++; delta[t]--; isTarget[t] = 1;
+        }
+        if (op == GSDF_OP_END || len == 0) break;
+        pc += len;
+    }
+    uint32_t ver = 1, next = 2, slot = 0;
+    long writer = -1;          // word index of the flag word of the op that filled the slot
+    bool writerRead = false;
+    std::vector<uint32_t> pstk;
+    int depth = 0;
+    auto fresh = [&] { ver = next++; };
+    auto retire = [&] { if (writer >= 0 && !writerRead) c[(size_t)writer] &= ~GSDF_RXY_WRITE; };  // nobody read it: plain op
+    for (uint32_t pc = 0; pc < nch;) {
+        const uint32_t op = c[4 * pc] & 0xff, len = (c[4 * pc] >> 8) & 0xff;
+        depth += delta[pc];
+        if (isTarget[pc]) fresh();  // a skipped region may or may not have moved p: what follows must not assume either
+        switch (op) {
+        case GSDF_OP_CYLINDER: case GSDF_OP_TORUS: case GSDF_OP_CIRCLE2D: case GSDF_OP_SCREW_ENTER: {
+            const size_t fw = 4 * (size_t)pc + (op == GSDF_OP_SCREW_ENTER ? 2 : 1);
+            if (slot == ver) { c[fw] |= GSDF_RXY_READ; writerRead = true; }
+            else if (depth == 0) { retire(); c[fw] |= GSDF_RXY_WRITE; slot = ver; writer = (long)fw; writerRead = false; }
+            if (op == GSDF_OP_SCREW_ENTER) fresh();  // p = (sawtooth, radius)
+        } break;
+        case GSDF_OP_PUSH_POS: pstk.push_back(ver); break;
+        case GSDF_OP_POP_POS: if (!pstk.empty()) { ver = pstk.back(); pstk.pop_back(); } else fresh(); break;
+        case GSDF_OP_PEEK_POS: if (!pstk.empty()) ver = pstk.back(); else fresh(); break;
+        case GSDF_OP_CIRC_ENTER: pstk.push_back(next++); fresh(); break;  // parks the rotated p0, continues at p1
+        case GSDF_OP_TRANSLATE: if (c[4 * (pc + 1)] != 0u || c[4 * (pc + 1) + 1] != 0u) fresh(); break;  // x - (+0) == x bit for bit
+        case GSDF_OP_SYMMETRY: if (c[4 * pc + 1] & 3u) fresh(); break;
+        case GSDF_OP_SCALE_POS: case GSDF_OP_TRANSFORM: case GSDF_OP_ROTATE2D: case GSDF_OP_TWIST: case GSDF_OP_ELONGATE:
+        case GSDF_OP_ELONGATE2D: case GSDF_OP_ARRAY_VAR: case GSDF_OP_ARRAY2D_VAR: case GSDF_OP_REVOLVE:
+            fresh(); break;
+        default: break;
+        }
+        if (op == GSDF_OP_END || len == 0) break;
+        pc += len;
+    }
+    retire();
+}
+
 }  // namespace
 
 bool Flatten(const Builder &b, NodeId root, Program &out, std::string &err) {
@@ -449,6 +506,10 @@ bool Flatten(const Builder &b, NodeId root, Program &out, std::string &err) {
     if (!e.emit(root, false, out.dim == 2)) { err = e.err; return false; }
     e.header(GSDF_OP_END, 1);
     if (e.d != 1) { err = "internal: distance stack imbalance"; return false; }
+    {   // experimental: only programs for a -DGSDF_RXY build of the library (a default build rejects the flags)
+        const char *rx = std::getenv("GSDF_RXY");
+        if (rx && *rx && *rx != '0') planRadiusReuse(out);
+    }
     out.dstack = e.dmax > 1 ? e.dmax - 1 : 1;  // top is cached in a register; slot 0 also absorbs the first push
     out.pstack = e.pmax;
     while (out.aux.size() % 4) out.aux.push_back(0.f);

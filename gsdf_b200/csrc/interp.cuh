@@ -31,6 +31,23 @@ struct Machine {
     int stride;                 // blockDim.x
     int dsp, psp;
     bool skip;                  // CTA-uniform: a slab guard fired, the next combiner keeps `a` (gsdf_program.h)
+#ifdef GSDF_RXY
+    float *rxy;                 // &radius cache[threadIdx.x] (experimental radius reuse, gsdf_program.h)
+    // r = Hypot(px, py), from the cache when the flattener proved it holds the radius of bit-identical x, y
+    __device__ __forceinline__ void radius(uint32_t flags, float (&r)[P]) {
+        if (flags & GSDF_RXY_READ) {
+#pragma unroll
+            for (int j = 0; j < P; j++) r[j] = rxy[j * stride];
+        } else {
+#pragma unroll
+            for (int j = 0; j < P; j++) r[j] = m32::hypot32(px[j], py[j]);
+            if (flags & GSDF_RXY_WRITE) {
+#pragma unroll
+                for (int j = 0; j < P; j++) rxy[j * stride] = r[j];
+            }
+        }
+    }
+#endif
 
     __device__ __forceinline__ void init(float *d, float *p, int s) {
         dstk = d; pstk = p; stride = s; dsp = -1; psp = 0; skip = false;
@@ -134,12 +151,41 @@ __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restri
         } break;
         case GSDF_OP_TORUS: {  // :59-68  f2=rGreater f3=rLesser
             m.pushD();
+#ifdef GSDF_RXY
+            float r[P];
+            m.radius(h.y, r);
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = norm2(r[j] - f2, m.pz[j]) - f3;
+#else
 #pragma unroll
             for (int j = 0; j < P; j++) m.top[j] = norm2(hypot32(m.px[j], m.py[j]) - f2, m.pz[j]) - f3;
+#endif
         } break;
         case GSDF_OP_CYLINDER: {  // :70-88
             const float4 c = ldf4(prog, pc + 1);
             m.pushD();
+#ifdef GSDF_RXY
+            {
+                float r[P];
+                m.radius(h.y, r);
+                if ((h.y & 1u) == 0u) {
+#pragma unroll
+                    for (int j = 0; j < P; j++) {
+                        float dx = r[j] - c.x;
+                        float dy = absf(m.pz[j]) - c.y;
+                        m.top[j] = minf(0.f, maxf(dx, dy)) + hypot32(maxf(0.f, dx), maxf(0.f, dy));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < P; j++) {
+                        float dx = r[j] - c.x + c.z;
+                        float dy = absf(m.pz[j]) - c.y;
+                        m.top[j] = minf(maxf(dx, dy), 0.f) + hypot32(maxf(dx, 0.f), maxf(dy, 0.f)) - c.z;
+                    }
+                }
+                break;
+            }
+#endif
             if (h.y == 0u) {
 #pragma unroll
                 for (int j = 0; j < P; j++) {
@@ -175,8 +221,15 @@ __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restri
         // ------------------------------------------------------------------ 2D primitives
         case GSDF_OP_CIRCLE2D: {  // :661
             m.pushD();
+#ifdef GSDF_RXY
+            float r[P];
+            m.radius(h.y, r);  // ms2.Norm = Hypot(x, y)
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = r[j] - f2;
+#else
 #pragma unroll
             for (int j = 0; j < P; j++) m.top[j] = norm2(m.px[j], m.py[j]) - f2;
+#endif
         } break;
         case GSDF_OP_RECT2D: {  // :685  f2=bx f3=by
             m.pushD();
@@ -656,10 +709,18 @@ __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restri
                 if (__syncthreads_and(dead)) { m.skip = true; pc = (int)(h.y >> 8); continue; }
             }
             m.pushD();
+#ifdef GSDF_RXY
+            float r[P];
+            m.radius(h.z, r);  // SCREW_ENTER keeps its radius flags in word 2 (word 1 is the slab guard)
+#endif
 #pragma unroll
             for (int j = 0; j < P; j++) {
                 float x = m.px[j], y = m.py[j], z = m.pz[j];
+#ifdef GSDF_RXY
+                float yy = r[j];
+#else
                 float yy = hypot32(x, y);
+#endif
                 yy += z * c.w;
                 float theta = m32::atan2(y, x);
                 float zz = z + c.y * theta / m32::kTwoPiF;

@@ -85,9 +85,15 @@ __device__ __forceinline__ void bulk_stage(void *s_dst, const void *g_src, uint3
 
 // Shared memory: [prog (+aux)] [mbarrier + tile slot, 16 bytes] [dstack] [pstack]
 __host__ __device__ inline uint32_t smem_stage_bytes(const ProgView &pv) { return pv.prog_bytes + (pv.stage_aux ? pv.aux_bytes : 0u); }
+// Radius cache of the experimental -DGSDF_RXY build (gsdf_program.h, "Radius reuse"): one float per point behind the stacks.
+#ifdef GSDF_RXY
+constexpr uint32_t kRxySlots = 1u;
+#else
+constexpr uint32_t kRxySlots = 0u;
+#endif
 template <int P>
 __host__ __device__ inline uint32_t smem_total_bytes(const ProgView &pv, int threads) {
-    return smem_stage_bytes(pv) + 16u + (uint32_t)threads * P * 4u * (pv.dslots + 3u * pv.pslots);
+    return smem_stage_bytes(pv) + 16u + (uint32_t)threads * P * 4u * (pv.dslots + 3u * pv.pslots + kRxySlots);
 }
 
 template <int P, class Gen, bool EXT>
@@ -123,12 +129,18 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval(ProgView pv, Gen gen) {
         // every thread of the tile runs the program (barriers inside); threads past the end redo the last item
         const uint64_t wc = w < nwork ? w : nwork - 1;
         m.init(dstk, pstk, blockDim.x);
+#ifdef GSDF_RXY
+        m.rxy = pstk + (size_t)pv.pslots * 3 * P * blockDim.x;
+#endif
         gen.load(wc, m.px, m.py, m.pz);
         run_program<P, EXT>(m, prog, aux);
         if (w < nwork) gen.store(w, m.top);
 #else
         if (w >= nwork) continue;
         m.init(dstk, pstk, blockDim.x);
+#ifdef GSDF_RXY
+        m.rxy = pstk + (size_t)pv.pslots * 3 * P * blockDim.x;
+#endif
         gen.load(w, m.px, m.py, m.pz);
         run_program<P, EXT>(m, prog, aux);
         gen.store(w, m.top);
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval_stream(ProgView pv, const
                                      : reinterpret_cast<const float4 *>(reinterpret_cast<const uint8_t *>(pv.g_prog) + pv.prog_bytes);
     float *dstk = reinterpret_cast<float *>(smem + stage + 16u) + threadIdx.x;
     float *pstk = dstk + (size_t)pv.dslots * P * blockDim.x;
-    const uint32_t stack_bytes = (uint32_t)blockDim.x * P * 4u * (pv.dslots + 3u * pv.pslots);
+    const uint32_t stack_bytes = (uint32_t)blockDim.x * P * 4u * (pv.dslots + 3u * pv.pslots + kRxySlots);
     const uint32_t tile_bytes = stream_stage_bytes<DIM>(blockDim.x);
     uint8_t *buf0 = smem + ((stage + 16u + stack_bytes + 127u) & ~127u);
     const uint32_t bar_u[2] = {smem_u32(bar), smem_u32(bar + 1)};
@@ -257,6 +269,9 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval_stream(ProgView pv, const
         const uint64_t next = tile + gridDim.x;
         if (threadIdx.x == 0 && next < nfull) issue(next, b ^ 1);   // stage b^1 was released by the barrier that ended the previous iteration
         m.init(dstk, pstk, blockDim.x);
+#ifdef GSDF_RXY
+        m.rxy = pstk + (size_t)pv.pslots * 3 * P * blockDim.x;
+#endif
         const uint64_t i0 = tile * pts_per_tile + (uint64_t)threadIdx.x * P;
         if (tile < nfull) {
             asm volatile(

@@ -127,6 +127,20 @@ enum gsdf_opcode {
  * is uniform over most tiles of a part whose threaded/extruded feature occupies a fraction of its volume. */
 enum gsdf_guard_kind { GSDF_GUARD_NONE = 0, GSDF_GUARD_DIFF = 1, GSDF_GUARD_MIN = 2, GSDF_GUARD_SMOOTH_UNION = 3 };
 
+/* Radius reuse -- EXPERIMENTAL, emitted only when GSDF_RXY=1 is set in the flattener's environment, accepted only by a
+ * library built with -DGSDF_RXY (gsdf_program_create of a default build rejects the flags).
+ *
+ * CYLINDER, TORUS, CIRCLE2D and SCREW_ENTER all start from r = math32.Hypot(p.x, p.y): an IEEE division and square root,
+ * about 30 instructions. On a part like the npt-flange the same x, y reach four such ops per evaluation (three coaxial
+ * cylinders whose translations only move z, and the screw). A post-pass of the flattener tracks, through the straight-
+ * line stream, which ops can change x or y (PUSH/POP/PEEK_POS restore an earlier state; a TRANSLATE by (+0, +0, tz) changes
+ * nothing) and marks a consumer GSDF_RXY_READ when the one-slot radius cache provably holds Hypot of bit-identical x, y,
+ * and GSDF_RXY_WRITE when it computes the radius for later readers. Writers are never inside a region a guard can skip,
+ * so the cache content is static. Reusing a value computed from identical bits is bit-identical by construction.
+ * Flag word: w1 for CYLINDER (bit 0 stays the rounding flag), TORUS and CIRCLE2D; w2 for SCREW_ENTER (w1 holds its guard). */
+#define GSDF_RXY_READ 0x100u
+#define GSDF_RXY_WRITE 0x200u
+
 /* Header that precedes the instruction chunks in the blob handed to gsdf_program_create (one 16-byte chunk x2). */
 typedef struct {
     uint32_t magic;      /* GSDF_PROGRAM_MAGIC */

@@ -22,6 +22,7 @@ EXTRUDE_EXIT MAX_BELOW PUSH_POS POP_POS PEEK_POS TRANSLATE SCALE_POS SYMMETRY TR
 ARRAY_VAR ARRAY2D_VAR CIRC_ENTER EXTRUDE_ENTER REVOLVE SCREW_ENTER CULL_UB2D BBOX_GUARD2D""".split()
 OP = {name: i for i, name in enumerate(OPS)}
 GUARD_DIFF, GUARD_MIN, GUARD_SMOOTH_UNION = 1, 2, 3
+RXY_READ, RXY_WRITE = 0x100, 0x200  # experimental radius reuse (include/gsdf_program.h)
 UNSUPPORTED = {OP["ELLIPSE2D"], OP["BEZIERQ2D"]}  # the EXT interpreter's primitives (double-precision cbrt, exp/log) are not modelled
 
 
@@ -118,6 +119,22 @@ def _run_tile(P, pos, M, stats):
     top = np.zeros(n, F)
     dstk, pstk = [], []
     skip = False
+    rxy = [None]  # the one-slot radius cache
+
+    def radius(flags):
+        """Hypot(px, py), from the cache when the program says it holds the radius of these very x, y."""
+        if flags & RXY_READ:
+            assert rxy[0] is not None, "radius cache read before any write"
+            # the flattener's claim, checked directly: the cached radius is Hypot of bit-identical x, y
+            assert np.array_equal(rxy[0].view(np.uint32), M.hypot(px, py).view(np.uint32)), "stale radius cache"
+            if stats is not None: stats["rxy_reads"] = stats.get("rxy_reads", 0) + 1
+            return rxy[0]
+        r = M.hypot(px, py)
+        if flags & RXY_WRITE:
+            rxy[0] = r
+            if stats is not None: stats["rxy_writes"] = stats.get("rxy_writes", 0) + 1
+        return r
+
     max_d = max_p = 0
     pc = 0
     u, f = P.u, P.f
@@ -154,14 +171,14 @@ def _run_tile(P, pos, M, stats):
             n3 = M.norm3(np.maximum(qx, 0), np.maximum(qy, 0), np.maximum(z, 0)) + np.minimum(F(0), np.maximum(qx, np.maximum(qy, z)))
             top = np.minimum(n1, np.minimum(n2, n3))
         elif name == "TORUS":
-            pushD(); top = M.norm2(M.hypot(px, py) - f2, pz) - f3
+            pushD(); top = M.norm2(radius(w1) - f2, pz) - f3
         elif name == "CYLINDER":
             pushD()
-            if w1 == 0:
-                dx, dy = M.hypot(px, py) - c1[0], np.abs(pz) - c1[1]
+            if w1 & 1 == 0:
+                dx, dy = radius(w1) - c1[0], np.abs(pz) - c1[1]
                 top = np.minimum(F(0), np.maximum(dx, dy)) + M.hypot(np.maximum(F(0), dx), np.maximum(F(0), dy))
             else:
-                dx, dy = M.hypot(px, py) - c1[0] + c1[2], np.abs(pz) - c1[1]
+                dx, dy = radius(w1) - c1[0] + c1[2], np.abs(pz) - c1[1]
                 top = np.minimum(np.maximum(dx, dy), F(0)) + M.hypot(np.maximum(dx, 0), np.maximum(dy, 0)) - c1[2]
         elif name == "HEX":
             pushD()
@@ -174,7 +191,7 @@ def _run_tile(P, pos, M, stats):
             d2 = z - c1[1]
             top = np.minimum(np.maximum(d1, d2), F(0)) + M.hypot(np.maximum(d1, 0), np.maximum(d2, 0))
         elif name == "CIRCLE2D":
-            pushD(); top = M.norm2(px, py) - f2
+            pushD(); top = radius(w1) - f2
         elif name == "RECT2D":
             pushD()
             dx, dy = np.abs(px) - f2, np.abs(py) - f3
@@ -383,7 +400,7 @@ def _run_tile(P, pos, M, stats):
                     continue
             pushD()
             x, y, z = px, py, pz
-            yy = M.hypot(x, y)
+            yy = radius(w2)
             yy = yy + z * c1[3]
             theta = M.atan2(y, x)
             zz = z + c1[1] * theta / F(2 * np.pi)

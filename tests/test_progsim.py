@@ -93,3 +93,40 @@ def test_box_guards_of_the_text_scene(oracle, bld, M, monkeypatch):
 def test_model_rejects_what_it_does_not_implement(bld):
     f = bld.flatten(bld.NewEllipse(1, 2))
     assert not progsim.Program(f["blob"], f["aux"]).supported()
+
+
+def test_radius_reuse_programs_are_bit_identical_and_gated(oracle, bld, M, monkeypatch):
+    """Experimental radius reuse (include/gsdf_program.h, GSDF_RXY=1 in the flattener's environment): consumers of
+    Hypot(p.x, p.y) are marked READ when the flattener proves the one-slot cache holds the radius of bit-identical x, y.
+    The model checks that claim directly at every read and the result against the oracle; a default build of the library
+    refuses such programs before it touches a device."""
+    import gsdf_b200
+    from gsdf_b200 import gleval, _lib
+    flange = gsdf.scene(bld, "npt-flange")
+    plain = bld.flatten(flange)["blob"]
+    monkeypatch.setenv("GSDF_RXY", "1")
+    f = bld.flatten(flange)
+    assert f["blob"] != plain and len(f["blob"]) == len(plain)
+    P = progsim.Program(f["blob"], f["aux"])
+    flags = []
+    pc = 0
+    while True:
+        op, ln = int(P.u[pc, 0]) & 0xff, (int(P.u[pc, 0]) >> 8) & 0xff
+        if progsim.OPS[op] in ("CYLINDER", "SCREW_ENTER"):
+            flags.append((progsim.OPS[op], int(P.u[pc, 2 if progsim.OPS[op] == "SCREW_ENTER" else 1]) & 0x300))
+        if op == 0:
+            break
+        pc += ln
+    # pipe cylinder computes and stores; the screw, the plate cylinder (translated along z only) and the bore read
+    assert flags == [("CYLINDER", progsim.RXY_WRITE), ("SCREW_ENTER", progsim.RXY_READ), ("CYLINDER", progsim.RXY_READ), ("CYLINDER", progsim.RXY_READ)]
+    reads = 0
+    shapes_ = shapes.all3d(bld) + shapes.all2d(bld) + shapes.dag3d(bld) + shapes.random_trees(bld, 1, 40, 3) + shapes.random_trees(bld, 1, 40, 2)
+    for name, s in shapes_:
+        st = {}
+        sim_vs_oracle(oracle, bld, M, name, s, stats=st)
+        reads += st.get("rxy_reads", 0)
+    assert reads >= 5
+    if "+rxy" not in gsdf_b200.version():
+        with pytest.raises(gsdf_b200.GsdfError) as e:
+            gleval.NewCUDASDF3(flange)
+        assert e.value.code == _lib.EPROGRAM and "GSDF_RXY" in str(e.value)
