@@ -681,7 +681,8 @@ __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restri
             for (int j = 0; j < P; j++) {
                 const float dx = maxf(maxf(bx.x - m.px[j], m.px[j] - bx.z), 0.f), dy = maxf(maxf(bx.y - m.py[j], m.py[j] - bx.w), 0.f);
                 const float w = m32::sqrt(dx * dx + dy * dy) * 0.9999f - f3;
-                dead &= guard_dead(h.y & 0xffu, w, m.top[j], 0.f);
+                // the box bounds the operand from below only OUTSIDE the box: a point inside it never votes for the skip
+                dead &= (dx > 0.f || dy > 0.f) && guard_dead(h.y & 0xffu, w, m.top[j], 0.f);
             }
             if (__syncthreads_and(dead)) { m.skip = true; pc = (int)(h.y >> 8); continue; }
         } break;

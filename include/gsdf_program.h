@@ -92,7 +92,9 @@ enum gsdf_opcode {
     GSDF_OP_CULL_UB2D,   /* w1=aux_off w2=npts w3=abs margin ; aux: anchor points (x,y) ON the operands' outlines.
                             push(U), U = (1+1e-4)*min_k |p - v_k| + margin >= min over the union's operands */
     GSDF_OP_BBOX_GUARD2D,/* w1=guard kind | target<<8, w3=abs margin, c1=(minx,miny,maxx,maxy) of the operand that follows:
-                            w = (1-1e-4)*dist(p, box) - margin <= operand(p) ; guard_dead(kind, w, top) for the whole tile
+                            w = (1-1e-4)*dist(p, box) - margin <= operand(p) for p OUTSIDE the box; the tile skips the operand iff every
+                            point of it lies outside the box and satisfies guard_dead(kind, w, top) (a point inside the box
+                            never votes for the skip: the box says nothing about the operand's value there)
                             => jump to `target` (the operand's combiner, which then keeps `top`) */
     GSDF_OP__COUNT
 };

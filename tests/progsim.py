@@ -23,6 +23,9 @@ ARRAY_VAR ARRAY2D_VAR CIRC_ENTER EXTRUDE_ENTER REVOLVE SCREW_ENTER CULL_UB2D BBO
 OP = {name: i for i, name in enumerate(OPS)}
 GUARD_DIFF, GUARD_MIN, GUARD_SMOOTH_UNION = 1, 2, 3
 RXY_READ, RXY_WRITE = 0x100, 0x200  # experimental radius reuse (include/gsdf_program.h)
+# True reproduces the box-guard predicate as first shipped (points INSIDE the operand's box could vote for the skip): kept so
+# that a test can show the overlapping-operand shapes of tests/shapes.py::overlap2d catch exactly that defect.
+LEGACY_BOX_GUARD = False
 UNSUPPORTED = {OP["ELLIPSE2D"], OP["BEZIERQ2D"]}  # the EXT interpreter's primitives (double-precision cbrt, exp/log) are not modelled
 
 
@@ -377,7 +380,8 @@ def _run_tile(P, pos, M, stats):
             dx = np.maximum(np.maximum(c1[0] - px, px - c1[2]), F(0))
             dy = np.maximum(np.maximum(c1[1] - py, py - c1[3]), F(0))
             w = np.sqrt(dx * dx + dy * dy) * F(0.9999) - f3
-            if guard_dead(w1 & 0xff, w, top, 0).all():
+            outside = (dx > 0) | (dy > 0) | LEGACY_BOX_GUARD  # the box bounds the operand from below only OUTSIDE the box
+            if (outside & guard_dead(w1 & 0xff, w, top, 0)).all():
                 if stats is not None: stats["fired"] = stats.get("fired", 0) + 1
                 skip = True; pc = w1 >> 8
                 continue

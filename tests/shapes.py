@@ -204,6 +204,34 @@ def dag3d(bld):
             ("shared_smooth", bld.SmoothUnion(0.2, twice, bld.Translate(twice, 0, 0, 0.9)))]
 
 
+def overlap2d(bld):
+    """Unions and differences of bounded 2-D shapes that OVERLAP: the operands' bounding boxes bound their values from below
+    only outside the boxes, so a box guard (include/gsdf_program.h) must never fire for a tile with points inside the
+    box. Found by the random-tree fuzz on the CPU model (tests/progsim.py); the text scenes never overlap."""
+    c = lambda r, x, y: bld.Translate2D(bld.NewCircle(r), x, y)
+    r = lambda w, h, x, y: bld.Translate2D(bld.NewRectangle(w, h), x, y)
+    star = bld.NewPolygon(nagon(5, 0.8))
+    return [
+        ("union_overlapping_circles", bld.Union2D(c(0.5, 0, 0), c(0.45, 0.3, 0.1), c(0.4, 0.15, 0.35), c(0.2, 1.5, 0))),
+        ("union_nested", bld.Union2D(c(0.9, 0, 0), c(0.3, 0.1, 0.1), r(0.4, 0.4, -0.2, 0.2), star)),
+        ("diff_line_minus_circle", bld.Difference2D(bld.NewLine2D(-0.9, -0.5, 0.3, 0.27, 0.06), c(0.74, -0.28, -0.23))),
+        ("diff_small_minus_big", bld.Difference2D(c(0.3, 0.5, 0), r(1.2, 1.2, 0, 0))),
+        ("diff_of_unions", bld.Difference2D(bld.Union2D(c(0.5, 0, 0), r(0.6, 0.3, 0.6, 0), star), bld.Union2D(c(0.3, 0.2, 0), c(0.25, 0.7, 0.1)))),
+        ("extruded_overlap", bld.Extrude(bld.Difference2D(bld.NewRoundedX(1.0, 0.07), c(0.87, -0.13, 0.5)), 1.7)),
+    ]
+
+
+def overlap2d_points(name, s):
+    """Evaluation points for overlap2d() shapes that put WHOLE 2048-point device tiles into the region where a box
+    guard voting with inside-the-box points would skip a live operand."""
+    pos = sample_points(s, dense=[128, 128] if s.is2d else [64, 64, 8])
+    if name == "diff_small_minus_big":   # outside the small circle, inside the big rectangle: max(a, -s) = -s > a there
+        g = append_grid(np.float32([-0.55, -0.55]), np.float32([0.55, 0.55]), [128, 128])
+        g = g[np.hypot(g[:, 0] - 0.5, g[:, 1]) - 0.3 > 0.02]
+        pos = np.concatenate([g[:8192], pos]).astype(np.float32)
+    return pos
+
+
 def all3d(bld):
     return primitives3d(bld) + binops3d(bld) + unary3d(bld) + threads3d(bld) + scenes3d(bld) + guards3d(bld)
 

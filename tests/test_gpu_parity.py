@@ -62,6 +62,14 @@ def test_random_trees_bit_identical(oracle, bld, seed, dim):
         check_field(name, s, oracle, shapes.sample_points(s))
 
 
+def test_box_guards_are_sound_for_overlapping_operands(oracle, bld):
+    """Unions / differences of OVERLAPPING bounded 2-D shapes (tests/shapes.py::overlap2d): a box guard must not fire for
+    a tile that has points inside the operand's box. The point sets put whole 2048-point tiles where the first version of
+    the guard skipped a live operand (found on the CPU model, tests/test_progsim.py)."""
+    for name, s in shapes.overlap2d(bld):
+        check_field(name, s, oracle, shapes.overlap2d_points(name, s))
+
+
 def test_evaluate_golden_fixtures(bld):
     g = np.load(os.path.join(GOLD, "distances.npz"))
     for name, s in shapes.all3d(bld) + shapes.all2d(bld):

@@ -90,6 +90,30 @@ def test_box_guards_of_the_text_scene(oracle, bld, M, monkeypatch):
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and (a < 0).any() and (a > 0).any()
 
 
+def test_box_guards_never_vote_with_points_inside_the_box(oracle, bld, M):
+    """A bounding box bounds an operand's value from below only OUTSIDE the box. The box guard as first shipped let points
+    inside the box vote for the skip (w = -margin there), which is harmless for text (glyphs do not overlap, holes lie
+    inside their glyph) but wrong for overlapping operands; the random-tree fuzz on this model found it. The overlap
+    corpus passes with the corrected predicate at every tile size and fails with the legacy one."""
+    for name, s in shapes.overlap2d(bld):
+        pos = shapes.overlap2d_points(name, s)
+        for tile in (64, progsim.TILE):
+            sim_vs_oracle(oracle, bld, M, name, s, pos[:4096] if tile == 64 else pos, tile=tile)
+    caught = 0
+    progsim.LEGACY_BOX_GUARD = True
+    try:
+        for name, s in shapes.overlap2d(bld):
+            pos = shapes.overlap2d_points(name, s)
+            f = bld.flatten(s)
+            got = progsim.run(progsim.Program(f["blob"], f["aux"]), pos, M)
+            t = oracle.Tree.from_shader(s)
+            want = t.eval2(pos) if s.is2d else t.eval3(pos)
+            caught += int((got.view(np.uint32) != want.view(np.uint32)).any())
+    finally:
+        progsim.LEGACY_BOX_GUARD = False
+    assert caught >= 2   # at the device's own tile size
+
+
 def test_model_rejects_what_it_does_not_implement(bld):
     f = bld.flatten(bld.NewEllipse(1, 2))
     assert not progsim.Program(f["blob"], f["aux"]).supported()
