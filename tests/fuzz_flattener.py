@@ -1,6 +1,7 @@
 """Offline fuzz of the host-side flattener on the CPU model (not collected by pytest; run it by hand):
 
-    python tests/fuzz_flattener.py [first_seed last_seed]        # GSDF_RXY=1 / GSDF_NO_GUARDS=1 select the variants
+    python tests/fuzz_flattener.py [first_seed last_seed]        # GSDF_RXY=1 / GSDF_NO_GUARDS=1 select the variants,
+                                                                 # FUZZ_RICH=1 adds threads, nuts, line sets, bounds wrappers
 
 For every seed it builds random 3-D and 2-D trees (tests/shapes.py::random_trees, depth 3 and 5), flattens them, runs the
 program on tests/progsim.py with small tiles (so that guards fire often) and compares with the oracle's evaluation of the
@@ -30,7 +31,7 @@ def main():
         for seed in range(s0, s1):
             bld = gsdf.Builder()
             for depth in (3, 5):
-                for name, s in shapes.random_trees(bld, seed, 12, dim, depth=depth):
+                for name, s in shapes.random_trees(bld, seed, 12, dim, depth=depth, rich=os.environ.get('FUZZ_RICH') is not None):
                     f = bld.flatten(s)
                     P = progsim.Program(f["blob"], f["aux"])
                     if not P.supported():

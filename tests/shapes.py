@@ -265,10 +265,22 @@ def sample_points(shader, margin=0.15, dense=None):
 
 
 # ---------------------------------------------------------------------------------------------- random trees
-def _rand2d(bld, rng, depth):
+def _rand2d(bld, rng, depth, rich=False):
     """A random 2-D tree of at most `depth` operation levels over random primitives (parameters inside the ranges the
-    reference's randomised tests draw from, gsdf_test.go:572-730)."""
+    reference's randomised tests draw from, gsdf_test.go:572-730). rich=True (CPU fuzz only; the draws of the default
+    mode are unchanged) adds line sets, multi-translations and thread profiles."""
     u = lambda a, b: float(rng.uniform(a, b))
+    if rich and rng.random() < 0.15:
+        k = int(rng.integers(0, 4))
+        T = gsdf.threads
+        if k == 0:
+            pts = rng.uniform(-1, 1, (int(rng.integers(2, 6)), 2, 2)).astype(np.float32)
+            return bld.NewLines2D(pts, u(0.05, 0.3))
+        if k == 1:
+            return bld.TranslateMulti2D(_rand2d(bld, rng, min(depth, 1), rich), rng.uniform(-1.5, 1.5, (int(rng.integers(1, 5)), 2)).astype(np.float32))
+        if k == 2:
+            return T.Thread(bld, T.ISO(u(0.8, 3.0), u(0.1, 0.5), bool(rng.integers(0, 2))))
+        return T.Thread(bld, [T.NPT(0.5), T.UTS(0.5, 13, True), T.Acme(1.0, 0.2), T.PlasticButtress(1.0, 0.2)][int(rng.integers(0, 4))])
     if depth <= 0 or rng.random() < 0.1:
         k = int(rng.integers(0, 10))
         if k == 0: return bld.NewCircle(u(0.3, 1.2))
@@ -282,11 +294,11 @@ def _rand2d(bld, rng, depth):
         if k == 8: return bld.NewArc(u(0.5, 1.2), u(0.3, 2.5), u(0.05, 0.2))
         return bld.NewRoundedX(u(0.5, 1.2), u(0.05, 0.2))
     k = int(rng.integers(0, 13))
-    a = _rand2d(bld, rng, depth - 1)
-    if k == 0: return bld.Union2D(a, _rand2d(bld, rng, depth - 1), *[_rand2d(bld, rng, 0) for _ in range(int(rng.integers(0, 3)))])
-    if k == 1: return bld.Difference2D(a, bld.Translate2D(_rand2d(bld, rng, depth - 1), u(-0.5, 0.5), u(-0.5, 0.5)))
-    if k == 2: return bld.Intersection2D(a, _rand2d(bld, rng, depth - 1))
-    if k == 3: return bld.Xor2D(a, bld.Translate2D(_rand2d(bld, rng, depth - 1), u(-0.5, 0.5), u(-0.5, 0.5)))
+    a = _rand2d(bld, rng, depth - 1, rich)
+    if k == 0: return bld.Union2D(a, _rand2d(bld, rng, depth - 1, rich), *[_rand2d(bld, rng, 0, rich) for _ in range(int(rng.integers(0, 3)))])
+    if k == 1: return bld.Difference2D(a, bld.Translate2D(_rand2d(bld, rng, depth - 1, rich), u(-0.5, 0.5), u(-0.5, 0.5)))
+    if k == 2: return bld.Intersection2D(a, _rand2d(bld, rng, depth - 1, rich))
+    if k == 3: return bld.Xor2D(a, bld.Translate2D(_rand2d(bld, rng, depth - 1, rich), u(-0.5, 0.5), u(-0.5, 0.5)))
     if k == 4: return bld.Translate2D(a, u(-1.5, 1.5), u(-1.5, 1.5))
     if k == 5: return bld.Rotate2D(a, u(-3, 3))
     if k == 6: return bld.Scale2D(a, u(0.3, 2.5))
@@ -299,8 +311,19 @@ def _rand2d(bld, rng, depth):
     return bld.CircularArray2D(bld.Translate2D(a, u(1.5, 3.0), 0), int(rng.integers(1, div + 1)), div)
 
 
-def _rand3d(bld, rng, depth):
+def _rand3d(bld, rng, depth, rich=False):
     u = lambda a, b: float(rng.uniform(a, b))
+    if rich and rng.random() < 0.12:
+        k = int(rng.integers(0, 5))
+        T = gsdf.threads
+        if k == 0: return T.Nut(bld, T.ISO(u(2, 4), 0.5, False), [T.NutHex, T.NutCircular][int(rng.integers(0, 2))])
+        if k == 1: return T.HexHead(bld, u(1, 3), u(1, 3), bool(rng.integers(0, 2)), bool(rng.integers(0, 2)))
+        if k == 2: return T.Screw(bld, u(1.0, 3.0), [T.NPT(0.5), T.UTS(0.5, 13, True), T.Acme(1.0, 0.2), T.ANSIButtress(1.0, 0.2)][int(rng.integers(0, 4))])
+        if k == 3:
+            inner = _rand3d(bld, rng, min(depth, 1), rich)
+            mn, mx = inner.Bounds()
+            return bld.OverloadShader3DBounds(inner, mn - 0.1, mx + 0.2)
+        return bld.NewBoundsBoxFrame(np.float32([-u(0.5, 1), -u(0.5, 1), -u(0.5, 1)]), np.float32([u(0.5, 1), u(0.5, 1), u(0.5, 1)]))
     if depth <= 0 or rng.random() < 0.2:
         k = int(rng.integers(0, 10))
         if k == 0: return bld.NewSphere(u(0.3, 1.2))
@@ -310,14 +333,14 @@ def _rand3d(bld, rng, depth):
         if k == 4: return bld.NewTorus(u(0.8, 1.5), u(0.1, 0.35))
         if k == 5: return bld.NewBoxFrame(u(0.8, 1.5), u(0.8, 1.5), u(0.8, 1.5), u(0.05, 0.15))
         if k == 6: return bld.NewTriangularPrism(u(0.5, 1.2), u(0.3, 1.5))
-        if k == 7: return bld.Extrude(_rand2d(bld, rng, 1), u(0.3, 2.0))
-        if k == 8: return bld.Revolve(bld.Translate2D(_rand2d(bld, rng, 1), u(1.5, 3.0), 0), 0 if rng.random() < 0.5 else u(0.1, 0.5))
+        if k == 7: return bld.Extrude(_rand2d(bld, rng, 1, rich), u(0.3, 2.0))
+        if k == 8: return bld.Revolve(bld.Translate2D(_rand2d(bld, rng, 1, rich), u(1.5, 3.0), 0), 0 if rng.random() < 0.5 else u(0.1, 0.5))
         T = gsdf.threads
         return T.Screw(bld, u(1.0, 3.0), T.ISO(u(0.8, 1.6), u(0.1, 0.3), bool(rng.integers(0, 2))))
     k = int(rng.integers(0, 18))
-    a = _rand3d(bld, rng, depth - 1)
-    other = lambda: bld.Translate(_rand3d(bld, rng, depth - 1), u(-0.6, 0.6), u(-0.6, 0.6), u(-0.6, 0.6))
-    if k == 0: return bld.Union(a, other(), *[_rand3d(bld, rng, 0) for _ in range(int(rng.integers(0, 3)))])
+    a = _rand3d(bld, rng, depth - 1, rich)
+    other = lambda: bld.Translate(_rand3d(bld, rng, depth - 1, rich), u(-0.6, 0.6), u(-0.6, 0.6), u(-0.6, 0.6))
+    if k == 0: return bld.Union(a, other(), *[_rand3d(bld, rng, 0, rich) for _ in range(int(rng.integers(0, 3)))])
     if k == 1: return bld.Difference(a, other())
     if k == 2: return bld.Intersection(a, other())
     if k == 3: return bld.Xor(a, other())
@@ -340,12 +363,12 @@ def _rand3d(bld, rng, depth):
                              [u(-0.2, 0.2), 0, u(0.8, 1.2), u(-0.5, 0.5)], [0, 0, 0, 1]])
 
 
-def random_trees(bld, seed, count, dim=3, depth=4, max_dstack=16, max_pstack=8):
+def random_trees(bld, seed, count, dim=3, depth=4, max_dstack=16, max_pstack=8, rich=False):
     """`count` seeded random trees (numpy Generator, PCG64: reproducible everywhere) that fit the interpreter's stacks."""
     rng = np.random.default_rng(seed)
     out = []
     while len(out) < count:
-        s = (_rand3d if dim == 3 else _rand2d)(bld, rng, depth)
+        s = (_rand3d if dim == 3 else _rand2d)(bld, rng, depth, rich)
         f = bld.flatten(s)
         if f["dstack"] > max_dstack or f["pstack"] > max_pstack:
             continue
