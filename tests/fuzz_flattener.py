@@ -37,13 +37,13 @@ def main():
                     if not P.supported():
                         continue
                     pos = shapes.sample_points(s)
-                    if len(pos) > 20000:
-                        pos = pos[::len(pos) // 20000 + 1]
+                    if len(pos) > int(os.environ.get("FUZZ_MAXPTS", "20000")):
+                        pos = pos[::len(pos) // int(os.environ.get("FUZZ_MAXPTS", "20000")) + 1]
                     t = O.Tree.from_shader(s)
                     want = t.eval2(pos) if s.is2d else t.eval3(pos)
                     n += 1
                     try:
-                        got = progsim.run(P, pos, M, tile=256)
+                        got = progsim.run(P, pos, M, tile=int(os.environ.get("FUZZ_TILE", "256")))
                     except AssertionError as e:
                         print("ASSERT", dim, seed, depth, name, e)
                         bad += 1
