@@ -422,3 +422,32 @@ def _run_tile(P, pos, M, stats):
     assert max(max_d - 1, 1) <= P.dstack and max_p <= P.pstack, (max_d, P.dstack, max_p, P.pstack)
     assert len(dstk) == 1 and not pstk and not skip, (len(dstk), len(pstk), skip)
     return top
+
+
+def main(argv):
+    """python tests/progsim.py program.blob program.aux points.npy [out.npy] -- run a flattened program (the two buffers a
+    host-side flattener hands to gsdf_program_create, e.g. written by the Go flattener of integration/go/) on the CPU
+    model and print / save the distances. Lets a maintainer check a flattener against the C++ one without a GPU."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import oracle as O
+    O.build()
+    blob = open(argv[1], "rb").read()
+    aux = np.fromfile(argv[2], dtype=np.float32)
+    pos = np.load(argv[3]).astype(np.float32)
+    P = Program(blob, aux)
+    assert P.supported(), "the model does not implement ellipse2D / quadbezier2d"
+    assert pos.ndim == 2 and pos.shape[1] == P.dim, "points must be (n, %d)" % P.dim
+    d = run(P, pos, Math(O))
+    if len(argv) > 4:
+        np.save(argv[4], d)
+    else:
+        np.set_printoptions(precision=9, suppress=False)
+        print(d)
+    return 0
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main(sys.argv))
