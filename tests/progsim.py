@@ -6,7 +6,7 @@ interpreter. Every float32 operation is an individually rounded numpy operation 
 it; the transcendental functions are the oracle's restated math32 routines, called per element. The oracle evaluates
 the TREE, so   progsim(flatten(tree)) == oracle(tree)   bit for bit is a check of the host-side flattener (operand
 order, derived constants, stack slots, position liveness, guard targets) that needs no GPU. It is test
-infrastructure: nothing in the product path imports it.
+infrastructure: nothing in the product path imports it. Every opcode is modelled.
 """
 import ctypes as C
 import struct
@@ -26,7 +26,7 @@ RXY_READ, RXY_WRITE = 0x100, 0x200  # experimental radius reuse (include/gsdf_pr
 # True reproduces the box-guard predicate as first shipped (points INSIDE the operand's box could vote for the skip): kept so
 # that a test can show the overlapping-operand shapes of tests/shapes.py::overlap2d catch exactly that defect.
 LEGACY_BOX_GUARD = False
-UNSUPPORTED = {OP["ELLIPSE2D"], OP["BEZIERQ2D"]}  # the EXT interpreter's primitives (double-precision cbrt, exp/log) are not modelled
+UNSUPPORTED = set()  # every opcode is modelled (ellipse2D / quadbezier2d: the EXT interpreter's primitives, per element)
 
 
 class Math:
@@ -42,6 +42,16 @@ class Math:
     def _2(self, fn, x, y):
         x, y = np.broadcast_arrays(np.asarray(x, F), np.asarray(y, F))
         return np.array([fn(C.c_float(float(a)), C.c_float(float(b))) for a, b in zip(x.ravel(), y.ravel())], dtype=F).reshape(x.shape)
+
+    def acos(self, x): return self._1(self.L.go_acos, x)
+    def cbrt(self, x): return self._1(self.L.go_cbrt, x)
+
+    def pow_frac(self, x, y):
+        """math32.Pow for the quadratic Bezier's cube roots: 0 -> 0, 1 -> 1, else Exp(y * Log(x)) (oracle go_pow_frac)."""
+        x = np.asarray(x, F)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            r = self._1(self.L.go_exp, F(y) * self._1(self.L.go_log, np.where(x > 0, x, F(1))))
+        return np.where(x == 0, F(0), np.where(x == 1, F(1), r)).astype(F)
 
     def sin(self, x): return self._1(self.L.go_sin, x)
     def cos(self, x): return self._1(self.L.go_cos, x)
@@ -256,6 +266,81 @@ def _run_tile(P, pos, M, stats):
             x, y = np.abs(px), np.abs(py)
             sub = F(0.5) * np.minimum(x + y, f2)
             top = M.norm2(x - sub, y - sub) - f3
+        elif name == "ELLIPSE2D":  # cpu_evaluators.go:750-791, interp.cuh EXT
+            pushD()
+            sq3 = F(1.7320508075688772)
+            x, y = np.abs(px), np.abs(py)
+            swap = x > y
+            a = np.where(swap, f3, f2).astype(F)
+            b = np.where(swap, f2, f3).astype(F)
+            x, y = np.where(swap, y, x).astype(F), np.where(swap, x, y).astype(F)
+            with np.errstate(all="ignore"):
+                l = b * b - a * a
+                mm = a * x / l; m2 = mm * mm
+                nn = b * y / l; n2 = nn * nn
+                c = (m2 + n2 - F(1)) / F(3)
+                c3_ = c * c * c
+                q = c3_ + F(2) * m2 * n2
+                d = c3_ + m2 * n2
+                g = mm + mm * n2
+                # d < 0 branch
+                hh = M.acos(q / c3_) / F(3)
+                sh, ch = M.sin(hh), M.cos(hh)
+                t = sq3 * sh
+                rx = np.sqrt(-c * (ch + t + F(2)) + m2)
+                ry = np.sqrt(-c * (ch - t + F(2)) + m2)
+                co1 = (ry + signf(l) * rx + np.abs(g) / (rx * ry) - mm) / F(2)
+                # d >= 0 branch
+                h2 = F(2) * mm * nn * np.sqrt(d)
+                s_ = signf(q + h2) * M.cbrt(np.abs(q + h2))
+                u_ = signf(q - h2) * M.cbrt(np.abs(q - h2))
+                rx2 = -s_ - u_ - F(4) * c + F(2) * m2
+                ry2 = sq3 * (s_ - u_)
+                rm = M.hypot(rx2, ry2)
+                co2 = (ry2 / np.sqrt(rm - rx2) + F(2) * g / rm - mm) / F(2)
+                co = np.where(d < 0, co1, co2).astype(F)
+                ex, ey = a * co, b * np.sqrt(F(1) - co * co)
+                top = M.norm2(ex - x, ey - y) * signf(y - ey)
+        elif name == "BEZIERQ2D":  # cpu_evaluators.go:581-659, interp.cuh EXT
+            pushD()
+            sq3 = F(1.7320508075688772)
+            third = F(1. / 3)
+            with np.errstate(all="ignore"):
+                dx, dy = c1[0] - px, c1[1] - py
+                ky = c3[0] * (F(2) * c3[3] + (dx * c2[0] + dy * c2[1])) / F(3)
+                kz = c3[0] * (dx * c1[2] + dy * c1[3])
+                g = ky - c3[2]
+                q = c3[1] * (F(2) * c3[2] - F(3) * ky) + kz
+                g3 = g * g * g
+                q2 = q * q
+                hh = q2 + F(4) * g3
+                # hh >= 0
+                sh = np.sqrt(hh)
+                xx, xy = F(0.5) * (sh + -q), F(0.5) * (-sh + -q)
+                k = (F(1.0) - g3 / q2) * g3 / q
+                small = np.abs(g) < F(0.001)
+                xx = np.where(small, k, xx).astype(F); xy = np.where(small, -k - q, xy).astype(F)
+                ux = signf(xx) * M.pow_frac(np.abs(xx), third)
+                uy = signf(xy) * M.pow_frac(np.abs(xy), third)
+                t = ux + uy
+                t = t - (t * (t * t + F(3.0) * g) + q) / (F(3.0) * t * t + F(3.0) * g)
+                t = clampf(t - c3[1], 0, 1)
+                wx, wy = dx + t * (c2[2] + t * c2[0]), dy + t * (c2[3] + t * c2[1])
+                res1 = wx * wx + wy * wy
+                # hh < 0
+                z = np.sqrt(-g)
+                xm = np.sqrt(F(0.5) + F(0.5) * (q / (F(2) * g * z)))
+                mm = xm * (xm * (xm * (xm * F(-0.008972) + F(0.039071)) - F(0.107074)) + F(0.576975)) + F(0.5)
+                nn = np.sqrt(F(1) - mm * mm)
+                nn = nn * sq3
+                tx = clampf((mm + mm) * z - c3[1], 0, 1)
+                ty = clampf((-nn - mm) * z - c3[1], 0, 1)
+                qxx, qxy = dx + tx * (c2[2] + tx * c2[0]), dy + tx * (c2[3] + tx * c2[1])
+                qyx, qyy = dx + ty * (c2[2] + ty * c2[0]), dy + ty * (c2[3] + ty * c2[1])
+                ddx, ddy = qxx * qxx + qxy * qxy, qyx * qyx + qyy * qyy
+                res2 = np.where(ddx < ddy, ddx, ddy)
+                res = np.where(hh >= 0, res1, res2).astype(F)
+                top = np.sqrt(res) - f2
         elif name == "POLY2D":
             rec = P.aux4[w1 >> 2:]
             ax, ay = px - rec[0][0], py - rec[0][1]

@@ -279,6 +279,9 @@ def _rand2d(bld, rng, depth, rich=False):
         if k == 1:
             return bld.TranslateMulti2D(_rand2d(bld, rng, min(depth, 1), rich), rng.uniform(-1.5, 1.5, (int(rng.integers(1, 5)), 2)).astype(np.float32))
         if k == 2:
+            if rng.random() < 0.5:
+                return bld.NewEllipse(u(0.3, 1.5), u(0.3, 1.5)) if rng.random() < 0.5 else \
+                    bld.NewQuadraticBezier2D((u(-1, 0), u(-1, 0)), (u(-0.5, 0.5), u(0.2, 1)), (u(0.2, 1), u(-0.5, 0.5)), u(0.03, 0.2))
             return T.Thread(bld, T.ISO(u(0.8, 3.0), u(0.1, 0.5), bool(rng.integers(0, 2))))
         return T.Thread(bld, [T.NPT(0.5), T.UTS(0.5, 13, True), T.Acme(1.0, 0.2), T.PlasticButtress(1.0, 0.2)][int(rng.integers(0, 4))])
     if depth <= 0 or rng.random() < 0.1:

@@ -114,9 +114,17 @@ def test_box_guards_never_vote_with_points_inside_the_box(oracle, bld, M):
     assert caught >= 2   # at the device's own tile size
 
 
-def test_model_rejects_what_it_does_not_implement(bld):
-    f = bld.flatten(bld.NewEllipse(1, 2))
-    assert not progsim.Program(f["blob"], f["aux"]).supported()
+def test_model_covers_every_opcode(oracle, bld, M):
+    """Every opcode of include/gsdf_program.h is modelled, the EXT interpreter's ellipse2D / quadbezier2d included
+    (their acos / cbrt / exp-log cube roots come from the oracle's math32 restatement)."""
+    import re, os
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "gsdf_program.h")).read()
+    enum = hdr[hdr.index("enum gsdf_opcode"):]
+    names = [n for n in re.findall(r"\bGSDF_OP_([A-Z0-9_]+)\b\s*(?:=\s*0\s*)?,", enum[:enum.index("};")]) if n != "_COUNT"]
+    assert names == progsim.OPS
+    for name, s in shapes.primitives2d(bld):
+        if "ellipse" in name or "bezier" in name:
+            assert sim_vs_oracle(oracle, bld, M, name, s, shapes.sample_points(s, dense=[40, 40])) is not None
 
 
 def test_radius_reuse_programs_are_bit_identical_and_gated(oracle, bld, M, monkeypatch):
