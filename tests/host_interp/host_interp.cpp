@@ -1,0 +1,39 @@
+// Test infrastructure: the device interpreter's own source (gsdf_b200/csrc/interp.cuh, math32.cuh) compiled for the host.
+// g++ -O2 -ffp-contract=off -I tests/host_interp/shim -I gsdf_b200/csrc ... -> every float32 operation rounds individually,
+// like nvcc -fmad=false with the _rn intrinsics on the device. What differs from the GPU: the math32 helpers take their
+// host branches (sqrtf, a / b instead of __fsqrt_rn, __fdiv_rn -- the same IEEE operations), one machine at a time
+// instead of 512 threads, and a guard's vote spans the 4 points of one machine instead of a 2048-point tile (a finer
+// tiling; guards must be value-preserving under ANY tiling).
+#include <cuda_runtime.h>  // the shim
+#include <vector>
+#include <algorithm>
+
+#include "interp.cuh"
+
+extern "C" int host_interp_eval(const uint32_t *chunks, const float *aux, uint32_t dslots, uint32_t pslots, int dim, const float *pos,
+                                float *out, size_t n, int ext) {
+    using namespace gsdfk;
+    constexpr int P = 4;
+    if (n == 0) return 0;
+    std::vector<float> dstk((size_t)P * (dslots + 1)), pstk((size_t)P * 3 * (pslots + 1));
+#ifdef GSDF_RXY
+    std::vector<float> rxy(P);  // the experimental radius cache (gsdf_program.h, "Radius reuse"): one float per point
+#endif
+    for (size_t i = 0; i < n; i += P) {
+        Machine<P> m;
+        m.init(dstk.data(), pstk.data(), 1);
+#ifdef GSDF_RXY
+        m.rxy = rxy.data();
+#endif
+        for (int j = 0; j < P; j++) {
+            const size_t idx = std::min(i + j, n - 1);
+            m.px[j] = pos[dim * idx];
+            m.py[j] = pos[dim * idx + 1];
+            m.pz[j] = dim == 3 ? pos[dim * idx + 2] : 0.f;
+        }
+        if (ext) run_program<P, true>(m, reinterpret_cast<const uint4 *>(chunks), reinterpret_cast<const float4 *>(aux));
+        else run_program<P, false>(m, reinterpret_cast<const uint4 *>(chunks), reinterpret_cast<const float4 *>(aux));
+        for (int j = 0; j < P && i + j < n; j++) out[i + j] = m.top[j];
+    }
+    return 0;
+}

@@ -1,0 +1,75 @@
+"""The interpreter source the GPU runs (interp.cuh), compiled for the host (tests/hostinterp.py), against the oracle: the
+same bit-for-bit bar as the GPU parity tests, on the CPU. This is what validated the box-guard correction of DESIGN.md
+section 2 on the real source before any GPU saw it (the previous revision of interp.cuh fails these tests on the
+overlapping-operand shapes and on two of the seeded random trees)."""
+import numpy as np
+import pytest
+
+import fontfix
+import hostinterp
+import progsim
+import shapes
+from gsdf_b200 import gsdf
+
+
+def check(oracle, bld, name, s, pos=None, variant=None):
+    pos = shapes.sample_points(s) if pos is None else pos
+    t = oracle.Tree.from_shader(s)
+    want = t.eval2(pos) if s.is2d else t.eval3(pos)
+    got = hostinterp.run(bld.flatten(s), pos, variant)
+    diff = (got.view(np.uint32) != want.view(np.uint32)) & ~(np.isnan(got) & np.isnan(want))
+    assert not diff.any(), "%s: %d of %d distances differ from the oracle" % (name, int(diff.sum()), len(pos))
+
+
+@pytest.mark.parametrize("corpus", ["all3d", "all2d", "dag3d"])
+def test_device_interpreter_source_matches_oracle(oracle, bld, corpus):
+    for name, s in getattr(shapes, corpus)(bld):
+        check(oracle, bld, name, s)
+
+
+def test_device_interpreter_source_on_random_trees(oracle, bld):
+    for dim in (3, 2):
+        for seed in (1, 2, 3):
+            for name, s in shapes.random_trees(bld, seed, 40, dim):
+                check(oracle, bld, name, s)
+        for name, s in shapes.random_trees(bld, 77, 60, dim, depth=5, rich=True):
+            check(oracle, bld, name, s)
+
+
+def test_device_interpreter_source_guards(oracle, bld, monkeypatch):
+    """Guards vote over the 4 points of one machine here (the finest tiling the source allows): slab guards on the
+    BASELINE scenes, box guards on overlapping operands and on a text line, each equal to the oracle; unguarded too."""
+    for name, s in shapes.overlap2d(bld):
+        check(oracle, bld, name, s, shapes.overlap2d_points(name, s)[:8192])
+    text = fontfix.text_scene(bld, "A8b")
+    mn, mx = text.Bounds()
+    pos = shapes.append_grid(mn - 0.05, mx + 0.05, [160, 60])
+    check(oracle, bld, "text", text, pos)
+    flange = gsdf.scene(bld, "npt-flange")
+    dense = shapes.sample_points(flange, dense=[48, 48, 24])
+    check(oracle, bld, "flange", flange, dense)
+    monkeypatch.setenv("GSDF_NO_GUARDS", "1")
+    check(oracle, bld, "text/no guards", text, pos)
+    check(oracle, bld, "flange/no guards", flange, dense)
+
+
+def test_experimental_radius_reuse_device_code(oracle, bld, monkeypatch):
+    """The -DGSDF_RXY side of interp.cuh (Machine::radius and the four consumers), which is not part of the default
+    build and has not run on a GPU: with GSDF_RXY=1 programs it must still equal the oracle bit for bit."""
+    monkeypatch.setenv("GSDF_RXY", "1")
+    flagged = 0
+    for name, s in shapes.all3d(bld) + shapes.all2d(bld) + shapes.dag3d(bld) + shapes.random_trees(bld, 5, 60, 3, depth=5, rich=True):
+        words = np.frombuffer(bld.flatten(s)["blob"], np.uint32, offset=32).reshape(-1, 4)
+        pc, hit = 0, False
+        while True:   # instruction headers only: CYLINDER / TORUS / CIRCLE2D keep the flags in w1, SCREW_ENTER in w2
+            op, ln = int(words[pc, 0]) & 0xff, (int(words[pc, 0]) >> 8) & 0xff
+            if op in (progsim.OP["CYLINDER"], progsim.OP["TORUS"], progsim.OP["CIRCLE2D"]):
+                hit |= bool(int(words[pc, 1]) & 0x300)
+            if op == progsim.OP["SCREW_ENTER"]:
+                hit |= bool(int(words[pc, 2]) & 0x300)
+            if op == 0:
+                break
+            pc += ln
+        flagged += hit
+        check(oracle, bld, name, s, variant="GSDF_RXY")
+    assert flagged >= 5
