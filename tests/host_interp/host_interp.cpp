@@ -37,3 +37,35 @@ extern "C" int host_interp_eval(const uint32_t *chunks, const float *aux, uint32
     }
     return 0;
 }
+
+// math32.cuh's elementary functions (host branches) over arrays, for dense comparisons with the oracle's restatement.
+extern "C" void host_m32_unary(int fn, const float *x, float *out, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        float s, c;
+        switch (fn) {
+        case 0: out[i] = m32::sin(x[i]); break;
+        case 1: out[i] = m32::cos(x[i]); break;
+        case 2: out[i] = m32::tan(x[i]); break;
+        case 3: out[i] = m32::atan(x[i]); break;
+        case 4: out[i] = m32::acos(x[i]); break;
+        case 5: out[i] = m32::cbrt32(x[i]); break;
+        case 6: out[i] = m32::log32(x[i]); break;
+        case 7: out[i] = m32::exp32(x[i]); break;
+        case 8: m32::sincos(x[i], s, c); out[i] = s; break;
+        case 9: m32::sincos(x[i], s, c); out[i] = c; break;
+        case 10: out[i] = m32::sqrt(x[i]); break;
+        default: out[i] = 0.f;
+        }
+    }
+}
+extern "C" void host_m32_binary(int fn, const float *x, const float *y, float *out, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        switch (fn) {
+        case 0: out[i] = m32::hypot32(x[i], y[i]); break;
+        case 1: out[i] = m32::atan2(x[i], y[i]); break;
+        case 2: out[i] = m32::minf(x[i], y[i]); break;
+        case 3: out[i] = m32::maxf(x[i], y[i]); break;
+        default: out[i] = 0.f;
+        }
+    }
+}
