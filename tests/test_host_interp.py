@@ -110,3 +110,19 @@ def test_math32_source_matches_oracle(oracle):
         if fn >= 2:
             d &= ~(np.isnan(x) | np.isnan(y))   # NaN operands: fminf / fmaxf return the other operand, Go returns NaN
         assert not d.any(), ofn
+
+
+@pytest.mark.parametrize("scene,resdiv,stride", [("npt-flange", 400, 1), ("bolt", 800, 32), ("knurled-cylinder", 1600, 128)])
+def test_full_size_baseline_lattices(oracle, bld, scene, resdiv, stride):
+    """BASELINE configs 1-3 at their full resolution: every corner of the npt-flange@400 lattice (6,711,685 points), every
+    32nd / 128th corner plane of bolt@800 and knurled-cylinder@1600 -- the interpreter source equals the oracle on each."""
+    s = gsdf.scene(bld, scene)
+    res = np.float32(s.Diagonal() / np.float32(resdiv))
+    lat = oracle.flat_lattice(*s.Bounds(), res)
+    nx, ny, nz = lat.n
+    ax = [(np.float32(lat.origin[a]) + np.arange(n + 1, dtype=np.float32) * res).astype(np.float32) for a, n in enumerate((nx, ny, nz))]
+    Z, Y, X = np.meshgrid(ax[2][::stride], ax[1], ax[0], indexing="ij")
+    pos = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1).astype(np.float32)
+    if scene == "npt-flange":
+        assert len(pos) == 6711685   # README.md:130 (+1 probe)
+    check(oracle, bld, scene, s, pos)
