@@ -47,7 +47,9 @@ public:
 private:
     struct Table { uint32_t off = 0, len = 0; };
     bool table(const char *tag, Table &t) const;
-    uint16_t u16(size_t o) const { return (uint16_t)((d_[o] << 8) | d_[o + 1]); }
+    // Every multi-byte read goes through here and is bounds-checked: offsets come from the file, and a damaged font must
+    // end in an error or an empty glyph, never in a read outside the buffer (found by fuzzing mutated fonts under ASan).
+    uint16_t u16(size_t o) const { return o + 2 <= d_.size() ? (uint16_t)((d_[o] << 8) | d_[o + 1]) : (uint16_t)0; }
     int16_t i16(size_t o) const { return (int16_t)u16(o); }
     uint32_t u32(size_t o) const { return ((uint32_t)u16(o) << 16) | u16(o + 2); }
     bool glyphRange(int idx, uint32_t &beg, uint32_t &end) const;

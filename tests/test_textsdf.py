@@ -232,3 +232,36 @@ def test_box_guards_are_emitted_for_the_text_union(bld, monkeypatch):
     monkeypatch.setenv("GSDF_NO_GUARDS", "1")
     plain = [o[1] for o in _ops(bld.flatten(s))]
     assert OP_CULL not in plain and OP_BBOX not in plain and plain.count(OP_MIN) == 6
+
+
+def test_damaged_fonts_fail_cleanly():
+    """LoadTTFBytes takes caller-supplied bytes (font.go:54): truncated or corrupted fonts must end in an error or a
+    parsed font, never in a crash. 600 seeded mutations of the fixture font (byte flips, truncations, 4-byte splats);
+    fuzzing the same mutations under AddressSanitizer found an out-of-bounds read in the cmap lookup, fixed by
+    bounds-checking every multi-byte read (host/textsdf.h)."""
+    base = bytearray(fontfix.subset_ttf())
+    rng = np.random.default_rng(3)
+    parsed = failed = 0
+    for it in range(600):
+        b = bytearray(base)
+        k = int(rng.integers(0, 3))
+        if k == 0:
+            for _ in range(int(rng.integers(1, 8))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        elif k == 1:
+            b = b[:int(rng.integers(0, len(b)))]
+        else:
+            i = int(rng.integers(0, len(b) - 4))
+            b[i:i + 4] = bytes(rng.integers(0, 256, 4, dtype=np.uint8))
+        f = textsdf.Font()
+        f.Configure(RelativeGlyphTolerance=0.01)
+        try:
+            f.LoadTTFBytes(bytes(b))
+            bld = gsdf.Builder(panic_on_error=False)
+            s = f.TextLine(bld, "Ab1~c8p23")
+            s.Bounds()
+            bld.flatten(s)
+            parsed += 1
+        except Exception:
+            failed += 1
+    assert parsed > 50 and failed > 50
