@@ -232,6 +232,42 @@ int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_
         if (op == GSDF_OP_END) { ended = true; break; }
     }
     if (!ended || pc != h.nchunks) return fail(GSDF_EPROGRAM, "program does not end with END at its last chunk");
+    // Stack discipline against the header. The stream is straight-line (a firing guard skips a region whose net effect
+    // on both stacks is zero), so one walk gives the depth at every instruction. The kernels size their shared-memory
+    // stacks from the header: a program that pushes deeper than it declares would write outside them.
+    int d = 0, dmax = 0, ps = 0, pmax = 0;
+    n = 0;
+    for (pc = 0; pc < h.nchunks; n++) {
+        const uint32_t op = chunks[4 * pc] & 0xff, len = (chunks[4 * pc] >> 8) & 0xff;
+        int dd = 0, dp = 0, needd = 0, needp = 0;
+        switch (op) {
+        case GSDF_OP_SPHERE: case GSDF_OP_BOX: case GSDF_OP_BOXFRAME: case GSDF_OP_TORUS: case GSDF_OP_CYLINDER: case GSDF_OP_HEX:
+        case GSDF_OP_CIRCLE2D: case GSDF_OP_RECT2D: case GSDF_OP_LINE2D: case GSDF_OP_LINES2D: case GSDF_OP_ARC2D: case GSDF_OP_EQTRI2D:
+        case GSDF_OP_HEX2D: case GSDF_OP_OCT2D: case GSDF_OP_DIAMOND2D: case GSDF_OP_ROUNDX2D: case GSDF_OP_POLY2D: case GSDF_OP_ELLIPSE2D:
+        case GSDF_OP_BEZIERQ2D: case GSDF_OP_CULL_UB2D: case GSDF_OP_ELONGATE: case GSDF_OP_ELONGATE2D: case GSDF_OP_EXTRUDE_ENTER:
+        case GSDF_OP_SCREW_ENTER:
+            dd = 1; break;
+        case GSDF_OP_MIN: case GSDF_OP_MAX: case GSDF_OP_DIFF: case GSDF_OP_XOR: case GSDF_OP_SMOOTH_UNION: case GSDF_OP_SMOOTH_DIFF:
+        case GSDF_OP_SMOOTH_INTERSECT: case GSDF_OP_ADD_BELOW: case GSDF_OP_EXTRUDE_EXIT: case GSDF_OP_MAX_BELOW:
+            dd = -1; needd = 2; break;
+        case GSDF_OP_OFFSET: case GSDF_OP_ANNULUS: case GSDF_OP_MULDIST: case GSDF_OP_SHELL_EXIT: case GSDF_OP_BBOX_GUARD2D:
+            needd = 1; break;
+        case GSDF_OP_PUSH_POS: case GSDF_OP_CIRC_ENTER: dp = 1; break;
+        case GSDF_OP_POP_POS: dp = -1; needp = 1; break;
+        case GSDF_OP_PEEK_POS: needp = 1; break;
+        default: break;
+        }
+        if (d < needd) return fail(GSDF_EPROGRAM, "instruction %u (opcode %u): distance stack underflow", n, op);
+        if (ps < needp) return fail(GSDF_EPROGRAM, "instruction %u (opcode %u): position stack underflow", n, op);
+        d += dd; ps += dp;
+        dmax = std::max(dmax, d); pmax = std::max(pmax, ps);
+        if (op == GSDF_OP_END) break;
+        pc += len;
+    }
+    if (d != 1 || ps != 0) return fail(GSDF_EPROGRAM, "program leaves %d distances and %d positions on its stacks (expected 1 and 0)", d, ps);
+    // the top of the distance stack lives in registers and slot 0 absorbs the first push: dmax values need dmax - 1 slots
+    if ((uint32_t)std::max(dmax - 1, 1) > h.dstack || (uint32_t)pmax > h.pstack)
+        return fail(GSDF_EPROGRAM, "program needs %d distance and %d position stack slots, its header declares %u and %u", std::max(dmax - 1, 1), pmax, h.dstack, h.pstack);
     return 0;
 }
 

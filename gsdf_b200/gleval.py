@@ -38,7 +38,9 @@ class _SDFCUDA:
         h = C.c_void_p()
         rc = lib.gsdfh_compile(shader.bld._h, shader.id, C.byref(h))
         if rc != 0:
-            raise GsdfError(rc, shader.bld.Err() or _lib.last_error())
+            msg = shader.bld.Err() or _lib.last_error()
+            shader.bld.ClearErrors()  # reported through the exception: must not poison later shape construction on this builder
+            raise GsdfError(rc, msg)
         self._h = h
         self._bounds = shader.Bounds()
 

@@ -200,6 +200,55 @@ def test_shared_subtrees_flatten_like_duplicated_ones(oracle, bld):
         assert np.isfinite(oracle.Tree.from_shader(s).eval3(shapes.sample_points(s))).all(), name
 
 
+def test_program_create_checks_the_stack_discipline_before_any_device_work(bld):
+    """gsdf_program_create validates the blob before it touches a device (so this runs without a GPU): the kernels size
+    their shared-memory stacks from the header, and a program that pushes deeper than its header declares, pops an empty
+    stack or leaves values behind is refused. Every program of the flattener passes (ECUDA here = accepted, no device)."""
+    import shapes
+    create = _lib.lib.gsdf_program_create
+
+    def rc_of(blob, aux):
+        aux = np.ascontiguousarray(aux, np.float32)
+        h = C.c_void_p()
+        rc = create(bytes(blob), len(blob), aux.ctypes.data_as(C.POINTER(C.c_float)) if aux.size else None, aux.size, C.byref(h))
+        if rc == 0:
+            _lib.lib.gsdf_program_destroy(h)
+        return rc
+    accepted = (_lib.OK, _lib.ECUDA)
+    for name, s in shapes.all3d(bld) + shapes.all2d(bld) + shapes.dag3d(bld) + shapes.overlap2d(bld) + shapes.random_trees(bld, 9, 60, 3, depth=5, rich=True):
+        f = bld.flatten(s)
+        assert rc_of(f["blob"], f["aux"]) in accepted, name
+    f = bld.flatten(gsdf.scene(bld, "npt-flange"))     # dstack 2, pstack 1
+    hdr = list(struct.unpack_from("<8I", f["blob"], 0))
+    assert (hdr[4], hdr[5]) == (2, 1)
+    for field, value in ((4, 1), (5, 0)):               # header declares fewer slots than the stream uses
+        h2 = list(hdr)
+        h2[field] = value
+        assert rc_of(struct.pack("<8I", *h2) + f["blob"][32:], f["aux"]) == _lib.EPROGRAM
+        assert "stack slots" in _lib.last_error()
+    words = np.frombuffer(f["blob"], np.uint32, offset=32).reshape(-1, 4).copy()
+    headers, pc = [], 0                                                        # (chunk index, opcode) of every instruction
+    while True:
+        op, ln = int(words[pc, 0]) & 0xff, (int(words[pc, 0]) >> 8) & 0xff
+        headers.append((pc, op))
+        if op == 0:
+            break
+        pc += ln
+    PUSH_POS, POP_POS, DIFF, OFFSET, MIN = 34, 35, 22, 27, 20
+    pop = [i for i, op in headers if op == POP_POS][0]
+    bad = words.copy()
+    bad[pop, 0] = (bad[pop, 0] & ~np.uint32(0xff)) | np.uint32(PUSH_POS)      # a POP_POS turned into a second PUSH_POS
+    assert rc_of(f["blob"][:32] + bad.tobytes(), f["aux"]) == _lib.EPROGRAM
+    bad = words.copy()
+    diff = [i for i, op in headers if op == DIFF][-1]                          # the last DIFF becomes OFFSET: a value is left behind
+    bad[diff, 0] = (bad[diff, 0] & ~np.uint32(0xff)) | np.uint32(OFFSET)
+    assert rc_of(f["blob"][:32] + bad.tobytes(), f["aux"]) == _lib.EPROGRAM
+    sphere = bld.flatten(bld.NewSphere(1))
+    w = np.frombuffer(sphere["blob"], np.uint32, offset=32).reshape(-1, 4).copy()
+    w[0, 0] = (w[0, 0] & ~np.uint32(0xff)) | np.uint32(MIN)                   # MIN on an empty stack
+    assert rc_of(sphere["blob"][:32] + w.tobytes(), sphere["aux"]) == _lib.EPROGRAM and "underflow" in _lib.last_error()
+
+
 def test_position_liveness(bld):
     """A transform whose position nobody reads again must not save it: scale(translate(sphere)) needs no P slots,
     union(translate(a), b) needs one."""
