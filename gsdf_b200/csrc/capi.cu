@@ -236,9 +236,11 @@ int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_
     // on both stacks is zero), so one walk gives the depth at every instruction. The kernels size their shared-memory
     // stacks from the header: a program that pushes deeper than it declares would write outside them.
     int d = 0, dmax = 0, ps = 0, pmax = 0;
+    std::vector<int> dAt(h.nchunks, -1), pAt(h.nchunks, -1);  // depths BEFORE the instruction that starts at a chunk
     n = 0;
     for (pc = 0; pc < h.nchunks; n++) {
         const uint32_t op = chunks[4 * pc] & 0xff, len = (chunks[4 * pc] >> 8) & 0xff;
+        dAt[pc] = d; pAt[pc] = ps;
         int dd = 0, dp = 0, needd = 0, needp = 0;
         switch (op) {
         case GSDF_OP_SPHERE: case GSDF_OP_BOX: case GSDF_OP_BOXFRAME: case GSDF_OP_TORUS: case GSDF_OP_CYLINDER: case GSDF_OP_HEX:
@@ -265,6 +267,25 @@ int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_
         pc += len;
     }
     if (d != 1 || ps != 0) return fail(GSDF_EPROGRAM, "program leaves %d distances and %d positions on its stacks (expected 1 and 0)", d, ps);
+    // A firing guard jumps to its target with the `skip` flag set: the skipped region must have produced exactly the one
+    // value its combiner would have consumed, and what lies between the target and that combiner may only restore p.
+    n = 0;
+    for (pc = 0; pc < h.nchunks; n++) {
+        const uint32_t op = chunks[4 * pc] & 0xff, len = (chunks[4 * pc] >> 8) & 0xff;
+        const bool slab = (op == GSDF_OP_EXTRUDE_ENTER || op == GSDF_OP_SCREW_ENTER) && (chunks[4 * pc + 1] & 0xff) != GSDF_GUARD_NONE;
+        if (slab || op == GSDF_OP_BBOX_GUARD2D) {
+            const uint32_t kind = chunks[4 * pc + 1] & 0xff, target = chunks[4 * pc + 1] >> 8;
+            if (dAt[target] != dAt[pc] + 1 || pAt[target] != pAt[pc] || dAt[pc] < 1)
+                return fail(GSDF_EPROGRAM, "instruction %u: the region its guard skips does not leave exactly one value for the combiner", n);
+            uint32_t q = target;
+            while (q < h.nchunks && (chunks[4 * q] & 0xff) == GSDF_OP_POP_POS) q += (chunks[4 * q] >> 8) & 0xff;
+            const uint32_t comb = q < h.nchunks ? (chunks[4 * q] & 0xff) : (uint32_t)GSDF_OP_END;
+            const uint32_t want = kind == GSDF_GUARD_MIN ? (uint32_t)GSDF_OP_MIN : kind == GSDF_GUARD_DIFF ? (uint32_t)GSDF_OP_DIFF : (uint32_t)GSDF_OP_SMOOTH_UNION;
+            if (comb != want) return fail(GSDF_EPROGRAM, "instruction %u: guard kind %u does not lead to its combiner", n, kind);
+        }
+        if (op == GSDF_OP_END) break;
+        pc += len;
+    }
     // the top of the distance stack lives in registers and slot 0 absorbs the first push: dmax values need dmax - 1 slots
     if ((uint32_t)std::max(dmax - 1, 1) > h.dstack || (uint32_t)pmax > h.pstack)
         return fail(GSDF_EPROGRAM, "program needs %d distance and %d position stack slots, its header declares %u and %u", std::max(dmax - 1, 1), pmax, h.dstack, h.pstack);

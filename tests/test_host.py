@@ -243,6 +243,20 @@ def test_program_create_checks_the_stack_discipline_before_any_device_work(bld):
     diff = [i for i, op in headers if op == DIFF][-1]                          # the last DIFF becomes OFFSET: a value is left behind
     bad[diff, 0] = (bad[diff, 0] & ~np.uint32(0xff)) | np.uint32(OFFSET)
     assert rc_of(f["blob"][:32] + bad.tobytes(), f["aux"]) == _lib.EPROGRAM
+    # a guard whose skipped region does not end right in front of its combiner: retarget the flange's screw guard (DIFF kind,
+    # lands on the POP_POS in front of the DIFF) one instruction further, behind the DIFF
+    SCREW_ENTER = 50
+    scr = [i for i, op in headers if op == SCREW_ENTER][0]
+    kind, target = int(words[scr, 1]) & 0xff, int(words[scr, 1]) >> 8
+    assert kind == 1 and dict(headers)[target] == POP_POS
+    after = [i for i, op in headers if i > target and op == DIFF][0]
+    nxt = headers[[i for i, _ in headers].index(after) + 1][0]
+    bad = words.copy()
+    bad[scr, 1] = np.uint32(kind | (nxt << 8))
+    assert rc_of(f["blob"][:32] + bad.tobytes(), f["aux"]) == _lib.EPROGRAM and "guard" in _lib.last_error()
+    bad = words.copy()
+    bad[scr, 1] = np.uint32(2 | (target << 8))                                 # MIN kind in front of a DIFF
+    assert rc_of(f["blob"][:32] + bad.tobytes(), f["aux"]) == _lib.EPROGRAM and "combiner" in _lib.last_error()
     sphere = bld.flatten(bld.NewSphere(1))
     w = np.frombuffer(sphere["blob"], np.uint32, offset=32).reshape(-1, 4).copy()
     w[0, 0] = (w[0, 0] & ~np.uint32(0xff)) | np.uint32(MIN)                   # MIN on an empty stack
