@@ -52,7 +52,10 @@ int gsdf_set_device(int device);
 /* Program -------------------------------------------------------------------------------------------- */
 /* Upload a flattened tree (include/gsdf_program.h). Replaces Programmer.WriteComputeSDF3 + NewComputeGPUSDF3
  * (glbuild/glbuild.go:175, gleval/gpu.go:35): "compile" is an upload of a few KB, done once.
- * blob = gsdf_program_header followed by header.nchunks 16-byte chunks; aux = side buffer of floats. */
+ * blob = gsdf_program_header followed by header.nchunks 16-byte chunks; aux = side buffer of floats.
+ * The blob is validated completely before any device work (GSDF_EPROGRAM otherwise): opcodes and lengths, aux ranges,
+ * guard kinds and targets, the distance / position stack discipline against the header's slot counts, and that every
+ * region a guard can skip leaves exactly the value its combiner consumes. */
 int gsdf_program_create(const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats, gsdf_program **out);
 /* Re-upload a (re-)flattened tree of the same dimension into an existing handle: device buffers, stream and scheduler
  * are reused, so an edited tree costs one small host->device copy (the GL path recompiles its shader instead,
