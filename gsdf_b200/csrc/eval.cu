@@ -1,0 +1,116 @@
+// eval.cu -- the interpreter kernels and their launchers. This is the slow translation unit (one k_eval instantiation per
+// generator and per {default, EXT} interpreter); nothing else includes interp.cuh.
+#include "eval_kernels.cuh"
+#include "internal.cuh"
+
+using namespace gsdfk;
+
+namespace gsdfi {
+
+namespace {
+
+constexpr int kMaxDev = 64;
+
+// Per-kernel, per-device launch facts. cudaFuncSetAttribute and occupancy are per device: the opt-in is made once per
+// (kernel, device) to the device's maximum (so no later, smaller program can lower it under a concurrent launch) and the
+// occupancy of each dynamic-shared-memory size seen is cached per device.
+struct KernelDevCache {
+    std::mutex mu;
+    bool optin[kMaxDev] = {};
+    struct Occ { uint32_t smem; int occ; };
+    std::vector<Occ> occ[kMaxDev];
+};
+
+template <class Kern>
+int kernel_occupancy(KernelDevCache &c, Kern kern, int dev, uint32_t smem, int threads, int *occ_out) {
+    if (dev < 0 || dev >= kMaxDev) return fail(GSDF_EINVAL, "device %d out of range", dev);
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (!c.optin[dev]) {
+        DevInfo di;
+        const int rc = device_info(dev, &di);
+        if (rc) return rc;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
+        c.optin[dev] = true;
+    }
+    for (const auto &o : c.occ[dev])
+        if (o.smem == smem) { *occ_out = o.occ; return 0; }
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    c.occ[dev].push_back({smem, occ});
+    *occ_out = occ;
+    return 0;
+}
+
+// persistent launch: at most one resident wave of CTAs; they pull tiles from the launch's scheduler slot
+template <int P, class Gen, bool EXT>
+int launch_eval_impl(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st, bool pdl, uint32_t *sched) {
+    static KernelDevCache cache;
+    auto kern = k_eval<P, Gen, EXT>;
+    const uint32_t smem = smem_total_bytes<P>(p->pv, kEvalThreads);
+    int occ = 0;
+    const int rc = kernel_occupancy(cache, kern, p->device, smem, kEvalThreads, &occ);
+    if (rc) return rc;
+    if (occ < 1) return fail(GSDF_EPROGRAM, "node program needs %u bytes of shared memory per CTA; does not fit", smem);
+    uint64_t blocks = (nwork_upper_bound + kEvalThreads - 1) / kEvalThreads;
+    blocks = std::min<uint64_t>(blocks, (uint64_t)p->sms * occ);
+    ProgView pv = p->pv;
+    pv.sched = sched ? sched : next_sched(p);
+    if (pdl) CU(launch_chain(true, kern, dim3((unsigned)blocks), dim3(kEvalThreads), smem, st, pv, gen));
+    else kern<<<(unsigned)blocks, kEvalThreads, smem, st>>>(pv, gen);
+    CU(cudaGetLastError());
+    return 0;
+}
+template <int P, class Gen>
+int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st, bool pdl, uint32_t *sched) {
+    if (nwork_upper_bound == 0) return 0;
+    return p->needs_ext ? launch_eval_impl<P, Gen, true>(p, gen, nwork_upper_bound, st, pdl, sched)
+                        : launch_eval_impl<P, Gen, false>(p, gen, nwork_upper_bound, st, pdl, sched);
+}
+
+// Streaming Evaluate (k_eval_stream): persistent grid, one resident wave, tiles dealt round-robin.
+template <int DIM, bool EXT>
+int launch_stream_impl(const gsdf_program *p, const float *d_pos, float *d_dist, uint64_t n, cudaStream_t st) {
+    static KernelDevCache cache;
+    auto kern = k_eval_stream<DIM, EXT>;
+    const uint32_t base = smem_total_bytes<4>(p->pv, kEvalThreads);
+    const uint32_t smem = ((base + 127u) & ~127u) + 2u * stream_stage_bytes<DIM>(kEvalThreads);
+    DevInfo di;
+    int rc = device_info(p->device, &di);
+    if (rc) return rc;
+    if (smem > (uint32_t)di.smem_optin) return 1;  // does not fit: caller falls back to k_eval
+    int occ = 0;
+    rc = kernel_occupancy(cache, kern, p->device, smem, kEvalThreads, &occ);
+    if (rc) return rc;
+    if (occ < 1) return 1;
+    const uint64_t tiles = (n + (uint64_t)kEvalThreads * 4 - 1) / ((uint64_t)kEvalThreads * 4);
+    const unsigned blocks = (unsigned)std::min<uint64_t>(tiles, (uint64_t)p->sms * occ);
+    kern<<<blocks, kEvalThreads, smem, st>>>(p->pv, d_pos, d_dist, n);
+    CU(cudaGetLastError());
+    return 0;
+}
+template <int DIM>
+int launch_stream(const gsdf_program *p, const float *d_pos, float *d_dist, uint64_t n, cudaStream_t st) {
+    static const bool off = getenv("GSDF_NO_STREAM") != nullptr;  // A/B switch
+    if (off || ((((uintptr_t)d_pos | (uintptr_t)d_dist) & 15) != 0) || n < (uint64_t)kEvalThreads * 4) return 1;
+    return p->needs_ext ? launch_stream_impl<DIM, true>(p, d_pos, d_dist, n, st) : launch_stream_impl<DIM, false>(p, d_pos, d_dist, n, st);
+}
+
+}  // namespace
+
+uint32_t *next_sched(const gsdf_program *p, int *slot_index) {
+    gsdf_program *q = const_cast<gsdf_program *>(p);
+    const uint32_t slot = q->sched_next.fetch_add(1u, std::memory_order_relaxed) % (uint32_t)kSchedRing;
+    if (slot_index) *slot_index = (int)slot;
+    return p->d_sched + 2 * slot;
+}
+
+int launch_points3(const gsdf_program *p, const GenPoints3 &g, uint64_t nwork, cudaStream_t st, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, false, sched); }
+int launch_points2(const gsdf_program *p, const GenPoints2 &g, uint64_t nwork, cudaStream_t st, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, false, sched); }
+int launch_grid4(const gsdf_program *p, const GenGrid<4> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, pdl, sched); }
+int launch_centers(const gsdf_program *p, const GenCenters &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched) { return launch_eval<1>(p, g, nwork, st, pdl, sched); }
+int launch_image(const gsdf_program *p, const GenImage &g, uint64_t nwork, cudaStream_t st, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, false, sched); }
+int launch_dc(const gsdf_program *p, const GenDC &g, uint64_t nwork, cudaStream_t st, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, false, sched); }
+int launch_stream3(const gsdf_program *p, const float *d_pos, float *d_dist, uint64_t n, cudaStream_t st) { return launch_stream<3>(p, d_pos, d_dist, n, st); }
+int launch_stream2(const gsdf_program *p, const float *d_pos, float *d_dist, uint64_t n, cudaStream_t st) { return launch_stream<2>(p, d_pos, d_dist, n, st); }
+
+}  // namespace gsdfi

@@ -245,13 +245,4 @@ void gsdfh_flat_info(const gsdfh_flat *f, int32_t info[5]) {
 }
 void gsdfh_flat_free(gsdfh_flat *f) { delete f; }
 
-int gsdfh_compile(gsdfh_builder *b, int32_t root, gsdf_program **out) {
-    gsdfh_flat *f = gsdfh_flatten(b, root);
-    if (!f) return GSDF_EPROGRAM;
-    int rc = gsdf_program_create(f->blob.data(), f->blob.size(), f->prog.aux.data(), f->prog.aux.size(), out);
-    if (rc) b->err = gsdf_last_error();
-    gsdfh_flat_free(f);
-    return rc;
-}
-
 }  // extern "C"

@@ -30,10 +30,32 @@ constexpr float kPiF = (float)kPi;
 constexpr float kTwoPiF = (float)(2 * kPi);
 
 M32_HD float absf(float x) { return fabsf(x); }
-// math32.Min/Max. fminf/fmaxf differ from Go only when an argument is NaN (Go propagates it); the reference's own
-// field-validity test rejects NaN fields (gsdf_test.go:887-910), so the single-instruction form is used.
-M32_HD float minf(float a, float b) { return fminf(a, b); }
-M32_HD float maxf(float a, float b) { return fmaxf(a, b); }
+// math32.Min/Max (Go math semantics): a NaN operand gives NaN, -0 orders below +0. On the device that is exactly PTX
+// min.NaN.f32 / max.NaN.f32 (sm_80+), one instruction like fminf/fmaxf -- which would DROP the NaN and let a union or
+// difference turn an invalid operand (ellipse2D far outside its bounds) into a finite distance. One corner is left:
+// Go returns -Inf for Min(NaN, -Inf) (+Inf for Max(NaN, +Inf)) because it tests the infinity first; here that is NaN.
+M32_HD float minf(float a, float b) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+#else
+    if (a != a || b != b) return __builtin_nanf("");
+    if (a == 0.f && b == 0.f) return __builtin_signbit(a) ? a : b;
+    return a < b ? a : b;
+#endif
+}
+M32_HD float maxf(float a, float b) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+#else
+    if (a != a || b != b) return __builtin_nanf("");
+    if (a == 0.f && b == 0.f) return __builtin_signbit(a) ? b : a;
+    return a > b ? a : b;
+#endif
+}
 
 M32_HD float sqrt(float x) {
 #ifdef __CUDA_ARCH__

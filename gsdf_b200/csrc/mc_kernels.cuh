@@ -1,463 +1,18 @@
-// kernels.cuh -- sm_100a kernels of the SDF evaluate + mesh path.
+// mc_kernels.cuh -- sm_100a kernels of the mesh stage (compiled in mesher.cu).
 //
-//   k_eval<P,Gen>      persistent CTAs pull 256-item tiles from an atomic counter; each thread interprets the node
-//                      program at P points produced by a generator functor (AoS point lists, the dense lattice, a
-//                      compacted quad list, prune-cube centres, image rows) and hands the distances to its sink.
 //   k_compact_quads    octree level-3 prune mask -> compacted list of 4-corner lattice quads that still need evaluating
-//   k_mc_count/emit    marching cubes. Classification from 4 coalesced row loads + shuffles. Pass 1 (warp per cell row)
-//                      writes a triangle count per row and a compact list of non-empty 32-cell segments; an exclusive
-//                      scan turns row counts into offsets; pass 2 (warp per listed segment) places each cell's
-//                      triangles with a warp inclusive scan. Output order is the reference FlatRenderer's (cell index
+//   k_mc_count/emit    marching cubes. Pass 1 writes a triangle count per 32-cell row segment and a compact list of
+//                      non-empty segments; an exclusive scan turns the counts into offsets; pass 2 (warp per listed
+//                      segment) places each cell's triangles. Output order is the reference FlatRenderer's (cell index
 //                      x fastest, flatrenderer.go:208-212) and fully deterministic.
-//   k_scan_*           three-kernel exclusive scan over row counts.
+//   k_scan_*           exclusive scans over segment counts (decoupled look-back, and the three-kernel A/B form).
 //   k_stl_pack         glrender/stl.go:33-61 record packing.
-//
-// The node program (+ side buffer when it fits) is staged into shared memory once per CTA by a 1-D bulk async copy
-// (cp.async.bulk.shared::cluster.global, completion on an mbarrier: SASS UBLKCP / SYNCS).
 #pragma once
-#include <cuda.h>
-#include <cuda_runtime.h>
-#include <stdint.h>
-
-#include "colormap.cuh"
-#include "interp.cuh"
+#include "generators.cuh"
+#include "math32.cuh"
 #include "mc_tables.cuh"
 
 namespace gsdfk {
-
-#ifndef GSDF_THREADS
-#define GSDF_THREADS 256
-#endif
-constexpr int kThreads = GSDF_THREADS;   // CTA size of the MC / scan / STL kernels and default of k_eval
-// Measured on B200 (scripts/ab_eval.py): 512-thread CTAs whose warps are kept on the same opcode body by a barrier
-// per instruction (GSDF_LOCKSTEP) cut instruction-fetch stalls: -13 % (flange) / -14 % (knurled) evaluate time
-// versus free-running 256-thread CTAs.
-#ifndef GSDF_EVAL_THREADS
-#define GSDF_EVAL_THREADS 512
-#endif
-constexpr int kEvalThreads = GSDF_EVAL_THREADS;  // CTA size of the interpreter kernel
-
-struct ProgView {
-    const uint4 *g_prog;     // device: program chunks followed by aux (16-byte aligned)
-    uint32_t prog_bytes;     // bytes of chunks
-    uint32_t aux_bytes;      // bytes of aux that follow the chunks
-    uint32_t stage_aux;      // 1: aux is staged to smem with the program; 0: read from global
-    uint32_t dslots, pslots; // stack slots
-    uint32_t *sched;         // [0] next tile, [1] finished CTAs (self-resetting work counter)
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// Programmatic dependent launch (PTX griddepcontrol). The kernels of one render form a chain in which each consumes
-// what its predecessor wrote. Every kernel of the chain (a) lets its successor's CTAs become resident as soon as all of
-// its own CTAs have started (pdl_trigger) and (b) does whatever does not depend on the predecessor -- staging the node
-// program, loading tables, initialising mbarriers -- before pdl_wait(), which returns once the predecessor grid has
-// completed and its writes are visible. Because every kernel waits before it touches chain data, completion is
-// transitive along the chain. Launched without the programmatic-serialization attribute both are no-ops.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-// Stage `bytes` (multiple of 16) from global to shared with one bulk async copy; all threads return after it landed.
-__device__ __forceinline__ void bulk_stage(void *s_dst, const void *g_src, uint32_t bytes, uint64_t *s_bar) {
-    const uint32_t bar = smem_u32(s_bar);
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_dst)),
-                     "l"(g_src), "r"(bytes), "r"(bar)
-                     : "memory");
-    }
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(bar)
-        : "memory");
-}
-
-// Shared memory: [prog (+aux)] [mbarrier + tile slot, 16 bytes] [dstack] [pstack]
-__host__ __device__ inline uint32_t smem_stage_bytes(const ProgView &pv) { return pv.prog_bytes + (pv.stage_aux ? pv.aux_bytes : 0u); }
-// Radius cache of the experimental -DGSDF_RXY build (gsdf_program.h, "Radius reuse"): one float per point behind the stacks.
-#ifdef GSDF_RXY
-constexpr uint32_t kRxySlots = 1u;
-#else
-constexpr uint32_t kRxySlots = 0u;
-#endif
-template <int P>
-__host__ __device__ inline uint32_t smem_total_bytes(const ProgView &pv, int threads) {
-    return smem_stage_bytes(pv) + 16u + (uint32_t)threads * P * 4u * (pv.dslots + 3u * pv.pslots + kRxySlots);
-}
-
-template <int P, class Gen, bool EXT>
-__global__ void __launch_bounds__(kEvalThreads) k_eval(ProgView pv, Gen gen) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t stage = smem_stage_bytes(pv);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + stage);
-    volatile uint32_t *s_tile = reinterpret_cast<volatile uint32_t *>(smem + stage + 8);
-    pdl_trigger();
-    bulk_stage(smem, pv.g_prog, stage, bar);  // the program was uploaded before the chain started: safe ahead of pdl_wait
-    const uint4 *prog = reinterpret_cast<const uint4 *>(smem);
-    const float4 *aux = pv.stage_aux ? reinterpret_cast<const float4 *>(smem + pv.prog_bytes)
-                                     : reinterpret_cast<const float4 *>(reinterpret_cast<const uint8_t *>(pv.g_prog) + pv.prog_bytes);
-    float *dstk = reinterpret_cast<float *>(smem + stage + 16u) + threadIdx.x;
-    float *pstk = dstk + (size_t)pv.dslots * P * blockDim.x;
-
-    Machine<P> m;
-    pdl_wait();
-    const uint64_t nwork = gen.work_items();
-    for (;;) {
-        if (threadIdx.x == 0) *s_tile = atomicAdd(pv.sched, 1u);
-        __syncthreads();
-        const uint64_t w = (uint64_t)(*s_tile) * blockDim.x + threadIdx.x;
-        __syncthreads();
-        if (w - threadIdx.x >= nwork) break;
-        if constexpr (Gen::kTileSkip) {  // generator-level CTA-uniform skip of a whole tile (GenDC: cubes outside this rank's region)
-            if (__syncthreads_and(gen.dead(w < nwork ? w : nwork - 1))) {
-                if (w < nwork) gen.store_dead(w);
-                continue;
-            }
-        }
-#ifdef GSDF_LOCKSTEP
-        // every thread of the tile runs the program (barriers inside); threads past the end redo the last item
-        const uint64_t wc = w < nwork ? w : nwork - 1;
-        m.init(dstk, pstk, blockDim.x);
-#ifdef GSDF_RXY
-        m.rxy = pstk + (size_t)pv.pslots * 3 * P * blockDim.x;
-#endif
-        gen.load(wc, m.px, m.py, m.pz);
-        run_program<P, EXT>(m, prog, aux);
-        if (w < nwork) gen.store(w, m.top);
-#else
-        if (w >= nwork) continue;
-        m.init(dstk, pstk, blockDim.x);
-#ifdef GSDF_RXY
-        m.rxy = pstk + (size_t)pv.pslots * 3 * P * blockDim.x;
-#endif
-        gen.load(w, m.px, m.py, m.pz);
-        run_program<P, EXT>(m, prog, aux);
-        gen.store(w, m.top);
-#endif
-    }
-    // the last CTA to leave re-arms the scheduler for the next launch
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(pv.sched + 1, 1u) == gridDim.x - 1) {
-            pv.sched[0] = 0u;
-            pv.sched[1] = 0u;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------- generators
-// gleval.SDF3.Evaluate on an AoS float3 list (gleval/gleval.go:15-24): 4 points per thread, 3x float4 loads.
-struct GenPoints3 {
-    static constexpr bool kTileSkip = false;
-    const float *pos; float *dist; uint64_t n; int vec;  // vec: both pointers 16-byte aligned
-    __device__ uint64_t work_items() const { return (n + 3) / 4; }
-    __device__ void load(uint64_t w, float (&x)[4], float (&y)[4], float (&z)[4]) const {
-        const uint64_t i0 = w * 4;
-        if (vec && i0 + 4 <= n) {
-            const float4 *p4 = reinterpret_cast<const float4 *>(pos) + w * 3;
-            const float4 a = __ldg(p4), b = __ldg(p4 + 1), c = __ldg(p4 + 2);
-            x[0] = a.x; y[0] = a.y; z[0] = a.z; x[1] = a.w; y[1] = b.x; z[1] = b.y;
-            x[2] = b.z; y[2] = b.w; z[2] = c.x; x[3] = c.y; y[3] = c.z; z[3] = c.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint64_t i = i0 + j < n ? i0 + j : n - 1;
-                x[j] = __ldg(pos + 3 * i); y[j] = __ldg(pos + 3 * i + 1); z[j] = __ldg(pos + 3 * i + 2);
-            }
-        }
-    }
-    __device__ void store(uint64_t w, const float (&d)[4]) const {
-        const uint64_t i0 = w * 4;
-        if (vec && i0 + 4 <= n) {
-            reinterpret_cast<float4 *>(dist)[w] = make_float4(d[0], d[1], d[2], d[3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (i0 + j < n) dist[i0 + j] = d[j];
-        }
-    }
-};
-// gleval.SDF2.Evaluate (gleval/gleval.go:28-37): AoS float2, 2x float4 loads per 4 points.
-struct GenPoints2 {
-    static constexpr bool kTileSkip = false;
-    const float *pos; float *dist; uint64_t n; int vec;
-    __device__ uint64_t work_items() const { return (n + 3) / 4; }
-    __device__ void load(uint64_t w, float (&x)[4], float (&y)[4], float (&z)[4]) const {
-        const uint64_t i0 = w * 4;
-        if (vec && i0 + 4 <= n) {
-            const float4 *p4 = reinterpret_cast<const float4 *>(pos) + w * 2;
-            const float4 a = __ldg(p4), b = __ldg(p4 + 1);
-            x[0] = a.x; y[0] = a.y; x[1] = a.z; y[1] = a.w; x[2] = b.x; y[2] = b.y; x[3] = b.z; y[3] = b.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint64_t i = i0 + j < n ? i0 + j : n - 1;
-                x[j] = __ldg(pos + 2 * i); y[j] = __ldg(pos + 2 * i + 1);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) z[j] = 0.f;
-    }
-    __device__ void store(uint64_t w, const float (&d)[4]) const {
-        const uint64_t i0 = w * 4;
-        if (vec && i0 + 4 <= n) {
-            reinterpret_cast<float4 *>(dist)[w] = make_float4(d[0], d[1], d[2], d[3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (i0 + j < n) dist[i0 + j] = d[j];
-        }
-    }
-};
-
-// gleval.SDF3.Evaluate / SDF2.Evaluate on device-resident point lists, streaming form. A tile is the AoS position block of
-// blockDim.x * 4 points -- one contiguous run of global memory (24 KB for float3, 16 KB for float2) -- fetched by ONE
-// 1-D bulk async copy (cp.async.bulk.shared::cluster.global -> SASS UBLKCP) into a double-buffered shared-memory stage:
-// the copy of tile i+1 is in flight while tile i is interpreted, so cheap trees (sphere, box: 16 B/eval) stay on the HBM
-// stream instead of alternating load and compute phases. Shared-memory reads are 3 (2) float4 per thread at a 48 (32)
-// byte stride: conflict-free per quarter-warp. Tiles are dealt round-robin to the persistent CTAs (cost per tile is
-// uniform); the last, partial tile takes the plain-load path. Requires 16-byte aligned pos/dist (else k_eval<GenPoints*>).
-// Shared memory: [prog (+aux)] [2 mbarriers] [dstack] [pstack] [stage 0] [stage 1]
-template <int DIM>
-__host__ __device__ inline uint32_t stream_stage_bytes(int threads) { return (uint32_t)threads * 4u * DIM * 4u; }
-
-template <int DIM, bool EXT>
-__global__ void __launch_bounds__(kEvalThreads) k_eval_stream(ProgView pv, const float *__restrict__ pos, float *__restrict__ dist, uint64_t n) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    constexpr int P = 4;
-    const uint32_t stage = smem_stage_bytes(pv);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + stage);  // bar[0]: program staging, then stage 0; bar[1]: stage 1
-    bulk_stage(smem, pv.g_prog, stage, bar);                     // completes phase 0 of bar[0]
-    const uint4 *prog = reinterpret_cast<const uint4 *>(smem);
-    const float4 *aux = pv.stage_aux ? reinterpret_cast<const float4 *>(smem + pv.prog_bytes)
-                                     : reinterpret_cast<const float4 *>(reinterpret_cast<const uint8_t *>(pv.g_prog) + pv.prog_bytes);
-    float *dstk = reinterpret_cast<float *>(smem + stage + 16u) + threadIdx.x;
-    float *pstk = dstk + (size_t)pv.dslots * P * blockDim.x;
-    const uint32_t stack_bytes = (uint32_t)blockDim.x * P * 4u * (pv.dslots + 3u * pv.pslots + kRxySlots);
-    const uint32_t tile_bytes = stream_stage_bytes<DIM>(blockDim.x);
-    uint8_t *buf0 = smem + ((stage + 16u + stack_bytes + 127u) & ~127u);
-    const uint32_t bar_u[2] = {smem_u32(bar), smem_u32(bar + 1)};
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_u[1]));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const uint64_t pts_per_tile = (uint64_t)blockDim.x * P;
-    const uint64_t nfull = n / pts_per_tile;               // tiles fetched by bulk copy
-    const uint64_t ntiles = (n + pts_per_tile - 1) / pts_per_tile;
-    uint32_t phase[2] = {1u, 0u};                          // bar[0] already went through phase 0 for the program
-    auto issue = [&](uint64_t tile, int b) {               // one elected thread
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_u[b]), "r"(tile_bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(buf0 + (size_t)b * tile_bytes)),
-                     "l"(reinterpret_cast<const uint8_t *>(pos) + tile * tile_bytes), "r"(tile_bytes), "r"(bar_u[b])
-                     : "memory");
-    };
-    uint64_t tile = blockIdx.x;
-    if (threadIdx.x == 0 && tile < nfull) issue(tile, 0);
-    Machine<P> m;
-    int b = 0;
-    for (; tile < ntiles; tile += gridDim.x, b ^= 1) {
-        const uint64_t next = tile + gridDim.x;
-        if (threadIdx.x == 0 && next < nfull) issue(next, b ^ 1);   // stage b^1 was released by the barrier that ended the previous iteration
-        m.init(dstk, pstk, blockDim.x);
-#ifdef GSDF_RXY
-        m.rxy = pstk + (size_t)pv.pslots * 3 * P * blockDim.x;
-#endif
-        const uint64_t i0 = tile * pts_per_tile + (uint64_t)threadIdx.x * P;
-        if (tile < nfull) {
-            asm volatile(
-                "{\n\t"
-                ".reg .pred p;\n\t"
-                "SW_LOOP:\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                "@p bra SW_DONE;\n\t"
-                "bra SW_LOOP;\n\t"
-                "SW_DONE:\n\t"
-                "}" ::"r"(bar_u[b]), "r"(phase[b])
-                : "memory");
-            phase[b] ^= 1u;
-            const float4 *s4 = reinterpret_cast<const float4 *>(buf0 + (size_t)b * tile_bytes) + threadIdx.x * DIM;
-            if (DIM == 3) {
-                const float4 a = s4[0], bq = s4[1], c = s4[2];
-                m.px[0] = a.x; m.py[0] = a.y; m.pz[0] = a.z; m.px[1] = a.w; m.py[1] = bq.x; m.pz[1] = bq.y;
-                m.px[2] = bq.z; m.py[2] = bq.w; m.pz[2] = c.x; m.px[3] = c.y; m.py[3] = c.z; m.pz[3] = c.w;
-            } else {
-                const float4 a = s4[0], bq = s4[1];
-                m.px[0] = a.x; m.py[0] = a.y; m.px[1] = a.z; m.py[1] = a.w; m.px[2] = bq.x; m.py[2] = bq.y; m.px[3] = bq.z; m.py[3] = bq.w;
-#pragma unroll
-                for (int j = 0; j < P; j++) m.pz[j] = 0.f;
-            }
-        } else {  // the partial tile: plain loads, points past the end repeat the last one
-#pragma unroll
-            for (int j = 0; j < P; j++) {
-                const uint64_t i = i0 + j < n ? i0 + j : n - 1;
-                m.px[j] = __ldg(pos + DIM * i); m.py[j] = __ldg(pos + DIM * i + 1); m.pz[j] = DIM == 3 ? __ldg(pos + DIM * i + 2) : 0.f;
-            }
-        }
-        run_program<P, EXT>(m, prog, aux);
-        if (i0 + P <= n) {
-            reinterpret_cast<float4 *>(dist)[i0 / P] = make_float4(m.top[0], m.top[1], m.top[2], m.top[3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < P; j++) if (i0 + j < n) dist[i0 + j] = m.top[j];
-        }
-        __syncthreads();  // every thread is done with stage b before it is refilled two iterations later
-    }
-}
-
-// Lattice description shared by the grid / mesher kernels.
-struct Lat {
-    float ox, oy, oz, res;
-    int nx, ny, nz;    // cells
-    int k0, nk;        // corner planes [k0, k0+nk) handled
-    int nqx;           // quads (4 corners) per row = ceil((nx+1)/4)
-    int pitch;         // floats per stored row
-    int vec;           // rows 16-byte aligned -> float4 stores
-};
-// FlatRenderer.evalKRange (glrender/flatrenderer.go:146-182): positions origin + float32(i)*res, x fastest.
-// Work unit = a quad of 4 consecutive corners of one lattice row, split over 4/P threads.
-// list==nullptr: every quad of the slab; else the compacted quad ids produced by k_compact_quads.
-template <int P>
-struct GenGrid {
-    static constexpr bool kTileSkip = false;
-    static_assert(P == 1 || P == 2 || P == 4, "P must divide 4");
-    Lat L; float *dist; const uint32_t *list; const uint32_t *count;
-    __device__ uint64_t work_items() const { return (list ? (uint64_t)*count : (uint64_t)L.nqx * (L.ny + 1) * L.nk) * (4 / P); }
-    __device__ void decode(uint64_t w, int &i0, int &j, int &k) const {
-        const uint32_t sub = (uint32_t)(w % (4 / P));
-        uint32_t q = list ? list[w / (4 / P)] : (uint32_t)(w / (4 / P));
-        const uint32_t m = q % (uint32_t)L.nqx; q /= (uint32_t)L.nqx;
-        j = (int)(q % (uint32_t)(L.ny + 1));
-        k = (int)(q / (uint32_t)(L.ny + 1));
-        i0 = (int)(4 * m + P * sub);
-    }
-    __device__ void load(uint64_t w, float (&x)[P], float (&y)[P], float (&z)[P]) const {
-        int i0, j, k;
-        decode(w, i0, j, k);
-        const float yy = L.oy + (float)j * L.res, zz = L.oz + (float)(L.k0 + k) * L.res;
-#pragma unroll
-        for (int t = 0; t < P; t++) {
-            const int i = min(i0 + t, L.nx);
-            x[t] = L.ox + (float)i * L.res; y[t] = yy; z[t] = zz;
-        }
-    }
-    __device__ void store(uint64_t w, const float (&d)[P]) const {
-        int i0, j, k;
-        decode(w, i0, j, k);
-        float *row = dist + ((size_t)k * (L.ny + 1) + j) * L.pitch + i0;
-        if (L.vec) {  // pitch is a multiple of 4 and covers every quad: no bounds check needed
-            if (P == 4) *reinterpret_cast<float4 *>(row) = make_float4(d[0], d[P > 1 ? 1 : 0], d[P > 2 ? 2 : 0], d[P > 3 ? 3 : 0]);
-            else if (P == 2) *reinterpret_cast<float2 *>(row) = make_float2(d[0], d[P > 1 ? 1 : 0]);
-            else row[0] = d[0];
-        } else {
-#pragma unroll
-            for (int t = 0; t < P; t++) if (i0 + t <= L.nx) row[t] = d[t];
-        }
-    }
-};
-
-// Octree prune (glrender/octreerenderer.go:180-191, 240-284): evaluate the centre of every level-3 cube (4 cells
-// wide) of the slab; keep it iff |d| < size*sqrt3/2. One cube per thread: the pass is small and latency bound, so it
-// wants threads, not per-thread ILP. Work items are block rows padded to whole warps (32*nwx per row), so a warp's 32
-// verdicts are exactly one word of the prune bit rows: the sink writes the word with one ballot (no byte mask, no second
-// pass) and adds the kept count to the Octree.TotalPruned bookkeeping.
-struct GenCenters {
-    static constexpr bool kTileSkip = false;
-    float ox, oy, oz, res; int nbx, nby, nbz, bz0, nwx; float half, maxDist; uint32_t *bits; uint32_t *kept;
-    __device__ uint64_t work_items() const { return (uint64_t)nwx * 32u * nby * nbz; }
-    __device__ void load(uint64_t w, float (&x)[1], float (&y)[1], float (&z)[1]) const {
-        const uint32_t rowlen = (uint32_t)nwx * 32u;
-        const uint32_t row = (uint32_t)(w / rowlen);
-        const int bx = min((int)(w - (uint64_t)row * rowlen), nbx - 1);  // padding lanes repeat the row's last cube
-        const int by = (int)(row % (uint32_t)nby), bz = (int)(row / (uint32_t)nby);
-        x[0] = (ox + (float)(4 * bx) * res) + half;
-        y[0] = (oy + (float)(4 * by) * res) + half;
-        z[0] = (oz + (float)(4 * (bz0 + bz)) * res) + half;
-    }
-    __device__ void store(uint64_t w, const float (&d)[1]) const {
-        const uint32_t rowlen = (uint32_t)nwx * 32u;
-        const uint32_t col = (uint32_t)(w % rowlen);
-        const bool keep = (int)col < nbx && !(fabsf(d[0]) >= maxDist);
-        const uint32_t word = __ballot_sync(__activemask(), keep);  // work items are multiples of 32: whole warps arrive here
-        if ((threadIdx.x & 31) == 0) {
-            bits[w >> 5] = word;  // word (w>>5) = row * nwx + col/32
-            if (word) atomicAdd(kept, (uint32_t)__popc(word));
-        }
-    }
-};
-
-// ImageRendererSDF2.Render positions (glrender/image.go:85-105). rgba != nullptr: the colour conversion is applied in
-// the sink and four RGBA8 pixels leave as one 16-byte store (image.go:112-116 fused); else the distances are stored.
-struct GenImage {
-    static constexpr bool kTileSkip = false;
-    // Work items are grouped into 2-D tiles of 32 quads x 16 rows (128 x 16 pixels = one 512-thread CTA tile), so that a
-    // tile is spatially compact and the CTA-uniform guards (gsdf_program.h) fire; a warp still covers 512 contiguous
-    // bytes of one image row.
-    float xmin, ymax, dx, dy; int w, h; float *dist; uint32_t *rgba; ColorConv cc;
-    __device__ uint32_t tiles_x() const { return ((uint32_t)(w + 3) / 4 + 31u) / 32u; }
-    __device__ uint64_t work_items() const { return (uint64_t)tiles_x() * (((uint32_t)h + 15u) / 16u) * 512u; }
-    __device__ void decode(uint64_t wi, int &q, int &j) const {
-        const uint32_t t = (uint32_t)(wi & 511u), tile = (uint32_t)(wi >> 9);
-        const uint32_t tx = tile % tiles_x(), ty = tile / tiles_x();
-        q = (int)(tx * 32u + (t & 31u));
-        j = (int)(ty * 16u + (t >> 5));
-    }
-    __device__ void load(uint64_t wi, float (&x)[4], float (&y)[4], float (&z)[4]) const {
-        int q, j;
-        decode(wi, q, j);
-        const float yy = ymax - (float)min(j, h - 1) * dy;
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const int i = min(4 * q + t, w - 1);
-            x[t] = (float)i * dx + xmin; y[t] = yy; z[t] = 0.f;
-        }
-    }
-    __device__ void store(uint64_t wi, const float (&d)[4]) const {
-        int q, j;
-        decode(wi, q, j);
-        if (j >= h || 4 * q >= w) return;
-        if (rgba) {
-            uint32_t c[4];
-#pragma unroll
-            for (int t = 0; t < 4; t++) c[t] = color_of(cc, d[t]);
-            uint32_t *row = rgba + (size_t)j * w;
-            if ((w & 3) == 0) {
-                *reinterpret_cast<uint4 *>(row + 4 * q) = make_uint4(c[0], c[1], c[2], c[3]);
-            } else {
-#pragma unroll
-                for (int t = 0; t < 4; t++) if (4 * q + t < w) row[4 * q + t] = c[t];
-            }
-            return;
-        }
-        float *row = dist + (size_t)j * w;
-        if ((w & 3) == 0) {
-            *reinterpret_cast<float4 *>(row + 4 * q) = make_float4(d[0], d[1], d[2], d[3]);
-        } else {
-#pragma unroll
-            for (int t = 0; t < 4; t++) if (4 * q + t < w) row[4 * q + t] = d[t];
-        }
-    }
-};
-
-// ---------------------------------------------------------------------------------------------- prune -> quad list
-struct MeshDims {
-    int nx, ny, nz;          // cells of the whole lattice
-    int cz0, cz1;            // slab of cells
-    int nbx, nby, nbz, bz0;  // 4-cell blocks covering the slab
-    int nqx;                 // quads per corner row
-    int pitch;               // grid row pitch (floats)
-    int nsx;                 // 32-cell segments per cell row
-    int nwx;                 // 32-bit words per block row of the bit mask = ceil(nbx/32)
-};
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
     const int lane = threadIdx.x & 31;

@@ -36,11 +36,15 @@ class _SDFCUDA:
             raise GsdfError(_lib.EINVAL, "%s does not implement %dD evaluator" % ("Shader", self._dim))  # gleval/cpu.go:60-66
         self.shader = shader
         h = C.c_void_p()
-        rc = lib.gsdfh_compile(shader.bld._h, shader.id, C.byref(h))
-        if rc != 0:
-            msg = shader.bld.Err() or _lib.last_error()
+        try:
+            f = shader.bld.flatten(shader)  # host layer (libgsdfhost.so): tree -> node program
+        except GsdfError as e:
             shader.bld.ClearErrors()  # reported through the exception: must not poison later shape construction on this builder
-            raise GsdfError(rc, msg)
+            raise e
+        aux = np.ascontiguousarray(f["aux"], dtype=np.float32)
+        rc = lib.gsdf_program_create(f["blob"], len(f["blob"]), aux.ctypes.data_as(C.POINTER(C.c_float)), aux.size, C.byref(h))
+        if rc != 0:
+            raise GsdfError(rc, _lib.last_error())
         self._h = h
         self._bounds = shader.Bounds()
 

@@ -11,7 +11,7 @@ import struct
 import numpy as np
 
 from . import _lib
-from ._lib import lib, check, GsdfError, Lattice
+from ._lib import lib, check, GsdfError, Lattice, PrunePlan
 
 marchingCubesMaxTriangles = 5  # marchcubes.go:11
 
@@ -38,11 +38,16 @@ class _Renderer:
     (or Reset); ReadTriangles streams the result out in FlatRenderer order."""
     _flags = 0
 
-    def __init__(self, sdf, cubeResolution, evalBufferSize=0, numParallel=1, cz_range=None, keep_cases=False, keep_grid=False, stage_timing=False):
+    def __init__(self, sdf, cubeResolution, evalBufferSize=0, numParallel=1, cz_range=None, keep_cases=False, keep_grid=False, stage_timing=False,
+                 prune=None):
         self._h = None
-        self.Reset(sdf, cubeResolution, cz_range=cz_range, keep_cases=keep_cases, keep_grid=keep_grid, stage_timing=stage_timing)
+        self.Reset(sdf, cubeResolution, cz_range=cz_range, keep_cases=keep_cases, keep_grid=keep_grid, stage_timing=stage_timing, prune=prune)
 
-    def Reset(self, sdf, cubeResolution, evalBufferSize=0, numParallel=1, cz_range=None, keep_cases=False, keep_grid=False, stage_timing=False):
+    def Reset(self, sdf, cubeResolution, evalBufferSize=0, numParallel=1, cz_range=None, keep_cases=False, keep_grid=False, stage_timing=False,
+              prune=None):
+        """prune (Octree only): None = the default plan (level 3 with margin 1.25, coarse levels in front on large
+        lattices); "literal" = the reference's rule at every level-3 cube (margin 1); or an explicit plan
+        [(level, margin), ...] ending with level 3 (include/gsdf_b200.h, gsdf_prune_plan)."""
         if not (cubeResolution > 0):
             raise GsdfError(_lib.EINVAL, "invalid renderer cube resolution")  # flatrenderer.go:38, octreerenderer.go:73
         self.Close()
@@ -53,9 +58,28 @@ class _Renderer:
         self.cz0, self.cz1 = int(cz0), int(cz1)
         flags = self._flags | (_lib.MESH_KEEP_CASES if keep_cases else 0) | (_lib.MESH_KEEP_GRID if keep_grid else 0) | \
             (_lib.MESH_STAGE_TIMING if stage_timing else 0)
+        self.flags = flags
+        self.plan = None
         h = C.c_void_p()
-        check(lib.gsdf_mesh_begin(sdf._h, C.byref(self.lat), self.cz0, self.cz1, flags, C.byref(h)))
+        if prune is not None and not (self._flags & _lib.MESH_PRUNE):
+            raise GsdfError(_lib.EINVAL, "prune plans belong to the Octree renderer")
+        if prune == "literal":
+            flags |= _lib.MESH_PRUNE_LITERAL
+            self.flags = flags
+            prune = None
+        if prune is not None:
+            self.plan = PrunePlan.make([l for l, _ in prune], [m for _, m in prune])
+            check(lib.gsdf_mesh_begin_plan(sdf._h, C.byref(self.lat), self.cz0, self.cz1, flags, C.byref(self.plan), C.byref(h)))
+        else:
+            if flags & _lib.MESH_PRUNE:
+                self.plan = PrunePlan()
+                check(lib.gsdf_prune_plan_default(C.byref(self.lat), flags, C.byref(self.plan)))
+            check(lib.gsdf_mesh_begin(sdf._h, C.byref(self.lat), self.cz0, self.cz1, flags, C.byref(h)))
         self._h = h
+
+    def Plan(self):
+        """The prune plan in use: [(level, margin), ...], coarse to fine ([] for the FlatRenderer)."""
+        return self.plan.levels() if self.plan is not None else []
 
     def Rerun(self):
         """Mesh the same slab again into the same device buffers (timing loops)."""
@@ -208,8 +232,126 @@ class SlabPipeline:
 
 
 class Octree(_Renderer):
-    """glrender.Octree: marching cubes with level-3 cube pruning (octreerenderer.go:15-284)."""
+    """glrender.Octree: marching cubes with octree cube pruning (octreerenderer.go:15-284), coarse to fine down to the
+    level-3 cubes (4 cells). See Reset for the prune plans."""
     _flags = _lib.MESH_PRUNE
+
+
+class MultiRenderer:
+    """One lattice meshed by several GPUs (or several pipelined Z-slabs of one GPU) from this process: gsdf_multi_*
+    (include/gsdf_b200.h), the device analogue of FlatRenderer.evalGrid's goroutine split (flatrenderer.go:103-141).
+    Satisfies the Renderer contract (ReadTriangles / RenderAll) on the last render; RenderToHost re-renders and delivers
+    every triangle in FlatRenderer order into one host buffer."""
+
+    def __init__(self, shader, cubeResolution, devices=(0,), slabs_per_device=1, prune=True, literal=False):
+        if not (cubeResolution > 0):
+            raise GsdfError(_lib.EINVAL, "invalid renderer cube resolution")
+        self._h = None
+        self.shader = shader
+        mn, mx = shader.Bounds()
+        self.lat = lattice_from_bounds(mn, mx, cubeResolution)
+        f = shader.bld.flatten(shader)
+        aux = np.ascontiguousarray(f["aux"], dtype=np.float32)
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        flags = (_lib.MESH_PRUNE if prune else 0) | (_lib.MESH_PRUNE_LITERAL if literal else 0)
+        h = C.c_void_p()
+        check(lib.gsdf_multi_begin(len(devices), devs, int(slabs_per_device), f["blob"], len(f["blob"]),
+                                   aux.ctypes.data_as(C.POINTER(C.c_float)), aux.size, C.byref(self.lat), flags, C.byref(h)))
+        self._h = h
+
+    def Update(self, shader):
+        """Re-flatten `shader` and hand it to every device (uploaded at the start of the next render)."""
+        f = shader.bld.flatten(shader)
+        aux = np.ascontiguousarray(f["aux"], dtype=np.float32)
+        check(lib.gsdf_multi_update(self._h, f["blob"], len(f["blob"]), aux.ctypes.data_as(C.POINTER(C.c_float)), aux.size))
+        self.shader = shader
+
+    def UpdateBlob(self, blob, aux):
+        check(lib.gsdf_multi_update(self._h, blob, len(blob), aux.ctypes.data_as(C.POINTER(C.c_float)), aux.size))
+
+    def Render(self):
+        """Render without read-back (device timing)."""
+        return int(check(lib.gsdf_multi_render(self._h, None, 0)))
+
+    def RenderToHost(self, dst):
+        """Render and deliver all triangles into dst (float32, capacity >= the count; pinned memory is written by DMA
+        directly). Returns the triangle count."""
+        if dst.dtype != np.float32 or not dst.flags.c_contiguous:
+            raise GsdfError(_lib.EINVAL, "dst must be C-contiguous float32")
+        return int(check(lib.gsdf_multi_render(self._h, C.c_void_p(dst.ctypes.data), dst.size // 9)))
+
+    def ReadTriangles(self, dst, userData=None):
+        if dst.dtype != np.float32 or not dst.flags.c_contiguous:
+            raise GsdfError(_lib.EINVAL, "dst must be C-contiguous float32 (n,3,3)")
+        cap = dst.size // 9
+        if cap < marchingCubesMaxTriangles:
+            raise ErrShortBuffer(_lib.ESHORT, "short buffer")
+        n = check(lib.gsdf_multi_read(self._h, C.c_void_p(dst.ctypes.data), cap))
+        if n == 0:
+            raise EOF()
+        return int(n)
+
+    def _stats(self):
+        e, p, t, ms = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_float()
+        check(lib.gsdf_multi_stats(self._h, C.byref(e), C.byref(p), C.byref(t), C.byref(ms)))
+        return e.value, p.value, t.value, ms.value
+
+    def Evaluations(self):
+        return self._stats()[0]
+
+    def TotalPruned(self):
+        return self._stats()[1]
+
+    def NumTriangles(self):
+        return self._stats()[2]
+
+    def DeviceMs(self):
+        return self._stats()[3]
+
+    def Slabs(self):
+        """(cuts, devices): nslabs+1 cell-layer cuts and the device of each slab."""
+        cuts = (C.c_int32 * 4097)()
+        devs = (C.c_int32 * 4096)()
+        n = check(lib.gsdf_multi_slabs(self._h, cuts, devs, 4096))
+        return [int(c) for c in cuts[:n + 1]], [int(d) for d in devs[:n]]
+
+    def AllTriangles(self):
+        nt = self.NumTriangles()
+        out = np.empty((nt, 3, 3), dtype=np.float32)
+        got = 0
+        check(lib.gsdf_multi_rewind(self._h))
+        while got < nt:
+            n = check(lib.gsdf_multi_read(self._h, C.c_void_p(out[got:].ctypes.data), max(nt - got, 5)))
+            if n == 0:
+                break
+            got += n
+        return out[:got]
+
+    def STLBytes(self):
+        nt = self.NumTriangles()
+        buf = np.empty(84 + 50 * nt, dtype=np.uint8)
+        n = check(lib.gsdf_multi_stl(self._h, C.c_void_p(buf.ctypes.data), buf.size))
+        return buf[:n].tobytes()
+
+    def Close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and lib is not None:
+            lib.gsdf_multi_destroy(h)
+
+    __del__ = Close
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """A numpy array in page-locked host memory from gsdf_host_alloc: transfers into it run by DMA without staging."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib.gsdf_host_alloc(max(n, 1))
+    if not p:
+        raise GsdfError(_lib.ENOMEM, _lib.last_error())
+    buf = (C.c_uint8 * max(n, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    import weakref
+    weakref.finalize(buf, lib.gsdf_host_free, p)  # buf is arr's base: freed when the last view goes
+    return arr
 
 
 class FlatRenderer(_Renderer):

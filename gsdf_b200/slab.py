@@ -10,18 +10,16 @@ import numpy as np
 
 
 def slab_cuts(nz, world, align=4):
-    """Cell-layer cut points [0, ..., nz]: near-equal slabs, interior cuts aligned down to the 4-cell prune blocks so
-    no block is evaluated by two ranks. Ranks beyond the available layers get empty slabs (cut == next cut)."""
+    """Cell-layer cut points [0, ..., nz] (gsdf_slab_cuts of the C ABI, the cuts gsdf_multi_begin uses): near-equal slabs;
+    interior cuts are aligned down to the 4-layer prune blocks while slabs are at least two blocks thick, thinner slabs keep
+    the exact split. More slabs than layers gives empty slabs at the end (cut == next cut)."""
+    import ctypes as C
+    from ._lib import lib, check
     if nz <= 0 or world <= 0:
         raise ValueError("nz and world must be positive")
-    cuts = [0]
-    for g in range(1, world):
-        c = (g * nz) // world
-        if align > 1:
-            c = (c // align) * align
-        cuts.append(max(c, cuts[-1]))
-    cuts.append(nz)
-    return cuts
+    cuts = (C.c_int32 * (world + 1))()
+    check(lib.gsdf_slab_cuts(int(nz), int(world), cuts))
+    return [int(c) for c in cuts]
 
 
 def rank_slab(nz, rank, world, align=4):

@@ -45,9 +45,17 @@ const char *gsdf_version(void);
 const char *gsdf_last_error(void);
 /* Number of CUDA devices visible, or <0. */
 int gsdf_device_count(void);
-/* Select the device later handles are created on (one process per GPU: pass LOCAL_RANK). Replaces
- * gleval.Init1x1GLFW (gleval/gpu.go:21) as the "bring the GPU up" call; no OS-thread pinning is needed. */
+/* Select the device that handles created LATER BY THE CALLING THREAD live on (one process per GPU: pass LOCAL_RANK).
+ * Replaces gleval.Init1x1GLFW (gleval/gpu.go:21) as the "bring the GPU up" call. The default is per thread; callers whose
+ * threads are not theirs to pin (goroutines) use gsdf_program_create_on / gsdf_multi_begin, which take the device
+ * explicitly. Every handle remembers its device: calls on a handle may come from any thread. */
 int gsdf_set_device(int device);
+/* Pinned (page-locked) host memory. Host pointers passed to gsdf_eval3/2, gsdf_mesh_read*, gsdf_multi_render may be any
+ * memory; when they point into memory from gsdf_host_alloc (or memory the caller registered with cudaHostRegister) the
+ * transfers run by DMA straight from / into the caller's buffer instead of through the library's staging buffers. A Go
+ * caller wraps the pointer with unsafe.Slice. */
+void *gsdf_host_alloc(size_t bytes);
+void gsdf_host_free(void *p);
 
 /* Program -------------------------------------------------------------------------------------------- */
 /* Upload a flattened tree (include/gsdf_program.h). Replaces Programmer.WriteComputeSDF3 + NewComputeGPUSDF3
@@ -57,19 +65,26 @@ int gsdf_set_device(int device);
  * guard kinds and targets, the distance / position stack discipline against the header's slot counts, and that every
  * region a guard can skip leaves exactly the value its combiner consumes. */
 int gsdf_program_create(const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats, gsdf_program **out);
+/* Same on an explicitly named device (no per-thread state involved). */
+int gsdf_program_create_on(int device, const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats, gsdf_program **out);
 /* Re-upload a (re-)flattened tree of the same dimension into an existing handle: device buffers, stream and scheduler
  * are reused, so an edited tree costs one small host->device copy (the GL path recompiles its shader instead,
  * gleval/gpu.go:35-54). Renderers bound to the handle see the new tree on their next run. */
 int gsdf_program_update(gsdf_program *p, const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats);
 void gsdf_program_destroy(gsdf_program *p);
-/* gleval Evaluations() counter (gleval/cpu.go:126, gleval/gpu.go:80): points successfully evaluated through
- * gsdf_eval3/gsdf_eval2 on this handle. */
+/* gleval Evaluations() counter (gleval/cpu.go:126, gleval/gpu.go:80): points evaluated through this handle -- host and
+ * device Evaluate calls, lattice and image evaluations, and the evaluations of the renderers bound to it (the reference's
+ * renderers call sdf.Evaluate, so its counter includes them too). */
 uint64_t gsdf_program_evaluations(const gsdf_program *p);
 
 /* Evaluate ------------------------------------------------------------------------------------------- */
 /* gleval.SDF3.Evaluate(pos []ms3.Vec, dist []float32, userData) (gleval/gleval.go:15-24). HOST pointers:
- * pos_xyz is n AoS float3 (ms3.Vec, 12 B), dist is n float32. Copies in, runs the kernel, copies out.
- * n==0 -> GSDF_EEMPTY (gleval/cpu.go:97-99). The Go shim checks len(pos)!=len(dist) -> GSDF_ELEN before calling. */
+ * pos_xyz is n AoS float3 (ms3.Vec, 12 B), dist is n float32. The call is pipelined: the batch is cut into chunks that
+ * move host -> device, through the kernel and device -> host on three rotating streams, so the copy of chunk i+1 and the
+ * read-back of chunk i-1 run under the kernel of chunk i (the GL path, gleval/gpu_cgo.go:194-258, uploads, dispatches and
+ * reads back serially). Pinned caller memory (gsdf_host_alloc) is transferred in place, other memory through the
+ * handle's pinned staging. n==0 -> GSDF_EEMPTY (gleval/cpu.go:97-99). The Go shim checks len(pos)!=len(dist) ->
+ * GSDF_ELEN before calling. */
 int gsdf_eval3(gsdf_program *p, const float *pos_xyz, float *dist, size_t n);
 /* gleval.SDF2.Evaluate (gleval/gleval.go:28-37): pos_xy is n AoS float2 (ms2.Vec, 8 B). */
 int gsdf_eval2(gsdf_program *p, const float *pos_xy, float *dist, size_t n);
@@ -101,13 +116,39 @@ enum {
     GSDF_MESH_PRUNE = 1u << 0,      /* octree level-3 prune (octreerenderer.go:180-191,240-284); off = FlatRenderer */
     GSDF_MESH_KEEP_CASES = 1u << 1, /* also keep the 8-bit cube-case index per cell (parity checks) */
     GSDF_MESH_KEEP_GRID = 1u << 2,  /* keep the distance lattice readable through gsdf_mesh_grid */
-    GSDF_MESH_STAGE_TIMING = 1u << 3 /* time every stage (gsdf_mesh_timings [0..3]): launches eagerly with events between the
+    GSDF_MESH_STAGE_TIMING = 1u << 3, /* time every stage (gsdf_mesh_timings [0..3]): launches eagerly with events between the
                                         stages; without it steady-state reruns replay one CUDA graph and only [4] is filled */
+    GSDF_MESH_PRUNE_LITERAL = 1u << 4 /* with GSDF_MESH_PRUNE: margin 1 at every level-3 cube (see gsdf_prune_plan) */
 };
+
+/* The coarse-to-fine prune. The reference's rule (octreePrunea, octreerenderer.go:240-284) drops a cube when
+ * |d(centre)| >= size * sqrt3/2. Its scheduler (octreerenderer.go:94-104,136-151) applies the rule first to the cubes of
+ * level top-4 (4096 cubes fill its 4680-cube prune buffer) and to level-3 cubes only for the part of the model that is
+ * still unrendered when that buffer drains -- which part that is depends on buffer sizes and un-vendored helpers. On
+ * fields that are not 1-Lipschitz (smooth blends, knurls) the literal rule at level 3 everywhere drops a few cells that
+ * hold surface, which the reference's own runs do not lose (README.md:152: 309,872 triangles from both renderers).
+ * A plan is a list of levels, coarse to fine (level L = cubes of 2^(L-1) cells, aligned to the lattice origin like
+ * ms3.Octree cubes); a cube is kept iff |d(centre)| < margin * size * sqrt3/2 and only the children of kept cubes are
+ * looked at on the next level. The last level must be 3 (the marching-cubes stage works on 4-cell blocks).
+ * Default plan (GSDF_MESH_PRUNE): level 3 with margin GSDF_PRUNE_MARGIN_DEFAULT, preceded by a coarse level on large
+ * lattices; it reproduces the dense sweep on every scene of the reference's examples, the README's two known answers
+ * included. GSDF_MESH_PRUNE_LITERAL: the same levels with margin 1 (bit-equal to the dense sweep on 1-Lipschitz fields). */
+#define GSDF_PRUNE_MARGIN_DEFAULT 1.25f
+#define GSDF_PRUNE_MAX_LEVELS 4
+typedef struct {
+    int32_t nlevels;
+    int32_t level[GSDF_PRUNE_MAX_LEVELS];  /* strictly descending, each in [3, 12], last == 3 */
+    float margin[GSDF_PRUNE_MAX_LEVELS];   /* >= 1 */
+} gsdf_prune_plan;
+/* The plan gsdf_mesh_begin uses for `flags` on this lattice. */
+int gsdf_prune_plan_default(const gsdf_lattice *lat, unsigned flags, gsdf_prune_plan *out);
 /* glrender.NewOctreeRenderer / FlatRenderer.Reset (octreerenderer.go:45, flatrenderer.go:37) on cells
  * cz in [cz0,cz1) of the lattice (Z-slab; pass 0,n[2] for everything). The whole slab is meshed on the device
  * inside this call; triangles stay in HBM until read. */
 int gsdf_mesh_begin(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, unsigned flags, gsdf_mesher **out);
+/* Same with an explicit prune plan (implies GSDF_MESH_PRUNE). */
+int gsdf_mesh_begin_plan(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, unsigned flags, const gsdf_prune_plan *plan,
+                         gsdf_mesher **out);
 /* Re-run the same slab on the same handle, reusing every device buffer (Renderer.Reset semantics). */
 int gsdf_mesh_rerun(gsdf_mesher *m);
 /* Point the mesher at another (3D) program on the same device, keeping lattice and buffers: Renderer.Reset with a
@@ -146,6 +187,39 @@ int gsdf_mesh_grid(gsdf_mesher *m, float *grid, size_t nfloats);
  * [2] classify+scan, [3] emit, [4] total. */
 int gsdf_mesh_timings(const gsdf_mesher *m, float ms[5]);
 void gsdf_mesh_destroy(gsdf_mesher *m);
+
+/* Multi-device mesher ---------------------------------------------------------------------------------------------- */
+/* One lattice meshed by several GPUs from ONE process: the device analogue of FlatRenderer.evalGrid's split of the corner
+ * planes over goroutines (glrender/flatrenderer.go:103-141). The cell layers are cut into ndev * slabs_per_device Z-slabs
+ * (one shared corner plane between neighbours, cuts on 4-layer block boundaries where the lattice allows), dealt round-robin
+ * to the devices -- slab j lives on devs[j % ndev] -- so that slabs finish in roughly their output order and a lattice
+ * whose surface is concentrated in a few layers still spreads over all devices. Every slab is an ordinary mesher with its
+ * own stream; every device has its own copy of the program, one host worker thread, and pinned staging. There is no
+ * collective: per-slab triangle buffers are concatenated in slab order in the caller's host buffer, which reproduces the
+ * single-device output bit for bit. ndev == 1 with several slabs pipelines one device: the read-back of slab i runs under
+ * the kernels of slab i+1 (the counts are read, not predicted). */
+typedef struct gsdf_multimesher gsdf_multimesher;
+int gsdf_multi_begin(int ndev, const int *devs, int slabs_per_device, const void *blob, size_t blob_bytes, const float *aux,
+                     size_t aux_floats, const gsdf_lattice *lat, unsigned flags, gsdf_multimesher **out);
+/* gsdf_program_update on every device's copy of the program. */
+int gsdf_multi_update(gsdf_multimesher *mm, const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats);
+/* Render the lattice and deliver every triangle, in FlatRenderer order, to tri9 (HOST memory for max_tris triangles; pinned
+ * memory is written by DMA directly). Returns the triangle count; if the buffer is too small nothing is copied and the
+ * call fails with GSDF_ESHORT (gsdf_multi_stats then tells the count). tri9 == NULL renders without read-back. */
+int64_t gsdf_multi_render(gsdf_multimesher *mm, float *tri9, size_t max_tris);
+/* Renderer.ReadTriangles on the last render: up to max_tris triangles from the read position (0 = io.EOF). */
+int64_t gsdf_multi_read(gsdf_multimesher *mm, float *tri9, size_t max_tris);
+/* Moves the read position of gsdf_multi_read back to the first triangle of the last render. */
+int gsdf_multi_rewind(gsdf_multimesher *mm);
+/* Totals of the last render; device_ms = the longest device time over the slabs' streams (may be NULL). */
+int gsdf_multi_stats(const gsdf_multimesher *mm, uint64_t *evals, uint64_t *pruned_unit_cubes, uint64_t *tris, float *device_ms);
+/* The partition: nslabs+1 cell-layer cuts and the device of each slab; returns nslabs (arrays may be NULL). */
+int gsdf_multi_slabs(const gsdf_multimesher *mm, int32_t *cuts, int32_t *devices, int max_slabs);
+/* WriteBinarySTL of the last render packed on the devices (per-slab records concatenated behind one header). */
+int64_t gsdf_multi_stl(gsdf_multimesher *mm, void *dst, size_t dst_bytes);
+void gsdf_multi_destroy(gsdf_multimesher *mm);
+/* The Z-slab cuts gsdf_multi_begin uses (host arithmetic): nslabs+1 ascending cell layers from 0 to nz. */
+int gsdf_slab_cuts(int nz, int nslabs, int32_t *cuts);
 
 /* Dual contouring --------------------------------------------------------------------------------------------- */
 /* glrender.DualContourRenderer (glrender/dual_contour.go:12-218) with its vertex placement strategies

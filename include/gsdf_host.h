@@ -10,7 +10,7 @@
 #include <stddef.h>
 #include <stdint.h>
 
-#include "gsdf_b200.h"
+#include "gsdf_b200.h" /* status codes only: libgsdfhost.so calls nothing of libgsdfb200.so */
 #include "gsdf_tree.h"
 
 #ifdef __cplusplus
@@ -96,9 +96,8 @@ const float *gsdfh_flat_aux(const gsdfh_flat *f, size_t *nfloats);
 void gsdfh_flat_info(const gsdfh_flat *f, int32_t info[5]);
 void gsdfh_flat_free(gsdfh_flat *f);
 
-/* NewCUDASDF3 / NewCUDASDF2: flatten + gsdf_program_create in one call (mirrors gleval.NewComputeGPUSDF3,
- * gleval/gpu.go:35). */
-int gsdfh_compile(gsdfh_builder *b, int32_t root, gsdf_program **out);
+/* NewCUDASDF3 / NewCUDASDF2 (mirrors gleval.NewComputeGPUSDF3, gleval/gpu.go:35) = gsdfh_flatten here + gsdf_program_create of
+ * libgsdfb200.so on the blob: this library has no CUDA dependency (bench.py's CPU reference arm loads it alone). */
 
 #ifdef __cplusplus
 }

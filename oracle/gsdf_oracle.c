@@ -1092,6 +1092,34 @@ int64_t go_flat_eval_grid(const go_tree *t, const go_lattice *lat, float *grid, 
     return err ? err : evals;
 }
 
+/* Corner planes [k0, k1) only (same positions as the whole-lattice call: origin + float32(k)*res with the ABSOLUTE plane
+ * index), written to `planes` as (k1-k0) x (ny+1) x (nx+1) floats. Lets tests compare single Z-slabs of lattices that are
+ * too large to evaluate whole on the CPU. */
+int64_t go_flat_eval_planes(const go_tree *t, const go_lattice *lat, int k0, int k1, float *planes, int nthreads, int batch) {
+    if (batch < 8 || nthreads < 1 || k0 < 0 || k1 > lat->n[2] + 1 || k0 >= k1) return -1;
+    int nk = k1 - k0;
+    int G = nthreads > nk ? nk : nthreads;
+    slab_job *jobs = (slab_job *)calloc(G, sizeof(slab_job));
+    pthread_t *th = (pthread_t *)calloc(G, sizeof(pthread_t));
+    if (!jobs || !th) { free(jobs); free(th); return -2; }
+    size_t sz = (size_t)(lat->n[0] + 1) * (lat->n[1] + 1);
+    for (int g = 0; g < G; g++) {
+        jobs[g].t = t; jobs[g].lat = lat; jobs[g].batch = batch;
+        jobs[g].grid = planes - (size_t)k0 * sz; /* the worker indexes by absolute plane; only [k0, k1) is touched */
+        jobs[g].k0 = k0 + (int)((int64_t)g * nk / G);
+        jobs[g].k1 = k0 + (int)((int64_t)(g + 1) * nk / G);
+    }
+    if (G == 1) slab_worker(&jobs[0]);
+    else {
+        for (int g = 0; g < G; g++) pthread_create(&th[g], NULL, slab_worker, &jobs[g]);
+        for (int g = 0; g < G; g++) pthread_join(th[g], NULL);
+    }
+    int64_t evals = 0; int err = 0;
+    for (int g = 0; g < G; g++) { evals += jobs[g].evals; if (jobs[g].err) err = jobs[g].err; }
+    free(jobs); free(th);
+    return err ? err : evals;
+}
+
 /* marchcubes.go:76-98 */
 static inline void mc_interp(const float *p1, const float *p2, float v1, float v2, float x, float *out) {
     const float eps = 1e-12f;
@@ -1205,6 +1233,58 @@ int64_t go_octree_prune_mask(const go_tree *t, const go_lattice *lat, uint8_t *m
     }
     free(c); free(d);
     return err ? err : kept;
+}
+
+/* Coarse-to-fine prune plan (include/gsdf_b200.h, gsdf_prune_plan): the same rule applied level by level, coarse to fine,
+ * to the children of surviving cubes only, with a margin on the threshold: keep iff |d(centre)| < margin * size * sqrt3/2.
+ * margin 1 on a single level 3 is go_octree_prune_mask above. Cubes of level L are 2^(L-1) cells wide and aligned to the
+ * lattice origin (ms3.Octree.CubeOrigin). mask = level-3 verdicts [nbz][nby][nbx]; *evals = centres evaluated. */
+int64_t go_octree_prune_plan(const go_tree *t, const go_lattice *lat, int nlevels, const int *levels, const float *margins, uint8_t *mask,
+                             int64_t *evals) {
+    if (nlevels < 1 || levels[nlevels - 1] != 3) return -1;
+    uint8_t *parent = NULL;
+    int pw = 0, pnx = 0, pny = 0;
+    int64_t nev = 0, kept = 0;
+    for (int li = 0; li < nlevels; li++) {
+        int w = 1 << (levels[li] - 1);
+        int ncx = (lat->n[0] + w - 1) / w, ncy = (lat->n[1] + w - 1) / w, ncz = (lat->n[2] + w - 1) / w;
+        size_t nc = (size_t)ncx * ncy * ncz;
+        uint8_t *cur = li == nlevels - 1 ? mask : (uint8_t *)malloc(nc);
+        v3 *c = (v3 *)malloc(sizeof(v3) * nc);
+        float *d = (float *)malloc(sizeof(float) * nc);
+        size_t *idx = (size_t *)malloc(sizeof(size_t) * nc);
+        if (!cur || !c || !d || !idx) { free(c); free(d); free(idx); return -2; }
+        float size = lat->res * (float)w;
+        float half = size * 0.5f;
+        float maxDist = size * (float)(GLRENDER_SQRT3 / 2) * margins[li];
+        size_t m = 0, i = 0;
+        for (int cz = 0; cz < ncz; cz++)
+            for (int cy = 0; cy < ncy; cy++)
+                for (int cx = 0; cx < ncx; cx++, i++) {
+                    cur[i] = 0;
+                    if (parent) {
+                        int r = pw / w;
+                        if (!parent[((size_t)(cz / r) * pny + (cy / r)) * pnx + (cx / r)]) continue;
+                    }
+                    c[m].x = (lat->origin[0] + (float)(w * cx) * lat->res) + half;
+                    c[m].y = (lat->origin[1] + (float)(w * cy) * lat->res) + half;
+                    c[m].z = (lat->origin[2] + (float)(w * cz) * lat->res) + half;
+                    idx[m++] = i;
+                }
+        int err = m ? eval3(t, t->root, c, d, m) : 0;
+        if (!err) {
+            kept = 0;
+            for (size_t k = 0; k < m; k++) { cur[idx[k]] = !(fabsf(d[k]) >= maxDist); kept += cur[idx[k]]; }
+            nev += (int64_t)m;
+        }
+        free(c); free(d); free(idx);
+        if (parent) free(parent);
+        parent = li == nlevels - 1 ? NULL : cur;
+        pw = w; pnx = ncx; pny = ncy;
+        if (err) { if (parent) free(parent); return err; }
+    }
+    if (evals) *evals = nev;
+    return kept;
 }
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -116,6 +116,9 @@ int64_t go_flat_march_slab(const go_lattice *lat, const float *grid, float *tri9
 /* octreerenderer.go:180-191,240-284: the level-3 prune rule on the flat lattice.
  * mask gets ceil(n/4)^3 bytes (x fastest): 1 if |d(centre)| < size*sqrt3/2 for the 4-cell cube, else 0.
  * returns the number of kept blocks or <0. */
+int64_t go_flat_eval_planes(const go_tree *t, const go_lattice *lat, int k0, int k1, float *planes, int nthreads, int batch);
+int64_t go_octree_prune_plan(const go_tree *t, const go_lattice *lat, int nlevels, const int *levels, const float *margins, uint8_t *mask,
+                             int64_t *evals);
 int64_t go_octree_prune_mask(const go_tree *t, const go_lattice *lat, uint8_t *mask);
 
 /* marchcubes.go:34-73 single cube (exported for table/unit tests). p: 8 corners xyz, v: 8 values. returns ntri. */

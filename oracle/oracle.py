@@ -92,12 +92,16 @@ def lib():
         L.go_octree_levels.argtypes = [f32p, f32p, C.c_float]
         L.go_flat_eval_grid.restype = C.c_int64
         L.go_flat_eval_grid.argtypes = [C.POINTER(GoTree), C.POINTER(GoLattice), vp, C.c_int, C.c_int]
+        L.go_flat_eval_planes.restype = C.c_int64
+        L.go_flat_eval_planes.argtypes = [C.POINTER(GoTree), C.POINTER(GoLattice), C.c_int, C.c_int, vp, C.c_int, C.c_int]
         L.go_flat_march.restype = C.c_int64
         L.go_flat_march.argtypes = [C.POINTER(GoLattice), vp, vp, C.c_int64, vp, vp]
         L.go_flat_march_slab.restype = C.c_int64
         L.go_flat_march_slab.argtypes = [C.POINTER(GoLattice), vp, vp, C.c_int64, vp, vp, C.c_int, C.c_int]
         L.go_octree_prune_mask.restype = C.c_int64
         L.go_octree_prune_mask.argtypes = [C.POINTER(GoTree), C.POINTER(GoLattice), vp]
+        L.go_octree_prune_plan.restype = C.c_int64
+        L.go_octree_prune_plan.argtypes = [C.POINTER(GoTree), C.POINTER(GoLattice), C.c_int, C.POINTER(C.c_int), f32p, vp, C.POINTER(C.c_int64)]
         L.go_mc_cube.restype = C.c_int
         L.go_mc_cube.argtypes = [f32p, f32p, f32p, C.POINTER(C.c_int)]
         L.go_stl_write.restype = C.c_int64
@@ -250,6 +254,33 @@ def flat_eval_grid(tree, lat, nthreads=1, batch=4096):
     return grid, int(ev)
 
 
+def flat_eval_planes(tree, lat, k0, k1, nthreads=1, batch=4096):
+    """Corner planes [k0, k1) of the lattice: float32[k1-k0, ny+1, nx+1], positions as in the whole-lattice sweep."""
+    nx, ny, nz = lat.n
+    out = np.empty((k1 - k0, ny + 1, nx + 1), dtype=np.float32)
+    ev = lib().go_flat_eval_planes(C.byref(tree.c), C.byref(lat), int(k0), int(k1), out.ctypes.data, nthreads, batch)
+    if ev < 0:
+        raise RuntimeError("oracle go_flat_eval_planes failed: %d" % ev)
+    return out
+
+
+def flat_march_planes(lat, planes, cz0, cz1, blockmask=None, want_cases=False):
+    """FlatRenderer.ReadTriangles restricted to cell layers [cz0, cz1), given only the corner planes [cz0, cz1] of the
+    lattice (flat_eval_planes(tree, lat, cz0, cz1 + 1)). Returns (triangles, cases[cz1-cz0, ny, nx] or None)."""
+    nx, ny, nz = lat.n
+    planes = np.ascontiguousarray(planes, dtype=np.float32)
+    assert planes.shape == (cz1 - cz0 + 1, ny + 1, nx + 1)
+    sz = (nx + 1) * (ny + 1) * 4
+    gp = planes.ctypes.data - cz0 * sz  # go_flat_march_slab indexes planes absolutely and touches [cz0, cz1] only
+    cases = np.empty((cz1 - cz0, ny, nx), dtype=np.uint8) if want_cases else None
+    cp = (cases.ctypes.data - cz0 * nx * ny) if cases is not None else None
+    mp = blockmask.ctypes.data if blockmask is not None else None
+    n = lib().go_flat_march_slab(C.byref(lat), gp, None, 0, cp, mp, cz0, cz1)
+    tris = np.empty((max(n, 1), 3, 3), dtype=np.float32)
+    n = lib().go_flat_march_slab(C.byref(lat), gp, tris.ctypes.data, n, cp, mp, cz0, cz1)
+    return tris[:n], cases
+
+
 def octree_prune_mask(tree, lat):
     nx, ny, nz = lat.n
     mask = np.empty(((nz + 3) // 4, (ny + 3) // 4, (nx + 3) // 4), dtype=np.uint8)
@@ -257,6 +288,20 @@ def octree_prune_mask(tree, lat):
     if kept < 0:
         raise RuntimeError("oracle go_octree_prune_mask failed: %d" % kept)
     return mask, int(kept)
+
+
+def octree_prune_plan(tree, lat, levels):
+    """Coarse-to-fine prune (gsdf_prune_plan): levels = [(level, margin), ...] ending with level 3. Returns the level-3
+    mask, the kept level-3 count and the number of cube centres evaluated."""
+    nx, ny, nz = lat.n
+    mask = np.empty(((nz + 3) // 4, (ny + 3) // 4, (nx + 3) // 4), dtype=np.uint8)
+    lv = (C.c_int * len(levels))(*[int(l) for l, _ in levels])
+    mg = (C.c_float * len(levels))(*[float(m) for _, m in levels])
+    ev = C.c_int64()
+    kept = lib().go_octree_prune_plan(C.byref(tree.c), C.byref(lat), len(levels), lv, mg, mask.ctypes.data, C.byref(ev))
+    if kept < 0:
+        raise RuntimeError("oracle go_octree_prune_plan failed: %d" % kept)
+    return mask, int(kept), int(ev.value)
 
 
 def flat_march(lat, grid, want_cases=False, blockmask=None, max_tris=None, cz_range=None):

@@ -23,9 +23,9 @@ for scene, resdiv in [("sphere", 70), ("npt-flange", 150), ("bolt", 120), ("knur
     grid, _ = O.flat_eval_grid(t, lat, nthreads=os.cpu_count() or 1)
     sdf = gleval.NewCUDASDF3(s)
     for prune in (True, False):
-        mask = O.octree_prune_mask(t, lat)[0] if prune else None
-        wt, wc = O.flat_march(lat, grid, want_cases=True, blockmask=mask)
         R = (glrender.Octree if prune else glrender.FlatRenderer)(sdf, res, keep_cases=True)
+        mask = O.octree_prune_plan(t, lat, R.Plan())[0] if prune else None
+        wt, wc = O.flat_march(lat, grid, want_cases=True, blockmask=mask)
         for run in range(3):  # eager, graph capture, graph replay
             if run:
                 R.Rerun()

@@ -176,13 +176,13 @@ def test_empty_and_tiny_meshes(oracle, bld):
             if cls is glrender.FlatRenderer:
                 assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), res
             else:
-                mask, _ = oracle.octree_prune_mask(t, lat)
+                mask, _, _ = oracle.octree_prune_plan(t, lat, R.Plan())
                 wp, _ = oracle.flat_march(lat, grid, blockmask=mask)
                 assert np.array_equal(got.view(np.uint32), wp.view(np.uint32)), res
 
 
 def test_programmatic_dependent_launch_is_bit_identical():
-    """The kernels of a render are chained by programmatic dependent launch (kernels.cuh pdl_trigger / pdl_wait; GSDF_PDL=0
+    """The kernels of a render are chained by programmatic dependent launch (generators.cuh pdl_trigger / pdl_wait; GSDF_PDL=0
     switches it off). The switch is read once per process, so the check runs in children: graph replays, eager renders
     and the 3-slab pipeline, with and without the programmatic edges, against stage-timed renders, which always use plain
     launches (scripts/check_pdl.py)."""

@@ -52,6 +52,25 @@ def test_evaluate_matches_oracle_on_reference_lattices(oracle, bld, corpus):
         check_field(name, s, oracle, shapes.sample_points(s))
 
 
+def test_nan_propagation_of_min_max_matches_go_on_gpu(oracle, bld):
+    """math32.Min / Max propagate NaN (gsdf.go:141-143 on Go's math semantics); the kernels use min.NaN.f32 / max.NaN.f32.
+    Far-field positions (ellipse2D turns NaN at |p| ~ 1e6 in the Go formula too) and NaN coordinates through every node
+    type and 60 random trees: NaN exactly where the oracle has NaN, bit-equal elsewhere."""
+    from test_host_interp import far_and_nan_points
+    todo = [(n, sh) for c in ("all3d", "all2d") for n, sh in getattr(shapes, c)(bld)]
+    todo += [(n, sh) for dim in (3, 2) for n, sh in shapes.random_trees(bld, 5, 30, dim)]
+    nans = 0
+    for name, s in todo:
+        pos = far_and_nan_points(s)
+        t = oracle.Tree.from_shader(s)
+        want = t.eval2(pos) if s.is2d else t.eval3(pos)
+        got, _ = gpu_eval(s, pos)
+        diff = (bits(got) != bits(want)) & ~(np.isnan(got) & np.isnan(want))
+        assert not diff.any(), (name, int(diff.sum()))
+        nans += int(np.isnan(want).sum())
+    assert nans > 100   # the inputs do exercise the NaN paths
+
+
 @pytest.mark.parametrize("dim", [3, 2])
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_random_trees_bit_identical(oracle, bld, seed, dim):
@@ -224,13 +243,19 @@ def test_grid_eval_matches_flatrenderer_lattice(oracle, bld):
 
 
 # ---------------------------------------------------------------------------------------------- mesher
-def oracle_mesh(oracle, s, res, prune):
+def oracle_mesh(oracle, s, res, plan):
+    """plan: [] = FlatRenderer, else the renderer's prune plan [(level, margin), ...] (glrender.Octree.Plan())."""
     t = oracle.Tree.from_shader(s)
     lat = oracle.flat_lattice(*s.Bounds(), res)
     grid, ev = oracle.flat_eval_grid(t, lat, nthreads=os.cpu_count() or 1)
-    mask = oracle.octree_prune_mask(t, lat)[0] if prune else None
+    mask, centres = None, 0
+    if plan:
+        mask, _, centres = oracle.octree_prune_plan(t, lat, plan)
     tris, cases = oracle.flat_march(lat, grid, want_cases=True, blockmask=mask)
-    return lat, grid, mask, tris, cases
+    return lat, grid, mask, tris, cases, centres
+
+
+PLANS = {"flat": False, "default": None, "literal": "literal", "two-level": [(5, 1.25), (3, 1.25)], "three-level-literal": [(6, 1.0), (4, 1.0), (3, 1.0)]}
 
 
 def test_sphere_41072_on_gpu(oracle, bld):
@@ -250,14 +275,22 @@ def test_sphere_41072_on_gpu(oracle, bld):
     assert np.array_equal(bits(glrender.RenderAll(f)), bits(tris))
 
 
-@pytest.mark.parametrize("prune", [False, True])
+@pytest.mark.parametrize("prune", list(PLANS))
 @pytest.mark.parametrize("scene,resdiv", [("sphere", 70), ("npt-flange", 150), ("bolt", 160), ("knurled-cylinder", 170)])
 def test_mesh_bit_identical_to_oracle(oracle, bld, scene, resdiv, prune):
+    """Every renderer mode against the oracle's restatement: the dense sweep, the default coarse-to-fine prune (level 3 with
+    margin 1.25), the reference's literal rule at level 3, and explicit multi-level plans (parent / child bookkeeping)."""
     s = bld.NewSphere(1.0) if scene == "sphere" else gsdf.scene(bld, scene)
     res = np.float32(s.Diagonal() / np.float32(resdiv))
-    lat, grid, mask, wt, wc = oracle_mesh(oracle, s, res, prune)
     sdf = gleval.NewCUDASDF3(s)
-    R = (glrender.Octree if prune else glrender.FlatRenderer)(sdf, res, keep_cases=True, keep_grid=True)
+    if PLANS[prune] is False:
+        R = glrender.FlatRenderer(sdf, res, keep_cases=True, keep_grid=True)
+    else:
+        R = glrender.Octree(sdf, res, keep_cases=True, keep_grid=True, prune=PLANS[prune])
+    prune = PLANS[prune] is not False
+    if prune:
+        assert R.Plan()[-1][0] == 3
+    lat, grid, mask, wt, wc, centres = oracle_mesh(oracle, s, res, R.Plan())
     assert list(R.lat.n) == list(lat.n)
     cases = R.Cases()
     assert int((cases != wc).sum()) == 0                       # cube-case indices bit-identical
@@ -274,19 +307,21 @@ def test_mesh_bit_identical_to_oracle(oracle, bld, scene, resdiv, prune):
         g = R.Grid()                                           # evaluated corners agree; pruned ones hold the fill value
         ev = bits(g) != np.uint32(0x7f7f7f7f)
         assert np.array_equal(bits(g)[ev], bits(grid)[ev]) and ev.sum() < grid.size
+        nq = (lat.n[0] + 1 + 3) // 4 * 4                       # evaluations = cube centres of every level + listed lattice quads
+        assert (R.Evaluations() - centres) % 4 == 0 and centres < R.Evaluations() <= centres + nq * (lat.n[1] + 1) * (lat.n[2] + 1)
     R.Rerun()                                                  # Reset/re-render reuses buffers and reproduces the result
     assert np.array_equal(bits(R.AllTriangles()), bits(wt))
 
 
-@pytest.mark.parametrize("prune", [False, True])
+@pytest.mark.parametrize("prune", ["flat", "default", "literal", "two-level"])
 def test_random_trees_mesh_bit_identical(oracle, bld, prune):
     """The mesher on seeded random trees (tests/shapes.py): lattice, cube-case indices, triangles and their order are
     the oracle's for shapes with thin shells, arrays and non-Lipschitz fields, with and without the octree prune."""
     for name, s in shapes.random_trees(bld, 11, 10, 3, depth=3):
         res = np.float32(s.Diagonal() / np.float32(60))
-        lat, grid, mask, wt, wc = oracle_mesh(oracle, s, res, prune)
         sdf = gleval.NewCUDASDF3(s)
-        R = (glrender.Octree if prune else glrender.FlatRenderer)(sdf, res, keep_cases=True)
+        R = glrender.FlatRenderer(sdf, res, keep_cases=True) if PLANS[prune] is False else glrender.Octree(sdf, res, keep_cases=True, prune=PLANS[prune])
+        lat, grid, mask, wt, wc, _ = oracle_mesh(oracle, s, res, R.Plan())
         assert list(R.lat.n) == list(lat.n), name
         assert int((R.Cases() != wc).sum()) == 0, name
         tris = R.AllTriangles()
@@ -318,15 +353,21 @@ def test_showerhead_resdiv350_readme_counts(oracle, bld):
     f = glrender.NewFlatRenderer(sdf, res)
     assert f.NumTriangles() == 309872 and f.Evaluations() == 1512024
     o = glrender.NewOctreeRenderer(sdf, res, 32768)
-    assert o.NumTriangles() == 309849  # level-3 prune rule on a non-Lipschitz field: see tests/test_oracle_kat.py
+    assert o.NumTriangles() == 309872  # README.md:152: the reference's octree run; default plan (level 3, margin 1.25)
+    assert o.Evaluations() < f.Evaluations()
     t = oracle.Tree.from_shader(s)
     lat = oracle.flat_lattice(*s.Bounds(), res)
     grid, _ = oracle.flat_eval_grid(t, lat, nthreads=os.cpu_count() or 1)
     want, _ = oracle.flat_march(lat, grid)
     assert np.array_equal(bits(f.AllTriangles()), bits(want))
+    assert np.array_equal(bits(o.AllTriangles()), bits(want))   # the pruned render equals the dense sweep bit for bit
+    # the reference's rule applied literally to EVERY level-3 cube drops 23 triangles on this field (smooth blends and
+    # knurls are not 1-Lipschitz); the reference's scheduler never gets to most of those cubes
+    lit = glrender.NewOctreeRenderer(sdf, res, 32768, prune="literal")
+    assert lit.NumTriangles() == 309849
     mask, _ = oracle.octree_prune_mask(t, lat)
     wantp, _ = oracle.flat_march(lat, grid, blockmask=mask)
-    assert np.array_equal(bits(o.AllTriangles()), bits(wantp))
+    assert np.array_equal(bits(lit.AllTriangles()), bits(wantp))
 
 
 def test_golden_mesh_fixtures(bld):
@@ -341,8 +382,9 @@ def test_golden_mesh_fixtures(bld):
         assert hashlib.sha256(tris.tobytes()).digest() == g[name + ".tri_sha"].tobytes()
         assert hashlib.sha256(R.Cases().tobytes()).digest() == g[name + ".case_sha"].tobytes()
         assert hashlib.sha256(R.STLBytes()).digest() == g[name + ".stl_sha"].tobytes()
-        P = glrender.Octree(sdf, np.float32(g[name + ".res"]))
+        P = glrender.Octree(sdf, np.float32(g[name + ".res"]), prune="literal")
         assert P.NumTriangles() == int(g[name + ".ntri_pruned"])
+        assert glrender.Octree(sdf, np.float32(g[name + ".res"])).NumTriangles() == int(g[name + ".ntri"])  # default plan == dense sweep
 
 
 def test_read_triangles_streaming_contract(bld):
@@ -391,7 +433,7 @@ def test_octree_awkward_resolutions_gpu(oracle, bld):
     r = glrender.NewOctreeRenderer(sdf, np.float32(1 / 32), 1 << 12)
     for res in [1 / 4, 1 / 8, 1 / 37, 1 / 4.000001, 1 / 13, 1 / 3.5]:
         r.Reset(sdf, np.float32(res))
-        _, _, _, wt, _ = oracle_mesh(oracle, s, np.float32(res), True)
+        _, _, _, wt, _, _ = oracle_mesh(oracle, s, np.float32(res), r.Plan())
         tris = glrender.RenderAll(r)
         assert len(tris) > 0 and np.array_equal(bits(tris), bits(wt))
 
@@ -496,7 +538,7 @@ def test_program_update_reuses_the_handle(oracle, bld):
     lat = oracle.flat_lattice(*a.Bounds(), res)
     tb = oracle.Tree.from_shader(b)
     grid, _ = oracle.flat_eval_grid(tb, lat)
-    mask, _ = oracle.octree_prune_mask(tb, lat)
+    mask, _, _ = oracle.octree_prune_plan(tb, lat, r.Plan())
     wt, _ = oracle.flat_march(lat, grid, blockmask=mask)
     assert r.NumTriangles() == len(wt) != n_a
     assert np.array_equal(bits(r.AllTriangles()), bits(wt))
@@ -531,7 +573,7 @@ def test_bounds_overload_and_driver(oracle, bld, capsys):
     tris = gsdfaux.RenderShader3D(w, gsdfaux.RenderConfig(STLOutput=buf, Resolution=0.09, UseGPU=True))
     out = capsys.readouterr().out
     assert "evaluated SDF" in out and "percent evaluations omitted in octree pruning step" in out and "render done" in out
-    lat, grid, mask, wt, _ = oracle_mesh(oracle, w, np.float32(0.09), True)
+    lat, grid, mask, wt, _, _ = oracle_mesh(oracle, w, np.float32(0.09), [(3, 1.25)])
     assert np.array_equal(bits(tris), bits(wt))
     buf.seek(0)
     assert np.array_equal(bits(glrender.ReadBinarySTL(buf)), bits(wt))

@@ -16,17 +16,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_library_exports_every_declared_symbol():
+    """include/gsdf_b200.h is exported by libgsdfb200.so, include/gsdf_host.h by libgsdfhost.so, and the ctypes binding
+    covers exactly the declared set. The host library has no CUDA dependency and calls nothing of the device library."""
     declared = set()
-    for h in ("gsdf_b200.h", "gsdf_host.h"):
+    for h, path in (("gsdf_b200.h", _lib.LIB_PATH), ("gsdf_host.h", _lib.HOST_LIB_PATH)):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-        declared |= set(re.findall(r"\b(gsdfh?_[a-z0-9_]+)\s*\(", src))
-    assert len(declared) >= 45
-    lib = C.CDLL(_lib.LIB_PATH)
-    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
-    assert not missing, missing
+        names = set(re.findall(r"\b(gsdfh?_[a-z0-9_]+)\s*\(", src))
+        assert len(names) >= 30
+        lib = C.CDLL(path)
+        missing = [s for s in sorted(names) if not hasattr(lib, s)]
+        assert not missing, (h, missing)
+        declared |= names
     bound = set(_lib.lib._gsdf_signatures)
     assert declared == bound, (declared ^ bound)
+    import subprocess
+    needed = subprocess.run(["readelf", "-d", _lib.HOST_LIB_PATH], capture_output=True, text=True).stdout
+    assert "cudart" not in needed and "libcuda" not in needed and "gsdfb200" not in needed
+    undefined = subprocess.run(["nm", "-D", "--undefined-only", _lib.HOST_LIB_PATH], capture_output=True, text=True).stdout
+    assert "gsdf_" not in undefined and "cuda" not in undefined.lower()
 
 
 def test_no_cpu_fallback_without_a_device(bld):

@@ -77,8 +77,9 @@ def test_experimental_radius_reuse_device_code(oracle, bld, monkeypatch):
 
 def test_math32_source_matches_oracle(oracle):
     """math32.cuh (the kernels' elementary functions, host branches) against the oracle's independent restatement of
-    chewxy/math32, input by input, special values included: bit-equal everywhere; Min/Max differ only in that the device
-    instruction drops a NaN operand where Go propagates it."""
+    chewxy/math32, input by input, special values included: bit-equal everywhere, NaN propagation of Min/Max included
+    (min.NaN.f32 / max.NaN.f32 on the device); the one corner left is Min(NaN, -Inf) / Max(NaN, +Inf), where Go tests the
+    infinity first."""
     import ctypes as C
     L = C.CDLL(hostinterp.build())
     OL = oracle.lib()
@@ -107,8 +108,8 @@ def test_math32_source_matches_oracle(oracle):
         L.host_m32_binary(fn, vp(x), vp(y), vp(out), C.c_size_t(len(x)))
         want = np.array([getattr(OL, ofn)(C.c_float(float(a)), C.c_float(float(b))) for a, b in zip(x, y)], np.float32)
         d = differs(out, want)
-        if fn >= 2:
-            d &= ~(np.isnan(x) | np.isnan(y))   # NaN operands: fminf / fmaxf return the other operand, Go returns NaN
+        if fn >= 2:   # Go: Min(NaN, -Inf) = -Inf, Max(NaN, +Inf) = +Inf; min.NaN / max.NaN give NaN
+            d &= ~((np.isnan(x) | np.isnan(y)) & (np.isinf(x) | np.isinf(y)))
         assert not d.any(), ofn
 
 
@@ -126,3 +127,27 @@ def test_full_size_baseline_lattices(oracle, bld, scene, resdiv, stride):
     if scene == "npt-flange":
         assert len(pos) == 6711685   # README.md:130 (+1 probe)
     check(oracle, bld, scene, s, pos)
+
+
+def far_and_nan_points(s, n=3000, seed=5):
+    """Positions far outside Bounds() (up to 1e7 times the size: where ellipse2D and friends produce NaN in the Go formulas
+    too) plus points with a NaN coordinate. No infinities: Min(NaN, -Inf) is the one documented corner (math32.cuh)."""
+    rng = np.random.default_rng(seed)
+    mn, mx = s.Bounds()
+    dim = len(mn)
+    c, h = (mn + mx) / 2, (mx - mn) / 2 + 1e-3
+    mag = 10.0 ** rng.uniform(0, 7, (n, 1))
+    pos = (c + rng.uniform(-1, 1, (n, dim)) * h * mag).astype(np.float32)
+    pos[::97, rng.integers(0, dim)] = np.nan
+    return pos
+
+
+def test_nan_propagation_of_min_max_matches_go(oracle, bld):
+    """math32.Min / Max propagate NaN (Go math semantics); so do the device's min.NaN.f32 / max.NaN.f32. Far-field and NaN
+    inputs through every node type: where the oracle yields NaN the interpreter source must, and the other way round."""
+    for corpus in ("all3d", "all2d"):
+        for name, s in getattr(shapes, corpus)(bld):
+            check(oracle, bld, name + "/far", s, far_and_nan_points(s))
+    for dim in (3, 2):
+        for name, s in shapes.random_trees(bld, 5, 30, dim):
+            check(oracle, bld, name + "/far", s, far_and_nan_points(s))

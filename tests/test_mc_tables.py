@@ -46,8 +46,8 @@ def test_oracle_and_cuda_tables_agree(oracle):
 
 
 def test_emit_kernel_pair_table_matches():
-    """kernels.cuh packs the 12 edge->corner pairs 4 bits per edge into two 64-bit literals."""
-    src = open(os.path.join(ROOT, "gsdf_b200", "csrc", "kernels.cuh")).read()
+    """mc_kernels.cuh packs the 12 edge->corner pairs 4 bits per edge into two 64-bit literals."""
+    src = open(os.path.join(ROOT, "gsdf_b200", "csrc", "mc_kernels.cuh")).read()
     m = re.search(r"\(0x([0-9a-f]+)ull >> \(4 \* e\)\) & 0xf\), cb = \(int\)\(\(0x([0-9a-f]+)ull >> \(4 \* e\)\)", src)
     assert m
     pa, pb = int(m.group(1), 16), int(m.group(2), 16)

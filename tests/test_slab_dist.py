@@ -16,7 +16,8 @@ def test_slab_cuts_cover_and_align():
             cuts = slab.slab_cuts(nz, world)
             assert cuts[0] == 0 and cuts[-1] == nz and len(cuts) == world + 1
             assert all(a <= b for a, b in zip(cuts[:-1], cuts[1:]))
-            assert all(c % 4 == 0 for c in cuts[1:-1])
+            if nz // world >= 8:   # slabs at least two prune blocks thick: interior cuts on block boundaries
+                assert all(c % 4 == 0 for c in cuts[1:-1])
             assert sum(b - a for a, b in zip(cuts[:-1], cuts[1:])) == nz
     assert slab.slab_cuts(84, 8) == [0, 8, 20, 28, 40, 52, 60, 72, 84]
     assert slab.rank_slab(84, 1, 2) == (40, 84)
