@@ -1,20 +1,23 @@
 #!/usr/bin/env python3
-"""bench.py -- the hot path on BASELINE.json's headline config: npt-flange at resdiv 400, tree -> pruned lattice
-evaluation -> marching cubes -> triangles (README.md:116,130 of the reference).
+"""bench.py -- the hot path on BASELINE.json's headline config: npt-flange at resdiv 400, tree -> coarse-to-fine pruned
+lattice evaluation -> marching cubes -> triangles (README.md:116,130 of the reference).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A step is one full render of the workload. Own arm (CUDA):
-  value   dense-equivalent SDF evaluations per second: lattice corners of the config (6,711,685; what the
-          reference's FlatRenderer evaluates, README.md:130) divided by the device time of the whole step
-          (prune + evaluate + classify + scan + emit), program and buffers resident in HBM, L2 flushed between steps.
-  e2e     the same metric through the reference-facing API with HOST buffers: upload the flattened tree, render,
-          read every triangle back into (pinned) host memory; wall clock per step.
-  N > 1   one process per GPU (torchrun). Default: every rank renders the full workload ("weak", independent
-          renders, no collective on the data path); the Z-slab partition of ONE lattice across the ranks
-          (north_star's layout, strong scaling) is timed as well and reported under "zslab".
-Reference arm (--impl reference): the CPU oracle's FlatRenderer restatement (the reference is Go and cannot run here)
-on all host threads, same config / metric / unit.
+A step is ONE render of ONE lattice (281x281x85 corners, 423,852 triangles).
+  value   dense-equivalent SDF evaluations per second: the lattice corners of the config (6,711,685 -- what the reference's
+          CPU path evaluates, README.md:130) divided by the device time of the step, program and buffers resident in HBM,
+          L2 flushed between steps. The evaluations actually executed (the prune skips most corners) are reported beside it
+          as evals_executed_per_sec; the ratio against the CPU arm is a ratio of times to the same triangles.
+  e2e     the same metric through the reference-facing C ABI with HOST buffers: upload the flattened tree, render, all
+          triangles in one pinned host buffer in FlatRenderer order; wall clock per step (gsdf_multi_update +
+          gsdf_multi_render: Z-slabs pipelined against their own read-back, counts read, nothing predicted).
+  N > 1   STRONG scaling: the one lattice is split into N Z-slabs (north_star's partition), one process per GPU under
+          torchrun, no collective on the data path; value = lattice corners / max-over-ranks device time. e2e at N > 1 is
+          the in-process multi-device driver (gsdf_multi_*: one host thread per GPU) run by rank 0 over all N GPUs while the
+          other ranks idle at a barrier -- the call a Go program makes.
+Reference arm (--impl reference): the CPU oracle's FlatRenderer restatement (the reference is Go and cannot run here) on
+all host threads, same config / metric / unit; it maps only the CUDA-free host library.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -31,11 +34,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "sdf_evals_per_sec"
+METRIC = "dense_equiv_sdf_evals_per_sec"
 UNIT = "evals/s"
 RESDIV = 400
 SCENE = "npt-flange"
-KERNELS_PER_STEP = 7  # centres (+prune bits), compact, fine eval, mc-count (TMA), look-back scan, mc-emit, finish (publish counters + re-arm)
+
+
+def workload_config(nx, ny, nz, evals, ntri):
+    """The same dict in both arms."""
+    return {"workload": "%s resdiv %d: %dx%dx%d-corner lattice -> marching-cubes triangles (README.md:116,130)" % (SCENE, RESDIV, nx + 1, ny + 1, nz + 1),
+            "evals_dense_equivalent_per_step": int(evals), "triangles_per_step": int(ntri)}
 
 
 def measured_peaks():
@@ -89,31 +97,32 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_scene():
+def build_scene(name=SCENE, resdiv=RESDIV):
     from gsdf_b200 import gsdf
     bld = gsdf.Builder()
-    s = gsdf.scene(bld, SCENE)
-    res = np.float32(s.Diagonal() / np.float32(RESDIV))
+    s = gsdf.scene(bld, name)
+    res = np.float32(s.Diagonal() / np.float32(resdiv))
     return bld, s, res
 
 
 def cpu_render(O, tree, lat, threads, reps):
     """The reference's CPU render step (gsdfaux.go:159-226): FlatRenderer grid evaluation on `threads` workers in
-    4096-point batches + the serial marching-cubes sweep. Returns (seconds per render, evals, triangles)."""
-    best = []
+    4096-point batches + the serial marching-cubes sweep. Returns (seconds per render list, evals, triangles)."""
+    times = []
     ev = ntri = 0
     for _ in range(reps):
         t0 = time.perf_counter()
         grid, ev = O.flat_eval_grid(tree, lat, nthreads=threads, batch=4096)
         tris, _ = O.flat_march(lat, grid)
-        best.append(time.perf_counter() - t0)
+        times.append(time.perf_counter() - t0)
         ntri = len(tris)
-    return best, ev, ntri
+    return times, ev, ntri
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    os.environ["GSDF_HOST_ONLY"] = "1"   # scene builders only: the CUDA library is never mapped in this arm
     from oracle import oracle as O
     O.build()
     bld, s, res = build_scene()
@@ -121,15 +130,16 @@ def run_reference(args, rank, world):
     lat = O.flat_lattice(*s.Bounds(), res)
     cores = os.cpu_count() or 1
     threads = max(1, cores - 1)  # gsdfaux.go:161-164: max(1, GOMAXPROCS-1)
-    cpu_render(O, tree, lat, threads, args.warmup)
+    cpu_render(O, tree, lat, threads, max(args.warmup, 1))
     times, ev, ntri = cpu_render(O, tree, lat, threads, args.steps)
     sec = sum(times) / len(times)
     value = ev / sec
+    nx, ny, nz = lat.n
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s resdiv %d: FlatRenderer dense lattice %dx%dx%d corners + serial marching cubes (CPU restatement of the reference; Go cannot run here)"
-                   % (SCENE, RESDIV, lat.n[0] + 1, lat.n[1] + 1, lat.n[2] + 1), "evals_per_step": ev, "triangles_per_step": ntri},
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(nx, ny, nz, ev, ntri),
+        "arm": {"renderer": "FlatRenderer (dense lattice on %d threads, 4096-point batches) + serial marching cubes: CPU restatement of the reference's path (Go cannot run here)" % threads},
         "triangles_per_sec": ntri / sec,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "full workload per step: %d lattice evaluations + marching cubes -> %d triangles, %d steps" % (ev, ntri, args.steps)},
@@ -142,8 +152,8 @@ def run_reference(args, rank, world):
 
 def bind_to_gpu_numa(local_rank):
     """Pin this rank's host threads to the CPUs local to its GPU (sysfs local_cpulist of the GPU's PCI function) before any
-    pinned buffer is allocated, so first-touch places the triangle staging buffers on the GPU's NUMA node. With 8 ranks
-    each moving 15 MB per step to the host, remote-node placement halves the end-to-end rate. No-op without NUMA info."""
+    pinned buffer is allocated, so first-touch places the triangle staging buffers on the GPU's NUMA node. No-op without
+    NUMA information."""
     try:
         import torch
         pr = torch.cuda.get_device_properties(local_rank)
@@ -165,13 +175,14 @@ def bind_to_gpu_numa(local_rank):
 
 def run_cuda(args, rank, local_rank, world):
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner / debug lines must not share stdout with the JSON line
+    import ctypes as C
     import torch
     import gsdf_b200
-    from gsdf_b200 import gsdf, gleval, glrender, _lib
+    from gsdf_b200 import gleval, glrender, slab, _lib
 
     torch.cuda.set_device(local_rank)
     gsdf_b200.set_device(local_rank)
-    numa = bind_to_gpu_numa(local_rank) if world > 1 else None
+    numa = bind_to_gpu_numa(local_rank) if world > 1 and args.numa else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -182,217 +193,171 @@ def run_cuda(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def allmax(x):
+    def allreduce(x, op):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=op)
         return float(t.item())
+
+    def allmax(x):
+        return allreduce(x, dist.ReduceOp.MAX) if dist is not None else float(x)
 
     def allsum(x):
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return allreduce(x, dist.ReduceOp.SUM) if dist is not None else float(x)
 
+    warm = max(args.warmup, 3)
     bld, s, res = build_scene()
     sdf = gleval.NewCUDASDF3(s)
-    R = glrender.NewOctreeRenderer(sdf, res, 1 << 15)
-    nx, ny, nz = R.lat.n
+    lat = glrender.lattice_from_bounds(*s.Bounds(), res)
+    nx, ny, nz = lat.n
     lattice_evals = (nx + 1) * (ny + 1) * (nz + 1)
-    ntri = R.NumTriangles()
-    evals_exec = R.Evaluations()
-
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def l2_flush():
         flush.fill_(1)
         torch.cuda.synchronize()
 
-    # ---------------- per-stage device times (roofline of the dominant kernel): same workload, launched eagerly with
-    # CUDA events between the stages. The headline loop below replays the render as one CUDA graph, inside which
-    # single kernels cannot be bracketed by events.
-    Rt = glrender.Octree(sdf, res, stage_timing=True)
-    stages = []
-    for i in range(max(args.warmup, 3) + min(args.steps, 50)):
-        l2_flush(); Rt.Rerun()
-        if i >= max(args.warmup, 3):
-            stages.append(Rt.Timings())
-    assert Rt.NumTriangles() == ntri
-    Rt.Close()
-
-    # ---------------- device-resident steps (value)
-    for _ in range(max(args.warmup, 3)):
+    # ---------------- device-resident steps (value): this rank's Z-slab of the ONE lattice (the whole lattice at N = 1)
+    cuts = slab.slab_cuts(nz, world)
+    R = glrender.NewOctreeRenderer(sdf, res, 1 << 15, cz_range=(cuts[rank], cuts[rank + 1]))
+    plan = R.Plan()
+    if world > 1 and not args.no_rebalance:
+        # equal layers are not equal work (the flange's plate faces sit in a few layers): two rounds of re-cutting by the
+        # evaluations each slab executed, from counts every rank reads off its own renderer (an all_gather of N integers
+        # at set-up time -- not on the data path)
+        for _ in range(2):
+            ev = torch.zeros(world, dtype=torch.float64, device="cuda")
+            ev[rank] = R.Evaluations()
+            dist.all_reduce(ev)
+            new = slab.rebalance_cuts(cuts, [float(v) for v in ev.tolist()])
+            if new == cuts:
+                break
+            cuts = new
+            R.Close()
+            R = glrender.NewOctreeRenderer(sdf, res, 1 << 15, cz_range=(cuts[rank], cuts[rank + 1]))
+    ntri_local = R.NumTriangles()
+    evals_local = R.Evaluations()
+    ntri = int(allsum(ntri_local))
+    evals_exec = int(allsum(evals_local))
+    for _ in range(warm):
         l2_flush(); R.Rerun()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     barrier()
     wall0 = time.perf_counter()
-    step_ms = []
+    step_ms, stages = [], []
     for _ in range(args.steps):
         l2_flush()
         R.Rerun()
-        step_ms.append(R.Timings()["total_ms"])
+        t = R.Timings()
+        step_ms.append(t["total_ms"])
+        stages.append(t)
     barrier()
     wall = time.perf_counter() - wall0
     dev_ms = allmax(sum(step_ms))
-    units = allsum(lattice_evals * args.steps)
-    value = units / (dev_ms * 1e-3)
-    tri_rate = allsum(ntri * args.steps) / (dev_ms * 1e-3)
+    value = lattice_evals * args.steps / (dev_ms * 1e-3)
+    mean = {k: sum(st[k] for st in stages) / len(stages) for k in stages[0]}
+    kernels_per_step = len(plan) + 6  # centre levels, compact, lattice eval, count, scan, emit, finish
 
     if args.device_only:
         if rank == 0:
             emit_json({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "ms_per_step": dev_ms / args.steps,
-                       "note": "--device-only: profiling aid, not a bench line", "stage_ms": {k: sum(st[k] for st in stages) / len(stages) for k in stages[0]}})
+                       "note": "--device-only: profiling aid, not a bench line", "stage_ms": mean})
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # ---------------- end to end through the public API with host buffers
-    import ctypes as C
-    host_tris = torch.empty((ntri + 8, 3, 3), dtype=torch.float32).pin_memory()
-    host_np = host_tris.numpy()
+    # ---------------- end to end through the C ABI with host buffers: rank 0 drives all N GPUs from one process
     flat = bld.flatten(s)
     blob, aux = flat["blob"], np.ascontiguousarray(flat["aux"])
-    h2d = len(blob) - 32 + aux.nbytes
-    d2h = ntri * 36 + 32
-
-    auxp = aux.ctypes.data_as(C.POINTER(C.c_float))
-
-    def e2e_step():
-        # upload the flattened tree (host -> device), render, read every triangle back to host memory: one
-        # synchronous round trip per step, nothing carried over between steps
-        _lib.check(_lib.lib.gsdf_program_update(sdf._h, blob, len(blob), auxp, aux.size))
-        R.Rerun()
-        got = 0
-        while got < ntri:
-            n = _lib.lib.gsdf_mesh_read(R._h, C.c_void_p(host_np[got:].ctypes.data), ntri + 8 - got)
-            if n <= 0:
-                break
-            got += n
-        return got
-
-    def timed(step):
-        for _ in range(max(args.warmup, 3)):
-            l2_flush(); step()
-        barrier()
-        times = []
-        for _ in range(args.steps):
-            l2_flush()
-            t0 = time.perf_counter()
-            got = step()
-            times.append(time.perf_counter() - t0)
-            assert got == ntri
-        barrier()
-        return allmax(sum(times))
-
-    single_sec = timed(e2e_step)
-    ref_tris = host_np[:ntri].copy()
-
-    # The same round trip through the Z-slab pipeline of the public API (glrender.SlabPipeline): the lattice is meshed as
-    # three Z-slabs on this GPU and each slab's triangles are copied to the host under the next slab's kernels. In steady
-    # state the copy sizes are predicted from the previous render and verified afterwards, so the step has no host
-    # synchronisation between slabs. This is the headline e2e path.
-    E2E_SLABS = 3
-    pipe = glrender.SlabPipeline(sdf, res, nslabs=E2E_SLABS)
-    host_np[:] = 0
-
-    def e2e_pipe_step():
-        _lib.check(_lib.lib.gsdf_program_update(sdf._h, blob, len(blob), auxp, aux.size))
-        return pipe.RenderToHost(host_np)
-
-    pipe_sec = timed(e2e_pipe_step)
-    assert np.array_equal(host_np[:ntri].view(np.uint32), ref_tris.view(np.uint32)), "slab pipeline and single renderer disagree"
-    pipe.Close()
-    # Both are calls a user can make; the headline is the faster one on this box (with several ranks behind one PCIe
-    # uplink the pipelined copies contend and the plain round trip can win). Both are always reported.
-    e2e_sec = min(pipe_sec, single_sec)
-    e2e_is_pipe = pipe_sec <= single_sec
-    e2e_value = units / e2e_sec
-
-    # Throughput form of the same loop (extra, not the headline): two renderers / two pinned buffers, the D2H copy of
-    # step i (gsdf_mesh_read_async) overlaps the kernels of step i+1. Every step still uploads its tree and delivers
-    # all its triangles to host memory inside the timed region.
-    R2 = [R, glrender.NewOctreeRenderer(sdf, res, 1 << 15)]
-    host2 = [host_np, torch.empty((ntri + 8, 3, 3), dtype=torch.float32).pin_memory().numpy()]
-
-    def overlapped(k):
-        for i in range(k):
-            j = i & 1
-            _lib.check(_lib.lib.gsdf_program_update(sdf._h, blob, len(blob), auxp, aux.size))
-            R2[j].Rerun()   # waits for this renderer's previous copy before touching its triangle buffer
-            n = _lib.lib.gsdf_mesh_read_async(R2[j]._h, C.c_void_p(host2[j].ctypes.data), ntri + 8)
-            assert n == ntri
-        for r in R2:
-            _lib.check(_lib.lib.gsdf_mesh_wait(r._h))
-
-    overlapped(4)
+    h2d = (len(blob) - 32 + aux.nbytes) * world
+    d2h = ntri * 36
+    e2e = None
+    e2e_launches = 0
     barrier()
-    t0 = time.perf_counter()
-    overlapped(args.steps)
-    ov_sec = allmax(time.perf_counter() - t0)
+    if rank == 0:
+        host = glrender.pinned_empty((ntri + 8, 3, 3))
+        ref_tris = None
+        table = {}
+        for spd in ((1, 3, 5) if world == 1 else (1, 2)):
+            M = glrender.MultiRenderer(s, res, devices=list(range(world)), slabs_per_device=spd)
+            assert M.NumTriangles() == ntri
+            if world > 1 and not args.no_rebalance:
+                M.Rebalance(2)
+
+            def step():
+                M.UpdateBlob(blob, aux)          # host -> device: the flattened tree, to every device
+                return M.RenderToHost(host)      # render + device -> host: every triangle, slab order, one buffer
+
+            for _ in range(warm):
+                l2_flush(); step()
+            times = []
+            for _ in range(args.steps):
+                l2_flush()
+                host[:8] = 0
+                t0 = time.perf_counter()
+                got = step()
+                times.append(time.perf_counter() - t0)
+                assert got == ntri
+            if ref_tris is None:
+                ref_tris = glrender.Octree(sdf, res).AllTriangles()
+            assert np.array_equal(host[:ntri].view(np.uint32), ref_tris.view(np.uint32)), "multi-slab output differs from the single renderer"
+            nsl = len(M.Slabs()[1])
+            table["slabs_per_device_%d" % spd] = {"ms_per_step": sum(times) / len(times) * 1e3, "slabs": nsl, "device_ms": M.DeviceMs()}
+            e2e_launches = max(e2e_launches, nsl * kernels_per_step)
+            M.Close()
+        best = min(table, key=lambda k: table[k]["ms_per_step"])
+        sec = table[best]["ms_per_step"] * 1e-3
+        e2e = {"value": lattice_evals / sec, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": sec * 1e3,
+               "triangles_per_sec": ntri / sec, "chosen": best, "by_slabs_per_device": table,
+               "path": "per step: gsdf_multi_update (flattened tree to every device) -> gsdf_multi_render into ONE pinned host buffer: every slab on its own "
+                       "stream, counts read from the device (no prediction), slab i's read-back under the kernels of the later slabs; "
+                       "slabs_per_device_1 at N=1 is the fully synchronous single-renderer round trip"}
     barrier()
-    assert np.array_equal(host2[1][:ntri].view(np.uint32), ref_tris.view(np.uint32)) and np.array_equal(host2[0][:ntri].view(np.uint32), ref_tris.view(np.uint32))
+
+    # ---------------- gleval.SDF3.Evaluate on host slices (the contract north_star names first), rank 0, N = 1 only
+    evaluate = None
+    if rank == 0 and world == 1:
+        evaluate = bench_evaluate(sdf, s, glrender, torch)
+
+    # ---------------- knurled-cylinder resdiv 1600 (BASELINE config 4) by Z-slab: strong scaling where slabs pay
+    knurled = None
+    if not args.no_knurled:
+        knurled = bench_knurled(rank, world, barrier, allmax, allsum, l2_flush, gleval, glrender, slab)
+
     clocks = sampler.stop() if rank == 0 else None
-    e2e_value = units / e2e_sec
-
-    # ---------------- Z-slab partition of ONE lattice across the ranks (north_star's layout; strong scaling)
-    zslab = None
-    if world > 1:
-        from gsdf_b200 import slab
-        cuts = slab.slab_cuts(nz, world)  # interior cuts aligned to the 4-cell prune blocks
-        Rz = glrender.NewOctreeRenderer(sdf, res, 1 << 15, cz_range=(cuts[rank], cuts[rank + 1]))
-        for _ in range(3):
-            l2_flush(); Rz.Rerun()
-        barrier()
-        zs = []
-        for _ in range(args.steps):
-            l2_flush(); Rz.Rerun(); zs.append(Rz.Timings()["total_ms"])
-        barrier()
-        zms = allmax(sum(zs))
-        ztri = allsum(Rz.NumTriangles())
-        zslab = {"scaling": "strong", "value": lattice_evals * args.steps / (zms * 1e-3), "unit": UNIT, "ms_per_step": zms / args.steps,
-                 "triangles_total": int(ztri), "cuts": cuts}
-
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # ---------------- roofline of the dominant kernel, from the live CUDA-event stage times
-    mean = {k: sum(st[k] for st in stages) / len(stages) for k in stages[0]}
+    # ---------------- roofline of the dominant kernel, from the stage times of the timed steps themselves (the kernels
+    # stamp %globaltimer inside the graph replay)
     peak, peak_src = measured_peaks()
-    fine_evals = evals_exec - ((nx + 3) // 4) * ((ny + 3) // 4) * ((nz + 3) // 4)
-    cand = {
-        "k_eval<GenGrid> (fine lattice evaluation)": (4.0 * fine_evals, mean["eval_ms"]),
-        "k_mc_emit (marching-cubes emit)": (4.0 * fine_evals + 36.0 * ntri, mean["emit_ms"]),
-    }
-    kname = max(cand, key=lambda k: cand[k][1])
-    kbytes, kms = cand[kname]
+    # executed = prune-cube centres + 4 per listed lattice quad; with the one-level plan on the whole lattice every level-3
+    # centre is evaluated, otherwise the centres (a few per cent) are left in
+    centres = ((nx + 3) // 4) * ((ny + 3) // 4) * ((nz + 3) // 4) if len(plan) == 1 and world == 1 else 0
+    fine_evals = max(evals_exec - centres, 0)
+    kname = "k_eval<GenGrid> (fine lattice evaluation)"
+    kbytes, kms = 4.0 * fine_evals / world, mean["eval_ms"]
     achieved = kbytes / (kms * 1e-3) / 1e9
-    traffic = None
+    traffic = winst = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(kname.split(" ")[0])
+            tj = json.load(open(tpath))
+            traffic, winst = tj.get("k_eval<GenGrid>"), tj.get("k_eval<GenGrid>.warp_inst")
         except Exception:
-            traffic = None
-
-    # What actually bounds the dominant kernel: warp-instruction issue. Warp instructions per launch come from the ncu
-    # capture of this same command (profiles/traffic.json, smsp__inst_executed.sum); the duration is the live one.
+            pass
     issue = None
-    try:
-        winst = json.load(open(tpath)).get(kname.split(" ")[0] + ".warp_inst")
-        if winst and clocks and clocks.get("sm_mhz"):
-            props = torch.cuda.get_device_properties(local_rank)
-            peak_issue = props.multi_processor_count * 4 * clocks["sm_mhz"] * 1e6  # 4 schedulers/SM, 1 warp-instr/clk each
-            ach = winst / (kms * 1e-3)
-            issue = {"bound": "warp-instruction issue (FP32/ALU/XU pipes)", "achieved": ach / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-instr/s",
-                     "frac": ach / peak_issue, "warp_instructions_per_launch": winst,
-                     "thread_instructions_per_eval": winst * 32 / max(fine_evals, 1),
-                     "source": "smsp__inst_executed.sum from profiles/ (ncu --set full) / live CUDA-event kernel time; peak = SMs x 4 x SM clock"}
-    except Exception:
-        issue = None
+    if winst and clocks and clocks.get("sm_mhz") and world == 1:
+        props = torch.cuda.get_device_properties(local_rank)
+        peak_issue = props.multi_processor_count * 4 * clocks["sm_mhz"] * 1e6  # 4 schedulers/SM, 1 warp-instr/clk each
+        ach = winst / (kms * 1e-3)
+        issue = {"bound": "warp-instruction issue (FP32/ALU/XU pipes)", "achieved": ach / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-instr/s",
+                 "frac": ach / peak_issue, "warp_instructions_per_launch": winst, "thread_instructions_per_eval": winst * 32 / max(fine_evals, 1),
+                 "source": "smsp__inst_executed.sum of the ncu capture under profiles/ / the live in-graph kernel time; peak = SMs x 4 x SM clock"}
 
     # ---------------- CPU baseline beside it (rank 0, N == 1 only): bounded sample of the same workload
     cpu = None
@@ -400,12 +365,11 @@ def run_cuda(args, rank, local_rank, world):
         from oracle import oracle as O
         O.build()
         tree = O.Tree.from_shader(s)
-        lat = O.flat_lattice(*s.Bounds(), res)
+        olat = O.flat_lattice(*s.Bounds(), res)
         threads = max(1, (os.cpu_count() or 1) - 1)
-        # bounded sample: full renders of the same workload until ~12 s of CPU work have accumulated
-        times, ev, nt = cpu_render(O, tree, lat, threads, 3)
+        times, ev, nt = cpu_render(O, tree, olat, threads, 3)
         reps = max(5, min(400, int(12.0 / max(sum(times) / len(times), 1e-3))))
-        times, ev, nt = cpu_render(O, tree, lat, threads, reps)
+        times, ev, nt = cpu_render(O, tree, olat, threads, reps)
         assert nt == ntri, "CPU oracle and CUDA path disagree on the triangle count"
         sec = sum(times) / len(times)
         cpu = {"value": ev / sec, "unit": UNIT, "cores": threads, "kind": "port",
@@ -413,41 +377,101 @@ def run_cuda(args, rank, local_rank, world):
                "triangles_per_sec": nt / sec, "ms_per_render": sec * 1e3}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s resdiv %d: octree level-3 prune + marching cubes on a %dx%dx%d-corner lattice%s" %
-                   (SCENE, RESDIV, nx + 1, ny + 1, nz + 1, "" if world == 1 else "; one full render per GPU per step"),
-                   "renderer": "Octree (prune)", "evals_per_step_dense_equivalent": lattice_evals, "evals_executed_per_step": evals_exec,
-                   "triangles_per_step": ntri, "l2": "flushed between steps (256 MiB write); working set 27 MB < 126 MB L2",
-                   "timing": "CUDA events on the launching stream around each step (one CUDA-graph replay of 7 kernel nodes chained by programmatic dependent launch), summed over the timed steps, max over ranks"},
-        "triangles_per_sec": tri_rate,
-        "evals_executed_per_sec": allsum(evals_exec * args.steps) / (dev_ms * 1e-3) if world == 1 else None,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(nx, ny, nz, lattice_evals, ntri),
+        "arm": {"renderer": "Octree: coarse-to-fine prune %s + marching cubes" % plan, "evals_executed_per_step": evals_exec,
+                "partition": "one lattice, %d Z-slab(s), cuts %s (one shared corner plane, no collective)" % (world, cuts),
+                "l2": "flushed between steps (256 MiB write); working set 27 MB < 126 MB L2",
+                "timing": "CUDA events on the launching stream around each step (one CUDA-graph replay of %d kernel nodes chained by programmatic "
+                          "dependent launch), summed over the timed steps, max over ranks" % kernels_per_step},
+        "triangles_per_sec": ntri * args.steps / (dev_ms * 1e-3),
+        "evals_executed_per_sec": evals_exec * args.steps / (dev_ms * 1e-3),
         "stage_ms": mean,
-        "stage_ms_note": "eager launches with events between stages (separate loop of the same workload); the timed steps replay one CUDA graph",
+        "stage_ms_note": "rank 0, from %globaltimer stamps the kernels of the timed graph replays write themselves (same loop as ms_per_step)",
         "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_sec * 1e3 / args.steps, "triangles_per_sec": ntri * world * args.steps / e2e_sec,
-                "path": "slab_pipeline" if e2e_is_pipe else "single_renderer",
-                "slab_pipeline": {"value": units / pipe_sec, "unit": UNIT, "ms_per_step": pipe_sec * 1e3 / args.steps,
-                                  "path": "per step: gsdf_program_update(upload flattened tree) -> glrender.SlabPipeline(%d Z-slabs).RenderToHost: gsdf_mesh_rerun_begin + gsdf_mesh_read_prefix_async per slab (copy of slab i under the kernels of slab i+1, copy sizes predicted from the previous step and verified), all triangles in pinned host memory when the step returns" % E2E_SLABS},
-                "single_renderer": {"value": units / single_sec, "unit": UNIT, "ms_per_step": single_sec * 1e3 / args.steps,
-                                    "path": "per step: gsdf_program_update -> gsdf_mesh_rerun -> gsdf_mesh_read, one renderer, fully synchronous"},
-                "overlapped": {"value": units / ov_sec, "unit": UNIT, "ms_per_step": ov_sec * 1e3 / args.steps,
-                               "note": "same per-step work, D2H of step i overlapped with the kernels of step i+1 (gsdf_mesh_read_async, two renderers)"}},
-        "gpu_launches": KERNELS_PER_STEP * args.steps,
+        "e2e": e2e,
+        "gpu_launches": kernels_per_step * args.steps,
+        "gpu_launches_e2e_per_step": e2e_launches,
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": kbytes, "avg_launch_ms": kms, "peak_source": peak_src,
-                     "note": "deep CSG trees are FP32-issue bound, not HBM bound (DESIGN.md); see profiles/ for issue-slot utilisation"},
+                     "note": "deep CSG trees are FP32-issue bound, not HBM bound (DESIGN.md); roofline_issue is the view that binds"},
         "roofline_issue": issue,
+        "evaluate_e2e": evaluate,
+        "knurled1600_zslab": knurled,
         "host_affinity": numa,
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
-    if zslab:
-        line["zslab"] = zslab
     emit_json(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def bench_evaluate(sdf, s, glrender, torch):
+    """gleval.SDF3.Evaluate(pos, dist) on HOST slices through gsdf_eval3 (pipelined chunks): the reference's batch size
+    (32768 points, the evaluation buffer of gsdfaux.go:150) and a 2^24-point batch, pinned and pageable. PCIe roofline:
+    12 B/eval travel host->device and 4 B/eval back on a full-duplex link, so the H2D direction bounds it."""
+    rng = np.random.default_rng(0)
+    mn, mx = s.Bounds()
+    out = {}
+    big = 1 << 24
+    ppos = glrender.pinned_empty((big, 3))
+    ppos[:] = (mn + rng.random((big, 3), dtype=np.float32) * (mx - mn)).astype(np.float32)
+    pdist = glrender.pinned_empty((big,))
+    # live H2D bandwidth of this box (pinned, 192 MiB)
+    dbuf = torch.empty(big * 3, dtype=torch.float32, device="cuda")
+    hsrc = torch.from_numpy(ppos.reshape(-1))
+    best = 1e9
+    for _ in range(4):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        dbuf.copy_(hsrc, non_blocking=True); torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    h2d_gbs = big * 12 / best / 1e9
+    del dbuf
+    for label, n, reps in (("batch_32768", 32768, 200), ("batch_2p24", big, 5)):
+        for kind in ("pinned", "pageable"):
+            if kind == "pinned":
+                pos, dst = ppos[:n], pdist[:n]
+            else:
+                pos, dst = np.array(ppos[:n]), np.empty(n, np.float32)
+                dst[:] = 0   # touch the pages once: first-touch faults are the allocator's cost, not the transfer's
+            for _ in range(2):
+                sdf.Evaluate(pos, dst)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                sdf.Evaluate(pos, dst)
+            sec = (time.perf_counter() - t0) / reps
+            out["%s_%s" % (label, kind)] = {"evals_per_sec": n / sec, "ms_per_call": sec * 1e3, "h2d_GBps": n * 12 / sec / 1e9,
+                                           "pcie_roofline_frac": (n * 12 / sec / 1e9) / h2d_gbs}
+    out["h2d_peak_GBps_measured"] = h2d_gbs
+    out["bytes_per_eval"] = {"h2d": 12, "d2h": 4}
+    out["path"] = "gsdf_eval3 on host memory: chunks of 256 Ki points rotate through three streams (copy in, k_eval_stream, copy out)"
+    return out
+
+
+def bench_knurled(rank, world, barrier, allmax, allsum, l2_flush, gleval, glrender, slab):
+    """BASELINE config 4: knurled-cylinder at resdiv 1600 (564x564x1408 corners = 447.9 M), one lattice split into `world`
+    Z-slabs. Device time per render, max over ranks."""
+    bld, s, res = build_scene("knurled-cylinder", 1600)
+    sdf = gleval.NewCUDASDF3(s)
+    lat = glrender.lattice_from_bounds(*s.Bounds(), res)
+    nz = lat.n[2]
+    cuts = slab.slab_cuts(nz, world)
+    R = glrender.NewOctreeRenderer(sdf, res, 1 << 15, cz_range=(cuts[rank], cuts[rank + 1]))
+    for _ in range(2):
+        l2_flush(); R.Rerun()
+    barrier()
+    ms = []
+    for _ in range(5):
+        l2_flush(); R.Rerun(); ms.append(R.Timings()["total_ms"])
+    barrier()
+    tot = allmax(sum(ms)) / len(ms)
+    dense = (lat.n[0] + 1) * (lat.n[1] + 1) * (nz + 1)
+    out = {"scaling": "strong", "ms_per_render": tot, "dense_equiv_evals_per_sec": dense / (tot * 1e-3), "evals_executed": int(allsum(R.Evaluations())),
+           "triangles": int(allsum(R.NumTriangles())), "lattice_corners": dense, "plan": R.Plan(), "cuts": cuts}
+    R.Close()
+    return out
 
 
 _JSON_OUT = None
@@ -470,19 +494,20 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-knurled", action="store_true")
+    ap.add_argument("--no-rebalance", action="store_true", help="keep the equal-layer Z-slab cuts (A/B)")
+    ap.add_argument("--numa", action="store_true", help="pin each rank to the CPUs local to its GPU")
     ap.add_argument("--device-only", action="store_true",
-                    help="profiling aid: run only the device-resident loops (stage-timed + graph replay) and print their summary, no e2e legs")
+                    help="profiling aid: run only the device-resident loop and print its summary, no e2e legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        if args.steps > 10:
-            args.steps = 10
         run_reference(args, rank, world)
     else:
         run_cuda(args, rank, local_rank, world)

@@ -113,6 +113,8 @@ def _load(host_only=False):
         "gsdf_multi_stl": (C.c_int64, [vp, vp, C.c_size_t]),
         "gsdf_multi_destroy": (None, [vp]),
         "gsdf_slab_cuts": (C.c_int, [C.c_int, C.c_int, i32p]),
+        "gsdf_slab_rebalance": (C.c_int, [C.c_int, C.c_int, i32p, C.POINTER(C.c_double), i32p]),
+        "gsdf_multi_rebalance": (C.c_int, [vp, C.c_int]),
         "gsdf_mesh_rerun": (C.c_int, [vp]),
         "gsdf_mesh_rerun_begin": (C.c_int, [vp]),
         "gsdf_mesh_rerun_end": (C.c_int, [vp]),

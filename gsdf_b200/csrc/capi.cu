@@ -138,7 +138,7 @@ int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_
 #ifdef GSDF_RXY
             if (fl == (GSDF_RXY_READ | GSDF_RXY_WRITE)) return fail(GSDF_EPROGRAM, "instruction %u: radius flags READ and WRITE are exclusive", n);
 #else
-            if (fl) return fail(GSDF_EPROGRAM, "instruction %u: radius-reuse flags need a library built with -DGSDF_RXY (unset GSDF_RXY in the flattener's environment)", n);
+            if (fl) return fail(GSDF_EPROGRAM, "instruction %u: radius-reuse flags, but this library was built with -DGSDF_NO_RXY (set GSDF_RXY=0 in the flattener's environment)", n);
 #endif
         }
         if (op == GSDF_OP_LINES2D) {
@@ -215,9 +215,9 @@ int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_
 extern "C" {
 
 #ifdef GSDF_RXY
-const char *gsdf_version(void) { return "gsdf-b200 0.2 (sm_100a) +rxy"; }  // radius-reuse build (gsdf_program.h)
+const char *gsdf_version(void) { return "gsdf-b200 0.2 (sm_100a) +rxy"; }  // with the radius slot (gsdf_program.h)
 #else
-const char *gsdf_version(void) { return "gsdf-b200 0.2 (sm_100a)"; }
+const char *gsdf_version(void) { return "gsdf-b200 0.2 (sm_100a) -rxy"; }
 #endif
 const char *gsdf_last_error(void) { return g_err.c_str(); }
 

@@ -43,7 +43,8 @@ int kernel_occupancy(KernelDevCache &c, Kern kern, int dev, uint32_t smem, int t
 
 // persistent launch: at most one resident wave of CTAs; they pull tiles from the launch's scheduler slot
 template <int P, class Gen, bool EXT>
-int launch_eval_impl(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st, bool pdl, uint32_t *sched) {
+int launch_eval_impl(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st, bool pdl, uint32_t *sched,
+                     unsigned long long *stamp) {
     static KernelDevCache cache;
     auto kern = k_eval<P, Gen, EXT>;
     const uint32_t smem = smem_total_bytes<P>(p->pv, kEvalThreads);
@@ -55,16 +56,18 @@ int launch_eval_impl(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper
     blocks = std::min<uint64_t>(blocks, (uint64_t)p->sms * occ);
     ProgView pv = p->pv;
     pv.sched = sched ? sched : next_sched(p);
+    pv.stamp = stamp;
     if (pdl) CU(launch_chain(true, kern, dim3((unsigned)blocks), dim3(kEvalThreads), smem, st, pv, gen));
     else kern<<<(unsigned)blocks, kEvalThreads, smem, st>>>(pv, gen);
     CU(cudaGetLastError());
     return 0;
 }
 template <int P, class Gen>
-int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st, bool pdl, uint32_t *sched) {
+int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st, bool pdl, uint32_t *sched,
+                unsigned long long *stamp = nullptr) {
     if (nwork_upper_bound == 0) return 0;
-    return p->needs_ext ? launch_eval_impl<P, Gen, true>(p, gen, nwork_upper_bound, st, pdl, sched)
-                        : launch_eval_impl<P, Gen, false>(p, gen, nwork_upper_bound, st, pdl, sched);
+    return p->needs_ext ? launch_eval_impl<P, Gen, true>(p, gen, nwork_upper_bound, st, pdl, sched, stamp)
+                        : launch_eval_impl<P, Gen, false>(p, gen, nwork_upper_bound, st, pdl, sched, stamp);
 }
 
 // Streaming Evaluate (k_eval_stream): persistent grid, one resident wave, tiles dealt round-robin.
@@ -84,7 +87,9 @@ int launch_stream_impl(const gsdf_program *p, const float *d_pos, float *d_dist,
     if (occ < 1) return 1;
     const uint64_t tiles = (n + (uint64_t)kEvalThreads * 4 - 1) / ((uint64_t)kEvalThreads * 4);
     const unsigned blocks = (unsigned)std::min<uint64_t>(tiles, (uint64_t)p->sms * occ);
-    kern<<<blocks, kEvalThreads, smem, st>>>(p->pv, d_pos, d_dist, n);
+    ProgView pv = p->pv;
+    pv.stamp = nullptr;
+    kern<<<blocks, kEvalThreads, smem, st>>>(pv, d_pos, d_dist, n);
     CU(cudaGetLastError());
     return 0;
 }
@@ -106,8 +111,12 @@ uint32_t *next_sched(const gsdf_program *p, int *slot_index) {
 
 int launch_points3(const gsdf_program *p, const GenPoints3 &g, uint64_t nwork, cudaStream_t st, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, false, sched); }
 int launch_points2(const gsdf_program *p, const GenPoints2 &g, uint64_t nwork, cudaStream_t st, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, false, sched); }
-int launch_grid4(const gsdf_program *p, const GenGrid<4> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, pdl, sched); }
-int launch_centers(const gsdf_program *p, const GenCenters &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched) { return launch_eval<1>(p, g, nwork, st, pdl, sched); }
+int launch_grid4(const gsdf_program *p, const GenGrid<4> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
+    return launch_eval<4>(p, g, nwork, st, pdl, sched, stamp);
+}
+int launch_centers(const gsdf_program *p, const GenCenters &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
+    return launch_eval<1>(p, g, nwork, st, pdl, sched, stamp);
+}
 int launch_image(const gsdf_program *p, const GenImage &g, uint64_t nwork, cudaStream_t st, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, false, sched); }
 int launch_dc(const gsdf_program *p, const GenDC &g, uint64_t nwork, cudaStream_t st, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, false, sched); }
 int launch_stream3(const gsdf_program *p, const float *d_pos, float *d_dist, uint64_t n, cudaStream_t st) { return launch_stream<3>(p, d_pos, d_dist, n, st); }

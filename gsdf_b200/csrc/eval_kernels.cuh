@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval(ProgView pv, Gen gen) {
 
     Machine<P> m;
     pdl_wait();
+    stage_stamp(pv.stamp);
     const uint64_t nwork = gen.work_items();
     for (;;) {
         if (threadIdx.x == 0) *s_tile = atomicAdd(pv.sched, 1u);

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/gsdf_program.h"
 #include "colormap.cuh"
 
 namespace gsdfk {
@@ -29,6 +30,7 @@ struct ProgView {
     uint32_t stage_aux;      // 1: aux is staged to smem with the program; 0: read from global
     uint32_t dslots, pslots; // stack slots
     uint32_t *sched;         // [0] next tile, [1] finished CTAs (self-resetting work counter)
+    unsigned long long *stamp;  // optional: receives %globaltimer when the kernel's first CTA starts its work (stage timing inside graphs)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -41,6 +43,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 // transitive along the chain. Launched without the programmatic-serialization attribute both are no-ops.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Stage stamps: every kernel of a render stores %globaltimer (ns) when its first CTA passes pdl_wait(), i.e. when its
+// predecessor has completed; differences of consecutive stamps are the stage times INSIDE a CUDA-graph replay, where
+// events cannot be recorded between the kernels without breaking the programmatic edges.
+__device__ __forceinline__ void stage_stamp(unsigned long long *slot) {
+    if (slot && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        *slot = t;
+    }
+}
 
 // Stage `bytes` (multiple of 16) from global to shared with one bulk async copy; all threads return after it landed.
 __device__ __forceinline__ void bulk_stage(void *s_dst, const void *g_src, uint32_t bytes, uint64_t *s_bar) {
@@ -70,7 +82,7 @@ __device__ __forceinline__ void bulk_stage(void *s_dst, const void *g_src, uint3
 
 // Shared memory: [prog (+aux)] [mbarrier + tile slot, 16 bytes] [dstack] [pstack]
 __host__ __device__ inline uint32_t smem_stage_bytes(const ProgView &pv) { return pv.prog_bytes + (pv.stage_aux ? pv.aux_bytes : 0u); }
-// Radius cache of the experimental -DGSDF_RXY build (gsdf_program.h, "Radius reuse"): one float per point behind the stacks.
+// Radius cache (gsdf_program.h, "Radius reuse"; absent from -DGSDF_NO_RXY builds): one float per point behind the stacks.
 #ifdef GSDF_RXY
 constexpr uint32_t kRxySlots = 1u;
 #else

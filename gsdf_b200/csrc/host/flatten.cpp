@@ -439,7 +439,7 @@ struct Emitter {
     }
 };
 
-// Radius reuse (include/gsdf_program.h, "Radius reuse"; experimental, GSDF_RXY=1): a post-pass over the finished
+// Radius reuse (include/gsdf_program.h, "Radius reuse"; GSDF_RXY=0 disables): a post-pass over the finished
 // straight-line stream. `ver` names the current (x, y) of the machine symbolically: ops that can change x or y give it a
 // fresh name, the position stack restores earlier names, and a one-slot cache remembers for which name the radius
 // Hypot(x, y) was stored. Stores happen only outside every region a guard can skip, so the simulation is exact.
@@ -506,9 +506,9 @@ bool Flatten(const Builder &b, NodeId root, Program &out, std::string &err) {
     if (!e.emit(root, false, out.dim == 2)) { err = e.err; return false; }
     e.header(GSDF_OP_END, 1);
     if (e.d != 1) { err = "internal: distance stack imbalance"; return false; }
-    {   // experimental: only programs for a -DGSDF_RXY build of the library (a default build rejects the flags)
+    {   // radius reuse (gsdf_program.h): on by default, GSDF_RXY=0 switches the post-pass off (A/B, -DGSDF_NO_RXY libraries)
         const char *rx = std::getenv("GSDF_RXY");
-        if (rx && *rx && *rx != '0') planRadiusReuse(out);
+        if (!(rx && *rx == '0')) planRadiusReuse(out);
     }
     out.dstack = e.dmax > 1 ? e.dmax - 1 : 1;  // top is cached in a register; slot 0 also absorbs the first push
     out.pstack = e.pmax;

@@ -143,8 +143,10 @@ int program_quiesce(gsdf_program *p);
 // nwork_upper_bound sizes the persistent grid (at most one resident wave). Returns 0 or a gsdf_status.
 int launch_points3(const gsdf_program *p, const gsdfk::GenPoints3 &g, uint64_t nwork, cudaStream_t st, uint32_t *sched);
 int launch_points2(const gsdf_program *p, const gsdfk::GenPoints2 &g, uint64_t nwork, cudaStream_t st, uint32_t *sched);
-int launch_grid4(const gsdf_program *p, const gsdfk::GenGrid<4> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched);
-int launch_centers(const gsdf_program *p, const gsdfk::GenCenters &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched);
+int launch_grid4(const gsdf_program *p, const gsdfk::GenGrid<4> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched,
+                 unsigned long long *stamp = nullptr);
+int launch_centers(const gsdf_program *p, const gsdfk::GenCenters &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched,
+                   unsigned long long *stamp = nullptr);
 int launch_image(const gsdf_program *p, const gsdfk::GenImage &g, uint64_t nwork, cudaStream_t st, uint32_t *sched);
 int launch_dc(const gsdf_program *p, const gsdfk::GenDC &g, uint64_t nwork, cudaStream_t st, uint32_t *sched);
 // streaming Evaluate: 0 launched, 1 not applicable (caller uses launch_points*), <0 error

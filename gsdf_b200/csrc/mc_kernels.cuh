@@ -31,11 +31,12 @@ __device__ __forceinline__ uint32_t bit_at(const uint32_t *row, int b) { return 
 // slab) and cx in [4m-1, 4m+3], i.e. blocks m-1 and m of up to four block rows. Survivors are appended
 // warp-aggregated: one ballot + one atomicAdd per 32 quads.
 __global__ void __launch_bounds__(kThreads) k_compact_quads(MeshDims D, const uint32_t *__restrict__ bits, uint32_t *__restrict__ list,
-                                                           uint32_t *__restrict__ count) {
+                                                           uint32_t *__restrict__ count, unsigned long long *stamp) {
     __shared__ uint32_t s_cnt[kThreads / 32];
     __shared__ uint32_t s_base;
     pdl_trigger();
     pdl_wait();
+    stage_stamp(stamp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nrows = (uint32_t)(D.ny + 1) * (uint32_t)(D.cz1 - D.cz0 + 1);
     const uint32_t rpg = gridDim.x * (blockDim.x >> 5);
@@ -114,6 +115,7 @@ struct MCArgs {
     uint32_t *seg_count;
     uint8_t *seg_cases;     // optional: the 32 cube-case indices of seg_list[i] at [32*i, 32*i+32) (k_mc_count_tma -> k_mc_emit),
                             // so that pass 2 does not classify again
+    unsigned long long *stamp;  // optional stage stamp slot of the kernel this struct is passed to
 };
 
 
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(kThreads) k_mc_count(MCArgs A) {
     pdl_trigger();
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = A.t_ntri[i];
     pdl_wait();
+    stage_stamp(A.stamp);
     __syncthreads();
     const MeshDims &D = A.D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -247,6 +250,7 @@ __global__ void __launch_bounds__(256) k_mc_count_tma(const __grid_constant__ CU
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     pdl_wait();  // the lattice (k_eval) and the prune bit rows are the predecessor's
+    stage_stamp(A.stamp);
     __syncthreads();
     const MeshDims &D = A.D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -358,6 +362,7 @@ __global__ void __launch_bounds__(256, 8) k_mc_count_tma4(const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     pdl_wait();  // the lattice (k_eval) and the prune bit rows are the predecessor's
+    stage_stamp(A.stamp);
     __syncthreads();
     const MeshDims &D = A.D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -478,6 +483,7 @@ __global__ void __launch_bounds__(kThreads) k_mc_emit(MCArgs A) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = A.t_ntri[i];
     for (int i = threadIdx.x; i < 256 * 16 / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_tris)[i] = reinterpret_cast<const uint4 *>(A.t_tris)[i];
     pdl_wait();
+    stage_stamp(A.stamp);
     __syncthreads();
     const MeshDims &D = A.D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -563,10 +569,16 @@ __global__ void __launch_bounds__(kThreads) k_mc_emit(MCArgs A) {
 // queue behind a device->host triangle read in flight (the 11 MB read of the previous Z-slab stalled the host's "how many
 // triangles?" wait by 200 us, scripts/exp_pipe.py); a store from an SM does not.
 __global__ void __launch_bounds__(256) k_finish_render(uint32_t *__restrict__ d_ctr, volatile uint32_t *h_ctr, int nctr,
-                                                      unsigned long long *__restrict__ scanstate, uint32_t nstate) {
+                                                      unsigned long long *__restrict__ scanstate, uint32_t nstate,
+                                                      unsigned long long *__restrict__ d_stamp, volatile unsigned long long *h_stamp, int nstamp) {
     pdl_wait();
+    if (d_stamp) stage_stamp(d_stamp + nstamp - 1);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (uint32_t)nctr) { h_ctr[i] = d_ctr[i]; d_ctr[i] = 0u; }
+    if (d_stamp && blockIdx.x == 0) {
+        __syncthreads();
+        if (threadIdx.x < (uint32_t)nstamp) h_stamp[threadIdx.x] = d_stamp[threadIdx.x];
+    }
     for (uint32_t k = i; k < nstate; k += gridDim.x * blockDim.x) scanstate[k] = 0ull;
     __threadfence_system();
 }
@@ -649,11 +661,13 @@ __global__ void __launch_bounds__(kThreads) k_scan_apply(uint32_t *__restrict__ 
 //   state = epoch << 34 | flag << 32 | value,  flag 1 = aggregate, 2 = inclusive prefix.
 constexpr int kScanTile = kThreads * 8;
 __global__ void __launch_bounds__(kThreads) k_scan_lookback(uint32_t *__restrict__ data, uint32_t n, unsigned long long *__restrict__ state,
-                                                           uint32_t *__restrict__ ticket, uint32_t epoch, unsigned long long *__restrict__ total) {
+                                                           uint32_t *__restrict__ ticket, uint32_t epoch, unsigned long long *__restrict__ total,
+                                                           unsigned long long *stamp) {
     __shared__ uint32_t s_w[kThreads / 32];
     __shared__ uint32_t s_tile, s_prefix;
     pdl_trigger();
     pdl_wait();
+    stage_stamp(stamp);
     const uint32_t ntiles = (n + kScanTile - 1) / kScanTile;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();

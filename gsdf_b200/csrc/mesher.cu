@@ -14,6 +14,7 @@
 using namespace gsdfk;
 using namespace gsdfi;
 
+constexpr int kMeshStamps = 8;
 constexpr int kMeshCtr = 24;  // words of a mesher's counter block (see gsdf_mesher::d_ctr)
 #define GSDF_MESH_PLAN_GIVEN 0u
 
@@ -44,6 +45,10 @@ struct gsdf_mesher {
     // interpreter launches (one pair per prune level + one for the lattice evaluation: never shared with another launch)
     uint32_t *d_ctr = nullptr;
     uint32_t *h_ctr = nullptr;  // pinned mirror
+    // stage stamps (%globaltimer, ns): [0] prune centres, [1] quad compaction, [2] lattice evaluation, [3] classification,
+    // [4] scan, [5] emit, [6] finish -- written by the kernels themselves, so they exist inside CUDA-graph replays too
+    unsigned long long *d_stamp = nullptr;
+    unsigned long long *h_stamp = nullptr;
     CUtensorMap tmap;             // 3-D view of d_grid for the TMA-staged classification
     const float *tmap_grid = nullptr;
     bool use_tma = true;
@@ -157,6 +162,7 @@ int mesh_run_begin(gsdf_mesher *m) {
     A.seg_list = m->d_seglist;
     A.seg_count = m->d_ctr + 5;
     A.seg_cases = (m->use_tma && pre_classified) ? m->d_segcases : nullptr;
+    A.stamp = nullptr;
     const unsigned mcgrid = grid_for(p->sms, nrows * (uint64_t)((D.nsx + 3) / 4), kThreads / 32, 16);
     if (m->use_tma && m->tmap_grid != m->d_grid) {  // (re)describe the lattice buffer: pitch x (ny+1) x nk floats
         if ((rc = make_grid_tensor_map(&m->tmap, m->d_grid, D.pitch, D.ny + 1, nk))) return rc;
@@ -182,17 +188,18 @@ int mesh_run_begin(gsdf_mesher *m) {
             if (li) { gc.P = m->lev[li - 1]; gc.shift = m->plan.level[li - 1] - m->plan.level[li]; }
             gc.kept = li == m->plan.nlevels - 1 ? m->d_ctr + 4 : nullptr;
             gc.evals = m->d_ctr + 7;
-            if ((rc = launch_centers(p, gc, (uint64_t)gc.L.nwx * 32u * gc.L.ncy * gc.L.ncz, st, pdl && li > 0, m->d_ctr + 8 + 2 * li))) return rc;
+            if ((rc = launch_centers(p, gc, (uint64_t)gc.L.nwx * 32u * gc.L.ncy * gc.L.ncz, st, pdl && li > 0, m->d_ctr + 8 + 2 * li,
+                                     li == 0 ? m->d_stamp + 0 : nullptr))) return rc;
         }
         const uint64_t ncrows = (uint64_t)(D.ny + 1) * nk;
-        CU(launch_chain(pdl, k_compact_quads, dim3(grid_for(p->sms, ncrows, kThreads / 32)), dim3(kThreads), 0, st, D, (const uint32_t *)m->d_mbits, m->d_list, m->d_ctr + 0));
+        CU(launch_chain(pdl, k_compact_quads, dim3(grid_for(p->sms, ncrows, kThreads / 32)), dim3(kThreads), 0, st, D, (const uint32_t *)m->d_mbits, m->d_list, m->d_ctr + 0, m->d_stamp + 1));
         CU(cudaGetLastError());
     }
     if (stage_events) CU(cudaEventRecord(m->ev[1], st));
     {
         GenGrid<4> g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
         // with a device-side list length the launch is sized for the worst case; surplus CTAs find no tile and exit
-        if ((rc = launch_grid4(p, g, nquads, st, pdl && prune, m->d_ctr + 8 + 2 * GSDF_PRUNE_MAX_LEVELS))) return rc;
+        if ((rc = launch_grid4(p, g, nquads, st, pdl && prune, m->d_ctr + 8 + 2 * GSDF_PRUNE_MAX_LEVELS, m->d_stamp + 2))) return rc;
     }
     if (stage_events) CU(cudaEventRecord(m->ev[2], st));
     if (m->use_tma) {
@@ -202,9 +209,13 @@ int mesh_run_begin(gsdf_mesher *m) {
         static const unsigned count_grid_cap = getenv("GSDF_COUNT_GRID") ? (unsigned)std::max(1, atoi(getenv("GSDF_COUNT_GRID"))) : 0u;
         unsigned cgrid = grid_for(p->sms, ntiles, 1, 16);
         if (count_grid_cap) cgrid = std::min(cgrid, count_grid_cap);
-        CU(launch_chain(pdl, count_v1 ? k_mc_count_tma : k_mc_count_tma4, dim3(cgrid), dim3(256), 0, st, m->tmap, A));
+        MCArgs Cn = A;
+        Cn.stamp = m->d_stamp + 3;
+        CU(launch_chain(pdl, count_v1 ? k_mc_count_tma : k_mc_count_tma4, dim3(cgrid), dim3(256), 0, st, m->tmap, Cn));
     } else {
-        CU(launch_chain(pdl, k_mc_count, dim3(mcgrid), dim3(kThreads), 0, st, A));
+        MCArgs Cn = A;
+        Cn.stamp = m->d_stamp + 3;
+        CU(launch_chain(pdl, k_mc_count, dim3(mcgrid), dim3(kThreads), 0, st, Cn));
     }
     CU(cudaGetLastError());
     if (scan3) {
@@ -216,20 +227,21 @@ int mesh_run_begin(gsdf_mesher *m) {
         CU(cudaGetLastError());
     } else {
         CU(launch_chain(pdl, k_scan_lookback, dim3((unsigned)nscantiles), dim3(kThreads), 0, st, m->d_seg, (uint32_t)nseg, m->d_scanstate, m->d_ctr + 6, epoch,
-                        reinterpret_cast<unsigned long long *>(m->d_ctr + 2)));
+                        reinterpret_cast<unsigned long long *>(m->d_ctr + 2), m->d_stamp + 4));
         CU(cudaGetLastError());
     }
     if (stage_events) CU(cudaEventRecord(m->ev[3], st));
     if (emitted) {
         MCArgs E = A;
         E.cases = nullptr;
+        E.stamp = m->d_stamp + 5;
         CU(launch_chain(pdl, k_mc_emit, dim3(mcgrid), dim3(kThreads), 0, st, E));
         CU(cudaGetLastError());
     }
     {   // publish the counters (cudaMallocHost memory is device-mapped under UVA) and re-arm the state for the next render
         const uint32_t nstate = (uint32_t)nscantiles;
         CU(launch_chain(pdl, k_finish_render, dim3((unsigned)std::min<uint64_t>(std::max<uint64_t>((nstate + 255) / 256, 1), 64)), dim3(256), 0, st,
-                        m->d_ctr, (volatile uint32_t *)m->h_ctr, kMeshCtr, m->d_scanstate, nstate));
+                        m->d_ctr, (volatile uint32_t *)m->h_ctr, kMeshCtr, m->d_scanstate, nstate, m->d_stamp, (volatile unsigned long long *)m->h_stamp, kMeshStamps));
         CU(cudaGetLastError());
     }
     return rc;
@@ -322,8 +334,13 @@ int mesh_run_end(gsdf_mesher *m) {
         m->evals = (uint64_t)(D.nx + 1) * (D.ny + 1) * nk;
         m->pruned = 0;
     }
-    if (use_graph) { for (int i = 0; i < 4; i++) m->ms[i] = 0.f; }  // stage events are not recorded inside the graph
-    else { for (int i = 0; i < 4; i++) cudaEventElapsedTime(&m->ms[i], m->ev[i], m->ev[i + 1]); }
+    if (use_graph) {
+        // no events between the kernels of a graph replay: the stage times come from the kernels' own %globaltimer stamps
+        const unsigned long long *t = m->h_stamp;
+        const unsigned long long t0 = prune ? t[0] : t[2];
+        auto msd = [](unsigned long long a, unsigned long long b) { return b > a ? (float)((double)(b - a) * 1e-6) : 0.f; };
+        m->ms[0] = msd(t0, t[2]); m->ms[1] = msd(t[2], t[3]); m->ms[2] = msd(t[3], t[5]); m->ms[3] = msd(t[5], t[6]);
+    } else { for (int i = 0; i < 4; i++) cudaEventElapsedTime(&m->ms[i], m->ev[i], m->ev[i + 1]); }
     cudaEventElapsedTime(&m->ms[4], m->ev[0], m->ev[4]);
     m->runs++;
     p->evals += m->evals;  // the reference's renderers evaluate through sdf.Evaluate: its counter includes them (gleval/gpu.go:80)
@@ -411,6 +428,9 @@ int gsdf_mesh_begin_plan(gsdf_program *p, const gsdf_lattice *lat, int cz0, int 
     cudaError_t e = cudaMalloc((void **)&m->d_ctr, kMeshCtr * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(m->d_ctr, 0, kMeshCtr * sizeof(uint32_t));  // every render leaves them zeroed for the next (k_finish_render)
     if (e == cudaSuccess) e = cudaMallocHost((void **)&m->h_ctr, kMeshCtr * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_stamp, kMeshStamps * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(m->d_stamp, 0, kMeshStamps * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&m->h_stamp, kMeshStamps * sizeof(unsigned long long));
     for (int i = 0; i < 5 && e == cudaSuccess; i++) e = cudaEventCreate(&m->ev[i]);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
@@ -548,6 +568,8 @@ void gsdf_mesh_destroy(gsdf_mesher *m) {
     cudaFree(m->d_grid); cudaFree(m->d_list); cudaFree(m->d_seg); cudaFree(m->d_seglist); cudaFree(m->d_segcases); cudaFree(m->d_scanstate); cudaFree(m->d_blocksum);
     cudaFree(m->d_tris); cudaFree(m->d_cases); cudaFree(m->d_stl); cudaFree(m->d_ctr);
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
+    cudaFree(m->d_stamp);
+    if (m->h_stamp) cudaFreeHost(m->h_stamp);
     for (auto &e : m->ev) if (e) cudaEventDestroy(e);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -706,9 +728,40 @@ void slab_cuts(int nz, int nslabs, int32_t *cuts) {
     cuts[nslabs] = nz;
 }
 
+// New cuts that equalise the cost per slab, from the cost each current slab reported: the cost is spread evenly over the
+// slab's layers (piecewise-constant density) and cut g lands where the cumulative cost reaches g/nslabs of the total. Every
+// slab keeps at least one layer. Cuts are not block-aligned: a straddled prune block has its centre evaluated by both
+// neighbours, which is cheaper than the imbalance a 4-layer granularity leaves on thin lattices.
+void slab_rebalance(int nz, int nslabs, const int32_t *cuts, const double *cost, int32_t *out) {
+    double total = 0;
+    for (int j = 0; j < nslabs; j++) total += std::max(cost[j], 0.0);
+    out[0] = 0; out[nslabs] = nz;
+    if (!(total > 0) || nslabs < 2) { for (int g = 1; g < nslabs; g++) out[g] = cuts[g]; return; }
+    int j = 0;
+    double before = 0;  // cost of the slabs in front of slab j
+    for (int g = 1; g < nslabs; g++) {
+        const double target = total * g / nslabs;
+        while (j < nslabs - 1 && before + std::max(cost[j], 0.0) < target) { before += std::max(cost[j], 0.0); j++; }
+        const double w = std::max(cost[j], 0.0);
+        const double frac = w > 0 ? (target - before) / w : 0.0;
+        int c = cuts[j] + (int)std::lround(frac * (cuts[j + 1] - cuts[j]));
+        c = std::max(c, out[g - 1] + 1);
+        c = std::min(c, nz - (nslabs - g));
+        out[g] = c;
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int gsdf_slab_rebalance(int nz, int nslabs, const int32_t *cuts, const double *cost, int32_t *out) {
+    if (!cuts || !cost || !out || nslabs < 1 || nz < nslabs) return fail(GSDF_EINVAL, "gsdf_slab_rebalance: bad argument");
+    if (cuts[0] != 0 || cuts[nslabs] != nz) return fail(GSDF_EINVAL, "gsdf_slab_rebalance: cuts must run from 0 to nz");
+    for (int j = 0; j < nslabs; j++) if (cuts[j + 1] <= cuts[j]) return fail(GSDF_EINVAL, "gsdf_slab_rebalance: empty slab %d", j);
+    slab_rebalance(nz, nslabs, cuts, cost, out);
+    return 0;
+}
 
 int gsdf_slab_cuts(int nz, int nslabs, int32_t *cuts) {
     if (!cuts || nz <= 0 || nslabs <= 0) return fail(GSDF_EINVAL, "gsdf_slab_cuts: nz and nslabs must be positive");
@@ -836,6 +889,35 @@ int64_t gsdf_multi_read(gsdf_multimesher *mm, float *tri9, size_t max_tris) {
     return (int64_t)got;  // 0 = io.EOF
 }
 
+int gsdf_multi_rebalance(gsdf_multimesher *mm, int rounds) {
+    if (!mm) return fail(GSDF_EINVAL, "gsdf_multi_rebalance: NULL handle");
+    int changed = 0;
+    for (int r = 0; r < rounds; r++) {
+        std::vector<double> cost(mm->nslabs);
+        for (int j = 0; j < mm->nslabs; j++) cost[j] = (double)mm->slab[j]->evals;
+        std::vector<int32_t> cuts(mm->nslabs + 1);
+        slab_rebalance(mm->lat.n[2], mm->nslabs, mm->cuts.data(), cost.data(), cuts.data());
+        if (cuts == mm->cuts) break;
+        for (int j = 0; j < mm->nslabs; j++) {
+            if (cuts[j] == mm->cuts[j] && cuts[j + 1] == mm->cuts[j + 1]) continue;
+            gsdf_mesher *fresh = nullptr;
+            const int rc = gsdf_mesh_begin(mm->prog[j % mm->ndev], &mm->lat, cuts[j], cuts[j + 1], mm->flags, &fresh);
+            if (rc) return rc;  // the old partition stays valid up to slab j; the caller sees the error
+            gsdf_mesh_destroy(mm->slab[j]);
+            mm->slab[j] = fresh;
+        }
+        mm->cuts = cuts;
+        changed = 1;
+    }
+    mm->ntri = mm->evals = mm->pruned = 0;
+    for (int j = 0; j < mm->nslabs; j++) {
+        mm->offs[j] = mm->ntri;
+        mm->ntri += mm->slab[j]->ntri; mm->evals += mm->slab[j]->evals; mm->pruned += mm->slab[j]->pruned;
+    }
+    mm->read_pos = 0;
+    return changed;
+}
+
 int gsdf_multi_rewind(gsdf_multimesher *mm) {
     if (!mm) return fail(GSDF_EINVAL, "gsdf_multi_rewind: NULL handle");
     mm->read_pos = 0;
@@ -943,7 +1025,7 @@ int dc_scan(gsdf_dualcontour *d, uint32_t *data, uint32_t n, cudaStream_t st) {
     }
     CU(cudaMemsetAsync(d->d_ctr, 0, 4 * sizeof(uint32_t), st));
     if (n == 0) return 0;
-    k_scan_lookback<<<(unsigned)ntiles, kThreads, 0, st>>>(data, n, d->d_scanstate, d->d_ctr, d->scan_epoch, reinterpret_cast<unsigned long long *>(d->d_ctr + 2));
+    k_scan_lookback<<<(unsigned)ntiles, kThreads, 0, st>>>(data, n, d->d_scanstate, d->d_ctr, d->scan_epoch, reinterpret_cast<unsigned long long *>(d->d_ctr + 2), nullptr);
     CU(cudaGetLastError());
     return 0;
 }

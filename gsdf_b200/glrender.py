@@ -269,6 +269,10 @@ class MultiRenderer:
     def UpdateBlob(self, blob, aux):
         check(lib.gsdf_multi_update(self._h, blob, len(blob), aux.ctypes.data_as(C.POINTER(C.c_float)), aux.size))
 
+    def Rebalance(self, rounds=2):
+        """Re-cut the Z-slabs by the evaluations each executed in its last render (gsdf_multi_rebalance)."""
+        return int(check(lib.gsdf_multi_rebalance(self._h, int(rounds))))
+
     def Render(self):
         """Render without read-back (device timing)."""
         return int(check(lib.gsdf_multi_render(self._h, None, 0)))

@@ -22,6 +22,19 @@ def slab_cuts(nz, world, align=4):
     return [int(c) for c in cuts]
 
 
+def rebalance_cuts(cuts, costs):
+    """gsdf_slab_rebalance: new cuts that equalise the per-slab cost (evaluations executed, or milliseconds) each slab of
+    `cuts` reported. Equal layers are not equal work on a pruned lattice."""
+    import ctypes as C
+    from ._lib import lib, check
+    n = len(cuts) - 1
+    cin = (C.c_int32 * (n + 1))(*[int(c) for c in cuts])
+    cost = (C.c_double * n)(*[float(c) for c in costs])
+    out = (C.c_int32 * (n + 1))()
+    check(lib.gsdf_slab_rebalance(int(cuts[-1]), n, cin, cost, out))
+    return [int(c) for c in out]
+
+
 def rank_slab(nz, rank, world, align=4):
     cuts = slab_cuts(nz, world, align)
     return cuts[rank], cuts[rank + 1]

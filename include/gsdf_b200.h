@@ -220,6 +220,14 @@ int64_t gsdf_multi_stl(gsdf_multimesher *mm, void *dst, size_t dst_bytes);
 void gsdf_multi_destroy(gsdf_multimesher *mm);
 /* The Z-slab cuts gsdf_multi_begin uses (host arithmetic): nslabs+1 ascending cell layers from 0 to nz. */
 int gsdf_slab_cuts(int nz, int nslabs, int32_t *cuts);
+/* Cuts that equalise a per-slab cost (host arithmetic): cost[j] is what slab j = [cuts[j], cuts[j+1]) cost in the last render
+ * (evaluations executed, or milliseconds); it is spread evenly over the slab's layers and out[] is cut where the cumulative
+ * cost reaches j/nslabs of the total. Pruned lattices put most of their work where the surface is, not where the volume is
+ * (SURVEY 8e): equal layers are not equal work. */
+int gsdf_slab_rebalance(int nz, int nslabs, const int32_t *cuts, const double *cost, int32_t *out);
+/* Up to `rounds` rounds of gsdf_slab_rebalance on the evaluations each slab executed in its last render; slabs whose range
+ * changes are rebuilt (and rendered once). Returns 1 if the partition changed, 0 if it was already balanced, <0 on error. */
+int gsdf_multi_rebalance(gsdf_multimesher *mm, int rounds);
 
 /* Dual contouring --------------------------------------------------------------------------------------------- */
 /* glrender.DualContourRenderer (glrender/dual_contour.go:12-218) with its vertex placement strategies

@@ -53,10 +53,9 @@ def test_device_interpreter_source_guards(oracle, bld, monkeypatch):
     check(oracle, bld, "flange/no guards", flange, dense)
 
 
-def test_experimental_radius_reuse_device_code(oracle, bld, monkeypatch):
-    """The -DGSDF_RXY side of interp.cuh (Machine::radius and the four consumers), which is not part of the default
-    build and has not run on a GPU: with GSDF_RXY=1 programs it must still equal the oracle bit for bit."""
-    monkeypatch.setenv("GSDF_RXY", "1")
+def test_radius_reuse_device_code_and_the_build_without_it(oracle, bld, monkeypatch):
+    """Radius reuse (Machine::radius and its four consumers) is part of the default build: flagged programs equal the oracle
+    bit for bit; so do unflagged programs (GSDF_RXY=0) on a -DGSDF_NO_RXY build of the same source."""
     flagged = 0
     for name, s in shapes.all3d(bld) + shapes.all2d(bld) + shapes.dag3d(bld) + shapes.random_trees(bld, 5, 60, 3, depth=5, rich=True):
         words = np.frombuffer(bld.flatten(s)["blob"], np.uint32, offset=32).reshape(-1, 4)
@@ -71,8 +70,11 @@ def test_experimental_radius_reuse_device_code(oracle, bld, monkeypatch):
                 break
             pc += ln
         flagged += hit
-        check(oracle, bld, name, s, variant="GSDF_RXY")
+        check(oracle, bld, name, s)
     assert flagged >= 5
+    monkeypatch.setenv("GSDF_RXY", "0")
+    for name, s in shapes.threads3d(bld) + shapes.scenes3d(bld):
+        check(oracle, bld, name, s, variant="GSDF_NO_RXY")
 
 
 def test_math32_source_matches_oracle(oracle):

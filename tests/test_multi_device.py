@@ -30,6 +30,22 @@ def test_slab_cuts_cover_every_layer_once():
                 assert all(b > a for a, b in zip(cuts[:-1], cuts[1:])), (nz, n, cuts)
 
 
+def test_rebalanced_cuts_equalise_the_cost():
+    """gsdf_slab_rebalance: cuts move towards the expensive slabs, every slab keeps a layer, totals are preserved."""
+    cuts = slab.slab_cuts(84, 8)
+    cost = [100, 10, 10, 10, 10, 10, 10, 50]
+    new = slab.rebalance_cuts(cuts, cost)
+    assert new[0] == 0 and new[-1] == 84 and all(b > a for a, b in zip(new[:-1], new[1:]))
+    dens = np.repeat(np.array(cost, float) / np.diff(cuts), np.diff(cuts))      # cost per layer under the old cuts
+    per = [dens[a:b].sum() for a, b in zip(new[:-1], new[1:])]
+    assert max(per) < 0.5 * max(cost) and max(per) / (sum(cost) / 8) < 1.6   # far better than 100 vs a mean of 26
+    assert slab.rebalance_cuts([0, 42, 84], [1, 3]) == [0, 56, 84]
+    assert slab.rebalance_cuts([0, 1, 2, 3], [0, 0, 5]) == [0, 1, 2, 3]           # nobody loses its last layer
+    assert slab.rebalance_cuts(cuts, [0] * 8) == cuts                             # no information: unchanged
+    with pytest.raises(gsdf_b200.GsdfError):
+        slab.rebalance_cuts([0, 5, 5, 9], [1, 1, 1])
+
+
 def test_default_prune_plan_arithmetic():
     lat = _lib.Lattice()
     plan = _lib.PrunePlan()
@@ -96,6 +112,13 @@ def test_multi_renderer_equals_single_renderer(bld, scene, resdiv):
         with pytest.raises(gsdf_b200.GsdfError) as e:
             M.RenderToHost(small)
         assert e.value.code == _lib.ESHORT
+        if spd > 1 or len(devs) > 1:       # re-cut by executed evaluations: another partition, the same triangles
+            before = M.Slabs()[0]
+            M.Rebalance(2)
+            after = M.Slabs()[0]
+            assert after[0] == 0 and after[-1] == before[-1] and len(after) == len(before)
+            pinned[:] = 0
+            assert M.RenderToHost(pinned) == len(want) and np.array_equal(bits(pinned[:len(want)]), bits(want)), (devs, spd, after)
         M.Close()
 
 
