@@ -184,14 +184,21 @@ def run_cuda(args, rank, local_rank, world):
     gsdf_b200.set_device(local_rank)
     numa = bind_to_gpu_numa(local_rank) if world > 1 and args.numa else None
     dist = None
+    cpu_group = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")   # host-side waits: an NCCL barrier would spin on the idle ranks' GPUs
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier(group=cpu_group)
 
     def allreduce(x, op):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
@@ -275,15 +282,15 @@ def run_cuda(args, rank, local_rank, world):
     d2h = ntri * 36
     e2e = None
     e2e_launches = 0
-    barrier()
+    host_barrier()   # ranks > 0 now sleep in a socket wait: their GPUs are idle while rank 0 drives all of them
     if rank == 0:
         host = glrender.pinned_empty((ntri + 8, 3, 3))
         ref_tris = None
         table = {}
-        for spd in ((1, 3, 5) if world == 1 else (1, 2)):
+        for spd in ((1, 3, 4) if world == 1 else (1, 2)):
             M = glrender.MultiRenderer(s, res, devices=list(range(world)), slabs_per_device=spd)
             assert M.NumTriangles() == ntri
-            if world > 1 and not args.no_rebalance:
+            if spd * world > 1 and not args.no_rebalance:
                 M.Rebalance(2)
 
             def step():
@@ -314,7 +321,7 @@ def run_cuda(args, rank, local_rank, world):
                "path": "per step: gsdf_multi_update (flattened tree to every device) -> gsdf_multi_render into ONE pinned host buffer: every slab on its own "
                        "stream, counts read from the device (no prediction), slab i's read-back under the kernels of the later slabs; "
                        "slabs_per_device_1 at N=1 is the fully synchronous single-renderer round trip"}
-    barrier()
+    host_barrier()
 
     # ---------------- gleval.SDF3.Evaluate on host slices (the contract north_star names first), rank 0, N = 1 only
     evaluate = None

@@ -108,6 +108,7 @@ def _load(host_only=False):
         "gsdf_multi_render": (C.c_int64, [vp, vp, C.c_size_t]),
         "gsdf_multi_read": (C.c_int64, [vp, vp, C.c_size_t]),
         "gsdf_multi_rewind": (C.c_int, [vp]),
+        "gsdf_multi_timeline": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int]),
         "gsdf_multi_stats": (C.c_int, [vp, u64p, u64p, u64p, f32p]),
         "gsdf_multi_slabs": (C.c_int, [vp, i32p, i32p, C.c_int]),
         "gsdf_multi_stl": (C.c_int64, [vp, vp, C.c_size_t]),

@@ -355,6 +355,8 @@ void gsdf_program_destroy(gsdf_program *p) {
         cudaFree(s.d_dist);
     }
     for (auto &e : p->user_ev) if (e) cudaEventDestroy(e);
+    if (p->upload_ev) cudaEventDestroy(p->upload_ev);
+    if (p->h_blob) cudaFreeHost(p->h_blob);
     if (p->stream) cudaStreamDestroy(p->stream);
     cudaFree(p->d_blob);
     cudaFree(p->d_sched);
@@ -657,6 +659,44 @@ int gsdf_colorconv_linear_gradient(float gradient_length, uint32_t rgba0, uint32
 }  // extern "C"
 
 namespace gsdfi {
+int program_update_async(gsdf_program *p, const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats) {
+    gsdf_program_header h;
+    const uint32_t *chunks = nullptr;
+    int rc = parse_blob(blob, blob_bytes, aux, aux_floats, h, chunks);
+    if (rc) return rc;
+    if ((int)h.dim != p->dim) return fail(GSDF_EINVAL, "cannot change a %dD program into a %dD one", p->dim, (int)h.dim);
+    const size_t prog_bytes = (size_t)h.nchunks * 16, aux_bytes = aux_floats * 4;
+    bool ext = false;
+    for (uint32_t pc = 0; pc < h.nchunks;) {
+        const uint32_t op = chunks[4 * pc] & 0xff, len = (chunks[4 * pc] >> 8) & 0xff;
+        if (op == GSDF_OP_ELLIPSE2D || op == GSDF_OP_BEZIERQ2D) ext = true;
+        pc += len ? len : 1;
+    }
+    const bool same_layout = p->d_blob && prog_bytes == p->pv.prog_bytes && aux_bytes == p->pv.aux_bytes && h.dstack == p->pv.dslots &&
+                             h.pstack == p->pv.pslots && ext == p->needs_ext;
+    if (!same_layout) return gsdf_program_update(p, blob, blob_bytes, aux, aux_floats);
+    CU(use_device(p->device));
+    if (p->h_blob_cap < prog_bytes + aux_bytes) {
+        if (p->h_blob) cudaFreeHost(p->h_blob);
+        p->h_blob = nullptr; p->h_blob_cap = 0;
+        CU(cudaHostAlloc((void **)&p->h_blob, 2 * (prog_bytes + aux_bytes) + 64, cudaHostAllocDefault));
+        p->h_blob_cap = 2 * (prog_bytes + aux_bytes) + 64;
+    }
+    if (!p->upload_ev) CU(cudaEventCreateWithFlags(&p->upload_ev, cudaEventDisableTiming));
+    if (p->upload_ev_recorded) CU(cudaEventSynchronize(p->upload_ev));  // the staging buffer is free again (normally long done)
+    std::memcpy(p->h_blob, chunks, prog_bytes);
+    if (aux_bytes) std::memcpy(p->h_blob + prog_bytes, aux, aux_bytes);
+    {   // device-side: nothing that still reads the old program may be overtaken
+        std::lock_guard<std::mutex> lk(p->dep_mu);
+        for (const auto &d : p->deps) CU(cudaStreamWaitEvent(p->stream, d.ev, 0));
+    }
+    CU(cudaMemcpyAsync(p->d_blob, p->h_blob, prog_bytes + aux_bytes, cudaMemcpyHostToDevice, p->stream));
+    CU(cudaEventRecord(p->upload_ev, p->stream));
+    p->upload_ev_recorded = true;
+    p->ninstr = h.ninstr;
+    return 0;
+}
+
 // full validation of a flattened program without touching a device (gsdf_multi_update keeps the blob for its workers)
 int check_program_blob(const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats, int dim) {
     gsdf_program_header h;

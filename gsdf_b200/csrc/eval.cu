@@ -114,6 +114,19 @@ int launch_points2(const gsdf_program *p, const GenPoints2 &g, uint64_t nwork, c
 int launch_grid4(const gsdf_program *p, const GenGrid<4> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
     return launch_eval<4>(p, g, nwork, st, pdl, sched, stamp);
 }
+int launch_grid1(const gsdf_program *p, const GenGrid<1> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
+    return launch_eval<1>(p, g, nwork, st, pdl, sched, stamp);
+}
+int eval_cta_slots(const gsdf_program *p, int *slots) {
+    static KernelDevCache cache;  // occupancy of the P = 4 lattice kernel (the P = 1 form is never lower)
+    int occ = 0;
+    const uint32_t smem = smem_total_bytes<4>(p->pv, kEvalThreads);
+    const int rc = p->needs_ext ? kernel_occupancy(cache, k_eval<4, GenGrid<4>, true>, p->device, smem, kEvalThreads, &occ)
+                                : kernel_occupancy(cache, k_eval<4, GenGrid<4>, false>, p->device, smem, kEvalThreads, &occ);
+    if (rc) return rc;
+    *slots = p->sms * std::max(occ, 1);
+    return 0;
+}
 int launch_centers(const gsdf_program *p, const GenCenters &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
     return launch_eval<1>(p, g, nwork, st, pdl, sched, stamp);
 }

@@ -122,6 +122,11 @@ struct gsdf_program {
     std::mutex dep_mu;
     struct Dependent { cudaEvent_t ev; gsdf_program **ref; };  // ref: the dependent's pointer to this program, nulled if the program goes first
     std::vector<Dependent> deps;
+    // asynchronous upload (program_update_async): pinned staging of the blob and the event the readers' streams wait for
+    uint8_t *h_blob = nullptr;
+    size_t h_blob_cap = 0;
+    cudaEvent_t upload_ev = nullptr;
+    bool upload_ev_recorded = false;
     // pinned staging of the pipelined host Evaluate (capi.cu)
     struct EvalSlot {
         float *h_pos = nullptr, *h_dist = nullptr, *d_pos = nullptr, *d_dist = nullptr;
@@ -135,6 +140,10 @@ namespace gsdfi {
 
 void program_add_dependent(gsdf_program *p, cudaEvent_t ev, gsdf_program **ref);
 void program_remove_dependent(gsdf_program *p, cudaEvent_t ev);
+// gsdf_program_update without a host synchronisation when the new program has the layout of the old one (same sizes, stack
+// slots and interpreter): the bytes go through the handle's pinned staging onto its stream behind a device-side wait for
+// every registered reader, and upload_ev is recorded for the next launches to wait on. Anything else: the synchronous path.
+int program_update_async(gsdf_program *p, const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats);
 int check_program_blob(const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats, int dim);
 // Waits until nothing on any stream can still be reading the program's device buffers.
 int program_quiesce(gsdf_program *p);
@@ -145,6 +154,12 @@ int launch_points3(const gsdf_program *p, const gsdfk::GenPoints3 &g, uint64_t n
 int launch_points2(const gsdf_program *p, const gsdfk::GenPoints2 &g, uint64_t nwork, cudaStream_t st, uint32_t *sched);
 int launch_grid4(const gsdf_program *p, const gsdfk::GenGrid<4> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched,
                  unsigned long long *stamp = nullptr);
+// the same lattice evaluation with ONE corner per thread (4 work items per quad): for listed work that fills less than about
+// one resident wave, where the render is bound by the latency of a tile, not by throughput. nwork counts quads x 4.
+int launch_grid1(const gsdf_program *p, const gsdfk::GenGrid<1> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched,
+                 unsigned long long *stamp = nullptr);
+// resident CTA slots of the lattice-evaluation kernel for this program (SMs x occupancy)
+int eval_cta_slots(const gsdf_program *p, int *slots);
 int launch_centers(const gsdf_program *p, const gsdfk::GenCenters &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched,
                    unsigned long long *stamp = nullptr);
 int launch_image(const gsdf_program *p, const gsdfk::GenImage &g, uint64_t nwork, cudaStream_t st, uint32_t *sched);

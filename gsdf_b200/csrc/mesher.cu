@@ -1,5 +1,6 @@
 // mesher.cu -- the mesh stage of the C ABI: gsdf_mesher (one Z-slab of a lattice on one device), gsdf_multimesher (one
 // lattice over several slabs and devices from one process), dual contouring and STL packing.
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdlib>
@@ -46,13 +47,14 @@ struct gsdf_mesher {
     uint32_t *d_ctr = nullptr;
     uint32_t *h_ctr = nullptr;  // pinned mirror
     // stage stamps (%globaltimer, ns): [0] prune centres, [1] quad compaction, [2] lattice evaluation, [3] classification,
-    // [4] scan, [5] emit, [6] finish -- written by the kernels themselves, so they exist inside CUDA-graph replays too
+    // [4] scan, [5] emit, [7] finish -- written by the kernels themselves, so they exist inside CUDA-graph replays too
     unsigned long long *d_stamp = nullptr;
     unsigned long long *h_stamp = nullptr;
     CUtensorMap tmap;             // 3-D view of d_grid for the TMA-staged classification
     const float *tmap_grid = nullptr;
     bool use_tma = true;
     uint64_t ntri = 0, evals = 0, pruned = 0, read_pos = 0;
+    uint32_t quad_hint = 0;       // listed quads of the previous render, rounded up to 4096
     cudaEvent_t ev[5] = {};
     cudaStream_t stream = nullptr;       // the render's stream: every mesher has its own, so slabs of one lattice overlap
     cudaStream_t copy_stream = nullptr;
@@ -104,6 +106,7 @@ int mesh_run_begin(gsdf_mesher *m) {
     CU(use_device(p->device));
     cudaStream_t st = m->stream;
     if (m->copy_stream) CU(cudaStreamSynchronize(m->copy_stream));  // an earlier async read may still use d_tris
+    if (p->upload_ev_recorded) CU(cudaStreamWaitEvent(st, p->upload_ev, 0));  // an asynchronous program upload (program_update_async) lands first
     const MeshDims &D = m->D;
     const bool prune = (m->flags & GSDF_MESH_PRUNE) != 0;
     const int nk = D.cz1 - D.cz0 + 1;
@@ -169,6 +172,20 @@ int mesh_run_begin(gsdf_mesher *m) {
         m->tmap_grid = m->d_grid;
     }
     const bool emitted = m->tri_cap > 0;  // optimistic emit into the existing buffer (steady state: no mid-pipeline host sync)
+    // Points per thread of the lattice evaluation. Four (the throughput form) unless the PREVIOUS render of this handle listed
+    // so few quads that one-corner tiles still fit in about one resident wave: then the stage is bound by the latency of a
+    // tile (~30 us at four points per thread, a quarter of that at one), which is what thin Z-slabs -- strong scaling, the
+    // first slab of a pipelined read-back -- pay for. The persistent grid is sized from the upper bound either way, so a
+    // render that lists more than the hint predicted is still correct, only slower.
+    int eval_p = 4;
+    {
+        static const int force_p = getenv("GSDF_EVAL_P") ? atoi(getenv("GSDF_EVAL_P")) : 0;  // A/B switch: 1 or 4
+        int slots = 0;
+        if ((rc = eval_cta_slots(p, &slots))) return rc;
+        if (prune && m->runs > 0 && (uint64_t)m->quad_hint * 4 <= (uint64_t)slots * kEvalThreads * 3) eval_p = 1;  // <= 3 short rounds
+        if (force_p == 1 && prune && m->runs > 0) eval_p = 1;
+        if (force_p == 4) eval_p = 4;
+    }
     static const bool scan3 = getenv("GSDF_SCAN3") != nullptr;  // A/B: the three-kernel scan
 
     // The launch sequence of one render. stage_events: record the per-stage timing events (eager path only).
@@ -197,9 +214,16 @@ int mesh_run_begin(gsdf_mesher *m) {
     }
     if (stage_events) CU(cudaEventRecord(m->ev[1], st));
     {
-        GenGrid<4> g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
         // with a device-side list length the launch is sized for the worst case; surplus CTAs find no tile and exit
-        if ((rc = launch_grid4(p, g, nquads, st, pdl && prune, m->d_ctr + 8 + 2 * GSDF_PRUNE_MAX_LEVELS, m->d_stamp + 2))) return rc;
+        uint32_t *sched = m->d_ctr + 8 + 2 * GSDF_PRUNE_MAX_LEVELS;
+        if (eval_p == 1) {  // latency-bound amount of listed work: one corner per thread, four times as many (short) tiles
+            GenGrid<1> g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
+            if ((rc = launch_grid1(p, g, std::min<uint64_t>(nquads, 2 * (uint64_t)m->quad_hint + 1024) * 4, st, pdl && prune, sched, m->d_stamp + 2))) return rc;
+        } else {
+            GenGrid<4> g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
+            const uint64_t bound = (prune && m->runs > 0) ? std::min<uint64_t>(nquads, 2 * (uint64_t)m->quad_hint + 1024) : nquads;
+            if ((rc = launch_grid4(p, g, bound, st, pdl && prune, sched, m->d_stamp + 2))) return rc;
+        }
     }
     if (stage_events) CU(cudaEventRecord(m->ev[2], st));
     if (m->use_tma) {
@@ -257,7 +281,8 @@ int mesh_run_begin(gsdf_mesher *m) {
         size_t tri_cap;
         ProgView pv;
         unsigned flags;
-        int ext, tma;
+        int ext, tma, eval_p;
+        uint32_t quad_hint;
     } key;
     std::memset(&key, 0, sizeof key);
     const void *kp[10] = {m->d_grid, nullptr, m->d_mbits, m->d_list, m->d_seg, m->d_seglist, m->d_scanstate, m->d_tris, m->d_cases, m->d_segcases};
@@ -265,6 +290,7 @@ int mesh_run_begin(gsdf_mesher *m) {
     for (int li = 0; li < GSDF_PRUNE_MAX_LEVELS; li++) key.lbits[li] = m->d_lbits[li];
     key.plan = m->plan; key.prog = p;
     key.tri_cap = m->tri_cap; key.pv = p->pv; key.flags = m->flags; key.ext = p->needs_ext ? 1 : 0; key.tma = m->use_tma ? 1 : 0;
+    key.eval_p = eval_p; key.quad_hint = (prune && m->runs > 0) ? m->quad_hint : 0u;
     const bool use_graph = m->allow_graph && !(m->flags & GSDF_MESH_STAGE_TIMING) && emitted && m->runs > 0 && !scan3;
     if (use_graph) {
         if (!m->gexec || m->gkey.size() != sizeof key || std::memcmp(m->gkey.data(), &key, sizeof key) != 0) {
@@ -329,6 +355,8 @@ int mesh_run_end(gsdf_mesher *m) {
     m->read_pos = 0;
     if (prune) {
         m->evals = (uint64_t)m->h_ctr[7] + 4ull * m->h_ctr[0];  // prune-cube centres of every level + the listed lattice quads
+        // hint for the next render's launch shape; rounded up so that small changes of the tree do not re-capture the graph
+        m->quad_hint = (m->h_ctr[0] + 4095u) & ~4095u;
         m->pruned = (nblocks - m->h_ctr[4]) * 64ull;  // Cube.DecomposesTo(1) of a level-3 cube = 8^2
     } else {
         m->evals = (uint64_t)(D.nx + 1) * (D.ny + 1) * nk;
@@ -339,7 +367,7 @@ int mesh_run_end(gsdf_mesher *m) {
         const unsigned long long *t = m->h_stamp;
         const unsigned long long t0 = prune ? t[0] : t[2];
         auto msd = [](unsigned long long a, unsigned long long b) { return b > a ? (float)((double)(b - a) * 1e-6) : 0.f; };
-        m->ms[0] = msd(t0, t[2]); m->ms[1] = msd(t[2], t[3]); m->ms[2] = msd(t[3], t[5]); m->ms[3] = msd(t[5], t[6]);
+        m->ms[0] = msd(t0, t[2]); m->ms[1] = msd(t[2], t[3]); m->ms[2] = msd(t[3], t[5]); m->ms[3] = msd(t[5], t[kMeshStamps - 1]);
     } else { for (int i = 0; i < 4; i++) cudaEventElapsedTime(&m->ms[i], m->ev[i], m->ev[i + 1]); }
     cudaEventElapsedTime(&m->ms[4], m->ev[0], m->ev[4]);
     m->runs++;
@@ -375,8 +403,18 @@ int gsdf_mesh_begin(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, 
     return gsdf_mesh_begin_plan(p, lat, cz0, cz1, flags & ~(unsigned)GSDF_MESH_PLAN_GIVEN, nullptr, out);
 }
 
+static int mesh_begin_prio(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, unsigned flags, const gsdf_prune_plan *plan,
+                           int stream_priority, gsdf_mesher **out);
+
 int gsdf_mesh_begin_plan(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, unsigned flags, const gsdf_prune_plan *plan,
                          gsdf_mesher **out) {
+    return mesh_begin_prio(p, lat, cz0, cz1, flags, plan, 0, out);
+}
+
+// stream_priority: 0 = default; -k = k steps towards the device's highest stream priority (the multi-device mesher gives the
+// slabs whose triangles leave first the right of way, so that their read-back starts while the later slabs still compute)
+static int mesh_begin_prio(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, unsigned flags, const gsdf_prune_plan *plan,
+                           int stream_priority, gsdf_mesher **out) {
     if (!p || !lat || !out) return fail(GSDF_EINVAL, "gsdf_mesh_begin: NULL argument");
     if (p->dim != 3) return fail(GSDF_EINVAL, "program is not 3D");
     if (!(lat->res > 0) || lat->n[0] <= 0 || lat->n[1] <= 0 || lat->n[2] <= 0) return fail(GSDF_ERES, "resolution not fine enough for marching cubes");
@@ -432,7 +470,12 @@ int gsdf_mesh_begin_plan(gsdf_program *p, const gsdf_lattice *lat, int cz0, int 
     if (e == cudaSuccess) e = cudaMemset(m->d_stamp, 0, kMeshStamps * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&m->h_stamp, kMeshStamps * sizeof(unsigned long long));
     for (int i = 0; i < 5 && e == cudaSuccess; i++) e = cudaEventCreate(&m->ev[i]);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        int least = 0, greatest = 0;
+        e = cudaDeviceGetStreamPriorityRange(&least, &greatest);  // numerically lower = higher priority
+        const int prio = std::max(greatest, std::min(least, least + stream_priority));
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&m->stream, cudaStreamNonBlocking, prio);
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { gsdf_mesh_destroy(m); return fail(GSDF_ECUDA, "mesher setup: %s", cudaGetErrorString(e)); }
     program_add_dependent(p, m->ev[4], &m->prog);
@@ -623,27 +666,43 @@ struct gsdf_multimesher {
     uint64_t ntri = 0, evals = 0, pruned = 0, read_pos = 0;
     std::vector<uint64_t> offs;                // per slab triangle offset of the last render
     float device_ms = 0;
+    // host-clock timeline of the last render in microseconds from the call: [0] slabs enqueued (worker 0), then per slab
+    // {count seen, copy enqueued}, last = everything delivered
+    std::vector<double> timeline;
+    std::chrono::steady_clock::time_point t_call;
     bool rendered = false;
     bool delivered = false;                    // the last render's triangles are already in the caller's buffer
     explicit gsdf_multimesher(int n) : count(n) {}
 };
 
+static int mesh_begin_prio(gsdf_program *p, const gsdf_lattice *lat, int cz0, int cz1, unsigned flags, const gsdf_prune_plan *plan,
+                           int stream_priority, gsdf_mesher **out);
+
 namespace {
+
+// the k-th slab of a device leaves k-th: earlier slabs get the higher stream priority
+int multi_slab_priority(const gsdf_multimesher *mm, int j) {
+    const int nper = (mm->nslabs + mm->ndev - 1) / mm->ndev;
+    return -(nper - 1 - j / mm->ndev);
+}
 
 int multi_worker_render(gsdf_multimesher *mm, int w) {
     const int dev = mm->devs[w];
     CU(use_device(dev));
     int rc;
-    if (mm->up_dirty[w]) {
-        if ((rc = gsdf_program_update(mm->prog[w], mm->up_blob.data(), mm->up_blob.size(), mm->up_aux.data(), mm->up_aux.size()))) return rc;
+    if (mm->up_dirty[w]) {  // no host synchronisation: the slabs' streams wait for the upload on the device
+        if ((rc = program_update_async(mm->prog[w], mm->up_blob.data(), mm->up_blob.size(), mm->up_aux.data(), mm->up_aux.size()))) return rc;
         mm->up_dirty[w] = 0;
     }
+    auto now_us = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - mm->t_call).count(); };
     for (int j = w; j < mm->nslabs; j += mm->ndev)
         if ((rc = mesh_run_begin(mm->slab[j]))) return rc;
+    if (w == 0) mm->timeline[0] = now_us();
     for (int j = w; j < mm->nslabs; j += mm->ndev) {
         gsdf_mesher *m = mm->slab[j];
         if ((rc = mesh_run_end(m))) return rc;
         mm->count[j].store((int64_t)m->ntri, std::memory_order_release);
+        mm->timeline[1 + 2 * j] = now_us();
         if (!mm->dst) continue;
         uint64_t off = 0;
         for (int i = 0; i < j; i++) {
@@ -660,6 +719,7 @@ int multi_worker_render(gsdf_multimesher *mm, int w) {
         if (mm->dst_pinned) {
             CU(cudaStreamWaitEvent(m->copy_stream, m->ev[4], 0));
             CU(cudaMemcpyAsync(mm->dst + 9 * off, m->d_tris, m->ntri * 9 * sizeof(float), cudaMemcpyDeviceToHost, m->copy_stream));
+            mm->timeline[2 + 2 * j] = now_us();
         } else {  // pageable destination: DMA into this device's pinned staging, then one host copy
             const size_t need = (size_t)m->ntri * 9;
             if (mm->h_stage_cap[w] < need) {
@@ -732,15 +792,17 @@ void slab_cuts(int nz, int nslabs, int32_t *cuts) {
 // slab's layers (piecewise-constant density) and cut g lands where the cumulative cost reaches g/nslabs of the total. Every
 // slab keeps at least one layer. Cuts are not block-aligned: a straddled prune block has its centre evaluated by both
 // neighbours, which is cheaper than the imbalance a 4-layer granularity leaves on thin lattices.
-void slab_rebalance(int nz, int nslabs, const int32_t *cuts, const double *cost, int32_t *out) {
-    double total = 0;
-    for (int j = 0; j < nslabs; j++) total += std::max(cost[j], 0.0);
+void slab_rebalance(int nz, int nslabs, const int32_t *cuts, const double *cost, int32_t *out, const double *share = nullptr) {
+    double total = 0, wsum = 0;
+    for (int j = 0; j < nslabs; j++) { total += std::max(cost[j], 0.0); wsum += share ? share[j] : 1.0; }
     out[0] = 0; out[nslabs] = nz;
     if (!(total > 0) || nslabs < 2) { for (int g = 1; g < nslabs; g++) out[g] = cuts[g]; return; }
     int j = 0;
     double before = 0;  // cost of the slabs in front of slab j
+    double wacc = 0;    // share of the new slabs in front of cut g
     for (int g = 1; g < nslabs; g++) {
-        const double target = total * g / nslabs;
+        wacc += share ? share[g - 1] : 1.0;
+        const double target = total * wacc / wsum;
         while (j < nslabs - 1 && before + std::max(cost[j], 0.0) < target) { before += std::max(cost[j], 0.0); j++; }
         const double w = std::max(cost[j], 0.0);
         const double frac = w > 0 ? (target - before) / w : 0.0;
@@ -798,7 +860,7 @@ int gsdf_multi_begin(int ndev, const int *devs, int slabs_per_device, const void
     for (int w = 0; w < mm->ndev && !rc; w++) rc = gsdf_program_create_on(mm->devs[w], blob, blob_bytes, aux, aux_floats, &mm->prog[w]);
     for (int j = 0; j < nslabs && !rc; j++) {
         if (mm->cuts[j + 1] <= mm->cuts[j]) { rc = fail(GSDF_EINVAL, "internal: empty Z-slab %d", j); break; }
-        rc = gsdf_mesh_begin(mm->prog[j % mm->ndev], lat, mm->cuts[j], mm->cuts[j + 1], flags, &mm->slab[j]);
+        rc = mesh_begin_prio(mm->prog[j % mm->ndev], lat, mm->cuts[j], mm->cuts[j + 1], flags, nullptr, multi_slab_priority(mm, j), &mm->slab[j]);
     }
     if (rc) { gsdf_multi_destroy(mm); return rc; }
     // totals of the construction render
@@ -833,6 +895,8 @@ int64_t gsdf_multi_render(gsdf_multimesher *mm, float *tri9, size_t max_tris) {
         else (void)cudaGetLastError();
     }
     for (auto &c : mm->count) c.store(-1, std::memory_order_relaxed);
+    mm->timeline.assign(2 + 2 * (size_t)mm->nslabs, 0.0);
+    mm->t_call = std::chrono::steady_clock::now();
     mm->abort_rc.store(0);
     mm->job_done.store(0);
     if (mm->ndev > 1) {
@@ -863,6 +927,7 @@ int64_t gsdf_multi_render(gsdf_multimesher *mm, float *tri9, size_t max_tris) {
         }
     }
     mm->device_ms = ms;
+    mm->timeline.back() = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - mm->t_call).count();
     mm->rendered = true;
     mm->read_pos = 0;
     mm->delivered = tri9 != nullptr && mm->ntri <= max_tris;
@@ -896,12 +961,16 @@ int gsdf_multi_rebalance(gsdf_multimesher *mm, int rounds) {
         std::vector<double> cost(mm->nslabs);
         for (int j = 0; j < mm->nslabs; j++) cost[j] = (double)mm->slab[j]->evals;
         std::vector<int32_t> cuts(mm->nslabs + 1);
-        slab_rebalance(mm->lat.n[2], mm->nslabs, mm->cuts.data(), cost.data(), cuts.data());
+        // One device pipelining its read-back: the first slab's compute and the last slab's copy are the two parts of the
+        // render nothing else runs under, so those two slabs get half a share of the work. Several devices: equal shares.
+        std::vector<double> share(mm->nslabs, 1.0);
+        if (mm->ndev == 1 && mm->nslabs >= 3) share.front() = share.back() = 0.5;
+        slab_rebalance(mm->lat.n[2], mm->nslabs, mm->cuts.data(), cost.data(), cuts.data(), share.data());
         if (cuts == mm->cuts) break;
         for (int j = 0; j < mm->nslabs; j++) {
             if (cuts[j] == mm->cuts[j] && cuts[j + 1] == mm->cuts[j + 1]) continue;
             gsdf_mesher *fresh = nullptr;
-            const int rc = gsdf_mesh_begin(mm->prog[j % mm->ndev], &mm->lat, cuts[j], cuts[j + 1], mm->flags, &fresh);
+            const int rc = mesh_begin_prio(mm->prog[j % mm->ndev], &mm->lat, cuts[j], cuts[j + 1], mm->flags, nullptr, multi_slab_priority(mm, j), &fresh);
             if (rc) return rc;  // the old partition stays valid up to slab j; the caller sees the error
             gsdf_mesh_destroy(mm->slab[j]);
             mm->slab[j] = fresh;
@@ -916,6 +985,13 @@ int gsdf_multi_rebalance(gsdf_multimesher *mm, int rounds) {
     }
     mm->read_pos = 0;
     return changed;
+}
+
+int gsdf_multi_timeline(const gsdf_multimesher *mm, double *us, int max_entries) {
+    if (!mm || !us) return fail(GSDF_EINVAL, "gsdf_multi_timeline: NULL argument");
+    const int n = (int)std::min<size_t>(mm->timeline.size(), (size_t)std::max(max_entries, 0));
+    for (int i = 0; i < n; i++) us[i] = mm->timeline[i];
+    return (int)mm->timeline.size();
 }
 
 int gsdf_multi_rewind(gsdf_multimesher *mm) {

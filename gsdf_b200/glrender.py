@@ -312,6 +312,14 @@ class MultiRenderer:
     def DeviceMs(self):
         return self._stats()[3]
 
+    def Timeline(self):
+        """Host-clock microseconds of the last RenderToHost (gsdf_multi_timeline): dict(enqueued, slabs=[(count seen, copy
+        enqueued)], delivered)."""
+        buf = (C.c_double * 8200)()
+        n = check(lib.gsdf_multi_timeline(self._h, buf, 8200))
+        v = [float(x) for x in buf[:n]]
+        return dict(enqueued=v[0], slabs=[(v[1 + 2 * j], v[2 + 2 * j]) for j in range((n - 2) // 2)], delivered=v[-1])
+
     def Slabs(self):
         """(cuts, devices): nslabs+1 cell-layer cuts and the device of each slab."""
         cuts = (C.c_int32 * 4097)()

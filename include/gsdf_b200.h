@@ -209,6 +209,10 @@ int gsdf_multi_update(gsdf_multimesher *mm, const void *blob, size_t blob_bytes,
 int64_t gsdf_multi_render(gsdf_multimesher *mm, float *tri9, size_t max_tris);
 /* Renderer.ReadTriangles on the last render: up to max_tris triangles from the read position (0 = io.EOF). */
 int64_t gsdf_multi_read(gsdf_multimesher *mm, float *tri9, size_t max_tris);
+/* Host-clock timeline of the last gsdf_multi_render, microseconds from the call: us[0] = every slab of worker 0 enqueued,
+ * us[1+2j] = slab j's counters seen, us[2+2j] = slab j's read-back enqueued (0 without a pinned destination), last entry =
+ * everything delivered. Returns the number of entries (2 + 2 * slabs). For profiles, not for control flow. */
+int gsdf_multi_timeline(const gsdf_multimesher *mm, double *us, int max_entries);
 /* Moves the read position of gsdf_multi_read back to the first triangle of the last render. */
 int gsdf_multi_rewind(gsdf_multimesher *mm);
 /* Totals of the last render; device_ms = the longest device time over the slabs' streams (may be NULL). */

@@ -22,7 +22,9 @@ def test_graph_replay_equals_eager(bld):
         assert np.array_equal(graph.AllTriangles().view(np.uint32), want.view(np.uint32)), i
         assert (graph.Evaluations(), graph.TotalPruned()) == (eager.Evaluations(), eager.TotalPruned())
     tg, te = graph.Timings(), eager.Timings()
-    assert tg["total_ms"] > 0 and tg["eval_ms"] == 0 and tg["emit_ms"] == 0     # no events inside a graph
+    # no events inside a graph: its stage times come from the kernels' own %globaltimer stamps and add up to the total
+    assert tg["total_ms"] > 0 and tg["eval_ms"] > 0 and tg["emit_ms"] > 0
+    assert 0.5 * tg["total_ms"] < tg["prune_ms"] + tg["eval_ms"] + tg["classify_ms"] + tg["emit_ms"] <= 1.05 * tg["total_ms"] + 0.01
     assert te["eval_ms"] > 0 and te["emit_ms"] > 0 and abs(sum(te[k] for k in ("prune_ms", "eval_ms", "classify_ms", "emit_ms")) - te["total_ms"]) < 0.02
 
 
