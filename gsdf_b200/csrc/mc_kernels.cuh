@@ -26,74 +26,64 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 
 __device__ __forceinline__ uint32_t bit_at(const uint32_t *row, int b) { return b < 0 ? 0u : (row[b >> 5] >> (b & 31)) & 1u; }
 
-// One warp per lattice corner row (j,k) of the slab: a quad (4 consecutive corners starting at 4m) must be evaluated
-// iff some kept block owns a cell touching one of its corners. Such cells have cy in {j-1,j}, cz in {k-1,k} (inside the
-// slab) and cx in [4m-1, 4m+3], i.e. blocks m-1 and m of up to four block rows. Survivors are appended
-// warp-aggregated: one ballot + one atomicAdd per 32 quads.
+// Quad list. A quad (4 consecutive corners of corner row (j,k) starting at 4m) must be evaluated iff some kept block owns a
+// cell touching one of its corners. Such cells have cy in {j-1,j}, cz in {k-1,k} (inside the slab) and cx in [4m-1, 4m+3],
+// i.e. blocks m-1 and m of up to four block rows. Work item = one 32-quad WORD of one corner row (lane per item, so a
+// 71-quad row costs 3 lanes, not a warp): need-word = word | word<<1 | carry of the previous word over the touching block
+// rows; the survivors of a warp's 32 words are appended with one atomicAdd per warp and expanded cooperatively (lane q
+// writes quad 32w+q of word w). Order: corner rows ascending within a warp's run, warps in arrival order.
 __global__ void __launch_bounds__(kThreads) k_compact_quads(MeshDims D, const uint32_t *__restrict__ bits, uint32_t *__restrict__ list,
                                                            uint32_t *__restrict__ count, unsigned long long *stamp) {
-    __shared__ uint32_t s_cnt[kThreads / 32];
-    __shared__ uint32_t s_base;
     pdl_trigger();
     pdl_wait();
     stage_stamp(stamp);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const uint32_t nrows = (uint32_t)(D.ny + 1) * (uint32_t)(D.cz1 - D.cz0 + 1);
-    const uint32_t rpg = gridDim.x * (blockDim.x >> 5);
-    const int nqw = (D.nqx + 31) >> 5;  // 32-quad words per corner row
-    // CTA-uniform trip count: every iteration the 8 warps take 8 consecutive rows and share ONE atomicAdd
-    for (uint32_t r0 = blockIdx.x * (blockDim.x >> 5); r0 < nrows; r0 += rpg) {
-        const uint32_t r = r0 + warp;
-        uint32_t mine = 0u;
-        // need-word w (kept by lane w of the warp; rows wider than 1024 quads loop) has bit q set iff quad 32w+q must
-        // be evaluated: blocks m and m-1 of the touching block rows, i.e. word | word<<1 | carry of the previous word.
-        for (int w0 = 0; w0 < nqw; w0 += 32) {
-            const int w = w0 + lane;
-            uint32_t needw = 0u;
-            if (r < nrows && w < nqw) {
-                const int j = (int)(r % (uint32_t)(D.ny + 1));
-                const int k = D.cz0 + (int)(r / (uint32_t)(D.ny + 1));
-                const int by0 = j - 1 >= 0 ? (j - 1) >> 2 : -1, by1 = j < D.ny ? j >> 2 : -1;
-                const int bz0 = k - 1 >= D.cz0 ? (k - 1) >> 2 : -1, bz1 = k < D.cz1 ? k >> 2 : -1;
+    const uint32_t nqw = (uint32_t)(D.nqx + 31) >> 5;  // 32-quad words per corner row
+    const uint64_t nitems = (uint64_t)nrows * nqw;
+    const uint64_t wpg = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t base = ((uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u; base < nitems; base += wpg * 32u) {
+        const uint64_t item = base + lane;
+        uint32_t needw = 0u, r = 0u, w = 0u;
+        if (item < nitems) {
+            r = (uint32_t)(item / nqw);
+            w = (uint32_t)(item - (uint64_t)r * nqw);
+            const int j = (int)(r % (uint32_t)(D.ny + 1));
+            const int k = D.cz0 + (int)(r / (uint32_t)(D.ny + 1));
+            const int by0 = j - 1 >= 0 ? (j - 1) >> 2 : -1, by1 = j < D.ny ? j >> 2 : -1;
+            const int bz0 = k - 1 >= D.cz0 ? (k - 1) >> 2 : -1, bz1 = k < D.cz1 ? k >> 2 : -1;
 #pragma unroll
-                for (int a = 0; a < 2; a++) {
-                    const int by = a ? by1 : by0;
-                    if (by < 0 || (a && by1 == by0)) continue;
+            for (int a = 0; a < 2; a++) {
+                const int by = a ? by1 : by0;
+                if (by < 0 || (a && by1 == by0)) continue;
 #pragma unroll
-                    for (int c = 0; c < 2; c++) {
-                        const int bz = c ? bz1 : bz0;
-                        if (bz < 0 || (c && bz1 == bz0)) continue;
-                        const uint32_t *row = bits + ((size_t)(bz - D.bz0) * D.nby + by) * D.nwx;
-                        const uint32_t cur = w < D.nwx ? row[w] : 0u;
-                        const uint32_t prev = (w >= 1 && w - 1 < D.nwx) ? row[w - 1] : 0u;
-                        needw |= cur | (cur << 1) | (prev >> 31);
-                    }
+                for (int c = 0; c < 2; c++) {
+                    const int bz = c ? bz1 : bz0;
+                    if (bz < 0 || (c && bz1 == bz0)) continue;
+                    const uint32_t *row = bits + ((size_t)(bz - D.bz0) * D.nby + by) * D.nwx;
+                    const uint32_t cur = (int)w < D.nwx ? row[w] : 0u;
+                    const uint32_t prev = (w >= 1 && (int)(w - 1) < D.nwx) ? row[w - 1] : 0u;
+                    needw |= cur | (cur << 1) | (prev >> 31);
                 }
-                const int rem = D.nqx - 32 * w;  // quads of this word that exist
-                if (rem < 32) needw &= (1u << rem) - 1u;
             }
-            // exclusive position of each word's quads inside the row chunk, then one CTA-wide atomic
-            const uint32_t pc = (uint32_t)__popc(needw);
-            const uint32_t incl = warp_incl_scan(pc);
-            const uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
-            if (lane == 0) s_cnt[warp] = wtot;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                uint32_t tot = 0;
-                for (int i = 0; i < kThreads / 32; i++) { const uint32_t c = s_cnt[i]; s_cnt[i] = tot; tot += c; }
-                s_base = tot ? atomicAdd(count, tot) : 0u;
-            }
-            __syncthreads();
-            // expand: lane q of the warp writes quad (32*ww + q) for every word ww of this chunk
-            const uint32_t wbase = s_base + s_cnt[warp];
-            for (int ww = 0; ww < 32 && w0 + ww < nqw; ww++) {
-                const uint32_t word = __shfl_sync(0xffffffffu, needw, ww);
-                if (word == 0u) continue;
-                const uint32_t off = __shfl_sync(0xffffffffu, incl - pc, ww);
-                if ((word >> lane) & 1u) list[wbase + off + __popc(word & ((1u << lane) - 1u))] = r * (uint32_t)D.nqx + (uint32_t)(32 * (w0 + ww) + lane);
-            }
-            mine += wtot;
-            __syncthreads();
+            const int rem = D.nqx - 32 * (int)w;  // quads of this word that exist
+            if (rem < 32) needw &= (1u << rem) - 1u;
+        }
+        const uint32_t pc = (uint32_t)__popc(needw);
+        const uint32_t incl = warp_incl_scan(pc);
+        const uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
+        if (wtot == 0u) continue;  // warp-uniform
+        uint32_t wbase = 0u;
+        if (lane == 0) wbase = atomicAdd(count, wtot);
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        uint32_t nonzero = __ballot_sync(0xffffffffu, needw != 0u);
+        while (nonzero) {  // warp-uniform: only the words that hold survivors
+            const int src = __ffs(nonzero) - 1;
+            nonzero &= nonzero - 1u;
+            const uint32_t word = __shfl_sync(0xffffffffu, needw, src);
+            const uint32_t off = __shfl_sync(0xffffffffu, incl - pc, src);
+            const uint32_t qid = __shfl_sync(0xffffffffu, r * (uint32_t)D.nqx + 32u * w, src);
+            if ((word >> lane) & 1u) list[wbase + off + __popc(word & ((1u << lane) - 1u))] = qid + (uint32_t)lane;
         }
     }
 }
@@ -116,7 +106,28 @@ struct MCArgs {
     uint8_t *seg_cases;     // optional: the 32 cube-case indices of seg_list[i] at [32*i, 32*i+32) (k_mc_count_tma -> k_mc_emit),
                             // so that pass 2 does not classify again
     unsigned long long *stamp;  // optional stage stamp slot of the kernel this struct is passed to
+    // When the emit pass is the last kernel of the render its last CTA does k_finish_render's work (fin_ctr != nullptr):
+    uint32_t *fin_ctr; volatile uint32_t *fin_hctr; int fin_nctr;
+    unsigned long long *fin_scanstate; uint32_t fin_nstate;
+    unsigned long long *fin_dstamp; volatile unsigned long long *fin_hstamp; int fin_nstamp;
+    uint32_t *fin_done;         // CTAs that finished emitting (one of the fin_nctr counters: re-armed with them)
 };
+
+// The end of a render: publish the device counters (and stage stamps) into mapped pinned host memory with plain stores and
+// re-arm counters + look-back scan state for the NEXT render. Run by all threads of ONE CTA.
+__device__ __forceinline__ void finish_render_cta(uint32_t *__restrict__ d_ctr, volatile uint32_t *h_ctr, int nctr, unsigned long long *__restrict__ scanstate,
+                                                  uint32_t nstate, unsigned long long *__restrict__ d_stamp, volatile unsigned long long *h_stamp, int nstamp) {
+    if (d_stamp && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        d_stamp[nstamp - 1] = t;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < (uint32_t)nctr; i += blockDim.x) { h_ctr[i] = d_ctr[i]; d_ctr[i] = 0u; }
+    for (uint32_t k = threadIdx.x; k < nstate; k += blockDim.x) scanstate[k] = 0ull;
+    if (d_stamp && threadIdx.x < (uint32_t)nstamp) h_stamp[threadIdx.x] = d_stamp[threadIdx.x];
+    __threadfence_system();
+}
 
 
 // marchcubes.go:76-98

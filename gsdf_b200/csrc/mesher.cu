@@ -10,6 +10,7 @@
 
 #include "internal.cuh"
 #include "mc_kernels.cuh"
+#include "mc_tile5.cuh"
 #include "dualcontour.cuh"
 
 using namespace gsdfk;
@@ -50,7 +51,9 @@ struct gsdf_mesher {
     // [4] scan, [5] emit, [7] finish -- written by the kernels themselves, so they exist inside CUDA-graph replays too
     unsigned long long *d_stamp = nullptr;
     unsigned long long *h_stamp = nullptr;
-    CUtensorMap tmap;             // 3-D view of d_grid for the TMA-staged classification
+    CUtensorMap tmap;             // 3-D view of d_grid for the TMA-staged classification (2-plane boxes, one-layer tiles)
+    CUtensorMap tmap5;            // the same view with 5-plane boxes (mc_tile5.cuh: four layers per tile)
+    bool tile5 = false;           // GSDF_MC_TILE5: the 4-layer-tile kernel pair instead of one-layer tiles + segment work list
     const float *tmap_grid = nullptr;
     bool use_tma = true;
     uint64_t ntri = 0, evals = 0, pruned = 0, read_pos = 0;
@@ -77,7 +80,7 @@ namespace {
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int make_grid_tensor_map(CUtensorMap *out, float *grid, int pitch, int rows, int planes) {
+int make_grid_tensor_map(CUtensorMap *out, float *grid, int pitch, int rows, int planes, int box_z) {
     static encode_tiled_fn fn = nullptr;
     if (!fn) {
         void *p = nullptr;
@@ -88,7 +91,7 @@ int make_grid_tensor_map(CUtensorMap *out, float *grid, int pitch, int rows, int
     }
     const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)planes};
     const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * 4 * (cuuint64_t)rows};  // bytes, dims 1..2
-    const cuuint32_t box[3] = {(cuuint32_t)kBoxX, (cuuint32_t)kBoxY, (cuuint32_t)kBoxZ};
+    const cuuint32_t box[3] = {(cuuint32_t)kBoxX, (cuuint32_t)kBoxY, (cuuint32_t)box_z};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, grid, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -166,9 +169,12 @@ int mesh_run_begin(gsdf_mesher *m) {
     A.seg_count = m->d_ctr + 5;
     A.seg_cases = (m->use_tma && pre_classified) ? m->d_segcases : nullptr;
     A.stamp = nullptr;
+    A.fin_ctr = nullptr; A.fin_hctr = nullptr; A.fin_nctr = 0; A.fin_scanstate = nullptr; A.fin_nstate = 0;
+    A.fin_dstamp = nullptr; A.fin_hstamp = nullptr; A.fin_nstamp = 0; A.fin_done = nullptr;
     const unsigned mcgrid = grid_for(p->sms, nrows * (uint64_t)((D.nsx + 3) / 4), kThreads / 32, 16);
     if (m->use_tma && m->tmap_grid != m->d_grid) {  // (re)describe the lattice buffer: pitch x (ny+1) x nk floats
-        if ((rc = make_grid_tensor_map(&m->tmap, m->d_grid, D.pitch, D.ny + 1, nk))) return rc;
+        if ((rc = make_grid_tensor_map(&m->tmap, m->d_grid, D.pitch, D.ny + 1, nk, kBoxZ))) return rc;
+        if ((rc = make_grid_tensor_map(&m->tmap5, m->d_grid, D.pitch, D.ny + 1, nk, kBox5Z))) return rc;
         m->tmap_grid = m->d_grid;
     }
     const bool emitted = m->tri_cap > 0;  // optimistic emit into the existing buffer (steady state: no mid-pipeline host sync)
@@ -209,7 +215,7 @@ int mesh_run_begin(gsdf_mesher *m) {
                                      li == 0 ? m->d_stamp + 0 : nullptr))) return rc;
         }
         const uint64_t ncrows = (uint64_t)(D.ny + 1) * nk;
-        CU(launch_chain(pdl, k_compact_quads, dim3(grid_for(p->sms, ncrows, kThreads / 32)), dim3(kThreads), 0, st, D, (const uint32_t *)m->d_mbits, m->d_list, m->d_ctr + 0, m->d_stamp + 1));
+        CU(launch_chain(pdl, k_compact_quads, dim3(grid_for(p->sms, (ncrows * (uint64_t)((D.nqx + 31) >> 5) + 31) / 32, kThreads / 32)), dim3(kThreads), 0, st, D, (const uint32_t *)m->d_mbits, m->d_list, m->d_ctr + 0, m->d_stamp + 1));
         CU(cudaGetLastError());
     }
     if (stage_events) CU(cudaEventRecord(m->ev[1], st));
@@ -226,7 +232,13 @@ int mesh_run_begin(gsdf_mesher *m) {
         }
     }
     if (stage_events) CU(cudaEventRecord(m->ev[2], st));
-    if (m->use_tma) {
+    const uint64_t ntiles5 = (uint64_t)((D.nsx + 3) / 4) * ((D.ny + kTileY - 1) / kTileY) * ((D.cz1 - D.cz0 + kT5Layers - 1) / kT5Layers);
+    const unsigned grid5 = grid_for(p->sms, ntiles5, 1, 8);
+    if (m->use_tma && m->tile5) {
+        MCArgs Cn = A;
+        Cn.stamp = m->d_stamp + 3;
+        CU(launch_chain(pdl, k_mc_count5, dim3(grid5), dim3(256), 0, st, m->tmap5, Cn));
+    } else if (m->use_tma) {
         const uint64_t ntiles = (uint64_t)((D.nsx + 3) / 4) * ((D.ny + kTileY - 1) / kTileY) * (D.cz1 - D.cz0);
         static const bool count_v1 = getenv("GSDF_COUNT_V1") != nullptr;  // A/B switch: one cell per lane, no prefetch
         // test knob: cap the grid so that small, oracle-checked lattices run many tiles per CTA through both stencil buffers
@@ -259,10 +271,17 @@ int mesh_run_begin(gsdf_mesher *m) {
         MCArgs E = A;
         E.cases = nullptr;
         E.stamp = m->d_stamp + 5;
-        CU(launch_chain(pdl, k_mc_emit, dim3(mcgrid), dim3(kThreads), 0, st, E));
+        if (m->use_tma && m->tile5) {
+            // the emit pass ends the render itself: its last CTA publishes the counters and re-arms the state
+            E.fin_ctr = m->d_ctr; E.fin_hctr = (volatile uint32_t *)m->h_ctr; E.fin_nctr = kMeshCtr;
+            E.fin_scanstate = m->d_scanstate; E.fin_nstate = (uint32_t)nscantiles;
+            E.fin_dstamp = m->d_stamp; E.fin_hstamp = (volatile unsigned long long *)m->h_stamp; E.fin_nstamp = kMeshStamps;
+            E.fin_done = m->d_ctr + kMeshCtr - 1;
+            CU(launch_chain(pdl, k_mc_emit5, dim3(grid5), dim3(256), 0, st, m->tmap5, E));
+        } else CU(launch_chain(pdl, k_mc_emit, dim3(mcgrid), dim3(kThreads), 0, st, E));
         CU(cudaGetLastError());
     }
-    {   // publish the counters (cudaMallocHost memory is device-mapped under UVA) and re-arm the state for the next render
+    if (!(emitted && m->use_tma && m->tile5)) {   // publish the counters (cudaMallocHost memory is device-mapped under UVA) and re-arm the state for the next render
         const uint32_t nstate = (uint32_t)nscantiles;
         CU(launch_chain(pdl, k_finish_render, dim3((unsigned)std::min<uint64_t>(std::max<uint64_t>((nstate + 255) / 256, 1), 64)), dim3(256), 0, st,
                         m->d_ctr, (volatile uint32_t *)m->h_ctr, kMeshCtr, m->d_scanstate, nstate, m->d_stamp, (volatile unsigned long long *)m->h_stamp, kMeshStamps));
@@ -289,7 +308,7 @@ int mesh_run_begin(gsdf_mesher *m) {
     std::memcpy(key.ptr, kp, sizeof kp);
     for (int li = 0; li < GSDF_PRUNE_MAX_LEVELS; li++) key.lbits[li] = m->d_lbits[li];
     key.plan = m->plan; key.prog = p;
-    key.tri_cap = m->tri_cap; key.pv = p->pv; key.flags = m->flags; key.ext = p->needs_ext ? 1 : 0; key.tma = m->use_tma ? 1 : 0;
+    key.tri_cap = m->tri_cap; key.pv = p->pv; key.flags = m->flags; key.ext = p->needs_ext ? 1 : 0; key.tma = (m->use_tma ? 1 : 0) | (m->tile5 ? 2 : 0);
     key.eval_p = eval_p; key.quad_hint = (prune && m->runs > 0) ? m->quad_hint : 0u;
     const bool use_graph = m->allow_graph && !(m->flags & GSDF_MESH_STAGE_TIMING) && emitted && m->runs > 0 && !scan3;
     if (use_graph) {
@@ -345,7 +364,13 @@ int mesh_run_end(gsdf_mesher *m) {
         A.cases = nullptr;
         // k_finish_render re-armed the counters already: give the emit its segment-list length back, clear again after
         CU(cudaMemcpyAsync(m->d_ctr + 5, m->h_ctr + 5, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        k_mc_emit<<<mcgrid, kThreads, 0, st>>>(A);
+        if (m->use_tma && m->tile5) {
+            const uint64_t ntiles5 = (uint64_t)((D.nsx + 3) / 4) * ((D.ny + kTileY - 1) / kTileY) * ((D.cz1 - D.cz0 + kT5Layers - 1) / kT5Layers);
+            A.stamp = nullptr;
+            k_mc_emit5<<<grid_for(p->sms, ntiles5, 1, 8), 256, 0, st>>>(m->tmap5, A);
+        } else {
+            k_mc_emit<<<mcgrid, kThreads, 0, st>>>(A);
+        }
         CU(cudaGetLastError());
         CU(cudaMemsetAsync(m->d_ctr, 0, 8 * sizeof(uint32_t), st));  // (the scheduler pairs behind them reset themselves)
         CU(cudaEventRecord(m->ev[4], st));
@@ -441,6 +466,10 @@ static int mesh_begin_prio(gsdf_program *p, const gsdf_lattice *lat, int cz0, in
     m->flags = flags;
     m->plan = pl;
     m->use_tma = getenv("GSDF_NO_TMA") == nullptr;  // A/B switch for the classification kernel
+    // A/B switch. GSDF_MC_TILE5=1 selects the 4-layer-tile pair (mc_tile5.cuh): measured on B200 (round 2) its count pass is
+    // 6 us faster than the one-layer-tile pass, its emit pass 25 us slower than the work-list emit (it classifies again, and
+    // a warp walks its row's segments serially) -- kept for the record, not the default.
+    m->tile5 = getenv("GSDF_MC_TILE5") != nullptr;
     m->allow_graph = getenv("GSDF_NO_GRAPH") == nullptr;  // A/B switch: eager launches instead of the CUDA graph
     MeshDims &D = m->D;
     D.nx = lat->n[0]; D.ny = lat->n[1]; D.nz = lat->n[2];
