@@ -1,0 +1,476 @@
+// mc_block.cuh -- marching cubes over the KEPT 4x4x4-cell prune blocks only (default since round 2).
+//
+// The tile kernels (mc_kernels.cuh, mc_tile5.cuh) sweep whole rows of the lattice: on a pruned lattice a quarter of their
+// lanes sit on kept blocks and a few per cent on cells that hold surface, and ncu shows both passes bound by instruction
+// issue, not by memory. Here the unit of work is one kept block and nothing else is touched:
+//   k_mesh_lists      (prune -> work lists) the quad list of the lattice evaluation AND the list of kept blocks
+//   k_mc_blk_count    warp per kept block: its 5x5x5 corner stencil arrives in shared memory by ONE 3-D tensor copy
+//                     (cp.async.bulk.tensor.3d, box 8x5x5, double-buffered per warp); 2 cells per lane are classified and
+//                     the triangle count of each of the block's 16 cell rows goes to blkcnt[segment][slot] (one byte;
+//                     a 32-cell row segment has 8 block slots). No atomics.
+//   k_scan_seg        decoupled look-back scan whose input is computed on the fly: the count of a segment is the sum of the
+//                     bytes of its KEPT slots (prune bit rows decide; stale bytes of other slots are never read as counts)
+//   k_mc_blk_emit     warp per kept block again: rows without triangles cost one 16-byte load; the others re-classify
+//                     their 64 cells from the staged stencil and deal the block's triangle vertices round-robin to the 32
+//                     lanes (owner cell by a shuffle search over the inclusive scan of the per-cell counts -- the
+//                     warp-level scan north_star asks for). A cell's triangles start at segoff[segment] + the kept slots
+//                     in front of its block + the cells in front of it in its row: FlatRenderer cell order, deterministic.
+// Output is bit-identical to k_mc_count / k_mc_emit.
+#pragma once
+#include "mc_kernels.cuh"
+
+namespace gsdfk {
+
+constexpr int kBlkBoxX = 8, kBlkBoxY = 5, kBlkBoxZ = 5;
+constexpr uint32_t kBlkBoxBytes = kBlkBoxX * kBlkBoxY * kBlkBoxZ * 4;  // 800
+constexpr uint32_t kBlkBufStride = 896;                                // 128-byte aligned per-warp stencil buffers
+constexpr int kBlkWarps = 8;
+
+struct BlkArgs {
+    MeshDims D;
+    float ox, oy, oz, res, cubeDiag;
+    const uint32_t *mbits;     // prune bit rows, nullptr = every block kept (FlatRenderer)
+    const uint32_t *blklist;   // kept blocks: (bzl * nby + by) * nbx + bx, bzl relative to D.bz0
+    const uint32_t *nblk;      // device-side length of blklist
+    uint2 *blkcnt;             // [segment] 8 bytes: triangles of block slot t in that 32-cell row segment
+    uint32_t *segoff;          // [segment] exclusive triangle offset (k_scan_seg)
+    const uint8_t *t_ntri;
+    const int8_t *t_tris;
+    float *tris;
+    uint64_t tri_capacity;
+    uint8_t *cases;            // optional, zero-initialised by the host: nx*ny*(cz1-cz0) bytes
+    uint32_t *overflow;
+    unsigned long long *stamp;
+    // the emit pass ends the render (see MCArgs)
+    uint32_t *fin_ctr; volatile uint32_t *fin_hctr; int fin_nctr;
+    unsigned long long *fin_scanstate; uint32_t fin_nstate;
+    unsigned long long *fin_dstamp; volatile unsigned long long *fin_hstamp; int fin_nstamp;
+    uint32_t *fin_done;
+};
+
+// ---------------------------------------------------------------------------------------------- prune -> work lists
+// Quad list exactly as k_compact_quads (lane per 32-quad word of a corner row), then the kept-block list (lane per 32-block
+// word of a block row). bits == nullptr: no quad list, every block of the slab is listed (FlatRenderer).
+__global__ void __launch_bounds__(kThreads) k_mesh_lists(MeshDims D, const uint32_t *__restrict__ bits, uint32_t *__restrict__ list,
+                                                        uint32_t *__restrict__ count, uint32_t *__restrict__ blklist, uint32_t *__restrict__ nblk,
+                                                        unsigned long long *stamp) {
+    pdl_trigger();
+    pdl_wait();
+    stage_stamp(stamp);
+    const int lane = threadIdx.x & 31;
+    const uint64_t wpg = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    const uint64_t w0 = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (bits && list) {
+        const uint32_t nrows = (uint32_t)(D.ny + 1) * (uint32_t)(D.cz1 - D.cz0 + 1);
+        const uint32_t nqw = (uint32_t)(D.nqx + 31) >> 5;  // 32-quad words per corner row
+        const uint64_t nitems = (uint64_t)nrows * nqw;
+        for (uint64_t base = w0 * 32u; base < nitems; base += wpg * 32u) {
+            const uint64_t item = base + lane;
+            uint32_t needw = 0u, r = 0u, w = 0u;
+            if (item < nitems) {
+                r = (uint32_t)(item / nqw);
+                w = (uint32_t)(item - (uint64_t)r * nqw);
+                const int j = (int)(r % (uint32_t)(D.ny + 1));
+                const int k = D.cz0 + (int)(r / (uint32_t)(D.ny + 1));
+                const int by0 = j - 1 >= 0 ? (j - 1) >> 2 : -1, by1 = j < D.ny ? j >> 2 : -1;
+                const int bz0 = k - 1 >= D.cz0 ? (k - 1) >> 2 : -1, bz1 = k < D.cz1 ? k >> 2 : -1;
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    const int by = a ? by1 : by0;
+                    if (by < 0 || (a && by1 == by0)) continue;
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const int bz = c ? bz1 : bz0;
+                        if (bz < 0 || (c && bz1 == bz0)) continue;
+                        const uint32_t *row = bits + ((size_t)(bz - D.bz0) * D.nby + by) * D.nwx;
+                        const uint32_t cur = (int)w < D.nwx ? row[w] : 0u;
+                        const uint32_t prev = (w >= 1 && (int)(w - 1) < D.nwx) ? row[w - 1] : 0u;
+                        needw |= cur | (cur << 1) | (prev >> 31);
+                    }
+                }
+                const int rem = D.nqx - 32 * (int)w;  // quads of this word that exist
+                if (rem < 32) needw &= (1u << rem) - 1u;
+            }
+            const uint32_t pc = (uint32_t)__popc(needw);
+            const uint32_t incl = warp_incl_scan(pc);
+            const uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
+            if (wtot == 0u) continue;  // warp-uniform
+            uint32_t wbase = 0u;
+            if (lane == 0) wbase = atomicAdd(count, wtot);
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            uint32_t nonzero = __ballot_sync(0xffffffffu, needw != 0u);
+            while (nonzero) {  // warp-uniform: only the words that hold survivors
+                const int src = __ffs(nonzero) - 1;
+                nonzero &= nonzero - 1u;
+                const uint32_t word = __shfl_sync(0xffffffffu, needw, src);
+                const uint32_t off = __shfl_sync(0xffffffffu, incl - pc, src);
+                const uint32_t qid = __shfl_sync(0xffffffffu, r * (uint32_t)D.nqx + 32u * w, src);
+                if ((word >> lane) & 1u) list[wbase + off + __popc(word & ((1u << lane) - 1u))] = qid + (uint32_t)lane;
+            }
+        }
+    }
+    {   // kept blocks
+        const uint64_t nitems = (uint64_t)D.nbz * D.nby * D.nwx;
+        for (uint64_t base = w0 * 32u; base < nitems; base += wpg * 32u) {
+            const uint64_t item = base + lane;
+            uint32_t word = 0u, brow = 0u, w = 0u;
+            if (item < nitems) {
+                brow = (uint32_t)(item / (uint32_t)D.nwx);
+                w = (uint32_t)(item - (uint64_t)brow * (uint32_t)D.nwx);
+                word = bits ? bits[item] : 0xffffffffu;
+                const int rem = D.nbx - 32 * (int)w;
+                if (rem < 32) word &= (1u << rem) - 1u;
+            }
+            const uint32_t pc = (uint32_t)__popc(word);
+            const uint32_t incl = warp_incl_scan(pc);
+            const uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
+            if (wtot == 0u) continue;
+            uint32_t wbase = 0u;
+            if (lane == 0) wbase = atomicAdd(nblk, wtot);
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            uint32_t nonzero = __ballot_sync(0xffffffffu, word != 0u);
+            while (nonzero) {
+                const int src = __ffs(nonzero) - 1;
+                nonzero &= nonzero - 1u;
+                const uint32_t wd = __shfl_sync(0xffffffffu, word, src);
+                const uint32_t off = __shfl_sync(0xffffffffu, incl - pc, src);
+                const uint32_t bid = __shfl_sync(0xffffffffu, brow * (uint32_t)D.nbx + 32u * w, src);
+                if ((wd >> lane) & 1u) blklist[wbase + off + __popc(wd & ((1u << lane) - 1u))] = bid + (uint32_t)lane;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- per-block helpers
+struct BlkPos {
+    int bx, by, bzl;   // block coordinates (bzl relative to D.bz0)
+    int x0, y0, z0;    // first cell (global cell coordinates)
+};
+__device__ __forceinline__ BlkPos blk_decode(const MeshDims &D, uint32_t bid) {
+    BlkPos b;
+    b.bx = (int)(bid % (uint32_t)D.nbx);
+    const uint32_t t = bid / (uint32_t)D.nbx;
+    b.by = (int)(t % (uint32_t)D.nby);
+    b.bzl = (int)(t / (uint32_t)D.nby);
+    b.x0 = 4 * b.bx; b.y0 = 4 * b.by; b.z0 = 4 * (D.bz0 + b.bzl);
+    return b;
+}
+// stencil copy of block b into `buf` (corner (x0+i, y0+j, z0+k) lands at buf[(k*5 + j)*8 + i]); plane index relative to cz0
+__device__ __forceinline__ void blk_issue(const CUtensorMap *tmap, float *buf, uint32_t bar, const MeshDims &D, const BlkPos &b) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBlkBoxBytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(buf)),
+                 "l"(tmap), "r"(b.x0), "r"(b.y0), "r"(b.z0 - D.cz0), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void blk_wait(uint32_t bar, uint32_t phase) {
+    if ((threadIdx.x & 31) == 0) asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "BW_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra BW_DONE;\n\t"
+        "bra BW_LOOP;\n\t"
+        "BW_DONE:\n\t"
+        "}" ::"r"(bar), "r"(phase)
+        : "memory");
+    __syncwarp();
+}
+// Cube-case index of cell (lx, ly, lz) of the block from the staged stencil; corner order flatrenderer.go:222-233, reject
+// rule :218-220, case index marchcubes.go:39-44. `valid`: the cell exists in the slab.
+__device__ __forceinline__ int blk_case(const float *buf, int lx, int ly, int lz, bool valid, float cubeDiag) {
+    const float *c = buf + (lz * 5 + ly) * 8 + lx;
+    const float v0 = c[0], v1 = c[1], v2 = c[9], v3 = c[8], v4 = c[40], v5 = c[41], v6 = c[49], v7 = c[48];
+    if (!valid || fabsf(v0) > cubeDiag) return 0;
+    return (v0 < 0.f ? 1 : 0) | (v1 < 0.f ? 2 : 0) | (v2 < 0.f ? 4 : 0) | (v3 < 0.f ? 8 : 0) | (v4 < 0.f ? 16 : 0) | (v5 < 0.f ? 32 : 0) |
+           (v6 < 0.f ? 64 : 0) | (v7 < 0.f ? 128 : 0);
+}
+// 32-cell row segment and block slot of cell row (cy, cz) of block column bx
+__device__ __forceinline__ uint32_t blk_segment(const MeshDims &D, int bx, int cy, int cz) {
+    return ((uint32_t)(cz - D.cz0) * (uint32_t)D.ny + (uint32_t)cy) * (uint32_t)D.nsx + (uint32_t)(bx >> 3);
+}
+
+// ---------------------------------------------------------------------------------------------- pass 1
+// Lane l: cell column lx = l & 3, row ly = (l >> 2) & 3, layers lz = l >> 4 and lz + 2.
+__global__ void __launch_bounds__(kBlkWarps * 32) k_mc_blk_count(const __grid_constant__ CUtensorMap tmap, BlkArgs A) {
+    __shared__ __align__(128) uint8_t s_buf[kBlkWarps][2][kBlkBufStride];
+    __shared__ __align__(8) uint64_t s_bar[kBlkWarps][2];
+    __shared__ uint8_t s_ntri[256];
+    pdl_trigger();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = A.t_ntri[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bar0 = smem_u32(&s_bar[warp][0]), bar1 = smem_u32(&s_bar[warp][1]);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdl_wait();  // lattice, bit rows and block list are the predecessors'
+    stage_stamp(A.stamp);
+    __syncthreads();
+    const MeshDims &D = A.D;
+    const uint32_t nblk = *A.nblk;
+    const uint32_t stride = gridDim.x * kBlkWarps;
+    const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
+    uint32_t phases = 0u;  // bit b = parity to wait for on buffer b
+    uint32_t it = blockIdx.x * kBlkWarps + warp;
+    int cur = 0;
+    if (it < nblk && lane == 0) blk_issue(&tmap, reinterpret_cast<float *>(s_buf[warp][0]), bar0, D, blk_decode(D, A.blklist[it]));
+    for (; it < nblk; it += stride, cur ^= 1) {
+        const BlkPos b = blk_decode(D, A.blklist[it]);
+        if (it + stride < nblk && lane == 0)  // the other buffer was released by the __syncwarp that ended the previous iteration
+            blk_issue(&tmap, reinterpret_cast<float *>(s_buf[warp][cur ^ 1]), cur ? bar0 : bar1, D, blk_decode(D, A.blklist[it + stride]));
+        blk_wait(cur ? bar1 : bar0, (phases >> cur) & 1u);
+        phases ^= 1u << cur;
+        const float *buf = reinterpret_cast<const float *>(s_buf[warp][cur]);
+        const int cx = b.x0 + lx, cy = b.y0 + ly;
+        const bool okxy = cx < D.nx && cy < D.ny;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int lzz = lz + 2 * h, cz = b.z0 + lzz;
+            const bool valid = okxy && cz >= D.cz0 && cz < D.cz1;
+            const int idx = blk_case(buf, lx, ly, lzz, valid, A.cubeDiag);
+            uint32_t n = s_ntri[idx];
+            n += __shfl_xor_sync(0xffffffffu, n, 1);
+            n += __shfl_xor_sync(0xffffffffu, n, 2);  // the four cells of the row
+            if (cy < D.ny && cz >= D.cz0 && cz < D.cz1) {
+                if (lx == 0) reinterpret_cast<uint8_t *>(A.blkcnt + blk_segment(D, b.bx, cy, cz))[b.bx & 7] = (uint8_t)n;
+                if (A.cases && cx < D.nx) A.cases[((size_t)(cz - D.cz0) * D.ny + cy) * D.nx + cx] = (uint8_t)idx;
+            }
+        }
+        __syncwarp();  // everybody is done with buf before it is refilled two iterations later
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- scan over segments
+// Triangle count of a segment = sum of the bytes of its kept block slots. kb = kept bits of the segment's 8 slots.
+__device__ __forceinline__ uint32_t seg_kept_bits(const MeshDims &D, const uint32_t *mbits, uint32_t row, uint32_t sx) {
+    const int cy = (int)(row % (uint32_t)D.ny), cz = D.cz0 + (int)(row / (uint32_t)D.ny);
+    uint32_t kb = 0xffu;
+    if (mbits) kb = (mbits[((size_t)((cz >> 2) - D.bz0) * D.nby + (cy >> 2)) * D.nwx + (sx >> 2)] >> (8u * (sx & 3u))) & 0xffu;
+    const int rem = D.nbx - 8 * (int)sx;  // block slots of this segment that exist
+    if (rem < 8) kb &= (1u << rem) - 1u;
+    return kb;
+}
+__device__ __forceinline__ uint32_t seg_masked_sum(uint2 c, uint32_t kb, int upto = 8) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const uint32_t byte = ((t < 4 ? c.x : c.y) >> (8 * (t & 3))) & 0xffu;
+        if (t < upto && ((kb >> t) & 1u)) s += byte;
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(kThreads) k_scan_seg(MeshDims D, const uint32_t *__restrict__ mbits, const uint2 *__restrict__ blkcnt, uint32_t *__restrict__ segoff,
+                                                      uint32_t n, unsigned long long *__restrict__ state, uint32_t *__restrict__ ticket, uint32_t epoch,
+                                                      unsigned long long *__restrict__ total, unsigned long long *stamp) {
+    __shared__ uint32_t s_w[kThreads / 32];
+    __shared__ uint32_t s_tile, s_prefix;
+    pdl_trigger();
+    pdl_wait();
+    stage_stamp(stamp);
+    const uint32_t ntiles = (n + kScanTile - 1) / kScanTile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= ntiles) return;
+    const uint32_t base = tile * kScanTile + threadIdx.x * 8;
+    uint32_t v[8], sum = 0;
+    {
+        uint32_t row = base / (uint32_t)D.nsx, sx = base - row * (uint32_t)D.nsx;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            v[i] = 0u;
+            if (base + i < n) {
+                const uint32_t kb = seg_kept_bits(D, mbits, row, sx);
+                if (kb) v[i] = seg_masked_sum(blkcnt[base + i], kb);
+            }
+            if (++sx == (uint32_t)D.nsx) { sx = 0u; row++; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) sum += v[i];
+    const uint32_t incl = warp_incl_scan(sum);
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t w = threadIdx.x < kThreads / 32 ? s_w[threadIdx.x] : 0u;
+        const uint32_t wi = warp_incl_scan(w);
+        if (threadIdx.x < kThreads / 32) s_w[threadIdx.x] = wi - w;
+        const uint32_t agg = __shfl_sync(0xffffffffu, wi, 31);  // tile aggregate
+        const unsigned long long tag = (unsigned long long)epoch << 34;
+        if (threadIdx.x == 0) {
+            const unsigned long long st = tag | ((tile == 0 ? 2ull : 1ull) << 32) | agg;
+            atomicExch(&state[tile], st);
+        }
+        uint32_t prefix = 0;
+        if (tile > 0) {
+            int look = (int)tile - 1;
+            for (;;) {
+                const int idx = look - (int)threadIdx.x;
+                unsigned long long st = 0;
+                if (idx >= 0) {
+                    do { st = *reinterpret_cast<volatile unsigned long long *>(&state[idx]); } while ((st >> 34) != epoch || ((st >> 32) & 3ull) == 0ull);
+                }
+                const uint32_t flag = idx >= 0 ? (uint32_t)((st >> 32) & 3ull) : 2u;  // before tile 0: inclusive prefix 0
+                const uint32_t val = idx >= 0 ? (uint32_t)st : 0u;
+                const unsigned incl_mask = __ballot_sync(0xffffffffu, flag == 2u);
+                const int stop = incl_mask ? __ffs(incl_mask) - 1 : 31;
+                uint32_t part = (int)threadIdx.x <= stop ? val : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                prefix += part;
+                if (incl_mask) break;
+                look -= 32;
+            }
+            if (threadIdx.x == 0) atomicExch(&state[tile], tag | (2ull << 32) | (unsigned long long)(prefix + agg));
+        }
+        if (threadIdx.x == 0) {
+            s_prefix = prefix;
+            if (tile == ntiles - 1) *total = (unsigned long long)prefix + agg;
+        }
+    }
+    __syncthreads();
+    uint32_t run = s_prefix + s_w[threadIdx.x >> 5] + (incl - sum);
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { o[i] = run; run += v[i]; }
+    if (base + 8 <= n) {
+        *reinterpret_cast<uint4 *>(segoff + base) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4 *>(segoff + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (base + i < n) segoff[base + i] = o[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- pass 2
+__global__ void __launch_bounds__(kBlkWarps * 32) k_mc_blk_emit(const __grid_constant__ CUtensorMap tmap, BlkArgs A) {
+    __shared__ __align__(128) uint8_t s_buf[kBlkWarps][2][kBlkBufStride];
+    __shared__ __align__(8) uint64_t s_bar[kBlkWarps][2];
+    __shared__ uint8_t s_ntri[256];
+    __shared__ __align__(16) int8_t s_tris[256 * 16];
+    pdl_trigger();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = A.t_ntri[i];
+    for (int i = threadIdx.x; i < 256 * 16 / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_tris)[i] = reinterpret_cast<const uint4 *>(A.t_tris)[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bar0 = smem_u32(&s_bar[warp][0]), bar1 = smem_u32(&s_bar[warp][1]);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdl_wait();
+    stage_stamp(A.stamp);
+    __syncthreads();
+    const MeshDims &D = A.D;
+    const uint32_t nblk = *A.nblk;
+    const uint32_t stride = gridDim.x * kBlkWarps;
+    const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
+    const float rr = A.res;
+    uint32_t phases = 0u;  // bit b = parity to wait for on buffer b
+    uint32_t it = blockIdx.x * kBlkWarps + warp;
+    int cur = 0;
+    if (it < nblk && lane == 0) blk_issue(&tmap, reinterpret_cast<float *>(s_buf[warp][0]), bar0, D, blk_decode(D, A.blklist[it]));
+    for (; it < nblk; it += stride, cur ^= 1) {
+        const BlkPos b = blk_decode(D, A.blklist[it]);
+        if (it + stride < nblk && lane == 0)
+            blk_issue(&tmap, reinterpret_cast<float *>(s_buf[warp][cur ^ 1]), cur ? bar0 : bar1, D, blk_decode(D, A.blklist[it + stride]));
+        // the counts pass 1 left for this block's rows: lane's rows are (ly, lz) and (ly, lz + 2)
+        const int cx = b.x0 + lx, cy = b.y0 + ly;
+        uint32_t rown[2] = {0u, 0u}, rowbase[2] = {0u, 0u};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int cz = b.z0 + lz + 2 * h;
+            if (cy < D.ny && cz >= D.cz0 && cz < D.cz1) {
+                const uint32_t seg = blk_segment(D, b.bx, cy, cz);
+                const uint2 c = A.blkcnt[seg];
+                const int slot = b.bx & 7;
+                rown[h] = ((slot < 4 ? c.x : c.y) >> (8 * (slot & 3))) & 0xffu;
+                if (rown[h]) {  // triangles of the kept slots in front of this block, behind the segment's offset
+                    const uint32_t kb = seg_kept_bits(D, A.mbits, (uint32_t)(cz - D.cz0) * (uint32_t)D.ny + (uint32_t)cy, (uint32_t)(b.bx >> 3));
+                    rowbase[h] = A.segoff[seg] + seg_masked_sum(c, kb, slot);
+                }
+            }
+        }
+        const bool any = __ballot_sync(0xffffffffu, (rown[0] | rown[1]) != 0u) != 0u;
+        blk_wait(cur ? bar1 : bar0, (phases >> cur) & 1u);  // (consumed even when the block turns out empty: the barrier phase must advance)
+        phases ^= 1u << cur;
+        if (any) {
+            const float *buf = reinterpret_cast<const float *>(s_buf[warp][cur]);
+            const bool okxy = cx < D.nx && cy < D.ny;
+            int index[2];
+            uint32_t n[2], obase[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int lzz = lz + 2 * h, cz = b.z0 + lzz;
+                const bool valid = okxy && cz >= D.cz0 && cz < D.cz1 && rown[h] != 0u;
+                index[h] = valid ? blk_case(buf, lx, ly, lzz, true, A.cubeDiag) : 0;
+                n[h] = s_ntri[index[h]];
+                // cells in front of this one in its row: exclusive prefix over the 4 lanes of the row
+                const uint32_t a1 = __shfl_up_sync(0xffffffffu, n[h], 1), a2 = __shfl_up_sync(0xffffffffu, n[h], 2), a3 = __shfl_up_sync(0xffffffffu, n[h], 3);
+                obase[h] = rowbase[h] + (lx >= 1 ? a1 : 0u) + (lx >= 2 ? a2 : 0u) + (lx >= 3 ? a3 : 0u);
+            }
+            // vertices of the block's triangles, dealt round-robin: cells in the order (h = 0: lanes 0..31), (h = 1: lanes 0..31)
+            const uint32_t incl0 = warp_incl_scan(n[0]);
+            const uint32_t tot0 = __shfl_sync(0xffffffffu, incl0, 31);
+            const uint32_t incl1 = tot0 + warp_incl_scan(n[1]);
+            const uint32_t total = __shfl_sync(0xffffffffu, incl1, 31);
+            for (uint32_t ibase = 0; ibase < 3u * total; ibase += 32) {  // warp-uniform trip count: shuffles use all lanes
+                const uint32_t item = ibase + lane;
+                const bool alive = item < 3u * total;
+                const uint32_t tri = alive ? item / 3u : total - 1u, j = alive ? item - 3u * tri : 0u;
+                const bool second = tri >= tot0;  // which of the two cell sets owns the triangle
+                int lo = 0;                       // owner = first lane whose inclusive count exceeds tri
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const uint32_t p0 = __shfl_sync(0xffffffffu, incl0, lo + step - 1), p1 = __shfl_sync(0xffffffffu, incl1, lo + step - 1);
+                    if ((second ? p1 : p0) <= tri) lo += step;
+                }
+                const int owner = lo;
+                const uint32_t e0 = __shfl_sync(0xffffffffu, incl0 - n[0], owner), e1 = __shfl_sync(0xffffffffu, incl1 - n[1], owner);
+                const int i0 = __shfl_sync(0xffffffffu, index[0], owner), i1 = __shfl_sync(0xffffffffu, index[1], owner);
+                const uint32_t b0 = __shfl_sync(0xffffffffu, obase[0], owner), b1 = __shfl_sync(0xffffffffu, obase[1], owner);
+                if (!alive) continue;
+                const uint32_t kk = tri - (second ? e1 : e0);
+                const int oindex = second ? i1 : i0;
+                const uint64_t o = (uint64_t)(second ? b1 : b0) + kk;
+                if (o >= A.tri_capacity) { *A.overflow = 1u; continue; }
+                const int olx = owner & 3, oly = (owner >> 2) & 3, olz = (owner >> 4) + (second ? 2 : 0);
+                // corner positions, flatrenderer.go:235-247
+                const float px0 = A.ox + (float)(b.x0 + olx) * rr, px1 = px0 + rr;
+                const float py0 = A.oy + (float)(b.y0 + oly) * rr, py1 = py0 + rr;
+                const float pz0 = A.oz + (float)(b.z0 + olz) * rr, pz1 = pz0 + rr;
+                // marchcubes.go:64-68: vertex j of the triangle is points[table[3k + 2 - j]]
+                const int e = s_tris[16 * oindex + 3 * (int)kk + 2 - (int)j];
+                // edge -> corner pair (marchcubes.go:101-114), packed 4 bits per edge
+                const int ca = (int)((0x321076543210ull >> (4 * e)) & 0xf), cb = (int)((0x765447650321ull >> (4 * e)) & 0xf);
+                const float3 pa = make_float3((((ca + 1) >> 1) & 1) ? px1 : px0, ((ca >> 1) & 1) ? py1 : py0, (ca >> 2) ? pz1 : pz0);
+                const float3 pb = make_float3((((cb + 1) >> 1) & 1) ? px1 : px0, ((cb >> 1) & 1) ? py1 : py0, (cb >> 2) ? pz1 : pz0);
+                // corner c of the cell: x bit ((c+1)>>1)&1, y bit (c>>1)&1, z bit c>>2 (flatrenderer.go:222-233)
+                const float *cc = buf + (olz * 5 + oly) * 8 + olx;
+                const float va = cc[(ca >> 2) * 40 + ((ca >> 1) & 1) * 8 + (((ca + 1) >> 1) & 1)];
+                const float vb = cc[(cb >> 2) * 40 + ((cb >> 1) & 1) * 8 + (((cb + 1) >> 1) & 1)];
+                const float3 q = mc_interp(pa, pb, va, vb);
+                float *dst = A.tris + 9 * o + 3 * j;
+                dst[0] = q.x; dst[1] = q.y; dst[2] = q.z;
+            }
+        }
+        __syncwarp();  // everybody is done with buf before it is refilled two iterations later
+    }
+    if (A.fin_ctr) {  // the last CTA to get here ends the render (k_finish_render's work, without its launch)
+        __shared__ uint32_t s_last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(A.fin_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            finish_render_cta(A.fin_ctr, A.fin_hctr, A.fin_nctr, A.fin_scanstate, A.fin_nstate, A.fin_dstamp, A.fin_hstamp, A.fin_nstamp);
+        }
+    }
+}
+
+}  // namespace gsdfk

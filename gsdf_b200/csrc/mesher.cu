@@ -11,6 +11,7 @@
 #include "internal.cuh"
 #include "mc_kernels.cuh"
 #include "mc_tile5.cuh"
+#include "mc_block.cuh"
 #include "dualcontour.cuh"
 
 using namespace gsdfk;
@@ -53,6 +54,13 @@ struct gsdf_mesher {
     unsigned long long *h_stamp = nullptr;
     CUtensorMap tmap;             // 3-D view of d_grid for the TMA-staged classification (2-plane boxes, one-layer tiles)
     CUtensorMap tmap5;            // the same view with 5-plane boxes (mc_tile5.cuh: four layers per tile)
+    // marching-cubes kernels: 2 = kept-block kernels (mc_block.cuh, default), 1 = 4-layer tiles (mc_tile5.cuh),
+    // 0 = one-layer tiles + segment work list (mc_kernels.cuh). GSDF_MC=block|tile5|v1 selects (A/B).
+    int mc_mode = 2;
+    uint32_t *d_blklist = nullptr; size_t blklist_cap = 0;   // kept blocks of the slab
+    uint2 *d_blkcnt = nullptr; size_t blkcnt_cap = 0;        // per 32-cell segment: 8 block-slot triangle counts
+    CUtensorMap tmapB;            // the lattice with 8x5x5 boxes: one kept block's corner stencil
+    uint32_t blk_hint = 0;        // kept blocks of the previous render, rounded up
     bool tile5 = false;           // GSDF_MC_TILE5: the 4-layer-tile kernel pair instead of one-layer tiles + segment work list
     const float *tmap_grid = nullptr;
     bool use_tma = true;
@@ -71,7 +79,8 @@ struct gsdf_mesher {
     // a render that was enqueued (mesh_run_begin) and not yet finished (mesh_run_end)
     bool pending = false, pend_graph = false, pend_emitted = false;
     MCArgs pendA{};
-    unsigned pend_mcgrid = 0;
+    BlkArgs pendB{};
+    unsigned pend_mcgrid = 0, pend_blkgrid = 0;
 };
 
 namespace {
@@ -80,7 +89,7 @@ namespace {
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int make_grid_tensor_map(CUtensorMap *out, float *grid, int pitch, int rows, int planes, int box_z) {
+int make_grid_tensor_map(CUtensorMap *out, float *grid, int pitch, int rows, int planes, int box_z, int box_x = kBoxX, int box_y = kBoxY) {
     static encode_tiled_fn fn = nullptr;
     if (!fn) {
         void *p = nullptr;
@@ -91,7 +100,7 @@ int make_grid_tensor_map(CUtensorMap *out, float *grid, int pitch, int rows, int
     }
     const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)planes};
     const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * 4 * (cuuint64_t)rows};  // bytes, dims 1..2
-    const cuuint32_t box[3] = {(cuuint32_t)kBoxX, (cuuint32_t)kBoxY, (cuuint32_t)box_z};
+    const cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, (cuuint32_t)box_z};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, grid, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -151,6 +160,14 @@ int mesh_run_begin(gsdf_mesher *m) {
     if (m->flags & GSDF_MESH_KEEP_CASES) {
         if ((rc = grow(m->d_cases, m->cases_cap, (size_t)ncells))) return rc;
     }
+    // the kept-block kernels pay on pruned lattices; a dense sweep (FlatRenderer: every block kept) is what the row-tile kernels
+    // are for (measured: flange@400 dense 0.269 ms with tiles, 0.303 ms with blocks)
+    const bool blockmc = m->use_tma && m->mc_mode == 2 && prune;
+    const uint64_t nblocks_slab = (uint64_t)D.nbx * D.nby * D.nbz;
+    if (blockmc) {
+        if ((rc = grow(m->d_blklist, m->blklist_cap, (size_t)nblocks_slab))) return rc;
+        if ((rc = grow(m->d_blkcnt, m->blkcnt_cap, (size_t)nseg))) return rc;
+    }
     const gsdf_lattice &lat = m->lat;
     MCArgs A;
     A.D = D;
@@ -171,10 +188,19 @@ int mesh_run_begin(gsdf_mesher *m) {
     A.stamp = nullptr;
     A.fin_ctr = nullptr; A.fin_hctr = nullptr; A.fin_nctr = 0; A.fin_scanstate = nullptr; A.fin_nstate = 0;
     A.fin_dstamp = nullptr; A.fin_hstamp = nullptr; A.fin_nstamp = 0; A.fin_done = nullptr;
+    BlkArgs BA{};
+    BA.D = D; BA.ox = A.ox; BA.oy = A.oy; BA.oz = A.oz; BA.res = A.res; BA.cubeDiag = A.cubeDiag;
+    BA.mbits = A.mbits; BA.blklist = m->d_blklist; BA.nblk = m->d_ctr + 5; BA.blkcnt = m->d_blkcnt; BA.segoff = m->d_seg;
+    BA.t_ntri = A.t_ntri; BA.t_tris = A.t_tris; BA.tris = m->d_tris; BA.tri_capacity = m->tri_cap / 9; BA.cases = A.cases;
+    BA.overflow = A.overflow;
+    // persistent grid of the block kernels: one warp per kept block, sized from the previous render's count when there is one
+    const uint64_t blk_bound = m->runs > 0 ? std::min<uint64_t>(nblocks_slab, 2 * (uint64_t)m->blk_hint + 256) : nblocks_slab;
+    const unsigned blkgrid = grid_for(p->sms, blk_bound, kBlkWarps, 8);
     const unsigned mcgrid = grid_for(p->sms, nrows * (uint64_t)((D.nsx + 3) / 4), kThreads / 32, 16);
     if (m->use_tma && m->tmap_grid != m->d_grid) {  // (re)describe the lattice buffer: pitch x (ny+1) x nk floats
         if ((rc = make_grid_tensor_map(&m->tmap, m->d_grid, D.pitch, D.ny + 1, nk, kBoxZ))) return rc;
         if ((rc = make_grid_tensor_map(&m->tmap5, m->d_grid, D.pitch, D.ny + 1, nk, kBox5Z))) return rc;
+        if ((rc = make_grid_tensor_map(&m->tmapB, m->d_grid, D.pitch, D.ny + 1, nk, kBlkBoxZ, kBlkBoxX, kBlkBoxY))) return rc;
         m->tmap_grid = m->d_grid;
     }
     const bool emitted = m->tri_cap > 0;  // optimistic emit into the existing buffer (steady state: no mid-pipeline host sync)
@@ -215,7 +241,16 @@ int mesh_run_begin(gsdf_mesher *m) {
                                      li == 0 ? m->d_stamp + 0 : nullptr))) return rc;
         }
         const uint64_t ncrows = (uint64_t)(D.ny + 1) * nk;
+        if (blockmc)
+            CU(launch_chain(pdl, k_mesh_lists, dim3(grid_for(p->sms, (ncrows * (uint64_t)((D.nqx + 31) >> 5) + 31) / 32, kThreads / 32)), dim3(kThreads), 0, st, D,
+                            (const uint32_t *)m->d_mbits, m->d_list, m->d_ctr + 0, m->d_blklist, m->d_ctr + 5, m->d_stamp + 1));
+        else
         CU(launch_chain(pdl, k_compact_quads, dim3(grid_for(p->sms, (ncrows * (uint64_t)((D.nqx + 31) >> 5) + 31) / 32, kThreads / 32)), dim3(kThreads), 0, st, D, (const uint32_t *)m->d_mbits, m->d_list, m->d_ctr + 0, m->d_stamp + 1));
+        CU(cudaGetLastError());
+    }
+    if (!prune && blockmc) {  // FlatRenderer: every block of the slab is listed (no bit rows, no quad list)
+        CU(launch_chain(false, k_mesh_lists, dim3(grid_for(p->sms, ((uint64_t)D.nbz * D.nby * D.nwx + 31) / 32, kThreads / 32)), dim3(kThreads), 0, st, D,
+                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, m->d_blklist, m->d_ctr + 5, (unsigned long long *)nullptr));
         CU(cudaGetLastError());
     }
     if (stage_events) CU(cudaEventRecord(m->ev[1], st));
@@ -228,13 +263,18 @@ int mesh_run_begin(gsdf_mesher *m) {
         } else {
             GenGrid<4> g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
             const uint64_t bound = (prune && m->runs > 0) ? std::min<uint64_t>(nquads, 2 * (uint64_t)m->quad_hint + 1024) : nquads;
-            if ((rc = launch_grid4(p, g, bound, st, pdl && prune, sched, m->d_stamp + 2))) return rc;
+            if ((rc = launch_grid4(p, g, bound, st, pdl && (prune || blockmc), sched, m->d_stamp + 2))) return rc;
         }
     }
     if (stage_events) CU(cudaEventRecord(m->ev[2], st));
     const uint64_t ntiles5 = (uint64_t)((D.nsx + 3) / 4) * ((D.ny + kTileY - 1) / kTileY) * ((D.cz1 - D.cz0 + kT5Layers - 1) / kT5Layers);
     const unsigned grid5 = grid_for(p->sms, ntiles5, 1, 8);
-    if (m->use_tma && m->tile5) {
+    if (blockmc) {
+        if (A.cases) CU(cudaMemsetAsync(A.cases, 0, (size_t)ncells, st));  // parity mode only: cells outside kept blocks have case 0
+        BlkArgs Cn = BA;
+        Cn.stamp = m->d_stamp + 3;
+        CU(launch_chain(pdl && !A.cases, k_mc_blk_count, dim3(blkgrid), dim3(kBlkWarps * 32), 0, st, m->tmapB, Cn));
+    } else if (m->use_tma && m->tile5) {
         MCArgs Cn = A;
         Cn.stamp = m->d_stamp + 3;
         CU(launch_chain(pdl, k_mc_count5, dim3(grid5), dim3(256), 0, st, m->tmap5, Cn));
@@ -261,6 +301,10 @@ int mesh_run_begin(gsdf_mesher *m) {
         CU(cudaGetLastError());
         k_scan_apply<<<(unsigned)nscanblocks, kThreads, 0, st>>>(m->d_seg, nseg, m->d_blocksum);
         CU(cudaGetLastError());
+    } else if (blockmc) {
+        CU(launch_chain(pdl, k_scan_seg, dim3((unsigned)nscantiles), dim3(kThreads), 0, st, D, (const uint32_t *)A.mbits, (const uint2 *)m->d_blkcnt, m->d_seg, (uint32_t)nseg,
+                        m->d_scanstate, m->d_ctr + 6, epoch, reinterpret_cast<unsigned long long *>(m->d_ctr + 2), m->d_stamp + 4));
+        CU(cudaGetLastError());
     } else {
         CU(launch_chain(pdl, k_scan_lookback, dim3((unsigned)nscantiles), dim3(kThreads), 0, st, m->d_seg, (uint32_t)nseg, m->d_scanstate, m->d_ctr + 6, epoch,
                         reinterpret_cast<unsigned long long *>(m->d_ctr + 2), m->d_stamp + 4));
@@ -271,7 +315,16 @@ int mesh_run_begin(gsdf_mesher *m) {
         MCArgs E = A;
         E.cases = nullptr;
         E.stamp = m->d_stamp + 5;
-        if (m->use_tma && m->tile5) {
+        if (blockmc) {
+            BlkArgs BE = BA;
+            BE.cases = nullptr;
+            BE.stamp = m->d_stamp + 5;
+            BE.fin_ctr = m->d_ctr; BE.fin_hctr = (volatile uint32_t *)m->h_ctr; BE.fin_nctr = kMeshCtr;
+            BE.fin_scanstate = m->d_scanstate; BE.fin_nstate = (uint32_t)nscantiles;
+            BE.fin_dstamp = m->d_stamp; BE.fin_hstamp = (volatile unsigned long long *)m->h_stamp; BE.fin_nstamp = kMeshStamps;
+            BE.fin_done = m->d_ctr + kMeshCtr - 1;
+            CU(launch_chain(pdl, k_mc_blk_emit, dim3(blkgrid), dim3(kBlkWarps * 32), 0, st, m->tmapB, BE));
+        } else if (m->use_tma && m->tile5) {
             // the emit pass ends the render itself: its last CTA publishes the counters and re-arms the state
             E.fin_ctr = m->d_ctr; E.fin_hctr = (volatile uint32_t *)m->h_ctr; E.fin_nctr = kMeshCtr;
             E.fin_scanstate = m->d_scanstate; E.fin_nstate = (uint32_t)nscantiles;
@@ -281,7 +334,7 @@ int mesh_run_begin(gsdf_mesher *m) {
         } else CU(launch_chain(pdl, k_mc_emit, dim3(mcgrid), dim3(kThreads), 0, st, E));
         CU(cudaGetLastError());
     }
-    if (!(emitted && m->use_tma && m->tile5)) {   // publish the counters (cudaMallocHost memory is device-mapped under UVA) and re-arm the state for the next render
+    if (!(emitted && m->use_tma && (m->tile5 || blockmc))) {   // publish the counters (cudaMallocHost memory is device-mapped under UVA) and re-arm the state for the next render
         const uint32_t nstate = (uint32_t)nscantiles;
         CU(launch_chain(pdl, k_finish_render, dim3((unsigned)std::min<uint64_t>(std::max<uint64_t>((nstate + 255) / 256, 1), 64)), dim3(256), 0, st,
                         m->d_ctr, (volatile uint32_t *)m->h_ctr, kMeshCtr, m->d_scanstate, nstate, m->d_stamp, (volatile unsigned long long *)m->h_stamp, kMeshStamps));
@@ -300,8 +353,9 @@ int mesh_run_begin(gsdf_mesher *m) {
         size_t tri_cap;
         ProgView pv;
         unsigned flags;
-        int ext, tma, eval_p;
-        uint32_t quad_hint;
+        int ext, tma, eval_p, mc_mode;
+        uint32_t quad_hint, blk_hint;
+        const void *blk[2];
     } key;
     std::memset(&key, 0, sizeof key);
     const void *kp[10] = {m->d_grid, nullptr, m->d_mbits, m->d_list, m->d_seg, m->d_seglist, m->d_scanstate, m->d_tris, m->d_cases, m->d_segcases};
@@ -310,6 +364,8 @@ int mesh_run_begin(gsdf_mesher *m) {
     key.plan = m->plan; key.prog = p;
     key.tri_cap = m->tri_cap; key.pv = p->pv; key.flags = m->flags; key.ext = p->needs_ext ? 1 : 0; key.tma = (m->use_tma ? 1 : 0) | (m->tile5 ? 2 : 0);
     key.eval_p = eval_p; key.quad_hint = (prune && m->runs > 0) ? m->quad_hint : 0u;
+    key.mc_mode = m->mc_mode; key.blk_hint = (blockmc && m->runs > 0) ? m->blk_hint : 0u;
+    key.blk[0] = m->d_blklist; key.blk[1] = m->d_blkcnt;
     const bool use_graph = m->allow_graph && !(m->flags & GSDF_MESH_STAGE_TIMING) && emitted && m->runs > 0 && !scan3;
     if (use_graph) {
         if (!m->gexec || m->gkey.size() != sizeof key || std::memcmp(m->gkey.data(), &key, sizeof key) != 0) {
@@ -333,7 +389,7 @@ int mesh_run_begin(gsdf_mesher *m) {
         if ((rc = enqueue(true, m->scan_epoch))) return rc;
     }
     CU(cudaEventRecord(m->ev[4], st));
-    m->pending = true; m->pend_graph = use_graph; m->pend_emitted = emitted; m->pendA = A; m->pend_mcgrid = mcgrid;
+    m->pending = true; m->pend_graph = use_graph; m->pend_emitted = emitted; m->pendA = A; m->pend_mcgrid = mcgrid; m->pendB = BA; m->pend_blkgrid = blkgrid;
     return 0;
 }
 
@@ -364,7 +420,11 @@ int mesh_run_end(gsdf_mesher *m) {
         A.cases = nullptr;
         // k_finish_render re-armed the counters already: give the emit its segment-list length back, clear again after
         CU(cudaMemcpyAsync(m->d_ctr + 5, m->h_ctr + 5, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        if (m->use_tma && m->tile5) {
+        if (m->use_tma && m->mc_mode == 2 && prune) {
+            BlkArgs BE = m->pendB;
+            BE.tris = m->d_tris; BE.tri_capacity = m->tri_cap / 9; BE.cases = nullptr; BE.stamp = nullptr;
+            k_mc_blk_emit<<<m->pend_blkgrid, kBlkWarps * 32, 0, st>>>(m->tmapB, BE);
+        } else if (m->use_tma && m->tile5) {
             const uint64_t ntiles5 = (uint64_t)((D.nsx + 3) / 4) * ((D.ny + kTileY - 1) / kTileY) * ((D.cz1 - D.cz0 + kT5Layers - 1) / kT5Layers);
             A.stamp = nullptr;
             k_mc_emit5<<<grid_for(p->sms, ntiles5, 1, 8), 256, 0, st>>>(m->tmap5, A);
@@ -382,6 +442,9 @@ int mesh_run_end(gsdf_mesher *m) {
         m->evals = (uint64_t)m->h_ctr[7] + 4ull * m->h_ctr[0];  // prune-cube centres of every level + the listed lattice quads
         // hint for the next render's launch shape; rounded up so that small changes of the tree do not re-capture the graph
         m->quad_hint = (m->h_ctr[0] + 4095u) & ~4095u;
+    }
+    m->blk_hint = (m->h_ctr[5] + 1023u) & ~1023u;  // listed blocks (block kernels) of this render
+    if (prune) {
         m->pruned = (nblocks - m->h_ctr[4]) * 64ull;  // Cube.DecomposesTo(1) of a level-3 cube = 8^2
     } else {
         m->evals = (uint64_t)(D.nx + 1) * (D.ny + 1) * nk;
@@ -470,6 +533,11 @@ static int mesh_begin_prio(gsdf_program *p, const gsdf_lattice *lat, int cz0, in
     // 6 us faster than the one-layer-tile pass, its emit pass 25 us slower than the work-list emit (it classifies again, and
     // a warp walks its row's segments serially) -- kept for the record, not the default.
     m->tile5 = getenv("GSDF_MC_TILE5") != nullptr;
+    if (const char *mc = getenv("GSDF_MC")) {
+        if (!strcmp(mc, "v1")) m->mc_mode = 0;
+        else if (!strcmp(mc, "tile5")) { m->mc_mode = 1; m->tile5 = true; }
+        else m->mc_mode = 2;
+    } else if (m->tile5) m->mc_mode = 1;
     m->allow_graph = getenv("GSDF_NO_GRAPH") == nullptr;  // A/B switch: eager launches instead of the CUDA graph
     MeshDims &D = m->D;
     D.nx = lat->n[0]; D.ny = lat->n[1]; D.nz = lat->n[2];
@@ -638,6 +706,7 @@ void gsdf_mesh_destroy(gsdf_mesher *m) {
     if (m->prog && m->ev[4]) program_remove_dependent(m->prog, m->ev[4]);
     for (auto &b : m->d_lbits) cudaFree(b);
     cudaFree(m->d_grid); cudaFree(m->d_list); cudaFree(m->d_seg); cudaFree(m->d_seglist); cudaFree(m->d_segcases); cudaFree(m->d_scanstate); cudaFree(m->d_blocksum);
+    cudaFree(m->d_blklist); cudaFree(m->d_blkcnt);
     cudaFree(m->d_tris); cudaFree(m->d_cases); cudaFree(m->d_stl); cudaFree(m->d_ctr);
     if (m->h_ctr) cudaFreeHost(m->h_ctr);
     cudaFree(m->d_stamp);
