@@ -170,7 +170,7 @@ int validate_program(const gsdf_program_header &h, const uint32_t *chunks, size_
         case GSDF_OP_MIN: case GSDF_OP_MAX: case GSDF_OP_DIFF: case GSDF_OP_XOR: case GSDF_OP_SMOOTH_UNION: case GSDF_OP_SMOOTH_DIFF:
         case GSDF_OP_SMOOTH_INTERSECT: case GSDF_OP_ADD_BELOW: case GSDF_OP_EXTRUDE_EXIT: case GSDF_OP_MAX_BELOW:
             dd = -1; needd = 2; break;
-        case GSDF_OP_OFFSET: case GSDF_OP_ANNULUS: case GSDF_OP_MULDIST: case GSDF_OP_SHELL_EXIT: case GSDF_OP_BBOX_GUARD2D:
+        case GSDF_OP_OFFSET: case GSDF_OP_ANNULUS: case GSDF_OP_MULDIST: case GSDF_OP_SHELL_EXIT: case GSDF_OP_BBOX_GUARD2D: case GSDF_OP_MIN_CONST:
             needd = 1; break;
         case GSDF_OP_PUSH_POS: case GSDF_OP_CIRC_ENTER: dp = 1; break;
         case GSDF_OP_POP_POS: dp = -1; needp = 1; break;

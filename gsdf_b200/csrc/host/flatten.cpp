@@ -91,6 +91,10 @@ struct Emitter {
             for (int k = 0; k < n.nchild; k++) anchorsOf(b.child(n, k), out);
             return;
         case GSDF_N_DIFF2D: {  // max(a, -b) <= |p - v| for v on a's outline and outside b: keep a's anchors clear of b's box
+            // ... which is only sound when b's Bounds() really encloses b: an OverloadShader2DBounds wrapper or a primitive with
+            // a loose / cosmetic box could leave an anchor INSIDE the hole, where max(a, -b) > 0 and the upper bound would be
+            // too small. Same whitelist as the guards themselves; otherwise this operand contributes no anchors.
+            if (!boxBounded(b.child(n, 1))) return;
             std::vector<Vec2> a;
             anchorsOf(b.child(n, 0), a);
             const Box2 bb = b.Bounds2(b.child(n, 1));
@@ -314,6 +318,7 @@ struct Emitter {
                 if (!emit(b.child(n, 0), false, is2d)) return false;
                 if (v > 0) { op0(GSDF_OP_MIN); popD(); }
             }
+            opf(GSDF_OP_MIN_CONST, 1e20f);  // the reference's fold starts from largenum (gsdf.go:21, cpu_evaluators.go:364,932)
             popP();  // restores p (harmless when not needed)
             return true;
         }
@@ -416,6 +421,7 @@ struct Emitter {
                 if (!emit(b.child(n, 0), false, true)) return false;
                 if (k > 0) { op0(GSDF_OP_MIN); popD(); }
             }
+            opf(GSDF_OP_MIN_CONST, 3.40282346638528859811704183484516925440e+38f);  // math.MaxFloat32, cpu_evaluators.go:1172
             popP();
             return true;
         }

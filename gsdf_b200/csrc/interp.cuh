@@ -517,6 +517,10 @@ __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restri
 #pragma unroll
             for (int j = 0; j < P; j++) m.top[j] = absf(m.top[j]) - f2;
             break;
+        case GSDF_OP_MIN_CONST:  // cpu_evaluators.go:364,932,1172: the folds start from a constant
+#pragma unroll
+            for (int j = 0; j < P; j++) m.top[j] = minf(f2, m.top[j]);
+            break;
         case GSDF_OP_MULDIST:
 #pragma unroll
             for (int j = 0; j < P; j++) m.top[j] = m.top[j] * f2;

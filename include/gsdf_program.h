@@ -96,6 +96,8 @@ enum gsdf_opcode {
                             point of it lies outside the box and satisfies guard_dead(kind, w, top) (a point inside the box
                             never votes for the skip: the box says nothing about the operand's value there)
                             => jump to `target` (the operand's combiner, which then keeps `top`) */
+    GSDF_OP_MIN_CONST,   /* top = min(w2, top): the accumulator seed of the reference's array folds (largenum = 1e20,
+                            cpu_evaluators.go:364,932; math.MaxFloat32 in translateMulti2D, :1172) applied behind the fold */
     GSDF_OP__COUNT
 };
 

@@ -68,6 +68,9 @@ const (
 	OpExtrudeEnter
 	OpRevolve
 	OpScrewEnter
+	OpCullUB2D    // box guards: upper bound of a 2-D union from anchor points on the operands' outlines
+	OpBBoxGuard2D // box guards: skip the operand that follows when the tile is farther from its box than the running value
+	OpMinConst    // top = min(w2, top): accumulator seed of the array folds (largenum, math.MaxFloat32)
 )
 
 const (
@@ -195,6 +198,21 @@ func (p *Program) PushP() {
 	}
 }
 func (p *Program) PopP() { p.Op0(OpPopPos); p.P-- }
+// BoxGuard emits BBOX_GUARD2D for an operand whose bounding box (in the current frame) is [minx,miny]-[maxx,maxy] and returns
+// the chunk word index of its header for PatchBoxGuard (flatten.cpp: boxGuard / patchBoxGuard).
+func (p *Program) BoxGuard(kind uint32, margin, minx, miny, maxx, maxy float32) int {
+	hw := len(p.Chunks)
+	p.Header(OpBBoxGuard2D, 2, kind, 0, fbits(margin))
+	p.Chunk(minx, miny, maxx, maxy)
+	return hw
+}
+
+// PatchBoxGuard makes the guard jump to the chunk that comes next: the operand's combiner, which then keeps the running value.
+func (p *Program) PatchBoxGuard(hw int, kind uint32) { p.Chunks[hw+1] = kind | uint32(len(p.Chunks)/4)<<8 }
+
+// BoxGuardsOn mirrors the C++ flattener: box guards are emitted unless GSDF_NO_GUARDS is set.
+func BoxGuardsOn() bool { return !guardsOff }
+
 func (p *Program) AlignAux(n int) uint32 {
 	for len(p.Aux)%n != 0 {
 		p.Aux = append(p.Aux, 0)

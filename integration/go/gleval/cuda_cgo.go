@@ -28,6 +28,48 @@ func InitCUDA(device int) error {
 	return nil
 }
 
+// HostAlloc returns n float32 in page-locked host memory (gsdf_host_alloc): Evaluate and the renderers' read-backs move data
+// from / into such slices by DMA directly instead of through the library's staging buffers. Free with HostFree.
+func HostAlloc(n int) []float32 {
+	p := C.gsdf_host_alloc(C.size_t(4 * n))
+	if p == nil {
+		return nil
+	}
+	return unsafe.Slice((*float32)(p), n)
+}
+func HostFree(s []float32) {
+	if len(s) > 0 {
+		C.gsdf_host_free(unsafe.Pointer(&s[0]))
+	}
+}
+
+// createProgramOn uploads to an explicitly named device: goroutines migrate between OS threads, so the per-thread default
+// of gsdf_set_device is not something Go code should lean on when it drives several GPUs.
+func createProgramOn(device int, blob []byte, aux []float32) (*C.gsdf_program, error) {
+	var h *C.gsdf_program
+	var auxp *C.float
+	if len(aux) > 0 {
+		auxp = (*C.float)(unsafe.Pointer(&aux[0]))
+	}
+	if rc := C.gsdf_program_create_on(C.int(device), unsafe.Pointer(&blob[0]), C.size_t(len(blob)), auxp, C.size_t(len(aux)), &h); rc != 0 {
+		return nil, cudaErr()
+	}
+	return h, nil
+}
+
+// NewCUDASDF3On is NewCUDASDF3 on the given device.
+func NewCUDASDF3On(device int, root glbuild.Shader3D) (*SDF3CUDA, error) {
+	blob, aux, err := glbuild.Flatten3(root)
+	if err != nil {
+		return nil, err
+	}
+	h, err := createProgramOn(device, blob, aux)
+	if err != nil {
+		return nil, err
+	}
+	return &SDF3CUDA{h: h, bb: root.Bounds()}, nil
+}
+
 func createProgram(blob []byte, aux []float32) (*C.gsdf_program, error) {
 	var h *C.gsdf_program
 	var auxp *C.float

@@ -91,9 +91,125 @@ func (u *OpUnion) AppendProgram(p *glbuild.Program, restore bool) error {
 	return nil
 }
 
+// ---- 2-D box guards (include/gsdf_program.h, "box guards"; flatten.cpp boxBounded / anchorsOf / boxScale) ----
+
+// boxBounded: shapes whose Bounds() truly encloses them and whose value outside that box is >= the distance to it: exact
+// primitives, translations, unions of such, and differences of such (max(a, -b) >= a). Bounds overrides are NOT in the list:
+// glbuild.Unwrap is not applied here on purpose, an OverloadShader2DBounds box is cosmetic.
+func boxBounded(s glbuild.Shader2D) bool {
+	switch n := s.(type) {
+	case *poly2D, *circle2D, *rect2D:
+		return true
+	case *translate2D:
+		return boxBounded(n.s)
+	case *diff2D:
+		return boxBounded(n.s1)
+	case *OpUnion2D:
+		for _, c := range n.joined {
+			if !boxBounded(c) {
+				return false
+			}
+		}
+		return len(n.joined) > 0
+	}
+	return false
+}
+
+// anchorsOf appends points ON the outline of s in the current frame: the value of s at p is <= |p - v| for each of them.
+func anchorsOf(s glbuild.Shader2D, out []ms2.Vec) []ms2.Vec {
+	switch n := s.(type) {
+	case *poly2D:
+		return append(out, n.vert...)
+	case *circle2D:
+		return append(out, ms2.Vec{X: n.r}, ms2.Vec{X: -n.r}, ms2.Vec{Y: n.r}, ms2.Vec{Y: -n.r})
+	case *rect2D:
+		hx, hy := 0.5*n.d.X, 0.5*n.d.Y
+		return append(out, ms2.Vec{X: hx, Y: hy}, ms2.Vec{X: -hx, Y: hy}, ms2.Vec{X: hx, Y: -hy}, ms2.Vec{X: -hx, Y: -hy})
+	case *translate2D:
+		first := len(out)
+		out = anchorsOf(n.s, out)
+		for i := first; i < len(out); i++ {
+			out[i].X += n.p.X
+			out[i].Y += n.p.Y
+		}
+		return out
+	case *OpUnion2D: // min(a, b) <= each operand
+		for _, c := range n.joined {
+			out = anchorsOf(c, out)
+		}
+		return out
+	case *diff2D: // max(a, -b) <= |p - v| for v on a's outline and outside b: only when b's box really encloses b
+		if !boxBounded(n.s2) {
+			return out
+		}
+		bb := n.s2.Bounds()
+		for _, v := range anchorsOf(n.s1, nil) {
+			if v.X < bb.Min.X || v.X > bb.Max.X || v.Y < bb.Min.Y || v.Y > bb.Max.Y {
+				out = append(out, v)
+			}
+		}
+		return out
+	}
+	return out
+}
+
+func boxScale(bb ms2.Box) float32 {
+	return 1e-5 * math.Max(math.Max(math.Abs(bb.Min.X), math.Abs(bb.Max.X)), math.Max(math.Abs(bb.Min.Y), math.Abs(bb.Max.Y)))
+}
+
 func (u *OpUnion2D) AppendProgram(p *glbuild.Program, restore bool) error {
 	if len(u.joined) < 2 {
 		return errors.New("OpUnion2D must have at least 2 elements")
+	}
+	// Union of bounded shapes (what forge/textsdf builds): an upper bound U of the union from a few anchor points per
+	// operand, pushed as an extra operand of the min fold, then a box guard in front of every bounded operand
+	// (flatten.cpp, GSDF_N_UNION2D). min(U, d1..dn) == min(d1..dn) because U >= the operand that owns the nearest anchor.
+	if glbuild.BoxGuardsOn() && len(u.joined) >= 3 {
+		var anchors []ms2.Vec
+		nbounded := 0
+		for _, c := range u.joined {
+			a := anchorsOf(c, nil)
+			want := 8
+			if len(a) < want {
+				want = len(a)
+			}
+			for i := 0; i < want; i++ {
+				anchors = append(anchors, a[i*len(a)/want])
+			}
+			if boxBounded(c) {
+				nbounded++
+			}
+		}
+		if len(anchors) > 0 && nbounded >= 2 {
+			if len(anchors)%2 != 0 {
+				anchors = append(anchors, anchors[len(anchors)-1])
+			}
+			margin := boxScale(u.Bounds())
+			off := p.AlignAux(4)
+			for _, v := range anchors {
+				p.Aux = append(p.Aux, v.X, v.Y)
+			}
+			p.Header(glbuild.OpCullUB2D, 1, off, uint32(len(anchors)), fbits(margin))
+			p.PushD()
+			for k, c := range u.joined {
+				last := k == len(u.joined)-1
+				gd := boxBounded(c)
+				hw := 0
+				if gd {
+					bb := c.Bounds()
+					hw = p.BoxGuard(glbuild.GuardMin, margin, bb.Min.X, bb.Min.Y, bb.Max.X, bb.Max.Y)
+				}
+				if err := glbuild.Emit(p, c, restore || !last); err != nil {
+					return err
+				}
+				if gd {
+					p.PatchBoxGuard(hw, glbuild.GuardMin) // lands on this operand's MIN, which keeps the running minimum
+				}
+				p.Op0(glbuild.OpMin)
+				p.PopD()
+			}
+			return nil
+		}
 	}
 	for k := range u.joined {
 		last := k == len(u.joined)-1
@@ -113,7 +229,27 @@ func (u *diff) AppendProgram(p *glbuild.Program, r bool) error {
 }
 func (u *intersect) AppendProgram(p *glbuild.Program, r bool) error   { return p.Binary(u.s1, u.s2, r, func() { p.Op0(glbuild.OpMax) }) }
 func (u *xor) AppendProgram(p *glbuild.Program, r bool) error         { return p.Binary(u.s1, u.s2, r, func() { p.Op0(glbuild.OpXor) }) }
-func (u *diff2D) AppendProgram(p *glbuild.Program, r bool) error      { return p.Binary(u.s1, u.s2, r, func() { p.Op0(glbuild.OpDiff) }) }
+// diff2D: the subtrahend gets a box guard -- tiles that stay outside the hole never evaluate it (flatten.cpp, binary()).
+func (u *diff2D) AppendProgram(p *glbuild.Program, r bool) error {
+	if err := glbuild.Emit(p, u.s1, true); err != nil {
+		return err
+	}
+	bguard := glbuild.BoxGuardsOn() && boxBounded(u.s2)
+	hw := 0
+	if bguard {
+		bb := u.s2.Bounds()
+		hw = p.BoxGuard(glbuild.GuardDiff, boxScale(bb), bb.Min.X, bb.Min.Y, bb.Max.X, bb.Max.Y)
+	}
+	if err := glbuild.Emit(p, u.s2, r); err != nil {
+		return err
+	}
+	if bguard {
+		p.PatchBoxGuard(hw, glbuild.GuardDiff) // lands on the DIFF op, which keeps `a`
+	}
+	p.Op0(glbuild.OpDiff)
+	p.PopD()
+	return nil
+}
 func (u *intersect2D) AppendProgram(p *glbuild.Program, r bool) error { return p.Binary(u.s1, u.s2, r, func() { p.Op0(glbuild.OpMax) }) }
 func (u *xor2D) AppendProgram(p *glbuild.Program, r bool) error       { return p.Binary(u.s1, u.s2, r, func() { p.Op0(glbuild.OpXor) }) }
 func (u *smoothUnion) AppendProgram(p *glbuild.Program, r bool) error {
@@ -219,6 +355,7 @@ func (u *array) AppendProgram(p *glbuild.Program, _ bool) error {
 			p.PopD()
 		}
 	}
+	p.Opf(glbuild.OpMinConst, largenum, 0) // the fold starts from largenum (cpu_evaluators.go:364)
 	p.PopP()
 	return nil
 }
@@ -238,6 +375,7 @@ func (u *array2D) AppendProgram(p *glbuild.Program, _ bool) error {
 			p.PopD()
 		}
 	}
+	p.Opf(glbuild.OpMinConst, largenum, 0) // cpu_evaluators.go:932
 	p.PopP()
 	return nil
 }
@@ -401,6 +539,7 @@ func (u *translateMulti2D) AppendProgram(p *glbuild.Program, _ bool) error {
 			p.PopD()
 		}
 	}
+	p.Opf(glbuild.OpMinConst, math.MaxFloat32, 0) // cpu_evaluators.go:1172
 	p.PopP()
 	return nil
 }

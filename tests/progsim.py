@@ -19,7 +19,7 @@ TILE = 2048  # points per CTA tile on the device (512 threads x 4 points): the g
 OPS = """END SPHERE BOX BOXFRAME TORUS CYLINDER HEX CIRCLE2D RECT2D LINE2D LINES2D ARC2D EQTRI2D HEX2D OCT2D DIAMOND2D ROUNDX2D
 POLY2D ELLIPSE2D BEZIERQ2D MIN MAX DIFF XOR SMOOTH_UNION SMOOTH_DIFF SMOOTH_INTERSECT OFFSET ANNULUS MULDIST SHELL_EXIT ADD_BELOW
 EXTRUDE_EXIT MAX_BELOW PUSH_POS POP_POS PEEK_POS TRANSLATE SCALE_POS SYMMETRY TRANSFORM ROTATE2D TWIST ELONGATE ELONGATE2D
-ARRAY_VAR ARRAY2D_VAR CIRC_ENTER EXTRUDE_ENTER REVOLVE SCREW_ENTER CULL_UB2D BBOX_GUARD2D""".split()
+ARRAY_VAR ARRAY2D_VAR CIRC_ENTER EXTRUDE_ENTER REVOLVE SCREW_ENTER CULL_UB2D BBOX_GUARD2D MIN_CONST""".split()
 OP = {name: i for i, name in enumerate(OPS)}
 GUARD_DIFF, GUARD_MIN, GUARD_SMOOTH_UNION = 1, 2, 3
 RXY_READ, RXY_WRITE = 0x100, 0x200  # experimental radius reuse (include/gsdf_program.h)
@@ -381,6 +381,8 @@ def _run_tile(P, pos, M, stats):
             top = top + f2
         elif name == "ANNULUS":
             top = np.abs(top) - f2
+        elif name == "MIN_CONST":
+            top = np.minimum(F(f2), top)
         elif name == "MULDIST":
             top = top * f2
         elif name == "SHELL_EXIT":

@@ -42,9 +42,8 @@ def test_go_opcodes_follow_the_c_enum():
     go_ops = re.findall(r"^\s*(Op\w+)", block, flags=re.M)
     assert go_ops[0] == "OpEnd" and len(go_ops) >= 50
     norm = lambda s: s.replace("GSDF_OP_", "").replace("_", "").lower()
-    # the Go list is a prefix of the C enum (the 2-D box-guard ops at its end are only emitted by the C++ flattener)
-    assert [g[2:].lower() for g in go_ops] == [norm(c) for c in c_ops[:len(go_ops)]]
-    assert {norm(c) for c in c_ops[len(go_ops):]} <= {"cullub2d", "bboxguard2d"}
+    # the Go list IS the C enum (box guards and the fold seed included: the Go flattener emits them like the C++ one)
+    assert [g[2:].lower() for g in go_ops] == [norm(c) for c in c_ops]
     # guard kinds, magic, version
     kinds = re.search(r"enum gsdf_guard_kind \{([^}]*)\}", hdr).group(1)
     kinds = [k.split("=")[0].strip() for k in kinds.split(",")]
@@ -122,6 +121,44 @@ def test_every_reference_node_type_has_an_emitter_reading_real_fields():
         assert typ in structs, typ
         for used in set(re.findall(r"\b%s\.(\w+)" % recv, chunk)):
             assert used in all_fields(typ) or (typ, used) in methods, (typ, used)
+
+
+def test_go_emitters_use_the_opcodes_the_cpp_flattener_uses_per_node_type():
+    """Every node type: the opcodes its Go AppendProgram emits are the opcodes its case in flatten.cpp emits (helpers that
+    exist on both sides -- position push / pop, box-guard emission -- hide the same ops on both sides). Catches an emitter
+    that forgets an exit op, a guard or the fold seed, or uses another combiner than the executable specification."""
+    go = read(GO, "gsdf", "cuda_flatten.go") + read(GO, "forge", "threads", "cuda_flatten.go")
+    cpp = read(ROOT, "gsdf_b200", "csrc", "host", "flatten.cpp")
+    circ = re.findall(r"glbuild\.Op(\w+)", go[go.index("func circ("):go.index("func (u *circarray) AppendProgram")])
+    gops = {}
+    for chunk in re.split(r"\n(?=func )", go):
+        m = re.match(r"func \((\w+) \*(\w+)\) AppendProgram\(", chunk)
+        if not m:
+            continue
+        ops = re.findall(r"glbuild\.Op(\w+)", chunk) + (circ if "circ(p" in chunk else [])
+        gops[m.group(2).lower()] = {o.lower() for o in ops}
+    body = cpp[cpp.index("bool emit(NodeId id"):cpp.index("// Radius reuse")]
+    cases = list(re.finditer(r"((?:\s*case GSDF_N_\w+:)+)", body))
+    cops = {}
+    for i, m in enumerate(cases):
+        blk = body[m.end(): cases[i + 1].start() if i + 1 < len(cases) else len(body)]
+        ops = {o.lower().replace("_", "") for o in re.findall(r"GSDF_OP_(\w+)", blk)}
+        for k in re.findall(r"GSDF_N_(\w+)", m.group(1)):
+            cops[k.lower().replace("_", "")] = ops
+    alias = {"opunion": "union", "opunion2d": "union2d", "diamond": "diamond2d", "equilateraltri2d": "eqtri2d", "extrusion": "extrude",
+             "quadbezier2d": "bezierq2d", "revolution": "revolve", "rotation2d": "rotate2d", "x2d": "roundx2d"}
+    checked = 0
+    for typ, ops in gops.items():
+        kind = alias.get(typ, typ)
+        assert kind in cops, typ
+        want = set(cops[kind])
+        if kind in ("array", "array2d"):          # one C++ case serves both node kinds
+            want -= {"array2dvar"} if kind == "array" else {"arrayvar"}
+        if kind in ("union", "union2d"):          # likewise: the 2-D box-guard ops sit in the shared union case
+            want -= {"cullub2d"} if kind == "union" else set()
+        assert ops == want, (typ, sorted(ops ^ want))
+        checked += 1
+    assert checked >= 50
 
 
 def test_cgo_calls_pass_as_many_arguments_as_the_prototypes_take():

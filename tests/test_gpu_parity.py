@@ -71,6 +71,17 @@ def test_nan_propagation_of_min_max_matches_go_on_gpu(oracle, bld):
     assert nans > 100   # the inputs do exercise the NaN paths
 
 
+def test_array_folds_start_from_the_reference_seed_on_gpu(oracle, bld):
+    """largenum (1e20) / math.MaxFloat32 as the first operand of the array folds (cpu_evaluators.go:364,932,1172): GSDF_OP_MIN_CONST."""
+    from test_host_interp import array_far_cases
+    for name, s, pos in array_far_cases(bld):
+        t = oracle.Tree.from_shader(s)
+        want = t.eval2(pos) if s.is2d else t.eval3(pos)
+        got, _ = gpu_eval(s, pos)
+        diff = (bits(got) != bits(want)) & ~(np.isnan(got) & np.isnan(want))
+        assert not diff.any(), (name, got, want)
+
+
 @pytest.mark.parametrize("dim", [3, 2])
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_random_trees_bit_identical(oracle, bld, seed, dim):

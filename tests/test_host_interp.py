@@ -153,3 +153,24 @@ def test_nan_propagation_of_min_max_matches_go(oracle, bld):
     for dim in (3, 2):
         for name, s in shapes.random_trees(bld, 5, 30, dim):
             check(oracle, bld, name + "/far", s, far_and_nan_points(s))
+
+
+def array_far_cases(bld):
+    """Array / Array2D / TranslateMulti2D evaluated so far away that the child's distance exceeds the reference's fold seeds
+    (largenum = 1e20, gsdf.go:21; math.MaxFloat32 in translateMulti2D): the result is the seed, not the distance."""
+    f = np.float32
+    a3 = bld.Array(bld.NewSphere(0.4), 1.0, 1.2, 0.9, 3, 2, 2)
+    a2 = bld.Array2D(bld.NewCircle(0.3), 1.0, 0.8, 3, 2)
+    tm = bld.TranslateMulti2D(bld.NewCircle(0.3), np.array([[0, 0], [1, 0.5], [2, -0.25]], f))
+    big3 = np.array([[1e22, 0, 0], [0, -3e24, 1e21], [5e19, 5e19, 5e19], [1e19, 0, 0], [0.3, 0.2, 0.1]], f)
+    big2 = np.array([[1e22, 0], [0, -3e24], [9e19, 9e19], [1e19, 0], [0.3, 0.2], [3e38, 3e38]], f)
+    return [("array/far", a3, big3), ("array2d/far", a2, big2), ("translatemulti2d/far", tm, big2)]
+
+
+def test_array_folds_start_from_the_reference_seed(oracle, bld):
+    for name, s, pos in array_far_cases(bld):
+        check(oracle, bld, name, s, pos)
+        t = oracle.Tree.from_shader(s)
+        want = t.eval2(pos) if s.is2d else t.eval3(pos)
+        if "translatemulti" not in name:
+            assert want[0] == np.float32(1e20)   # the seed shows
