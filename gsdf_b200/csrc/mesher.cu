@@ -195,7 +195,10 @@ int mesh_run_begin(gsdf_mesher *m) {
     BA.overflow = A.overflow;
     // persistent grid of the block kernels: one warp per kept block, sized from the previous render's count when there is one
     const uint64_t blk_bound = m->runs > 0 ? std::min<uint64_t>(nblocks_slab, 2 * (uint64_t)m->blk_hint + 256) : nblocks_slab;
-    const unsigned blkgrid = grid_for(p->sms, blk_bound, kBlkWarps, 8);
+    // test knob: cap the grid so that on small, oracle-checked lattices every warp walks many blocks through both stencil buffers
+    static const unsigned blk_grid_cap = getenv("GSDF_BLK_GRID") ? (unsigned)std::max(1, atoi(getenv("GSDF_BLK_GRID"))) : 0u;
+    unsigned blkgrid = grid_for(p->sms, blk_bound, kBlkWarps, 8);
+    if (blk_grid_cap) blkgrid = std::min(blkgrid, blk_grid_cap);
     const unsigned mcgrid = grid_for(p->sms, nrows * (uint64_t)((D.nsx + 3) / 4), kThreads / 32, 16);
     if (m->use_tma && m->tmap_grid != m->d_grid) {  // (re)describe the lattice buffer: pitch x (ny+1) x nk floats
         if ((rc = make_grid_tensor_map(&m->tmap, m->d_grid, D.pitch, D.ny + 1, nk, kBoxZ))) return rc;

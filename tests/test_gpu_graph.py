@@ -196,14 +196,17 @@ def test_programmatic_dependent_launch_is_bit_identical():
         assert r.returncode == 0 and "PDL CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("cap", ["3", "37"])
-def test_count_kernel_tile_loop_matches_oracle(cap):
-    """On the small lattices the oracle can mesh, the classification kernel's default grid gives every CTA one tile, so
-    its tile loop (mbarrier phase flips, stencil buffer reuse, kept and pruned tiles in any order) would only be checked
-    against known triangle COUNTS at full size. The child caps the grid (GSDF_COUNT_GRID, read once per process): each
-    CTA then walks tens of tiles, and cases and triangles are compared with the oracle (tests/count_pipeline_child.py)."""
+@pytest.mark.parametrize("knobs", [{"GSDF_BLK_GRID": "1"}, {"GSDF_BLK_GRID": "5"}, {"GSDF_MC": "v1", "GSDF_COUNT_GRID": "3"},
+                                   {"GSDF_MC": "v1", "GSDF_COUNT_GRID": "37"}, {"GSDF_MC": "tile5"}, {"GSDF_EVAL_P": "1"}, {"GSDF_RXY": "0"}],
+                         ids=lambda k: "+".join("%s=%s" % kv for kv in k.items()))
+def test_marching_cubes_kernel_variants_match_oracle(knobs):
+    """Every marching-cubes kernel family, in a child process with its A/B knob set (the knobs are read once per process):
+    the kept-block kernels (default) with the grid capped to 1 and 5 CTAs, so that every warp walks tens of blocks through both
+    stencil buffers and mbarrier phases; the one-layer-tile pair with a capped grid (tile loop, stencil reuse, kept and pruned
+    tiles in any order); the 4-layer-tile pair; one-corner-per-thread lattice evaluation; programs without radius-reuse flags.
+    Cases and triangles are compared with the oracle, eager, graph capture and graph replay (tests/count_pipeline_child.py)."""
     import os, subprocess, sys
     here = os.path.dirname(os.path.abspath(__file__))
-    env = dict(os.environ, GSDF_COUNT_GRID=cap)
+    env = dict(os.environ, **knobs)
     r = subprocess.run([sys.executable, os.path.join(here, "count_pipeline_child.py")], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "COUNT PIPELINE OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
