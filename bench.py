@@ -287,6 +287,15 @@ def run_cuda(args, rank, local_rank, world):
         host = glrender.pinned_empty((ntri + 8, 3, 3))
         ref_tris = None
         table = {}
+        # the e2e steps run on every GPU of the box from this process: flush the L2 of each of them between steps
+        flushes = [flush] + [torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % i) for i in range(1, world)]
+
+        def l2_flush_all():
+            for i, f in enumerate(flushes):
+                f.fill_(1)
+            for i in range(world):
+                torch.cuda.synchronize(i)
+
         for spd in ((1, 3, 4) if world == 1 else (1, 2)):
             M = glrender.MultiRenderer(s, res, devices=list(range(world)), slabs_per_device=spd)
             assert M.NumTriangles() == ntri
@@ -298,10 +307,10 @@ def run_cuda(args, rank, local_rank, world):
                 return M.RenderToHost(host)      # render + device -> host: every triangle, slab order, one buffer
 
             for _ in range(warm):
-                l2_flush(); step()
+                l2_flush_all(); step()
             times = []
             for _ in range(args.steps):
-                l2_flush()
+                l2_flush_all()
                 host[:8] = 0
                 t0 = time.perf_counter()
                 got = step()
@@ -311,7 +320,10 @@ def run_cuda(args, rank, local_rank, world):
                 ref_tris = glrender.Octree(sdf, res).AllTriangles()
             assert np.array_equal(host[:ntri].view(np.uint32), ref_tris.view(np.uint32)), "multi-slab output differs from the single renderer"
             nsl = len(M.Slabs()[1])
-            table["slabs_per_device_%d" % spd] = {"ms_per_step": sum(times) / len(times) * 1e3, "slabs": nsl, "device_ms": M.DeviceMs()}
+            tl = M.Timeline()   # host-clock microseconds of the LAST timed step: slabs enqueued, per slab (count seen, copy enqueued), delivered
+            table["slabs_per_device_%d" % spd] = {"ms_per_step": sum(times) / len(times) * 1e3, "slabs": nsl, "device_ms": M.DeviceMs(), "cuts": M.Slabs()[0],
+                                                  "last_step_timeline_us": {"enqueued": round(tl["enqueued"], 1), "slabs": [[round(a, 1), round(c, 1)] for a, c in tl["slabs"]],
+                                                                            "delivered": round(tl["delivered"], 1)}}
             e2e_launches = max(e2e_launches, nsl * kernels_per_step)
             M.Close()
         best = min(table, key=lambda k: table[k]["ms_per_step"])
@@ -453,7 +465,8 @@ def bench_evaluate(sdf, s, glrender, torch):
                                            "pcie_roofline_frac": (n * 12 / sec / 1e9) / h2d_gbs}
     out["h2d_peak_GBps_measured"] = h2d_gbs
     out["bytes_per_eval"] = {"h2d": 12, "d2h": 4}
-    out["path"] = "gsdf_eval3 on host memory: chunks of 256 Ki points rotate through three streams (copy in, k_eval_stream, copy out)"
+    out["path"] = ("gsdf_eval3 on host memory: chunks of 256 Ki points rotate through three streams (copy in, k_eval_stream, copy out); pageable "
+                   "batches of 8 chunks or more are dealt to up to four host threads, each with its own three streams and pinned staging")
     return out
 
 

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 
 #include "internal.cuh"
 
@@ -346,7 +347,7 @@ void gsdf_program_destroy(gsdf_program *p) {
     cudaSetDevice(p->device);
     if (p->stream) (void)program_quiesce(p);
     for (const auto &d : p->deps) if (d.ref) *d.ref = nullptr;  // renderers that outlive their program fail cleanly instead of dangling
-    for (auto &s : p->slot) {
+    for (auto &lane : p->slot) for (auto &s : lane) {
         if (s.st) cudaStreamDestroy(s.st);
         if (s.done) cudaEventDestroy(s.done);
         if (s.h_pos) cudaFreeHost(s.h_pos);
@@ -430,34 +431,30 @@ static bool is_pinned(const void *ptr) {
 // gleval.SDF3.Evaluate on host slices, pipelined. Chunk i travels host -> device, through the kernel and device -> host on
 // slot stream i % 3; the three slots overlap one another, so in steady state the PCIe link carries the next chunk in and
 // the previous chunk out while the SMs interpret the current one. Pinned caller memory is the DMA source / target itself;
-// other memory goes through the slot's pinned staging (the calling thread copies chunk i+1 in while chunk i is in flight).
-static int eval_host(gsdf_program *p, const float *pos, float *dist, size_t n, int dim) {
-    if (!p || !pos || !dist) return fail(GSDF_EINVAL, "gsdf_eval: NULL argument");
-    if (p->dim != dim) return fail(GSDF_EINVAL, "program is %dD, called as %dD", p->dim, dim);
-    if (n == 0) return fail(GSDF_EEMPTY, "empty buffers");
+// other memory (a Go slice, a numpy array) goes through the slot's pinned staging, and because one host thread copies at
+// ~8 GB/s while the link moves ~55 GB/s, large pageable batches are dealt to up to four lanes -- host threads that live for
+// the call, each with its own three slots, each running the same pipeline over every fourth chunk.
+constexpr int kEvalLanes = 4;
+
+// chunks c = first, first + stride, ... of the batch through the three slots of one lane
+static int eval_host_lane(gsdf_program *p, gsdf_program::EvalSlot *slots, const float *pos, float *dist, size_t n, int dim, size_t chunk,
+                          size_t first, size_t stride, bool pin_in, bool pin_out) {
     CU(use_device(p->device));
-    const char *ce = getenv("GSDF_EVAL_CHUNK");  // test / tuning knob (read per call: a call costs microseconds at least)
-    const size_t chunk_env = ce ? (size_t)atoll(ce) : 0;
-    // chunks of 256 Ki points (3 MB in, 1 MB out): long enough for the link to stream, short enough that ramp-up and
-    // drain of the pipeline stay small; a batch smaller than two chunks goes as one
-    size_t chunk = chunk_env ? chunk_env : (size_t)256 << 10;
-    chunk = std::max<size_t>((chunk + 2047) & ~(size_t)2047, 2048);  // whole tiles of the streaming kernel
-    if (n < 2 * chunk) chunk = n;
-    const bool pin_in = is_pinned(pos), pin_out = is_pinned(dist);
     const size_t nchunks = (n + chunk - 1) / chunk;
     struct Pending { size_t off = 0, cnt = 0; bool live = false; } pend[3];
     int rc = 0;
     auto drain = [&](int s) -> int {  // wait for the slot's previous chunk and hand its distances to the caller
-        gsdf_program::EvalSlot &S = p->slot[s];
+        gsdf_program::EvalSlot &S = slots[s];
         if (!pend[s].live) return 0;
         CU(cudaEventSynchronize(S.done));
         if (!pin_out) std::memcpy(dist + pend[s].off, S.h_dist, pend[s].cnt * sizeof(float));
         pend[s].live = false;
         return 0;
     };
-    for (size_t c = 0; c < nchunks && !rc; c++) {
-        const int s = (int)(c % 3);
-        gsdf_program::EvalSlot &S = p->slot[s];
+    size_t k = 0;
+    for (size_t c = first; c < nchunks && !rc; c += stride, k++) {
+        const int s = (int)(k % 3);
+        gsdf_program::EvalSlot &S = slots[s];
         if ((rc = drain(s))) break;
         const size_t off = c * chunk, cnt = std::min(chunk, n - off);
         if (!S.st) {
@@ -484,15 +481,54 @@ static int eval_host(gsdf_program *p, const float *pos, float *dist, size_t n, i
         CU(cudaEventRecord(S.done, S.st));
         pend[s].off = off; pend[s].cnt = cnt; pend[s].live = true;
     }
-    for (size_t k = 0; k < 3; k++) {  // oldest first
-        const int s = (int)((nchunks + k) % 3);
+    for (size_t j = 0; j < 3; j++) {  // oldest first
+        const int s = (int)((k + j) % 3);
         const int drc = drain(s);
         if (!rc) rc = drc;
     }
-    if (rc) {
-        for (auto &S : p->slot) if (S.st) cudaStreamSynchronize(S.st);
-        return rc;
+    if (rc)
+        for (int s = 0; s < 3; s++) if (slots[s].st) cudaStreamSynchronize(slots[s].st);
+    return rc;
+}
+
+static int eval_host(gsdf_program *p, const float *pos, float *dist, size_t n, int dim) {
+    if (!p || !pos || !dist) return fail(GSDF_EINVAL, "gsdf_eval: NULL argument");
+    if (p->dim != dim) return fail(GSDF_EINVAL, "program is %dD, called as %dD", p->dim, dim);
+    if (n == 0) return fail(GSDF_EEMPTY, "empty buffers");
+    CU(use_device(p->device));
+    const char *ce = getenv("GSDF_EVAL_CHUNK");  // test / tuning knobs (read per call: a call costs microseconds at least)
+    const size_t chunk_env = ce ? (size_t)atoll(ce) : 0;
+    const char *le = getenv("GSDF_EVAL_LANES");
+    // chunks of 256 Ki points (3 MB in, 1 MB out): long enough for the link to stream, short enough that ramp-up and
+    // drain of the pipeline stay small; a batch smaller than two chunks goes as one
+    size_t chunk = chunk_env ? chunk_env : (size_t)256 << 10;
+    chunk = std::max<size_t>((chunk + 2047) & ~(size_t)2047, 2048);  // whole tiles of the streaming kernel
+    if (n < 2 * chunk) chunk = n;
+    const bool pin_in = is_pinned(pos), pin_out = is_pinned(dist);
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    int lanes = 1;
+    if (!(pin_in && pin_out) && nchunks >= 8) lanes = (int)std::min<size_t>(kEvalLanes, nchunks / 2);  // host copies are the bottleneck
+    if (le) lanes = std::max(1, std::min(kEvalLanes, atoi(le)));
+    lanes = (int)std::min<size_t>((size_t)lanes, nchunks);
+    int rc = 0;
+    if (lanes <= 1) {
+        rc = eval_host_lane(p, p->slot[0], pos, dist, n, dim, chunk, 0, 1, pin_in, pin_out);
+    } else {
+        int lrc[kEvalLanes] = {0, 0, 0, 0};
+        std::string lerr[kEvalLanes];
+        std::vector<std::thread> th;
+        for (int l = 1; l < lanes; l++)
+            th.emplace_back([&, l] {
+                lrc[l] = eval_host_lane(p, p->slot[l], pos, dist, n, dim, chunk, (size_t)l, (size_t)lanes, pin_in, pin_out);
+                if (lrc[l]) lerr[l] = g_err;  // the message lives in this thread's error slot
+            });
+        lrc[0] = eval_host_lane(p, p->slot[0], pos, dist, n, dim, chunk, 0, (size_t)lanes, pin_in, pin_out);
+        for (auto &t : th) t.join();
+        rc = lrc[0];
+        for (int l = 1; l < lanes && !rc; l++)
+            if (lrc[l]) rc = fail(lrc[l], "%s", lerr[l].c_str());
     }
+    if (rc) return rc;
     p->evals += n;
     return 0;
 }

@@ -133,7 +133,7 @@ struct gsdf_program {
         size_t cap = 0;  // points
         cudaStream_t st = nullptr;
         cudaEvent_t done = nullptr;
-    } slot[3];
+    } slot[4][3];   // [lane][slot]: up to four host threads, three chunks in flight each
 };
 
 namespace gsdfi {

@@ -245,12 +245,14 @@ def test_device_pointer_from_another_gpu_is_rejected(bld):
 
 # ---------------------------------------------------------------------------------------------- pipelined host Evaluate
 @pytest.mark.gpu
-@pytest.mark.parametrize("chunk", [0, 2048, 6144])
-def test_host_evaluate_is_chunked_and_exact(oracle, bld, monkeypatch, chunk):
-    """gsdf_eval3 / gsdf_eval2 on host slices: three rotating chunks in flight; ragged sizes, pinned and pageable buffers,
-    sizes below / at / above the chunk size all equal the oracle."""
+@pytest.mark.parametrize("chunk,lanes", [(0, 0), (2048, 0), (6144, 0), (2048, 3), (4096, 4)])
+def test_host_evaluate_is_chunked_and_exact(oracle, bld, monkeypatch, chunk, lanes):
+    """gsdf_eval3 / gsdf_eval2 on host slices: three rotating chunks in flight per lane, up to four lanes (host threads) for
+    pageable memory; ragged sizes, pinned and pageable buffers, sizes below / at / above the chunk size all equal the oracle."""
     if chunk:
         monkeypatch.setenv("GSDF_EVAL_CHUNK", str(chunk))
+    if lanes:
+        monkeypatch.setenv("GSDF_EVAL_LANES", str(lanes))
     import importlib
     rng = np.random.default_rng(11)
     s3 = gsdf.scene(bld, "bolt")
