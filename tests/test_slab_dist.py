@@ -54,9 +54,24 @@ def _worker(rank, world, port, out_path):
         mine, _ = O.flat_march(lat, grid, blockmask=mask, cz_range=(cz0, cz1))
         total = S.total_count(len(mine))
         allt = S.gather_triangles(mine, dst=0)
+        # bench.py's set-up step: every rank contributes the cost of its slab (here: its triangle count), all ranks derive the
+        # same re-balanced cuts from the gathered costs, and the re-cut slabs still concatenate to the whole mesh
+        import torch
+        cost = torch.zeros(world, dtype=torch.float64)
+        cost[rank] = len(mine)
+        dist.all_reduce(cost)
+        cuts = S.slab_cuts(lat.n[2], world)
+        new = S.rebalance_cuts(cuts, [float(v) for v in cost.tolist()])
+        mine2, _ = O.flat_march(lat, grid, blockmask=mask, cz_range=(new[rank], new[rank + 1]))
+        allt2 = S.gather_triangles(mine2, dst=0)
+        counts = torch.zeros(world, dtype=torch.float64)
+        counts[rank] = len(mine2)
+        dist.all_reduce(counts)
         if rank == 0:
             whole, _ = O.flat_march(lat, grid, blockmask=mask)
             ok = total == len(whole) and allt.shape == whole.shape and np.array_equal(allt.view(np.uint32), whole.view(np.uint32))
+            ok = ok and allt2.shape == whole.shape and np.array_equal(allt2.view(np.uint32), whole.view(np.uint32))
+            ok = ok and new[0] == 0 and new[-1] == lat.n[2] and float(counts.max()) <= float(cost.max())   # no worse balanced than before
             with open(out_path, "w") as f:
                 f.write("ok %d %d" % (total, len(whole)) if ok else "mismatch %d %d" % (total, len(whole)))
         else:
