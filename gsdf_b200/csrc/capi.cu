@@ -623,7 +623,7 @@ static int image_run(gsdf_program *p, const float bbmin[2], const float bbmax[2]
     g.rgba = color ? reinterpret_cast<uint32_t *>(target) : nullptr;
     g.cc.kind = GSDF_CONV_DEFAULT;
     if (conv) { g.cc.kind = conv->kind; for (int i = 0; i < 7; i++) g.cc.p[i] = conv->p[i]; g.cc.c0 = conv->c0; g.cc.c1 = conv->c1; }
-    rc = launch_image(p, g, (uint64_t)((((w + 3) / 4) + 31) / 32) * ((h + 15) / 16) * 512u, st, nullptr);
+    rc = launch_image(p, g, GenImage::items_for(w, h), st, nullptr);
     if (rc) return rc;
     p->evals += n;
     if (d_out) return note_user_stream(p, st);

@@ -1,6 +1,6 @@
 // eval_kernels.cuh -- the interpreter kernels (compiled once, in eval.cu).
 //
-//   k_eval<P,Gen>      persistent CTAs pull 512-item tiles from an atomic counter; each thread interprets the node
+//   k_eval<P,Gen>      persistent CTAs pull kEvalThreads-item tiles from an atomic counter; each thread interprets the node
 //                      program at P points produced by a generator functor (AoS point lists, the dense lattice, a
 //                      compacted quad list, prune-cube centres, image rows) and hands the distances to its sink.
 //   k_eval_stream      gleval.SDF3.Evaluate on device-resident point lists, bulk-async double-buffered position tiles.
@@ -14,7 +14,7 @@
 namespace gsdfk {
 
 template <int P, class Gen, bool EXT>
-__global__ void __launch_bounds__(kEvalThreads) k_eval(ProgView pv, Gen gen) {
+__global__ void __launch_bounds__(kEvalThreads, GSDF_EVAL_MINB) k_eval(ProgView pv, Gen gen) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t stage = smem_stage_bytes(pv);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + stage);
@@ -31,11 +31,18 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval(ProgView pv, Gen gen) {
     pdl_wait();
     stage_stamp(pv.stamp);
     const uint64_t nwork = gen.work_items();
-    for (;;) {
-        if (threadIdx.x == 0) *s_tile = atomicAdd(pv.sched, 1u);
-        __syncthreads();
-        const uint64_t w = (uint64_t)(*s_tile) * blockDim.x + threadIdx.x;
-        __syncthreads();
+    // the first tile of a CTA is its own index (no round trip to the counter: thin slabs are one tile per CTA and latency
+    // bound); further tiles come from the launch's scheduler counter, offset by the grid size
+    for (bool first = true;; first = false) {
+        uint64_t w;
+        if (first) {
+            w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        } else {
+            if (threadIdx.x == 0) *s_tile = gridDim.x + atomicAdd(pv.sched, 1u);
+            __syncthreads();
+            w = (uint64_t)(*s_tile) * blockDim.x + threadIdx.x;
+            __syncthreads();
+        }
         if (w - threadIdx.x >= nwork) break;
         if constexpr (Gen::kTileSkip) {  // generator-level CTA-uniform skip of a whole tile (GenDC: cubes outside this rank's region)
             if (__syncthreads_and(gen.dead(w < nwork ? w : nwork - 1))) {

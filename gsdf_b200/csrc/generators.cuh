@@ -15,13 +15,20 @@ namespace gsdfk {
 #define GSDF_THREADS 256
 #endif
 constexpr int kThreads = GSDF_THREADS;   // CTA size of the MC / scan / STL kernels and default of k_eval
-// Measured on B200 (scripts/ab_eval.py): 512-thread CTAs whose warps are kept on the same opcode body by a barrier
-// per instruction (GSDF_LOCKSTEP) cut instruction-fetch stalls: -13 % (flange) / -14 % (knurled) evaluate time
-// versus free-running 256-thread CTAs.
+// Measured on B200 (scripts/ab_eval.py): CTAs whose warps are kept on the same opcode body by a barrier per instruction
+// (GSDF_LOCKSTEP) cut instruction-fetch stalls: -13 % (flange) / -14 % (knurled) evaluate time versus free-running
+// 256-thread CTAs. CTA size (scripts/gpu_r2_ab_cta.sh, graph replays, flange@400 / bolt@400 / knurled@500 evaluate time):
+// 512 threads x 2 CTAs per SM (64 registers) 77 / 77 / 449 us; 384 x 3 (56 registers, no spill: 36 warps per SM and three
+// independent lockstep convoys) 70 / 72 / 442 us; 256 x 4 69 / 66 / 470; 128 x 8 67 / 63 / 508 (more convoys, but the
+// many-opcode knurled tree thrashes the instruction cache); register caps that spill (48, 40) lose everywhere.
 #ifndef GSDF_EVAL_THREADS
-#define GSDF_EVAL_THREADS 512
+#define GSDF_EVAL_THREADS 384
 #endif
 constexpr int kEvalThreads = GSDF_EVAL_THREADS;  // CTA size of the interpreter kernel
+#ifndef GSDF_EVAL_MINB
+#define GSDF_EVAL_MINB 3  // resident CTAs per SM the interpreter kernel is compiled for (register cap 65536 / threads / MINB)
+#endif
+constexpr int kImgTileRows = kEvalThreads / 32;  // image work items: tiles of 32 quads x kImgTileRows rows = one CTA tile
 
 struct ProgView {
     const uint4 *g_prog;     // device: program chunks followed by aux (16-byte aligned)
@@ -280,17 +287,20 @@ struct GenCenters {
 // the sink and four RGBA8 pixels leave as one 16-byte store (image.go:112-116 fused); else the distances are stored.
 struct GenImage {
     static constexpr bool kTileSkip = false;
-    // Work items are grouped into 2-D tiles of 32 quads x 16 rows (128 x 16 pixels = one 512-thread CTA tile), so that a
-    // tile is spatially compact and the CTA-uniform guards (gsdf_program.h) fire; a warp still covers 512 contiguous
+    // Work items are grouped into 2-D tiles of 32 quads x kImgTileRows rows (128 x 12 pixels = one 384-thread CTA tile), so that
+    // a tile is spatially compact and the CTA-uniform guards (gsdf_program.h) fire; a warp still covers 512 contiguous
     // bytes of one image row.
     float xmin, ymax, dx, dy; int w, h; float *dist; uint32_t *rgba; ColorConv cc;
+    __host__ __device__ static uint64_t items_for(int w, int h) {
+        return (uint64_t)((((uint32_t)(w + 3) / 4) + 31u) / 32u) * (((uint32_t)h + kImgTileRows - 1u) / kImgTileRows) * (32u * kImgTileRows);
+    }
     __device__ uint32_t tiles_x() const { return ((uint32_t)(w + 3) / 4 + 31u) / 32u; }
-    __device__ uint64_t work_items() const { return (uint64_t)tiles_x() * (((uint32_t)h + 15u) / 16u) * 512u; }
+    __device__ uint64_t work_items() const { return items_for(w, h); }
     __device__ void decode(uint64_t wi, int &q, int &j) const {
-        const uint32_t t = (uint32_t)(wi & 511u), tile = (uint32_t)(wi >> 9);
+        const uint32_t tile = (uint32_t)(wi / (32u * kImgTileRows)), t = (uint32_t)(wi - (uint64_t)tile * (32u * kImgTileRows));
         const uint32_t tx = tile % tiles_x(), ty = tile / tiles_x();
         q = (int)(tx * 32u + (t & 31u));
-        j = (int)(ty * 16u + (t >> 5));
+        j = (int)(ty * kImgTileRows + (t >> 5));
     }
     __device__ void load(uint64_t wi, float (&x)[4], float (&y)[4], float (&z)[4]) const {
         int q, j;

@@ -46,6 +46,8 @@ struct BlkArgs {
     unsigned long long *fin_scanstate; uint32_t fin_nstate;
     unsigned long long *fin_dstamp; volatile unsigned long long *fin_hstamp; int fin_nstamp;
     uint32_t *fin_done;
+    // the emit pass runs the segment scan itself (no k_scan_seg launch): scan_state != nullptr
+    unsigned long long *scan_state; uint32_t *scan_ticket, *scan_done; uint32_t scan_epoch, scan_nseg; unsigned long long *scan_total;
 };
 
 // ---------------------------------------------------------------------------------------------- prune -> work lists
@@ -261,19 +263,13 @@ __device__ __forceinline__ uint32_t seg_masked_sum(uint2 c, uint32_t kb, int upt
     return s;
 }
 
-__global__ void __launch_bounds__(kThreads) k_scan_seg(MeshDims D, const uint32_t *__restrict__ mbits, const uint2 *__restrict__ blkcnt, uint32_t *__restrict__ segoff,
-                                                      uint32_t n, unsigned long long *__restrict__ state, uint32_t *__restrict__ ticket, uint32_t epoch,
-                                                      unsigned long long *__restrict__ total, unsigned long long *stamp) {
-    __shared__ uint32_t s_w[kThreads / 32];
-    __shared__ uint32_t s_tile, s_prefix;
-    pdl_trigger();
-    pdl_wait();
-    stage_stamp(stamp);
+// One tile (kScanTile segments) of the decoupled look-back scan, by all kThreads threads of a CTA. Flag values of a tile's
+// state word: 1 = aggregate published, 2 = inclusive prefix published. done_counter (scan inside the emit pass): += 1 once
+// the tile's offsets are in segoff.
+__device__ __forceinline__ void scan_seg_tile(const MeshDims &D, const uint32_t *__restrict__ mbits, const uint2 *__restrict__ blkcnt, uint32_t *__restrict__ segoff,
+                                              uint32_t n, unsigned long long *__restrict__ state, uint32_t epoch, unsigned long long *__restrict__ total,
+                                              uint32_t tile, uint32_t *s_w, uint32_t *s_prefix, uint32_t *done_counter) {
     const uint32_t ntiles = (n + kScanTile - 1) / kScanTile;
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if (tile >= ntiles) return;
     const uint32_t base = tile * kScanTile + threadIdx.x * 8;
     uint32_t v[8], sum = 0;
     {
@@ -283,7 +279,7 @@ __global__ void __launch_bounds__(kThreads) k_scan_seg(MeshDims D, const uint32_
             v[i] = 0u;
             if (base + i < n) {
                 const uint32_t kb = seg_kept_bits(D, mbits, row, sx);
-                if (kb) v[i] = seg_masked_sum(blkcnt[base + i], kb);
+                if (kb) v[i] = seg_masked_sum(__ldcg(blkcnt + base + i), kb);
             }
             if (++sx == (uint32_t)D.nsx) { sx = 0u; row++; }
         }
@@ -293,12 +289,12 @@ __global__ void __launch_bounds__(kThreads) k_scan_seg(MeshDims D, const uint32_
     const uint32_t incl = warp_incl_scan(sum);
     if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
     __syncthreads();
+    const unsigned long long tag = (unsigned long long)epoch << 34;
     if (threadIdx.x < 32) {
         const uint32_t w = threadIdx.x < kThreads / 32 ? s_w[threadIdx.x] : 0u;
         const uint32_t wi = warp_incl_scan(w);
         if (threadIdx.x < kThreads / 32) s_w[threadIdx.x] = wi - w;
         const uint32_t agg = __shfl_sync(0xffffffffu, wi, 31);  // tile aggregate
-        const unsigned long long tag = (unsigned long long)epoch << 34;
         if (threadIdx.x == 0) {
             const unsigned long long st = tag | ((tile == 0 ? 2ull : 1ull) << 32) | agg;
             atomicExch(&state[tile], st);
@@ -326,12 +322,12 @@ __global__ void __launch_bounds__(kThreads) k_scan_seg(MeshDims D, const uint32_
             if (threadIdx.x == 0) atomicExch(&state[tile], tag | (2ull << 32) | (unsigned long long)(prefix + agg));
         }
         if (threadIdx.x == 0) {
-            s_prefix = prefix;
+            *s_prefix = prefix;
             if (tile == ntiles - 1) *total = (unsigned long long)prefix + agg;
         }
     }
     __syncthreads();
-    uint32_t run = s_prefix + s_w[threadIdx.x >> 5] + (incl - sum);
+    uint32_t run = *s_prefix + s_w[threadIdx.x >> 5] + (incl - sum);
     uint32_t o[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) { o[i] = run; run += v[i]; }
@@ -342,6 +338,27 @@ __global__ void __launch_bounds__(kThreads) k_scan_seg(MeshDims D, const uint32_
 #pragma unroll
         for (int i = 0; i < 8; i++) if (base + i < n) segoff[base + i] = o[i];
     }
+    if (done_counter) {  // release the tile's offsets to the emit phase of every CTA
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(done_counter, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_scan_seg(MeshDims D, const uint32_t *__restrict__ mbits, const uint2 *__restrict__ blkcnt, uint32_t *__restrict__ segoff,
+                                                      uint32_t n, unsigned long long *__restrict__ state, uint32_t *__restrict__ ticket, uint32_t epoch,
+                                                      unsigned long long *__restrict__ total, unsigned long long *stamp) {
+    __shared__ uint32_t s_w[kThreads / 32];
+    __shared__ uint32_t s_tile, s_prefix[2];
+    pdl_trigger();
+    pdl_wait();
+    stage_stamp(stamp);
+    const uint32_t ntiles = (n + kScanTile - 1) / kScanTile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= ntiles) return;
+    scan_seg_tile(D, mbits, blkcnt, segoff, n, state, epoch, total, tile, s_w, s_prefix, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------- pass 2
@@ -368,10 +385,39 @@ __global__ void __launch_bounds__(kBlkWarps * 32) k_mc_blk_emit(const __grid_con
     const uint32_t stride = gridDim.x * kBlkWarps;
     const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
     const float rr = A.res;
+    const bool fused = A.scan_state != nullptr;
+    // the first stencil copy goes out before the scan phase: it is in flight while this CTA scans
+    if (fused && blockIdx.x * kBlkWarps + warp < nblk && lane == 0)
+        blk_issue(&tmap, reinterpret_cast<float *>(s_buf[warp][0]), bar0, D, blk_decode(D, A.blklist[blockIdx.x * kBlkWarps + warp]));
+    if (fused) {
+        // Segment scan inside the emit pass: CTAs take scan tiles by ticket until none is left. A tile only ever waits for tiles
+        // with smaller tickets, i.e. for CTAs that are already running, so no co-residency of the whole grid is needed; then
+        // one thread per CTA waits (with back-off) until every tile has written its offsets.
+        __shared__ uint32_t s_w[kThreads / 32];
+        __shared__ uint32_t s_tile, s_prefix[2];
+        const uint32_t ntiles = (A.scan_nseg + kScanTile - 1) / kScanTile;
+        for (;;) {
+            if (threadIdx.x == 0) s_tile = *reinterpret_cast<volatile uint32_t *>(A.scan_ticket) >= ntiles ? ntiles : atomicAdd(A.scan_ticket, 1u);
+            __syncthreads();
+            const uint32_t tile = s_tile;
+            if (tile >= ntiles) break;
+            scan_seg_tile(D, A.mbits, A.blkcnt, A.segoff, A.scan_nseg, A.scan_state, A.scan_epoch, A.scan_total, tile, s_w, s_prefix, A.scan_done);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            uint32_t d;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(d) : "l"(A.scan_done) : "memory");
+                if (d >= ntiles) break;
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+    }
     uint32_t phases = 0u;  // bit b = parity to wait for on buffer b
     uint32_t it = blockIdx.x * kBlkWarps + warp;
     int cur = 0;
-    if (it < nblk && lane == 0) blk_issue(&tmap, reinterpret_cast<float *>(s_buf[warp][0]), bar0, D, blk_decode(D, A.blklist[it]));
+    if (!fused && it < nblk && lane == 0) blk_issue(&tmap, reinterpret_cast<float *>(s_buf[warp][0]), bar0, D, blk_decode(D, A.blklist[it]));
     for (; it < nblk; it += stride, cur ^= 1) {
         const BlkPos b = blk_decode(D, A.blklist[it]);
         if (it + stride < nblk && lane == 0)
@@ -389,7 +435,8 @@ __global__ void __launch_bounds__(kBlkWarps * 32) k_mc_blk_emit(const __grid_con
                 rown[h] = ((slot < 4 ? c.x : c.y) >> (8 * (slot & 3))) & 0xffu;
                 if (rown[h]) {  // triangles of the kept slots in front of this block, behind the segment's offset
                     const uint32_t kb = seg_kept_bits(D, A.mbits, (uint32_t)(cz - D.cz0) * (uint32_t)D.ny + (uint32_t)cy, (uint32_t)(b.bx >> 3));
-                    rowbase[h] = A.segoff[seg] + seg_masked_sum(c, kb, slot);
+                    const uint32_t so = fused ? __ldcg(A.segoff + seg) : A.segoff[seg];  // (fused: written during this kernel)
+                    rowbase[h] = so + seg_masked_sum(c, kb, slot);
                 }
             }
         }

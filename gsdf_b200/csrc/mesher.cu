@@ -45,7 +45,8 @@ struct gsdf_mesher {
     uint8_t *d_stl = nullptr; size_t stl_cap = 0;
     // device counters: [0] quad list length, [1] overflow flag, [2..3] total triangles (u64), [4] kept level-3 cubes,
     // [5] listed segments, [6] scan ticket, [7] prune-cube centres evaluated, [8..17] work-tile schedulers of this mesher's
-    // interpreter launches (one pair per prune level + one for the lattice evaluation: never shared with another launch)
+    // interpreter launches (one pair per prune level + one for the lattice evaluation: never shared with another launch),
+    // [18] scan tiles finished (scan inside the emit pass), [23] CTAs of the last kernel that are done
     uint32_t *d_ctr = nullptr;
     uint32_t *h_ctr = nullptr;  // pinned mirror
     // stage stamps (%globaltimer, ns): [0] prune centres, [1] quad compaction, [2] lattice evaluation, [3] classification,
@@ -197,7 +198,8 @@ int mesh_run_begin(gsdf_mesher *m) {
     const uint64_t blk_bound = m->runs > 0 ? std::min<uint64_t>(nblocks_slab, 2 * (uint64_t)m->blk_hint + 256) : nblocks_slab;
     // test knob: cap the grid so that on small, oracle-checked lattices every warp walks many blocks through both stencil buffers
     static const unsigned blk_grid_cap = getenv("GSDF_BLK_GRID") ? (unsigned)std::max(1, atoi(getenv("GSDF_BLK_GRID"))) : 0u;
-    unsigned blkgrid = grid_for(p->sms, blk_bound, kBlkWarps, 8);
+    static const int blk_waves = getenv("GSDF_BLK_WAVES") ? std::max(1, atoi(getenv("GSDF_BLK_WAVES"))) : 8;  // A/B knob: CTAs per SM of the block kernels' grid
+    unsigned blkgrid = grid_for(p->sms, blk_bound, kBlkWarps, blk_waves);
     if (blk_grid_cap) blkgrid = std::min(blkgrid, blk_grid_cap);
     const unsigned mcgrid = grid_for(p->sms, nrows * (uint64_t)((D.nsx + 3) / 4), kThreads / 32, 16);
     if (m->use_tma && m->tmap_grid != m->d_grid) {  // (re)describe the lattice buffer: pitch x (ny+1) x nk floats
@@ -222,6 +224,10 @@ int mesh_run_begin(gsdf_mesher *m) {
         if (force_p == 4) eval_p = 4;
     }
     static const bool scan3 = getenv("GSDF_SCAN3") != nullptr;  // A/B: the three-kernel scan
+    // default: the segment scan runs inside the emit pass of the block kernels; GSDF_SCAN_FUSED=0 launches k_scan_seg (A/B)
+    static const bool scan_fused_on = !scan3 && !(getenv("GSDF_SCAN_FUSED") != nullptr && getenv("GSDF_SCAN_FUSED")[0] == '0');
+    static const uint64_t scan_fused_max = getenv("GSDF_SCAN_FUSED_MAX") ? (uint64_t)atoll(getenv("GSDF_SCAN_FUSED_MAX")) : (1ull << 40);
+    const bool scan_fused = scan_fused_on && nscantiles <= scan_fused_max;
 
     // The launch sequence of one render. stage_events: record the per-stage timing events (eager path only).
     // Programmatic dependent launch between the kernels of the render: every kernel but the first carries the
@@ -304,6 +310,8 @@ int mesh_run_begin(gsdf_mesher *m) {
         CU(cudaGetLastError());
         k_scan_apply<<<(unsigned)nscanblocks, kThreads, 0, st>>>(m->d_seg, nseg, m->d_blocksum);
         CU(cudaGetLastError());
+    } else if (blockmc && scan_fused && emitted) {
+        // no scan launch: the emit pass takes the scan tiles by ticket before it emits (mc_block.cuh)
     } else if (blockmc) {
         CU(launch_chain(pdl, k_scan_seg, dim3((unsigned)nscantiles), dim3(kThreads), 0, st, D, (const uint32_t *)A.mbits, (const uint2 *)m->d_blkcnt, m->d_seg, (uint32_t)nseg,
                         m->d_scanstate, m->d_ctr + 6, epoch, reinterpret_cast<unsigned long long *>(m->d_ctr + 2), m->d_stamp + 4));
@@ -326,6 +334,10 @@ int mesh_run_begin(gsdf_mesher *m) {
             BE.fin_scanstate = m->d_scanstate; BE.fin_nstate = (uint32_t)nscantiles;
             BE.fin_dstamp = m->d_stamp; BE.fin_hstamp = (volatile unsigned long long *)m->h_stamp; BE.fin_nstamp = kMeshStamps;
             BE.fin_done = m->d_ctr + kMeshCtr - 1;
+            if (scan_fused) {
+                BE.scan_state = m->d_scanstate; BE.scan_ticket = m->d_ctr + 6; BE.scan_done = m->d_ctr + 18; BE.scan_epoch = epoch; BE.scan_nseg = (uint32_t)nseg;
+                BE.scan_total = reinterpret_cast<unsigned long long *>(m->d_ctr + 2);
+            }
             CU(launch_chain(pdl, k_mc_blk_emit, dim3(blkgrid), dim3(kBlkWarps * 32), 0, st, m->tmapB, BE));
         } else if (m->use_tma && m->tile5) {
             // the emit pass ends the render itself: its last CTA publishes the counters and re-arms the state

@@ -1171,13 +1171,22 @@ int64_t go_flat_march(const go_lattice *lat, const float *grid, float *tri9, int
 
 /* Same sweep restricted to cell layers cz in [cz0,cz1): what one rank of the Z-slab partition produces (the
  * reference's own split is evalGrid's k-slabs, flatrenderer.go:120-122). grid/cases/blockmask cover the WHOLE lattice. */
+int64_t go_flat_march_slab_w(const go_lattice *lat, const float *grid, float *tri9, int64_t max_tris, uint8_t *cases,
+                             const uint8_t *blockmask, int mask_w, int cz0, int cz1);
 int64_t go_flat_march_slab(const go_lattice *lat, const float *grid, float *tri9, int64_t max_tris, uint8_t *cases,
                            const uint8_t *blockmask, int cz0, int cz1) {
+    return go_flat_march_slab_w(lat, grid, tri9, max_tris, cases, blockmask, 4, cz0, cz1);
+}
+/* mask_w: width in cells of the cubes blockmask describes (4 = level-3 cubes, 2 = level-2 cubes of a plan that ends with
+ * level 2, include/gsdf_b200.h); the mask is [ceil(nz/w)][ceil(ny/w)][ceil(nx/w)]. */
+int64_t go_flat_march_slab_w(const go_lattice *lat, const float *grid, float *tri9, int64_t max_tris, uint8_t *cases,
+                             const uint8_t *blockmask, int mask_w, int cz0, int cz1) {
     int nx = lat->n[0], ny = lat->n[1], nz = lat->n[2];
     size_t sy = (size_t)nx + 1, sz = sy * ((size_t)ny + 1);
     float r = lat->res;
     float cubeDiag = (float)(2 * GLRENDER_SQRT3) * r; /* Go folds 2*sqrt3 as a constant, then float32 multiply */
-    int nbx = (nx + 3) / 4, nby = (ny + 3) / 4;
+    if (mask_w < 1) mask_w = 4;
+    int nbx = (nx + mask_w - 1) / mask_w, nby = (ny + mask_w - 1) / mask_w;
     int64_t ntri = 0;
     if (cz0 < 0) cz0 = 0;
     if (cz1 > nz) cz1 = nz;
@@ -1186,7 +1195,7 @@ int64_t go_flat_march_slab(const go_lattice *lat, const float *grid, float *tri9
             for (int cx = 0; cx < nx; cx++) {
                 size_t ci = (size_t)cx + (size_t)nx * ((size_t)cy + (size_t)ny * cz);
                 if (cases) cases[ci] = 0;
-                if (blockmask && !blockmask[(size_t)(cx >> 2) + (size_t)nbx * ((size_t)(cy >> 2) + (size_t)nby * (cz >> 2))]) continue;
+                if (blockmask && !blockmask[(size_t)(cx / mask_w) + (size_t)nbx * ((size_t)(cy / mask_w) + (size_t)nby * (cz / mask_w))]) continue;
                 size_t base = (size_t)cx + (size_t)cy * sy + (size_t)cz * sz;
                 if (fabsf(grid[base]) > cubeDiag) continue;
                 float v[8] = {grid[base], grid[base + 1], grid[base + 1 + sy], grid[base + sy],
@@ -1241,7 +1250,9 @@ int64_t go_octree_prune_mask(const go_tree *t, const go_lattice *lat, uint8_t *m
  * lattice origin (ms3.Octree.CubeOrigin). mask = level-3 verdicts [nbz][nby][nbx]; *evals = centres evaluated. */
 int64_t go_octree_prune_plan(const go_tree *t, const go_lattice *lat, int nlevels, const int *levels, const float *margins, uint8_t *mask,
                              int64_t *evals) {
-    if (nlevels < 1 || levels[nlevels - 1] != 3) return -1;
+    /* the plan ends with level 3, or with level 3 followed by level 2 (the mask then describes the 2-cell cubes) */
+    if (nlevels < 1) return -1;
+    if (levels[nlevels - 1] != 3 && !(levels[nlevels - 1] == 2 && nlevels >= 2 && levels[nlevels - 2] == 3)) return -1;
     uint8_t *parent = NULL;
     int pw = 0, pnx = 0, pny = 0;
     int64_t nev = 0, kept = 0;

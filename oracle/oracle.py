@@ -98,6 +98,8 @@ def lib():
         L.go_flat_march.argtypes = [C.POINTER(GoLattice), vp, vp, C.c_int64, vp, vp]
         L.go_flat_march_slab.restype = C.c_int64
         L.go_flat_march_slab.argtypes = [C.POINTER(GoLattice), vp, vp, C.c_int64, vp, vp, C.c_int, C.c_int]
+        L.go_flat_march_slab_w.restype = C.c_int64
+        L.go_flat_march_slab_w.argtypes = [C.POINTER(GoLattice), vp, vp, C.c_int64, vp, vp, C.c_int, C.c_int, C.c_int]
         L.go_octree_prune_mask.restype = C.c_int64
         L.go_octree_prune_mask.argtypes = [C.POINTER(GoTree), C.POINTER(GoLattice), vp]
         L.go_octree_prune_plan.restype = C.c_int64
@@ -275,10 +277,23 @@ def flat_march_planes(lat, planes, cz0, cz1, blockmask=None, want_cases=False):
     cases = np.empty((cz1 - cz0, ny, nx), dtype=np.uint8) if want_cases else None
     cp = (cases.ctypes.data - cz0 * nx * ny) if cases is not None else None
     mp = blockmask.ctypes.data if blockmask is not None else None
-    n = lib().go_flat_march_slab(C.byref(lat), gp, None, 0, cp, mp, cz0, cz1)
+    mw = _mask_width(lat, blockmask)
+    n = lib().go_flat_march_slab_w(C.byref(lat), gp, None, 0, cp, mp, mw, cz0, cz1)
     tris = np.empty((max(n, 1), 3, 3), dtype=np.float32)
-    n = lib().go_flat_march_slab(C.byref(lat), gp, tris.ctypes.data, n, cp, mp, cz0, cz1)
+    n = lib().go_flat_march_slab_w(C.byref(lat), gp, tris.ctypes.data, n, cp, mp, mw, cz0, cz1)
     return tris[:n], cases
+
+
+def _mask_width(lat, blockmask):
+    """Cube width (cells) a prune mask describes, from its shape: 4 (plan ending with level 3) or 2 (ending with level 2)."""
+    if blockmask is None:
+        return 4
+    nx, ny, nz = lat.n
+    for w in (4, 2):
+        if tuple(blockmask.shape) == ((nz + w - 1) // w, (ny + w - 1) // w, (nx + w - 1) // w):
+            assert blockmask.dtype == np.uint8 and blockmask.flags["C_CONTIGUOUS"]
+            return w
+    raise ValueError("prune mask shape %r fits neither 4-cell nor 2-cell cubes of the lattice" % (blockmask.shape,))
 
 
 def octree_prune_mask(tree, lat):
@@ -291,10 +306,12 @@ def octree_prune_mask(tree, lat):
 
 
 def octree_prune_plan(tree, lat, levels):
-    """Coarse-to-fine prune (gsdf_prune_plan): levels = [(level, margin), ...] ending with level 3. Returns the level-3
-    mask, the kept level-3 count and the number of cube centres evaluated."""
+    """Coarse-to-fine prune (gsdf_prune_plan): levels = [(level, margin), ...] ending with level 3, or with level 3 followed
+    by level 2. Returns the mask of the last level (4-cell or 2-cell cubes), its kept count and the number of cube centres
+    evaluated."""
     nx, ny, nz = lat.n
-    mask = np.empty(((nz + 3) // 4, (ny + 3) // 4, (nx + 3) // 4), dtype=np.uint8)
+    w = 1 << (int(levels[-1][0]) - 1)
+    mask = np.empty(((nz + w - 1) // w, (ny + w - 1) // w, (nx + w - 1) // w), dtype=np.uint8)
     lv = (C.c_int * len(levels))(*[int(l) for l, _ in levels])
     mg = (C.c_float * len(levels))(*[float(m) for _, m in levels])
     ev = C.c_int64()
@@ -313,10 +330,11 @@ def flat_march(lat, grid, want_cases=False, blockmask=None, max_tris=None, cz_ra
     cases = np.empty((nz, ny, nx), dtype=np.uint8) if want_cases else None
     mp = blockmask.ctypes.data if blockmask is not None else None
     cp = cases.ctypes.data if cases is not None else None
+    mw = _mask_width(lat, blockmask)
     if max_tris is None:
-        max_tris = lib().go_flat_march_slab(C.byref(lat), grid.ctypes.data, None, 0, cp, mp, cz0, cz1)
+        max_tris = lib().go_flat_march_slab_w(C.byref(lat), grid.ctypes.data, None, 0, cp, mp, mw, cz0, cz1)
     tris = np.empty((max(max_tris, 1), 3, 3), dtype=np.float32)
-    n = lib().go_flat_march_slab(C.byref(lat), grid.ctypes.data, tris.ctypes.data, max_tris, cp, mp, cz0, cz1)
+    n = lib().go_flat_march_slab_w(C.byref(lat), grid.ctypes.data, tris.ctypes.data, max_tris, cp, mp, mw, cz0, cz1)
     return tris[:min(n, max_tris)], cases
 
 

@@ -14,7 +14,7 @@ import struct
 import numpy as np
 
 F = np.float32
-TILE = 2048  # points per CTA tile on the device (512 threads x 4 points): the granularity of the guards' "all points" vote
+TILE = 1536  # points per CTA tile on the device (384 threads x 4 points): the granularity of the guards' "all points" vote
 
 OPS = """END SPHERE BOX BOXFRAME TORUS CYLINDER HEX CIRCLE2D RECT2D LINE2D LINES2D ARC2D EQTRI2D HEX2D OCT2D DIAMOND2D ROUNDX2D
 POLY2D ELLIPSE2D BEZIERQ2D MIN MAX DIFF XOR SMOOTH_UNION SMOOTH_DIFF SMOOTH_INTERSECT OFFSET ANNULUS MULDIST SHELL_EXIT ADD_BELOW
