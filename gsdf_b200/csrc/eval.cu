@@ -70,6 +70,26 @@ int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_boun
                         : launch_eval_impl<P, Gen, false>(p, gen, nwork_upper_bound, st, pdl, sched, stamp);
 }
 
+template <bool EXT>
+int launch_prune_fine_impl(const gsdf_program *p, const PruneFine &g, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
+    static KernelDevCache cache;
+    auto kern = k_prune_fine<EXT>;
+    const uint32_t smem = smem_total_bytes<1>(p->pv, kEvalThreads) + prune_fine_extra_bytes(kEvalThreads);
+    int occ = 0;
+    const int rc = kernel_occupancy(cache, kern, p->device, smem, kEvalThreads, &occ);
+    if (rc) return rc;
+    if (occ < 1) return fail(GSDF_EPROGRAM, "node program needs %u bytes of shared memory per CTA; does not fit", smem);
+    const uint64_t nwork = (uint64_t)g.L.nwx * 32u * g.L.ncy * g.L.ncz;
+    uint64_t blocks = (nwork + kEvalThreads - 1) / kEvalThreads;
+    blocks = std::max<uint64_t>(std::min<uint64_t>(blocks, (uint64_t)p->sms * occ), 1);
+    ProgView pv = p->pv;
+    pv.sched = sched ? sched : next_sched(p);
+    pv.stamp = stamp;
+    CU(launch_chain(pdl, kern, dim3((unsigned)blocks), dim3(kEvalThreads), smem, st, pv, g));
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // Streaming Evaluate (k_eval_stream): persistent grid, one resident wave, tiles dealt round-robin.
 template <int DIM, bool EXT>
 int launch_stream_impl(const gsdf_program *p, const float *d_pos, float *d_dist, uint64_t n, cudaStream_t st) {
@@ -116,6 +136,9 @@ int launch_grid4(const gsdf_program *p, const GenGrid<4> &g, uint64_t nwork, cud
 }
 int launch_grid1(const gsdf_program *p, const GenGrid<1> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
     return launch_eval<1>(p, g, nwork, st, pdl, sched, stamp);
+}
+int launch_prune_fine(const gsdf_program *p, const PruneFine &g, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
+    return p->needs_ext ? launch_prune_fine_impl<true>(p, g, st, pdl, sched, stamp) : launch_prune_fine_impl<false>(p, g, st, pdl, sched, stamp);
 }
 int eval_cta_slots(const gsdf_program *p, int *slots) {
     static KernelDevCache cache;  // occupancy of the P = 4 lattice kernel (the P = 1 form is never lower)

@@ -81,6 +81,168 @@ __global__ void __launch_bounds__(kEvalThreads, GSDF_EVAL_MINB) k_eval(ProgView 
     }
 }
 
+// ---------------------------------------------------------------------------------------------- prune levels 3 + 2
+// See PruneFine (generators.cuh). Work items are level-3 cube rows padded to whole warps, exactly as GenCenters'.
+// Shared memory: [prog (+aux)] [mbarrier + tile slot, 16 bytes] [dstack] [pstack] [radius] (one point per thread), then
+// [parent slots: blockDim u32] [child masks: blockDim u32] [warp sums: 32 u32] [kept count]
+__host__ __device__ inline uint32_t prune_fine_extra_bytes(int threads) { return (uint32_t)threads * 8u + 32u * 4u + 16u; }
+
+template <bool EXT>
+__global__ void __launch_bounds__(kEvalThreads, GSDF_EVAL_MINB) k_prune_fine(ProgView pv, PruneFine g) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t stage = smem_stage_bytes(pv);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + stage);
+    volatile uint32_t *s_tile = reinterpret_cast<volatile uint32_t *>(smem + stage + 8);
+    pdl_trigger();
+    bulk_stage(smem, pv.g_prog, stage, bar);
+    const uint4 *prog = reinterpret_cast<const uint4 *>(smem);
+    const float4 *aux = pv.stage_aux ? reinterpret_cast<const float4 *>(smem + pv.prog_bytes)
+                                     : reinterpret_cast<const float4 *>(reinterpret_cast<const uint8_t *>(pv.g_prog) + pv.prog_bytes);
+    float *dstk = reinterpret_cast<float *>(smem + stage + 16u) + threadIdx.x;
+    float *pstk = dstk + (size_t)pv.dslots * blockDim.x;
+    uint32_t *s_par = reinterpret_cast<uint32_t *>(smem + smem_total_bytes<1>(pv, blockDim.x));
+    uint32_t *s_cm = s_par + blockDim.x;
+    uint32_t *s_wsum = s_cm + blockDim.x;
+    volatile uint32_t *s_kept = s_wsum + 32;
+    const PruneLevel &L = g.L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t rowlen = (uint32_t)L.nwx * 32u;
+    const uint64_t nwork = (uint64_t)rowlen * L.ncy * L.ncz;
+
+    Machine<1> m;
+    pdl_wait();
+    stage_stamp(pv.stamp);
+    for (bool first = true;; first = false) {
+        uint64_t w0;  // first work item of the tile
+        if (first) {
+            w0 = (uint64_t)blockIdx.x * blockDim.x;
+        } else {
+            if (threadIdx.x == 0) *s_tile = gridDim.x + atomicAdd(pv.sched, 1u);
+            __syncthreads();
+            w0 = (uint64_t)(*s_tile) * blockDim.x;
+            __syncthreads();
+        }
+        if (w0 >= nwork) break;
+        const uint64_t w = w0 + threadIdx.x;
+        const bool inrange = w < nwork;  // whole warps: nwork and the tile size are multiples of 32
+        const uint64_t wc = inrange ? w : nwork - 1;
+        int cx, cy, cz;
+        {
+            const uint32_t row = (uint32_t)(wc / rowlen);
+            cx = (int)(wc - (uint64_t)row * rowlen);
+            cy = (int)(row % (uint32_t)L.ncy);
+            cz = (int)(row / (uint32_t)L.ncy);
+        }
+        bool alive = inrange && cx < L.ncx;
+        if (alive && g.P.bits) {
+            const int px = cx >> g.shift, py = cy >> g.shift, pz = ((L.cz0 + cz) >> g.shift) - g.P.cz0;
+            alive = (g.P.bits[((size_t)pz * g.P.ncy + py) * g.P.nwx + (px >> 5)] >> (px & 31)) & 1u;
+        }
+        uint32_t *row2 = g.bits2 + (((size_t)2 * cz) * (2 * L.ncy) + 2 * cy) * (2 * L.nwx) + 2 * (cx >> 5);  // (dz, dy) = (0, 0)
+        const size_t dy2 = (size_t)2 * L.nwx, dz2 = (size_t)2 * L.ncy * dy2;
+        if (__syncthreads_and(!alive)) {  // every cube of the tile has a pruned parent (or is padding): nothing to evaluate
+            if (inrange && lane == 0) {
+                L.bits[w >> 5] = 0u;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    uint32_t *r = row2 + (q >> 1) * dz2 + (q & 1) * dy2;
+                    r[0] = 0u; r[1] = 0u;
+                }
+            }
+            continue;
+        }
+        // ---- level 3: the cube's own centre (padding lanes and lanes behind a pruned parent repeat a valid cube)
+        m.init(dstk, pstk, blockDim.x);
+#ifdef GSDF_RXY
+        m.rxy = pstk + (size_t)pv.pslots * 3 * blockDim.x;
+#endif
+        {
+            const int ccx = min(cx, L.ncx - 1);
+            m.px[0] = (g.ox + (float)(L.w * ccx) * g.res) + L.half;
+            m.py[0] = (g.oy + (float)(L.w * cy) * g.res) + L.half;
+            m.pz[0] = (g.oz + (float)(L.w * (L.cz0 + cz)) * g.res) + L.half;
+        }
+        run_program<1, EXT>(m, prog, aux);
+        const bool keep = alive && !(fabsf(m.top[0]) >= L.maxDist);
+        // ---- compact the survivors of the tile
+        const uint32_t kb = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_wsum[warp] = (uint32_t)__popc(kb);
+        s_cm[threadIdx.x] = 0u;
+        __syncthreads();
+        uint32_t slot = (uint32_t)__popc(kb & ((1u << lane) - 1u));
+        for (int ww = 0; ww < warp; ww++) slot += s_wsum[ww];
+        if (keep) s_par[slot] = threadIdx.x;
+        if (threadIdx.x == 0) {
+            uint32_t k = 0;
+            for (int ww = 0; ww < nwarps; ww++) k += s_wsum[ww];
+            *s_kept = k;
+        }
+        __syncthreads();
+        const uint32_t nchild = 8u * *s_kept;
+        // ---- level 2: the eight children of every survivor, blockDim.x at a time
+        uint32_t nev2 = 0;
+        for (uint32_t base = 0; base < nchild; base += blockDim.x) {  // CTA-uniform trip count
+            const uint32_t item = base + threadIdx.x;
+            const bool valid = item < nchild;
+            const uint32_t it = valid ? item : nchild - 1u;
+            const uint32_t par = s_par[it >> 3], c = it & 7u;
+            const uint64_t wp = w0 + par;
+            const uint32_t prow = (uint32_t)(wp / rowlen);
+            const int pcx = (int)(wp - (uint64_t)prow * rowlen), pcy = (int)(prow % (uint32_t)L.ncy), pcz = (int)(prow / (uint32_t)L.ncy);
+            const int c2x = 2 * pcx + (int)(c & 1u), c2y = 2 * pcy + (int)((c >> 1) & 1u), c2z = 2 * (L.cz0 + pcz) + (int)(c >> 2);
+            const bool exists = 2 * c2x < g.nx && 2 * c2y < g.ny && 2 * c2z < g.nz;
+            m.init(dstk, pstk, blockDim.x);
+#ifdef GSDF_RXY
+            m.rxy = pstk + (size_t)pv.pslots * 3 * blockDim.x;
+#endif
+            m.px[0] = (g.ox + (float)(2 * c2x) * g.res) + g.half2;
+            m.py[0] = (g.oy + (float)(2 * c2y) * g.res) + g.half2;
+            m.pz[0] = (g.oz + (float)(2 * c2z) * g.res) + g.half2;
+            run_program<1, EXT>(m, prog, aux);
+            if (valid && exists) {
+                nev2++;
+                if (!(fabsf(m.top[0]) >= g.maxDist2)) atomicOr(&s_cm[par], 1u << c);
+            }
+        }
+        __syncthreads();
+        // ---- publish: level-3 word, child masks, level-2 rows (E, O words), counters
+        const uint32_t cm = s_cm[threadIdx.x];  // zero unless this thread's cube survived with children
+        const uint32_t word3 = __ballot_sync(0xffffffffu, cm != 0u);
+        const uint32_t nlive = (uint32_t)__popc(__ballot_sync(0xffffffffu, alive));
+        uint32_t n2 = (uint32_t)__popc(cm);
+        uint32_t ne = nev2;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { n2 += __shfl_xor_sync(0xffffffffu, n2, o); ne += __shfl_xor_sync(0xffffffffu, ne, o); }
+        if (inrange) {
+            if (cx < L.ncx) g.childmask[((size_t)cz * L.ncy + cy) * L.ncx + cx] = (uint8_t)cm;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {  // q = dy + 2 dz
+                const uint32_t e = __ballot_sync(0xffffffffu, (cm >> (2 * q)) & 1u), o = __ballot_sync(0xffffffffu, (cm >> (2 * q + 1)) & 1u);
+                if (lane == 0) {
+                    uint32_t *r = row2 + (q >> 1) * dz2 + (q & 1) * dy2;
+                    r[0] = e; r[1] = o;
+                }
+            }
+            if (lane == 0) {
+                L.bits[w >> 5] = word3;
+                if (word3 && g.kept) atomicAdd(g.kept, (uint32_t)__popc(word3));
+                if (n2 && g.kept2) atomicAdd(g.kept2, n2);
+                if (nlive + ne) atomicAdd(g.evals, nlive + ne);
+            }
+        } else if (ne && lane == 0) {
+            atomicAdd(g.evals, ne);
+        }
+        __syncthreads();  // the shared lists are reused by the next tile
+    }
+    if (threadIdx.x == 0) {  // the last CTA to leave re-arms the scheduler for the next launch
+        __threadfence();
+        if (atomicAdd(pv.sched + 1, 1u) == gridDim.x - 1) {
+            pv.sched[0] = 0u;
+            pv.sched[1] = 0u;
+        }
+    }
+}
+
 // gleval.SDF3.Evaluate / SDF2.Evaluate on device-resident point lists, streaming form. A tile is the AoS position block of
 // blockDim.x * 4 points -- one contiguous run of global memory (24 KB for float3, 16 KB for float2) -- fetched by ONE
 // 1-D bulk async copy (cp.async.bulk.shared::cluster.global -> SASS UBLKCP) into a double-buffered shared-memory stage:

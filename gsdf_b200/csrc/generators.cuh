@@ -283,6 +283,28 @@ struct GenCenters {
     }
 };
 
+// The last two levels of a plan that ends with level 2 (2-cell cubes), in ONE launch (k_prune_fine, eval_kernels.cuh): a CTA
+// evaluates the centres of a tile of level-3 cubes, compacts the survivors in shared memory and evaluates their eight
+// children in the same tile loop -- no launch between the two levels, and a child is only ever evaluated by the CTA that
+// kept its parent. A level-3 cube none of whose children survives is dropped as well. Outputs: the level-3 bit rows
+// (what the marching-cubes stage and its work lists read), one child-mask byte per level-3 cube (bit dx + 2 dy + 4 dz;
+// the marching-cubes kernels mask their cells with it: corners of dropped children are never evaluated) and the level-2
+// rows the quad list is built from: per level-2 row (2 cz + dz, 2 cy + dy) and per 32 parents two words, E = children with
+// dx = 0 and O = children with dx = 1, so that "quad m is touched" is E | O | (O << 1 | carry) without bit interleaving.
+struct PruneFine {
+    float ox, oy, oz, res;
+    PruneLevel L;             // level 3 on this slab (bits: output)
+    PruneLevel P;             // its parent level (P.bits == nullptr: none)
+    int shift;                // log2(P.w / L.w)
+    int nx, ny, nz;           // cells of the whole lattice: a 2-cell cube exists iff its first cell does
+    float half2, maxDist2;    // level 2: size/2 and margin * size * sqrt3/2
+    uint32_t *bits2;          // [2 L.ncz][2 L.ncy][2 L.nwx]: words (E, O) per 32 parents
+    uint8_t *childmask;       // [L.ncz][L.ncy][L.ncx]
+    uint32_t *kept;           // += level-3 cubes that keep at least one child
+    uint32_t *kept2;          // += surviving level-2 cubes
+    uint32_t *evals;          // += centres evaluated (both levels)
+};
+
 // ImageRendererSDF2.Render positions (glrender/image.go:85-105). rgba != nullptr: the colour conversion is applied in
 // the sink and four RGBA8 pixels leave as one 16-byte store (image.go:112-116 fused); else the distances are stored.
 struct GenImage {

@@ -162,6 +162,8 @@ int launch_grid1(const gsdf_program *p, const gsdfk::GenGrid<1> &g, uint64_t nwo
 int eval_cta_slots(const gsdf_program *p, int *slots);
 int launch_centers(const gsdf_program *p, const gsdfk::GenCenters &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched,
                    unsigned long long *stamp = nullptr);
+// prune levels 3 and 2 of a plan that ends with level 2, in one launch (k_prune_fine)
+int launch_prune_fine(const gsdf_program *p, const gsdfk::PruneFine &g, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp = nullptr);
 int launch_image(const gsdf_program *p, const gsdfk::GenImage &g, uint64_t nwork, cudaStream_t st, uint32_t *sched);
 int launch_dc(const gsdf_program *p, const gsdfk::GenDC &g, uint64_t nwork, cudaStream_t st, uint32_t *sched);
 // streaming Evaluate: 0 launched, 1 not applicable (caller uses launch_points*), <0 error

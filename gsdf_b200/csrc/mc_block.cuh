@@ -30,6 +30,7 @@ struct BlkArgs {
     MeshDims D;
     float ox, oy, oz, res, cubeDiag;
     const uint32_t *mbits;     // prune bit rows, nullptr = every block kept (FlatRenderer)
+    const uint8_t *childmask;  // plan ending with level 2: per block, which of its eight 2-cell cubes survived (nullptr: all)
     const uint32_t *blklist;   // kept blocks: (bzl * nby + by) * nbx + bx, bzl relative to D.bz0
     const uint32_t *nblk;      // device-side length of blklist
     uint2 *blkcnt;             // [segment] 8 bytes: triangles of block slot t in that 32-cell row segment
@@ -53,9 +54,11 @@ struct BlkArgs {
 // ---------------------------------------------------------------------------------------------- prune -> work lists
 // Quad list exactly as k_compact_quads (lane per 32-quad word of a corner row), then the kept-block list (lane per 32-block
 // word of a block row). bits == nullptr: no quad list, every block of the slab is listed (FlatRenderer).
+// bits2 != nullptr (plan ending with level 2, PruneFine): a quad is needed iff a kept 2-CELL cube touches it -- quad m of
+// corner row (j, k) is touched by the cubes 2m-1, 2m, 2m+1 of the level-2 rows (j-1)>>1, j>>1 x (k-1)>>1, k>>1.
 __global__ void __launch_bounds__(kThreads) k_mesh_lists(MeshDims D, const uint32_t *__restrict__ bits, uint32_t *__restrict__ list,
                                                         uint32_t *__restrict__ count, uint32_t *__restrict__ blklist, uint32_t *__restrict__ nblk,
-                                                        unsigned long long *stamp) {
+                                                        unsigned long long *stamp, const uint32_t *__restrict__ bits2) {
     pdl_trigger();
     pdl_wait();
     stage_stamp(stamp);
@@ -74,8 +77,9 @@ __global__ void __launch_bounds__(kThreads) k_mesh_lists(MeshDims D, const uint3
                 w = (uint32_t)(item - (uint64_t)r * nqw);
                 const int j = (int)(r % (uint32_t)(D.ny + 1));
                 const int k = D.cz0 + (int)(r / (uint32_t)(D.ny + 1));
-                const int by0 = j - 1 >= 0 ? (j - 1) >> 2 : -1, by1 = j < D.ny ? j >> 2 : -1;
-                const int bz0 = k - 1 >= D.cz0 ? (k - 1) >> 2 : -1, bz1 = k < D.cz1 ? k >> 2 : -1;
+                const int sh = bits2 ? 1 : 2;  // log2 of the cube width the rows describe
+                const int by0 = j - 1 >= 0 ? (j - 1) >> sh : -1, by1 = j < D.ny ? j >> sh : -1;
+                const int bz0 = k - 1 >= D.cz0 ? (k - 1) >> sh : -1, bz1 = k < D.cz1 ? k >> sh : -1;
 #pragma unroll
                 for (int a = 0; a < 2; a++) {
                     const int by = a ? by1 : by0;
@@ -84,10 +88,17 @@ __global__ void __launch_bounds__(kThreads) k_mesh_lists(MeshDims D, const uint3
                     for (int c = 0; c < 2; c++) {
                         const int bz = c ? bz1 : bz0;
                         if (bz < 0 || (c && bz1 == bz0)) continue;
-                        const uint32_t *row = bits + ((size_t)(bz - D.bz0) * D.nby + by) * D.nwx;
-                        const uint32_t cur = (int)w < D.nwx ? row[w] : 0u;
-                        const uint32_t prev = (w >= 1 && (int)(w - 1) < D.nwx) ? row[w - 1] : 0u;
-                        needw |= cur | (cur << 1) | (prev >> 31);
+                        if (bits2) {
+                            const uint32_t *row = bits2 + ((size_t)(bz - 2 * D.bz0) * (2 * D.nby) + by) * (2 * D.nwx);
+                            const uint32_t e = (int)w < D.nwx ? row[2 * w] : 0u, o = (int)w < D.nwx ? row[2 * w + 1] : 0u;
+                            const uint32_t oprev = (w >= 1 && (int)(w - 1) < D.nwx) ? row[2 * (w - 1) + 1] : 0u;
+                            needw |= e | o | (o << 1) | (oprev >> 31);
+                        } else {
+                            const uint32_t *row = bits + ((size_t)(bz - D.bz0) * D.nby + by) * D.nwx;
+                            const uint32_t cur = (int)w < D.nwx ? row[w] : 0u;
+                            const uint32_t prev = (w >= 1 && (int)(w - 1) < D.nwx) ? row[w - 1] : 0u;
+                            needw |= cur | (cur << 1) | (prev >> 31);
+                        }
                     }
                 }
                 const int rem = D.nqx - 32 * (int)w;  // quads of this word that exist
@@ -221,6 +232,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) k_mc_blk_count(const __grid_co
         const BlkPos b = blk_decode(D, A.blklist[it]);
         if (it + stride < nblk && lane == 0)  // the other buffer was released by the __syncwarp that ended the previous iteration
             blk_issue(&tmap, reinterpret_cast<float *>(s_buf[warp][cur ^ 1]), cur ? bar0 : bar1, D, blk_decode(D, A.blklist[it + stride]));
+        const uint32_t cm = A.childmask ? A.childmask[A.blklist[it]] : 0xffu;
         blk_wait(cur ? bar1 : bar0, (phases >> cur) & 1u);
         phases ^= 1u << cur;
         const float *buf = reinterpret_cast<const float *>(s_buf[warp][cur]);
@@ -229,7 +241,8 @@ __global__ void __launch_bounds__(kBlkWarps * 32) k_mc_blk_count(const __grid_co
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int lzz = lz + 2 * h, cz = b.z0 + lzz;
-            const bool valid = okxy && cz >= D.cz0 && cz < D.cz1;
+            // (h = child layer dz: lz is 0 or 1) corners of a dropped 2-cell cube were never evaluated: its cells hold no surface
+            const bool valid = okxy && cz >= D.cz0 && cz < D.cz1 && ((cm >> ((lx >> 1) + 2 * (ly >> 1) + 4 * h)) & 1u);
             const int idx = blk_case(buf, lx, ly, lzz, valid, A.cubeDiag);
             uint32_t n = s_ntri[idx];
             n += __shfl_xor_sync(0xffffffffu, n, 1);
@@ -367,6 +380,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) k_mc_blk_emit(const __grid_con
     __shared__ __align__(8) uint64_t s_bar[kBlkWarps][2];
     __shared__ uint8_t s_ntri[256];
     __shared__ __align__(16) int8_t s_tris[256 * 16];
+    __shared__ uint2 s_list[kBlkWarps][64 * 5];  // per warp: the triangles of the block being emitted (a cell has at most 5)
     pdl_trigger();
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = A.t_ntri[i];
     for (int i = threadIdx.x; i < 256 * 16 / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_tris)[i] = reinterpret_cast<const uint4 *>(A.t_tris)[i];
@@ -440,6 +454,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) k_mc_blk_emit(const __grid_con
                 }
             }
         }
+        const uint32_t cm = A.childmask ? A.childmask[A.blklist[it]] : 0xffu;
         const bool any = __ballot_sync(0xffffffffu, (rown[0] | rown[1]) != 0u) != 0u;
         blk_wait(cur ? bar1 : bar0, (phases >> cur) & 1u);  // (consumed even when the block turns out empty: the barrier phase must advance)
         phases ^= 1u << cur;
@@ -451,38 +466,38 @@ __global__ void __launch_bounds__(kBlkWarps * 32) k_mc_blk_emit(const __grid_con
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int lzz = lz + 2 * h, cz = b.z0 + lzz;
-                const bool valid = okxy && cz >= D.cz0 && cz < D.cz1 && rown[h] != 0u;
+                const bool valid = okxy && cz >= D.cz0 && cz < D.cz1 && rown[h] != 0u && ((cm >> ((lx >> 1) + 2 * (ly >> 1) + 4 * h)) & 1u);
                 index[h] = valid ? blk_case(buf, lx, ly, lzz, true, A.cubeDiag) : 0;
                 n[h] = s_ntri[index[h]];
                 // cells in front of this one in its row: exclusive prefix over the 4 lanes of the row
                 const uint32_t a1 = __shfl_up_sync(0xffffffffu, n[h], 1), a2 = __shfl_up_sync(0xffffffffu, n[h], 2), a3 = __shfl_up_sync(0xffffffffu, n[h], 3);
                 obase[h] = rowbase[h] + (lx >= 1 ? a1 : 0u) + (lx >= 2 ? a2 : 0u) + (lx >= 3 ? a3 : 0u);
             }
-            // vertices of the block's triangles, dealt round-robin: cells in the order (h = 0: lanes 0..31), (h = 1: lanes 0..31)
+            // The block's triangles in output order of its cells (h = 0: lanes 0..31, then h = 1): every lane lists the triangles
+            // of its two cells at the positions the warp scan of the counts gives (the warp-level scan north_star asks for) -- one
+            // entry per triangle: output slot, cube case, triangle number within the cell, cell. The vertices are then dealt
+            // round-robin, lane = vertex, and a vertex finds its triangle with one shared-memory load instead of a search.
             const uint32_t incl0 = warp_incl_scan(n[0]);
             const uint32_t tot0 = __shfl_sync(0xffffffffu, incl0, 31);
             const uint32_t incl1 = tot0 + warp_incl_scan(n[1]);
             const uint32_t total = __shfl_sync(0xffffffffu, incl1, 31);
-            for (uint32_t ibase = 0; ibase < 3u * total; ibase += 32) {  // warp-uniform trip count: shuffles use all lanes
-                const uint32_t item = ibase + lane;
-                const bool alive = item < 3u * total;
-                const uint32_t tri = alive ? item / 3u : total - 1u, j = alive ? item - 3u * tri : 0u;
-                const bool second = tri >= tot0;  // which of the two cell sets owns the triangle
-                int lo = 0;                       // owner = first lane whose inclusive count exceeds tri
+            uint2 *lst = s_list[warp];
 #pragma unroll
-                for (int step = 16; step > 0; step >>= 1) {
-                    const uint32_t p0 = __shfl_sync(0xffffffffu, incl0, lo + step - 1), p1 = __shfl_sync(0xffffffffu, incl1, lo + step - 1);
-                    if ((second ? p1 : p0) <= tri) lo += step;
-                }
-                const int owner = lo;
-                const uint32_t e0 = __shfl_sync(0xffffffffu, incl0 - n[0], owner), e1 = __shfl_sync(0xffffffffu, incl1 - n[1], owner);
-                const int i0 = __shfl_sync(0xffffffffu, index[0], owner), i1 = __shfl_sync(0xffffffffu, index[1], owner);
-                const uint32_t b0 = __shfl_sync(0xffffffffu, obase[0], owner), b1 = __shfl_sync(0xffffffffu, obase[1], owner);
-                if (!alive) continue;
-                const uint32_t kk = tri - (second ? e1 : e0);
-                const int oindex = second ? i1 : i0;
-                const uint64_t o = (uint64_t)(second ? b1 : b0) + kk;
+            for (int h = 0; h < 2; h++) {
+                const uint32_t first = h ? incl1 - n[1] : incl0 - n[0];
+                for (uint32_t k = 0; k < n[h]; k++)
+                    lst[first + k] = make_uint2(obase[h] + k, (uint32_t)index[h] | (k << 8) | ((uint32_t)(lane + 32 * h) << 11));
+            }
+            __syncwarp();
+            for (uint32_t item = lane; item < 3u * total; item += 32) {
+                const uint32_t tri = item / 3u, j = item - 3u * tri;
+                const uint2 ent = lst[tri];
+                const uint64_t o = ent.x;
                 if (o >= A.tri_capacity) { *A.overflow = 1u; continue; }
+                const int oindex = (int)(ent.y & 0xffu);
+                const uint32_t kk = (ent.y >> 8) & 7u;
+                const int owner = (int)((ent.y >> 11) & 31u);
+                const bool second = (ent.y >> 16) != 0u;
                 const int olx = owner & 3, oly = (owner >> 2) & 3, olz = (owner >> 4) + (second ? 2 : 0);
                 // corner positions, flatrenderer.go:235-247
                 const float px0 = A.ox + (float)(b.x0 + olx) * rr, px1 = px0 + rr;

@@ -33,6 +33,10 @@ struct gsdf_mesher {
     gsdf_prune_plan plan{};
     PruneLevel lev[GSDF_PRUNE_MAX_LEVELS]{};
     uint32_t *d_lbits[GSDF_PRUNE_MAX_LEVELS] = {}; size_t lbits_cap[GSDF_PRUNE_MAX_LEVELS] = {};
+    // plan ending with level 2 (PruneFine, generators.cuh): nl3 = levels down to level 3, then the 2-cell cubes
+    bool fine = false; int nl3 = 0; float half2 = 0.f, maxDist2 = 0.f;
+    uint32_t *d_bits2 = nullptr; size_t bits2_cap = 0;        // level-2 rows (E, O words)
+    uint8_t *d_childmask = nullptr; size_t childmask_cap = 0; // per level-3 block: surviving children
     uint32_t *d_list = nullptr; size_t list_cap = 0;
     uint32_t *d_seg = nullptr; size_t seg_cap = 0;
     uint32_t *d_seglist = nullptr; size_t seglist_cap = 0;
@@ -75,6 +79,7 @@ struct gsdf_mesher {
     cudaGraphExec_t gexec = nullptr;
     std::vector<uint8_t> gkey;  // snapshot of every pointer / size the captured launches were built from
     bool allow_graph = true;
+    bool pdl_chain = true;        // programmatic dependent launch between the kernels of a render (see multi_slab_pdl)
     int device = 0;   // device of the program the mesher was created on (destroy must not touch prog: it may be gone)
     uint64_t runs = 0;
     // a render that was enqueued (mesh_run_begin) and not yet finished (mesh_run_end)
@@ -150,12 +155,16 @@ int mesh_run_begin(gsdf_mesher *m) {
         m->scan_epoch = 1;
     }
     if (prune) {
-        for (int li = 0; li < m->plan.nlevels; li++) {
+        for (int li = 0; li < m->nl3; li++) {
             PruneLevel &Lv = m->lev[li];
             if ((rc = grow(m->d_lbits[li], m->lbits_cap[li], (size_t)Lv.nwx * Lv.ncy * Lv.ncz))) return rc;
             Lv.bits = m->d_lbits[li];
         }
-        m->d_mbits = m->d_lbits[m->plan.nlevels - 1];
+        m->d_mbits = m->d_lbits[m->nl3 - 1];
+        if (m->fine) {
+            if ((rc = grow(m->d_bits2, m->bits2_cap, (size_t)8 * D.nwx * D.nby * D.nbz))) return rc;
+            if ((rc = grow(m->d_childmask, m->childmask_cap, (size_t)D.nbx * D.nby * D.nbz))) return rc;
+        }
         if ((rc = grow(m->d_list, m->list_cap, (size_t)nquads))) return rc;
     }
     if (m->flags & GSDF_MESH_KEEP_CASES) {
@@ -191,11 +200,17 @@ int mesh_run_begin(gsdf_mesher *m) {
     A.fin_dstamp = nullptr; A.fin_hstamp = nullptr; A.fin_nstamp = 0; A.fin_done = nullptr;
     BlkArgs BA{};
     BA.D = D; BA.ox = A.ox; BA.oy = A.oy; BA.oz = A.oz; BA.res = A.res; BA.cubeDiag = A.cubeDiag;
+    BA.childmask = (prune && m->fine) ? m->d_childmask : nullptr;
     BA.mbits = A.mbits; BA.blklist = m->d_blklist; BA.nblk = m->d_ctr + 5; BA.blkcnt = m->d_blkcnt; BA.segoff = m->d_seg;
     BA.t_ntri = A.t_ntri; BA.t_tris = A.t_tris; BA.tris = m->d_tris; BA.tri_capacity = m->tri_cap / 9; BA.cases = A.cases;
     BA.overflow = A.overflow;
     // persistent grid of the block kernels: one warp per kept block, sized from the previous render's count when there is one
-    const uint64_t blk_bound = m->runs > 0 ? std::min<uint64_t>(nblocks_slab, 2 * (uint64_t)m->blk_hint + 256) : nblocks_slab;
+    // (launch shapes follow the previous render's counts plus a margin, not the worst case: resident CTAs that find no work
+    // still hold registers and shared memory, and under programmatic launch they hold them early -- on a device shared by
+    // several slabs that kept the other slabs' kernels out; a render that outgrows the hint is still correct, only slower)
+    static const unsigned hint_slack = getenv("GSDF_HINT_SLACK") ? (unsigned)std::max(0, atoi(getenv("GSDF_HINT_SLACK"))) : 8u;  // margin = hint / slack (0: the old 2x)
+    auto with_margin = [&](uint64_t hint, uint64_t floor_) { return hint_slack ? hint + hint / hint_slack + floor_ : 2 * hint + floor_; };
+    const uint64_t blk_bound = m->runs > 0 ? std::min<uint64_t>(nblocks_slab, with_margin(m->blk_hint, 256)) : nblocks_slab;
     // test knob: cap the grid so that on small, oracle-checked lattices every warp walks many blocks through both stencil buffers
     static const unsigned blk_grid_cap = getenv("GSDF_BLK_GRID") ? (unsigned)std::max(1, atoi(getenv("GSDF_BLK_GRID"))) : 0u;
     static const int blk_waves = getenv("GSDF_BLK_WAVES") ? std::max(1, atoi(getenv("GSDF_BLK_WAVES"))) : 8;  // A/B knob: CTAs per SM of the block kernels' grid
@@ -235,16 +250,28 @@ int mesh_run_begin(gsdf_mesher *m) {
     static const bool pdl_on = !(getenv("GSDF_PDL") != nullptr && getenv("GSDF_PDL")[0] == '0');  // default on; GSDF_PDL=0 is the A/B switch
     auto enqueue = [&](bool stage_events, uint32_t epoch) -> int {
     int rc = 0;
-    const bool pdl = pdl_on && !stage_events && !scan3 && !(m->flags & GSDF_MESH_KEEP_GRID);
+    const bool pdl = pdl_on && m->pdl_chain && !stage_events && !scan3 && !(m->flags & GSDF_MESH_KEEP_GRID);
     if (m->flags & GSDF_MESH_KEEP_GRID) CU(cudaMemsetAsync(m->d_grid, 0x7f, (size_t)D.pitch * (D.ny + 1) * nk * sizeof(float), st));
     // counters and look-back scan state are already zero: re-armed by the previous render's k_finish_render (or by the allocation)
     if (prune) {
-        for (int li = 0; li < m->plan.nlevels; li++) {  // coarse to fine; each level looks only at the children of kept cubes
+        for (int li = 0; li < m->nl3; li++) {  // coarse to fine; each level looks only at the children of kept cubes
+            if (m->fine && li == m->nl3 - 1) {  // levels 3 and 2 in one launch
+                PruneFine pf{};
+                pf.ox = lat.origin[0]; pf.oy = lat.origin[1]; pf.oz = lat.origin[2]; pf.res = lat.res;
+                pf.L = m->lev[li];
+                if (li) { pf.P = m->lev[li - 1]; pf.shift = m->plan.level[li - 1] - m->plan.level[li]; }
+                pf.nx = D.nx; pf.ny = D.ny; pf.nz = D.nz;
+                pf.half2 = m->half2; pf.maxDist2 = m->maxDist2;
+                pf.bits2 = m->d_bits2; pf.childmask = m->d_childmask;
+                pf.kept = m->d_ctr + 4; pf.kept2 = m->d_ctr + 19; pf.evals = m->d_ctr + 7;
+                if ((rc = launch_prune_fine(p, pf, st, pdl && li > 0, m->d_ctr + 8 + 2 * li, li == 0 ? m->d_stamp + 0 : nullptr))) return rc;
+                continue;
+            }
             GenCenters gc{};
             gc.ox = lat.origin[0]; gc.oy = lat.origin[1]; gc.oz = lat.origin[2]; gc.res = lat.res;
             gc.L = m->lev[li];
             if (li) { gc.P = m->lev[li - 1]; gc.shift = m->plan.level[li - 1] - m->plan.level[li]; }
-            gc.kept = li == m->plan.nlevels - 1 ? m->d_ctr + 4 : nullptr;
+            gc.kept = li == m->nl3 - 1 ? m->d_ctr + 4 : nullptr;
             gc.evals = m->d_ctr + 7;
             if ((rc = launch_centers(p, gc, (uint64_t)gc.L.nwx * 32u * gc.L.ncy * gc.L.ncz, st, pdl && li > 0, m->d_ctr + 8 + 2 * li,
                                      li == 0 ? m->d_stamp + 0 : nullptr))) return rc;
@@ -252,14 +279,16 @@ int mesh_run_begin(gsdf_mesher *m) {
         const uint64_t ncrows = (uint64_t)(D.ny + 1) * nk;
         if (blockmc)
             CU(launch_chain(pdl, k_mesh_lists, dim3(grid_for(p->sms, (ncrows * (uint64_t)((D.nqx + 31) >> 5) + 31) / 32, kThreads / 32)), dim3(kThreads), 0, st, D,
-                            (const uint32_t *)m->d_mbits, m->d_list, m->d_ctr + 0, m->d_blklist, m->d_ctr + 5, m->d_stamp + 1));
+                            (const uint32_t *)m->d_mbits, m->d_list, m->d_ctr + 0, m->d_blklist, m->d_ctr + 5, m->d_stamp + 1,
+                            (const uint32_t *)(m->fine ? m->d_bits2 : nullptr)));
         else
         CU(launch_chain(pdl, k_compact_quads, dim3(grid_for(p->sms, (ncrows * (uint64_t)((D.nqx + 31) >> 5) + 31) / 32, kThreads / 32)), dim3(kThreads), 0, st, D, (const uint32_t *)m->d_mbits, m->d_list, m->d_ctr + 0, m->d_stamp + 1));
         CU(cudaGetLastError());
     }
     if (!prune && blockmc) {  // FlatRenderer: every block of the slab is listed (no bit rows, no quad list)
         CU(launch_chain(false, k_mesh_lists, dim3(grid_for(p->sms, ((uint64_t)D.nbz * D.nby * D.nwx + 31) / 32, kThreads / 32)), dim3(kThreads), 0, st, D,
-                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, m->d_blklist, m->d_ctr + 5, (unsigned long long *)nullptr));
+                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, m->d_blklist, m->d_ctr + 5, (unsigned long long *)nullptr,
+                        (const uint32_t *)nullptr));
         CU(cudaGetLastError());
     }
     if (stage_events) CU(cudaEventRecord(m->ev[1], st));
@@ -268,10 +297,10 @@ int mesh_run_begin(gsdf_mesher *m) {
         uint32_t *sched = m->d_ctr + 8 + 2 * GSDF_PRUNE_MAX_LEVELS;
         if (eval_p == 1) {  // latency-bound amount of listed work: one corner per thread, four times as many (short) tiles
             GenGrid<1> g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
-            if ((rc = launch_grid1(p, g, std::min<uint64_t>(nquads, 2 * (uint64_t)m->quad_hint + 1024) * 4, st, pdl && prune, sched, m->d_stamp + 2))) return rc;
+            if ((rc = launch_grid1(p, g, std::min<uint64_t>(nquads, with_margin(m->quad_hint, 1024)) * 4, st, pdl && prune, sched, m->d_stamp + 2))) return rc;
         } else {
             GenGrid<4> g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
-            const uint64_t bound = (prune && m->runs > 0) ? std::min<uint64_t>(nquads, 2 * (uint64_t)m->quad_hint + 1024) : nquads;
+            const uint64_t bound = (prune && m->runs > 0) ? std::min<uint64_t>(nquads, with_margin(m->quad_hint, 1024)) : nquads;
             if ((rc = launch_grid4(p, g, bound, st, pdl && (prune || blockmc), sched, m->d_stamp + 2))) return rc;
         }
     }
@@ -368,9 +397,9 @@ int mesh_run_begin(gsdf_mesher *m) {
         size_t tri_cap;
         ProgView pv;
         unsigned flags;
-        int ext, tma, eval_p, mc_mode;
+        int ext, tma, eval_p, mc_mode, pdl_chain;
         uint32_t quad_hint, blk_hint;
-        const void *blk[2];
+        const void *blk[4];
     } key;
     std::memset(&key, 0, sizeof key);
     const void *kp[10] = {m->d_grid, nullptr, m->d_mbits, m->d_list, m->d_seg, m->d_seglist, m->d_scanstate, m->d_tris, m->d_cases, m->d_segcases};
@@ -379,8 +408,9 @@ int mesh_run_begin(gsdf_mesher *m) {
     key.plan = m->plan; key.prog = p;
     key.tri_cap = m->tri_cap; key.pv = p->pv; key.flags = m->flags; key.ext = p->needs_ext ? 1 : 0; key.tma = (m->use_tma ? 1 : 0) | (m->tile5 ? 2 : 0);
     key.eval_p = eval_p; key.quad_hint = (prune && m->runs > 0) ? m->quad_hint : 0u;
+    key.pdl_chain = m->pdl_chain ? 1 : 0;
     key.mc_mode = m->mc_mode; key.blk_hint = (blockmc && m->runs > 0) ? m->blk_hint : 0u;
-    key.blk[0] = m->d_blklist; key.blk[1] = m->d_blkcnt;
+    key.blk[0] = m->d_blklist; key.blk[1] = m->d_blkcnt; key.blk[2] = m->d_bits2; key.blk[3] = m->d_childmask;
     const bool use_graph = m->allow_graph && !(m->flags & GSDF_MESH_STAGE_TIMING) && emitted && m->runs > 0 && !scan3;
     if (use_graph) {
         if (!m->gexec || m->gkey.size() != sizeof key || std::memcmp(m->gkey.data(), &key, sizeof key) != 0) {
@@ -459,7 +489,10 @@ int mesh_run_end(gsdf_mesher *m) {
         m->quad_hint = (m->h_ctr[0] + 4095u) & ~4095u;
     }
     m->blk_hint = (m->h_ctr[5] + 1023u) & ~1023u;  // listed blocks (block kernels) of this render
-    if (prune) {
+    if (prune && m->fine) {  // the finest cubes of the plan are 2 cells wide: Cube.DecomposesTo(1) = 8
+        const uint64_t n2 = (uint64_t)((D.nx + 1) / 2) * ((D.ny + 1) / 2) * (uint64_t)(((D.cz1 + 1) >> 1) - (D.cz0 >> 1));
+        m->pruned = (n2 - m->h_ctr[19]) * 8ull;
+    } else if (prune) {
         m->pruned = (nblocks - m->h_ctr[4]) * 64ull;  // Cube.DecomposesTo(1) of a level-3 cube = 8^2
     } else {
         m->evals = (uint64_t)(D.nx + 1) * (D.ny + 1) * nk;
@@ -498,6 +531,16 @@ int gsdf_prune_plan_default(const gsdf_lattice *lat, unsigned flags, gsdf_prune_
     if (nblocks >= (1ull << 20)) { out->level[n] = 5; out->margin[n++] = GSDF_PRUNE_MARGIN_DEFAULT; }
     out->level[n] = 3;
     out->margin[n++] = (flags & GSDF_MESH_PRUNE_LITERAL) ? 1.0f : GSDF_PRUNE_MARGIN_DEFAULT;
+    // The 2-cell level (corners of dropped 2-cell cubes inside kept 4-cell blocks are not evaluated: -37 % evaluations on the
+    // reference's example parts) is NOT part of the default plan: at margin 1.25 it loses 714 of the 309,872 triangles of the
+    // README's fibonacci-showerhead run (a steep, non-Lipschitz field; margin 2 would be needed and keeps 82 % of the cubes),
+    // and on flange@400 its extra rounds cost the prune stage what the evaluation saves. Explicit plans may end
+    // with it; GSDF_PRUNE_FINE=1 adds it to the default plan (A/B switch).
+    static const bool fine_on = getenv("GSDF_PRUNE_FINE") != nullptr && getenv("GSDF_PRUNE_FINE")[0] == '1';
+    // (the 2-cell level lives in the kept-block marching-cubes kernels: not with the A/B kernel sets)
+    const char *mc = getenv("GSDF_MC");
+    const bool blockmode = !getenv("GSDF_NO_TMA") && !getenv("GSDF_MC_TILE5") && (!mc || (strcmp(mc, "v1") != 0 && strcmp(mc, "tile5") != 0));
+    if (fine_on && blockmode && !(flags & GSDF_MESH_PRUNE_LITERAL)) { out->level[n] = 2; out->margin[n++] = GSDF_PRUNE_MARGIN_DEFAULT; }
     out->nlevels = n;
     return 0;
 }
@@ -526,9 +569,11 @@ static int mesh_begin_prio(gsdf_program *p, const gsdf_lattice *lat, int cz0, in
     if (plan) {
         flags |= GSDF_MESH_PRUNE;
         pl = *plan;
-        if (pl.nlevels < 1 || pl.nlevels > GSDF_PRUNE_MAX_LEVELS || pl.level[pl.nlevels - 1] != 3) return fail(GSDF_EINVAL, "prune plan: 1..%d levels, the last one level 3", GSDF_PRUNE_MAX_LEVELS);
+        const bool ends2 = pl.nlevels >= 2 && pl.nlevels <= GSDF_PRUNE_MAX_LEVELS && pl.level[pl.nlevels - 1] == 2 && pl.level[pl.nlevels - 2] == 3;
+        if (pl.nlevels < 1 || pl.nlevels > GSDF_PRUNE_MAX_LEVELS || (pl.level[pl.nlevels - 1] != 3 && !ends2))
+            return fail(GSDF_EINVAL, "prune plan: 1..%d levels ending with level 3, or with level 3 followed by level 2", GSDF_PRUNE_MAX_LEVELS);
         for (int i = 0; i < pl.nlevels; i++) {
-            if (pl.level[i] < 3 || pl.level[i] > 12 || (i && pl.level[i] >= pl.level[i - 1])) return fail(GSDF_EINVAL, "prune plan: levels must descend strictly within [3, 12]");
+            if (pl.level[i] < 2 || pl.level[i] > 12 || (i && pl.level[i] >= pl.level[i - 1])) return fail(GSDF_EINVAL, "prune plan: levels must descend strictly within [2, 12]");
             if (!(pl.margin[i] >= 1.0f) || std::isinf(pl.margin[i])) return fail(GSDF_EINVAL, "prune plan: margins must be finite and >= 1");
         }
     } else if (flags & GSDF_MESH_PRUNE) {
@@ -564,7 +609,16 @@ static int mesh_begin_prio(gsdf_program *p, const gsdf_lattice *lat, int cz0, in
     D.pitch = D.nqx * 4;
     D.nsx = (D.nx + 31) / 32;
     D.nwx = (D.nbx + 31) / 32;
-    for (int li = 0; li < pl.nlevels; li++) {  // cubes of level L are 2^(L-1) cells wide and aligned to the lattice origin
+    m->fine = pl.nlevels >= 2 && pl.level[pl.nlevels - 1] == 2;
+    // the 2-cell level lives in the kept-block marching-cubes kernels only; the A/B kernel sets fall back to the plan's level 3
+    if (m->fine && !(m->use_tma && m->mc_mode == 2)) { m->fine = false; pl.nlevels--; m->plan = pl; }
+    m->nl3 = pl.nlevels - (m->fine ? 1 : 0);
+    if (m->fine) {
+        const float size2 = lat->res * 2.0f;
+        m->half2 = size2 * 0.5f;
+        m->maxDist2 = size2 * (float)(1.73205080757 / 2) * pl.margin[pl.nlevels - 1];
+    }
+    for (int li = 0; li < m->nl3; li++) {  // cubes of level L are 2^(L-1) cells wide and aligned to the lattice origin
         PruneLevel &Lv = m->lev[li];
         Lv.w = 1 << (pl.level[li] - 1);
         Lv.ncx = (D.nx + Lv.w - 1) / Lv.w; Lv.ncy = (D.ny + Lv.w - 1) / Lv.w;
@@ -720,6 +774,7 @@ void gsdf_mesh_destroy(gsdf_mesher *m) {
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->prog && m->ev[4]) program_remove_dependent(m->prog, m->ev[4]);
     for (auto &b : m->d_lbits) cudaFree(b);
+    cudaFree(m->d_bits2); cudaFree(m->d_childmask);
     cudaFree(m->d_grid); cudaFree(m->d_list); cudaFree(m->d_seg); cudaFree(m->d_seglist); cudaFree(m->d_segcases); cudaFree(m->d_scanstate); cudaFree(m->d_blocksum);
     cudaFree(m->d_blklist); cudaFree(m->d_blkcnt);
     cudaFree(m->d_tris); cudaFree(m->d_cases); cudaFree(m->d_stl); cudaFree(m->d_ctr);
@@ -792,6 +847,17 @@ static int mesh_begin_prio(gsdf_program *p, const gsdf_lattice *lat, int cz0, in
                            int stream_priority, gsdf_mesher **out);
 
 namespace {
+
+// Programmatic dependent launch per slab. The chain of the slab that leaves first is latency critical and keeps it; under
+// it the CTAs of kernel i+1 are resident (waiting) while kernel i runs, which on a device shared by several slabs keeps the
+// other slabs' kernels out (measured: three slabs ran one after the other, 68 + 106 + 98 us). The later slabs of a device
+// are launched plainly and overlap. GSDF_MULTI_PDL=all|first|none is the A/B switch (default first).
+bool multi_slab_pdl(const gsdf_multimesher *mm, int j) {
+    static const char *mode = getenv("GSDF_MULTI_PDL");
+    if (mode && !strcmp(mode, "all")) return true;
+    if (mode && !strcmp(mode, "none")) return false;
+    return j / mm->ndev == 0;
+}
 
 // the k-th slab of a device leaves k-th: earlier slabs get the higher stream priority
 int multi_slab_priority(const gsdf_multimesher *mm, int j) {
@@ -974,6 +1040,7 @@ int gsdf_multi_begin(int ndev, const int *devs, int slabs_per_device, const void
     for (int j = 0; j < nslabs && !rc; j++) {
         if (mm->cuts[j + 1] <= mm->cuts[j]) { rc = fail(GSDF_EINVAL, "internal: empty Z-slab %d", j); break; }
         rc = mesh_begin_prio(mm->prog[j % mm->ndev], lat, mm->cuts[j], mm->cuts[j + 1], flags, nullptr, multi_slab_priority(mm, j), &mm->slab[j]);
+        if (!rc) mm->slab[j]->pdl_chain = multi_slab_pdl(mm, j);
     }
     if (rc) { gsdf_multi_destroy(mm); return rc; }
     // totals of the construction render
@@ -1040,6 +1107,16 @@ int64_t gsdf_multi_render(gsdf_multimesher *mm, float *tri9, size_t max_tris) {
         }
     }
     mm->device_ms = ms;
+    static const bool dbg_stamps = getenv("GSDF_MULTI_DEBUG") != nullptr;  // profiles: the slabs' in-graph stage stamps on one clock
+    if (dbg_stamps) {
+        unsigned long long t0 = ~0ull;
+        for (int j = 0; j < mm->nslabs; j++) for (int k = 0; k < kMeshStamps; k++) if (mm->slab[j]->h_stamp[k]) t0 = std::min(t0, mm->slab[j]->h_stamp[k]);
+        for (int j = 0; j < mm->nslabs; j++) {
+            const unsigned long long *t = mm->slab[j]->h_stamp;
+            auto us = [&](int k) { return t[k] ? (double)(t[k] - t0) * 1e-3 : -1.0; };
+            fprintf(stderr, "  slab %d stamps us: prune %.1f lists %.1f eval %.1f count %.1f scan %.1f emit %.1f end %.1f\n", j, us(0), us(1), us(2), us(3), us(4), us(5), us(7));
+        }
+    }
     mm->timeline.back() = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - mm->t_call).count();
     mm->rendered = true;
     mm->read_pos = 0;
@@ -1085,6 +1162,7 @@ int gsdf_multi_rebalance(gsdf_multimesher *mm, int rounds) {
             gsdf_mesher *fresh = nullptr;
             const int rc = mesh_begin_prio(mm->prog[j % mm->ndev], &mm->lat, cuts[j], cuts[j + 1], mm->flags, nullptr, multi_slab_priority(mm, j), &fresh);
             if (rc) return rc;  // the old partition stays valid up to slab j; the caller sees the error
+            fresh->pdl_chain = multi_slab_pdl(mm, j);
             gsdf_mesh_destroy(mm->slab[j]);
             mm->slab[j] = fresh;
         }

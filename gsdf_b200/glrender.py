@@ -47,7 +47,7 @@ class _Renderer:
               prune=None):
         """prune (Octree only): None = the default plan (level 3 with margin 1.25, coarse levels in front on large
         lattices); "literal" = the reference's rule at every level-3 cube (margin 1); or an explicit plan
-        [(level, margin), ...] ending with level 3 (include/gsdf_b200.h, gsdf_prune_plan)."""
+        [(level, margin), ...] ending with level 3 or with levels 3, 2 (include/gsdf_b200.h, gsdf_prune_plan)."""
         if not (cubeResolution > 0):
             raise GsdfError(_lib.EINVAL, "invalid renderer cube resolution")  # flatrenderer.go:38, octreerenderer.go:73
         self.Close()

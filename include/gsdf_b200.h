@@ -129,15 +129,18 @@ enum {
  * hold surface, which the reference's own runs do not lose (README.md:152: 309,872 triangles from both renderers).
  * A plan is a list of levels, coarse to fine (level L = cubes of 2^(L-1) cells, aligned to the lattice origin like
  * ms3.Octree cubes); a cube is kept iff |d(centre)| < margin * size * sqrt3/2 and only the children of kept cubes are
- * looked at on the next level. The last level must be 3 (the marching-cubes stage works on 4-cell blocks).
+ * looked at on the next level. A plan ends with level 3 (the marching-cubes stage works on 4-cell blocks), optionally
+ * followed by level 2: the 2-cell cubes inside kept blocks decide which lattice corners are evaluated at all and which
+ * cells the marching-cubes stage looks at (levels 3 and 2 run as one launch).
  * Default plan (GSDF_MESH_PRUNE): level 3 with margin GSDF_PRUNE_MARGIN_DEFAULT, preceded by a coarse level on large
  * lattices; it reproduces the dense sweep on every scene of the reference's examples, the README's two known answers
- * included. GSDF_MESH_PRUNE_LITERAL: the same levels with margin 1 (bit-equal to the dense sweep on 1-Lipschitz fields). */
+ * included (level 2 is left to explicit plans: with margin 1.25 it loses triangles on the steepest of those fields).
+ * GSDF_MESH_PRUNE_LITERAL: the same levels with margin 1 (bit-equal to the dense sweep on 1-Lipschitz fields). */
 #define GSDF_PRUNE_MARGIN_DEFAULT 1.25f
 #define GSDF_PRUNE_MAX_LEVELS 4
 typedef struct {
     int32_t nlevels;
-    int32_t level[GSDF_PRUNE_MAX_LEVELS];  /* strictly descending, each in [3, 12], last == 3 */
+    int32_t level[GSDF_PRUNE_MAX_LEVELS];  /* strictly descending, each in [2, 12], ending with 3 or with 3, 2 */
     float margin[GSDF_PRUNE_MAX_LEVELS];   /* >= 1 */
 } gsdf_prune_plan;
 /* The plan gsdf_mesh_begin uses for `flags` on this lattice. */

@@ -56,7 +56,7 @@ def test_flange_resdiv400_whole_lattice(oracle, bld):
         assert np.array_equal(R.Cases(), wpc)
         assert np.array_equal(bits(R.AllTriangles()), bits(want))
         assert R.STLBytes() == wstl
-        assert R.TotalPruned() == (mask.size - kept) * 64
+        assert R.TotalPruned() == (mask.size - kept) * (1 << (R.Plan()[-1][0] - 1)) ** 3
         assert centres < R.Evaluations() < ev // 3
         R.Close()
     F.Close()

@@ -266,7 +266,8 @@ def oracle_mesh(oracle, s, res, plan):
     return lat, grid, mask, tris, cases, centres
 
 
-PLANS = {"flat": False, "default": None, "literal": "literal", "two-level": [(5, 1.25), (3, 1.25)], "three-level-literal": [(6, 1.0), (4, 1.0), (3, 1.0)]}
+PLANS = {"flat": False, "default": None, "literal": "literal", "level-3": [(3, 1.25)], "two-level": [(5, 1.25), (3, 1.25)],
+         "three-level-literal": [(6, 1.0), (4, 1.0), (3, 1.0)], "fine": [(3, 1.25), (2, 1.25)], "three-level-fine": [(5, 1.25), (3, 1.25), (2, 1.5)]}
 
 
 def test_sphere_41072_on_gpu(oracle, bld):
@@ -300,7 +301,7 @@ def test_mesh_bit_identical_to_oracle(oracle, bld, scene, resdiv, prune):
         R = glrender.Octree(sdf, res, keep_cases=True, keep_grid=True, prune=PLANS[prune])
     prune = PLANS[prune] is not False
     if prune:
-        assert R.Plan()[-1][0] == 3
+        assert R.Plan()[-1][0] in (2, 3)   # explicit plans may end with the 2-cell level
     lat, grid, mask, wt, wc, centres = oracle_mesh(oracle, s, res, R.Plan())
     assert list(R.lat.n) == list(lat.n)
     cases = R.Cases()
@@ -314,7 +315,7 @@ def test_mesh_bit_identical_to_oracle(oracle, bld, scene, resdiv, prune):
         assert R.Evaluations() == grid.size and R.TotalPruned() == 0
     else:
         kept = int(mask.sum())
-        assert R.TotalPruned() == (mask.size - kept) * 64
+        assert R.TotalPruned() == (mask.size - kept) * (1 << (R.Plan()[-1][0] - 1)) ** 3   # Cube.DecomposesTo(1) of the finest cubes
         g = R.Grid()                                           # evaluated corners agree; pruned ones hold the fill value
         ev = bits(g) != np.uint32(0x7f7f7f7f)
         assert np.array_equal(bits(g)[ev], bits(grid)[ev]) and ev.sum() < grid.size
