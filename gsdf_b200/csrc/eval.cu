@@ -17,7 +17,7 @@ constexpr int kMaxDev = 64;
 struct KernelDevCache {
     std::mutex mu;
     bool optin[kMaxDev] = {};
-    struct Occ { uint32_t smem; int occ; };
+    struct Occ { uint32_t smem; int threads; int occ; };
     std::vector<Occ> occ[kMaxDev];
 };
 
@@ -33,41 +33,56 @@ int kernel_occupancy(KernelDevCache &c, Kern kern, int dev, uint32_t smem, int t
         c.optin[dev] = true;
     }
     for (const auto &o : c.occ[dev])
-        if (o.smem == smem) { *occ_out = o.occ; return 0; }
+        if (o.smem == smem && o.threads == threads) { *occ_out = o.occ; return 0; }
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-    c.occ[dev].push_back({smem, occ});
+    c.occ[dev].push_back({smem, threads, occ});
     *occ_out = occ;
     return 0;
 }
 
 // persistent launch: at most one resident wave of CTAs; they pull tiles from the launch's scheduler slot
+// CTA size of a launch. The kernels are compiled for kEvalThreads (launch bounds, register cap) and may be launched with
+// fewer threads: every lockstep barrier then spans fewer warps and an SM holds more independent CTAs. Measured on B200
+// (scripts/gpu_r2_ab_cta.sh: 128 against 384 threads, flange@400 / bolt@400 / knurled@500 lattice evaluation): 67 / 63 / 508 us
+// against 70 / 72 / 442 us -- short programs gain, the 40-instruction knurled tree with its large opcode bodies (atan2, two
+// sincos per circular-array entry) loses to instruction-cache misses of nine free-running CTAs per SM. Hence: small CTAs
+// for programs of at most kSmallProgram instructions and for the one-point-per-thread centre pass (latency bound); the
+// compiled size otherwise. GSDF_EVAL_CTA=<threads> overrides (A/B).
+constexpr int kSmallCta = 128;
+constexpr uint32_t kSmallProgram = 24;
+int eval_cta_threads(const gsdf_program *p, bool latency_bound) {
+    static const int forced = getenv("GSDF_EVAL_CTA") ? atoi(getenv("GSDF_EVAL_CTA")) : 0;
+    if (forced >= 32 && forced <= kEvalThreads && forced % 32 == 0) return forced;
+    return (latency_bound || p->ninstr <= kSmallProgram) ? kSmallCta : kEvalThreads;
+}
+
 template <int P, class Gen, bool EXT>
 int launch_eval_impl(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st, bool pdl, uint32_t *sched,
-                     unsigned long long *stamp) {
+                     unsigned long long *stamp, int threads) {
     static KernelDevCache cache;
     auto kern = k_eval<P, Gen, EXT>;
-    const uint32_t smem = smem_total_bytes<P>(p->pv, kEvalThreads);
+    const uint32_t smem = smem_total_bytes<P>(p->pv, threads);
     int occ = 0;
-    const int rc = kernel_occupancy(cache, kern, p->device, smem, kEvalThreads, &occ);
+    const int rc = kernel_occupancy(cache, kern, p->device, smem, threads, &occ);
     if (rc) return rc;
     if (occ < 1) return fail(GSDF_EPROGRAM, "node program needs %u bytes of shared memory per CTA; does not fit", smem);
-    uint64_t blocks = (nwork_upper_bound + kEvalThreads - 1) / kEvalThreads;
+    uint64_t blocks = (nwork_upper_bound + threads - 1) / threads;
     blocks = std::min<uint64_t>(blocks, (uint64_t)p->sms * occ);
     ProgView pv = p->pv;
     pv.sched = sched ? sched : next_sched(p);
     pv.stamp = stamp;
-    if (pdl) CU(launch_chain(true, kern, dim3((unsigned)blocks), dim3(kEvalThreads), smem, st, pv, gen));
-    else kern<<<(unsigned)blocks, kEvalThreads, smem, st>>>(pv, gen);
+    if (pdl) CU(launch_chain(true, kern, dim3((unsigned)blocks), dim3(threads), smem, st, pv, gen));
+    else kern<<<(unsigned)blocks, threads, smem, st>>>(pv, gen);
     CU(cudaGetLastError());
     return 0;
 }
 template <int P, class Gen>
 int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st, bool pdl, uint32_t *sched,
-                unsigned long long *stamp = nullptr) {
+                unsigned long long *stamp = nullptr, int threads = kEvalThreads) {
     if (nwork_upper_bound == 0) return 0;
-    return p->needs_ext ? launch_eval_impl<P, Gen, true>(p, gen, nwork_upper_bound, st, pdl, sched, stamp)
-                        : launch_eval_impl<P, Gen, false>(p, gen, nwork_upper_bound, st, pdl, sched, stamp);
+    return p->needs_ext ? launch_eval_impl<P, Gen, true>(p, gen, nwork_upper_bound, st, pdl, sched, stamp, threads)
+                        : launch_eval_impl<P, Gen, false>(p, gen, nwork_upper_bound, st, pdl, sched, stamp, threads);
 }
 
 template <bool EXT>
@@ -132,26 +147,28 @@ uint32_t *next_sched(const gsdf_program *p, int *slot_index) {
 int launch_points3(const gsdf_program *p, const GenPoints3 &g, uint64_t nwork, cudaStream_t st, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, false, sched); }
 int launch_points2(const gsdf_program *p, const GenPoints2 &g, uint64_t nwork, cudaStream_t st, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, false, sched); }
 int launch_grid4(const gsdf_program *p, const GenGrid<4> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
-    return launch_eval<4>(p, g, nwork, st, pdl, sched, stamp);
+    return launch_eval<4>(p, g, nwork, st, pdl, sched, stamp, eval_cta_threads(p, false));
 }
 int launch_grid1(const gsdf_program *p, const GenGrid<1> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
-    return launch_eval<1>(p, g, nwork, st, pdl, sched, stamp);
+    return launch_eval<1>(p, g, nwork, st, pdl, sched, stamp, eval_cta_threads(p, true));
 }
 int launch_prune_fine(const gsdf_program *p, const PruneFine &g, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
     return p->needs_ext ? launch_prune_fine_impl<true>(p, g, st, pdl, sched, stamp) : launch_prune_fine_impl<false>(p, g, st, pdl, sched, stamp);
 }
-int eval_cta_slots(const gsdf_program *p, int *slots) {
+int eval_cta_slots(const gsdf_program *p, int *slots, int *threads_out) {
     static KernelDevCache cache;  // occupancy of the P = 4 lattice kernel (the P = 1 form is never lower)
     int occ = 0;
-    const uint32_t smem = smem_total_bytes<4>(p->pv, kEvalThreads);
-    const int rc = p->needs_ext ? kernel_occupancy(cache, k_eval<4, GenGrid<4>, true>, p->device, smem, kEvalThreads, &occ)
-                                : kernel_occupancy(cache, k_eval<4, GenGrid<4>, false>, p->device, smem, kEvalThreads, &occ);
+    const int threads = eval_cta_threads(p, false);
+    const uint32_t smem = smem_total_bytes<4>(p->pv, threads);
+    const int rc = p->needs_ext ? kernel_occupancy(cache, k_eval<4, GenGrid<4>, true>, p->device, smem, threads, &occ)
+                                : kernel_occupancy(cache, k_eval<4, GenGrid<4>, false>, p->device, smem, threads, &occ);
     if (rc) return rc;
     *slots = p->sms * std::max(occ, 1);
+    if (threads_out) *threads_out = threads;
     return 0;
 }
 int launch_centers(const gsdf_program *p, const GenCenters &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
-    return launch_eval<1>(p, g, nwork, st, pdl, sched, stamp);
+    return launch_eval<1>(p, g, nwork, st, pdl, sched, stamp, eval_cta_threads(p, true));
 }
 int launch_image(const gsdf_program *p, const GenImage &g, uint64_t nwork, cudaStream_t st, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, false, sched); }
 int launch_dc(const gsdf_program *p, const GenDC &g, uint64_t nwork, cudaStream_t st, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, false, sched); }

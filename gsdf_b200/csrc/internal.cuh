@@ -158,8 +158,8 @@ int launch_grid4(const gsdf_program *p, const gsdfk::GenGrid<4> &g, uint64_t nwo
 // one resident wave, where the render is bound by the latency of a tile, not by throughput. nwork counts quads x 4.
 int launch_grid1(const gsdf_program *p, const gsdfk::GenGrid<1> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched,
                  unsigned long long *stamp = nullptr);
-// resident CTA slots of the lattice-evaluation kernel for this program (SMs x occupancy)
-int eval_cta_slots(const gsdf_program *p, int *slots);
+// resident CTA slots of the lattice-evaluation kernel for this program (SMs x occupancy) and the CTA size it is launched with
+int eval_cta_slots(const gsdf_program *p, int *slots, int *threads = nullptr);
 int launch_centers(const gsdf_program *p, const gsdfk::GenCenters &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched,
                    unsigned long long *stamp = nullptr);
 // prune levels 3 and 2 of a plan that ends with level 2, in one launch (k_prune_fine)

@@ -48,8 +48,7 @@ struct BlkArgs {
     unsigned long long *fin_dstamp; volatile unsigned long long *fin_hstamp; int fin_nstamp;
     uint32_t *fin_done;
     // the emit pass runs the segment scan itself (no k_scan_seg launch): scan_state != nullptr
-    unsigned long long *scan_state; uint32_t *scan_ticket, *scan_done; uint32_t scan_epoch, scan_nseg; unsigned long long *scan_total;
-};
+    unsigned long long *scan_state; uint32_t *scan_ticket, *scan_done; uint32_t scan_epoch, scan_nseg; unsigned long long *scan_total;};
 
 // ---------------------------------------------------------------------------------------------- prune -> work lists
 // Quad list exactly as k_compact_quads (lane per 32-quad word of a corner row), then the kept-block list (lane per 32-block
@@ -203,7 +202,29 @@ __device__ __forceinline__ uint32_t blk_segment(const MeshDims &D, int bx, int c
 }
 
 // ---------------------------------------------------------------------------------------------- pass 1
-// Lane l: cell column lx = l & 3, row ly = (l >> 2) & 3, layers lz = l >> 4 and lz + 2.
+// Pass 1 of one block from its staged stencil. Lane l: cell column lx = l & 3, row ly = (l >> 2) & 3, layers lz = l >> 4 and
+// lz + 2. Writes the triangle count of each of the block's 16 cell rows (and the case indices in parity mode).
+__device__ __forceinline__ void blk_count_block(const BlkArgs &A, const BlkPos &b, uint32_t cm, const float *buf, const uint8_t *s_ntri, int lane) {
+    const MeshDims &D = A.D;
+    const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
+    const int cx = b.x0 + lx, cy = b.y0 + ly;
+    const bool okxy = cx < D.nx && cy < D.ny;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int lzz = lz + 2 * h, cz = b.z0 + lzz;
+        // (h = child layer dz: lz is 0 or 1) corners of a dropped 2-cell cube were never evaluated: its cells hold no surface
+        const bool valid = okxy && cz >= D.cz0 && cz < D.cz1 && ((cm >> ((lx >> 1) + 2 * (ly >> 1) + 4 * h)) & 1u);
+        const int idx = blk_case(buf, lx, ly, lzz, valid, A.cubeDiag);
+        uint32_t n = s_ntri[idx];
+        n += __shfl_xor_sync(0xffffffffu, n, 1);
+        n += __shfl_xor_sync(0xffffffffu, n, 2);  // the four cells of the row
+        if (cy < D.ny && cz >= D.cz0 && cz < D.cz1) {
+            if (lx == 0) reinterpret_cast<uint8_t *>(A.blkcnt + blk_segment(D, b.bx, cy, cz))[b.bx & 7] = (uint8_t)n;
+            if (A.cases && cx < D.nx) A.cases[((size_t)(cz - D.cz0) * D.ny + cy) * D.nx + cx] = (uint8_t)idx;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kBlkWarps * 32) k_mc_blk_count(const __grid_constant__ CUtensorMap tmap, BlkArgs A) {
     __shared__ __align__(128) uint8_t s_buf[kBlkWarps][2][kBlkBufStride];
     __shared__ __align__(8) uint64_t s_bar[kBlkWarps][2];
@@ -223,7 +244,6 @@ __global__ void __launch_bounds__(kBlkWarps * 32) k_mc_blk_count(const __grid_co
     const MeshDims &D = A.D;
     const uint32_t nblk = *A.nblk;
     const uint32_t stride = gridDim.x * kBlkWarps;
-    const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
     uint32_t phases = 0u;  // bit b = parity to wait for on buffer b
     uint32_t it = blockIdx.x * kBlkWarps + warp;
     int cur = 0;
@@ -235,23 +255,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) k_mc_blk_count(const __grid_co
         const uint32_t cm = A.childmask ? A.childmask[A.blklist[it]] : 0xffu;
         blk_wait(cur ? bar1 : bar0, (phases >> cur) & 1u);
         phases ^= 1u << cur;
-        const float *buf = reinterpret_cast<const float *>(s_buf[warp][cur]);
-        const int cx = b.x0 + lx, cy = b.y0 + ly;
-        const bool okxy = cx < D.nx && cy < D.ny;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int lzz = lz + 2 * h, cz = b.z0 + lzz;
-            // (h = child layer dz: lz is 0 or 1) corners of a dropped 2-cell cube were never evaluated: its cells hold no surface
-            const bool valid = okxy && cz >= D.cz0 && cz < D.cz1 && ((cm >> ((lx >> 1) + 2 * (ly >> 1) + 4 * h)) & 1u);
-            const int idx = blk_case(buf, lx, ly, lzz, valid, A.cubeDiag);
-            uint32_t n = s_ntri[idx];
-            n += __shfl_xor_sync(0xffffffffu, n, 1);
-            n += __shfl_xor_sync(0xffffffffu, n, 2);  // the four cells of the row
-            if (cy < D.ny && cz >= D.cz0 && cz < D.cz1) {
-                if (lx == 0) reinterpret_cast<uint8_t *>(A.blkcnt + blk_segment(D, b.bx, cy, cz))[b.bx & 7] = (uint8_t)n;
-                if (A.cases && cx < D.nx) A.cases[((size_t)(cz - D.cz0) * D.ny + cy) * D.nx + cx] = (uint8_t)idx;
-            }
-        }
+        blk_count_block(A, b, cm, reinterpret_cast<const float *>(s_buf[warp][cur]), s_ntri, lane);
         __syncwarp();  // everybody is done with buf before it is refilled two iterations later
     }
 }
@@ -375,12 +379,139 @@ __global__ void __launch_bounds__(kThreads) k_scan_seg(MeshDims D, const uint32_
 }
 
 // ---------------------------------------------------------------------------------------------- pass 2
+constexpr int kBlkListCap = 32 * 5;  // triangles of one half-block (32 cells, at most 5 each)
+
+// What pass 1 left for the lane's two cell rows (ly, lz) and (ly, lz + 2) of block b: the row's triangle count and where
+// the row's triangles start in the output (segment offset + the kept block slots in front of this one). cg: the offsets were
+// written during this kernel (scan inside the pass): read them around L1. (Loading the rows of block i+1 before block i is
+// emitted was measured: 63 instead of 40 registers, no gain.)
+__device__ __forceinline__ void blk_emit_rows(const BlkArgs &A, const BlkPos &b, int lane, bool cg, uint32_t (&rown)[2], uint32_t (&rowbase)[2]) {
+    const MeshDims &D = A.D;
+    const int ly = (lane >> 2) & 3, lz = lane >> 4;
+    const int cy = b.y0 + ly;
+    rown[0] = rown[1] = 0u; rowbase[0] = rowbase[1] = 0u;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int cz = b.z0 + lz + 2 * h;
+        if (cy < D.ny && cz >= D.cz0 && cz < D.cz1) {
+            const uint32_t seg = blk_segment(D, b.bx, cy, cz);
+            const uint2 c = cg ? __ldcg(A.blkcnt + seg) : A.blkcnt[seg];
+            const int slot = b.bx & 7;
+            rown[h] = ((slot < 4 ? c.x : c.y) >> (8 * (slot & 3))) & 0xffu;
+            if (rown[h]) {  // triangles of the kept slots in front of this block, behind the segment's offset
+                const uint32_t kb = seg_kept_bits(D, A.mbits, (uint32_t)(cz - D.cz0) * (uint32_t)D.ny + (uint32_t)cy, (uint32_t)(b.bx >> 3));
+                const uint32_t so = cg ? __ldcg(A.segoff + seg) : A.segoff[seg];
+                rowbase[h] = so + seg_masked_sum(c, kb, slot);
+            }
+        }
+    }
+}
+
+// The triangles of block b from its staged stencil (warp-uniform call). Per half-block (h = 0: layers 0, 1; h = 1: layers
+// 2, 3) every lane lists the triangles of its cell at the positions the warp scan of the counts gives (the warp-level scan
+// north_star asks for) -- one entry per triangle: output slot, cube case, triangle number within the cell, cell -- and the
+// vertices are then dealt round-robin, lane = vertex: a vertex finds its triangle with one shared-memory load. A cell's
+// triangles start at its row's base + the cells in front of it in the row: FlatRenderer cell order, deterministic.
+__device__ __forceinline__ void blk_emit_tris(const BlkArgs &A, const BlkPos &b, uint32_t cm, const float *buf, const uint8_t *s_ntri, const int8_t *s_tris,
+                                              uint2 *lst, int lane, const uint32_t (&rown)[2], const uint32_t (&rowbase)[2]) {
+    const MeshDims &D = A.D;
+    const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
+    const int cx = b.x0 + lx, cy = b.y0 + ly;
+    const bool okxy = cx < D.nx && cy < D.ny;
+    const float rr = A.res;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        if (__ballot_sync(0xffffffffu, rown[h] != 0u) == 0u) continue;  // warp-uniform
+        const int lzz = lz + 2 * h, cz = b.z0 + lzz;
+        const bool valid = okxy && cz >= D.cz0 && cz < D.cz1 && rown[h] != 0u && ((cm >> ((lx >> 1) + 2 * (ly >> 1) + 4 * h)) & 1u);
+        const int index = valid ? blk_case(buf, lx, ly, lzz, true, A.cubeDiag) : 0;
+        const uint32_t n = s_ntri[index];
+        // cells in front of this one in its row: exclusive prefix over the 4 lanes of the row
+        const uint32_t a1 = __shfl_up_sync(0xffffffffu, n, 1), a2 = __shfl_up_sync(0xffffffffu, n, 2), a3 = __shfl_up_sync(0xffffffffu, n, 3);
+        const uint32_t obase = rowbase[h] + (lx >= 1 ? a1 : 0u) + (lx >= 2 ? a2 : 0u) + (lx >= 3 ? a3 : 0u);
+        const uint32_t incl = warp_incl_scan(n);
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t k = 0; k < n; k++) lst[incl - n + k] = make_uint2(obase + k, (uint32_t)index | (k << 8) | ((uint32_t)lane << 11));
+        __syncwarp();
+        for (uint32_t item = lane; item < 3u * total; item += 32) {
+            const uint32_t tri = item / 3u, j = item - 3u * tri;
+            const uint2 ent = lst[tri];
+            const uint64_t o = ent.x;
+            if (o >= A.tri_capacity) { *A.overflow = 1u; continue; }
+            const int oindex = (int)(ent.y & 0xffu);
+            const uint32_t kk = (ent.y >> 8) & 7u;
+            const int owner = (int)(ent.y >> 11);
+            const int olx = owner & 3, oly = (owner >> 2) & 3, olz = (owner >> 4) + 2 * h;
+            // corner positions, flatrenderer.go:235-247
+            const float px0 = A.ox + (float)(b.x0 + olx) * rr, px1 = px0 + rr;
+            const float py0 = A.oy + (float)(b.y0 + oly) * rr, py1 = py0 + rr;
+            const float pz0 = A.oz + (float)(b.z0 + olz) * rr, pz1 = pz0 + rr;
+            // marchcubes.go:64-68: vertex j of the triangle is points[table[3k + 2 - j]]
+            const int e = s_tris[16 * oindex + 3 * (int)kk + 2 - (int)j];
+            // edge -> corner pair (marchcubes.go:101-114), packed 4 bits per edge
+            const int ca = (int)((0x321076543210ull >> (4 * e)) & 0xf), cb = (int)((0x765447650321ull >> (4 * e)) & 0xf);
+            const float3 pa = make_float3((((ca + 1) >> 1) & 1) ? px1 : px0, ((ca >> 1) & 1) ? py1 : py0, (ca >> 2) ? pz1 : pz0);
+            const float3 pb = make_float3((((cb + 1) >> 1) & 1) ? px1 : px0, ((cb >> 1) & 1) ? py1 : py0, (cb >> 2) ? pz1 : pz0);
+            // corner c of the cell: x bit ((c+1)>>1)&1, y bit (c>>1)&1, z bit c>>2 (flatrenderer.go:222-233)
+            const float *cc = buf + (olz * 5 + oly) * 8 + olx;
+            const float va = cc[(ca >> 2) * 40 + ((ca >> 1) & 1) * 8 + (((ca + 1) >> 1) & 1)];
+            const float vb = cc[(cb >> 2) * 40 + ((cb >> 1) & 1) * 8 + (((cb + 1) >> 1) & 1)];
+            const float3 q = mc_interp(pa, pb, va, vb);
+            float *dst = A.tris + 9 * o + 3 * j;
+            dst[0] = q.x; dst[1] = q.y; dst[2] = q.z;
+        }
+        __syncwarp();  // the list is rewritten by the next half-block
+    }
+}
+
+// The scan phase of a pass that scans by itself: CTAs take scan tiles by ticket until none is left. A tile only ever waits
+// for tiles with smaller tickets, i.e. for CTAs that are already running, so no co-residency of the whole grid is needed;
+// then one thread per CTA waits (with back-off) until every tile has written its offsets. All threads of the CTA call.
+__device__ __forceinline__ void blk_scan_phase(const BlkArgs &A, uint32_t *s_w, uint32_t *s_tile, uint32_t *s_prefix) {
+    const uint32_t ntiles = (A.scan_nseg + kScanTile - 1) / kScanTile;
+    for (;;) {
+        if (threadIdx.x == 0) *s_tile = *reinterpret_cast<volatile uint32_t *>(A.scan_ticket) >= ntiles ? ntiles : atomicAdd(A.scan_ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = *s_tile;
+        if (tile >= ntiles) break;
+        scan_seg_tile(A.D, A.mbits, A.blkcnt, A.segoff, A.scan_nseg, A.scan_state, A.scan_epoch, A.scan_total, tile, s_w, s_prefix, A.scan_done);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        uint32_t d;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(d) : "l"(A.scan_done) : "memory");
+            if (d >= ntiles) break;
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+
+// The last CTA of the render's last kernel publishes the counters and re-arms the state (k_finish_render's work, without
+// its launch). All threads of the CTA call.
+__device__ __forceinline__ void blk_finish(const BlkArgs &A, uint32_t *s_last) {
+    if (!A.fin_ctr) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        *s_last = atomicAdd(A.fin_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (*s_last) {
+        __threadfence();
+        finish_render_cta(A.fin_ctr, A.fin_hctr, A.fin_nctr, A.fin_scanstate, A.fin_nstate, A.fin_dstamp, A.fin_hstamp, A.fin_nstamp);
+    }
+}
+
 __global__ void __launch_bounds__(kBlkWarps * 32) k_mc_blk_emit(const __grid_constant__ CUtensorMap tmap, BlkArgs A) {
     __shared__ __align__(128) uint8_t s_buf[kBlkWarps][2][kBlkBufStride];
     __shared__ __align__(8) uint64_t s_bar[kBlkWarps][2];
     __shared__ uint8_t s_ntri[256];
     __shared__ __align__(16) int8_t s_tris[256 * 16];
-    __shared__ uint2 s_list[kBlkWarps][64 * 5];  // per warp: the triangles of the block being emitted (a cell has at most 5)
+    __shared__ uint2 s_list[kBlkWarps][kBlkListCap];
+    __shared__ uint32_t s_w[kThreads / 32];
+    __shared__ uint32_t s_tile, s_prefix[2], s_last;
     pdl_trigger();
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ntri[i] = A.t_ntri[i];
     for (int i = threadIdx.x; i < 256 * 16 / 16; i += blockDim.x) reinterpret_cast<uint4 *>(s_tris)[i] = reinterpret_cast<const uint4 *>(A.t_tris)[i];
@@ -397,142 +528,27 @@ __global__ void __launch_bounds__(kBlkWarps * 32) k_mc_blk_emit(const __grid_con
     const MeshDims &D = A.D;
     const uint32_t nblk = *A.nblk;
     const uint32_t stride = gridDim.x * kBlkWarps;
-    const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
-    const float rr = A.res;
-    const bool fused = A.scan_state != nullptr;
-    // the first stencil copy goes out before the scan phase: it is in flight while this CTA scans
-    if (fused && blockIdx.x * kBlkWarps + warp < nblk && lane == 0)
-        blk_issue(&tmap, reinterpret_cast<float *>(s_buf[warp][0]), bar0, D, blk_decode(D, A.blklist[blockIdx.x * kBlkWarps + warp]));
-    if (fused) {
-        // Segment scan inside the emit pass: CTAs take scan tiles by ticket until none is left. A tile only ever waits for tiles
-        // with smaller tickets, i.e. for CTAs that are already running, so no co-residency of the whole grid is needed; then
-        // one thread per CTA waits (with back-off) until every tile has written its offsets.
-        __shared__ uint32_t s_w[kThreads / 32];
-        __shared__ uint32_t s_tile, s_prefix[2];
-        const uint32_t ntiles = (A.scan_nseg + kScanTile - 1) / kScanTile;
-        for (;;) {
-            if (threadIdx.x == 0) s_tile = *reinterpret_cast<volatile uint32_t *>(A.scan_ticket) >= ntiles ? ntiles : atomicAdd(A.scan_ticket, 1u);
-            __syncthreads();
-            const uint32_t tile = s_tile;
-            if (tile >= ntiles) break;
-            scan_seg_tile(D, A.mbits, A.blkcnt, A.segoff, A.scan_nseg, A.scan_state, A.scan_epoch, A.scan_total, tile, s_w, s_prefix, A.scan_done);
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-            uint32_t d;
-            for (;;) {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(d) : "l"(A.scan_done) : "memory");
-                if (d >= ntiles) break;
-                __nanosleep(64);
-            }
-        }
-        __syncthreads();
-    }
+    const bool fused = A.scan_state != nullptr;  // the segment scan runs inside this pass (no k_scan_seg launch)
     uint32_t phases = 0u;  // bit b = parity to wait for on buffer b
     uint32_t it = blockIdx.x * kBlkWarps + warp;
     int cur = 0;
-    if (!fused && it < nblk && lane == 0) blk_issue(&tmap, reinterpret_cast<float *>(s_buf[warp][0]), bar0, D, blk_decode(D, A.blklist[it]));
+    // the first stencil copy goes out before the scan phase: it is in flight while this CTA scans
+    if (it < nblk && lane == 0) blk_issue(&tmap, reinterpret_cast<float *>(s_buf[warp][0]), bar0, D, blk_decode(D, A.blklist[it]));
+    if (fused) blk_scan_phase(A, s_w, &s_tile, s_prefix);
     for (; it < nblk; it += stride, cur ^= 1) {
-        const BlkPos b = blk_decode(D, A.blklist[it]);
+        const uint32_t bid = A.blklist[it];
+        const BlkPos b = blk_decode(D, bid);
         if (it + stride < nblk && lane == 0)
             blk_issue(&tmap, reinterpret_cast<float *>(s_buf[warp][cur ^ 1]), cur ? bar0 : bar1, D, blk_decode(D, A.blklist[it + stride]));
-        // the counts pass 1 left for this block's rows: lane's rows are (ly, lz) and (ly, lz + 2)
-        const int cx = b.x0 + lx, cy = b.y0 + ly;
-        uint32_t rown[2] = {0u, 0u}, rowbase[2] = {0u, 0u};
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int cz = b.z0 + lz + 2 * h;
-            if (cy < D.ny && cz >= D.cz0 && cz < D.cz1) {
-                const uint32_t seg = blk_segment(D, b.bx, cy, cz);
-                const uint2 c = A.blkcnt[seg];
-                const int slot = b.bx & 7;
-                rown[h] = ((slot < 4 ? c.x : c.y) >> (8 * (slot & 3))) & 0xffu;
-                if (rown[h]) {  // triangles of the kept slots in front of this block, behind the segment's offset
-                    const uint32_t kb = seg_kept_bits(D, A.mbits, (uint32_t)(cz - D.cz0) * (uint32_t)D.ny + (uint32_t)cy, (uint32_t)(b.bx >> 3));
-                    const uint32_t so = fused ? __ldcg(A.segoff + seg) : A.segoff[seg];  // (fused: written during this kernel)
-                    rowbase[h] = so + seg_masked_sum(c, kb, slot);
-                }
-            }
-        }
-        const uint32_t cm = A.childmask ? A.childmask[A.blklist[it]] : 0xffu;
-        const bool any = __ballot_sync(0xffffffffu, (rown[0] | rown[1]) != 0u) != 0u;
+        uint32_t rown[2], rowbase[2];
+        blk_emit_rows(A, b, lane, fused, rown, rowbase);
+        const uint32_t cm = A.childmask ? A.childmask[bid] : 0xffu;
         blk_wait(cur ? bar1 : bar0, (phases >> cur) & 1u);  // (consumed even when the block turns out empty: the barrier phase must advance)
         phases ^= 1u << cur;
-        if (any) {
-            const float *buf = reinterpret_cast<const float *>(s_buf[warp][cur]);
-            const bool okxy = cx < D.nx && cy < D.ny;
-            int index[2];
-            uint32_t n[2], obase[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int lzz = lz + 2 * h, cz = b.z0 + lzz;
-                const bool valid = okxy && cz >= D.cz0 && cz < D.cz1 && rown[h] != 0u && ((cm >> ((lx >> 1) + 2 * (ly >> 1) + 4 * h)) & 1u);
-                index[h] = valid ? blk_case(buf, lx, ly, lzz, true, A.cubeDiag) : 0;
-                n[h] = s_ntri[index[h]];
-                // cells in front of this one in its row: exclusive prefix over the 4 lanes of the row
-                const uint32_t a1 = __shfl_up_sync(0xffffffffu, n[h], 1), a2 = __shfl_up_sync(0xffffffffu, n[h], 2), a3 = __shfl_up_sync(0xffffffffu, n[h], 3);
-                obase[h] = rowbase[h] + (lx >= 1 ? a1 : 0u) + (lx >= 2 ? a2 : 0u) + (lx >= 3 ? a3 : 0u);
-            }
-            // The block's triangles in output order of its cells (h = 0: lanes 0..31, then h = 1): every lane lists the triangles
-            // of its two cells at the positions the warp scan of the counts gives (the warp-level scan north_star asks for) -- one
-            // entry per triangle: output slot, cube case, triangle number within the cell, cell. The vertices are then dealt
-            // round-robin, lane = vertex, and a vertex finds its triangle with one shared-memory load instead of a search.
-            const uint32_t incl0 = warp_incl_scan(n[0]);
-            const uint32_t tot0 = __shfl_sync(0xffffffffu, incl0, 31);
-            const uint32_t incl1 = tot0 + warp_incl_scan(n[1]);
-            const uint32_t total = __shfl_sync(0xffffffffu, incl1, 31);
-            uint2 *lst = s_list[warp];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t first = h ? incl1 - n[1] : incl0 - n[0];
-                for (uint32_t k = 0; k < n[h]; k++)
-                    lst[first + k] = make_uint2(obase[h] + k, (uint32_t)index[h] | (k << 8) | ((uint32_t)(lane + 32 * h) << 11));
-            }
-            __syncwarp();
-            for (uint32_t item = lane; item < 3u * total; item += 32) {
-                const uint32_t tri = item / 3u, j = item - 3u * tri;
-                const uint2 ent = lst[tri];
-                const uint64_t o = ent.x;
-                if (o >= A.tri_capacity) { *A.overflow = 1u; continue; }
-                const int oindex = (int)(ent.y & 0xffu);
-                const uint32_t kk = (ent.y >> 8) & 7u;
-                const int owner = (int)((ent.y >> 11) & 31u);
-                const bool second = (ent.y >> 16) != 0u;
-                const int olx = owner & 3, oly = (owner >> 2) & 3, olz = (owner >> 4) + (second ? 2 : 0);
-                // corner positions, flatrenderer.go:235-247
-                const float px0 = A.ox + (float)(b.x0 + olx) * rr, px1 = px0 + rr;
-                const float py0 = A.oy + (float)(b.y0 + oly) * rr, py1 = py0 + rr;
-                const float pz0 = A.oz + (float)(b.z0 + olz) * rr, pz1 = pz0 + rr;
-                // marchcubes.go:64-68: vertex j of the triangle is points[table[3k + 2 - j]]
-                const int e = s_tris[16 * oindex + 3 * (int)kk + 2 - (int)j];
-                // edge -> corner pair (marchcubes.go:101-114), packed 4 bits per edge
-                const int ca = (int)((0x321076543210ull >> (4 * e)) & 0xf), cb = (int)((0x765447650321ull >> (4 * e)) & 0xf);
-                const float3 pa = make_float3((((ca + 1) >> 1) & 1) ? px1 : px0, ((ca >> 1) & 1) ? py1 : py0, (ca >> 2) ? pz1 : pz0);
-                const float3 pb = make_float3((((cb + 1) >> 1) & 1) ? px1 : px0, ((cb >> 1) & 1) ? py1 : py0, (cb >> 2) ? pz1 : pz0);
-                // corner c of the cell: x bit ((c+1)>>1)&1, y bit (c>>1)&1, z bit c>>2 (flatrenderer.go:222-233)
-                const float *cc = buf + (olz * 5 + oly) * 8 + olx;
-                const float va = cc[(ca >> 2) * 40 + ((ca >> 1) & 1) * 8 + (((ca + 1) >> 1) & 1)];
-                const float vb = cc[(cb >> 2) * 40 + ((cb >> 1) & 1) * 8 + (((cb + 1) >> 1) & 1)];
-                const float3 q = mc_interp(pa, pb, va, vb);
-                float *dst = A.tris + 9 * o + 3 * j;
-                dst[0] = q.x; dst[1] = q.y; dst[2] = q.z;
-            }
-        }
+        blk_emit_tris(A, b, cm, reinterpret_cast<const float *>(s_buf[warp][cur]), s_ntri, s_tris, s_list[warp], lane, rown, rowbase);
         __syncwarp();  // everybody is done with buf before it is refilled two iterations later
     }
-    if (A.fin_ctr) {  // the last CTA to get here ends the render (k_finish_render's work, without its launch)
-        __shared__ uint32_t s_last;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            s_last = atomicAdd(A.fin_done, 1u) == gridDim.x - 1 ? 1u : 0u;
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            finish_render_cta(A.fin_ctr, A.fin_hctr, A.fin_nctr, A.fin_scanstate, A.fin_nstate, A.fin_dstamp, A.fin_hstamp, A.fin_nstamp);
-        }
-    }
+    blk_finish(A, &s_last);
 }
 
 }  // namespace gsdfk

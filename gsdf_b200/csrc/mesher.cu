@@ -18,7 +18,7 @@ using namespace gsdfk;
 using namespace gsdfi;
 
 constexpr int kMeshStamps = 8;
-constexpr int kMeshCtr = 24;  // words of a mesher's counter block (see gsdf_mesher::d_ctr)
+constexpr int kMeshCtr = 32;  // words of a mesher's counter block (see gsdf_mesher::d_ctr)
 #define GSDF_MESH_PLAN_GIVEN 0u
 
 // ------------------------------------------------------------------------------------------------ mesher
@@ -50,7 +50,7 @@ struct gsdf_mesher {
     // device counters: [0] quad list length, [1] overflow flag, [2..3] total triangles (u64), [4] kept level-3 cubes,
     // [5] listed segments, [6] scan ticket, [7] prune-cube centres evaluated, [8..17] work-tile schedulers of this mesher's
     // interpreter launches (one pair per prune level + one for the lattice evaluation: never shared with another launch),
-    // [18] scan tiles finished (scan inside the emit pass), [23] CTAs of the last kernel that are done
+    // [18] scan tiles finished (scan inside the emit pass), [19] kept 2-cell cubes, [31] CTAs of the last kernel that are done
     uint32_t *d_ctr = nullptr;
     uint32_t *h_ctr = nullptr;  // pinned mirror
     // stage stamps (%globaltimer, ns): [0] prune centres, [1] quad compaction, [2] lattice evaluation, [3] classification,
@@ -232,9 +232,9 @@ int mesh_run_begin(gsdf_mesher *m) {
     int eval_p = 4;
     {
         static const int force_p = getenv("GSDF_EVAL_P") ? atoi(getenv("GSDF_EVAL_P")) : 0;  // A/B switch: 1 or 4
-        int slots = 0;
-        if ((rc = eval_cta_slots(p, &slots))) return rc;
-        if (prune && m->runs > 0 && (uint64_t)m->quad_hint * 4 <= (uint64_t)slots * kEvalThreads * 3) eval_p = 1;  // <= 3 short rounds
+        int slots = 0, cta = kEvalThreads;
+        if ((rc = eval_cta_slots(p, &slots, &cta))) return rc;
+        if (prune && m->runs > 0 && (uint64_t)m->quad_hint * 4 <= (uint64_t)slots * (uint64_t)cta * 3) eval_p = 1;  // <= 3 short rounds
         if (force_p == 1 && prune && m->runs > 0) eval_p = 1;
         if (force_p == 4) eval_p = 4;
     }
