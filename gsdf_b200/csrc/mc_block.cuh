@@ -34,6 +34,7 @@ struct BlkArgs {
     const uint32_t *blklist;   // kept blocks: (bzl * nby + by) * nbx + bx, bzl relative to D.bz0
     const uint32_t *nblk;      // device-side length of blklist
     uint2 *blkcnt;             // [segment] 8 bytes: triangles of block slot t in that 32-cell row segment
+    unsigned long long *tilesum;  // != nullptr: the count pass also adds every row count to the sum of its scan tile (see scan_seg_tile)
     uint32_t *segoff;          // [segment] exclusive triangle offset (k_scan_seg)
     const uint8_t *t_ntri;
     const int8_t *t_tris;
@@ -64,11 +65,16 @@ __global__ void __launch_bounds__(kThreads) k_mesh_lists(MeshDims D, const uint3
     const int lane = threadIdx.x & 31;
     const uint64_t wpg = (uint64_t)gridDim.x * (blockDim.x >> 5);
     const uint64_t w0 = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (bits && list) {
-        const uint32_t nrows = (uint32_t)(D.ny + 1) * (uint32_t)(D.cz1 - D.cz0 + 1);
-        const uint32_t nqw = (uint32_t)(D.nqx + 31) >> 5;  // 32-quad words per corner row
-        const uint64_t nitems = (uint64_t)nrows * nqw;
-        for (uint64_t base = w0 * 32u; base < nitems; base += wpg * 32u) {
+    // one index space for both lists: [0, nq_pad) the 32-quad words (padded to whole warps), then the block words -- a warp
+    // builds one list or the other, so the two list-building chains (loads -> scan -> atomic -> stores) run side by side
+    const uint32_t nrows = (uint32_t)(D.ny + 1) * (uint32_t)(D.cz1 - D.cz0 + 1);
+    const uint32_t nqw = (uint32_t)(D.nqx + 31) >> 5;  // 32-quad words per corner row
+    const uint64_t nq_items = (bits && list) ? (uint64_t)nrows * nqw : 0ull;
+    const uint64_t nq_pad = (nq_items + 31ull) & ~31ull;
+    const uint64_t nb_items = (uint64_t)D.nbz * D.nby * D.nwx;
+    for (uint64_t base = w0 * 32u; base < nq_pad + nb_items; base += wpg * 32u) {
+        if (base < nq_pad) {
+            const uint64_t nitems = nq_items;
             const uint64_t item = base + lane;
             uint32_t needw = 0u, r = 0u, w = 0u;
             if (item < nitems) {
@@ -119,12 +125,9 @@ __global__ void __launch_bounds__(kThreads) k_mesh_lists(MeshDims D, const uint3
                 const uint32_t qid = __shfl_sync(0xffffffffu, r * (uint32_t)D.nqx + 32u * w, src);
                 if ((word >> lane) & 1u) list[wbase + off + __popc(word & ((1u << lane) - 1u))] = qid + (uint32_t)lane;
             }
-        }
-    }
-    {   // kept blocks
-        const uint64_t nitems = (uint64_t)D.nbz * D.nby * D.nwx;
-        for (uint64_t base = w0 * 32u; base < nitems; base += wpg * 32u) {
-            const uint64_t item = base + lane;
+        } else {  // kept blocks
+            const uint64_t nitems = nb_items;
+            const uint64_t item = base - nq_pad + lane;
             uint32_t word = 0u, brow = 0u, w = 0u;
             if (item < nitems) {
                 brow = (uint32_t)(item / (uint32_t)D.nwx);
@@ -219,7 +222,11 @@ __device__ __forceinline__ void blk_count_block(const BlkArgs &A, const BlkPos &
         n += __shfl_xor_sync(0xffffffffu, n, 1);
         n += __shfl_xor_sync(0xffffffffu, n, 2);  // the four cells of the row
         if (cy < D.ny && cz >= D.cz0 && cz < D.cz1) {
-            if (lx == 0) reinterpret_cast<uint8_t *>(A.blkcnt + blk_segment(D, b.bx, cy, cz))[b.bx & 7] = (uint8_t)n;
+            if (lx == 0) {
+                const uint32_t seg = blk_segment(D, b.bx, cy, cz);
+                reinterpret_cast<uint8_t *>(A.blkcnt + seg)[b.bx & 7] = (uint8_t)n;
+                if (A.tilesum && n) atomicAdd(A.tilesum + seg / kScanTile, (unsigned long long)n);  // (no return value: a reduction at L2)
+            }
             if (A.cases && cx < D.nx) A.cases[((size_t)(cz - D.cz0) * D.ny + cy) * D.nx + cx] = (uint8_t)idx;
         }
     }
@@ -280,12 +287,15 @@ __device__ __forceinline__ uint32_t seg_masked_sum(uint2 c, uint32_t kb, int upt
     return s;
 }
 
-// One tile (kScanTile segments) of the decoupled look-back scan, by all kThreads threads of a CTA. Flag values of a tile's
-// state word: 1 = aggregate published, 2 = inclusive prefix published. done_counter (scan inside the emit pass): += 1 once
-// the tile's offsets are in segoff.
+// One tile (kScanTile segments) of the segment scan, by all kThreads threads of a CTA. Two ways to the tile's prefix:
+//   tilesums: the count pass has already added every row count to state[tile of its segment] (a plain sum, no flags), so the
+//             prefix is the sum of the words in front -- one coalesced read, nothing to wait for (used up to kTileSumMax tiles);
+//   else:     decoupled look-back; flag values of a tile's state word: 1 = aggregate published, 2 = inclusive prefix published.
+// done_counter (scan inside the emit pass): += 1 once the tile's offsets are in segoff.
+constexpr uint32_t kTileSumMax = 1024;
 __device__ __forceinline__ void scan_seg_tile(const MeshDims &D, const uint32_t *__restrict__ mbits, const uint2 *__restrict__ blkcnt, uint32_t *__restrict__ segoff,
                                               uint32_t n, unsigned long long *__restrict__ state, uint32_t epoch, unsigned long long *__restrict__ total,
-                                              uint32_t tile, uint32_t *s_w, uint32_t *s_prefix, uint32_t *done_counter) {
+                                              uint32_t tile, uint32_t *s_w, uint32_t *s_prefix, uint32_t *done_counter, bool tilesums) {
     const uint32_t ntiles = (n + kScanTile - 1) / kScanTile;
     const uint32_t base = tile * kScanTile + threadIdx.x * 8;
     uint32_t v[8], sum = 0;
@@ -306,6 +316,28 @@ __device__ __forceinline__ void scan_seg_tile(const MeshDims &D, const uint32_t 
     const uint32_t incl = warp_incl_scan(sum);
     if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
     __syncthreads();
+    if (tilesums) {
+        uint32_t part = 0;
+        for (uint32_t t = threadIdx.x; t < tile; t += kThreads) part += (uint32_t)__ldcg(state + t);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        __shared__ uint32_t s_part[kThreads / 32];
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const uint32_t w = threadIdx.x < kThreads / 32 ? s_w[threadIdx.x] : 0u;
+            const uint32_t wi = warp_incl_scan(w);
+            if (threadIdx.x < kThreads / 32) s_w[threadIdx.x] = wi - w;
+            const uint32_t agg = __shfl_sync(0xffffffffu, wi, 31);  // tile aggregate
+            uint32_t prefix = threadIdx.x < kThreads / 32 ? s_part[threadIdx.x] : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) prefix += __shfl_xor_sync(0xffffffffu, prefix, o);
+            if (threadIdx.x == 0) {
+                *s_prefix = prefix;
+                if (tile == ntiles - 1) *total = (unsigned long long)prefix + agg;
+            }
+        }
+    } else {
     const unsigned long long tag = (unsigned long long)epoch << 34;
     if (threadIdx.x < 32) {
         const uint32_t w = threadIdx.x < kThreads / 32 ? s_w[threadIdx.x] : 0u;
@@ -343,6 +375,7 @@ __device__ __forceinline__ void scan_seg_tile(const MeshDims &D, const uint32_t 
             if (tile == ntiles - 1) *total = (unsigned long long)prefix + agg;
         }
     }
+    }
     __syncthreads();
     uint32_t run = *s_prefix + s_w[threadIdx.x >> 5] + (incl - sum);
     uint32_t o[8];
@@ -364,7 +397,7 @@ __device__ __forceinline__ void scan_seg_tile(const MeshDims &D, const uint32_t 
 
 __global__ void __launch_bounds__(kThreads) k_scan_seg(MeshDims D, const uint32_t *__restrict__ mbits, const uint2 *__restrict__ blkcnt, uint32_t *__restrict__ segoff,
                                                       uint32_t n, unsigned long long *__restrict__ state, uint32_t *__restrict__ ticket, uint32_t epoch,
-                                                      unsigned long long *__restrict__ total, unsigned long long *stamp) {
+                                                      unsigned long long *__restrict__ total, unsigned long long *stamp, int tilesums) {
     __shared__ uint32_t s_w[kThreads / 32];
     __shared__ uint32_t s_tile, s_prefix[2];
     pdl_trigger();
@@ -375,7 +408,7 @@ __global__ void __launch_bounds__(kThreads) k_scan_seg(MeshDims D, const uint32_
     __syncthreads();
     const uint32_t tile = s_tile;
     if (tile >= ntiles) return;
-    scan_seg_tile(D, mbits, blkcnt, segoff, n, state, epoch, total, tile, s_w, s_prefix, nullptr);
+    scan_seg_tile(D, mbits, blkcnt, segoff, n, state, epoch, total, tile, s_w, s_prefix, nullptr, tilesums != 0);
 }
 
 // ---------------------------------------------------------------------------------------------- pass 2
@@ -474,7 +507,7 @@ __device__ __forceinline__ void blk_scan_phase(const BlkArgs &A, uint32_t *s_w, 
         __syncthreads();
         const uint32_t tile = *s_tile;
         if (tile >= ntiles) break;
-        scan_seg_tile(A.D, A.mbits, A.blkcnt, A.segoff, A.scan_nseg, A.scan_state, A.scan_epoch, A.scan_total, tile, s_w, s_prefix, A.scan_done);
+        scan_seg_tile(A.D, A.mbits, A.blkcnt, A.segoff, A.scan_nseg, A.scan_state, A.scan_epoch, A.scan_total, tile, s_w, s_prefix, A.scan_done, A.tilesum != nullptr);
         __syncthreads();
     }
     if (threadIdx.x == 0) {

@@ -201,6 +201,10 @@ int mesh_run_begin(gsdf_mesher *m) {
     BlkArgs BA{};
     BA.D = D; BA.ox = A.ox; BA.oy = A.oy; BA.oz = A.oz; BA.res = A.res; BA.cubeDiag = A.cubeDiag;
     BA.childmask = (prune && m->fine) ? m->d_childmask : nullptr;
+    // (tile sums accumulated by the count pass -- 158 k reductions on 104 addresses -- cost the count pass 13 us and save the
+    // scan 2: off; GSDF_TILESUM=1 is the A/B switch)
+    static const bool tilesum_on = getenv("GSDF_TILESUM") != nullptr && getenv("GSDF_TILESUM")[0] == '1';
+    BA.tilesum = (tilesum_on && nscantiles <= kTileSumMax) ? m->d_scanstate : nullptr;
     BA.mbits = A.mbits; BA.blklist = m->d_blklist; BA.nblk = m->d_ctr + 5; BA.blkcnt = m->d_blkcnt; BA.segoff = m->d_seg;
     BA.t_ntri = A.t_ntri; BA.t_tris = A.t_tris; BA.tris = m->d_tris; BA.tri_capacity = m->tri_cap / 9; BA.cases = A.cases;
     BA.overflow = A.overflow;
@@ -278,7 +282,7 @@ int mesh_run_begin(gsdf_mesher *m) {
         }
         const uint64_t ncrows = (uint64_t)(D.ny + 1) * nk;
         if (blockmc)
-            CU(launch_chain(pdl, k_mesh_lists, dim3(grid_for(p->sms, (ncrows * (uint64_t)((D.nqx + 31) >> 5) + 31) / 32, kThreads / 32)), dim3(kThreads), 0, st, D,
+            CU(launch_chain(pdl, k_mesh_lists, dim3(grid_for(p->sms, (ncrows * (uint64_t)((D.nqx + 31) >> 5) + 31) / 32 + ((uint64_t)D.nbz * D.nby * D.nwx + 31) / 32, kThreads / 32)), dim3(kThreads), 0, st, D,
                             (const uint32_t *)m->d_mbits, m->d_list, m->d_ctr + 0, m->d_blklist, m->d_ctr + 5, m->d_stamp + 1,
                             (const uint32_t *)(m->fine ? m->d_bits2 : nullptr)));
         else
@@ -343,7 +347,7 @@ int mesh_run_begin(gsdf_mesher *m) {
         // no scan launch: the emit pass takes the scan tiles by ticket before it emits (mc_block.cuh)
     } else if (blockmc) {
         CU(launch_chain(pdl, k_scan_seg, dim3((unsigned)nscantiles), dim3(kThreads), 0, st, D, (const uint32_t *)A.mbits, (const uint2 *)m->d_blkcnt, m->d_seg, (uint32_t)nseg,
-                        m->d_scanstate, m->d_ctr + 6, epoch, reinterpret_cast<unsigned long long *>(m->d_ctr + 2), m->d_stamp + 4));
+                        m->d_scanstate, m->d_ctr + 6, epoch, reinterpret_cast<unsigned long long *>(m->d_ctr + 2), m->d_stamp + 4, BA.tilesum ? 1 : 0));
         CU(cudaGetLastError());
     } else {
         CU(launch_chain(pdl, k_scan_lookback, dim3((unsigned)nscantiles), dim3(kThreads), 0, st, m->d_seg, (uint32_t)nseg, m->d_scanstate, m->d_ctr + 6, epoch,

@@ -54,7 +54,8 @@ type PruneLevel struct {
 	Margin float32
 }
 
-// NewCUDARendererPlan is NewCUDARenderer with an explicit prune plan (coarse to fine, the last level must be 3). The default
+// NewCUDARendererPlan is NewCUDARenderer with an explicit prune plan (coarse to fine, ending with level 3 or with levels 3, 2:
+// the 2-cell level decides which corners inside kept 4-cell blocks are evaluated at all). The default
 // plan of NewCUDARenderer is level 3 with margin 1.25 (plus coarse levels on large lattices): it reproduces the dense sweep
 // on every example scene, README.md:152's 309,872 included; []PruneLevel{{3, 1}} is the literal rule at every level-3 cube.
 func NewCUDARendererPlan(s *gleval.SDF3CUDA, res float32, plan []PruneLevel, cz0, cz1 int) (*MesherCUDA, error) {

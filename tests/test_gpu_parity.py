@@ -468,6 +468,14 @@ def test_z_slabs_concatenate_to_the_whole(bld):
             ev += r.Evaluations()
         assert np.array_equal(bits(np.concatenate(parts)), bits(wt)), cuts
         assert np.array_equal(np.concatenate(cparts), wc), cuts
+    # the same with a plan that ends with the 2-cell level (levels 3 + 2 in one launch, child masks in the marching-cubes
+    # kernels): slabs whose cuts split 4-cell blocks and 2-cell cubes still concatenate to the whole, which equals the default
+    fine = [(3, 1.25), (2, 1.25)]
+    wf = glrender.Octree(sdf, res, prune=fine)
+    assert np.array_equal(bits(wf.AllTriangles()), bits(wt)) and wf.Evaluations() < whole.Evaluations()
+    for cuts in ([0, 8, 20, nz], [0, 5, 6, 23, nz], [0, 1, nz]):
+        parts = [glrender.Octree(sdf, res, cz_range=(a, b), prune=fine).AllTriangles() for a, b in zip(cuts[:-1], cuts[1:])]
+        assert np.array_equal(bits(np.concatenate(parts)), bits(wt)), cuts
 
 
 def test_image_eval_matches_oracle(oracle, bld):
