@@ -215,6 +215,10 @@ def run_cuda(args, rank, local_rank, world):
     warm = max(args.warmup, 3)
     bld, s, res = build_scene()
     sdf = gleval.NewCUDASDF3(s)
+    # what constructing the GPU evaluator does in the reference (it compiles the tree's shader, gleval/gpu.go:35-54): kernels
+    # specialised for this tree's instruction stream, compiled by NVRTC (a few seconds, outside every timed region). Where
+    # NVRTC is missing the interpreter kernels run (same results); the line says which.
+    specialised = (not args.no_specialize) and sdf.Specialize()
     lat = glrender.lattice_from_bounds(*s.Bounds(), res)
     nx, ny, nz = lat.n
     lattice_evals = (nx + 1) * (ny + 1) * (nz + 1)
@@ -299,6 +303,8 @@ def run_cuda(args, rank, local_rank, world):
         for spd in ((1, 3, 4) if world == 1 else (1, 2)):
             M = glrender.MultiRenderer(s, res, devices=list(range(world)), slabs_per_device=spd)
             assert M.NumTriangles() == ntri
+            if specialised:
+                M.Specialize()
             if spd * world > 1 and not args.no_rebalance:
                 M.Rebalance(2)
 
@@ -343,7 +349,7 @@ def run_cuda(args, rank, local_rank, world):
     # ---------------- knurled-cylinder resdiv 1600 (BASELINE config 4) by Z-slab: strong scaling where slabs pay
     knurled = None
     if not args.no_knurled:
-        knurled = bench_knurled(rank, world, barrier, allmax, allsum, l2_flush, gleval, glrender, slab)
+        knurled = bench_knurled(rank, world, barrier, allmax, allsum, l2_flush, gleval, glrender, slab, specialised)
 
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
@@ -358,7 +364,8 @@ def run_cuda(args, rank, local_rank, world):
     # centre is evaluated, otherwise the centres (a few per cent) are left in
     centres = ((nx + 3) // 4) * ((ny + 3) // 4) * ((nz + 3) // 4) if len(plan) == 1 and world == 1 else 0
     fine_evals = max(evals_exec - centres, 0)
-    kname = "k_eval<GenGrid> (fine lattice evaluation)"
+    kname = ("k_jit_grid4 (fine lattice evaluation, kernel specialised for the tree at run time)" if specialised
+             else "k_eval<GenGrid> (fine lattice evaluation, interpreter)")
     kbytes, kms = 4.0 * fine_evals / world, mean["eval_ms"]
     achieved = kbytes / (kms * 1e-3) / 1e9
     traffic = winst = None
@@ -366,7 +373,8 @@ def run_cuda(args, rank, local_rank, world):
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            traffic, winst = tj.get("k_eval<GenGrid>"), tj.get("k_eval<GenGrid>.warp_inst")
+            tk = "k_jit_grid4" if specialised else "k_eval<GenGrid>"
+            traffic, winst = tj.get(tk), tj.get(tk + ".warp_inst")
         except Exception:
             pass
     issue = None
@@ -400,6 +408,8 @@ def run_cuda(args, rank, local_rank, world):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(nx, ny, nz, lattice_evals, ntri),
         "arm": {"renderer": "Octree: coarse-to-fine prune %s + marching cubes" % plan, "evals_executed_per_step": evals_exec,
+                "kernels": ("lattice evaluation and prune-centre pass specialised for the tree at run time (gsdf_program_specialize: NVRTC, compiled before "
+                            "the timed region, as the reference compiles its shader at construction)" if specialised else "interpreter kernels"),
                 "partition": "one lattice, %d Z-slab(s), cuts %s (one shared corner plane, no collective)" % (world, cuts),
                 "l2": "flushed between steps (256 MiB write); working set 27 MB < 126 MB L2",
                 "timing": "CUDA events on the launching stream around each step (one CUDA-graph replay of %d kernel nodes chained by programmatic "
@@ -470,11 +480,12 @@ def bench_evaluate(sdf, s, glrender, torch):
     return out
 
 
-def bench_knurled(rank, world, barrier, allmax, allsum, l2_flush, gleval, glrender, slab):
+def bench_knurled(rank, world, barrier, allmax, allsum, l2_flush, gleval, glrender, slab, specialise):
     """BASELINE config 4: knurled-cylinder at resdiv 1600 (564x564x1408 corners = 447.9 M), one lattice split into `world`
     Z-slabs. Device time per render, max over ranks."""
     bld, s, res = build_scene("knurled-cylinder", 1600)
     sdf = gleval.NewCUDASDF3(s)
+    special = bool(specialise and sdf.Specialize())
     lat = glrender.lattice_from_bounds(*s.Bounds(), res)
     nz = lat.n[2]
     cuts = slab.slab_cuts(nz, world)
@@ -493,7 +504,7 @@ def bench_knurled(rank, world, barrier, allmax, allsum, l2_flush, gleval, glrend
                 "triangles": int(allsum(R.NumTriangles())), "plan": R.Plan()}
 
     R = glrender.NewOctreeRenderer(sdf, res, 1 << 15, cz_range=(cuts[rank], cuts[rank + 1]))
-    out = {"scaling": "strong", "lattice_corners": dense, "cuts": cuts}
+    out = {"scaling": "strong", "lattice_corners": dense, "cuts": cuts, "kernels": "specialised at run time" if special else "interpreter"}
     out.update(timed(R))
     plan = R.Plan()
     R.Close()
@@ -532,6 +543,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-knurled", action="store_true")
+    ap.add_argument("--no-specialize", action="store_true", help="keep the interpreter kernels (A/B)")
     ap.add_argument("--no-rebalance", action="store_true", help="keep the equal-layer Z-slab cuts (A/B)")
     ap.add_argument("--numa", action="store_true", help="pin each rank to the CPUs local to its GPU")
     ap.add_argument("--device-only", action="store_true",

@@ -19,7 +19,7 @@ class GsdfError(RuntimeError):
 
 
 # gsdf_status (include/gsdf_b200.h)
-OK, EINVAL, ELEN, EEMPTY, ECUDA, ENOMEM, EPROGRAM, ESHORT, ERES = 0, -1, -2, -3, -4, -5, -6, -7, -8
+OK, EINVAL, ELEN, EEMPTY, ECUDA, ENOMEM, EPROGRAM, ESHORT, ERES, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6, -7, -8, -9
 MESH_PRUNE, MESH_KEEP_CASES, MESH_KEEP_GRID, MESH_STAGE_TIMING, MESH_PRUNE_LITERAL = 1, 2, 4, 8, 16
 PRUNE_MARGIN_DEFAULT, PRUNE_MAX_LEVELS = 1.25, 4
 DC_NAIVE, DC_LEAST_SQUARES, DC_LEAST_SQUARES_CHISELED = 0, 1, 2
@@ -90,6 +90,9 @@ def _load(host_only=False):
         "gsdf_program_create": (C.c_int, [vp, C.c_size_t, f32p, C.c_size_t, C.POINTER(vp)]),
         "gsdf_program_create_on": (C.c_int, [C.c_int, vp, C.c_size_t, f32p, C.c_size_t, C.POINTER(vp)]),
         "gsdf_program_update": (C.c_int, [vp, vp, C.c_size_t, f32p, C.c_size_t]),
+        "gsdf_program_specialize": (C.c_int, [vp]),
+        "gsdf_program_is_specialized": (C.c_int, [vp]),
+        "gsdf_jit_compile": (C.c_int64, [vp, C.c_size_t, f32p, C.c_size_t]),
         "gsdf_program_destroy": (None, [vp]),
         "gsdf_program_evaluations": (C.c_uint64, [vp]),
         "gsdf_eval3": (C.c_int, [vp, vp, vp, C.c_size_t]),
@@ -109,6 +112,7 @@ def _load(host_only=False):
         "gsdf_multi_read": (C.c_int64, [vp, vp, C.c_size_t]),
         "gsdf_multi_rewind": (C.c_int, [vp]),
         "gsdf_multi_timeline": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int]),
+        "gsdf_multi_specialize": (C.c_int, [vp]),
         "gsdf_multi_stats": (C.c_int, [vp, u64p, u64p, u64p, f32p]),
         "gsdf_multi_slabs": (C.c_int, [vp, i32p, i32p, C.c_int]),
         "gsdf_multi_stl": (C.c_int64, [vp, vp, C.c_size_t]),

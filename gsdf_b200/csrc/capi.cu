@@ -299,6 +299,7 @@ static int upload_blob(gsdf_program *p, const gsdf_program_header &h, const uint
     // stage aux with the program when program + aux + stacks stay under ~100 KB (>= 2 CTAs/SM)
     const uint32_t stacks = kEvalThreads * 4u * 4u * (h.dstack + 3u * h.pstack + kRxySlots);
     p->pv.stage_aux = (prog_bytes + aux_bytes + stacks + 16 <= 100 * 1024) ? 1u : 0u;
+    program_note_structure(p, h, chunks);
     return 0;
 }
 
@@ -730,7 +731,14 @@ int program_update_async(gsdf_program *p, const void *blob, size_t blob_bytes, c
     CU(cudaEventRecord(p->upload_ev, p->stream));
     p->upload_ev_recorded = true;
     p->ninstr = h.ninstr;
+    program_note_structure(p, h, chunks);
     return 0;
+}
+
+void program_note_structure(gsdf_program *p, const gsdf_program_header &h, const uint32_t *chunks) {
+    p->h_words.assign(chunks, chunks + (size_t)h.nchunks * 4);
+    p->skey = program_structure_key(h, chunks, p->needs_ext, p->pv.stage_aux != 0);
+    if (p->jit && p->jit->key != p->skey) p->jit.reset();  // (the interpreter runs until gsdf_program_specialize is called again)
 }
 
 // full validation of a flattened program without touching a device (gsdf_multi_update keeps the blob for its workers)

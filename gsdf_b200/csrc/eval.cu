@@ -1,5 +1,8 @@
 // eval.cu -- the interpreter kernels and their launchers. This is the slow translation unit (one k_eval instantiation per
 // generator and per {default, EXT} interpreter); nothing else includes interp.cuh.
+#include <map>
+#include <tuple>
+
 #include "eval_kernels.cuh"
 #include "internal.cuh"
 
@@ -57,6 +60,15 @@ int eval_cta_threads(const gsdf_program *p, bool latency_bound) {
     return (latency_bound || p->ninstr <= kSmallProgram) ? kSmallCta : kEvalThreads;
 }
 
+// CTA size of the run-time compiled kernels (no lockstep barriers inside). Short programs: 128 threads (flange@400: 47.2 us
+// at 128 threads, 47.7 at 192, 49.5 at 256, 52.3 at 384). Long programs, whose straight-line code (knurled: ~130 KB) streams
+// through the instruction cache whatever the CTA size: 256 (knurled@500: 449 us at 128, 433 at 256). GSDF_JIT_CTA overrides.
+int jit_cta_threads(const gsdf_program *p) {
+    static const int forced = getenv("GSDF_JIT_CTA") ? atoi(getenv("GSDF_JIT_CTA")) : 0;
+    if (forced >= 32 && forced <= kEvalThreads && forced % 32 == 0) return forced;
+    return p->ninstr <= kSmallProgram ? kSmallCta : 256;
+}
+
 template <int P, class Gen, bool EXT>
 int launch_eval_impl(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st, bool pdl, uint32_t *sched,
                      unsigned long long *stamp, int threads) {
@@ -77,6 +89,57 @@ int launch_eval_impl(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper
     CU(cudaGetLastError());
     return 0;
 }
+// The same launch with a kernel compiled at run time for this program's structure (jit.cu): a cudaKernel_t from a
+// context-independent library; attribute opt-in and occupancy are kept per (kernel, device) like the built-in kernels'.
+struct JitLaunchFacts {
+    std::mutex mu;
+    std::map<std::pair<const void *, int>, bool> optin;                       // (kernel, device)
+    std::map<std::tuple<const void *, int, uint32_t, int>, int> occ;          // (kernel, device, smem, threads)
+};
+template <int P, class Gen>
+int launch_jit(const gsdf_program *p, cudaKernel_t kernel, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st, bool pdl, uint32_t *sched,
+               unsigned long long *stamp, int threads) {
+    static JitLaunchFacts facts;
+    const void *fn = reinterpret_cast<const void *>(kernel);
+    const uint32_t smem = smem_total_bytes<P>(p->pv, threads);
+    int occ = 0;
+    {
+        std::lock_guard<std::mutex> lk(facts.mu);
+        bool &done = facts.optin[{fn, p->device}];
+        if (!done) {
+            DevInfo di;
+            const int rc = device_info(p->device, &di);
+            if (rc) return rc;
+            CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
+            done = true;
+        }
+        auto key = std::make_tuple(fn, p->device, smem, threads);
+        auto it = facts.occ.find(key);
+        if (it == facts.occ.end()) {
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem));
+            facts.occ[key] = occ;
+        } else occ = it->second;
+    }
+    if (occ < 1) return fail(GSDF_EPROGRAM, "node program needs %u bytes of shared memory per CTA; does not fit", smem);
+    uint64_t blocks = (nwork_upper_bound + threads - 1) / threads;
+    blocks = std::min<uint64_t>(blocks, (uint64_t)p->sms * occ);
+    ProgView pv = p->pv;
+    pv.sched = sched ? sched : next_sched(p);
+    pv.stamp = stamp;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    Gen g = gen;
+    void *args[2] = {&pv, &g};
+    CU(cudaLaunchKernelExC(&cfg, fn, args));
+    return 0;
+}
+inline const JitEntry *jit_of(const gsdf_program *p) { return (p->jit && p->jit->key == p->skey) ? p->jit.get() : nullptr; }
+
 template <int P, class Gen>
 int launch_eval(const gsdf_program *p, const Gen &gen, uint64_t nwork_upper_bound, cudaStream_t st, bool pdl, uint32_t *sched,
                 unsigned long long *stamp = nullptr, int threads = kEvalThreads) {
@@ -147,9 +210,11 @@ uint32_t *next_sched(const gsdf_program *p, int *slot_index) {
 int launch_points3(const gsdf_program *p, const GenPoints3 &g, uint64_t nwork, cudaStream_t st, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, false, sched); }
 int launch_points2(const gsdf_program *p, const GenPoints2 &g, uint64_t nwork, cudaStream_t st, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, false, sched); }
 int launch_grid4(const gsdf_program *p, const GenGrid<4> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
+    if (nwork && jit_of(p)) return launch_jit<4>(p, jit_of(p)->grid4, g, nwork, st, pdl, sched, stamp, jit_cta_threads(p));
     return launch_eval<4>(p, g, nwork, st, pdl, sched, stamp, eval_cta_threads(p, false));
 }
 int launch_grid1(const gsdf_program *p, const GenGrid<1> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
+    if (nwork && jit_of(p)) return launch_jit<1>(p, jit_of(p)->grid1, g, nwork, st, pdl, sched, stamp, jit_cta_threads(p));
     return launch_eval<1>(p, g, nwork, st, pdl, sched, stamp, eval_cta_threads(p, true));
 }
 int launch_prune_fine(const gsdf_program *p, const PruneFine &g, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
@@ -158,7 +223,7 @@ int launch_prune_fine(const gsdf_program *p, const PruneFine &g, cudaStream_t st
 int eval_cta_slots(const gsdf_program *p, int *slots, int *threads_out) {
     static KernelDevCache cache;  // occupancy of the P = 4 lattice kernel (the P = 1 form is never lower)
     int occ = 0;
-    const int threads = eval_cta_threads(p, false);
+    const int threads = jit_of(p) ? jit_cta_threads(p) : eval_cta_threads(p, false);
     const uint32_t smem = smem_total_bytes<4>(p->pv, threads);
     const int rc = p->needs_ext ? kernel_occupancy(cache, k_eval<4, GenGrid<4>, true>, p->device, smem, threads, &occ)
                                 : kernel_occupancy(cache, k_eval<4, GenGrid<4>, false>, p->device, smem, threads, &occ);
@@ -168,6 +233,7 @@ int eval_cta_slots(const gsdf_program *p, int *slots, int *threads_out) {
     return 0;
 }
 int launch_centers(const gsdf_program *p, const GenCenters &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
+    if (nwork && jit_of(p)) return launch_jit<1>(p, jit_of(p)->centers, g, nwork, st, pdl, sched, stamp, jit_cta_threads(p));
     return launch_eval<1>(p, g, nwork, st, pdl, sched, stamp, eval_cta_threads(p, true));
 }
 int launch_image(const gsdf_program *p, const GenImage &g, uint64_t nwork, cudaStream_t st, uint32_t *sched) { return launch_eval<4>(p, g, nwork, st, false, sched); }

@@ -13,8 +13,17 @@
 
 namespace gsdfk {
 
-template <int P, class Gen, bool EXT>
-__global__ void __launch_bounds__(kEvalThreads, GSDF_EVAL_MINB) k_eval(ProgView pv, Gen gen) {
+// How a tile's threads run the node program: the interpreter loop (RunInterp), or the straight-line specialisation of one
+// program that jit.cu generates and compiles at run time (RunSpecial there).
+template <int P, bool EXT>
+struct RunInterp {
+    __device__ __forceinline__ void operator()(Machine<P> &m, const uint4 *__restrict__ prog, const float4 *__restrict__ aux) const { run_program<P, EXT>(m, prog, aux); }
+};
+
+// The body of k_eval, shared with the run-time compiled kernels. ALL_RUN: every thread of a tile runs the program (barriers or
+// CTA-wide guard votes inside); threads past the end redo the last item.
+template <int P, bool ALL_RUN, class Gen, class Run>
+__device__ __forceinline__ void eval_body(ProgView pv, Gen gen, Run run) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t stage = smem_stage_bytes(pv);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + stage);
@@ -50,26 +59,25 @@ __global__ void __launch_bounds__(kEvalThreads, GSDF_EVAL_MINB) k_eval(ProgView 
                 continue;
             }
         }
-#ifdef GSDF_LOCKSTEP
-        // every thread of the tile runs the program (barriers inside); threads past the end redo the last item
-        const uint64_t wc = w < nwork ? w : nwork - 1;
-        m.init(dstk, pstk, blockDim.x);
+        if constexpr (ALL_RUN) {
+            const uint64_t wc = w < nwork ? w : nwork - 1;
+            m.init(dstk, pstk, blockDim.x);
 #ifdef GSDF_RXY
-        m.rxy = pstk + (size_t)pv.pslots * 3 * P * blockDim.x;
+            m.rxy = pstk + (size_t)pv.pslots * 3 * P * blockDim.x;
 #endif
-        gen.load(wc, m.px, m.py, m.pz);
-        run_program<P, EXT>(m, prog, aux);
-        if (w < nwork) gen.store(w, m.top);
-#else
-        if (w >= nwork) continue;
-        m.init(dstk, pstk, blockDim.x);
+            gen.load(wc, m.px, m.py, m.pz);
+            run(m, prog, aux);
+            if (w < nwork) gen.store(w, m.top);
+        } else {
+            if (w >= nwork) continue;
+            m.init(dstk, pstk, blockDim.x);
 #ifdef GSDF_RXY
-        m.rxy = pstk + (size_t)pv.pslots * 3 * P * blockDim.x;
+            m.rxy = pstk + (size_t)pv.pslots * 3 * P * blockDim.x;
 #endif
-        gen.load(w, m.px, m.py, m.pz);
-        run_program<P, EXT>(m, prog, aux);
-        gen.store(w, m.top);
-#endif
+            gen.load(w, m.px, m.py, m.pz);
+            run(m, prog, aux);
+            gen.store(w, m.top);
+        }
     }
     // the last CTA to leave re-arms the scheduler for the next launch
     if (threadIdx.x == 0) {
@@ -79,6 +87,16 @@ __global__ void __launch_bounds__(kEvalThreads, GSDF_EVAL_MINB) k_eval(ProgView 
             pv.sched[1] = 0u;
         }
     }
+}
+
+#ifdef GSDF_LOCKSTEP
+constexpr bool kInterpAllRun = true;
+#else
+constexpr bool kInterpAllRun = false;
+#endif
+template <int P, class Gen, bool EXT>
+__global__ void __launch_bounds__(kEvalThreads, GSDF_EVAL_MINB) k_eval(ProgView pv, Gen gen) {
+    eval_body<P, kInterpAllRun>(pv, gen, RunInterp<P, EXT>());
 }
 
 // ---------------------------------------------------------------------------------------------- prune levels 3 + 2

@@ -2,12 +2,18 @@
 // programmatic-dependent-launch helpers, the bulk-async program staging, the lattice description and the generator
 // functors that feed the interpreter kernel (eval_kernels.cuh) with positions and take its distances.
 #pragma once
+#ifdef __CUDACC_RTC__  // run-time compilation of a specialised kernel (jit.cu): no system headers, no image generator
+#include "rtc_types.cuh"
+#else
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 #include "../../include/gsdf_program.h"
+#ifndef __CUDACC_RTC__
 #include "colormap.cuh"
+#endif
 
 namespace gsdfk {
 
@@ -305,6 +311,7 @@ struct PruneFine {
     uint32_t *evals;          // += centres evaluated (both levels)
 };
 
+#ifndef __CUDACC_RTC__
 // ImageRendererSDF2.Render positions (glrender/image.go:85-105). rgba != nullptr: the colour conversion is applied in
 // the sink and four RGBA8 pixels leave as one 16-byte store (image.go:112-116 fused); else the distances are stored.
 struct GenImage {
@@ -360,6 +367,8 @@ struct GenImage {
         }
     }
 };
+
+#endif  // __CUDACC_RTC__
 
 // ---------------------------------------------------------------------------------------------- prune -> quad list
 struct MeshDims {

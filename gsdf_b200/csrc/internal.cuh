@@ -11,7 +11,9 @@
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <memory>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "../../include/gsdf_b200.h"
@@ -94,6 +96,16 @@ inline gsdfk::Lat make_lat(const gsdf_lattice *lat, int k0, int k1, int pitch, b
 
 }  // namespace gsdfi
 
+namespace gsdfi {
+// Kernels compiled at run time for one program structure (jit.cu); shared by every program and device with that structure.
+struct JitEntry {
+    std::string key;
+    cudaLibrary_t lib[3] = {};
+    cudaKernel_t grid4 = nullptr, grid1 = nullptr, centers = nullptr;
+    ~JitEntry();
+};
+}  // namespace gsdfi
+
 constexpr int kSchedRing = 64;  // scheduler slots of a program (one pair of counters per in-flight interpreter launch)
 
 struct gsdf_program {
@@ -114,6 +126,11 @@ struct gsdf_program {
     std::atomic<uint32_t> sched_next{0};
     size_t blob_cap = 0;          // bytes allocated at d_blob
     bool needs_ext = false;       // program contains ellipse2D / quadbezier2d -> EXT interpreter instantiation
+    // run-time specialisation (jit.cu): host copy of the instruction chunks, the structural key they give, and the compiled
+    // kernels in use (valid while jit->key == skey; an update that changes the structure drops them)
+    std::vector<uint32_t> h_words;
+    std::string skey;
+    std::shared_ptr<gsdfi::JitEntry> jit;
     // Streams other than `stream` that may still be reading d_blob: caller-supplied streams of the *_device entry points
     // (one event per scheduler slot, recorded behind the launch) and the streams of meshers created on this program
     // (they register their completion event). gsdf_program_update / destroy wait for all of them.
@@ -145,6 +162,11 @@ void program_remove_dependent(gsdf_program *p, cudaEvent_t ev);
 // every registered reader, and upload_ev is recorded for the next launches to wait on. Anything else: the synchronous path.
 int program_update_async(gsdf_program *p, const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats);
 int check_program_blob(const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats, int dim);
+// jit.cu
+std::string program_structure_key(const gsdf_program_header &h, const uint32_t *chunks, bool ext, bool stage_aux);
+int program_specialize(gsdf_program *p);
+// keeps h_words / skey of a program current and drops a specialisation the new structure no longer matches
+void program_note_structure(gsdf_program *p, const gsdf_program_header &h, const uint32_t *chunks);
 // Waits until nothing on any stream can still be reading the program's device buffers.
 int program_quiesce(gsdf_program *p);
 

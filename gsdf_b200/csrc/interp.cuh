@@ -8,8 +8,12 @@
 // Stacks live in shared memory, laid out [slot][component][point][thread] so a warp access is one conflict-free
 // 128-byte wavefront. The distance-stack top and the current position stay in registers.
 #pragma once
+#ifdef __CUDACC_RTC__
+#include "rtc_types.cuh"
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 #include "../../include/gsdf_program.h"
 #include "math32.cuh"
@@ -98,25 +102,21 @@ __device__ __forceinline__ bool guard_dead(uint32_t kind, float w, float a, floa
     return (w - a) >= k && a != 0.f;
 }
 
-// Runs the program at the P positions already loaded in m.px/py/pz; result in m.top.
 // EXT selects the instantiation that also carries the rarely used heavy 2-D primitives (ellipse2D, quadbezier2d: double
 // precision cbrt, exp/log). Keeping them out of the default kernel matters: with them compiled in, the kernel needs a
 // real call stack and the common path slows down by ~20 % (measured); programs that contain them run the EXT kernel.
+// One instruction: h = prog[pc] (the caller loads it; a specialised kernel passes the opcode word as a constant, so that the
+// switch folds to the one body). Returns false at END; pc moves to the next instruction or to a guard's target.
 template <int P, bool EXT>
-__device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restrict__ prog, const float4 *__restrict__ aux) {
+__device__ __forceinline__ bool exec_one(Machine<P> &m, const uint4 h, const uint4 *__restrict__ prog, int &pc, const float4 *__restrict__ aux) {
     using namespace m32;
-    int pc = 0;
-    for (;;) {
-#ifdef GSDF_LOCKSTEP
-        __syncthreads();  // keep the CTA's warps on the same opcode body: one instruction-cache stream per CTA
-#endif
-        const uint4 h = prog[pc];
+    {
         const uint32_t op = h.x & 0xffu;
         const int len = (int)((h.x >> 8) & 0xffu);
         const float f2 = __uint_as_float(h.z), f3 = __uint_as_float(h.w);
         switch (op) {
         case GSDF_OP_END:
-            return;
+            return false;
         // ------------------------------------------------------------------ 3D primitives
         case GSDF_OP_SPHERE: {  // cpu_evaluators.go:20-26
             m.pushD();
@@ -688,14 +688,14 @@ __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restri
                 // the box bounds the operand from below only OUTSIDE the box: a point inside it never votes for the skip
                 dead &= (dx > 0.f || dy > 0.f) && guard_dead(h.y & 0xffu, w, m.top[j], 0.f);
             }
-            if (__syncthreads_and(dead)) { m.skip = true; pc = (int)(h.y >> 8); continue; }
+            if (__syncthreads_and(dead)) { m.skip = true; pc = (int)(h.y >> 8); return true; }
         } break;
         case GSDF_OP_EXTRUDE_ENTER: {  // :524-527  f2=h/2
             if (h.y & 0xffu) {
                 bool dead = true;
 #pragma unroll
                 for (int j = 0; j < P; j++) dead &= guard_dead(h.y & 0xffu, absf(m.pz[j]) - f2, m.top[j], f3);
-                if (__syncthreads_and(dead)) { m.skip = true; pc = (int)(h.y >> 8); continue; }
+                if (__syncthreads_and(dead)) { m.skip = true; pc = (int)(h.y >> 8); return true; }
             }
             m.pushD();
 #pragma unroll
@@ -711,7 +711,7 @@ __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restri
                 bool dead = true;
 #pragma unroll
                 for (int j = 0; j < P; j++) dead &= guard_dead(h.y & 0xffu, absf(m.pz[j]) - c.z, m.top[j], f3);
-                if (__syncthreads_and(dead)) { m.skip = true; pc = (int)(h.y >> 8); continue; }
+                if (__syncthreads_and(dead)) { m.skip = true; pc = (int)(h.y >> 8); return true; }
             }
             m.pushD();
 #ifdef GSDF_RXY
@@ -737,9 +737,22 @@ __device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restri
             }
         } break;
         default:
-            return;  // unknown opcode: rejected at gsdf_program_create, never reached
+            return false;  // unknown opcode: rejected at gsdf_program_create, never reached
         }
         pc += len;
+    }
+    return true;
+}
+
+// Runs the program at the P positions already loaded in m.px/py/pz; result in m.top.
+template <int P, bool EXT>
+__device__ __forceinline__ void run_program(Machine<P> &m, const uint4 *__restrict__ prog, const float4 *__restrict__ aux) {
+    int pc = 0;
+    for (;;) {
+#ifdef GSDF_LOCKSTEP
+        __syncthreads();  // keep the CTA's warps on the same opcode body: one instruction-cache stream per CTA
+#endif
+        if (!exec_one<P, EXT>(m, prog[pc], prog, pc, aux)) return;
     }
 }
 

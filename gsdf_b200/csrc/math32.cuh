@@ -9,10 +9,14 @@
 // Everything is __host__ __device__ so the flattener pre-computes constants (tan(taper), sincos of fixed angles)
 // with the same code the kernels run.
 #pragma once
+#ifdef __CUDACC_RTC__
+#include "rtc_types.cuh"
+#else
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#endif
 
 #define M32_HD __host__ __device__ __forceinline__
 // Large helpers (hypot, atan2, sincos) can be kept out of line to shrink the interpreter's instruction footprint

@@ -398,6 +398,7 @@ int mesh_run_begin(gsdf_mesher *m) {
         const void *lbits[GSDF_PRUNE_MAX_LEVELS];
         gsdf_prune_plan plan;
         const void *prog;
+        const void *jit;   // run-time compiled kernels in use (gsdf_program_specialize after a capture re-captures)
         size_t tri_cap;
         ProgView pv;
         unsigned flags;
@@ -410,6 +411,7 @@ int mesh_run_begin(gsdf_mesher *m) {
     std::memcpy(key.ptr, kp, sizeof kp);
     for (int li = 0; li < GSDF_PRUNE_MAX_LEVELS; li++) key.lbits[li] = m->d_lbits[li];
     key.plan = m->plan; key.prog = p;
+    key.jit = (p->jit && p->jit->key == p->skey) ? (const void *)p->jit.get() : nullptr;
     key.tri_cap = m->tri_cap; key.pv = p->pv; key.flags = m->flags; key.ext = p->needs_ext ? 1 : 0; key.tma = (m->use_tma ? 1 : 0) | (m->tile5 ? 2 : 0);
     key.eval_p = eval_p; key.quad_hint = (prune && m->runs > 0) ? m->quad_hint : 0u;
     key.pdl_chain = m->pdl_chain ? 1 : 0;
@@ -1066,6 +1068,16 @@ int gsdf_multi_update(gsdf_multimesher *mm, const void *blob, size_t blob_bytes,
     mm->up_blob.assign((const uint8_t *)blob, (const uint8_t *)blob + blob_bytes);
     mm->up_aux.assign(aux, aux + aux_floats);
     for (auto &d : mm->up_dirty) d = 1;
+    return 0;
+}
+
+int gsdf_multi_specialize(gsdf_multimesher *mm) {
+    if (!mm) return fail(GSDF_EINVAL, "gsdf_multi_specialize: NULL handle");
+    for (int w = 0; w < mm->ndev; w++) {
+        CU(use_device(mm->devs[w]));
+        const int rc = program_specialize(mm->prog[w]);  // compiled once per structure: the other devices share the code
+        if (rc) return rc;
+    }
     return 0;
 }
 

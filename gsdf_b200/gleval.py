@@ -56,6 +56,21 @@ class _SDFCUDA:
         self.shader = shader
         self._bounds = shader.Bounds()
 
+    def Specialize(self):
+        """Compile kernels specialised for this tree's instruction stream (gsdf_program_specialize: what constructing the GPU
+        evaluator does in the reference, which compiles a GLSL shader per tree, gleval/gpu.go:35-54). Renderers built on this
+        evaluator then use them for the lattice evaluation and the prune-centre passes: bit-identical results, faster.
+        Returns True when the specialised kernels are in use, False when run-time compilation is not available here (the
+        interpreter kernels keep running)."""
+        rc = lib.gsdf_program_specialize(self._h)
+        if rc == _lib.EUNSUPPORTED:
+            return False
+        check(rc)
+        return True
+
+    def Specialized(self):
+        return bool(lib.gsdf_program_is_specialized(self._h))
+
     def Close(self):
         h, self._h = getattr(self, "_h", None), None
         if h and lib is not None:  # lib can already be gone at interpreter shutdown

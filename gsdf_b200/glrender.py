@@ -266,6 +266,15 @@ class MultiRenderer:
         check(lib.gsdf_multi_update(self._h, f["blob"], len(f["blob"]), aux.ctypes.data_as(C.POINTER(C.c_float)), aux.size))
         self.shader = shader
 
+    def Specialize(self):
+        """gsdf_multi_specialize: run-time compiled kernels for this tree on every device (see gleval SDF3CUDA.Specialize).
+        True when in use, False when run-time compilation is not available."""
+        rc = lib.gsdf_multi_specialize(self._h)
+        if rc == _lib.EUNSUPPORTED:
+            return False
+        check(rc)
+        return True
+
     def UpdateBlob(self, blob, aux):
         check(lib.gsdf_multi_update(self._h, blob, len(blob), aux.ctypes.data_as(C.POINTER(C.c_float)), aux.size))
 

@@ -34,7 +34,8 @@ typedef enum {
     GSDF_ENOMEM = -5,
     GSDF_EPROGRAM = -6, /* malformed node program */
     GSDF_ESHORT = -7,   /* io.ErrShortBuffer: triangle buffer < 5 (octreerenderer.go:132, flatrenderer.go:187) */
-    GSDF_ERES = -8      /* "resolution not fine enough for marching cubes" (flatrenderer.go:53, octreerenderer.go:232) */
+    GSDF_ERES = -8,     /* "resolution not fine enough for marching cubes" (flatrenderer.go:53, octreerenderer.go:232) */
+    GSDF_EUNSUPPORTED = -9 /* an optional facility is not available here (run-time compilation); the caller carries on without it */
 } gsdf_status;
 
 typedef struct gsdf_program gsdf_program; /* a compiled tree resident on one device */
@@ -71,6 +72,20 @@ int gsdf_program_create_on(int device, const void *blob, size_t blob_bytes, cons
  * are reused, so an edited tree costs one small host->device copy (the GL path recompiles its shader instead,
  * gleval/gpu.go:35-54). Renderers bound to the handle see the new tree on their next run. */
 int gsdf_program_update(gsdf_program *p, const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats);
+/* Compiles kernels specialised for this program's instruction stream (NVRTC, loaded at run time) and uses them for the
+ * lattice evaluation and the prune-centre passes of every renderer built on the program: what constructing the GPU evaluator
+ * does in the reference (it generates and compiles a GLSL compute shader per tree, glbuild/glbuild.go:175-214,
+ * gleval/gpu.go:35-54). The program becomes straight-line code around the interpreter's own opcode bodies, so results stay
+ * bit-identical; only the structure is compiled in (opcodes, flags, jump targets), operands are still read from the program, so
+ * gsdf_program_update with new parameters of the same tree keeps the specialisation and an update that changes the structure
+ * drops it (call again). Compiled code is cached per structure for the life of the process (one compilation of ~2 s per
+ * distinct tree shape). Returns 0, or GSDF_EUNSUPPORTED when NVRTC is not available / GSDF_JIT=0 / the program is 2-D: the
+ * interpreter kernels then keep running -- same results, slower. */
+int gsdf_program_specialize(gsdf_program *p);
+/* 1 when the specialised kernels are in use for the program's current structure. */
+int gsdf_program_is_specialized(const gsdf_program *p);
+/* The compilation step alone, without a device (build checks, tests): CUBIN size in bytes or a negative gsdf_status. */
+int64_t gsdf_jit_compile(const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats);
 void gsdf_program_destroy(gsdf_program *p);
 /* gleval Evaluations() counter (gleval/cpu.go:126, gleval/gpu.go:80): points evaluated through this handle -- host and
  * device Evaluate calls, lattice and image evaluations, and the evaluations of the renderers bound to it (the reference's
@@ -206,6 +221,8 @@ int gsdf_multi_begin(int ndev, const int *devs, int slabs_per_device, const void
                      size_t aux_floats, const gsdf_lattice *lat, unsigned flags, gsdf_multimesher **out);
 /* gsdf_program_update on every device's copy of the program. */
 int gsdf_multi_update(gsdf_multimesher *mm, const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats);
+/* gsdf_program_specialize for the program of every device of the handle (one compilation, shared). 0 or GSDF_EUNSUPPORTED. */
+int gsdf_multi_specialize(gsdf_multimesher *mm);
 /* Render the lattice and deliver every triangle, in FlatRenderer order, to tri9 (HOST memory for max_tris triangles; pinned
  * memory is written by DMA directly). Returns the triangle count; if the buffer is too small nothing is copied and the
  * call fails with GSDF_ESHORT (gsdf_multi_stats then tells the count). tri9 == NULL renders without read-back. */

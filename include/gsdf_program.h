@@ -23,7 +23,9 @@
 #ifndef GSDF_PROGRAM_H
 #define GSDF_PROGRAM_H
 
+#ifndef __CUDACC_RTC__ /* (run-time compiled kernels bring their own fixed-width types: no system headers under NVRTC) */
 #include <stdint.h>
+#endif
 
 #define GSDF_PROGRAM_MAGIC 0x46445347u /* "GSDF" */
 #define GSDF_PROGRAM_VERSION 1u

@@ -140,6 +140,18 @@ func (m *MultiMesherCUDA) Update(root glbuild.Shader3D) error {
 	return nil
 }
 
+// Specialize compiles kernels for the tree's instruction stream once and uses them on every device (gleval.SDF3CUDA.Specialize).
+func (m *MultiMesherCUDA) Specialize() (bool, error) {
+	switch rc := C.gsdf_multi_specialize(m.h); rc {
+	case 0:
+		return true, nil
+	case C.GSDF_EUNSUPPORTED:
+		return false, nil
+	default:
+		return false, cudaErr()
+	}
+}
+
 // Rebalance re-cuts the slabs by the evaluations each executed last (equal layers are not equal work on a pruned lattice).
 func (m *MultiMesherCUDA) Rebalance(rounds int) error {
 	if C.gsdf_multi_rebalance(m.h, C.int(rounds)) < 0 {

@@ -8,6 +8,8 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for name, resdiv in [("npt-flange", 400), ("bolt", 400), ("knurled-cylinder", 500)]:
     s = gsdf.scene(b, name)
     sdf = gleval.NewCUDASDF3(s)
+    if os.environ.get("GSDF_AB_SPECIAL"):
+        print("specialised:", sdf.Specialize(), flush=True)
     res = np.float32(s.Diagonal() / np.float32(resdiv))
     for cls in (glrender.Octree, glrender.FlatRenderer):
         R = cls(sdf, res, stage_timing=os.environ.get("GSDF_AB_GRAPH") is None)

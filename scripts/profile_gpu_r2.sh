@@ -7,7 +7,8 @@ mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep gpurun_out/*.raw.csv gpurun_out/launches.csv
 B="python bench.py --steps 3 --warmup 1 --no-cpu-baseline --device-only"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/bench_under_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_eval -s 6 -c 2 -f -o gpurun_out/prof_k_eval $B > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:k_eval|k_jit" -s 6 -c 2 -f -o gpurun_out/prof_k_eval $B > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_eval -s 6 -c 2 -f -o gpurun_out/prof_k_eval_interp $B --no-specialize > /dev/null 2>&1
 M=$(cat scripts/ncu_metrics.txt)
 for k in "k_mc_blk_emit" "k_mc_blk_count" "k_mesh_lists"; do
   ncu --metrics $M --clock-control none -k regex:$k -s 3 -c 1 -f -o gpurun_out/prof_$k $B > /dev/null 2>&1

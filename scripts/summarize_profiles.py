@@ -67,7 +67,9 @@ def main():
                     u = units.get(key, "byte").lower()
                     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
                 short = name.split("::")[-1].split("<")[0].strip()
-                if "GenGrid" in d["Kernel Name"]:
+                if "k_jit_" in d["Kernel Name"]:
+                    short = re.sub(r"\(.*", "", d["Kernel Name"]).strip()   # k_jit_grid4 / k_jit_grid1 / k_jit_centers
+                elif "GenGrid" in d["Kernel Name"]:
                     short = "k_eval<GenGrid>"
                 elif "GenCenters" in d["Kernel Name"]:
                     short = "k_eval<GenCenters>"
