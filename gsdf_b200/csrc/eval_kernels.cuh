@@ -47,6 +47,7 @@ __device__ __forceinline__ void eval_body(ProgView pv, Gen gen, Run run) {
         if (first) {
             w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
         } else {
+            if ((uint64_t)gridDim.x * blockDim.x >= nwork) break;  // the first tiles covered the work: nothing to fetch
             if (threadIdx.x == 0) *s_tile = gridDim.x + atomicAdd(pv.sched, 1u);
             __syncthreads();
             w = (uint64_t)(*s_tile) * blockDim.x + threadIdx.x;
@@ -81,6 +82,63 @@ __device__ __forceinline__ void eval_body(ProgView pv, Gen gen, Run run) {
     }
     // the last CTA to leave re-arms the scheduler for the next launch
     if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(pv.sched + 1, 1u) == gridDim.x - 1) {
+            pv.sched[0] = 0u;
+            pv.sched[1] = 0u;
+        }
+    }
+}
+
+// The same for kernels whose warps are independent (the run-time compiled ones: no lockstep barriers, guards vote per warp):
+// a tile is the 32 work items of ONE warp, fetched by the warp itself, so the tail of the launch is balanced at warp
+// granularity and nothing inside the tile loop waits for another warp.
+template <int P, class Gen, class Run>
+__device__ __forceinline__ void eval_body_warp(ProgView pv, Gen gen, Run run) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t stage = smem_stage_bytes(pv);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + stage);
+    pdl_trigger();
+    bulk_stage(smem, pv.g_prog, stage, bar);
+    const uint4 *prog = reinterpret_cast<const uint4 *>(smem);
+    const float4 *aux = pv.stage_aux ? reinterpret_cast<const float4 *>(smem + pv.prog_bytes)
+                                     : reinterpret_cast<const float4 *>(reinterpret_cast<const uint8_t *>(pv.g_prog) + pv.prog_bytes);
+    float *dstk = reinterpret_cast<float *>(smem + stage + 16u) + threadIdx.x;
+    float *pstk = dstk + (size_t)pv.dslots * P * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u, wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
+
+    Machine<P> m;
+    pdl_wait();
+    stage_stamp(pv.stamp);
+    const uint64_t nwork = gen.work_items();
+    for (bool first = true;; first = false) {
+        uint32_t tile = blockIdx.x * wpb + (threadIdx.x >> 5);  // a warp's first tile is its own index: no counter round trip
+        if (!first) {
+            // (when the first tiles cover the work -- the centre pass, thin slabs -- there is nothing to fetch: thousands of
+            // same-address atomics, or reads, at the end of a one-tile-per-warp launch cost microseconds)
+            if ((uint64_t)nwarps * 32u >= nwork) break;
+            if (lane == 0) tile = nwarps + atomicAdd(pv.sched, 1u);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+        }
+        const uint64_t w = (uint64_t)tile * 32u + lane;
+        if (w - lane >= nwork) break;
+        const uint64_t wc = w < nwork ? w : nwork - 1;  // lanes past the end redo the last item (warp-wide votes inside)
+        if constexpr (Gen::kTileSkip) {
+            if (__all_sync(0xffffffffu, gen.dead(wc))) {
+                if (w < nwork) gen.store_dead(w);
+                continue;
+            }
+        }
+        m.init(dstk, pstk, blockDim.x);
+#ifdef GSDF_RXY
+        m.rxy = pstk + (size_t)pv.pslots * 3 * P * blockDim.x;
+#endif
+        gen.load(wc, m.px, m.py, m.pz);
+        run(m, prog, aux);
+        if (w < nwork) gen.store(w, m.top);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // the last CTA to leave re-arms the scheduler for the next launch
         __threadfence();
         if (atomicAdd(pv.sched + 1, 1u) == gridDim.x - 1) {
             pv.sched[0] = 0u;
@@ -135,6 +193,7 @@ __global__ void __launch_bounds__(kEvalThreads, GSDF_EVAL_MINB) k_prune_fine(Pro
         if (first) {
             w0 = (uint64_t)blockIdx.x * blockDim.x;
         } else {
+            if ((uint64_t)gridDim.x * blockDim.x >= nwork) break;  // the first tiles covered the work: nothing to fetch
             if (threadIdx.x == 0) *s_tile = gridDim.x + atomicAdd(pv.sched, 1u);
             __syncthreads();
             w0 = (uint64_t)(*s_tile) * blockDim.x;

@@ -24,6 +24,16 @@
 #define GSDF_LOCKSTEP 1
 #endif
 
+// The vote of a slab / box guard (gsdf_program.h): all points of the voting unit must agree before the unit jumps. The
+// interpreter votes CTA-wide (its warps walk the program in lockstep anyway); the run-time compiled kernels (jit.cu), which
+// have no lockstep barriers, define GSDF_WARP_GUARDS and vote per warp -- a guard is value-preserving at any granularity,
+// so results do not depend on the choice.
+#ifdef GSDF_WARP_GUARDS
+#define GSDF_GUARD_VOTE(pred) __all_sync(0xffffffffu, (pred))
+#else
+#define GSDF_GUARD_VOTE(pred) __syncthreads_and(pred)
+#endif
+
 namespace gsdfk {
 
 template <int P>
@@ -688,14 +698,14 @@ __device__ __forceinline__ bool exec_one(Machine<P> &m, const uint4 h, const uin
                 // the box bounds the operand from below only OUTSIDE the box: a point inside it never votes for the skip
                 dead &= (dx > 0.f || dy > 0.f) && guard_dead(h.y & 0xffu, w, m.top[j], 0.f);
             }
-            if (__syncthreads_and(dead)) { m.skip = true; pc = (int)(h.y >> 8); return true; }
+            if (GSDF_GUARD_VOTE(dead)) { m.skip = true; pc = (int)(h.y >> 8); return true; }
         } break;
         case GSDF_OP_EXTRUDE_ENTER: {  // :524-527  f2=h/2
             if (h.y & 0xffu) {
                 bool dead = true;
 #pragma unroll
                 for (int j = 0; j < P; j++) dead &= guard_dead(h.y & 0xffu, absf(m.pz[j]) - f2, m.top[j], f3);
-                if (__syncthreads_and(dead)) { m.skip = true; pc = (int)(h.y >> 8); return true; }
+                if (GSDF_GUARD_VOTE(dead)) { m.skip = true; pc = (int)(h.y >> 8); return true; }
             }
             m.pushD();
 #pragma unroll
@@ -711,7 +721,7 @@ __device__ __forceinline__ bool exec_one(Machine<P> &m, const uint4 h, const uin
                 bool dead = true;
 #pragma unroll
                 for (int j = 0; j < P; j++) dead &= guard_dead(h.y & 0xffu, absf(m.pz[j]) - c.z, m.top[j], f3);
-                if (__syncthreads_and(dead)) { m.skip = true; pc = (int)(h.y >> 8); return true; }
+                if (GSDF_GUARD_VOTE(dead)) { m.skip = true; pc = (int)(h.y >> 8); return true; }
             }
             m.pushD();
 #ifdef GSDF_RXY
