@@ -379,6 +379,18 @@ struct MeshDims {
     int pitch;               // grid row pitch (floats)
     int nsx;                 // 32-cell segments per cell row
     int nwx;                 // 32-bit words per block row of the bit mask = ceil(nbx/32)
+    // n / nbx and n / nby for n < 2^31 as __umulhi(n, mul) >> shr (mul == 0: divisor 1): the block kernels decode two block
+    // ids per block, and a 32-bit division by a run-time divisor is ~35 instructions
+    uint32_t nbx_mul, nbx_shr, nby_mul, nby_shr;
 };
+__host__ __device__ inline void fastdiv_init(uint32_t d, uint32_t &mul, uint32_t &shr) {
+    if (d <= 1u) { mul = 0u; shr = 0u; return; }
+    uint32_t lg = 0;
+    while ((1ull << lg) < d) lg++;          // ceil(log2 d)
+    const uint32_t p = 31u + lg;
+    mul = (uint32_t)(((1ull << p) + d - 1u) / d);
+    shr = p - 32u;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, uint32_t mul, uint32_t shr) { return mul ? __umulhi(n, mul) >> shr : n; }
 
 }  // namespace gsdfk

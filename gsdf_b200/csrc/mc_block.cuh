@@ -163,10 +163,10 @@ struct BlkPos {
 };
 __device__ __forceinline__ BlkPos blk_decode(const MeshDims &D, uint32_t bid) {
     BlkPos b;
-    b.bx = (int)(bid % (uint32_t)D.nbx);
-    const uint32_t t = bid / (uint32_t)D.nbx;
-    b.by = (int)(t % (uint32_t)D.nby);
-    b.bzl = (int)(t / (uint32_t)D.nby);
+    const uint32_t t = fastdiv(bid, D.nbx_mul, D.nbx_shr);
+    b.bx = (int)(bid - t * (uint32_t)D.nbx);
+    b.bzl = (int)fastdiv(t, D.nby_mul, D.nby_shr);
+    b.by = (int)(t - (uint32_t)b.bzl * (uint32_t)D.nby);
     b.x0 = 4 * b.bx; b.y0 = 4 * b.by; b.z0 = 4 * (D.bz0 + b.bzl);
     return b;
 }
@@ -269,6 +269,13 @@ __global__ void __launch_bounds__(kBlkWarps * 32) k_mc_blk_count(const __grid_co
 
 // ---------------------------------------------------------------------------------------------- scan over segments
 // Triangle count of a segment = sum of the bytes of its kept block slots. kb = kept bits of the segment's 8 slots.
+__device__ __forceinline__ uint32_t seg_kept_bits_at(const MeshDims &D, const uint32_t *mbits, int cy, int cz, uint32_t sx) {
+    uint32_t kb = 0xffu;
+    if (mbits) kb = (mbits[((size_t)((cz >> 2) - D.bz0) * D.nby + (cy >> 2)) * D.nwx + (sx >> 2)] >> (8u * (sx & 3u))) & 0xffu;
+    const int rem = D.nbx - 8 * (int)sx;  // block slots of this segment that exist
+    if (rem < 8) kb &= (1u << rem) - 1u;
+    return kb;
+}
 __device__ __forceinline__ uint32_t seg_kept_bits(const MeshDims &D, const uint32_t *mbits, uint32_t row, uint32_t sx) {
     const int cy = (int)(row % (uint32_t)D.ny), cz = D.cz0 + (int)(row / (uint32_t)D.ny);
     uint32_t kb = 0xffu;
@@ -432,7 +439,7 @@ __device__ __forceinline__ void blk_emit_rows(const BlkArgs &A, const BlkPos &b,
             const int slot = b.bx & 7;
             rown[h] = ((slot < 4 ? c.x : c.y) >> (8 * (slot & 3))) & 0xffu;
             if (rown[h]) {  // triangles of the kept slots in front of this block, behind the segment's offset
-                const uint32_t kb = seg_kept_bits(D, A.mbits, (uint32_t)(cz - D.cz0) * (uint32_t)D.ny + (uint32_t)cy, (uint32_t)(b.bx >> 3));
+                const uint32_t kb = seg_kept_bits_at(D, A.mbits, cy, cz, (uint32_t)(b.bx >> 3));
                 const uint32_t so = cg ? __ldcg(A.segoff + seg) : A.segoff[seg];
                 rowbase[h] = so + seg_masked_sum(c, kb, slot);
             }

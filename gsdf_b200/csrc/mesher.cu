@@ -615,6 +615,8 @@ static int mesh_begin_prio(gsdf_program *p, const gsdf_lattice *lat, int cz0, in
     D.pitch = D.nqx * 4;
     D.nsx = (D.nx + 31) / 32;
     D.nwx = (D.nbx + 31) / 32;
+    fastdiv_init((uint32_t)D.nbx, D.nbx_mul, D.nbx_shr);
+    fastdiv_init((uint32_t)D.nby, D.nby_mul, D.nby_shr);
     m->fine = pl.nlevels >= 2 && pl.level[pl.nlevels - 1] == 2;
     // the 2-cell level lives in the kept-block marching-cubes kernels only; the A/B kernel sets fall back to the plan's level 3
     if (m->fine && !(m->use_tma && m->mc_mode == 2)) { m->fine = false; pl.nlevels--; m->plan = pl; }
