@@ -170,6 +170,19 @@ struct GenPoints2 {
     }
 };
 
+// n / d for n < 2^31 and a run-time divisor as __umulhi(n, mul) >> shr (mul == 0: divisor 1); a 32-bit hardware-less division
+// by a run-time divisor is ~18-35 instructions.
+__host__ __device__ inline void fastdiv_init(uint32_t d, uint32_t &mul, uint32_t &shr) {
+    if (d <= 1u) { mul = 0u; shr = 0u; return; }
+    uint32_t lg = 0;
+    while ((1ull << lg) < d) lg++;          // ceil(log2 d)
+    const uint32_t p = 31u + lg;
+    mul = (uint32_t)(((1ull << p) + d - 1u) / d);
+    shr = p - 32u;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, uint32_t mul, uint32_t shr) { return mul ? __umulhi(n, mul) >> shr : n; }
+
+
 // Lattice description shared by the grid / mesher kernels.
 struct Lat {
     float ox, oy, oz, res;
@@ -178,6 +191,9 @@ struct Lat {
     int nqx;           // quads (4 corners) per row = ceil((nx+1)/4)
     int pitch;         // floats per stored row
     int vec;           // rows 16-byte aligned -> float4 stores
+    // quad id -> (m, j, k) by multiply-shift (fastdiv) when the slab has fewer than 2^31 quads (fdiv != 0): decode runs twice per
+    // work item (load, store), two divisions each -- 10 % of the instructions of a one-corner-per-thread evaluation of the flange
+    uint32_t fdiv, nqx_mul, nqx_shr, nyp_mul, nyp_shr;
 };
 // FlatRenderer.evalKRange (glrender/flatrenderer.go:146-182): positions origin + float32(i)*res, x fastest.
 // Work unit = a quad of 4 consecutive corners of one lattice row, split over 4/P threads.
@@ -191,9 +207,17 @@ struct GenGrid {
     __device__ void decode(uint64_t w, int &i0, int &j, int &k) const {
         const uint32_t sub = (uint32_t)(w % (4 / P));
         uint32_t q = list ? list[w / (4 / P)] : (uint32_t)(w / (4 / P));
-        const uint32_t m = q % (uint32_t)L.nqx; q /= (uint32_t)L.nqx;
-        j = (int)(q % (uint32_t)(L.ny + 1));
-        k = (int)(q / (uint32_t)(L.ny + 1));
+        uint32_t m;
+        if (L.fdiv) {
+            const uint32_t r = fastdiv(q, L.nqx_mul, L.nqx_shr);
+            m = q - r * (uint32_t)L.nqx;
+            k = (int)fastdiv(r, L.nyp_mul, L.nyp_shr);
+            j = (int)(r - (uint32_t)k * (uint32_t)(L.ny + 1));
+        } else {
+            m = q % (uint32_t)L.nqx; q /= (uint32_t)L.nqx;
+            j = (int)(q % (uint32_t)(L.ny + 1));
+            k = (int)(q / (uint32_t)(L.ny + 1));
+        }
         i0 = (int)(4 * m + P * sub);
     }
     __device__ void load(uint64_t w, float (&x)[P], float (&y)[P], float (&z)[P]) const {
@@ -235,6 +259,9 @@ struct PruneLevel {
     int nwx;                  // 32-bit words per cube row of the bit mask
     float half, maxDist;      // size/2 and margin * size * sqrt3/2
     uint32_t *bits;           // [ncz][ncy][nwx]
+    // work item -> (cx, cy, cz) by multiply-shift when the level has fewer than 2^31 padded cubes (fdiv != 0): GenCenters decodes
+    // three times per cube (dead, load, store), and w / rowlen on a 64-bit work item is the most expensive division there is
+    uint32_t fdiv, row_mul, row_shr, ncy_mul, ncy_shr;
 };
 struct GenCenters {
     static constexpr bool kTileSkip = true;
@@ -247,6 +274,14 @@ struct GenCenters {
     __device__ uint64_t work_items() const { return (uint64_t)L.nwx * 32u * L.ncy * L.ncz; }
     __device__ void decode(uint64_t w, int &cx, int &cy, int &cz) const {
         const uint32_t rowlen = (uint32_t)L.nwx * 32u;
+        if (L.fdiv) {
+            const uint32_t w32 = (uint32_t)w;
+            const uint32_t row = fastdiv(w32, L.row_mul, L.row_shr);
+            cx = (int)(w32 - row * rowlen);
+            cz = (int)fastdiv(row, L.ncy_mul, L.ncy_shr);
+            cy = (int)(row - (uint32_t)cz * (uint32_t)L.ncy);
+            return;
+        }
         const uint32_t row = (uint32_t)(w / rowlen);
         cx = (int)(w - (uint64_t)row * rowlen);
         cy = (int)(row % (uint32_t)L.ncy);
@@ -383,14 +418,4 @@ struct MeshDims {
     // ids per block, and a 32-bit division by a run-time divisor is ~35 instructions
     uint32_t nbx_mul, nbx_shr, nby_mul, nby_shr;
 };
-__host__ __device__ inline void fastdiv_init(uint32_t d, uint32_t &mul, uint32_t &shr) {
-    if (d <= 1u) { mul = 0u; shr = 0u; return; }
-    uint32_t lg = 0;
-    while ((1ull << lg) < d) lg++;          // ceil(log2 d)
-    const uint32_t p = 31u + lg;
-    mul = (uint32_t)(((1ull << p) + d - 1u) / d);
-    shr = p - 32u;
-}
-__device__ __forceinline__ uint32_t fastdiv(uint32_t n, uint32_t mul, uint32_t shr) { return mul ? __umulhi(n, mul) >> shr : n; }
-
 }  // namespace gsdfk

@@ -122,19 +122,35 @@ M32_HD float xatan(float x) {
     z = div(mul(z, num), den);
     return add(mul(x, z), x);
 }
+// atan.go's satan has three ranges, each with its own division and xatan call; atan mirrors negative arguments. Here the
+// OPERANDS of the one division and the terms of the final sum are selected by range and every lane runs the same
+// instructions: a warp whose lanes fall into different ranges (any warp that sees a few degrees of a screw) no longer
+// executes all three paths one after the other, and the code is a third of the size. Same operations on the same values
+// as the three-path form, so the same bits: x / 1 == x exactly, and atan(-x) evaluates satan(|x|) as before.
 M32_HD float satan(float x) {
     const float Morebits = 6.123233995736765886130e-17f;
     const float Tan3pio8 = 2.41421356237309504880f;
-    if (x <= 0.66f) return xatan(x);
-    if (x > Tan3pio8) return add(add((float)(kPi / 2), -xatan(div(1.0f, x))), Morebits);
-    return add(add((float)(kPi / 4), xatan(div(add(x, -1.0f), add(x, 1.0f)))), mul(0.5f, Morebits));
+    const bool small = x <= 0.66f;
+    const bool big = x > Tan3pio8;
+    const float num = small ? x : (big ? 1.0f : add(x, -1.0f));
+    const float den = small ? 1.0f : (big ? x : add(x, 1.0f));
+    const float t = xatan(div(num, den));
+    const float r = add(add(big ? (float)(kPi / 2) : (float)(kPi / 4), big ? -t : t), big ? Morebits : mul(0.5f, Morebits));
+    return small ? t : r;
 }
 M32_HD float atan(float x) {
-    if (x == 0.0f) return x;
-    if (x > 0.0f) return satan(x);
-    return -satan(-x);
+    const float s = satan(fabsf(x));
+    return x == 0.0f ? x : (x > 0.0f ? s : -s);
 }
 M32_BIG float atan2(float y, float x) {
+    // atan2.go tests its special operands (NaN, zero, infinity) one by one in front of the quotient; lattice points are
+    // finite and non-zero, so ONE test sends them straight to the quotient and the chain stays out of their way
+    const float ay = fabsf(y), ax = fabsf(x);
+    if (ay > 0.0f && ay < INFINITY && ax > 0.0f && ax < INFINITY) {
+        float q = atan(div(y, x));
+        if (x < 0.0f) return q <= 0.0f ? add(q, kPiF) : add(q, -kPiF);
+        return q;
+    }
     if (y != y || x != x) return NAN;
     if (y == 0.0f) {
         if (x >= 0.0f && !signbit(x)) return copysignf(0.0f, y);
@@ -145,10 +161,7 @@ M32_BIG float atan2(float y, float x) {
         if (x > 0.0f) return isinf(y) ? copysignf((float)(kPi / 4), y) : copysignf(0.0f, y);
         return isinf(y) ? copysignf((float)(3 * kPi / 4), y) : copysignf(kPiF, y);
     }
-    if (isinf(y)) return copysignf((float)(kPi / 2), y);
-    float q = atan(div(y, x));
-    if (x < 0.0f) return q <= 0.0f ? add(q, kPiF) : add(q, -kPiF);
-    return q;
+    return copysignf((float)(kPi / 2), y);  // y is infinite, x finite and non-zero
 }
 
 // ---- sin / cos / tan (math32 sin.go, tan.go) ----

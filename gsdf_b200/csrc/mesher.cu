@@ -633,6 +633,9 @@ static int mesh_begin_prio(gsdf_program *p, const gsdf_lattice *lat, int cz0, in
         Lv.cz0 = cz0 / Lv.w;
         Lv.ncz = (cz1 + Lv.w - 1) / Lv.w - Lv.cz0;
         Lv.nwx = (Lv.ncx + 31) / 32;
+        Lv.fdiv = (uint64_t)Lv.nwx * 32u * (uint64_t)Lv.ncy * (uint64_t)std::max(Lv.ncz, 1) < (1ull << 31) ? 1u : 0u;
+        fastdiv_init((uint32_t)Lv.nwx * 32u, Lv.row_mul, Lv.row_shr);
+        fastdiv_init((uint32_t)Lv.ncy, Lv.ncy_mul, Lv.ncy_shr);
         const float size = lat->res * (float)Lv.w;                            // ms3.Octree.CubeSize
         Lv.half = size * 0.5f;
         Lv.maxDist = size * (float)(1.73205080757 / 2) * pl.margin[li];         // octreerenderer.go:182 with glrender.go:9, times the margin

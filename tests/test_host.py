@@ -398,3 +398,29 @@ def test_slab_guards_are_planted_where_they_are_sound(bld, monkeypatch):
     monkeypatch.setenv("GSDF_NO_GUARDS", "1")
     for name, s in shapes.guards3d(bld):
         assert all((w1 & 0xff) == 0 for pc, op, ln, w1 in _instructions(bld.flatten(s)["blob"]) if op in enter), name
+
+
+def test_multiply_shift_division_constants():
+    """generators.cuh fastdiv_init / fastdiv (work-item decode of the lattice, prune-centre and kept-block kernels): for every
+    divisor d the kernels can meet and every n < 2^31, __umulhi(n, mul) >> shr == n // d. Python restatement of the two
+    functions (the GPU parity tests run the real ones on every lattice size of the suite)."""
+    def init(d):
+        if d <= 1:
+            return 0, 0
+        lg = 0
+        while (1 << lg) < d:
+            lg += 1
+        p = 31 + lg
+        return ((1 << p) + d - 1) // d, p - 32
+
+    rng = np.random.default_rng(5)
+    divisors = list(range(1, 3000)) + [int(x) for x in rng.integers(3000, 1 << 30, 400)] + [(1 << k) + s for k in range(2, 31) for s in (-1, 0, 1)]
+    edge = np.array([0, 1, 2, (1 << 31) - 1, (1 << 31) - 2, 1 << 30], dtype=np.uint64)
+    for d in divisors:
+        mul, shr = init(d)
+        assert mul < (1 << 32)
+        n = np.concatenate([edge, rng.integers(0, 1 << 31, 64).astype(np.uint64),
+                            (np.arange(1, 40, dtype=np.uint64) * np.uint64(d)) % np.uint64(1 << 31),
+                            ((np.arange(1, 40, dtype=np.uint64) * np.uint64(d)) - np.uint64(1)) % np.uint64(1 << 31)])
+        got = ((n * np.uint64(mul)) >> np.uint64(32)) >> np.uint64(shr) if mul else n
+        assert np.array_equal(got, n // np.uint64(d)), d
