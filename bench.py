@@ -375,7 +375,7 @@ def run_cuda(args, rank, local_rank, world):
     # centre is evaluated, otherwise the centres (a few per cent) are left in
     centres = ((nx + 3) // 4) * ((ny + 3) // 4) * ((nz + 3) // 4) if len(plan) == 1 and world == 1 else 0
     fine_evals = max(evals_exec - centres, 0)
-    kname = ("k_jit_grid4 (fine lattice evaluation, kernel specialised for the tree at run time)" if specialised
+    kname = ("k_jit_grid2 (fine lattice evaluation, kernel specialised for the tree at run time, two corners per thread)" if specialised
              else "k_eval<GenGrid> (fine lattice evaluation, interpreter)")
     kbytes, kms = 4.0 * fine_evals / world, mean["eval_ms"]
     achieved = kbytes / (kms * 1e-3) / 1e9
@@ -384,7 +384,7 @@ def run_cuda(args, rank, local_rank, world):
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            tk = "k_jit_grid4" if specialised else "k_eval<GenGrid>"
+            tk = "k_jit_grid2" if specialised else "k_eval<GenGrid>"
             traffic, winst = tj.get(tk), tj.get(tk + ".warp_inst")
         except Exception:
             pass

@@ -93,6 +93,7 @@ def _load(host_only=False):
         "gsdf_program_specialize": (C.c_int, [vp]),
         "gsdf_program_is_specialized": (C.c_int, [vp]),
         "gsdf_jit_compile": (C.c_int64, [vp, C.c_size_t, f32p, C.c_size_t]),
+        "gsdf_program_device_image": (C.c_int64, [vp, C.c_size_t, f32p, C.c_size_t, vp, C.c_size_t]),
         "gsdf_program_destroy": (None, [vp]),
         "gsdf_program_evaluations": (C.c_uint64, [vp]),
         "gsdf_eval3": (C.c_int, [vp, vp, vp, C.c_size_t]),

@@ -268,8 +268,47 @@ static int parse_blob(const void *blob, size_t blob_bytes, const float *aux, siz
     return validate_program(h, chunks, aux_floats);
 }
 
+// Operand tables the library derives from a validated program before it goes to the device (the flattened format and its
+// producers -- flatten.cpp, the Go flattener -- stay as they are). circarray (cpu_evaluators.go:1056-1078) rotates every point
+// by angle*i0 and angle*i1, i0, i1 integers in [0, ncirc]: Sincos of those ncirc+1 angles is computed here once, with the
+// same math32 restatement the kernels run (math32.cuh, host side, -ffp-contract=off), appended to the side buffer as
+// (sin, cos) pairs, and the table's position (in float4 units, +1) goes into the unused fourth operand word of CIRC_ENTER.
+// The kernel then loads two pairs instead of running two Sincos per point; operands outside the table (NaN) take the
+// computed path. Word 3 == 0 (every blob that did not pass through here) means no table.
+static void augment_program(const gsdf_program_header &h, const uint32_t *chunks, const float *aux, size_t aux_floats, std::vector<uint32_t> &c2,
+                            std::vector<float> &a2) {
+    c2.assign(chunks, chunks + (size_t)h.nchunks * 4);
+    a2.assign(aux, aux + aux_floats);
+    for (uint32_t pc = 0; pc < h.nchunks;) {
+        const uint32_t op = c2[4 * pc] & 0xff, len = (c2[4 * pc] >> 8) & 0xff;
+        if (op == GSDF_OP_CIRC_ENTER && len >= 2 && pc + 1 < h.nchunks) {
+            float angle, ncirc;
+            std::memcpy(&angle, &c2[4 * (pc + 1)], 4);
+            std::memcpy(&ncirc, &c2[4 * (pc + 1) + 1], 4);
+            if (ncirc >= 1.0f && ncirc <= 4096.0f && ncirc == (float)(int)ncirc) {
+                const int n = (int)ncirc;
+                while (a2.size() & 3) a2.push_back(0.0f);
+                c2[4 * (pc + 1) + 3] = (uint32_t)(a2.size() / 4) + 1u;
+                for (int i = 0; i <= n; i++) {
+                    float sn, cs;
+                    m32::sincos(m32::mul(angle, (float)i), sn, cs);
+                    a2.push_back(sn); a2.push_back(cs);
+                }
+                while (a2.size() & 3) a2.push_back(0.0f);
+            }
+        }
+        pc += len ? len : 1;
+    }
+}
+
 // copies chunks + aux into p->d_blob (growing it if needed) and refreshes the kernel-side view
-static int upload_blob(gsdf_program *p, const gsdf_program_header &h, const uint32_t *chunks, const float *aux, size_t aux_floats) {
+static int upload_blob(gsdf_program *p, const gsdf_program_header &h, const uint32_t *chunks_in, const float *aux_in, size_t aux_floats_in) {
+    std::vector<uint32_t> c2;
+    std::vector<float> a2;
+    augment_program(h, chunks_in, aux_in, aux_floats_in, c2, a2);
+    const uint32_t *chunks = c2.data();
+    const float *aux = a2.data();
+    const size_t aux_floats = a2.size();
     const size_t prog_bytes = (size_t)h.nchunks * 16, aux_bytes = aux_floats * 4;
     if (prog_bytes + aux_bytes + 16 > p->blob_cap) {
         if (p->d_blob) cudaFree(p->d_blob);
@@ -301,6 +340,23 @@ static int upload_blob(gsdf_program *p, const gsdf_program_header &h, const uint
     p->pv.stage_aux = (prog_bytes + aux_bytes + stacks + 16 <= 100 * 1024) ? 1u : 0u;
     program_note_structure(p, h, chunks);
     return 0;
+}
+
+int64_t gsdf_program_device_image(const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats, void *image, size_t image_bytes) {
+    gsdf_program_header h;
+    const uint32_t *chunks = nullptr;
+    const int rc = parse_blob(blob, blob_bytes, aux, aux_floats, h, chunks);
+    if (rc) return rc;
+    std::vector<uint32_t> c2;
+    std::vector<float> a2;
+    augment_program(h, chunks, aux, aux_floats, c2, a2);
+    const size_t need = c2.size() * 4 + a2.size() * 4;
+    if (image) {
+        if (image_bytes < need) return fail(GSDF_ESHORT, "device image needs %zu bytes, %zu given", need, image_bytes);
+        std::memcpy(image, c2.data(), c2.size() * 4);
+        if (!a2.empty()) std::memcpy(static_cast<uint8_t *>(image) + c2.size() * 4, a2.data(), a2.size() * 4);
+    }
+    return (int64_t)need;
 }
 
 int gsdf_program_create_on(int device, const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats, gsdf_program **out) {
@@ -698,11 +754,16 @@ int gsdf_colorconv_linear_gradient(float gradient_length, uint32_t rgba0, uint32
 namespace gsdfi {
 int program_update_async(gsdf_program *p, const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats) {
     gsdf_program_header h;
-    const uint32_t *chunks = nullptr;
-    int rc = parse_blob(blob, blob_bytes, aux, aux_floats, h, chunks);
+    const uint32_t *chunks_in = nullptr;
+    int rc = parse_blob(blob, blob_bytes, aux, aux_floats, h, chunks_in);
     if (rc) return rc;
     if ((int)h.dim != p->dim) return fail(GSDF_EINVAL, "cannot change a %dD program into a %dD one", p->dim, (int)h.dim);
-    const size_t prog_bytes = (size_t)h.nchunks * 16, aux_bytes = aux_floats * 4;
+    std::vector<uint32_t> c2;
+    std::vector<float> a2;
+    augment_program(h, chunks_in, aux, aux_floats, c2, a2);  // (same tables as upload_blob: the layout comparison below is on the augmented sizes)
+    const uint32_t *chunks = c2.data();
+    const float *aux2 = a2.data();
+    const size_t prog_bytes = (size_t)h.nchunks * 16, aux_bytes = a2.size() * 4;
     bool ext = false;
     for (uint32_t pc = 0; pc < h.nchunks;) {
         const uint32_t op = chunks[4 * pc] & 0xff, len = (chunks[4 * pc] >> 8) & 0xff;
@@ -722,7 +783,7 @@ int program_update_async(gsdf_program *p, const void *blob, size_t blob_bytes, c
     if (!p->upload_ev) CU(cudaEventCreateWithFlags(&p->upload_ev, cudaEventDisableTiming));
     if (p->upload_ev_recorded) CU(cudaEventSynchronize(p->upload_ev));  // the staging buffer is free again (normally long done)
     std::memcpy(p->h_blob, chunks, prog_bytes);
-    if (aux_bytes) std::memcpy(p->h_blob + prog_bytes, aux, aux_bytes);
+    if (aux_bytes) std::memcpy(p->h_blob + prog_bytes, aux2, aux_bytes);
     {   // device-side: nothing that still reads the old program may be overtaken
         std::lock_guard<std::mutex> lk(p->dep_mu);
         for (const auto &d : p->deps) CU(cudaStreamWaitEvent(p->stream, d.ev, 0));

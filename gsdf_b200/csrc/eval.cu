@@ -217,6 +217,11 @@ int launch_grid1(const gsdf_program *p, const GenGrid<1> &g, uint64_t nwork, cud
     if (nwork && jit_of(p)) return launch_jit<1>(p, jit_of(p)->grid1, g, nwork, st, pdl, sched, stamp, jit_cta_threads(p));
     return launch_eval<1>(p, g, nwork, st, pdl, sched, stamp, eval_cta_threads(p, true));
 }
+bool has_grid2(const gsdf_program *p) { return jit_of(p) && jit_of(p)->grid2; }
+int launch_grid2(const gsdf_program *p, const GenGrid<2> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
+    if (!has_grid2(p)) return fail(GSDF_EUNSUPPORTED, "two corners per thread needs the specialised kernels");
+    return nwork ? launch_jit<2>(p, jit_of(p)->grid2, g, nwork, st, pdl, sched, stamp, jit_cta_threads(p)) : 0;
+}
 int launch_prune_fine(const gsdf_program *p, const PruneFine &g, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp) {
     return p->needs_ext ? launch_prune_fine_impl<true>(p, g, st, pdl, sched, stamp) : launch_prune_fine_impl<false>(p, g, st, pdl, sched, stamp);
 }

@@ -101,10 +101,11 @@ inline gsdfk::Lat make_lat(const gsdf_lattice *lat, int k0, int k1, int pitch, b
 
 namespace gsdfi {
 // Kernels compiled at run time for one program structure (jit.cu); shared by every program and device with that structure.
+constexpr int kJitKernels = 4;
 struct JitEntry {
     std::string key;
-    cudaLibrary_t lib[3] = {};
-    cudaKernel_t grid4 = nullptr, grid1 = nullptr, centers = nullptr;
+    cudaLibrary_t lib[kJitKernels] = {};
+    cudaKernel_t grid4 = nullptr, grid1 = nullptr, centers = nullptr, grid2 = nullptr;
     ~JitEntry();
 };
 }  // namespace gsdfi
@@ -181,6 +182,9 @@ int launch_grid4(const gsdf_program *p, const gsdfk::GenGrid<4> &g, uint64_t nwo
                  unsigned long long *stamp = nullptr);
 // the same lattice evaluation with ONE corner per thread (4 work items per quad): for listed work that fills less than about
 // one resident wave, where the render is bound by the latency of a tile, not by throughput. nwork counts quads x 4.
+// two corners per thread: run-time compiled kernels only (has_grid2)
+bool has_grid2(const gsdf_program *p);
+int launch_grid2(const gsdf_program *p, const gsdfk::GenGrid<2> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched, unsigned long long *stamp);
 int launch_grid1(const gsdf_program *p, const gsdfk::GenGrid<1> &g, uint64_t nwork, cudaStream_t st, bool pdl, uint32_t *sched,
                  unsigned long long *stamp = nullptr);
 // resident CTA slots of the lattice-evaluation kernel for this program (SMs x occupancy) and the CTA size it is launched with

@@ -651,8 +651,9 @@ __device__ __forceinline__ bool exec_one(Machine<P> &m, const uint4 h, const uin
                 m.px[j] = x - c.x * rx; m.py[j] = y - c.y * ry;
             }
         } break;
-        case GSDF_OP_CIRC_ENTER: {  // :1056-1078  c=(angle,ncirc,ninsm1)
+        case GSDF_OP_CIRC_ENTER: {  // :1056-1078  c=(angle,ncirc,ninsm1,table)
             const float4 c = ldf4(prog, pc + 1);
+            const uint32_t tab = __float_as_uint(c.w);
             float x0[P], y0[P];
 #pragma unroll
             for (int j = 0; j < P; j++) {
@@ -663,8 +664,16 @@ __device__ __forceinline__ bool exec_one(Machine<P> &m, const uint4 h, const uin
                 float i0, i1;
                 if (id >= c.z) { i0 = c.z; i1 = 0.f; } else { i0 = id; i1 = id + 1.f; }
                 float s0, c0, s1, c1;
-                m32::sincos(c.x * i0, s0, c0);
-                m32::sincos(c.x * i1, s1, c1);
+                // Sincos(angle * i) for i = 0..ncirc from the table the library appended to the side buffer (capi.cu
+                // augment_program; word 3 of the operands = its position + 1, 0 = no table); anything else (NaN) is computed
+                if (tab && i0 >= 0.f && i0 <= c.y && i1 >= 0.f && i1 <= c.y) {
+                    const float2 *T = reinterpret_cast<const float2 *>(aux + (tab - 1u));
+                    const float2 t0 = T[(int)i0], t1 = T[(int)i1];
+                    s0 = t0.x; c0 = t0.y; s1 = t1.x; c1 = t1.y;
+                } else {
+                    m32::sincos(c.x * i0, s0, c0);
+                    m32::sincos(c.x * i1, s1, c1);
+                }
                 x0[j] = c0 * x + s0 * y; y0[j] = -s0 * x + c0 * y;
                 m.px[j] = c1 * x + s1 * y; m.py[j] = -s1 * x + c1 * y;
             }

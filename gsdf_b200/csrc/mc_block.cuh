@@ -284,14 +284,12 @@ __device__ __forceinline__ uint32_t seg_kept_bits(const MeshDims &D, const uint3
     if (rem < 8) kb &= (1u << rem) - 1u;
     return kb;
 }
+// sum of the count bytes of the kept slots t < upto: the kept bits are spread to one byte each (bit i of a nibble -> byte i) and
+// dotted with the eight count bytes, two dp4a instead of an 8-step select-and-add chain
+__device__ __forceinline__ uint32_t spread4(uint32_t nibble) { return ((nibble & 0xfu) * 0x00204081u) & 0x01010101u; }
 __device__ __forceinline__ uint32_t seg_masked_sum(uint2 c, uint32_t kb, int upto = 8) {
-    uint32_t s = 0;
-#pragma unroll
-    for (int t = 0; t < 8; t++) {
-        const uint32_t byte = ((t < 4 ? c.x : c.y) >> (8 * (t & 3))) & 0xffu;
-        if (t < upto && ((kb >> t) & 1u)) s += byte;
-    }
-    return s;
+    const uint32_t m = kb & ((1u << upto) - 1u);
+    return __dp4a(c.x, spread4(m), 0u) + __dp4a(c.y, spread4(m >> 4), 0u);
 }
 
 // One tile (kScanTile segments) of the segment scan, by all kThreads threads of a CTA. Two ways to the tile's prefix:
@@ -427,23 +425,28 @@ constexpr int kBlkListCap = 32 * 5;  // triangles of one half-block (32 cells, a
 // emitted was measured: 63 instead of 40 registers, no gain.)
 __device__ __forceinline__ void blk_emit_rows(const BlkArgs &A, const BlkPos &b, int lane, bool cg, uint32_t (&rown)[2], uint32_t (&rowbase)[2]) {
     const MeshDims &D = A.D;
+    // a block has 16 cell rows and every lane needs two of them, shared with the three other lanes of its row: lane l looks up
+    // row l & 15 (ry = l & 3, rz = (l >> 2) & 3) once and the lanes pick their rows up by shuffle
+    const int ry = lane & 3, rz = (lane >> 2) & 3;
+    const int cy = b.y0 + ry, cz = b.z0 + rz;
+    uint32_t rn = 0u, rb = 0u;
+    if (cy < D.ny && cz >= D.cz0 && cz < D.cz1) {
+        const uint32_t seg = blk_segment(D, b.bx, cy, cz);
+        const uint2 c = cg ? __ldcg(A.blkcnt + seg) : A.blkcnt[seg];
+        const int slot = b.bx & 7;
+        rn = ((slot < 4 ? c.x : c.y) >> (8 * (slot & 3))) & 0xffu;
+        if (rn) {  // triangles of the kept slots in front of this block, behind the segment's offset
+            const uint32_t kb = seg_kept_bits_at(D, A.mbits, cy, cz, (uint32_t)(b.bx >> 3));
+            const uint32_t so = cg ? __ldcg(A.segoff + seg) : A.segoff[seg];
+            rb = so + seg_masked_sum(c, kb, slot);
+        }
+    }
     const int ly = (lane >> 2) & 3, lz = lane >> 4;
-    const int cy = b.y0 + ly;
-    rown[0] = rown[1] = 0u; rowbase[0] = rowbase[1] = 0u;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        const int cz = b.z0 + lz + 2 * h;
-        if (cy < D.ny && cz >= D.cz0 && cz < D.cz1) {
-            const uint32_t seg = blk_segment(D, b.bx, cy, cz);
-            const uint2 c = cg ? __ldcg(A.blkcnt + seg) : A.blkcnt[seg];
-            const int slot = b.bx & 7;
-            rown[h] = ((slot < 4 ? c.x : c.y) >> (8 * (slot & 3))) & 0xffu;
-            if (rown[h]) {  // triangles of the kept slots in front of this block, behind the segment's offset
-                const uint32_t kb = seg_kept_bits_at(D, A.mbits, cy, cz, (uint32_t)(b.bx >> 3));
-                const uint32_t so = cg ? __ldcg(A.segoff + seg) : A.segoff[seg];
-                rowbase[h] = so + seg_masked_sum(c, kb, slot);
-            }
-        }
+        const int src = ly + 4 * (lz + 2 * h);
+        rown[h] = __shfl_sync(0xffffffffu, rn, src);
+        rowbase[h] = __shfl_sync(0xffffffffu, rb, src);
     }
 }
 

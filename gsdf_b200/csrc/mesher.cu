@@ -235,12 +235,17 @@ int mesh_run_begin(gsdf_mesher *m) {
     // render that lists more than the hint predicted is still correct, only slower.
     int eval_p = 4;
     {
-        static const int force_p = getenv("GSDF_EVAL_P") ? atoi(getenv("GSDF_EVAL_P")) : 0;  // A/B switch: 1 or 4
+        static const int force_p = getenv("GSDF_EVAL_P") ? atoi(getenv("GSDF_EVAL_P")) : 0;  // A/B switch: 1, 2 or 4
         int slots = 0, cta = kEvalThreads;
         if ((rc = eval_cta_slots(p, &slots, &cta))) return rc;
         if (prune && m->runs > 0 && (uint64_t)m->quad_hint * 4 <= (uint64_t)slots * (uint64_t)cta * 3) eval_p = 1;  // <= 3 short rounds
         if (force_p == 1 && prune && m->runs > 0) eval_p = 1;
         if (force_p == 4) eval_p = 4;
+        // the run-time compiled kernels also come with two corners per thread: half the straight-line code per tile and a
+        // 40-register cap (12 resident CTAs of 128 threads instead of 9). Measured against four: flange@400 39 vs 39 us, bolt@400 43
+        // vs 45, knurled@500 349 vs 368 -- the throughput form whenever the kernels are specialised
+        if (eval_p == 4 && force_p != 4 && has_grid2(p)) eval_p = 2;
+        if (force_p == 2 && has_grid2(p)) eval_p = 2;
     }
     static const bool scan3 = getenv("GSDF_SCAN3") != nullptr;  // A/B: the three-kernel scan
     // default: the segment scan runs inside the emit pass of the block kernels; GSDF_SCAN_FUSED=0 launches k_scan_seg (A/B)
@@ -302,6 +307,10 @@ int mesh_run_begin(gsdf_mesher *m) {
         if (eval_p == 1) {  // latency-bound amount of listed work: one corner per thread, four times as many (short) tiles
             GenGrid<1> g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
             if ((rc = launch_grid1(p, g, std::min<uint64_t>(nquads, with_margin(m->quad_hint, 1024)) * 4, st, pdl && prune, sched, m->d_stamp + 2))) return rc;
+        } else if (eval_p == 2) {
+            GenGrid<2> g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
+            const uint64_t bound = (prune && m->runs > 0) ? std::min<uint64_t>(nquads, with_margin(m->quad_hint, 1024)) : nquads;
+            if ((rc = launch_grid2(p, g, bound * 2, st, pdl && (prune || blockmc), sched, m->d_stamp + 2))) return rc;
         } else {
             GenGrid<4> g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
             const uint64_t bound = (prune && m->runs > 0) ? std::min<uint64_t>(nquads, with_margin(m->quad_hint, 1024)) : nquads;

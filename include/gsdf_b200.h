@@ -86,6 +86,13 @@ int gsdf_program_specialize(gsdf_program *p);
 int gsdf_program_is_specialized(const gsdf_program *p);
 /* The compilation step alone, without a device (build checks, tests): CUBIN size in bytes or a negative gsdf_status. */
 int64_t gsdf_jit_compile(const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats);
+/* What gsdf_program_create / _update put on the device for a flattened program, without a device (tests, debugging): the
+ * instruction chunks (16 bytes each, header stripped) followed by the side buffer, to which the library appends operand
+ * tables it derives itself -- today Sincos(angle * i), i = 0..ncirc, for every circarray (gsdf.go circarray.Evaluate,
+ * cpu_evaluators.go:1056-1078), whose position goes into the unused fourth operand word of GSDF_OP_CIRC_ENTER. Returns the
+ * image size in bytes (the side buffer starts at 16 * nchunks); copies it when image != NULL and image_bytes suffices,
+ * GSDF_ESHORT when it does not. */
+int64_t gsdf_program_device_image(const void *blob, size_t blob_bytes, const float *aux, size_t aux_floats, void *image, size_t image_bytes);
 void gsdf_program_destroy(gsdf_program *p);
 /* gleval Evaluations() counter (gleval/cpu.go:126, gleval/gpu.go:80): points evaluated through this handle -- host and
  * device Evaluate calls, lattice and image evaluations, and the evaluations of the renderers bound to it (the reference's

@@ -20,7 +20,7 @@ from gsdf_b200 import gsdf, _lib
 b = gsdf.Builder(); s = gsdf.scene(b, "npt-flange"); f = b.flatten(s); aux = np.ascontiguousarray(f["aux"], dtype=np.float32)
 assert _lib.lib.gsdf_jit_compile(f["blob"], len(f["blob"]), aux.ctypes.data_as(C.POINTER(C.c_float)), aux.size) > 0, _lib.last_error()
 PY
-for k in k_jit_grid4 k_jit_grid1 k_jit_centers; do
+for k in k_jit_grid2 k_jit_grid4 k_jit_grid1 k_jit_centers; do
   [ -f $D/$k.cubin ] || continue
   n=$(cuobjdump -sass $D/$k.cubin | grep -cE "^\s+/\*[0-9a-f]{4,6}\*/")
   for op in UBLKCP ACQBULK PREEXIT; do printf "%-12s x%-3s %s (run-time compiled for npt-flange: %s SASS instructions)\n" $op $(cuobjdump -sass $D/$k.cubin | grep -c $op) $k $n; done

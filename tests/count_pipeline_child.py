@@ -22,6 +22,8 @@ for scene, resdiv in [("sphere", 70), ("npt-flange", 150), ("bolt", 120), ("knur
     lat = O.flat_lattice(*s.Bounds(), res)
     grid, _ = O.flat_eval_grid(t, lat, nthreads=os.cpu_count() or 1)
     sdf = gleval.NewCUDASDF3(s)
+    if os.environ.get("GSDF_CHILD_SPECIALIZE"):  # the run-time compiled kernels (two corners per thread exists only there)
+        assert sdf.Specialize(), "run-time compilation unavailable"
     for prune in (True, False):
         cases = os.environ.get("GSDF_CHILD_NO_CASES") is None  # (parity mode launches the count pass without a programmatic edge)
         R = (glrender.Octree if prune else glrender.FlatRenderer)(sdf, res, keep_cases=cases)

@@ -9,6 +9,7 @@
 #define __device__
 #define __forceinline__ inline __attribute__((always_inline))
 #define __noinline__ __attribute__((noinline))
+struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct uint4 { uint32_t x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }

@@ -2,6 +2,8 @@
 same bit-for-bit bar as the GPU parity tests, on the CPU. This is what validated the box-guard correction of DESIGN.md
 section 2 on the real source before any GPU saw it (the previous revision of interp.cuh fails these tests on the
 overlapping-operand shapes and on two of the seeded random trees)."""
+import struct
+
 import numpy as np
 import pytest
 
@@ -174,3 +176,52 @@ def test_array_folds_start_from_the_reference_seed(oracle, bld):
         want = t.eval2(pos) if s.is2d else t.eval3(pos)
         if "translatemulti" not in name:
             assert want[0] == np.float32(1e20)   # the seed shows
+
+
+def device_image(flat):
+    """The program as gsdf_program_create uploads it (gsdf_program_device_image): chunks + side buffer with the operand
+    tables the library appends (Sincos tables of circular arrays), repacked as a flatten() dict for hostinterp.run."""
+    import ctypes as C
+    from gsdf_b200 import _lib
+    blob = flat["blob"]
+    aux = np.ascontiguousarray(flat["aux"], np.float32)
+    auxp = aux.ctypes.data_as(C.POINTER(C.c_float))
+    need = _lib.lib.gsdf_program_device_image(blob, len(blob), auxp, aux.size, None, 0)
+    assert need > 0, _lib.last_error()
+    img = (C.c_uint8 * need)()
+    assert _lib.lib.gsdf_program_device_image(blob, len(blob), auxp, aux.size, img, need) == need
+    nchunks = struct.unpack_from("<8I", blob, 0)[2]
+    raw = bytes(img)
+    return {"blob": bytes(blob[:32]) + raw[:16 * nchunks], "aux": np.frombuffer(raw, np.float32, offset=16 * nchunks).copy()}, nchunks
+
+
+def test_circular_array_tables_of_the_device_image(oracle, bld):
+    """The library replaces the two Sincos per point of a circular array by loads from a table it appends to the side buffer
+    when a program is uploaded (capi.cu augment_program, interp.cuh CIRC_ENTER). The augmented image -- exactly what the device
+    gets -- run through the interpreter source equals the oracle bit for bit: the circular arrays of the corpora (3-D and 2-D,
+    partial and full circles), the knurled cylinder on lattice planes, and far / NaN positions (which leave the table)."""
+    seen = 0
+    cases = [(n, s) for n, s in shapes.all3d(bld) + shapes.all2d(bld) if "circarray" in n]
+    cases.append(("knurled-cylinder", gsdf.scene(bld, "knurled-cylinder")))
+    for name, s in cases:
+        flat = bld.flatten(s)
+        img, nchunks = device_image(flat)
+        words = np.frombuffer(img["blob"], np.uint32, offset=32)
+        ntab = 0
+        pc = 0
+        while pc < nchunks:
+            op, ln = int(words[4 * pc]) & 0xff, (int(words[4 * pc]) >> 8) & 0xff
+            if op == progsim.OPS.index("CIRC_ENTER"):
+                assert words[4 * (pc + 1) + 3] != 0, name
+                ntab += 1
+            pc += ln if ln else 1
+        assert ntab >= 1 and len(img["aux"]) > len(flat["aux"]), name
+        seen += ntab
+        t = oracle.Tree.from_shader(s)
+        for pos in (shapes.sample_points(s), far_and_nan_points(s)):
+            want = t.eval2(pos) if s.is2d else t.eval3(pos)
+            for f in (img, flat):  # with the tables and (the blob as flattened) without
+                got = hostinterp.run(f, pos)
+                diff = (got.view(np.uint32) != want.view(np.uint32)) & ~(np.isnan(got) & np.isnan(want))
+                assert not diff.any(), "%s: %d of %d distances differ from the oracle" % (name, int(diff.sum()), len(pos))
+    assert seen >= 4
