@@ -311,7 +311,7 @@ def run_cuda(args, rank, local_rank, world):
             for i in range(world):
                 torch.cuda.synchronize(i)
 
-        for spd in ((1, 3, 4) if world == 1 else (1, 2)):
+        for spd in ((1, 2, 3, 4) if world == 1 else (1, 2)):
             M = glrender.MultiRenderer(s, res, devices=list(range(world)), slabs_per_device=spd)
             assert M.NumTriangles() == ntri
             if specialised:
