@@ -285,6 +285,7 @@ static void augment_program(const gsdf_program_header &h, const uint32_t *chunks
             float angle, ncirc;
             std::memcpy(&angle, &c2[4 * (pc + 1)], 4);
             std::memcpy(&ncirc, &c2[4 * (pc + 1) + 1], 4);
+            c2[4 * (pc + 1) + 3] = 0u;  // the word belongs to the library: whatever a blob carries there never reaches the kernel
             if (ncirc >= 1.0f && ncirc <= 4096.0f && ncirc == (float)(int)ncirc) {
                 const int n = (int)ncirc;
                 while (a2.size() & 3) a2.push_back(0.0f);

@@ -225,3 +225,52 @@ def test_circular_array_tables_of_the_device_image(oracle, bld):
                 diff = (got.view(np.uint32) != want.view(np.uint32)) & ~(np.isnan(got) & np.isnan(want))
                 assert not diff.any(), "%s: %d of %d distances differ from the oracle" % (name, int(diff.sum()), len(pos))
     assert seen >= 4
+    # seeded random compositions that contain a circular array somewhere in the tree
+    circ, nrand = progsim.OPS.index("CIRC_ENTER"), 0
+    for dim in (3, 2):
+        for name, s in shapes.random_trees(bld, 11, 120, dim) + shapes.random_trees(bld, 78, 60, dim, depth=5, rich=True):
+            flat = bld.flatten(s)
+            words = np.frombuffer(flat["blob"], np.uint32, offset=32)
+            nchunks = struct.unpack_from("<8I", flat["blob"], 0)[2]
+            pc, has = 0, False
+            while pc < nchunks:
+                op, ln = int(words[4 * pc]) & 0xff, (int(words[4 * pc]) >> 8) & 0xff
+                has |= op == circ
+                pc += ln if ln else 1
+            if not has:
+                continue
+            nrand += 1
+            img, _ = device_image(flat)
+            pos = shapes.sample_points(s)
+            t = oracle.Tree.from_shader(s)
+            want = t.eval2(pos) if s.is2d else t.eval3(pos)
+            got = hostinterp.run(img, pos)
+            diff = (got.view(np.uint32) != want.view(np.uint32)) & ~(np.isnan(got) & np.isnan(want))
+            assert not diff.any(), "%s: %d of %d distances differ from the oracle" % (name, int(diff.sum()), len(pos))
+    assert nrand >= 5, nrand
+
+
+def test_device_image_owns_the_table_word(bld):
+    """The fourth operand word of CIRC_ENTER belongs to the library: a blob that carries something there (a flattener bug, a
+    hostile blob) gets it overwritten -- by the table position, or by 0 when no table is built -- so the kernel can never be
+    sent to read outside the side buffer."""
+    s = [s for n, s in shapes.all3d(bld) if n == "circarray"][0]
+    flat = bld.flatten(s)
+    blob = bytearray(flat["blob"])
+    words = np.frombuffer(bytes(blob), np.uint32, offset=32)
+    nchunks = struct.unpack_from("<8I", blob, 0)[2]
+    circ, pc, at = progsim.OPS.index("CIRC_ENTER"), 0, None
+    while pc < nchunks:
+        op, ln = int(words[4 * pc]) & 0xff, (int(words[4 * pc]) >> 8) & 0xff
+        if op == circ:
+            at = pc + 1
+        pc += ln if ln else 1
+    assert at is not None
+    struct.pack_into("<I", blob, 32 + 16 * at + 12, 0x7fffffff)
+    good, _ = device_image(flat)
+    bad, _ = device_image({"blob": bytes(blob), "aux": flat["aux"]})
+    assert good["blob"] == bad["blob"] and np.array_equal(good["aux"], bad["aux"])
+    # a fractional instance count builds no table: the word is cleared
+    struct.pack_into("<f", blob, 32 + 16 * at + 4, 6.5)
+    img, _ = device_image({"blob": bytes(blob), "aux": flat["aux"]})
+    assert struct.unpack_from("<I", img["blob"], 32 + 16 * at + 12)[0] == 0 and len(img["aux"]) == len(np.atleast_1d(flat["aux"]))
