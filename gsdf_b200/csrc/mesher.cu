@@ -84,6 +84,7 @@ struct gsdf_mesher {
     uint64_t runs = 0;
     // a render that was enqueued (mesh_run_begin) and not yet finished (mesh_run_end)
     bool pending = false, pend_graph = false, pend_emitted = false;
+    bool last_reemit = false;  // the render just finished had to grow the triangle buffer and emit again (mesh_run_end)
     MCArgs pendA{};
     BlkArgs pendB{};
     unsigned pend_mcgrid = 0, pend_blkgrid = 0;
@@ -472,6 +473,7 @@ int mesh_run_end(gsdf_mesher *m) {
     CU(cudaEventSynchronize(m->ev[4]));  // the counters were published to m->h_ctr by the last kernel of the sequence
     uint64_t total;
     std::memcpy(&total, m->h_ctr + 2, 8);
+    m->last_reemit = !emitted || total * 9 > m->tri_cap;
     if (!emitted || total * 9 > m->tri_cap) {
         if (m->copy_stream) CU(cudaStreamSynchronize(m->copy_stream));  // a speculative prefix read may be using d_tris
         if ((rc = grow(m->d_tris, m->tri_cap, (size_t)std::max<uint64_t>(total, 1) * 9))) return rc;
@@ -860,6 +862,7 @@ struct gsdf_multimesher {
     std::chrono::steady_clock::time_point t_call;
     bool rendered = false;
     bool delivered = false;                    // the last render's triangles are already in the caller's buffer
+    cudaStream_t copyk_stream = nullptr;       // device-driven read-back (k_copy_out), one device only
     explicit gsdf_multimesher(int n) : count(n) {}
 };
 
@@ -885,6 +888,98 @@ int multi_slab_priority(const gsdf_multimesher *mm, int j) {
     return -(nper - 1 - j / mm->ndev);
 }
 
+// Device-driven read-back (A/B: GSDF_MULTI_COPYK=1, one device, page-locked destination). The host normally learns a slab's
+// triangle count from the counters its last kernel publishes and then enqueues the copy -- and while an earlier slab's DMA is
+// in flight that news arrives ~50 us late. Here the copy of slab j is a small kernel enqueued up front on one
+// high-priority stream behind the slab's completion event: it reads the counts of slabs 0..j from their mapped host counters
+// itself, and writes the slab's triangles into the caller's buffer at the right offset in 16-byte aligned vectors. CTAs of 128
+// threads x <= 32 registers fit beside the persistent grids of the slabs still running (they all leave 4096 registers per SM).
+constexpr int kCopyKMaxSlabs = 32;
+struct CopyOutArgs {
+    const float *src;
+    float *dst;
+    const uint32_t *hctr[kCopyKMaxSlabs];
+    int j;
+    unsigned long long max_tris, src_cap_tris;
+};
+constexpr int kCopyKThreads = 128;
+__global__ void __launch_bounds__(kCopyKThreads, 16) k_copy_out(const CopyOutArgs a) {
+    __shared__ unsigned long long s_off, s_n;
+    if (threadIdx.x == 0) {
+        unsigned long long off = 0;
+        for (int i = 0; i < a.j; i++) off += *reinterpret_cast<const volatile unsigned long long *>(a.hctr[i] + 2);
+        s_off = off;
+        s_n = *reinterpret_cast<const volatile unsigned long long *>(a.hctr[a.j] + 2);
+    }
+    __syncthreads();
+    const unsigned long long off = s_off, n = s_n;
+    // (count beyond the buffer the slab emitted into, or beyond the destination: the host notices the same and copies the classic way)
+    if (n == 0 || n > a.src_cap_tris || off + n > a.max_tris || n >= (1ull << 28)) return;
+    const uint32_t nfl = (uint32_t)n * 9u;
+    float *d = a.dst + off * 9ull;
+    const float *s = a.src;
+    uint32_t head = ((16u - (uint32_t)(reinterpret_cast<uintptr_t>(d) & 15u)) & 15u) / 4u;
+    if (head > nfl) head = nfl;
+    const uint32_t nv = (nfl - head) / 4u, tail = nfl - head - 4u * nv;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (tid < head) d[tid] = s[tid];
+    if (tid < tail) d[head + 4u * nv + tid] = s[head + 4u * nv + tid];
+    float4 *dv = reinterpret_cast<float4 *>(d + head);
+    const float *sv = s + head;
+    for (uint32_t i = tid; i < nv; i += 2u * nth) {
+        const uint32_t k1 = i + nth;
+        const float4 v0 = make_float4(__ldcs(sv + 4u * i), __ldcs(sv + 4u * i + 1), __ldcs(sv + 4u * i + 2), __ldcs(sv + 4u * i + 3));
+        float4 v1 = v0;
+        if (k1 < nv) v1 = make_float4(__ldcs(sv + 4u * k1), __ldcs(sv + 4u * k1 + 1), __ldcs(sv + 4u * k1 + 2), __ldcs(sv + 4u * k1 + 3));
+        dv[i] = v0;
+        if (k1 < nv) dv[k1] = v1;
+    }
+}
+
+// one device, page-locked destination: every slab's read-back enqueued up front (see k_copy_out)
+int multi_render_copyk(gsdf_multimesher *mm) {
+    int rc;
+    auto now_us = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - mm->t_call).count(); };
+    if (!mm->copyk_stream) {
+        int least = 0, greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CU(cudaStreamCreateWithPriority(&mm->copyk_stream, cudaStreamNonBlocking, greatest));
+    }
+    static const int ctas = getenv("GSDF_MULTI_COPYK_CTAS") ? std::max(1, atoi(getenv("GSDF_MULTI_COPYK_CTAS"))) : 148;
+    for (int j = 0; j < mm->nslabs; j++)
+        if ((rc = mesh_run_begin(mm->slab[j]))) return rc;
+    for (int j = 0; j < mm->nslabs; j++) {
+        gsdf_mesher *m = mm->slab[j];
+        CopyOutArgs a{};
+        a.src = m->d_tris; a.dst = mm->dst; a.j = j; a.max_tris = mm->max_tris; a.src_cap_tris = m->tri_cap / 9;
+        for (int i = 0; i <= j; i++) a.hctr[i] = mm->slab[i]->h_ctr;
+        CU(cudaStreamWaitEvent(mm->copyk_stream, m->ev[4], 0));
+        k_copy_out<<<ctas, kCopyKThreads, 0, mm->copyk_stream>>>(a);
+        CU(cudaGetLastError());
+    }
+    mm->timeline[0] = now_us();
+    uint64_t off = 0;
+    bool redo_from_here = false;
+    for (int j = 0; j < mm->nslabs; j++) {
+        gsdf_mesher *m = mm->slab[j];
+        if ((rc = mesh_run_end(m))) return rc;
+        mm->count[j].store((int64_t)m->ntri, std::memory_order_release);
+        mm->timeline[1 + 2 * j] = mm->timeline[2 + 2 * j] = now_us();
+        mm->offs[j] = off;
+        // a slab that had to grow its buffer and emit again was skipped by its copy kernel (count > capacity): classic copy
+        if ((m->last_reemit || m->ntri >= (1ull << 28)) && m->ntri && off + m->ntri <= mm->max_tris) {
+            CU(cudaStreamWaitEvent(m->copy_stream, m->ev[4], 0));
+            CU(cudaMemcpyAsync(mm->dst + 9 * off, m->d_tris, m->ntri * 9 * sizeof(float), cudaMemcpyDeviceToHost, m->copy_stream));
+            redo_from_here = true;
+        }
+        off += m->ntri;
+    }
+    CU(cudaStreamSynchronize(mm->copyk_stream));
+    if (redo_from_here)
+        for (int j = 0; j < mm->nslabs; j++) CU(cudaStreamSynchronize(mm->slab[j]->copy_stream));
+    return 0;
+}
+
 int multi_worker_render(gsdf_multimesher *mm, int w) {
     const int dev = mm->devs[w];
     CU(use_device(dev));
@@ -894,6 +989,8 @@ int multi_worker_render(gsdf_multimesher *mm, int w) {
         mm->up_dirty[w] = 0;
     }
     auto now_us = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - mm->t_call).count(); };
+    static const bool copyk = getenv("GSDF_MULTI_COPYK") != nullptr && getenv("GSDF_MULTI_COPYK")[0] == '1';  // A/B switch
+    if (copyk && mm->ndev == 1 && mm->dst && mm->dst_pinned && mm->nslabs <= kCopyKMaxSlabs) return multi_render_copyk(mm);
     for (int j = w; j < mm->nslabs; j += mm->ndev)
         if ((rc = mesh_run_begin(mm->slab[j]))) return rc;
     if (w == 0) mm->timeline[0] = now_us();
@@ -1251,6 +1348,7 @@ void gsdf_multi_destroy(gsdf_multimesher *mm) {
     for (auto *m : mm->slab) if (m) gsdf_mesh_destroy(m);
     for (auto *p : mm->prog) if (p) gsdf_program_destroy(p);
     for (auto *h : mm->h_stage) if (h) cudaFreeHost(h);
+    if (mm->copyk_stream) cudaStreamDestroy(mm->copyk_stream);
     delete mm;
     (void)cudaGetLastError();
 }

@@ -14,6 +14,8 @@ host = glrender.pinned_empty((ntri + 8, 3, 3))
 tag = " ".join("%s=%s" % (k, v) for k, v in sorted(os.environ.items()) if k.startswith("GSDF_") and k != "GSDF_B200_LIB")
 for spd in [int(a) for a in sys.argv[1:]] or [1, 2, 3, 4]:
     M = glrender.MultiRenderer(s, res, devices=[0], slabs_per_device=spd)
+    if os.environ.get("GSDF_AB_SPECIAL"):
+        M.Specialize()
     for reb in (0, 1):
         if reb:
             if spd == 1: continue

@@ -273,3 +273,18 @@ def test_host_evaluate_is_chunked_and_exact(oracle, bld, monkeypatch, chunk, lan
             assert np.array_equal(bits(pout), bits(want)), (dim, n, "pinned")
             sdf.Evaluate(ppos, out)
             assert np.array_equal(bits(out), bits(want)), (dim, n, "pinned in, pageable out")
+
+
+@pytest.mark.gpu
+def test_device_driven_read_back_matches_the_single_renderer():
+    """GSDF_MULTI_COPYK=1: the multi-slab driver's read-back as kernels enqueued up front that read the slabs' triangle
+    counts themselves (mesher.cu k_copy_out) instead of copies the host enqueues once it has seen a count. The switch is read
+    once per process, so the check runs in a child: 1-7 slabs, first and steady-state renders, re-cut slabs, a pageable
+    destination (which keeps the classic path) -- the destination always equals the single renderer's triangles bit for bit
+    and nothing is written behind them (tests/multi_copyk_child.py)."""
+    import os, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for mode in ("1", "0"):
+        env = dict(os.environ, GSDF_MULTI_COPYK=mode)
+        r = subprocess.run([sys.executable, os.path.join(here, "multi_copyk_child.py")], env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0 and "MULTI COPYK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
