@@ -126,7 +126,12 @@ __device__ __forceinline__ void finish_render_cta(uint32_t *__restrict__ d_ctr, 
     for (uint32_t i = threadIdx.x; i < (uint32_t)nctr; i += blockDim.x) { h_ctr[i] = d_ctr[i]; d_ctr[i] = 0u; }
     for (uint32_t k = threadIdx.x; k < nstate; k += blockDim.x) scanstate[k] = 0ull;
     if (d_stamp && threadIdx.x < (uint32_t)nstamp) h_stamp[threadIdx.x] = d_stamp[threadIdx.x];
+    // No system-scope fence here: the host (and the copy kernels of the multi-slab driver) read these words only behind the
+    // stream's completion event, which orders them. With a fence the last CTA of a slab waited ~14 us for it whenever an earlier
+    // slab's DMA was in flight (measured: second of two slabs seen at 221 instead of 236 us; GSDF_SYSFENCE builds it back in)
+#ifdef GSDF_SYSFENCE
     __threadfence_system();
+#endif
 }
 
 
