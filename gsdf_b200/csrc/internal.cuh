@@ -91,6 +91,7 @@ inline gsdfk::Lat make_lat(const gsdf_lattice *lat, int k0, int k1, int pitch, b
     L.nqx = (lat->n[0] + 1 + 3) / 4;
     L.pitch = pitch;
     L.vec = vec ? 1 : 0;
+    L.hq = 0;
     L.fdiv = (uint64_t)L.nqx * (uint64_t)(L.ny + 1) * (uint64_t)(L.nk > 0 ? L.nk : 1) < (1ull << 31) ? 1u : 0u;
     gsdfk::fastdiv_init((uint32_t)L.nqx, L.nqx_mul, L.nqx_shr);
     gsdfk::fastdiv_init((uint32_t)(L.ny + 1), L.nyp_mul, L.nyp_shr);

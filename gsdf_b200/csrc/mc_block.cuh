@@ -56,9 +56,13 @@ struct BlkArgs {
 // word of a block row). bits == nullptr: no quad list, every block of the slab is listed (FlatRenderer).
 // bits2 != nullptr (plan ending with level 2, PruneFine): a quad is needed iff a kept 2-CELL cube touches it -- quad m of
 // corner row (j, k) is touched by the cubes 2m-1, 2m, 2m+1 of the level-2 rows (j-1)>>1, j>>1 x (k-1)>>1, k>>1.
+// half != 0 (the consumer evaluates two corners per thread, GenGrid<2> with Lat::hq): the quad list holds HALF-quads,
+// 2 * quad + h. A quad whose own block column is kept in one of the touching block rows lists both halves; a quad that is
+// only needed as the last corner column of the kept block on its left lists its first half alone (its corners 4m+2, 4m+3
+// -- and 4m+1 -- are read by nobody). `count` then counts half-quads.
 __global__ void __launch_bounds__(kThreads) k_mesh_lists(MeshDims D, const uint32_t *__restrict__ bits, uint32_t *__restrict__ list,
                                                         uint32_t *__restrict__ count, uint32_t *__restrict__ blklist, uint32_t *__restrict__ nblk,
-                                                        unsigned long long *stamp, const uint32_t *__restrict__ bits2) {
+                                                        unsigned long long *stamp, const uint32_t *__restrict__ bits2, int half) {
     pdl_trigger();
     pdl_wait();
     stage_stamp(stamp);
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(kThreads) k_mesh_lists(MeshDims D, const uint3
         if (base < nq_pad) {
             const uint64_t nitems = nq_items;
             const uint64_t item = base + lane;
-            uint32_t needw = 0u, r = 0u, w = 0u;
+            uint32_t needw = 0u, fullw = 0u, r = 0u, w = 0u;
             if (item < nitems) {
                 r = (uint32_t)(item / nqw);
                 w = (uint32_t)(item - (uint64_t)r * nqw);
@@ -98,18 +102,22 @@ __global__ void __launch_bounds__(kThreads) k_mesh_lists(MeshDims D, const uint3
                             const uint32_t e = (int)w < D.nwx ? row[2 * w] : 0u, o = (int)w < D.nwx ? row[2 * w + 1] : 0u;
                             const uint32_t oprev = (w >= 1 && (int)(w - 1) < D.nwx) ? row[2 * (w - 1) + 1] : 0u;
                             needw |= e | o | (o << 1) | (oprev >> 31);
+                            fullw = needw;  // (2-cell cubes: every listed quad keeps both halves)
                         } else {
                             const uint32_t *row = bits + ((size_t)(bz - D.bz0) * D.nby + by) * D.nwx;
                             const uint32_t cur = (int)w < D.nwx ? row[w] : 0u;
                             const uint32_t prev = (w >= 1 && (int)(w - 1) < D.nwx) ? row[w - 1] : 0u;
                             needw |= cur | (cur << 1) | (prev >> 31);
+                            fullw |= cur;
                         }
                     }
                 }
                 const int rem = D.nqx - 32 * (int)w;  // quads of this word that exist
                 if (rem < 32) needw &= (1u << rem) - 1u;
+                fullw = half ? (fullw & needw) : 0u;
             }
-            const uint32_t pc = (uint32_t)__popc(needw);
+            // list entries of this lane's word: one per needed quad, two where both halves are listed
+            const uint32_t pc = (uint32_t)__popc(needw) + (uint32_t)__popc(fullw);
             const uint32_t incl = warp_incl_scan(pc);
             const uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
             if (wtot == 0u) continue;  // warp-uniform
@@ -123,7 +131,18 @@ __global__ void __launch_bounds__(kThreads) k_mesh_lists(MeshDims D, const uint3
                 const uint32_t word = __shfl_sync(0xffffffffu, needw, src);
                 const uint32_t off = __shfl_sync(0xffffffffu, incl - pc, src);
                 const uint32_t qid = __shfl_sync(0xffffffffu, r * (uint32_t)D.nqx + 32u * w, src);
-                if ((word >> lane) & 1u) list[wbase + off + __popc(word & ((1u << lane) - 1u))] = qid + (uint32_t)lane;
+                if (!half) {
+                    if ((word >> lane) & 1u) list[wbase + off + __popc(word & ((1u << lane) - 1u))] = qid + (uint32_t)lane;
+                } else {
+                    const uint32_t fw = __shfl_sync(0xffffffffu, fullw, src);
+                    if ((word >> lane) & 1u) {
+                        const uint32_t below = (1u << lane) - 1u;
+                        const uint32_t at = wbase + off + (uint32_t)__popc(word & below) + (uint32_t)__popc(fw & below);
+                        const uint32_t hq = 2u * (qid + (uint32_t)lane);
+                        list[at] = hq;
+                        if ((fw >> lane) & 1u) list[at + 1u] = hq + 1u;
+                    }
+                }
             }
         } else {  // kept blocks
             const uint64_t nitems = nb_items;

@@ -88,6 +88,7 @@ struct gsdf_mesher {
     MCArgs pendA{};
     BlkArgs pendB{};
     unsigned pend_mcgrid = 0, pend_blkgrid = 0;
+    bool pend_half = false;  // the pending render's work list holds half-quads (Lat::hq)
 };
 
 namespace {
@@ -166,7 +167,8 @@ int mesh_run_begin(gsdf_mesher *m) {
             if ((rc = grow(m->d_bits2, m->bits2_cap, (size_t)8 * D.nwx * D.nby * D.nbz))) return rc;
             if ((rc = grow(m->d_childmask, m->childmask_cap, (size_t)D.nbx * D.nby * D.nbz))) return rc;
         }
-        if ((rc = grow(m->d_list, m->list_cap, (size_t)nquads))) return rc;
+        // (half-quad lists of the two-corners-per-thread lattice kernel: up to two entries per quad)
+        if ((rc = grow(m->d_list, m->list_cap, (size_t)nquads * (has_grid2(p) ? 2u : 1u)))) return rc;
     }
     if (m->flags & GSDF_MESH_KEEP_CASES) {
         if ((rc = grow(m->d_cases, m->cases_cap, (size_t)ncells))) return rc;
@@ -248,6 +250,16 @@ int mesh_run_begin(gsdf_mesher *m) {
         if (eval_p == 4 && force_p != 4 && has_grid2(p)) eval_p = 2;
         if (force_p == 2 && has_grid2(p)) eval_p = 2;
     }
+    // Two corners per thread can read a list of half-quads (k_mesh_lists, Lat::hq): boundary quads list their first half only,
+    // 5-9 % fewer lattice evaluations. Building the finer list costs the list kernel 2-4 us, so it is used once the previous
+    // render listed at least 2^19 quads: flange@400 (0.4 M quads) 40 -> 38 us of evaluation against 16 -> 18 us of prune,
+    // knurled@500 (1.25 M) 310 -> 281 against 38 -> 42. GSDF_HALF_QUADS=0 / 1 switch it off / on whatever the size (A/B, tests).
+    static const int half_env = getenv("GSDF_HALF_QUADS") ? (getenv("GSDF_HALF_QUADS")[0] == '0' ? 0 : 1) : -1;
+    constexpr uint32_t kHalfQuadMin = 1u << 19;
+    // (in half mode the hint is half-quads / 2, a little below the quads listed: a render stays in the mode down to 3/4 of
+    // the threshold, so that a lattice near it does not flip -- and re-capture its graph -- every other render)
+    const bool half_wanted = half_env >= 0 ? half_env == 1 : (m->runs > 0 && m->quad_hint >= (m->pend_half ? kHalfQuadMin / 4 * 3 : kHalfQuadMin));
+    const bool half = half_wanted && prune && blockmc && eval_p == 2 && nquads < (1ull << 31) && m->list_cap >= 2 * nquads;
     static const bool scan3 = getenv("GSDF_SCAN3") != nullptr;  // A/B: the three-kernel scan
     // default: the segment scan runs inside the emit pass of the block kernels; GSDF_SCAN_FUSED=0 launches k_scan_seg (A/B)
     static const bool scan_fused_on = !scan3 && !(getenv("GSDF_SCAN_FUSED") != nullptr && getenv("GSDF_SCAN_FUSED")[0] == '0');
@@ -290,7 +302,7 @@ int mesh_run_begin(gsdf_mesher *m) {
         if (blockmc)
             CU(launch_chain(pdl, k_mesh_lists, dim3(grid_for(p->sms, (ncrows * (uint64_t)((D.nqx + 31) >> 5) + 31) / 32 + ((uint64_t)D.nbz * D.nby * D.nwx + 31) / 32, kThreads / 32)), dim3(kThreads), 0, st, D,
                             (const uint32_t *)m->d_mbits, m->d_list, m->d_ctr + 0, m->d_blklist, m->d_ctr + 5, m->d_stamp + 1,
-                            (const uint32_t *)(m->fine ? m->d_bits2 : nullptr)));
+                            (const uint32_t *)(m->fine ? m->d_bits2 : nullptr), half ? 1 : 0));
         else
         CU(launch_chain(pdl, k_compact_quads, dim3(grid_for(p->sms, (ncrows * (uint64_t)((D.nqx + 31) >> 5) + 31) / 32, kThreads / 32)), dim3(kThreads), 0, st, D, (const uint32_t *)m->d_mbits, m->d_list, m->d_ctr + 0, m->d_stamp + 1));
         CU(cudaGetLastError());
@@ -298,7 +310,7 @@ int mesh_run_begin(gsdf_mesher *m) {
     if (!prune && blockmc) {  // FlatRenderer: every block of the slab is listed (no bit rows, no quad list)
         CU(launch_chain(false, k_mesh_lists, dim3(grid_for(p->sms, ((uint64_t)D.nbz * D.nby * D.nwx + 31) / 32, kThreads / 32)), dim3(kThreads), 0, st, D,
                         (const uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, m->d_blklist, m->d_ctr + 5, (unsigned long long *)nullptr,
-                        (const uint32_t *)nullptr));
+                        (const uint32_t *)nullptr, 0));
         CU(cudaGetLastError());
     }
     if (stage_events) CU(cudaEventRecord(m->ev[1], st));
@@ -310,6 +322,7 @@ int mesh_run_begin(gsdf_mesher *m) {
             if ((rc = launch_grid1(p, g, std::min<uint64_t>(nquads, with_margin(m->quad_hint, 1024)) * 4, st, pdl && prune, sched, m->d_stamp + 2))) return rc;
         } else if (eval_p == 2) {
             GenGrid<2> g{make_lat(&lat, D.cz0, D.cz0 + nk, D.pitch, true), m->d_grid, prune ? m->d_list : nullptr, prune ? m->d_ctr + 0 : nullptr};
+            g.L.hq = half ? 1 : 0;  // (the bound below is 2 * quads either way: an upper bound of the half-quads listed)
             const uint64_t bound = (prune && m->runs > 0) ? std::min<uint64_t>(nquads, with_margin(m->quad_hint, 1024)) : nquads;
             if ((rc = launch_grid2(p, g, bound * 2, st, pdl && (prune || blockmc), sched, m->d_stamp + 2))) return rc;
         } else {
@@ -450,7 +463,7 @@ int mesh_run_begin(gsdf_mesher *m) {
         if ((rc = enqueue(true, m->scan_epoch))) return rc;
     }
     CU(cudaEventRecord(m->ev[4], st));
-    m->pending = true; m->pend_graph = use_graph; m->pend_emitted = emitted; m->pendA = A; m->pend_mcgrid = mcgrid; m->pendB = BA; m->pend_blkgrid = blkgrid;
+    m->pending = true; m->pend_graph = use_graph; m->pend_emitted = emitted; m->pendA = A; m->pend_mcgrid = mcgrid; m->pendB = BA; m->pend_blkgrid = blkgrid; m->pend_half = half;
     return 0;
 }
 
@@ -501,9 +514,10 @@ int mesh_run_end(gsdf_mesher *m) {
     m->ntri = total;
     m->read_pos = 0;
     if (prune) {
-        m->evals = (uint64_t)m->h_ctr[7] + 4ull * m->h_ctr[0];  // prune-cube centres of every level + the listed lattice quads
-        // hint for the next render's launch shape; rounded up so that small changes of the tree do not re-capture the graph
-        m->quad_hint = (m->h_ctr[0] + 4095u) & ~4095u;
+        // prune-cube centres of every level + the listed lattice quads (4 corners each) or half-quads (2 corners each)
+        m->evals = (uint64_t)m->h_ctr[7] + (m->pend_half ? 2ull : 4ull) * m->h_ctr[0];
+        // hint for the next render's launch shape, in quads; rounded up so that small changes of the tree do not re-capture the graph
+        m->quad_hint = ((m->pend_half ? (m->h_ctr[0] + 1u) / 2u : m->h_ctr[0]) + 4095u) & ~4095u;
     }
     m->blk_hint = (m->h_ctr[5] + 1023u) & ~1023u;  // listed blocks (block kernels) of this render
     if (prune && m->fine) {  // the finest cubes of the plan are 2 cells wide: Cube.DecomposesTo(1) = 8

@@ -200,7 +200,8 @@ def test_programmatic_dependent_launch_is_bit_identical():
                                    {"GSDF_MC": "v1", "GSDF_COUNT_GRID": "37"}, {"GSDF_MC": "tile5"}, {"GSDF_EVAL_P": "1"}, {"GSDF_RXY": "0"},
                                    {"GSDF_SCAN_FUSED": "0"}, {"GSDF_BLK_GRID": "3", "GSDF_CHILD_NO_CASES": "1"}, {"GSDF_TILESUM": "1"},
                                    {"GSDF_PRUNE_FINE": "1"}, {"GSDF_EVAL_CTA": "384"}, {"GSDF_EVAL_CTA": "64"},
-                                   {"GSDF_CHILD_SPECIALIZE": "1"}, {"GSDF_EVAL_P": "4", "GSDF_CHILD_SPECIALIZE": "1"}],
+                                   {"GSDF_CHILD_SPECIALIZE": "1"}, {"GSDF_EVAL_P": "4", "GSDF_CHILD_SPECIALIZE": "1"},
+                                   {"GSDF_HALF_QUADS": "1", "GSDF_CHILD_SPECIALIZE": "1"}],
                          ids=lambda k: "+".join("%s=%s" % kv for kv in k.items()))
 def test_marching_cubes_kernel_variants_match_oracle(knobs):
     """Every marching-cubes kernel family, in a child process with its A/B knob set (the knobs are read once per process):
@@ -209,7 +210,7 @@ def test_marching_cubes_kernel_variants_match_oracle(knobs):
     tiles in any order); the 4-layer-tile pair; one-corner-per-thread lattice evaluation; programs without radius-reuse flags;
     the stand-alone segment scan (the default runs it inside the emit pass); the block kernels without the parity-mode case store; scan-tile sums
     accumulated by the count pass; the 2-cell prune level in the default plan; interpreter CTAs of 384 and of 64 threads; the run-time compiled kernels with
-    two (their default) and with four corners per thread.
+    two (their default) and with four corners per thread, and with half-quad work lists forced on (large lattices only otherwise).
     Cases and triangles are compared with the oracle, eager, graph capture and graph replay (tests/count_pipeline_child.py)."""
     import os, subprocess, sys
     here = os.path.dirname(os.path.abspath(__file__))
