@@ -203,7 +203,9 @@ int gsdf_mesh_rerun_end(gsdf_mesher *m);
 int64_t gsdf_mesh_read_prefix_async(gsdf_mesher *m, float *tri9, size_t ntris);
 /* Device pointer to the slab's triangle buffer (9 floats per triangle) and its count, for on-device consumers. */
 int gsdf_mesh_device_triangles(gsdf_mesher *m, const float **d_tri9, uint64_t *ntri);
-/* Evaluations() / Octree.TotalPruned() / len(triangles) (gsdfaux/gsdfaux.go:219-226). */
+/* Evaluations() / Octree.TotalPruned() / len(triangles) (gsdfaux/gsdfaux.go:219-226). evals counts the evaluations the render
+ * executed: prune-cube centres + the listed lattice corners (whole quads of 4 corners, or -- specialised kernels on lattices
+ * that list 2^19 quads or more -- half-quads of 2, which leaves out 5-9 % of the corners nobody reads). */
 int gsdf_mesh_stats(const gsdf_mesher *m, uint64_t *evals, uint64_t *pruned_unit_cubes, uint64_t *tris);
 /* Parity hooks: per-cell case indices (nx*ny*(cz1-cz0) bytes) and the corner lattice of the slab. */
 int gsdf_mesh_cases(gsdf_mesher *m, uint8_t *cases, size_t nbytes);
